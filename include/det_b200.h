@@ -1,0 +1,192 @@
+/*
+ * det_b200.h -- C ABI of libdet_b200.so: the B200-native (sm_100a) post-backbone detection hot path.
+ *
+ * The reference (andompesta/object-detection-pytorch-rust) has NO native/FFI layer: its boundary for this
+ * path is a set of Python callables.  Each entry point below names the reference
+ * callable it replaces (paths relative to the reference root).  The Python package `det_b200` mirrors those
+ * callables 1:1 and forwards here through ctypes; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; plain pointers + sizes only;
+ *   - the library never allocates, frees or retains memory: outputs and workspaces are caller-owned;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no internal synchronisation;
+ *   - return value: DET_OK (0) or a negative DET_ERR_* code; det_last_error() gives a message;
+ *   - boxes are fp32 XYXY rows, indices int64, labels int8, counts int32 (reference dtypes);
+ *   - all floating-point work is IEEE fp32 with FMA contraction disabled, so IoU / keep decisions are
+ *     bit-identical to the reference's CPU torch path.
+ */
+#ifndef DET_B200_H
+#define DET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DET_OK 0
+#define DET_ERR_BAD_ARG (-1)      /* null pointer, negative size, inconsistent shape            */
+#define DET_ERR_UNSUPPORTED (-2)  /* size beyond a documented limit                              */
+#define DET_ERR_WORKSPACE (-3)    /* workspace too small (see the matching *_workspace_bytes)    */
+#define DET_ERR_CUDA (-4)         /* a CUDA runtime call failed; see det_last_error()            */
+#define DET_ERR_ALIGN (-5)        /* pointer not aligned as documented                           */
+
+#define DET_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DET_API __attribute__((visibility("default")))
+#else
+#define DET_API
+#endif
+
+DET_API int det_abi_version(void);
+DET_API const char* det_last_error(void);
+/* number of SMs of the current device (grid sizing); negative on error */
+DET_API int det_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (2) pairwise box overlap -- replaces pairwise_iou / pairwise_ioa / pairwise_intersection /
+ *     matched_boxlist_iou, python/src/structures/boxes.py:193, :217, :173, :235.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DET_OVERLAP_IOU 0
+#define DET_OVERLAP_IOA 1
+#define DET_OVERLAP_INTERSECTION 2
+/* out[n*m + j]; boxes1 (n,4), boxes2 (m,4), 16-byte aligned rows */
+DET_API int det_pairwise_overlap(const float* boxes1, int64_t n, const float* boxes2, int64_t m, int mode, float* out,
+                         void* stream);
+/* out[i] = IoU(boxes1[i], boxes2[i]) without the empty-box guard (0/0 -> NaN), boxes.py:235 */
+DET_API int det_matched_iou(const float* boxes1, const float* boxes2, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) box codec -- replaces Box2BoxTransform.apply_deltas / get_deltas,
+ *     python/src/models/components/box_regression.py:75 and :33.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* deltas (m, k*4), boxes (m,4) -> out (m, k*4).  weights = (wx,wy,ww,wh). */
+DET_API int det_apply_deltas(const float* deltas, const float* boxes, int64_t m, int k, float wx, float wy, float ww,
+                     float wh, float scale_clamp, float* out, void* stream);
+/* src (m,4), tgt (m,4) -> out (m,4).  *invalid_flag (device int32, caller-zeroed) is set to 1 if any src width
+ * <= 0 (the reference asserts, box_regression.py:72). */
+DET_API int det_get_deltas(const float* src, const float* tgt, int64_t m, float wx, float wy, float ww, float wh, float* out,
+                   int32_t* invalid_flag, void* stream);
+/* grid anchors of one level, order (h,w,a) -- replaces AnchorGenerator._grid_anchors,
+ * python/src/models/modules/anchor_generators.py:158.  cell_anchors (a,4) device. out (h*w*a,4). */
+DET_API int det_grid_anchors(const float* cell_anchors, int a, int h, int w, int stride, float offset, float* out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) RPN head decode, DELTA mode -- replaces the layout change + _decode_proposals,
+ *     python/src/models/rpn.py:270-284 and :330-348 (anchors synthesised in-kernel, never read).
+ *     objectness (n,a,h,w) NCHW, deltas (n,a*4,h,w) NCHW -> logits_out (n,h*w*a), boxes_out (n,h*w*a,4).
+ *     `out_img_stride` = number of anchors between consecutive images in the outputs (>= h*w*a) and
+ *     `out_offset` the first anchor slot of this level, so all levels can land in one (n,R[,4]) buffer.
+ * ---------------------------------------------------------------------------------------------------------- */
+DET_API int det_rpn_decode_level(const float* objectness, const float* deltas, int n, int a, int h, int w, int stride,
+                         float offset, const float* cell_anchors, float wx, float wy, float ww, float wh,
+                         float scale_clamp, float* logits_out, float* boxes_out, int64_t out_img_stride,
+                         int64_t out_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (3) batched, category-partitioned NMS -- replaces batched_nms, python/src/utils.py:96 (and through it
+ *     torchvision.ops.batched_nms / nms), for a whole batch of images in one call.
+ *
+ *   boxes (n, m_max, 4), scores (n, m_max), categories (n, m_max) int64 or NULL (single category),
+ *   counts (n) int32 or NULL (every image has m_max boxes).
+ *   keep (n, max_out) int64: kept indices into the image's own m_max rows, by descending score, ties by
+ *   lower index; keep_counts (n) int32 = min(#kept, max_out).
+ *   mode: DET_NMS_AUTO reproduces the reference's CPU rule per image (count <= 1000 -> torchvision's
+ *         coordinate-offset trick evaluated in fp32, else per-category); the other two force a branch.
+ *   limits: m_max <= 131071, 0 <= category < 32768.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DET_NMS_AUTO 0
+#define DET_NMS_PER_CATEGORY 1
+#define DET_NMS_OFFSET_TRICK 2
+DET_API int64_t det_nms_workspace_bytes(int n, int64_t m_max);
+DET_API int det_nms_batched(const float* boxes, const float* scores, const int64_t* categories, const int32_t* counts,
+                    int n, int64_t m_max, double iou_threshold, int mode, int64_t max_out, int64_t* keep,
+                    int32_t* keep_counts, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (3) RPN proposal selection for the whole batch -- replaces find_top_rpn_proposals,
+ *     python/src/models/utils.py:9-109: per-level top-k, finite filter, clip, small-box filter, per-level NMS,
+ *     post-NMS top-k.  Input: all levels concatenated, boxes (n, r, 4), logits (n, r); level_sizes_host[l] =
+ *     anchors of level l (sum = r, l < 16); image_sizes (n,2) int32 device (h,w).
+ *     out_boxes (n, post_nms_topk, 4), out_logits (n, post_nms_topk), out_counts (n) int32.
+ *     *nonfinite_flag (device int32, caller-zeroed) is set if a selected box/logit is Inf/NaN (the reference
+ *     raises FloatingPointError in training, models/utils.py:82).
+ * ---------------------------------------------------------------------------------------------------------- */
+DET_API int64_t det_rpn_proposals_workspace_bytes(int n, int64_t r);
+DET_API int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r, const int64_t* level_sizes_host,
+                      int num_levels, const int32_t* image_sizes, double nms_thresh, int64_t pre_nms_topk,
+                      int64_t post_nms_topk, float min_box_size, float* out_boxes, float* out_logits,
+                      int32_t* out_counts, int32_t* nonfinite_flag, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1)+(3) YOLO-grid head: fused decode + score threshold + per-class NMS, one launch for the batch.
+ *     No reference implementation exists; the specification is oracle/ref_torch.py
+ *     yolo_decode / yolo_select_nms.  head (n, s, s, b*5+c) channels-last fp32; priors (b,2) device (w,h).
+ *     Optional dense outputs (NULL to skip): boxes (n,p,4), conf (n,p), scores (n,p,c), p = s*s*b.
+ *     Detections: det_flat (n,max_det) int64 = predictor*c + class, det_boxes (n,max_det,4), det_scores
+ *     (n,max_det), det_count (n) int32, by descending score.  limit: p*c <= 4096, c <= 1024.
+ * ---------------------------------------------------------------------------------------------------------- */
+DET_API int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
+                        float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
+                        float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
+                        int64_t* det_flat, float* det_boxes, float* det_scores, int32_t* det_count, void* stream);
+
+/* dense anchor head (YOLOv3-style, NCHW): head (n, a*(5+c), h, w) -> boxes (n,h*w*a,4), best score, best class.
+ * anchors_wh (a,2) device.  Output slots as in det_rpn_decode_level. */
+DET_API int det_dense_decode_level(const float* head, int n, int a, int c, int h, int w, int stride, const float* anchors_wh,
+                           float scale_clamp, float* boxes_out, float* score_out, int64_t* class_out,
+                           int64_t out_img_stride, int64_t out_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (4a) IoU target assignment -- replaces pairwise_iou + Matcher.__call__ + set_low_quality_matches_ as driven
+ *      by label_and_sample_anchors, python/src/models/rpn.py:161-168 / components/matcher.py:53-120, for the
+ *      whole batch and without materialising the (G,R) matrix.
+ *      gt_boxes (sum_g,4) concatenated, gt_offsets (n+1) int32, anchors (r,4).
+ *      thresholds_host (num_thresholds) ascending, labels_host (num_thresholds+1) in {-1,0,1}.
+ *      matched_idx (n,r) int64, labels (n,r) int8, matched_iou (n,r) fp32 or NULL.
+ * ---------------------------------------------------------------------------------------------------------- */
+DET_API int64_t det_match_workspace_bytes(int n, int64_t r, int64_t sum_g);
+DET_API int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors,
+                      int64_t r, const float* thresholds_host, const int32_t* labels_host, int num_thresholds,
+                      int allow_low_quality, int64_t* matched_idx, int8_t* labels, float* matched_iou,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+/* Matcher on a materialised quality matrix (g,r) -- Matcher.__call__, matcher.py:53. */
+DET_API int det_match_quality(const float* quality, int64_t g, int64_t r, const float* thresholds_host,
+                      const int32_t* labels_host, int num_thresholds, int allow_low_quality, int64_t* matched_idx,
+                      int8_t* labels, int32_t* negative_flag, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Uniform random fg/bg subsample on the device (statistically, not stream-, equivalent to subsample_labels +
+ * _subsample_labels, python/src/utils.py:34 / models/rpn.py:108): keeps min(#pos, int(s*f)) positives and
+ * min(#neg, s-#pos) negatives per image, everything else becomes -1.  labels (n,r) int8 in place. */
+DET_API int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, float positive_fraction, uint64_t seed,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (4b) fused RPN loss forward + backward -- replaces losses + _dense_box_regression_loss + get_deltas,
+ *      python/src/models/rpn.py:187-244, components/box_regression.py:128-168, :33-73, and autograd's backward.
+ *      logits (n,r), deltas (n,r,4), labels (n,r) int8, matched_idx (n,r) int64, gt as above, anchors (r,4).
+ *      loss_type 0 = smooth-L1(beta) (beta<1e-5 -> L1), 1 = GIoU.
+ *      sums (8) fp32, caller-zeroed: [0]=objectness BCE sum, [1]=localisation sum, [2]=#pos, [3]=#neg.
+ *      grad_logits (n,r) / grad_deltas (n,r,4): d(sum)/d(input) * grad_scale_{cls,loc}; NULL to skip backward.
+ * ---------------------------------------------------------------------------------------------------------- */
+DET_API int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
+                 const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r, float wx,
+                 float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
+                 float grad_scale_cls, float grad_scale_loc, float* sums, float* grad_logits, float* grad_deltas,
+                 void* stream);
+
+/* YOLO-grid fused loss forward + backward (own specification: oracle/ref_torch.py yolo_loss).
+ * head (n,s,s,b*5+c); labels (n,p) int8; matched_idx (n,p) int64; gt_classes (sum_g) int64.
+ * sums (8): [0]=loc, [1]=obj, [2]=cls, [3]=#pos, [4]=#neg.  grad_head same shape as head (fully written). */
+DET_API int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
+                  const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
+                  int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
+                  float* sums, float* grad_head, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DET_B200_H */

@@ -1,0 +1,394 @@
+// Large path of the batched NMS: images with up to 131071 boxes each, any number of images per call.
+//
+// Data layout in the caller's workspace (HBM), all arrays image-major with a padded row of Mp = roundup(m_max,
+// 2048) slots: two u64 key buffers (ping-pong for the merge passes), boxes in sorted order (float4) + their
+// areas, one state byte and one kept-list slot per position, and two segment work lists.
+// Launch sequence: [stats] -> keys -> tile sort -> log2(Mp/2048) merge passes -> gather (+segment discovery)
+//   -> warp segments (persistent, atomic work counter) -> CTA segments (persistent) -> re-key kept -> sort -> emit.
+#pragma once
+#include "nms_core.cuh"
+
+namespace det {
+
+constexpr int kLargeIdxBits = 17;
+constexpr int kTile = 2048;
+constexpr int kSortThreads = 256;
+constexpr int kVT = kTile / kSortThreads;
+constexpr int kLargeWarpSegMax = 256;  // segments up to this length are swept by one warp
+constexpr int kSegThreads = 256;
+
+struct LargeImg {
+    int32_t cnt;
+    int32_t trick;
+    int32_t fast;
+    float span;
+    int32_t nkept;
+    int32_t bad;
+    int32_t nsurv;
+    int32_t pad;
+};
+
+struct LargeLayout {
+    int n;
+    int64_t m_max, mp, segcap;
+    int64_t off_info, off_ctr, off_keys_a, off_keys_b, off_sbox, off_sarea, off_state, off_klist, off_seg_small,
+        off_seg_large, total;
+    LargeLayout(int n_, int64_t m_) : n(n_), m_max(m_) {
+        mp = (m_max + kTile - 1) / kTile * kTile;
+        segcap = mp < 32768 ? mp : 32768;
+        int64_t o = 0;
+        auto take = [&](int64_t bytes) {
+            int64_t at = o;
+            o += (bytes + 255) / 256 * 256;
+            return at;
+        };
+        off_info = take((int64_t)sizeof(LargeImg) * n);
+        off_ctr = take(64);
+        off_keys_a = take(8 * n * mp);
+        off_keys_b = take(8 * n * mp);
+        off_sbox = take(16 * n * mp);
+        off_sarea = take(4 * n * mp);
+        off_state = take(n * mp);
+        off_klist = take(4 * n * mp);
+        off_seg_small = take(16 * n * segcap);
+        off_seg_large = take(16 * n * segcap);
+        total = o;
+    }
+};
+
+struct LargeWs {
+    LargeImg* info;
+    int32_t* ctr;  // [0] #small segs, [1] #large segs, [2] next small, [3] next large
+    uint64_t *keys_a, *keys_b;
+    float4* sbox;
+    float* sarea;
+    uint8_t* state;
+    int32_t* klist;
+    int4 *seg_small, *seg_large;
+    LargeWs(const LargeLayout& l, void* base) {
+        char* b = static_cast<char*>(base);
+        info = reinterpret_cast<LargeImg*>(b + l.off_info);
+        ctr = reinterpret_cast<int32_t*>(b + l.off_ctr);
+        keys_a = reinterpret_cast<uint64_t*>(b + l.off_keys_a);
+        keys_b = reinterpret_cast<uint64_t*>(b + l.off_keys_b);
+        sbox = reinterpret_cast<float4*>(b + l.off_sbox);
+        sarea = reinterpret_cast<float*>(b + l.off_sarea);
+        state = reinterpret_cast<uint8_t*>(b + l.off_state);
+        klist = reinterpret_cast<int32_t*>(b + l.off_klist);
+        seg_small = reinterpret_cast<int4*>(b + l.off_seg_small);
+        seg_large = reinterpret_cast<int4*>(b + l.off_seg_large);
+    }
+};
+
+using KLL = KeyLayout<kLargeIdxBits>;
+
+// ---- per-image mode + coordinate statistics ------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+large_stats_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats,
+                   const int32_t* __restrict__ counts, int64_t m_max, float thr_f, int mode, LargeImg* info) {
+    __shared__ float r_max[8], r_min[8];
+    __shared__ int r_flag[8];
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int cnt = counts ? counts[img] : (int)m_max;
+    cnt = max(0, min(cnt, (int)m_max));
+    const bool trick = (mode == DET_NMS_AUTO) ? (cnt <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
+    float mx = -INFINITY, mn = INFINITY;
+    int fin = 1, maxcat = 0;
+    if (trick) {
+        for (int i = tid; i < cnt; i += 256) {
+            const float4 b = boxes[(int64_t)img * m_max + i];
+            mx = max_nan(mx, max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w)));
+            mn = min_nan(mn, min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w)));
+            fin &= (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
+            if (cats) maxcat = max(maxcat, (int)cats[(int64_t)img * m_max + i]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        fin &= __shfl_xor_sync(0xffffffffu, fin, o);
+        maxcat = max(maxcat, __shfl_xor_sync(0xffffffffu, maxcat, o));
+    }
+    if (lane == 0) {
+        r_max[wid] = mx;
+        r_min[wid] = mn;
+        r_flag[wid] = fin | (maxcat << 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            mx = max_nan(mx, r_max[w]);
+            mn = min_nan(mn, r_min[w]);
+            fin &= r_flag[w] & 1;
+            maxcat = max(maxcat, r_flag[w] >> 1);
+        }
+        LargeImg li;
+        li.cnt = cnt;
+        li.trick = trick ? 1 : 0;
+        li.span = trick ? mx + 1.0f : 0.f;
+        const float far = mx + (float)maxcat * li.span;
+        li.fast = (!trick) || (fin && mn > -1.0f && thr_f >= 0.0f && isfinite(far));
+        li.nkept = 0;
+        li.bad = 0;
+        li.nsurv = cnt;
+        li.pad = 0;
+        info[img] = li;
+    }
+}
+
+// ---- keys ----------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+large_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cats, int64_t m_max, int64_t mp,
+                  LargeImg* info, uint64_t* __restrict__ keys) {
+    const int img = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= mp) return;
+    const LargeImg li = info[img];
+    uint64_t k = kSentinelKey;
+    if (i < li.cnt) {
+        const int64_t c = cats ? cats[(int64_t)img * m_max + i] : 0;
+        if (c < 0 || c >= (1 << kSegBits) - 1) info[img].bad = 1;
+        const bool by_cat = !li.trick || li.fast;
+        k = KLL::make(by_cat ? (uint32_t)(c & ((1 << kSegBits) - 1)) : 0u, scores[(int64_t)img * m_max + i], (uint32_t)i);
+    }
+    keys[(int64_t)img * mp + i] = k;
+}
+
+// ---- sort: 2048-key tiles in shared memory, then merge-path passes ------------------------------------
+static __global__ void __launch_bounds__(kSortThreads) sort_tiles_kernel(uint64_t* __restrict__ keys, int64_t mp) {
+    __shared__ uint64_t s[kTile];
+    uint64_t* g = keys + (int64_t)blockIdx.y * mp + (int64_t)blockIdx.x * kTile;
+#pragma unroll
+    for (int v = 0; v < kVT; ++v) s[threadIdx.x + v * kSortThreads] = g[threadIdx.x + v * kSortThreads];
+    __syncthreads();
+    cta_bitonic_sort<kSortThreads>(s, kTile);
+#pragma unroll
+    for (int v = 0; v < kVT; ++v) g[threadIdx.x + v * kSortThreads] = s[threadIdx.x + v * kSortThreads];
+}
+
+// first index a in [lo,hi] of the merge path crossing diagonal d of (A[0..na), B[0..nb)); keys are unique
+template <typename P>
+__device__ __forceinline__ int64_t merge_path(P A, int64_t na, P B, int64_t nb, int64_t d) {
+    int64_t lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (A[mid] < B[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+static __global__ void __launch_bounds__(kSortThreads)
+merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t mp, int64_t width) {
+    __shared__ uint64_t s[kTile];
+    __shared__ int64_t s_cut[2];
+    const uint64_t* kin = in + (int64_t)blockIdx.y * mp;
+    uint64_t* kout = out + (int64_t)blockIdx.y * mp;
+    const int64_t out0 = (int64_t)blockIdx.x * kTile;
+    const int64_t lo = out0 / (2 * width) * (2 * width);
+    const int64_t a_len = min(width, mp - lo);
+    const int64_t b_lo = lo + a_len;
+    const int64_t b_len = max((int64_t)0, min(width, mp - b_lo));
+    const uint64_t* A = kin + lo;
+    const uint64_t* B = kin + b_lo;
+    const int64_t d0 = out0 - lo, d1 = min(d0 + (int64_t)kTile, a_len + b_len);
+    if (threadIdx.x < 2) s_cut[threadIdx.x] = merge_path(A, a_len, B, b_len, threadIdx.x ? d1 : d0);
+    __syncthreads();
+    const int64_t a0 = s_cut[0], a1 = s_cut[1];
+    const int64_t b0 = d0 - a0, b1 = d1 - a1;
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+    for (int t = threadIdx.x; t < na; t += kSortThreads) s[t] = A[a0 + t];
+    for (int t = threadIdx.x; t < nb; t += kSortThreads) s[na + t] = B[b0 + t];
+    __syncthreads();
+    const uint64_t* sa = s;
+    const uint64_t* sb = s + na;
+    const int total = na + nb;
+    const int diag = min((int)threadIdx.x * kVT, total);
+    int ai = (int)merge_path(sa, (int64_t)na, sb, (int64_t)nb, (int64_t)diag);
+    int bi = diag - ai;
+    uint64_t r[kVT];
+#pragma unroll
+    for (int v = 0; v < kVT; ++v) {
+        const bool has = diag + v < total;
+        const bool take_a = has && (bi >= nb || (ai < na && sa[ai] < sb[bi]));
+        r[v] = has ? (take_a ? sa[ai] : sb[bi]) : 0;
+        ai += (has && take_a) ? 1 : 0;
+        bi += (has && !take_a) ? 1 : 0;
+    }
+#pragma unroll
+    for (int v = 0; v < kVT; ++v)
+        if (diag + v < total) kout[out0 + diag + v] = r[v];
+}
+
+// sorts every image's row of mp keys ascending; returns the buffer that holds the result
+static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStream_t st) {
+    dim3 grid((unsigned)(mp / kTile), (unsigned)n);
+    sort_tiles_kernel<<<grid, kSortThreads, 0, st>>>(a, mp);
+    uint64_t *src = a, *dst = b;
+    for (int64_t width = kTile; width < mp; width *= 2) {
+        merge_pass_kernel<<<grid, kSortThreads, 0, st>>>(src, dst, mp, width);
+        uint64_t* t = src;
+        src = dst;
+        dst = t;
+    }
+    return src;
+}
+
+// push segment [s,e) of image img on the short or long work list
+__device__ __forceinline__ void push_segment(int img, int s, int e, int32_t* ctr, int4* seg_small, int4* seg_large) {
+    if (e - s <= kLargeWarpSegMax) {
+        const int slot = atomicAdd(&ctr[0], 1);
+        seg_small[slot] = make_int4(img, s, e, 0);
+    } else {
+        const int slot = atomicAdd(&ctr[1], 1);
+        seg_large[slot] = make_int4(img, s, e, 0);
+    }
+}
+
+// upper end of the segment that starts at p: first position in (p, cnt) whose segment field differs
+__device__ __forceinline__ int segment_end(const uint64_t* k, int p, int cnt, uint32_t sg) {
+    int lo = p + 1, hi = cnt;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KLL::seg(k[mid]) > sg) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// ---- gather boxes into sorted order (+ coordinate offset), discover segments -------------------------
+static __global__ void __launch_bounds__(256)
+large_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats, int64_t m_max, int64_t mp,
+                    const LargeImg* __restrict__ info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
+                    float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* ctr, int4* seg_small,
+                    int4* seg_large) {
+    const int img = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const LargeImg li = info[img];
+    if (p >= li.cnt) return;
+    const uint64_t* k = keys + (int64_t)img * mp;
+    const uint64_t key = k[p];
+    const int i = (int)KLL::idx(key);
+    float4 b = boxes[(int64_t)img * m_max + i];
+    if (li.trick) {
+        const int64_t c = cats ? cats[(int64_t)img * m_max + i] : 0;
+        const float off = (float)c * li.span;
+        b.x += off; b.y += off; b.z += off; b.w += off;
+    }
+    sbox[(int64_t)img * mp + p] = b;
+    sarea[(int64_t)img * mp + p] = box_area(b);
+    state[(int64_t)img * mp + p] = 0;
+    const uint32_t sg = KLL::seg(key);
+    if (p == 0 || KLL::seg(k[p - 1]) != sg) push_segment(img, p, segment_end(k, p, li.cnt, sg), ctr, seg_small, seg_large);
+}
+
+// ---- persistent segment kernels ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128)
+large_warp_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const float* __restrict__ sarea,
+                           uint8_t* state, int32_t* klist, int32_t* ctr, const int4* __restrict__ seg_small,
+                           float thr_f, int max_keep) {
+    const int lane = threadIdx.x & 31;
+    const int total = ctr[0];
+    while (true) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&ctr[2], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= total) break;
+        const int4 sg = seg_small[i];
+        const int64_t o = (int64_t)sg.x * mp;
+        warp_segment_nms<int32_t>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
+    }
+}
+
+static __global__ void __launch_bounds__(kSegThreads)
+large_cta_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const float* __restrict__ sarea,
+                          uint8_t* state, int32_t* klist, int32_t* ctr, const int4* __restrict__ seg_large,
+                          float thr_f, int max_keep) {
+    __shared__ uint32_t rowbits[kSegThreads * (kSegThreads / 32)];
+    __shared__ uint32_t amask[kSegThreads / 32];
+    __shared__ int s_nk, s_next;
+    const int total = ctr[1];
+    while (true) {
+        if (threadIdx.x == 0) s_next = atomicAdd(&ctr[3], 1);
+        __syncthreads();
+        const int i = s_next;
+        __syncthreads();
+        if (i >= total) break;
+        const int4 sg = seg_large[i];
+        const int64_t o = (int64_t)sg.x * mp;
+        cta_segment_nms<kSegThreads, int32_t>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
+                                              rowbits, amask, &s_nk);
+    }
+}
+
+// ---- kept -> output keys, count -----------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+large_rekey_kernel(int64_t mp, LargeImg* info, const uint64_t* __restrict__ keys, const uint8_t* __restrict__ state,
+                   uint64_t* __restrict__ keys_out) {
+    const int img = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int cnt = info[img].cnt;
+    bool kept = false;
+    if (p < mp) {
+        kept = (p < cnt) && state[(int64_t)img * mp + p] == 2;
+        keys_out[(int64_t)img * mp + p] = kept ? KLL::strip_seg(keys[(int64_t)img * mp + p]) : kSentinelKey;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&info[img].nkept, __popc(bal));
+}
+
+static __global__ void __launch_bounds__(256)
+large_emit_kernel(int64_t mp, const LargeImg* __restrict__ info, const uint64_t* __restrict__ keys, int64_t max_out,
+                  int64_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
+    const int img = blockIdx.y;
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const LargeImg li = info[img];
+    const int64_t nout = li.bad ? 0 : min((int64_t)li.nkept, max_out);
+    if (j < nout) keep[(int64_t)img * max_out + j] = (int64_t)KLL::idx(keys[(int64_t)img * mp + j]);
+    if (j == 0) keep_counts[img] = li.bad ? -1 : (int32_t)nout;
+}
+
+// runs the two persistent segment kernels over the lists built by a gather kernel
+static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float thr_f, int max_keep, cudaStream_t st) {
+    const int sms = sm_count();
+    large_warp_segments_kernel<<<sms * 8, 128, 0, st>>>(lay.mp, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
+                                                        ws.seg_small, thr_f, max_keep);
+    DET_LAUNCH_OK("large_warp_segments_kernel");
+    large_cta_segments_kernel<<<sms * 2, kSegThreads, 0, st>>>(lay.mp, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
+                                                               ws.seg_large, thr_f, max_keep);
+    DET_LAUNCH_OK("large_cta_segments_kernel");
+    return DET_OK;
+}
+
+static int large_nms_run(const LargeLayout& lay, void* workspace, const float* boxes, const float* scores,
+                         const int64_t* cats, const int32_t* counts, float thr_f, int mode, int64_t max_out,
+                         int64_t* keep, int32_t* keep_counts, cudaStream_t st) {
+    LargeWs ws(lay, workspace);
+    const int n = lay.n;
+    const int64_t mp = lay.mp;
+    auto b4 = reinterpret_cast<const float4*>(boxes);
+    cudaError_t e = cudaMemsetAsync(ws.ctr, 0, 64, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    large_stats_kernel<<<n, 256, 0, st>>>(b4, cats, counts, lay.m_max, thr_f, mode, ws.info);
+    DET_LAUNCH_OK("large_stats_kernel");
+    dim3 grid_e((unsigned)((mp + 255) / 256), (unsigned)n);
+    large_keys_kernel<<<grid_e, 256, 0, st>>>(scores, cats, lay.m_max, mp, ws.info, ws.keys_a);
+    DET_LAUNCH_OK("large_keys_kernel");
+    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st);
+    uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
+    DET_LAUNCH_OK("sort_rows");
+    large_gather_kernel<<<grid_e, 256, 0, st>>>(b4, cats, lay.m_max, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state,
+                                                ws.ctr, ws.seg_small, ws.seg_large);
+    DET_LAUNCH_OK("large_gather_kernel");
+    const int max_keep = (int)min(max_out, (int64_t)lay.m_max);
+    int rc = run_segment_kernels(lay, ws, thr_f, max_keep, st);
+    if (rc != DET_OK) return rc;
+    large_rekey_kernel<<<grid_e, 256, 0, st>>>(mp, ws.info, sorted, ws.state, other);
+    DET_LAUNCH_OK("large_rekey_kernel");
+    uint64_t* final_keys = sort_rows(other, sorted, n, mp, st);
+    DET_LAUNCH_OK("sort_rows(2)");
+    dim3 grid_o((unsigned)((min(max_out, lay.m_max) + 255) / 256), (unsigned)n);
+    large_emit_kernel<<<grid_o, 256, 0, st>>>(mp, ws.info, final_keys, max_out, keep, keep_counts);
+    DET_LAUNCH_OK("large_emit_kernel");
+    return DET_OK;
+}
+
+}  // namespace det

@@ -1,0 +1,17 @@
+"""det_b200 -- B200-native (sm_100a) post-backbone detection hot path.
+
+Drop-in for the reference's Python callables on that path; every op forwards to
+hand-written CUDA kernels in ``libdet_b200.so`` through the C ABI of ``include/det_b200.h``.
+There is no CPU path and no PyTorch fallback.
+"""
+from . import _native
+from .structures import (Boxes, Instances, pairwise_iou, pairwise_ioa, pairwise_intersection,
+                         matched_boxlist_iou)
+from .box_regression import Box2BoxTransform
+from .anchors import AnchorGenerator, generate_cell_anchors
+from .nms import batched_nms, nms, nms_images
+
+__all__ = [
+    "Boxes", "Instances", "pairwise_iou", "pairwise_ioa", "pairwise_intersection", "matched_boxlist_iou",
+    "Box2BoxTransform", "AnchorGenerator", "generate_cell_anchors", "batched_nms", "nms", "nms_images",
+]

@@ -1,0 +1,119 @@
+"""GPU parity: batched NMS kernels vs the CPU oracle -- kept indices and counts bit-exact."""
+import pytest
+import torch
+
+from tests.util import gen, rand_boxes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def det():
+    import det_b200
+    return det_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ref_torch
+    return ref_torch
+
+
+def _case(n, ncat, seed, frame=640.0, quant=False, ties=False):
+    g = gen(seed)
+    b = rand_boxes(n, frame, g)
+    if quant:
+        b = b.round()
+    s = torch.rand(n, generator=g)
+    if ties:
+        s = (s * 16).round() / 16
+    c = torch.randint(0, ncat, (n,), generator=g)
+    return b, s, c
+
+
+@pytest.mark.parametrize("n,ncat", [(1, 1), (2, 1), (31, 3), (100, 1), (257, 5), (900, 80), (1000, 20), (1001, 20),
+                                     (1024, 7), (1960, 20), (2048, 80), (3000, 80), (4096, 1), (4097, 3),
+                                     (6000, 5), (25200, 80), (25200, 1)])
+@pytest.mark.parametrize("thr", [0.5, 0.7])
+def test_batched_nms_matches_oracle(det, O, n, ncat, thr):
+    b, s, c = _case(n, ncat, seed=n * 7 + ncat, quant=(n % 2 == 0), ties=(n % 3 == 0))
+    want = O.batched_nms(b, s, c, thr)
+    got = det.batched_nms(b.cuda(), s.cuda(), c.cuda(), thr).cpu()
+    assert got.dtype == torch.int64
+    assert got.numel() == want.numel()
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("n", [50, 700, 5000])
+def test_nms_single_category_vs_torchvision_semantics(det, O, n):
+    b, s, _ = _case(n, 1, seed=n, frame=200.0)
+    assert torch.equal(det.nms(b.cuda(), s.cuda(), 0.3).cpu(), O.nms(b, s, 0.3))
+
+
+def test_threshold_is_strict_and_double(det, O):
+    # IoU exactly 0.5 is kept (strict >); IoU == float32(0.7) is kept against the double 0.7
+    b = torch.tensor([[0, 0, 2, 1], [0, 0, 1, 1.0]])
+    s = torch.tensor([1.0, 0.5])
+    assert det.nms(b.cuda(), s.cuda(), 0.5).tolist() == [0, 1]
+    b = torch.tensor([[0, 0, 10, 1], [0, 0, 7, 1.0]])
+    assert det.nms(b.cuda(), s.cuda(), 0.7).tolist() == O.nms(b, s, 0.7).tolist() == [0, 1]
+    assert det.nms(b.cuda(), s.cuda(), 0.6999).tolist() == O.nms(b, s, 0.6999).tolist() == [0]
+
+
+def test_nan_scores_and_degenerate_boxes(det, O):
+    g = gen(3)
+    b = rand_boxes(300, 100.0, g)
+    s = torch.rand(300, generator=g)
+    s[::17] = float("nan")
+    b[5] = torch.tensor([1.0, 1.0, 1.0, 1.0])
+    b[6] = torch.tensor([1.0, 1.0, 1.0, 1.0])
+    c = torch.randint(0, 3, (300,), generator=g)
+    for mode_n in (300,):
+        assert torch.equal(det.batched_nms(b.cuda(), s.cuda(), c.cuda(), 0.5).cpu(), O.batched_nms(b, s, c, 0.5))
+
+
+def test_offset_trick_with_negative_coordinates(det, O):
+    # coordinates below -1 can make boxes of different categories overlap after the offset: general path
+    g = gen(9)
+    b = rand_boxes(400, 300.0, g) - 150.0
+    s = torch.rand(400, generator=g)
+    c = torch.randint(0, 4, (400,), generator=g)
+    assert torch.equal(det.batched_nms(b.cuda(), s.cuda(), c.cuda(), 0.3).cpu(), O.batched_nms(b, s, c, 0.3))
+
+
+def test_images_batch_with_counts(det, O):
+    g = gen(21)
+    n_img, m = 9, 1500
+    boxes = torch.stack([rand_boxes(m, 400.0, g) for _ in range(n_img)])
+    scores = torch.rand(n_img, m, generator=g)
+    cats = torch.randint(0, 20, (n_img, m), generator=g)
+    counts = torch.tensor([1500, 0, 1, 999, 1000, 1001, 1499, 64, 65], dtype=torch.int32)
+    keep, kc = det.nms_images(boxes.cuda(), scores.cuda(), cats.cuda(), counts.cuda(), 0.5)
+    keep, kc = keep.cpu(), kc.cpu()
+    for i in range(n_img):
+        k = int(counts[i])
+        want = O.batched_nms(boxes[i, :k], scores[i, :k], cats[i, :k], 0.5)
+        assert int(kc[i]) == want.numel()
+        assert torch.equal(keep[i, :want.numel()], want)
+
+
+def test_images_batch_large_path_max_out(det, O):
+    g = gen(22)
+    n_img, m = 3, 7000
+    boxes = torch.stack([rand_boxes(m, 500.0, g) for _ in range(n_img)])
+    scores = torch.rand(n_img, m, generator=g)
+    cats = torch.randint(0, 5, (n_img, m), generator=g)
+    counts = torch.tensor([7000, 4500, 10], dtype=torch.int32)
+    keep, kc = det.nms_images(boxes.cuda(), scores.cuda(), cats.cuda(), counts.cuda(), 0.6, max_out=300)
+    keep, kc = keep.cpu(), kc.cpu()
+    for i in range(n_img):
+        k = int(counts[i])
+        want = O.batched_nms(boxes[i, :k], scores[i, :k], cats[i, :k], 0.6)[:300]
+        assert int(kc[i]) == want.numel()
+        assert torch.equal(keep[i, :want.numel()], want)
+
+
+def test_bad_category_raises(det):
+    b = torch.tensor([[0, 0, 1, 1.0]]).cuda()
+    with pytest.raises(ValueError):
+        det.batched_nms(b, torch.tensor([1.0]).cuda(), torch.tensor([-3]).cuda(), 0.5)
