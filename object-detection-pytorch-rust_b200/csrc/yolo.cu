@@ -1,0 +1,315 @@
+// Grid / anchor detection-head decode (subsystem 1) for the two YOLO-style layouts named by the north star.
+//
+//  * det_yolo_decode_nms : S x S x (B*5+C) channels-last grid head.  ONE launch for the whole batch, one CTA per
+//    image: coalesced 16-byte loads of the image's logits into shared memory, sigmoid/exp decode, conf x class
+//    scores, score threshold with an order-preserving block-scan compaction, and the per-class NMS of
+//    nms_small.cuh -- the candidates never leave shared memory.
+//  * det_dense_decode_level : dense anchor head in the conv layout (N, A*(5+C), H, W).  A thread owns 4 consecutive
+//    spatial positions: every channel plane is read with coalesced 16-byte loads, the class arg-max is kept in
+//    registers, outputs are (h, w, a)-ordered boxes / best score / best class.
+//
+// No reference implementation exists for either; the specification is
+// oracle/ref_torch.py (yolo_decode, yolo_select_nms, dense_decode).
+#include "nms_small.cuh"
+
+namespace det {
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+struct YoloCandidates {
+    const float4* pbox;
+    const float* cscore;
+    const uint16_t* cflat;
+    int C;
+    __device__ __forceinline__ float4 box(int i) const { return pbox[cflat[i] / C]; }
+    __device__ __forceinline__ float score(int i) const { return cscore[i]; }
+    __device__ __forceinline__ int64_t cat(int i) const { return (int64_t)(cflat[i] % C); }
+};
+
+struct YoloParams {
+    int n, s, b, c;
+    float stride_x, stride_y, img_w, img_h, scale_clamp, score_thresh, thr_f;
+    int clip, mode;
+    int64_t max_det;
+};
+
+constexpr int kYoloMaxPred = 1024;
+constexpr int kYoloMaxHead = 6144;
+
+template <int CAP>
+__global__ void __launch_bounds__(kSmallThreads)
+yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict__ priors, YoloParams prm,
+                       float4* __restrict__ dense_boxes, float* __restrict__ dense_conf,
+                       float* __restrict__ dense_scores, int64_t* __restrict__ det_flat,
+                       float4* __restrict__ det_boxes, float* __restrict__ det_scores,
+                       int32_t* __restrict__ det_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSmem<CAP>& sm = *reinterpret_cast<SmallSmem<CAP>*>(smem_raw);
+    unsigned char* extra = smem_raw + ((sizeof(SmallSmem<CAP>) + 15) / 16) * 16;
+    const int S2 = prm.s * prm.s, B = prm.b, C = prm.c, ch = B * 5 + C, P = S2 * B, PC = P * C;
+    float4* pbox = reinterpret_cast<float4*>(extra);
+    float* cscore = reinterpret_cast<float*>(pbox + P);
+    float* hs = cscore + CAP;
+    uint16_t* cflat = reinterpret_cast<uint16_t*>(hs + ((S2 * ch + 3) & ~3));
+    __shared__ int s_warp_tot[kSmallThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int img = blockIdx.x;
+
+    // ---- stage this image's logits: 16-byte coalesced loads over the aligned interior of its span
+    const int64_t g0 = (int64_t)img * S2 * ch, g1 = g0 + (int64_t)S2 * ch;
+    const float4* head4 = reinterpret_cast<const float4*>(head);
+    for (int64_t v = (g0 >> 2) + tid; v < ((g1 + 3) >> 2); v += kSmallThreads) {
+        const int64_t base = v << 2;
+        if (base >= g0 && base + 4 <= g1) {
+            const float4 q = ld_stream(head4 + v);
+            float* d = hs + (base - g0);
+            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+        } else {
+            for (int e = 0; e < 4; ++e)
+                if (base + e >= g0 && base + e < g1) hs[base + e - g0] = ld_stream(head + base + e);
+        }
+    }
+    __syncthreads();
+    // ---- decode: boxes + confidences per predictor, class probabilities per cell (in place over the logits)
+    for (int p = tid; p < P; p += kSmallThreads) {
+        const int cell = p / B, bi = p - cell * B;
+        const int row = cell / prm.s, col = cell - row * prm.s;
+        float* t = hs + cell * ch + bi * 5;
+        const float2 pr = priors[bi];
+        const float cx = (sigmoidf_ref(t[0]) + (float)col) * prm.stride_x;
+        const float cy = (sigmoidf_ref(t[1]) + (float)row) * prm.stride_y;
+        float tw = t[2], th = t[3];
+        tw = (tw > prm.scale_clamp) ? prm.scale_clamp : tw;
+        th = (th > prm.scale_clamp) ? prm.scale_clamp : th;
+        const float w = expf(tw) * pr.x, h = expf(th) * pr.y;
+        float4 bx = make_float4(cx - 0.5f * w, cy - 0.5f * h, cx + 0.5f * w, cy + 0.5f * h);
+        if (prm.clip) {  // torch clamp(min=0,max=W): NaN stays NaN
+            bx.x = min_nan(max_nan(bx.x, 0.f), prm.img_w); bx.z = min_nan(max_nan(bx.z, 0.f), prm.img_w);
+            bx.y = min_nan(max_nan(bx.y, 0.f), prm.img_h); bx.w = min_nan(max_nan(bx.w, 0.f), prm.img_h);
+        }
+        pbox[p] = bx;
+        const float conf = sigmoidf_ref(t[4]);
+        t[4] = conf;
+        if (dense_boxes) dense_boxes[(int64_t)img * P + p] = bx;
+        if (dense_conf) dense_conf[(int64_t)img * P + p] = conf;
+    }
+    for (int i = tid; i < S2 * C; i += kSmallThreads) {
+        const int cell = i / C, ci = i - cell * C;
+        float* q = hs + cell * ch + B * 5 + ci;
+        *q = sigmoidf_ref(*q);
+    }
+    __syncthreads();
+    // ---- scores, threshold, order-preserving compaction (each thread owns a contiguous run of flat ids)
+    const int per = (PC + kSmallThreads - 1) / kSmallThreads;
+    const int f0 = min(tid * per, PC), f1 = min(f0 + per, PC);
+    int mine = 0;
+    for (int f = f0; f < f1; ++f) {
+        const int p = f / C, ci = f - p * C;
+        const int cell = p / B, bi = p - cell * B;
+        const float sc = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + ci];
+        mine += (sc > prm.score_thresh) ? 1 : 0;
+        if (dense_scores) dense_scores[(int64_t)img * PC + f] = sc;
+    }
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads();
+    int offset = incl - mine, cnt = 0;
+    for (int w = 0; w < kSmallThreads / 32; ++w) {
+        const int tot = s_warp_tot[w];
+        if (w < wid) offset += tot;
+        cnt += tot;
+    }
+    for (int f = f0; f < f1; ++f) {
+        const int p = f / C, ci = f - p * C;
+        const int cell = p / B, bi = p - cell * B;
+        const float sc = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + ci];
+        if (sc > prm.score_thresh) {
+            cflat[offset] = (uint16_t)f;
+            cscore[offset] = sc;
+            ++offset;
+        }
+    }
+    __syncthreads();
+    // ---- per-class NMS in shared memory
+    const int cap_out = (int)min(prm.max_det, (int64_t)CAP);
+    const YoloCandidates src{pbox, cscore, cflat, C};
+    const int kept = small_nms_body<CAP>(sm, src, cnt, prm.thr_f, prm.mode, cap_out);
+    const int nout = kept < 0 ? 0 : min(kept, cap_out);
+    using KL = KeyLayout<kSmallIdxBits>;
+    for (int j = tid; j < nout; j += kSmallThreads) {
+        const int i = (int)KL::idx(sm.keys[j]);
+        const int f = cflat[i];
+        const int64_t o = (int64_t)img * prm.max_det + j;
+        det_flat[o] = f;
+        if (det_boxes) det_boxes[o] = pbox[f / C];
+        if (det_scores) det_scores[o] = cscore[i];
+    }
+    if (tid == 0) det_count[img] = nout;
+}
+
+template <int CAP>
+static int launch_yolo(const float* head, const float* priors, const YoloParams& prm, float* dense_boxes,
+                       float* dense_conf, float* dense_scores, int64_t* det_flat, float* det_boxes, float* det_scores,
+                       int32_t* det_count, cudaStream_t st) {
+    const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c, P = S2 * prm.b;
+    size_t smem = ((sizeof(SmallSmem<CAP>) + 15) / 16) * 16;
+    smem += sizeof(float4) * P + sizeof(float) * CAP + sizeof(float) * ((S2 * ch + 3) & ~3) + sizeof(uint16_t) * CAP;
+    cudaError_t e = cudaFuncSetAttribute(yolo_decode_nms_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(yolo_decode_nms_kernel)");
+    yolo_decode_nms_kernel<CAP><<<prm.n, kSmallThreads, smem, st>>>(
+        head, reinterpret_cast<const float2*>(priors), prm, reinterpret_cast<float4*>(dense_boxes), dense_conf,
+        dense_scores, det_flat, reinterpret_cast<float4*>(det_boxes), det_scores, det_count);
+    DET_LAUNCH_OK("yolo_decode_nms_kernel");
+    return DET_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense anchor head, conv layout
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256)
+dense_decode_level_kernel(const float* __restrict__ head, int a, int c, int h, int w, float stride,
+                          const float2* __restrict__ anchors_wh, float scale_clamp, float4* __restrict__ boxes_out,
+                          float* __restrict__ score_out, int64_t* __restrict__ class_out, int64_t out_img_stride,
+                          int64_t out_offset) {
+    const int64_t hw = (int64_t)h * w;
+    const int64_t groups = (hw + V - 1) / V;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    if (g >= groups) return;
+    const int64_t p0 = g * V;
+    const int nch = 5 + c;
+    float colf[V], rowf[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        colf[v] = (float)((p0 + v) % w);
+        rowf[v] = (float)((p0 + v) / w);
+    }
+    const int64_t obase = (int64_t)img * out_img_stride + out_offset;
+    for (int ai = 0; ai < a; ++ai) {
+        const float* pl = head + ((int64_t)(img * a + ai) * nch) * hw + p0;
+        float t[5][V];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (V == 4) {
+                const float4 q = ld_stream(reinterpret_cast<const float4*>(pl + k * hw));
+                t[k][0] = q.x; t[k][1] = q.y; t[k][2] = q.z; t[k][3] = q.w;
+            } else {
+                t[k][0] = ld_stream(pl + k * hw);
+            }
+        }
+        float best[V];
+        int bidx[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            best[v] = -INFINITY;
+            bidx[v] = 0;
+        }
+        // running arg-max over the class planes; first maximum wins, a NaN wins over everything (torch.max)
+#pragma unroll 4
+        for (int k = 0; k < c; ++k) {
+            float q[V];
+            if (V == 4) {
+                const float4 q4 = ld_stream(reinterpret_cast<const float4*>(pl + (int64_t)(5 + k) * hw));
+                q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+            } else {
+                q[0] = ld_stream(pl + (int64_t)(5 + k) * hw);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const bool take = (k == 0) || (q[v] > best[v]) || (q[v] != q[v] && best[v] == best[v]);
+                best[v] = take ? q[v] : best[v];
+                bidx[v] = take ? k : bidx[v];
+            }
+        }
+        const float2 awh = anchors_wh[ai];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float cx = (sigmoidf_ref(t[0][v]) + colf[v]) * stride;
+            const float cy = (sigmoidf_ref(t[1][v]) + rowf[v]) * stride;
+            float tw = t[2][v], th = t[3][v];
+            tw = (tw > scale_clamp) ? scale_clamp : tw;
+            th = (th > scale_clamp) ? scale_clamp : th;
+            const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
+            const int64_t o = obase + (p0 + v) * a + ai;
+            boxes_out[o] = make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh);
+            score_out[o] = sigmoidf_ref(t[4][v]) * (c > 0 ? sigmoidf_ref(best[v]) : 1.0f);
+            class_out[o] = (int64_t)bidx[v];
+        }
+    }
+}
+
+}  // namespace det
+
+using namespace det;
+
+extern "C" {
+
+int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
+                        float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
+                        float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
+                        int64_t* det_flat, float* det_boxes, float* det_scores, int32_t* det_count, void* stream) {
+    DET_CHECK_ARG(n >= 0 && s >= 1 && b >= 1 && c >= 1 && max_det >= 1, "bad size");
+    DET_CHECK_ARG(mode >= DET_NMS_AUTO && mode <= DET_NMS_OFFSET_TRICK, "unknown mode");
+    if (n == 0) return DET_OK;
+    DET_CHECK_ARG(head && priors && det_flat && det_count, "null pointer");
+    const int64_t P = (int64_t)s * s * b, PC = P * c, HS = (int64_t)s * s * (b * 5 + c);
+    if (P > kYoloMaxPred || PC > 4096 || HS > kYoloMaxHead || c > 1024) {
+        set_error("grid head too large for the fused kernel (limits: s*s*b <= 1024, s*s*b*c <= 4096, "
+                  "s*s*(5b+c) <= 6144); use det_dense_decode_level + det_nms_batched");
+        return DET_ERR_UNSUPPORTED;
+    }
+    if (!aligned16(head) || (dense_boxes && !aligned16(dense_boxes)) || (det_boxes && !aligned16(det_boxes))) {
+        set_error("head / box outputs must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    YoloParams prm;
+    prm.n = n; prm.s = s; prm.b = b; prm.c = c;
+    prm.stride_x = (float)((double)img_w / (double)s);
+    prm.stride_y = (float)((double)img_h / (double)s);
+    prm.img_w = (float)img_w; prm.img_h = (float)img_h;
+    prm.scale_clamp = scale_clamp; prm.score_thresh = score_thresh;
+    prm.thr_f = float_threshold_below(iou_threshold);
+    prm.clip = clip; prm.mode = mode; prm.max_det = max_det;
+    cudaStream_t st = as_stream(stream);
+    if (PC <= 1024)
+        return launch_yolo<1024>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+    if (PC <= 2048)
+        return launch_yolo<2048>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+    return launch_yolo<4096>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+}
+
+int det_dense_decode_level(const float* head, int n, int a, int c, int h, int w, int stride, const float* anchors_wh,
+                           float scale_clamp, float* boxes_out, float* score_out, int64_t* class_out,
+                           int64_t out_img_stride, int64_t out_offset, void* stream) {
+    DET_CHECK_ARG(n >= 0 && a >= 1 && c >= 0 && h >= 0 && w >= 0, "bad size");
+    const int64_t hw = (int64_t)h * w;
+    if (n == 0 || hw == 0) return DET_OK;
+    DET_CHECK_ARG(head && anchors_wh && boxes_out && score_out && class_out, "null pointer");
+    DET_CHECK_ARG(out_offset >= 0 && out_img_stride >= hw * a + out_offset, "output slot out of range");
+    DET_CHECK_ARG(n <= 65535, "n > 65535");
+    if (!aligned16(boxes_out)) {
+        set_error("boxes_out must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    auto awh = reinterpret_cast<const float2*>(anchors_wh);
+    auto bo = reinterpret_cast<float4*>(boxes_out);
+    cudaStream_t st = as_stream(stream);
+    if (hw % 4 == 0 && aligned16(head)) {
+        dim3 grid((unsigned)((hw / 4 + 255) / 256), (unsigned)n);
+        dense_decode_level_kernel<4><<<grid, 256, 0, st>>>(head, a, c, h, w, (float)stride, awh, scale_clamp, bo,
+                                                           score_out, class_out, out_img_stride, out_offset);
+    } else {
+        dim3 grid((unsigned)((hw + 255) / 256), (unsigned)n);
+        dense_decode_level_kernel<1><<<grid, 256, 0, st>>>(head, a, c, h, w, (float)stride, awh, scale_clamp, bo,
+                                                           score_out, class_out, out_img_stride, out_offset);
+    }
+    DET_LAUNCH_OK("dense_decode_level_kernel");
+    return DET_OK;
+}
+
+}  // extern "C"

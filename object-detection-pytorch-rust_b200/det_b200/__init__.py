@@ -10,8 +10,10 @@ from .structures import (Boxes, Instances, pairwise_iou, pairwise_ioa, pairwise_
 from .box_regression import Box2BoxTransform
 from .anchors import AnchorGenerator, generate_cell_anchors
 from .nms import batched_nms, nms, nms_images
+from .yolo import YoloGridHead, DenseAnchorHead
 
 __all__ = [
     "Boxes", "Instances", "pairwise_iou", "pairwise_ioa", "pairwise_intersection", "matched_boxlist_iou",
     "Box2BoxTransform", "AnchorGenerator", "generate_cell_anchors", "batched_nms", "nms", "nms_images",
+    "YoloGridHead", "DenseAnchorHead",
 ]

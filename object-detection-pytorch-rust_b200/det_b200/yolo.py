@@ -1,0 +1,127 @@
+"""YOLO-style grid / dense anchor heads: decode + score threshold + per-class NMS.
+
+The reference has no such head; the specification is this repository's own
+(oracle/ref_torch.py: yolo_decode, yolo_select_nms, dense_decode) -- parity is pinned by that oracle only.
+Arithmetic: det_yolo_decode_nms / det_dense_decode_level (csrc/yolo.cu) + det_nms_batched.
+"""
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+from .nms import nms_images, MODE_AUTO
+
+_DEFAULT_SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+class YoloGridHead:
+    """S x S x (B*5+C) channels-last grid head (YOLOv1 geometry, sigmoid/exp parameterisation)."""
+
+    def __init__(self, grid: int = 7, num_boxes: int = 2, num_classes: int = 20, image_size: Tuple[int, int] = (448, 448),
+                 priors: Optional[Sequence[Sequence[float]]] = None, scale_clamp: float = _DEFAULT_SCALE_CLAMP,
+                 clip: bool = True):
+        self.S, self.B, self.C = int(grid), int(num_boxes), int(num_classes)
+        self.image_size = (int(image_size[0]), int(image_size[1]))
+        if priors is None:  # one cell and three cells wide, square
+            cw, chh = self.image_size[1] / self.S, self.image_size[0] / self.S
+            priors = [[cw * (1 + 2 * i), chh * (1 + 2 * i)] for i in range(self.B)]
+        self.priors = torch.tensor(priors, dtype=torch.float32).reshape(self.B, 2)
+        self.scale_clamp = float(scale_clamp)
+        self.clip = bool(clip)
+        self._dev_priors = {}
+
+    @property
+    def num_predictors(self) -> int:
+        return self.S * self.S * self.B
+
+    def priors_on(self, device) -> torch.Tensor:
+        k = str(device)
+        if k not in self._dev_priors:
+            self._dev_priors[k] = self.priors.to(device).contiguous()
+        return self._dev_priors[k]
+
+    def detect(self, head: torch.Tensor, score_thresh: float = 0.25, iou_thresh: float = 0.5,
+               max_det: Optional[int] = None, return_dense: bool = False, mode: int = MODE_AUTO, out=None):
+        """head (N,S,S,B*5+C) -> dict(flat (N,K) int64 = predictor*C+class, boxes (N,K,4), scores (N,K),
+        count (N) int32) with K = max_det padding, by descending score; one launch, no host synchronisation.
+        With return_dense the decoded boxes/conf/scores of every predictor are written too.
+        `out` may carry a dict returned by an earlier call with the same shapes to reuse its buffers."""
+        N.require_cuda(head)
+        h = N.f32c(head)
+        n = h.shape[0]
+        assert tuple(h.shape[1:]) == (self.S, self.S, self.B * 5 + self.C), h.shape
+        P, C = self.num_predictors, self.C
+        max_det = P * C if max_det is None else int(max_det)
+        dev = h.device
+        if out is None:
+            out = {"flat": torch.empty((n, max_det), dtype=torch.int64, device=dev),
+                   "boxes": torch.empty((n, max_det, 4), dtype=torch.float32, device=dev),
+                   "scores": torch.empty((n, max_det), dtype=torch.float32, device=dev),
+                   "count": torch.empty((n,), dtype=torch.int32, device=dev), "num_classes": C}
+            if return_dense:
+                out.update(dense_boxes=torch.empty((n, P, 4), dtype=torch.float32, device=dev),
+                           dense_conf=torch.empty((n, P), dtype=torch.float32, device=dev),
+                           dense_scores=torch.empty((n, P, C), dtype=torch.float32, device=dev))
+        if n:
+            with torch.cuda.device(dev):
+                N.call("det_yolo_decode_nms", N.ptr(h), n, self.S, self.B, C, self.image_size[0], self.image_size[1],
+                       N.ptr(self.priors_on(dev)), self.scale_clamp, int(self.clip), float(score_thresh),
+                       float(iou_thresh), int(mode), N.ptr(out.get("dense_boxes")), N.ptr(out.get("dense_conf")),
+                       N.ptr(out.get("dense_scores")), max_det, N.ptr(out["flat"]), N.ptr(out["boxes"]),
+                       N.ptr(out["scores"]), N.ptr(out["count"]), N.stream())
+        return out
+
+    def decode(self, head: torch.Tensor):
+        """Dense decode only: boxes (N,P,4), conf (N,P), scores (N,P,C)."""
+        r = self.detect(head, score_thresh=float("inf"), max_det=1, return_dense=True)
+        return r["dense_boxes"], r["dense_conf"], r["dense_scores"]
+
+
+class DenseAnchorHead:
+    """Multi-level dense anchor head in the conv layout (N, A*(5+C), Hl, Wl) per level (YOLOv3-style decode)."""
+
+    def __init__(self, strides: Sequence[int], anchors_wh: Sequence[Sequence[Sequence[float]]], num_classes: int,
+                 scale_clamp: float = _DEFAULT_SCALE_CLAMP):
+        self.strides = [int(s) for s in strides]
+        self.anchors = [torch.tensor(a, dtype=torch.float32).reshape(-1, 2) for a in anchors_wh]
+        assert len(self.anchors) == len(self.strides)
+        self.C = int(num_classes)
+        self.scale_clamp = float(scale_clamp)
+        self._dev = {}
+
+    def _anchors_on(self, device):
+        k = str(device)
+        if k not in self._dev:
+            self._dev[k] = [a.to(device).contiguous() for a in self.anchors]
+        return self._dev[k]
+
+    def decode(self, heads: List[torch.Tensor], out=None):
+        """-> boxes (N,R,4), scores (N,R), classes (N,R) int64 with all levels concatenated, order (level,h,w,a)."""
+        N.require_cuda(*heads)
+        dev = heads[0].device
+        n = heads[0].shape[0]
+        sizes = [h.shape[2] * h.shape[3] * a.shape[0] for h, a in zip(heads, self.anchors)]
+        R = sum(sizes)
+        if out is None:
+            out = (torch.empty((n, R, 4), dtype=torch.float32, device=dev),
+                   torch.empty((n, R), dtype=torch.float32, device=dev),
+                   torch.empty((n, R), dtype=torch.int64, device=dev))
+        boxes, scores, classes = out
+        off = 0
+        with torch.cuda.device(dev):
+            for h, a, s, sz in zip(heads, self._anchors_on(dev), self.strides, sizes):
+                hc = N.f32c(h)
+                assert hc.shape[1] == a.shape[0] * (5 + self.C), hc.shape
+                N.call("det_dense_decode_level", N.ptr(hc), n, a.shape[0], self.C, hc.shape[2], hc.shape[3], s,
+                       N.ptr(a), self.scale_clamp, N.ptr(boxes), N.ptr(scores), N.ptr(classes), R, off, N.stream())
+                off += sz
+        return boxes, scores, classes
+
+    def detect(self, heads: List[torch.Tensor], iou_thresh: float = 0.5, max_det: Optional[int] = None,
+               mode: int = MODE_AUTO):
+        """decode + per-class NMS over all R boxes of every image: (boxes, scores, classes, keep (N,max_det),
+        keep_counts (N))."""
+        boxes, scores, classes = self.decode(heads)
+        keep, cnt = nms_images(boxes, scores, classes, None, iou_thresh, max_det, mode)
+        return boxes, scores, classes, keep, cnt

@@ -447,11 +447,11 @@ def roi_label_proposals(proposal_boxes: torch.Tensor, gt_boxes: torch.Tensor, gt
 # YOLO-grid superset (NO reference implementation -- this repository's own specification)
 # --------------------------------------------------------------------------------------
 def yolo_decode(head: torch.Tensor, num_boxes: int, num_classes: int, image_hw: Tuple[int, int],
-                priors: torch.Tensor, scale_clamp: float = DEFAULT_SCALE_CLAMP):
+                priors: torch.Tensor, scale_clamp: float = DEFAULT_SCALE_CLAMP, clip: bool = True):
     """head (N,S,S,B*5+C) channels-last: per cell B x (tx,ty,tw,th,tconf) then C class logits.
         cx=(sigmoid(tx)+col)*stride_x  cy=(sigmoid(ty)+row)*stride_y
         w =exp(min(tw,clamp))*prior_w[b]   h=exp(min(th,clamp))*prior_h[b]
-        box=(cx-0.5w, cy-0.5h, cx+0.5w, cy+0.5h)   conf=sigmoid(tconf)
+        box=(cx-0.5w, cy-0.5h, cx+0.5w, cy+0.5h), clamped to [0,W]x[0,H] when clip;   conf=sigmoid(tconf)
         score[b,c]=conf[b]*sigmoid(class_logit[c])
     Returns boxes (N,S*S*B,4), conf (N,S*S*B), scores (N,S*S*B,C); predictor order (row,col,b)."""
     n, s1, s2, ch = head.shape
@@ -467,6 +467,9 @@ def yolo_decode(head: torch.Tensor, num_boxes: int, num_classes: int, image_hw: 
     w = torch.exp(torch.clamp(t[..., 2], max=scale_clamp)) * priors[:, 0].view(1, 1, 1, B)
     h = torch.exp(torch.clamp(t[..., 3], max=scale_clamp)) * priors[:, 1].view(1, 1, 1, B)
     boxes = torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), dim=-1).reshape(n, -1, 4)
+    if clip:
+        boxes[..., 0::2].clamp_(min=0, max=W)
+        boxes[..., 1::2].clamp_(min=0, max=H)
     conf = torch.sigmoid(t[..., 4])
     pcls = torch.sigmoid(head[..., B * 5:].float())
     scores = (conf[..., None] * pcls[:, :, :, None, :]).reshape(n, -1, C)
@@ -485,6 +488,33 @@ def yolo_select_nms(boxes: torch.Tensor, scores: torch.Tensor, score_thresh: flo
     if max_det is not None:
         keep = keep[:max_det]
     return (pi[keep] * C + ci[keep]), cb[keep], cs[keep], ci[keep]
+
+
+def dense_decode(head: torch.Tensor, num_anchors: int, num_classes: int, stride: int, anchors_wh: torch.Tensor,
+                 scale_clamp: float = DEFAULT_SCALE_CLAMP):
+    """Dense anchor head of one level in the conv layout (N, A*(5+C), H, W) (own specification):
+        cx=(sigmoid(tx)+col)*stride  cy=(sigmoid(ty)+row)*stride  w=exp(min(tw,clamp))*aw  h=exp(min(th,clamp))*ah
+        class = argmax_c logit_c (first maximum), score = sigmoid(tobj) * sigmoid(max logit)
+    Returns boxes (N,HWA,4), score (N,HWA), class (N,HWA) int64, order (h,w,a)."""
+    n, _, H, W = head.shape
+    A, C = num_anchors, num_classes
+    t = head.view(n, A, 5 + C, H, W).float()
+    col = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    row = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1)
+    cx = (torch.sigmoid(t[:, :, 0]) + col) * float(stride)
+    cy = (torch.sigmoid(t[:, :, 1]) + row) * float(stride)
+    w = torch.exp(torch.clamp(t[:, :, 2], max=scale_clamp)) * anchors_wh[:, 0].view(1, A, 1, 1)
+    h = torch.exp(torch.clamp(t[:, :, 3], max=scale_clamp)) * anchors_wh[:, 1].view(1, A, 1, 1)
+    boxes = torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), dim=-1)  # N,A,H,W,4
+    obj = torch.sigmoid(t[:, :, 4])
+    if C > 0:
+        cmax, cidx = t[:, :, 5:].max(dim=2)
+        score = obj * torch.sigmoid(cmax)
+    else:
+        cidx = torch.zeros_like(obj, dtype=torch.int64)
+        score = obj * 1.0
+    boxes = boxes.permute(0, 2, 3, 1, 4).reshape(n, -1, 4)
+    return boxes, score.permute(0, 2, 3, 1).reshape(n, -1), cidx.permute(0, 2, 3, 1).reshape(n, -1)
 
 
 def yolo_grid_anchors(S: int, image_hw: Tuple[int, int], priors: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,116 @@
+"""GPU parity: YOLO-grid fused decode+NMS and dense-head decode vs the oracle (own spec; unpinned by reference)."""
+import pytest
+import torch
+
+from tests.util import gen, assert_boxes_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def det():
+    import det_b200
+    return det_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ref_torch
+    return ref_torch
+
+
+@pytest.mark.parametrize("n,seed,thr", [(16, 0, 0.25), (256, 1, 0.25), (256, 1, 0.2)])
+def test_yolo_grid_decode_and_nms(det, O, n, seed, thr):
+    """BASELINE.json configs[0]/[1]: 7x7x(2*5+20) head, 448x448, score thr 0.25, per-class NMS IoU 0.5."""
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    head = torch.randn(n, 7, 7, 30, generator=gen(seed))
+    r = yh.detect(head.cuda(), thr, 0.5, return_dense=True)
+    ob, oc, osc = O.yolo_decode(head, 2, 20, (448, 448), yh.priors)
+    gb, gc, gs = r["dense_boxes"].cpu(), r["dense_conf"].cpu(), r["dense_scores"].cpu()
+    # decode: fp32 within 1e-5 relative (transcendentals differ by a few ulp between CUDA and the CPU library)
+    assert_boxes_close(gb, ob, rtol=1e-5)
+    torch.testing.assert_close(gc, oc, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gs, osc, rtol=1e-5, atol=1e-6)
+    # NMS: bit-exact kept indices and counts on identical inputs (the GPU's own decoded values)
+    cnt = r["count"].cpu()
+    flat, kb, ks = r["flat"].cpu(), r["boxes"].cpu(), r["scores"].cpu()
+    modes = set()
+    for i in range(n):
+        wf, wb, ws, wc = O.yolo_select_nms(gb[i], gs[i], thr, 0.5)
+        modes.add(int((gs[i] > thr).sum()) <= 1000)
+        k = int(cnt[i])
+        assert k == wf.numel(), i
+        assert torch.equal(flat[i, :k], wf), i
+        assert torch.equal(kb[i, :k], wb) and torch.equal(ks[i, :k], ws)
+    if thr < 0.25:
+        assert modes == {True, False}  # both the offset-trick and the per-category branch were exercised
+
+
+def test_yolo_grid_end_to_end_indices_match_full_oracle(det, O):
+    """Kept (predictor,class) ids of the fused kernel vs the oracle run from the raw logits; the only admissible
+    differences are knife-edge score/IoU comparisons moved by the few-ulp transcendental differences."""
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    head = torch.randn(64, 7, 7, 30, generator=gen(5))
+    r = yh.detect(head.cuda(), 0.25, 0.5)
+    ob, oc, osc = O.yolo_decode(head, 2, 20, (448, 448), yh.priors)
+    same = 0
+    for i in range(64):
+        wf, _, _, _ = O.yolo_select_nms(ob[i], osc[i], 0.25, 0.5)
+        k = int(r["count"][i])
+        if k == wf.numel() and torch.equal(r["flat"][i, :k].cpu(), wf):
+            same += 1
+    assert same >= 62, same
+
+
+def test_yolo_no_clip_and_other_shapes(det, O):
+    yh = det.YoloGridHead(5, 3, 7, (320, 480), priors=[[30, 60], [100, 80], [200, 220]], clip=False)
+    head = torch.randn(9, 5, 5, 22, generator=gen(8)) * 1.5
+    r = yh.detect(head.cuda(), 0.1, 0.45, return_dense=True)
+    ob, oc, osc = O.yolo_decode(head, 3, 7, (320, 480), yh.priors, clip=False)
+    gb, gs = r["dense_boxes"].cpu(), r["dense_scores"].cpu()
+    assert_boxes_close(gb, ob, rtol=1e-5)
+    for i in range(9):
+        wf, wb, ws, wc = O.yolo_select_nms(gb[i], gs[i], 0.1, 0.45)
+        k = int(r["count"][i])
+        assert k == wf.numel() and torch.equal(r["flat"][i, :k].cpu(), wf)
+
+
+def test_yolo_max_det_and_empty(det, O):
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    head = torch.randn(4, 7, 7, 30, generator=gen(2))
+    r = yh.detect(head.cuda(), 0.25, 0.5, max_det=10, return_dense=True)
+    assert r["flat"].shape == (4, 10)
+    for i in range(4):
+        wf, _, _, _ = O.yolo_select_nms(r["dense_boxes"][i].cpu(), r["dense_scores"][i].cpu(), 0.25, 0.5, max_det=10)
+        assert int(r["count"][i]) == wf.numel() and torch.equal(r["flat"][i, :wf.numel()].cpu(), wf)
+    r = yh.detect(head.cuda(), 2.0, 0.5)  # nothing passes
+    assert r["count"].cpu().tolist() == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("hw", [(20, 20), (7, 9)])
+def test_dense_decode_level(det, O, hw):
+    A, C, stride = 3, 80, 32
+    wh = [[116.0, 90.0], [156.0, 198.0], [373.0, 326.0]]
+    head = torch.randn(3, A * (5 + C), hw[0], hw[1], generator=gen(4))
+    dh = det.DenseAnchorHead([stride], [wh], C)
+    gb, gs, gc = dh.decode([head.cuda()])
+    ob, os_, oc = O.dense_decode(head, A, C, stride, torch.tensor(wh))
+    assert torch.equal(gc.cpu(), oc)
+    assert_boxes_close(gb.cpu(), ob, rtol=1e-5)
+    torch.testing.assert_close(gs.cpu(), os_, rtol=1e-5, atol=1e-6)
+
+
+def test_dense_head_detect_three_levels(det, O):
+    """BASELINE.json configs[3] geometry at reduced spatial size: 3 levels, A=3, C=80, all boxes to NMS."""
+    C = 80
+    strides = [8, 16, 32]
+    wh = [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]]]
+    g = gen(3)
+    heads = [torch.randn(2, 3 * (5 + C), 160 // s, 160 // s, generator=g) for s in strides]
+    dh = det.DenseAnchorHead(strides, wh, C)
+    boxes, scores, classes, keep, cnt = dh.detect([h.cuda() for h in heads], 0.5)
+    R = boxes.shape[1]
+    assert R == 3 * (20 * 20 + 10 * 10 + 5 * 5)
+    for i in range(2):
+        want = O.batched_nms(boxes[i].cpu(), scores[i].cpu(), classes[i].cpu(), 0.5)
+        assert int(cnt[i]) == want.numel() and torch.equal(keep[i, :want.numel()].cpu(), want)

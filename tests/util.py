@@ -24,3 +24,15 @@ def ulp_diff(a, b):
     ai = torch.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
     bi = torch.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
     return (ai - bi).abs().max().item() if a.numel() else 0
+
+
+def assert_boxes_close(got, want, rtol=1e-5):
+    """fp32 boxes within `rtol` of the box's own scale (largest |coordinate| or side): corners are differences of a
+    centre and a half-size, so the error of the transcendental shows up relative to those, not to the corner."""
+    assert got.shape == want.shape
+    g, w = got.reshape(-1, 4).double(), want.reshape(-1, 4).double()
+    side = torch.maximum((w[:, 2] - w[:, 0]).abs(), (w[:, 3] - w[:, 1]).abs())
+    scale = torch.maximum(w.abs().amax(dim=1), side).clamp_min(1.0)
+    err = (g - w).abs().amax(dim=1)
+    bad = err > rtol * scale
+    assert not bool(bad.any()), f"{int(bad.sum())} boxes off by more than {rtol} rel; worst {float((err / scale).max()):.3e}"
