@@ -170,21 +170,24 @@ DET_API int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_sampl
  *      logits (n,r), deltas (n,r,4), labels (n,r) int8, matched_idx (n,r) int64, gt as above, anchors (r,4).
  *      loss_type 0 = smooth-L1(beta) (beta<1e-5 -> L1), 1 = GIoU.
  *      sums (8) fp32, caller-zeroed: [0]=objectness BCE sum, [1]=localisation sum, [2]=#pos, [3]=#neg.
- *      grad_logits (n,r) / grad_deltas (n,r,4): d(sum)/d(input) * grad_scale_{cls,loc}; NULL to skip backward.
+ *      grad_logits (n,r) / grad_deltas (n,r,4): d(sum)/d(input) * grad_scale_{cls,loc} [* upstream[0|1]];
+ *      NULL to skip backward.  upstream: device float[2] (d total / d cls_loss, d total / d loc_loss) or NULL (= 1),
+ *      read by the kernel so an autograd backward needs no host synchronisation.
  * ---------------------------------------------------------------------------------------------------------- */
 DET_API int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
                  const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r, float wx,
                  float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
-                 float grad_scale_cls, float grad_scale_loc, float* sums, float* grad_logits, float* grad_deltas,
-                 void* stream);
+                 float grad_scale_cls, float grad_scale_loc, const float* upstream, float* sums, float* grad_logits,
+                 float* grad_deltas, void* stream);
 
 /* YOLO-grid fused loss forward + backward (own specification: oracle/ref_torch.py yolo_loss).
  * head (n,s,s,b*5+c); labels (n,p) int8; matched_idx (n,p) int64; gt_classes (sum_g) int64.
- * sums (8): [0]=loc, [1]=obj, [2]=cls, [3]=#pos, [4]=#neg.  grad_head same shape as head (fully written). */
+ * sums (8): [0]=loc, [1]=obj, [2]=cls, [3]=#pos, [4]=#neg.  grad_head same shape as head (fully written) or NULL.
+ * grad = d(lambda_coord*loc + obj + cls)/d(head) * grad_scale [* upstream[0..2] per term], upstream device float[3] or NULL. */
 DET_API int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                   const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                   int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                  float* sums, float* grad_head, void* stream);
+                  const float* upstream, float* sums, float* grad_head, void* stream);
 
 #ifdef __cplusplus
 }

@@ -351,9 +351,13 @@ __global__ void __launch_bounds__(kLossThreads)
 rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ deltas, const int8_t* __restrict__ labels,
                 const int64_t* __restrict__ matched, const float4* __restrict__ gt, const int32_t* __restrict__ gt_off,
                 const float4* __restrict__ anchors, int64_t total, int64_t r, CodecW wt, float beta, float gs_cls,
-                float gs_loc, float* __restrict__ sums, float* __restrict__ grad_logits,
-                float4* __restrict__ grad_deltas) {
+                float gs_loc, const float* __restrict__ upstream, float* __restrict__ sums,
+                float* __restrict__ grad_logits, float4* __restrict__ grad_deltas) {
     __shared__ float s_part[4][kLossThreads / 32];
+    if (upstream) {
+        gs_cls *= upstream[0];
+        gs_loc *= upstream[1];
+    }
     float acc_cls = 0.f, acc_loc = 0.f;
     int npos = 0, nneg = 0;
     const int64_t nquads = (total + 3) >> 2;
@@ -441,9 +445,11 @@ struct YoloLossParams {
 __global__ void __launch_bounds__(128)
 yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labels, const int64_t* __restrict__ matched,
                  const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
-                 const float2* __restrict__ priors, YoloLossParams prm, float* __restrict__ sums,
-                 float* __restrict__ grad_head) {
+                 const float2* __restrict__ priors, YoloLossParams prm, const float* __restrict__ upstream,
+                 float* __restrict__ sums, float* __restrict__ grad_head) {
     __shared__ float s_part[5][4];
+    const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
+                up_cls = upstream ? upstream[2] : 1.f;
     const int S2 = prm.s * prm.s, B = prm.b, C = prm.c, ch = B * 5 + C;
     const int64_t cells = (int64_t)prm.n * S2;
     const int64_t ci = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -465,7 +471,7 @@ yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labe
                 const float wgt = (lab == 1) ? 1.0f : prm.lambda_noobj;
                 const float ls = fminf(tc, 0.f) - log1pf(expf(-fabsf(tc)));
                 a_obj += wgt * ((1.f - y) * tc - ls);
-                gc = wgt * (1.f / (1.f + expf(-tc)) - y) * prm.grad_scale;
+                gc = wgt * (1.f / (1.f + expf(-tc)) - y) * prm.grad_scale * up_obj;
                 a_pos += lab == 1;
                 a_neg += lab == 0;
             }
@@ -480,7 +486,7 @@ yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labe
                 const float sx = 1.f / (1.f + expf(-t[bi * 5 + 0])), sy = 1.f / (1.f + expf(-t[bi * 5 + 1]));
                 const float dx = sx - xs, dy = sy - ys, dw = t[bi * 5 + 2] - tws, dh = t[bi * 5 + 3] - ths;
                 a_loc += dx * dx + dy * dy + dw * dw + dh * dh;
-                const float k2 = 2.0f * prm.lambda_coord * prm.grad_scale;
+                const float k2 = 2.0f * prm.lambda_coord * prm.grad_scale * up_loc;
                 gx = k2 * dx * sx * (1.f - sx);
                 gy = k2 * dy * sy * (1.f - sy);
                 gw = k2 * dw;
@@ -491,7 +497,7 @@ yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labe
                     const float y = (k == cls) ? 1.f : 0.f;
                     const float ls = fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
                     a_cls += (1.f - y) * x - ls;
-                    if (g) g[B * 5 + k] += (1.f / (1.f + expf(-x)) - y) * prm.grad_scale;
+                    if (g) g[B * 5 + k] += (1.f / (1.f + expf(-x)) - y) * prm.grad_scale * up_cls;
                 }
             }
             if (g) {
@@ -559,7 +565,7 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
     MatchRule rule;
     int rc = fill_rule(rule, thresholds_host, labels_host, num_thresholds, allow_low_quality);
     if (rc != DET_OK) return rc;
-    if (allow_low_quality && (!workspace || workspace_bytes < det_match_workspace_bytes(n, r, sum_g))) {
+    if (allow_low_quality && sum_g > 0 && (!workspace || workspace_bytes < (int64_t)sizeof(float) * sum_g)) {
         set_error("workspace too small");
         return DET_ERR_WORKSPACE;
     }
@@ -630,8 +636,8 @@ int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, floa
 int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
                  const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r, float wx,
                  float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
-                 float grad_scale_cls, float grad_scale_loc, float* sums, float* grad_logits, float* grad_deltas,
-                 void* stream) {
+                 float grad_scale_cls, float grad_scale_loc, const float* upstream, float* sums, float* grad_logits,
+                 float* grad_deltas, void* stream) {
     (void)scale_clamp;
     DET_CHECK_ARG(n >= 0 && r >= 0, "negative size");
     if (loss_type != 0) {
@@ -654,7 +660,7 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
     rpn_loss_kernel<<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(
         logits, reinterpret_cast<const float4*>(deltas), labels, matched_idx, reinterpret_cast<const float4*>(gt_boxes),
         gt_offsets, reinterpret_cast<const float4*>(anchors), total, r, CodecW{wx, wy, ww, wh}, smooth_l1_beta,
-        grad_scale_cls, grad_scale_loc, sums, grad_logits, reinterpret_cast<float4*>(grad_deltas));
+        grad_scale_cls, grad_scale_loc, upstream, sums, grad_logits, reinterpret_cast<float4*>(grad_deltas));
     DET_LAUNCH_OK("rpn_loss_kernel");
     return DET_OK;
 }
@@ -662,7 +668,7 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
 int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                   const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                   int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                  float* sums, float* grad_head, void* stream) {
+                  const float* upstream, float* sums, float* grad_head, void* stream) {
     DET_CHECK_ARG(n >= 0 && s >= 1 && b >= 1 && c >= 0, "bad size");
     if (n == 0) return DET_OK;
     DET_CHECK_ARG(head && labels && matched_idx && gt_offsets && priors && sums, "null pointer");
@@ -678,7 +684,7 @@ int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matche
     const int64_t cells = (int64_t)n * s * s;
     yolo_loss_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, as_stream(stream)>>>(
         head, labels, matched_idx, reinterpret_cast<const float4*>(gt_boxes), gt_classes, gt_offsets,
-        reinterpret_cast<const float2*>(priors), prm, sums, grad_head);
+        reinterpret_cast<const float2*>(priors), prm, upstream, sums, grad_head);
     DET_LAUNCH_OK("yolo_loss_kernel");
     return DET_OK;
 }

@@ -1,0 +1,219 @@
+// RPN proposal selection for the whole batch in one call (subsystem 3, reference row a7).
+//
+// Replaces find_top_rpn_proposals (python/src/models/utils.py:9-109), which sorts every level fully, gathers, and then
+// loops over the images in Python with >= 4 host synchronisations each.  Here:
+//   keys (level | descending logit | anchor index) -> one segmented sort per image -> gather of the first pre_nms_topk
+//   of every level with the finite / clip / min-size filters fused in -> per-(image, level) greedy NMS (nms_core.cuh)
+//   -> re-key kept by (descending logit | index) -> sort -> emit the first post_nms_topk boxes + logits per image.
+// No host synchronisation; the "training diverged" condition (models/utils.py:79-84) is reported through a device flag.
+#include "nms_large.cuh"
+
+namespace det {
+
+constexpr int kMaxLevels = 16;
+struct LevelTable {
+    int num_levels;
+    int64_t off[kMaxLevels + 1];
+};
+
+__device__ __forceinline__ int level_of(const LevelTable& t, int64_t i) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxLevels; ++k)
+        if (k < t.num_levels && i >= t.off[k]) l = k;
+    return l;
+}
+
+static __global__ void __launch_bounds__(256)
+rpn_keys_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LargeImg* info,
+                uint64_t* __restrict__ keys) {
+    const int img = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= mp) return;
+    if (i == 0) {
+        LargeImg li;
+        li.cnt = (int32_t)r; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0; li.nsurv = 0; li.pad = 0;
+        info[img] = li;
+    }
+    uint64_t k = kSentinelKey;
+    if (i < r) k = KLL::make((uint32_t)level_of(lt, i), logits[(int64_t)img * r + i], (uint32_t)i);
+    keys[(int64_t)img * mp + i] = k;
+}
+
+__device__ __forceinline__ float4 clip_box(float4 b, float w, float h) {
+    // Boxes.clip, structures/boxes.py:62-65 (inputs are finite here)
+    b.x = fminf(fmaxf(b.x, 0.f), w); b.z = fminf(fmaxf(b.z, 0.f), w);
+    b.y = fminf(fmaxf(b.y, 0.f), h); b.w = fminf(fmaxf(b.w, 0.f), h);
+    return b;
+}
+
+static __global__ void __launch_bounds__(256)
+rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ logits, int64_t r, int64_t mp,
+                  LevelTable lt, int64_t pre_nms_topk, const int32_t* __restrict__ image_sizes, float min_size,
+                  LargeImg* info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
+                  float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* ctr, int4* seg_small, int4* seg_large,
+                  int32_t* __restrict__ nonfinite_flag) {
+    const int img = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool survivor = false;
+    if (p < r) {
+        const uint64_t key = keys[(int64_t)img * mp + p];
+        const int64_t i = KLL::idx(key);
+        const int l = (int)KLL::seg(key);
+        const int64_t rank = p - lt.off[l];  // a level's keys occupy the same slot range after the sort
+        const int64_t take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
+        uint8_t st = 1;
+        if (rank < take) {
+            float4 b = boxes[(int64_t)img * r + i];
+            const float sc = logits[(int64_t)img * r + i];
+            const bool fin = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w) && isfinite(sc);
+            if (!fin) {
+                if (nonfinite_flag) *nonfinite_flag = 1;
+            } else {
+                b = clip_box(b, (float)image_sizes[2 * img + 1], (float)image_sizes[2 * img]);
+                if ((b.z - b.x) > min_size && (b.w - b.y) > min_size) {  // Boxes.nonempty, boxes.py:67-80
+                    st = 0;
+                    survivor = true;
+                    sbox[(int64_t)img * mp + p] = b;
+                    sarea[(int64_t)img * mp + p] = box_area(b);
+                }
+            }
+            if (rank == 0) push_segment(img, (int)p, (int)(p + take), ctr, seg_small, seg_large);
+        }
+        state[(int64_t)img * mp + p] = st;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, survivor);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&info[img].nsurv, __popc(bal));
+}
+
+// images with <= 1000 surviving boxes take torchvision's coordinate-offset branch: box + level * (max + 1) in fp32
+static __global__ void __launch_bounds__(256)
+rpn_offset_kernel(int64_t r, int64_t mp, const LargeImg* __restrict__ info, const uint64_t* __restrict__ keys,
+                  float4* __restrict__ sbox, float* __restrict__ sarea, const uint8_t* __restrict__ state) {
+    __shared__ float s_max[8];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int ns = info[img].nsurv;
+    if (ns == 0 || ns > 1000) return;
+    float mx = -INFINITY;
+    for (int64_t p = tid; p < r; p += 256)
+        if (state[(int64_t)img * mp + p] == 0) {
+            const float4 b = sbox[(int64_t)img * mp + p];
+            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+        }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+    __syncthreads();
+    mx = s_max[0];
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_max[w]);
+    const float span = mx + 1.0f;
+    for (int64_t p = tid; p < r; p += 256)
+        if (state[(int64_t)img * mp + p] == 0) {
+            const float off = (float)KLL::seg(keys[(int64_t)img * mp + p]) * span;
+            float4 b = sbox[(int64_t)img * mp + p];
+            b.x += off; b.y += off; b.z += off; b.w += off;
+            sbox[(int64_t)img * mp + p] = b;
+            sarea[(int64_t)img * mp + p] = box_area(b);
+        }
+}
+
+static __global__ void __launch_bounds__(256)
+rpn_emit_kernel(const float4* __restrict__ boxes, const float* __restrict__ logits, int64_t r, int64_t mp,
+                const LargeImg* __restrict__ info, const uint64_t* __restrict__ keys,
+                const int32_t* __restrict__ image_sizes, int64_t post_nms_topk, float4* __restrict__ out_boxes,
+                float* __restrict__ out_logits, int32_t* __restrict__ out_counts) {
+    const int img = blockIdx.y;
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t nout = min((int64_t)info[img].nkept, post_nms_topk);
+    if (j < nout) {
+        const int64_t i = KLL::idx(keys[(int64_t)img * mp + j]);
+        out_boxes[(int64_t)img * post_nms_topk + j] =
+            clip_box(boxes[(int64_t)img * r + i], (float)image_sizes[2 * img + 1], (float)image_sizes[2 * img]);
+        out_logits[(int64_t)img * post_nms_topk + j] = logits[(int64_t)img * r + i];
+    }
+    if (j == 0) out_counts[img] = (int32_t)nout;
+}
+
+}  // namespace det
+
+using namespace det;
+
+extern "C" {
+
+int64_t det_rpn_proposals_workspace_bytes(int n, int64_t r) {
+    if (n <= 0 || r <= 0) return 256;
+    return LargeLayout(n, r).total;
+}
+
+int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r, const int64_t* level_sizes_host,
+                      int num_levels, const int32_t* image_sizes, double nms_thresh, int64_t pre_nms_topk,
+                      int64_t post_nms_topk, float min_box_size, float* out_boxes, float* out_logits,
+                      int32_t* out_counts, int32_t* nonfinite_flag, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+    DET_CHECK_ARG(n >= 0 && r >= 0 && pre_nms_topk >= 0 && post_nms_topk >= 0, "negative size");
+    DET_CHECK_ARG(num_levels >= 1 && num_levels <= kMaxLevels && level_sizes_host, "1..16 levels");
+    if (n == 0) return DET_OK;
+    DET_CHECK_ARG(out_counts, "null output");
+    cudaStream_t st = as_stream(stream);
+    if (r == 0 || post_nms_topk == 0 || pre_nms_topk == 0) {
+        cudaError_t e = cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * (size_t)n, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        return DET_OK;
+    }
+    DET_CHECK_ARG(boxes && logits && image_sizes && out_boxes && out_logits, "null pointer");
+    DET_CHECK_ARG(n <= 65535, "n > 65535");
+    if (r > (1 << kLargeIdxBits) - 1) {
+        set_error("r %lld exceeds the limit 131071 anchors per image", (long long)r);
+        return DET_ERR_UNSUPPORTED;
+    }
+    LevelTable lt;
+    lt.num_levels = num_levels;
+    int64_t acc = 0;
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        lt.off[l] = acc;
+        if (l < num_levels) {
+            DET_CHECK_ARG(level_sizes_host[l] >= 0, "negative level size");
+            acc += level_sizes_host[l];
+        }
+    }
+    DET_CHECK_ARG(acc == r, "level sizes must sum to r");
+    if (!aligned16(boxes) || !aligned16(out_boxes) || !aligned16(workspace)) {
+        set_error("boxes/out_boxes/workspace must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    LargeLayout lay(n, r);
+    if (!workspace || workspace_bytes < lay.total) {
+        set_error("workspace too small: need %lld bytes", (long long)lay.total);
+        return DET_ERR_WORKSPACE;
+    }
+    LargeWs ws(lay, workspace);
+    const int64_t mp = lay.mp;
+    const float thr_f = float_threshold_below(nms_thresh);
+    auto b4 = reinterpret_cast<const float4*>(boxes);
+    cudaError_t e = cudaMemsetAsync(ws.ctr, 0, 64, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    dim3 grid_e((unsigned)((mp + 255) / 256), (unsigned)n);
+    rpn_keys_kernel<<<grid_e, 256, 0, st>>>(logits, r, mp, lt, ws.info, ws.keys_a);
+    DET_LAUNCH_OK("rpn_keys_kernel");
+    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st);
+    uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
+    DET_LAUNCH_OK("sort_rows");
+    rpn_gather_kernel<<<grid_e, 256, 0, st>>>(b4, logits, r, mp, lt, pre_nms_topk, image_sizes, min_box_size, ws.info,
+                                              sorted, ws.sbox, ws.sarea, ws.state, ws.ctr, ws.seg_small, ws.seg_large,
+                                              nonfinite_flag);
+    DET_LAUNCH_OK("rpn_gather_kernel");
+    rpn_offset_kernel<<<n, 256, 0, st>>>(r, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state);
+    DET_LAUNCH_OK("rpn_offset_kernel");
+    int rc = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
+    if (rc != DET_OK) return rc;
+    large_rekey_kernel<<<grid_e, 256, 0, st>>>(mp, ws.info, sorted, ws.state, other);
+    DET_LAUNCH_OK("large_rekey_kernel");
+    uint64_t* final_keys = sort_rows(other, sorted, n, mp, st);
+    DET_LAUNCH_OK("sort_rows(2)");
+    dim3 grid_o((unsigned)((min(post_nms_topk, r) + 255) / 256), (unsigned)n);
+    rpn_emit_kernel<<<grid_o, 256, 0, st>>>(b4, logits, r, mp, ws.info, final_keys, image_sizes, post_nms_topk,
+                                            reinterpret_cast<float4*>(out_boxes), out_logits, out_counts);
+    DET_LAUNCH_OK("rpn_emit_kernel");
+    return DET_OK;
+}
+
+}  // extern "C"

@@ -44,9 +44,9 @@ PROTOTYPES = {
     "det_match_quality": (c_i, [c_p, c_l, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "det_subsample_labels": (c_i, [c_p, c_i, c_l, c_i, c_f, c_u64, c_p]),
     "det_rpn_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f,
-                           c_p, c_p, c_p, c_p]),
+                           c_p, c_p, c_p, c_p, c_p]),
     "det_yolo_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
-                            c_p]),
+                            c_p, c_p]),
 }
 
 _lib = None

@@ -1,0 +1,47 @@
+"""Data-parallel plumbing: the path shards by image; the only collective is one SUM all-reduce of
+the 8-float loss/count vector per training step (NCCL over NVLink on GPUs, gloo in the CPU tests).  Inference
+(decode + NMS) needs no collective."""
+import os
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from torchrun's environment; initialises the process group when world_size > 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, **kw)
+    return rank, world, local
+
+
+def shard_range(num_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous batch shard [lo, hi) of rank `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(num_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sums_(sums: torch.Tensor) -> torch.Tensor:
+    """In-place SUM all-reduce of the loss/count vector over all ranks (no-op for a single process).
+    The local sums must already be scaled by the GLOBAL normaliser (pass num_images_global to the loss)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    return sums
+
+
+def global_num_images(local_n: int, device=None) -> int:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([local_n], dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        return int(t.item())
+    return local_n

@@ -1,0 +1,103 @@
+"""IoU -> (matched gt index, label) assignment -- drop-in for ``Matcher``
+(reference python/src/models/components/matcher.py:8-120).  Arithmetic: det_match_quality (materialised matrix) and
+det_match_anchors (fused IoU + matching for a whole batch, csrc/assign_loss.cu)."""
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def _rule_arrays(thresholds: Sequence[float], labels: Sequence[int]):
+    thr = (ctypes.c_float * max(len(thresholds), 1))(*[float(t) for t in thresholds])
+    lab = (ctypes.c_int32 * len(labels))(*[int(l) for l in labels])
+    return thr, lab
+
+
+class Matcher:
+    def __init__(self, thresholds: List[float], labels: List[int], allow_low_quality_matches: bool = True):
+        thresholds = list(thresholds)
+        assert thresholds[0] > 0
+        bounds = [-float("inf")] + thresholds + [float("inf")]
+        assert all(lo <= hi for lo, hi in zip(bounds[:-1], bounds[1:]))
+        assert all(l in [-1, 0, 1] for l in labels)
+        assert len(labels) == len(bounds) - 1
+        self.thresholds = bounds            # same attribute layout as the reference (with the +-inf sentinels)
+        self.labels = list(labels)
+        self.allow_low_quality_matches = allow_low_quality_matches
+        self._inner = thresholds            # finite thresholds handed to the kernels
+
+    @classmethod
+    def build(cls, conf):
+        return cls(thresholds=conf.thresholds, labels=conf.labels,
+                   allow_low_quality_matches=conf.allow_low_quality_matches)
+
+    def __call__(self, match_quality_matrix: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(G,R) quality matrix -> (int64[R] matched gt index, int8[R] label in {-1,0,1})."""
+        q = match_quality_matrix
+        assert q.dim() == 2
+        N.require_cuda(q)
+        q = N.f32c(q)
+        g, r = q.shape
+        matches = torch.empty((r,), dtype=torch.int64, device=q.device)
+        labels = torch.empty((r,), dtype=torch.int8, device=q.device)
+        if r == 0:
+            return matches, labels
+        flag = torch.zeros(1, dtype=torch.int32, device=q.device)
+        ws = torch.empty((max(g, 1),), dtype=torch.float32, device=q.device)
+        thr, lab = _rule_arrays(self._inner, self.labels)
+        with torch.cuda.device(q.device):
+            N.call("det_match_quality", N.ptr(q), g, r, thr, lab, len(self._inner),
+                   int(self.allow_low_quality_matches), N.ptr(matches), N.ptr(labels), N.ptr(flag), N.ptr(ws),
+                   ws.numel() * 4, N.stream())
+        assert flag.item() == 0  # reference: assert torch.all(match_quality_matrix >= 0)
+        return matches, labels
+
+    def match_boxes(self, gt_boxes: Sequence[torch.Tensor], anchors: torch.Tensor, return_iou: bool = False):
+        """Fused batch form: per image IoU(gt_i, anchors) + matching without materialising the matrices.
+        gt_boxes: list of (G_i,4) tensors; anchors (R,4).  Returns matched (N,R) int64, labels (N,R) int8
+        [, matched IoU (N,R)], and the packed gt table (sum_G,4) + int32 offsets (N+1) used by the loss kernel."""
+        N.require_cuda(anchors, *gt_boxes)
+        dev = anchors.device
+        a = N.f32c(anchors)
+        n, r = len(gt_boxes), a.shape[0]
+        sizes = [int(g.shape[0]) for g in gt_boxes]
+        table = N.f32c(torch.cat([g.reshape(-1, 4) for g in gt_boxes], dim=0)) if n else a.new_zeros((0, 4))
+        off_host = [0]
+        for s in sizes:
+            off_host.append(off_host[-1] + s)
+        offsets = torch.tensor(off_host, dtype=torch.int32).to(dev, non_blocking=True)
+        return self.match_packed(table, offsets, n, a, return_iou) + (table, offsets)
+
+    def match_packed(self, table: torch.Tensor, offsets: torch.Tensor, n: int, anchors: torch.Tensor,
+                     return_iou: bool = False):
+        """As match_boxes, for an already packed gt table (sum_G,4) + device int32 offsets (n+1)."""
+        dev = anchors.device
+        r, sum_g = anchors.shape[0], table.shape[0]
+        matched = torch.empty((n, r), dtype=torch.int64, device=dev)
+        labels = torch.empty((n, r), dtype=torch.int8, device=dev)
+        miou = torch.empty((n, r), dtype=torch.float32, device=dev) if return_iou else None
+        if n and r:
+            ws = torch.empty((max(sum_g, 1),), dtype=torch.float32, device=dev)
+            thr, lab = _rule_arrays(self._inner, self.labels)
+            with torch.cuda.device(dev):
+                N.call("det_match_anchors", N.ptr(table), N.ptr(offsets), n, sum_g, N.ptr(anchors), r, thr, lab,
+                       len(self._inner), int(self.allow_low_quality_matches), N.ptr(matched), N.ptr(labels),
+                       N.ptr(miou), N.ptr(ws), ws.numel() * 4, N.stream())
+        return (matched, labels, miou) if return_iou else (matched, labels)
+
+
+def subsample_labels_(labels: torch.Tensor, num_samples: int, positive_fraction: float, seed: int) -> torch.Tensor:
+    """In-place device fg/bg subsample of (N,R) int8 labels in {-1,0,1}: keeps min(#pos, int(S*f)) positives and
+    min(#neg, S-#pos) negatives per image, chosen uniformly at random (counter-based hash of seed,image,anchor);
+    everything else becomes -1.  Same counts/distribution as reference subsample_labels + _subsample_labels
+    (python/src/utils.py:34, models/rpn.py:108); the random stream necessarily differs from torch.randperm."""
+    N.require_cuda(labels)
+    assert labels.dtype == torch.int8 and labels.is_contiguous() and labels.dim() == 2
+    n, r = labels.shape
+    if n and r:
+        with torch.cuda.device(labels.device):
+            N.call("det_subsample_labels", N.ptr(labels), n, r, int(num_samples), float(positive_fraction),
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, N.stream())
+    return labels

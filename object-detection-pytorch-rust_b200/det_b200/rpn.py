@@ -1,0 +1,288 @@
+"""RPN hot path -- drop-in for the post-head methods of ``RegionProposalNetwork``
+(reference python/src/models/rpn.py:17-357): layout change + decode, label_and_sample_anchors, losses,
+predict_proposals.  The conv head itself is out of scope: ``forward`` takes the head's
+NCHW outputs.  Two API levels:
+  * the reference's own signatures (lists of per-level / per-image tensors, ``Boxes``, ``Instances``);
+  * batched zero-synchronisation forms (``decode_heads``, ``assign``, ``fused_losses``) the former are built on.
+"""
+import math
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _native as N
+from .anchors import AnchorGenerator
+from .box_regression import Box2BoxTransform, _DEFAULT_SCALE_CLAMP
+from .matcher import Matcher, subsample_labels_
+from .proposals import find_top_rpn_proposals, rpn_proposals_batched
+from .structures import Boxes, Instances
+
+
+class Assignment:
+    """Result of the batched target assignment: labels (N,R) int8, matched (N,R) int64 indices into each image's own
+    gt boxes, the packed gt table (sum_G,4) and its int32 offsets (N+1)."""
+
+    def __init__(self, labels, matched, gt_table, gt_offsets):
+        self.labels, self.matched, self.gt_table, self.gt_offsets = labels, matched, gt_table, gt_offsets
+
+
+class _FusedRPNLoss(torch.autograd.Function):
+    """Forward: one pass that reduces the BCE / L1 sums (no gradient stores).  Backward: the same kernel with the
+    upstream gradients read on the device, writing grad_logits / grad_deltas.  `fused_losses(..., with_grads=True)`
+    is the single-launch fwd+bwd form used when the caller drives backward by hand."""
+
+    @staticmethod
+    def forward(ctx, logits, deltas, owner, asg, n_norm):
+        sums = owner._run_loss(logits, deltas, asg, n_norm, None, None, None)
+        ctx.owner, ctx.asg, ctx.n_norm = owner, asg, n_norm
+        ctx.save_for_backward(logits, deltas)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        logits, deltas = ctx.saved_tensors
+        up = grad_sums[:2].contiguous().float()
+        gl = torch.empty_like(logits)
+        gd = torch.empty_like(deltas)
+        scratch = ctx.owner._run_loss(logits, deltas, ctx.asg, ctx.n_norm, up, gl, gd)
+        del scratch
+        return gl, gd, None, None, None
+
+
+class RegionProposalNetwork:
+    def __init__(self, strides: Sequence[int], anchor_sizes=((32,), (64,), (128,), (256,), (512,)),
+                 aspect_ratios=((0.5, 1.0, 2.0),), anchor_offset: float = 0.0,
+                 iou_thresholds=(0.3, 0.7), iou_labels=(0, -1, 1), allow_low_quality_matches: bool = True,
+                 box2box_weights=(1.0, 1.0, 1.0, 1.0), scale_clamp: float = _DEFAULT_SCALE_CLAMP,
+                 batch_size_per_image: int = 256, positive_fraction: float = 0.5,
+                 pre_nms_topk: Tuple[int, int] = (12000, 6000), post_nms_topk: Tuple[int, int] = (2000, 1000),
+                 nms_thresh: float = 0.7, min_box_size: float = 0.0, loss_weight=(1.0, 1.0),
+                 box_reg_loss_type: str = "smooth_l1", smooth_l1_beta: float = 0.0, head=None):
+        """Defaults = reference python/src/config/rpn.py:113-130 (pre/post_nms_topk are indexed by `training`)."""
+        self.anchor_generator = AnchorGenerator(list(strides), anchor_sizes, aspect_ratios, anchor_offset)
+        self.anchor_matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches)
+        self.box2box_transform = Box2BoxTransform(box2box_weights, scale_clamp)
+        self.batch_size_per_image = batch_size_per_image
+        self.positive_fraction = positive_fraction
+        self.pre_nms_topk = pre_nms_topk
+        self.post_nms_topk = post_nms_topk
+        self.nms_thresh = nms_thresh
+        self.min_box_size = float(min_box_size)
+        self.loss_weight = loss_weight
+        self.box_reg_loss_type = box_reg_loss_type
+        self.smooth_l1_beta = smooth_l1_beta
+        self.head = head
+        self.training = False
+        self._sample_seed = 0
+
+    @classmethod
+    def build(cls, conf, input_shapes):
+        strides = [input_shapes[f].stride for f in conf.in_features]
+        return cls(strides, conf.anchor_generator.sizes, conf.anchor_generator.aspect_ratios,
+                   conf.anchor_generator.offset, conf.anchor_matcher.thresholds, conf.anchor_matcher.labels,
+                   conf.anchor_matcher.allow_low_quality_matches, conf.box2box_transform.weights,
+                   conf.box2box_transform.scale_clamp, conf.batch_size_per_image, conf.positive_fraction,
+                   conf.pre_nms_topk, conf.post_nms_topk, conf.nms_thresh, conf.min_box_size, conf.loss_weight,
+                   conf.box_reg_loss_type, conf.smooth_l1_beta)
+
+    def train(self, mode: bool = True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    # ------------------------------------------------------------------ decode
+    def decode_heads(self, pred_objectness: List[torch.Tensor], pred_deltas: List[torch.Tensor]):
+        """Conv-layout head outputs, per level (N,A,Hi,Wi) and (N,A*4,Hi,Wi) -> logits (N,R), proposals (N,R,4) with all
+        levels concatenated in (level,h,w,a) order; anchors are synthesised in the kernel (rpn.py:270-284 + :330-348)."""
+        N.require_cuda(*pred_objectness, *pred_deltas)
+        dev = pred_objectness[0].device
+        n = pred_objectness[0].shape[0]
+        cells = self.anchor_generator.device_cell_anchors(dev)
+        sizes = [o.shape[1] * o.shape[2] * o.shape[3] for o in pred_objectness]
+        R = sum(sizes)
+        logits = torch.empty((n, R), dtype=torch.float32, device=dev)
+        boxes = torch.empty((n, R, 4), dtype=torch.float32, device=dev)
+        off = 0
+        w = self.box2box_transform.weights
+        with torch.cuda.device(dev):
+            for o, d, cell, stride, sz in zip(pred_objectness, pred_deltas, cells, self.anchor_generator.strides, sizes):
+                oc, dc = N.f32c(o), N.f32c(d)
+                a, h, wd = oc.shape[1], oc.shape[2], oc.shape[3]
+                assert dc.shape[1] == a * 4 and a == cell.shape[0]
+                N.call("det_rpn_decode_level", N.ptr(oc), N.ptr(dc), n, a, h, wd, int(stride),
+                       float(self.anchor_generator.offset), N.ptr(cell), *w, self.box2box_transform.scale_clamp,
+                       N.ptr(logits), N.ptr(boxes), R, off, N.stream())
+                off += sz
+        return logits, boxes, sizes
+
+    def _decode_proposals(self, anchors: List[Boxes], pred_anchor_deltas: List[torch.Tensor]) -> List[torch.Tensor]:
+        """Reference signature (rpn.py:330): per level (N,HiWiA,4) deltas + anchors -> (N,HiWiA,4) proposals."""
+        out = []
+        for a, d in zip(anchors, pred_anchor_deltas):
+            n = d.shape[0]
+            at = a.tensor if isinstance(a, Boxes) else a
+            rep = at.unsqueeze(0).expand(n, -1, -1).reshape(-1, 4)
+            out.append(self.box2box_transform.apply_deltas(d.reshape(-1, 4), rep).view(n, -1, 4))
+        return out
+
+    # ------------------------------------------------------------------ assignment
+    def assign(self, anchors: torch.Tensor, gt_boxes: List[torch.Tensor], sample: bool = True,
+               seed: Optional[int] = None) -> Assignment:
+        """Batched IoU -> Matcher -> (optional) device fg/bg subsample; no (G,R) matrix, no per-image loop."""
+        gts = [g.tensor if isinstance(g, Boxes) else g for g in gt_boxes]
+        matched, labels, table, offsets = self.anchor_matcher.match_boxes(gts, anchors)
+        if sample:
+            if seed is None:
+                self._sample_seed += 1
+                seed = self._sample_seed
+            subsample_labels_(labels, self.batch_size_per_image, self.positive_fraction, seed)
+        return Assignment(labels, matched, table, offsets)
+
+    @torch.no_grad()
+    def label_and_sample_anchors(self, anchors: List[Boxes], gt_instances: List[Instances]):
+        """Reference signature (rpn.py:132): -> (list of int8[R] labels, list of (R,4) matched gt boxes)."""
+        at = Boxes.cat(anchors).tensor
+        gt_boxes = [x.gt_boxes for x in gt_instances]
+        asg = self.assign(at, gt_boxes, sample=True)
+        gt_labels, matched_gt = [], []
+        for i, g in enumerate(gt_boxes):
+            gt_labels.append(asg.labels[i])
+            gt_t = g.tensor if isinstance(g, Boxes) else g
+            matched_gt.append(torch.zeros_like(at) if len(gt_t) == 0 else gt_t[asg.matched[i]])
+        return gt_labels, matched_gt
+
+    # ------------------------------------------------------------------ losses
+    def _run_loss(self, logits, deltas, asg: Assignment, n_norm, upstream, grad_logits, grad_deltas):
+        n, r = logits.shape
+        dev = logits.device
+        sums = torch.zeros((8,), dtype=torch.float32, device=dev)
+        if self.box_reg_loss_type not in ("smooth_l1", "giou"):
+            raise ValueError(f"Invalid dense box regression loss type '{self.box_reg_loss_type}'")
+        norm = float(self.batch_size_per_image * n_norm)
+        w_cls = float(getattr(self.loss_weight, "cls_loss", self.loss_weight[0] if isinstance(self.loss_weight, (tuple, list)) else 1.0))
+        w_loc = float(getattr(self.loss_weight, "loc_loss", self.loss_weight[1] if isinstance(self.loss_weight, (tuple, list)) else 1.0))
+        w = self.box2box_transform.weights
+        with torch.cuda.device(dev):
+            N.call("det_rpn_loss", N.ptr(logits), N.ptr(deltas), N.ptr(asg.labels), N.ptr(asg.matched),
+                   N.ptr(asg.gt_table), N.ptr(asg.gt_offsets), N.ptr(self._anchors_for_loss), n, r, *w,
+                   self.box2box_transform.scale_clamp, 0 if self.box_reg_loss_type == "smooth_l1" else 1,
+                   float(self.smooth_l1_beta), w_cls / norm, w_loc / norm, N.ptr(upstream), N.ptr(sums),
+                   N.ptr(grad_logits), N.ptr(grad_deltas), N.stream())
+        # [0] cls sum, [1] loc sum -> weighted, normalised losses in place (rpn.py:238-243)
+        sums[0] *= w_cls / norm
+        sums[1] *= w_loc / norm
+        return sums
+
+    def fused_losses(self, anchors: torch.Tensor, logits: torch.Tensor, deltas: torch.Tensor, asg: Assignment,
+                     num_images_global: Optional[int] = None, with_grads: bool = False):
+        """logits (N,R), deltas (N,R,4).  Returns {"cls_loss","loc_loss","num_pos_anchors","num_neg_anchors"} (device
+        scalars, autograd-connected to logits/deltas) -- or, with_grads=True, additionally grad_logits/grad_deltas from
+        the SAME launch (fused forward+backward, detached).  `num_images_global` = batch size over all data-parallel
+        ranks (normaliser = batch_size_per_image * that, rpn.py:238)."""
+        N.require_cuda(anchors, logits, deltas)
+        self._anchors_for_loss = N.f32c(anchors)
+        lg, dl = logits.contiguous(), deltas.contiguous()
+        n_norm = lg.shape[0] if num_images_global is None else int(num_images_global)
+        if with_grads:
+            gl, gd = torch.empty_like(lg), torch.empty_like(dl)
+            sums = self._run_loss(lg.detach(), dl.detach(), asg, n_norm, None, gl, gd)
+        else:
+            sums = _FusedRPNLoss.apply(lg, dl, self, asg, n_norm)
+        out = {"cls_loss": sums[0], "loc_loss": sums[1], "num_pos_anchors": sums[2].detach(),
+               "num_neg_anchors": sums[3].detach(), "sums": sums}
+        if with_grads:
+            out["grad_logits"], out["grad_deltas"] = gl, gd
+        return out
+
+    def losses(self, anchors: List[Boxes], pred_objectness_logits: List[torch.Tensor], gt_labels: List[torch.Tensor],
+               pred_anchor_deltas: List[torch.Tensor], gt_boxes: List[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Reference signature (rpn.py:187): per-level logits (N,HiWiA) / deltas (N,HiWiA,4), per-image labels int8[R]
+        and matched gt boxes (R,4) -> {"cls_loss", "loc_loss"}."""
+        at = Boxes.cat(anchors).tensor
+        labels = torch.stack(gt_labels).contiguous()
+        n, r = labels.shape
+        logits = pred_objectness_logits[0] if len(pred_objectness_logits) == 1 else torch.cat(pred_objectness_logits, 1)
+        deltas = pred_anchor_deltas[0] if len(pred_anchor_deltas) == 1 else torch.cat(pred_anchor_deltas, 1)
+        table = N.f32c(torch.stack(gt_boxes).reshape(-1, 4))      # matched boxes as an (N*R,4) table ...
+        matched = torch.arange(r, device=at.device, dtype=torch.int64).repeat(n, 1)  # ... indexed by the anchor id
+        offsets = (torch.arange(n + 1, device=at.device, dtype=torch.int64) * r).to(torch.int32)
+        res = self.fused_losses(at, logits, deltas, Assignment(labels, matched, table, offsets))
+        return {"cls_loss": res["cls_loss"], "loc_loss": res["loc_loss"]}
+
+    # ------------------------------------------------------------------ proposals
+    def predict_proposals(self, anchors: List[Boxes], pred_objectness_logits: List[torch.Tensor],
+                          pred_anchor_deltas: List[torch.Tensor], image_sizes: List[Tuple[int, int]]):
+        """Reference signature (rpn.py:299)."""
+        with torch.no_grad():
+            props = self._decode_proposals(anchors, pred_anchor_deltas)
+            return find_top_rpn_proposals(props, pred_objectness_logits, image_sizes, self.nms_thresh,
+                                          self.pre_nms_topk[self.training], self.post_nms_topk[self.training],
+                                          self.min_box_size, self.training)
+
+    @torch.no_grad()
+    def proposals_from_heads(self, pred_objectness: List[torch.Tensor], pred_deltas: List[torch.Tensor],
+                             image_sizes: torch.Tensor):
+        """Zero-synchronisation inference path: conv-layout heads -> padded proposals (N,K,4), logits (N,K), counts (N)."""
+        logits, boxes, sizes = self.decode_heads(pred_objectness, pred_deltas)
+        return rpn_proposals_batched(boxes, logits, sizes, image_sizes, self.nms_thresh,
+                                     self.pre_nms_topk[self.training], self.post_nms_topk[self.training],
+                                     self.min_box_size)
+
+    def forward(self, images, features: Dict[str, torch.Tensor] = None, gt_instances: Optional[List[Instances]] = None,
+                head_outputs=None):
+        """`forward` of the reference (rpn.py:246) from the head outputs: (objectness list, deltas list) in the conv
+        layout, either passed as `head_outputs` or produced by the optional `head` callable from `features`."""
+        if head_outputs is None:
+            assert self.head is not None, "pass head_outputs=(objectness, deltas) or construct with head=..."
+            head_outputs = self.head(features)
+        obj, dlt = head_outputs
+        image_sizes = images.image_sizes if hasattr(images, "image_sizes") else images
+        feats_hw = [tuple(o.shape[-2:]) for o in obj]
+        anchors = self.anchor_generator.grid_anchors(feats_hw, obj[0].device)
+        n = obj[0].shape[0]
+        logits = [o.permute(0, 2, 3, 1).reshape(n, -1) for o in obj]
+        deltas = [d.view(n, -1, 4, d.shape[-2], d.shape[-1]).permute(0, 3, 4, 1, 2).reshape(n, -1, 4) for d in dlt]
+        losses = {}
+        if self.training:
+            assert gt_instances is not None, "RPN requires gt_instances in training!"
+            at = torch.cat(anchors, 0)
+            asg = self.assign(at, [x.gt_boxes for x in gt_instances])
+            res = self.fused_losses(at, torch.cat(logits, 1), torch.cat(deltas, 1), asg)
+            losses = {"cls_loss": res["cls_loss"], "loc_loss": res["loc_loss"]}
+        sizes = torch.tensor([[int(h), int(w)] for h, w in image_sizes], dtype=torch.int32).to(obj[0].device)
+        ob, os_, cnt, flag = self.proposals_from_heads(obj, dlt, sizes)
+        counts = cnt.tolist()
+        if self.training and int(flag.item()):
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+        proposals = []
+        for i, sz in enumerate(image_sizes):
+            inst = Instances(tuple(sz))
+            inst.proposal_boxes = Boxes(ob[i, :counts[i]])
+            inst.objectness_logits = os_[i, :counts[i]]
+            proposals.append(inst)
+        return proposals, losses
+
+    __call__ = forward
+
+
+def _dense_box_regression_loss(anchors: List[Boxes], box2box_transform: Box2BoxTransform,
+                               pred_anchor_deltas: List[torch.Tensor], gt_boxes: List[torch.Tensor],
+                               fg_mask: torch.Tensor, box_reg_loss_type="smooth_l1", smooth_l1_beta=0.0):
+    """Reference signature (components/box_regression.py:128): summed localisation loss over fg_mask."""
+    if box_reg_loss_type not in ("smooth_l1", "giou"):
+        raise ValueError(f"Invalid dense box regression loss type '{box_reg_loss_type}'")
+    rpn = RegionProposalNetwork([1], box2box_weights=box2box_transform.weights,
+                                scale_clamp=box2box_transform.scale_clamp, batch_size_per_image=1,
+                                box_reg_loss_type=box_reg_loss_type, smooth_l1_beta=smooth_l1_beta)
+    at = type(anchors[0]).cat(anchors).tensor
+    n, r = fg_mask.shape
+    deltas = pred_anchor_deltas[0] if len(pred_anchor_deltas) == 1 else torch.cat(pred_anchor_deltas, 1)
+    labels = torch.where(fg_mask, 1, -1).to(torch.int8).contiguous()
+    table = N.f32c(torch.stack(gt_boxes).reshape(-1, 4))
+    matched = torch.arange(r, device=at.device, dtype=torch.int64).repeat(n, 1)
+    offsets = (torch.arange(n + 1, device=at.device, dtype=torch.int64) * r).to(torch.int32)
+    logits = torch.zeros((n, r), dtype=torch.float32, device=at.device)
+    res = rpn.fused_losses(at, logits, deltas, Assignment(labels, matched, table, offsets), num_images_global=1)
+    return res["loc_loss"]

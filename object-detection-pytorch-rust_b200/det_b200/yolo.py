@@ -10,6 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _native as N
+from .matcher import Matcher
 from .nms import nms_images, MODE_AUTO
 
 _DEFAULT_SCALE_CLAMP = math.log(1000.0 / 16)
@@ -76,6 +77,100 @@ class YoloGridHead:
         """Dense decode only: boxes (N,P,4), conf (N,P), scores (N,P,C)."""
         r = self.detect(head, score_thresh=float("inf"), max_det=1, return_dense=True)
         return r["dense_boxes"], r["dense_conf"], r["dense_scores"]
+
+
+class _FusedYoloLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, head, owner, asg, gt_classes, norm):
+        sums = owner._run_loss(head, asg, gt_classes, norm, None, None)
+        ctx.owner, ctx.asg, ctx.gt_classes, ctx.norm = owner, asg, gt_classes, norm
+        ctx.save_for_backward(head)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        (head,) = ctx.saved_tensors
+        up = grad_sums[:3].contiguous().float()
+        gh = torch.empty_like(head)
+        ctx.owner._run_loss(head, ctx.asg, ctx.gt_classes, ctx.norm, up, gh)
+        return gh, None, None, None, None
+
+
+class YoloAssignment:
+    def __init__(self, labels, matched, gt_table, gt_offsets):
+        self.labels, self.matched, self.gt_table, self.gt_offsets = labels, matched, gt_table, gt_offsets
+
+
+class YoloGridTrainer:
+    """Training side of the grid head: IoU target assignment of the S*S*B predictors (the reference's pairwise_iou +
+    Matcher machinery on cell-centred prior boxes) and the fused localisation / objectness / class loss with its
+    backward (specification: oracle/ref_torch.py yolo_grid_anchors, yolo_loss; no reference implementation)."""
+
+    def __init__(self, head: YoloGridHead, iou_thresholds=(0.3, 0.7), iou_labels=(0, -1, 1),
+                 allow_low_quality_matches: bool = True, lambda_coord: float = 5.0, lambda_noobj: float = 0.5):
+        self.head = head
+        self.matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches)
+        self.lambda_coord, self.lambda_noobj = float(lambda_coord), float(lambda_noobj)
+        self._anchors = {}
+
+    def prior_boxes(self, device) -> torch.Tensor:
+        """(S*S*B,4) cell-centred prior boxes, order (row,col,b)."""
+        k = str(device)
+        if k not in self._anchors:
+            h = self.head
+            H, W = h.image_size
+            sx, sy = W / h.S, H / h.S
+            cx = ((torch.arange(h.S, dtype=torch.float32) + 0.5) * sx).view(1, h.S, 1).expand(h.S, h.S, h.B)
+            cy = ((torch.arange(h.S, dtype=torch.float32) + 0.5) * sy).view(h.S, 1, 1).expand(h.S, h.S, h.B)
+            pw = h.priors[:, 0].view(1, 1, -1).expand(h.S, h.S, -1)
+            ph = h.priors[:, 1].view(1, 1, -1).expand(h.S, h.S, -1)
+            a = torch.stack((cx - 0.5 * pw, cy - 0.5 * ph, cx + 0.5 * pw, cy + 0.5 * ph), dim=-1).reshape(-1, 4)
+            self._anchors[k] = a.to(device).contiguous()
+        return self._anchors[k]
+
+    def assign(self, gt_boxes: List[torch.Tensor]) -> YoloAssignment:
+        dev = gt_boxes[0].device
+        matched, labels, table, offsets = self.matcher.match_boxes(list(gt_boxes), self.prior_boxes(dev))
+        return YoloAssignment(labels, matched, table, offsets)
+
+    def assign_packed(self, gt_table: torch.Tensor, gt_offsets: torch.Tensor, n: int) -> YoloAssignment:
+        matched, labels = self.matcher.match_packed(gt_table, gt_offsets, n, self.prior_boxes(gt_table.device))
+        return YoloAssignment(labels, matched, gt_table, gt_offsets)
+
+    def _run_loss(self, head_t, asg, gt_classes, norm, upstream, grad_head):
+        h = self.head
+        n = head_t.shape[0]
+        sums = torch.zeros((8,), dtype=torch.float32, device=head_t.device)
+        with torch.cuda.device(head_t.device):
+            N.call("det_yolo_loss", N.ptr(head_t), N.ptr(asg.labels), N.ptr(asg.matched), N.ptr(asg.gt_table),
+                   N.ptr(gt_classes), N.ptr(asg.gt_offsets), n, h.S, h.B, h.C, h.image_size[0], h.image_size[1],
+                   N.ptr(h.priors_on(head_t.device)), self.lambda_coord, self.lambda_noobj, 1.0 / norm,
+                   N.ptr(upstream), N.ptr(sums), N.ptr(grad_head), N.stream())
+        sums[0] *= self.lambda_coord / norm
+        sums[1] *= 1.0 / norm
+        sums[2] *= 1.0 / norm
+        return sums
+
+    def loss(self, head_t: torch.Tensor, asg: YoloAssignment, gt_classes: torch.Tensor,
+             normalizer: Optional[float] = None, with_grads: bool = False):
+        """head (N,S,S,B*5+C) fp32; gt_classes (sum_G,) int64 packed like asg.gt_table.  Returns {"loc_loss",
+        "obj_loss","cls_loss","num_pos","num_neg"} (autograd-connected) and, with_grads=True, "grad_head" from the same
+        launch (fused forward+backward)."""
+        N.require_cuda(head_t, gt_classes)
+        ht = head_t.contiguous()
+        assert ht.dtype == torch.float32
+        gc = gt_classes.to(torch.int64).contiguous()
+        norm = float(ht.shape[0] if normalizer is None else normalizer)
+        if with_grads:
+            gh = torch.empty_like(ht)
+            sums = self._run_loss(ht.detach(), asg, gc, norm, None, gh)
+        else:
+            sums = _FusedYoloLoss.apply(ht, self, asg, gc, norm)
+        out = {"loc_loss": sums[0], "obj_loss": sums[1], "cls_loss": sums[2], "num_pos": sums[3].detach(),
+               "num_neg": sums[4].detach(), "sums": sums}
+        if with_grads:
+            out["grad_head"] = gh
+        return out
 
 
 class DenseAnchorHead:

@@ -1,0 +1,115 @@
+"""GPU parity: RPN decode from the conv layout, proposal selection (find_top_rpn_proposals) vs the oracle."""
+import pytest
+import torch
+
+from tests.util import gen, rand_boxes, assert_boxes_close
+
+pytestmark = pytest.mark.gpu
+
+STRIDES = [4, 8, 16, 32, 64]
+SIZES = [[32], [64], [128], [256], [512]]
+RATIOS = [[0.5, 1.0, 2.0]]
+
+
+@pytest.fixture(scope="module")
+def det():
+    import det_b200
+    return det_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ref_torch
+    return ref_torch
+
+
+def _heads(n, img, g, scale=1.0):
+    obj = [torch.randn(n, 3, img // s, img // s, generator=g) for s in STRIDES]
+    dlt = [torch.randn(n, 12, img // s, img // s, generator=g) * scale for s in STRIDES]
+    return obj, dlt
+
+
+def _oracle_decode(O, obj, dlt, img, weights=(1.0, 1.0, 1.0, 1.0)):
+    cells = [O.cell_anchors(s, RATIOS[0]) for s in SIZES]
+    anchors = O.grid_anchors([(img // s, img // s) for s in STRIDES], STRIDES, cells, 0.0)
+    lg, dl = zip(*[O.head_to_hwa(o, d) for o, d in zip(obj, dlt)])
+    props = O.decode_proposals(anchors, list(dl), weights)
+    return anchors, list(lg), list(dl), props
+
+
+@pytest.mark.parametrize("img", [448, 224])
+def test_decode_heads_matches_oracle(det, O, img):
+    g = gen(img)
+    obj, dlt = _heads(3, img, g, 0.5)
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS)
+    logits, boxes, sizes = rpn.decode_heads([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, img)
+    assert sizes == [a.shape[0] for a in anchors]
+    if img == 448:
+        assert sum(sizes) == 50127
+    assert torch.equal(logits.cpu(), torch.cat(lg, 1))          # pure layout change: bit-exact
+    assert_boxes_close(boxes.cpu(), torch.cat(props, 1), rtol=1e-5)
+
+
+def test_reference_signature_decode_proposals(det, O):
+    g = gen(1)
+    obj, dlt = _heads(2, 128, g)
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, 128, (10.0, 10.0, 5.0, 5.0))
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS, box2box_weights=(10.0, 10.0, 5.0, 5.0))
+    got = rpn._decode_proposals([det.Boxes(a.cuda()) for a in anchors], [d.cuda() for d in dl])
+    for a, b in zip(got, props):
+        assert_boxes_close(a.cpu(), b, rtol=1e-5)
+
+
+@pytest.mark.parametrize("img,pre,post,training", [(448, 12000, 2000, False), (448, 6000, 1000, True),
+                                                   (128, 12000, 2000, False), (64, 50, 20, False)])
+def test_find_top_rpn_proposals_matches_oracle(det, O, img, pre, post, training):
+    """Kept boxes/logits and counts bit-exact on identical inputs (the proposals fed to both sides are the same)."""
+    g = gen(img + pre)
+    n = 3
+    obj, dlt = _heads(n, img, g, 0.3)
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, img)
+    sizes = [(img, img), (img - 17, img), (img, img - 40)]
+    want = O.find_top_rpn_proposals(props, lg, sizes, 0.7, pre, post, 0.0, training)
+    got = det.find_top_rpn_proposals([p.cuda() for p in props], [l.cuda() for l in lg], sizes, 0.7, pre, post, 0.0,
+                                     training)
+    assert len(got) == n
+    for i in range(n):
+        wb, ws = want[i]
+        assert len(got[i]) == wb.shape[0], (i, len(got[i]), wb.shape[0])
+        assert torch.equal(got[i].objectness_logits.cpu(), ws)
+        assert torch.equal(got[i].proposal_boxes.tensor.cpu(), wb)
+        assert got[i].image_size == sizes[i]
+
+
+def test_find_top_rpn_proposals_min_size_and_nonfinite(det, O):
+    g = gen(77)
+    obj, dlt = _heads(2, 128, g, 0.3)
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, 128)
+    props[0][0, 5, 2] = float("inf")
+    lg[1][1, 7] = float("nan")
+    sizes = [(128, 128), (100, 128)]
+    want = O.find_top_rpn_proposals([p.clone() for p in props], lg, sizes, 0.7, 1000, 300, 8.0, False)
+    got = det.find_top_rpn_proposals([p.cuda() for p in props], [l.cuda() for l in lg], sizes, 0.7, 1000, 300, 8.0, False)
+    for i in range(2):
+        assert torch.equal(got[i].proposal_boxes.tensor.cpu(), want[i][0])
+        assert torch.equal(got[i].objectness_logits.cpu(), want[i][1])
+    with pytest.raises(FloatingPointError):
+        det.find_top_rpn_proposals([p.cuda() for p in props], [l.cuda() for l in lg], sizes, 0.7, 1000, 300, 8.0, True)
+
+
+def test_forward_eval_from_heads(det, O):
+    g = gen(9)
+    obj, dlt = _heads(2, 224, g, 0.3)
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS).eval()
+    sizes = [(224, 224), (200, 210)]
+    props, losses = rpn.forward(sizes, head_outputs=([o.cuda() for o in obj], [d.cuda() for d in dlt]))
+    assert losses == {}
+    # oracle fed with the GPU's own decoded proposals (identical inputs to the selection stage)
+    logits, boxes, lsz = rpn.decode_heads([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    pl = list(torch.split(boxes.cpu(), lsz, dim=1))
+    ll = list(torch.split(logits.cpu(), lsz, dim=1))
+    want = O.find_top_rpn_proposals(pl, ll, sizes, 0.7, 12000, 2000, 0.0, False)
+    for i in range(2):
+        assert torch.equal(props[i].proposal_boxes.tensor.cpu(), want[i][0])
+        assert torch.equal(props[i].objectness_logits.cpu(), want[i][1])

@@ -1,0 +1,230 @@
+"""GPU parity: IoU target assignment (Matcher), device subsampling, fused RPN / YOLO loss forward+backward."""
+import pytest
+import torch
+
+from tests.util import gen, rand_boxes
+
+pytestmark = pytest.mark.gpu
+
+STRIDES = [4, 8, 16, 32, 64]
+SIZES = [[32], [64], [128], [256], [512]]
+RATIOS = [[0.5, 1.0, 2.0]]
+
+
+@pytest.fixture(scope="module")
+def det():
+    import det_b200
+    return det_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ref_torch
+    return ref_torch
+
+
+def _anchors(O, img=448):
+    cells = [O.cell_anchors(s, RATIOS[0]) for s in SIZES]
+    return torch.cat(O.grid_anchors([(img // s, img // s) for s in STRIDES], STRIDES, cells, 0.0), 0)
+
+
+def _gts(n, g, frame=448.0, gmax=16):
+    out = []
+    for i in range(n):
+        k = int(torch.randint(1, gmax + 1, (1,), generator=g))
+        b = rand_boxes(k, frame, g)
+        b[:, 2:].clamp_(max=frame)
+        out.append(b)
+    return out
+
+
+@pytest.mark.parametrize("thr,lab,lq", [((0.3, 0.7), (0, -1, 1), True), ((0.5,), (0, 1), False), ((0.3, 0.7), (0, -1, 1), False)])
+def test_matcher_on_matrix_bit_exact(det, O, thr, lab, lq):
+    g = gen(3)
+    gt, anc = rand_boxes(23, 448.0, g), _anchors(O)[::5].contiguous()
+    q = O.pairwise_iou(gt, anc)
+    q[4] = 0.0  # a gt overlapping nothing: the zero-IoU low-quality quirk (matcher.py:114-120)
+    q[:, 100] = q[0, 100]  # column ties -> lowest gt index
+    wi, wl = O.match(q, list(thr), list(lab), lq)
+    gi, gl = det.Matcher(list(thr), list(lab), lq)(q.cuda())
+    assert gi.dtype == torch.int64 and gl.dtype == torch.int8
+    assert torch.equal(gi.cpu(), wi) and torch.equal(gl.cpu(), wl)
+
+
+def test_matcher_edges(det, O):
+    m = det.Matcher([0.3, 0.7], [0, -1, 1], True)
+    i, l = m(torch.zeros(0, 9).cuda())
+    assert i.tolist() == [0] * 9 and l.tolist() == [0] * 9 and l.dtype == torch.int8
+    q = torch.tensor([[0.3, 0.7, 0.29999998, 0.6999999, 0.0, 1.0]])
+    wi, wl = O.match(q, [0.3, 0.7], [0, -1, 1], False)
+    gi, gl = det.Matcher([0.3, 0.7], [0, -1, 1], False)(q.cuda())
+    assert torch.equal(gl.cpu(), wl) and wl.tolist() == [-1, 1, 0, -1, 0, 1]
+    with pytest.raises(AssertionError):
+        m(torch.tensor([[0.5, -0.1]]).cuda())
+
+
+@pytest.mark.parametrize("n", [1, 7])
+def test_fused_assignment_matches_oracle(det, O, n):
+    """label + matched index of every anchor bit-exact vs pairwise_iou -> Matcher per image (pre-subsample)."""
+    g = gen(40 + n)
+    anc = _anchors(O)
+    gts = _gts(n, g)
+    if n > 2:
+        gts[1] = torch.zeros(0, 4)                       # image without gt
+        gts[2] = torch.cat([gts[2], torch.tensor([[440.0, 440.0, 440.5, 440.5]])])  # tiny gt
+    wl, wi = O.label_anchors(anc, gts)
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS)
+    asg = rpn.assign(anc.cuda(), [b.cuda() for b in gts], sample=False)
+    assert asg.labels.shape == (n, 50127)
+    for i in range(n):
+        assert torch.equal(asg.labels[i].cpu(), wl[i]), i
+        assert torch.equal(asg.matched[i].cpu(), wi[i]), i
+
+
+def test_device_subsample_counts_and_uniformity(det, O):
+    g = gen(8)
+    n, r = 6, 50127
+    lab = torch.full((n, r), -1, dtype=torch.int8)
+    npos = [0, 5, 128, 129, 3000, 50]
+    nneg = [10, 100, 40000, 300, 47000, 0]
+    for i in range(n):
+        perm = torch.randperm(r, generator=g)
+        lab[i, perm[:npos[i]]] = 1
+        lab[i, perm[npos[i]:npos[i] + nneg[i]]] = 0
+    out = det.subsample_labels_(lab.cuda().clone(), 256, 0.5, seed=1).cpu()
+    for i in range(n):
+        wp, wn = O.subsample_counts(npos[i], nneg[i], 256, 0.5)
+        assert int((out[i] == 1).sum()) == wp and int((out[i] == 0).sum()) == wn
+        assert bool(((out[i] == 1) <= (lab[i] == 1)).all()) and bool(((out[i] == 0) <= (lab[i] == 0)).all())
+    # different seeds choose different subsets; the same seed is reproducible
+    a = det.subsample_labels_(lab.cuda().clone(), 256, 0.5, seed=2).cpu()
+    b = det.subsample_labels_(lab.cuda().clone(), 256, 0.5, seed=2).cpu()
+    assert torch.equal(a, b) and not torch.equal(a, out)
+    # uniformity: over many seeds every negative of image 3 (300 negatives, 128 kept) is picked ~ 128/300 of the time
+    hits = torch.zeros(r)
+    row = lab[3:4].cuda()
+    for s in range(200):
+        hits += (det.subsample_labels_(row.clone(), 256, 0.5, seed=100 + s)[0].cpu() == 0).float()
+    frac = hits[lab[3] == 0] / 200.0
+    assert abs(float(frac.mean()) - 128 / 300) < 1e-6 and float(frac.min()) > 0.25 and float(frac.max()) < 0.6
+
+
+def _rpn_loss_case(O, n, seed, beta=0.0):
+    g = gen(seed)
+    anc = _anchors(O)
+    gts = _gts(n, g)
+    labs, idxs = O.label_anchors(anc, gts)
+    labs = [O.rpn_subsample_(l, 256, 0.5) for l in labs]
+    matched_boxes = [gt[i] for gt, i in zip(gts, idxs)]
+    logits = torch.randn(n, anc.shape[0], generator=g)
+    deltas = torch.randn(n, anc.shape[0], 4, generator=g) * 0.5
+    return anc, gts, labs, idxs, matched_boxes, logits, deltas
+
+
+@pytest.mark.parametrize("beta", [0.0, 0.11])
+def test_rpn_loss_forward_backward_vs_oracle(det, O, beta):
+    n = 4
+    torch.manual_seed(0)
+    anc, gts, labs, idxs, mboxes, logits, deltas = _rpn_loss_case(O, n, 5, beta)
+    lg = logits.clone().requires_grad_(True)
+    dl = deltas.clone().requires_grad_(True)
+    want = O.rpn_losses(anc, lg, torch.stack(labs), dl, torch.stack(mboxes), smooth_l1_beta=beta)
+    (want["cls_loss"] + 2.0 * want["loc_loss"]).backward()
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS, smooth_l1_beta=beta)
+    # (a) the batched fast path with autograd
+    table = torch.cat(gts, 0).cuda()
+    off = torch.tensor([0] + list(torch.tensor([len(x) for x in gts]).cumsum(0)), dtype=torch.int32).cuda()
+    asg = det.Assignment(torch.stack(labs).cuda(), torch.stack(idxs).cuda(), table, off)
+    glg = logits.cuda().requires_grad_(True)
+    gdl = deltas.cuda().requires_grad_(True)
+    res = rpn.fused_losses(anc.cuda(), glg, gdl, asg)
+    (res["cls_loss"] + 2.0 * res["loc_loss"]).backward()
+    torch.testing.assert_close(res["cls_loss"].cpu(), want["cls_loss"].detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(res["loc_loss"].cpu(), want["loc_loss"].detach(), rtol=1e-5, atol=1e-7)
+    assert int(res["num_pos_anchors"]) == want["num_pos"] and int(res["num_neg_anchors"]) == want["num_neg"]
+    torch.testing.assert_close(glg.grad.cpu(), lg.grad, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(gdl.grad.cpu(), dl.grad, rtol=1e-5, atol=1e-9)
+    # (b) single-launch fused forward+backward (upstream gradient 1 for both terms)
+    res2 = rpn.fused_losses(anc.cuda(), logits.cuda(), deltas.cuda(), asg, with_grads=True)
+    lg2 = logits.clone().requires_grad_(True)
+    dl2 = deltas.clone().requires_grad_(True)
+    w2 = O.rpn_losses(anc, lg2, torch.stack(labs), dl2, torch.stack(mboxes), smooth_l1_beta=beta)
+    (w2["cls_loss"] + w2["loc_loss"]).backward()
+    torch.testing.assert_close(res2["grad_logits"].cpu(), lg2.grad, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(res2["grad_deltas"].cpu(), dl2.grad, rtol=1e-5, atol=1e-9)
+    # (c) the reference's own signature: lists per level / per image
+    lsz = [37632, 9408, 2352, 588, 147]
+    out = rpn.losses([det.Boxes(a.cuda()) for a in torch.split(anc, lsz)],
+                     [x.cuda() for x in torch.split(logits, lsz, dim=1)], [l.cuda() for l in labs],
+                     [x.cuda() for x in torch.split(deltas, lsz, dim=1)], [m.cuda() for m in mboxes])
+    torch.testing.assert_close(out["cls_loss"].cpu(), want["cls_loss"].detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out["loc_loss"].cpu(), want["loc_loss"].detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_label_and_sample_anchors_reference_signature(det, O):
+    g = gen(12)
+    anc = _anchors(O)
+    gts = _gts(3, g)
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS)
+    lsz = [37632, 9408, 2352, 588, 147]
+    insts = []
+    for b in gts:
+        inst = det.Instances((448, 448))
+        inst.gt_boxes = det.Boxes(b.cuda())
+        insts.append(inst)
+    labels, mboxes = rpn.label_and_sample_anchors([det.Boxes(a.cuda()) for a in torch.split(anc, lsz)], insts)
+    wl, wi = O.label_anchors(anc, gts)
+    for i in range(3):
+        l = labels[i].cpu()
+        npos_avail, nneg_avail = int((wl[i] == 1).sum()), int((wl[i] == 0).sum())
+        wp, wn = O.subsample_counts(npos_avail, nneg_avail, 256, 0.5)
+        assert int((l == 1).sum()) == wp and int((l == 0).sum()) == wn
+        assert bool(((l == 1) <= (wl[i] == 1)).all()) and bool(((l == 0) <= (wl[i] == 0)).all())
+        assert torch.equal(mboxes[i].cpu(), gts[i][wi[i]])
+
+
+def test_yolo_assign_and_loss_vs_oracle(det, O):
+    g = gen(31)
+    n = 6
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    tr = det.YoloGridTrainer(yh)
+    gts = _gts(n, g)
+    gcls = [torch.randint(0, 20, (len(b),), generator=g) for b in gts]
+    head = torch.randn(n, 7, 7, 30, generator=g)
+    anchors = O.yolo_grid_anchors(7, (448, 448), yh.priors)
+    assert torch.equal(tr.prior_boxes("cuda").cpu(), anchors)
+    wl, wi = O.label_anchors(anchors, gts)
+    asg = tr.assign([b.cuda() for b in gts])
+    assert torch.equal(asg.labels.cpu(), torch.stack(wl)) and torch.equal(asg.matched.cpu(), torch.stack(wi))
+    hc = head.clone().requires_grad_(True)
+    want = O.yolo_loss(hc, torch.stack(wl), torch.stack(wi), gts, gcls, 2, 20, (448, 448), yh.priors)
+    (want["loc_loss"] + want["obj_loss"] + want["cls_loss"]).backward()
+    hg = head.cuda().requires_grad_(True)
+    res = tr.loss(hg, asg, torch.cat(gcls).cuda())
+    (res["loc_loss"] + res["obj_loss"] + res["cls_loss"]).backward()
+    for k in ("loc_loss", "obj_loss", "cls_loss"):
+        torch.testing.assert_close(res[k].cpu(), want[k].detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(hg.grad.cpu(), hc.grad, rtol=1e-5, atol=1e-8)
+    res2 = tr.loss(head.cuda(), asg, torch.cat(gcls).cuda(), with_grads=True)
+    torch.testing.assert_close(res2["grad_head"].cpu(), hc.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_forward_training_from_heads(det, O):
+    g = gen(19)
+    n, img = 2, 224
+    obj = [torch.randn(n, 3, img // s, img // s, generator=g) for s in STRIDES]
+    dlt = [torch.randn(n, 12, img // s, img // s, generator=g) * 0.3 for s in STRIDES]
+    gts = _gts(n, g, 224.0)
+    insts = []
+    for b in gts:
+        inst = det.Instances((img, img))
+        inst.gt_boxes = det.Boxes(b.cuda())
+        insts.append(inst)
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS).train()
+    o_g = [o.cuda().requires_grad_(True) for o in obj]
+    d_g = [d.cuda().requires_grad_(True) for d in dlt]
+    props, losses = rpn.forward([(img, img)] * n, head_outputs=(o_g, d_g), gt_instances=insts)
+    assert set(losses) == {"cls_loss", "loc_loss"} and len(props) == n
+    (losses["cls_loss"] + losses["loc_loss"]).backward()
+    assert all(t.grad is not None and torch.isfinite(t.grad).all() for t in o_g + d_g)
+    assert float(losses["cls_loss"]) > 0 and all(len(p) <= 1000 for p in props)
