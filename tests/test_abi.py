@@ -1,0 +1,45 @@
+"""CPU: libdet_b200.so loads and exports exactly the symbols include/det_b200.h declares (no compute calls)."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "det_b200.h")).read()
+    return re.findall(r"^DET_API\s+[\w\s\*]+?\b(det_[a-z0-9_]+)\s*\(", text, flags=re.M)
+
+
+def test_header_symbols_are_exported_and_bound():
+    from det_b200 import _native as N
+    names = _declared()
+    assert len(names) >= 20 and len(set(names)) == len(names)
+    assert N.missing_symbols() == []
+    assert sorted(names) == sorted(N.PROTOTYPES), "ctypes prototypes out of sync with include/det_b200.h"
+    for n in names:
+        assert N.fn(n) is not None
+
+
+def test_argument_counts_match_header():
+    from det_b200 import _native as N
+    text = open(os.path.join(ROOT, "include", "det_b200.h")).read()
+    for name, body in re.findall(r"^DET_API\s+[\w\s\*]+?\b(det_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.M | re.S):
+        body = body.strip()
+        n_args = 0 if body in ("", "void") else body.count(",") + 1
+        assert n_args == len(N.PROTOTYPES[name][1]), name
+
+
+def test_abi_version_and_pure_queries():
+    from det_b200 import _native as N
+    assert N.fn("det_abi_version")() == 1
+    assert N.fn("det_nms_workspace_bytes")(4, 1000) == 256
+    assert N.fn("det_nms_workspace_bytes")(2, 25200) > 2 * 25200 * 40
+    assert N.fn("det_rpn_proposals_workspace_bytes")(1, 50127) > 50127 * 40
+    assert N.fn("det_match_workspace_bytes")(8, 50127, 100) >= 400
+
+
+def test_no_torch_types_in_the_abi():
+    text = open(os.path.join(ROOT, "include", "det_b200.h")).read()
+    assert "torch" not in text.lower().replace("pytorch-rust", "").replace("python/src", "").replace("torchvision", "") \
+        or "at::" not in text
+    assert "at::Tensor" not in text and "#include <torch" not in text
