@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the post-backbone detection hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Primary workload (BASELINE.json configs[1]): YOLO-style 7x7x(2*5+20) head, batch 256 per GPU, 448x448, score
+threshold 0.25, per-class NMS IoU 0.5, top-300 detections per image.  A step = one batch through the fused
+decode+NMS kernel.  Weak scaling: every rank owns its own batches, no collective on the inference path.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (inputs resident in HBM, rotating over a pool larger than
+L2, CUDA-graph replay); `e2e` goes through the public Python API with pinned host buffers, H2D + D2H inside the timed
+region; `roofline` is the fused kernel's algorithmic bytes / measured launch time against MEASURED_PEAKS.json;
+`cpu_baseline` is the CPU oracle (torch CPU ops + C greedy NMS) on a bounded sample; `extras` carries the training
+step (assignment + loss fwd/bwd, BASELINE configs[2]) and the dense-head decode+NMS (configs[3]).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "object-detection-pytorch-rust_b200"))
+
+import torch  # noqa: E402
+
+L2_BYTES = 126 * 1024 * 1024
+IMG = (448, 448)
+S, B, C = 7, 2, 20
+BATCH = 256
+SCORE_THR, IOU_THR, MAX_DET = 0.25, 0.5, 300
+WORKLOAD = "yolo7x7x30_b256_decode+perclass_nms"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(key):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, dev):
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def make_heads(pool, seed, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(pool, BATCH, S, S, B * 5 + C, generator=g)
+    return t.pin_memory() if pinned else t
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (the reference has no YOLO head; for this workload the oracle is the CPU statement)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step(O, head, priors):
+    boxes, conf, scores = O.yolo_decode(head, B, C, IMG, priors)
+    kept = 0
+    for i in range(head.shape[0]):
+        f, _, _, _ = O.yolo_select_nms(boxes[i], scores[i], SCORE_THR, IOU_THR, MAX_DET)
+        kept += f.numel()
+    return kept
+
+
+def cpu_sample_size(O, priors, budget_s, steps):
+    head = torch.randn(8, S, S, B * 5 + C, generator=torch.Generator().manual_seed(1))
+    cpu_step(O, head, priors)
+    t0 = time.perf_counter()
+    cpu_step(O, head, priors)
+    per_img = (time.perf_counter() - t0) / 8
+    n = int(budget_s / max(steps, 1) / max(per_img, 1e-6))
+    return max(1, min(BATCH, n))
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU implementation of the same path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import ref_torch as O
+    import det_b200
+    torch.set_num_threads(os.cpu_count() or 1)
+    priors = det_b200.YoloGridHead(S, B, C, IMG).priors
+    n_img = cpu_sample_size(O, priors, 150.0, args.steps + args.warmup)
+    heads = torch.randn(4, n_img, S, S, B * 5 + C, generator=torch.Generator().manual_seed(1))
+    for w in range(args.warmup):
+        cpu_step(O, heads[w % 4], priors)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_step(O, heads[k % 4], priors)
+    dt = time.perf_counter() - t0
+    val = n_img * args.steps / dt
+    sample = f"{n_img} of {BATCH} images per step (oracle: torch CPU decode + C greedy NMS, per-image loop)"
+    print(json.dumps({
+        "impl": "reference", "metric": "images/sec decode+NMS", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": n_img, "grid": S, "boxes": B, "classes": C,
+                   "score_thresh": SCORE_THR, "iou_thresh": IOU_THR, "max_det": MAX_DET},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# extras: training step (configs[2]) and dense head (configs[3])
+# ----------------------------------------------------------------------------------------------------------------
+def time_region(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def synth_gt(n, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    counts = torch.randint(1, 17, (n,), generator=g)
+    tot = int(counts.sum())
+    xy = torch.rand(tot, 2, generator=g) * 0.8 * 448
+    wh = torch.rand(tot, 2, generator=g) * 0.2 * 448 + 1
+    boxes = torch.cat([xy, (xy + wh).clamp(max=448.0)], 1)
+    cls = torch.randint(0, 20, (tot,), generator=g)
+    off = torch.zeros(n + 1, dtype=torch.int32)
+    off[1:] = counts.cumsum(0).to(torch.int32)
+    return boxes.to(dev), cls.to(dev), off.to(dev), tot
+
+
+def extras_train(det, dev, world, peak, quick):
+    out = {}
+    n = 1024
+    # (i) YOLO grid head: assignment (Matcher on prior boxes) + fused loc/obj/cls loss fwd+bwd, batch 1024 per GPU
+    yh = det.YoloGridHead(S, B, C, IMG)
+    tr = det.YoloGridTrainer(yh)
+    gtb, gtc, off, tot = synth_gt(n, 2, dev)
+    pool = 8 if quick else 24
+    heads = [torch.randn(n, S, S, B * 5 + C, device=dev) for _ in range(pool)]
+    state = {"i": 0}
+
+    def step_grid():
+        h = heads[state["i"] % pool]
+        state["i"] += 1
+        asg = tr.assign_packed(gtb, off, n)
+        res = tr.loss(h, asg, gtc, with_grads=True)
+        det.dist.allreduce_sums_(res["sums"])
+
+    ms = time_region(step_grid, 30 if quick else 200)
+    out["train_grid_b1024"] = {"workload": "yolo7x7x30 assign+loss fwd/bwd, batch 1024/GPU", "ms_per_step": ms,
+                               "images_per_s_per_gpu": n / ms * 1e3}
+    # (ii) reference-native RPN form: R = 50127 anchors (FPN-18 @ 448), Matcher([0.3,0.7]), 256 samples, L1 + BCE
+    rpn = det.RegionProposalNetwork([4, 8, 16, 32, 64])
+    anchors = torch.cat(rpn.anchor_generator.grid_anchors([(448 // s, 448 // s) for s in (4, 8, 16, 32, 64)], dev), 0)
+    R = anchors.shape[0]
+    nb = 256 if quick else 1024
+    gtb2, _, off2, tot2 = synth_gt(nb, 3, dev)
+    logits = torch.randn(nb, R, device=dev)
+    deltas = torch.randn(nb, R, 4, device=dev) * 0.5
+    gl, gd = torch.empty_like(logits), torch.empty_like(deltas)
+    rpn._anchors_for_loss = anchors
+    st = {"seed": 0}
+
+    def step_assign():
+        matched, labels = rpn.anchor_matcher.match_packed(gtb2, off2, nb, anchors)
+        st["seed"] += 1
+        det.subsample_labels_(labels, 256, 0.5, st["seed"])
+        st["asg"] = det.Assignment(labels, matched, gtb2, off2)
+
+    def step_loss():
+        sums = rpn._run_loss(logits, deltas, st["asg"], nb * world, None, gl, gd)
+        det.dist.allreduce_sums_(sums)
+
+    ms_a = time_region(step_assign, 5 if quick else 20)
+    ms_l = time_region(step_loss, 5 if quick else 20)
+    loss_bytes = nb * (49 * R) + 16 * tot2 + 20
+    assign_bytes = nb * 9 * R + 16 * tot2
+    out["train_rpn_r50127"] = {
+        "workload": f"RPN form R=50127, batch {nb}/GPU: match+subsample, fused loss fwd+bwd (+8-float allreduce)",
+        "ms_assign": ms_a, "ms_loss_fwd_bwd": ms_l, "images_per_s_per_gpu": nb / (ms_a + ms_l) * 1e3,
+        "loss_roofline": {"bound": "hbm", "achieved": loss_bytes / ms_l / 1e6, "peak": peak, "unit": "GB/s",
+                          "frac": loss_bytes / ms_l / 1e6 / peak, "algorithmic_bytes": loss_bytes},
+        "assign_roofline": {"bound": "hbm", "achieved": assign_bytes / ms_a / 1e6, "peak": peak, "unit": "GB/s",
+                            "frac": assign_bytes / ms_a / 1e6 / peak, "algorithmic_bytes": assign_bytes,
+                            "note": "IoU ALU-bound: 16 gt x 50127 anchors x 2 passes per image"},
+    }
+    return out
+
+
+def extras_dense(det, dev, peak, quick):
+    n, C80 = (8 if quick else 32), 80
+    strides = [8, 16, 32]
+    wh = [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]]]
+    dh = det.DenseAnchorHead(strides, wh, C80)
+    g = torch.Generator(device=dev).manual_seed(3)
+    pool = 2 if quick else 6
+    heads = []
+    for _ in range(pool):
+        hs = [torch.randn(n, 3 * (5 + C80), 640 // s, 640 // s, device=dev, generator=g) for s in strides]
+        for h in hs:
+            h.view(n, 3, 5 + C80, h.shape[2], h.shape[3])[:, :, 4] -= 4.0  # objectness bias (SURVEY Cfg4)
+        heads.append(hs)
+    R = 25200
+    outbuf = (torch.empty((n, R, 4), device=dev), torch.empty((n, R), device=dev),
+              torch.empty((n, R), dtype=torch.int64, device=dev))
+    st = {"i": 0}
+
+    def step_decode():
+        dh.decode(heads[st["i"] % pool], out=outbuf)
+        st["i"] += 1
+
+    ms_d = time_region(step_decode, 5 if quick else 20)
+    boxes, scores, classes = outbuf
+    keep, cnt = det.nms_images(boxes, scores, classes, None, 0.5, 1000)
+
+    def step_nms():
+        det.nms_images(boxes, scores, classes, None, 0.5, 1000)
+
+    ms_n = time_region(step_nms, 3 if quick else 10)
+    dec_bytes = n * 9273600
+    k_tot = int(cnt.sum())
+    nms_bytes = n * 28 * R + 8 * k_tot + 8 * n
+    return {"dense_head_25200x80": {
+        "workload": f"dense head 3x(80^2+40^2+20^2) anchors x 80 classes, batch {n}: decode, then 25200-box per-class NMS",
+        "ms_decode": ms_d, "ms_nms": ms_n, "images_per_s": n / (ms_d + ms_n) * 1e3,
+        "decode_roofline": {"bound": "hbm", "achieved": dec_bytes / ms_d / 1e6, "peak": peak, "unit": "GB/s",
+                            "frac": dec_bytes / ms_d / 1e6 / peak, "algorithmic_bytes": dec_bytes},
+        "nms_roofline": {"bound": "hbm", "achieved": nms_bytes / ms_n / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": nms_bytes / ms_n / 1e6 / peak, "algorithmic_bytes": nms_bytes,
+                         "note": "sort + greedy sweep: latency/ALU-bound, not HBM-bound"},
+        "kept_per_image": k_tot / n}}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="smaller extras / CPU sample (CI)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import det_b200 as det
+    det._native.lib()  # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    rank, world, local = det.dist.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    peak, peak_src = load_peaks()
+
+    yh = det.YoloGridHead(S, B, C, IMG)
+    img_bytes = S * S * (B * 5 + C) * 4
+    pool = L2_BYTES // (BATCH * img_bytes) + 8  # rotating pool of input batches larger than L2
+    heads = make_heads(pool, 1 + rank).to(dev)
+    outs = [yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET) for i in range(4)]
+    torch.cuda.synchronize()
+
+    # CUDA graph with one launch per pool entry (launch-bound loop -> graph replay)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        for i in range(pool):
+            yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+    launches = {"n": 0}
+
+    def run_steps(k):
+        full, rem = divmod(k, pool)
+        for _ in range(full):
+            graph.replay()
+        for i in range(rem):
+            yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+        launches["n"] += k
+
+    run_steps(args.warmup)
+    sampler = ClockSampler(local)
+    barrier(world)
+    sampler.start()
+    launches["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(args.steps)
+    e1.record()
+    barrier(world)
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    ms_step = ms_total / args.steps
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # algorithmic bytes of one launch: logits read + kept detections written (fused: no decode hand-off)
+    kept = sum(int(o["count"].sum()) for o in outs) / len(outs)
+    algo_bytes = BATCH * img_bytes + kept * (8 + 16 + 4) + BATCH * 4
+    achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": load_traffic("yolo_decode_nms_kernel"), "kernel": "yolo_decode_nms_kernel<2048>",
+                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                "note": "4 MB per launch = 0.6 us at the HBM peak: this configuration is latency-bound "
+                        "(in-shared-memory sort + greedy sweep per image), see extras for the HBM-bound kernels"}
+
+    # end to end through the public API with host buffers (pinned), H2D + D2H inside the timed region
+    e2e_steps = max(3, min(args.steps, 2000))
+    hpool = 8
+    host_in = make_heads(hpool, 100 + rank, pinned=True)
+    dev_in = [torch.empty((BATCH, S, S, B * 5 + C), device=dev) for _ in range(2)]
+    host_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs[0].items()
+                 if isinstance(v, torch.Tensor)} for _ in range(2)]
+
+    def e2e_step(i):
+        d = dev_in[i % 2]
+        d.copy_(host_in[i % hpool], non_blocking=True)
+        o = yh.detect(d, SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+        for k, v in host_out[i % 2].items():
+            v.copy_(o[k], non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier(world)
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    h2d = BATCH * img_bytes
+    d2h = sum(v.numel() * v.element_size() for v in host_out[0].values())
+    e2e = {"value": world * BATCH * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps}
+
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras.update(extras_train(det, dev, world, peak, args.quick))
+            if world == 1 or rank == 0:
+                extras.update(extras_dense(det, dev, peak, args.quick))
+        except Exception as e:  # noqa: BLE001
+            extras["error"] = f"{type(e).__name__}: {e}"
+        barrier(world)
+
+    cpu_baseline = None
+    if rank == 0:
+        from oracle import ref_torch as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_img = cpu_sample_size(O, yh.priors, 4.0 if args.quick else 15.0, 1)
+        sample = make_heads(1, 1)[0][:n_img]
+        cpu_step(O, sample[:4], yh.priors)
+        t0 = time.perf_counter()
+        cpu_step(O, sample, yh.priors)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n_img / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n_img} images of the same synthetic batch, one pass ({dt:.1f} s): oracle torch-CPU "
+                                  "decode + C greedy NMS, per-image loop"}
+        print(json.dumps({
+            "metric": "images/sec decode+NMS", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": BATCH, "grid": S, "boxes": B, "classes": C,
+                       "image": list(IMG), "score_thresh": SCORE_THR, "iou_thresh": IOU_THR, "max_det": MAX_DET,
+                       "l2": f"inputs rotate over a pool of {pool} batches = {pool * BATCH * img_bytes / 2**20:.0f} MiB "
+                             "> 126 MiB L2", "launch": "CUDA graph replay, one kernel per step"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "extras": extras,
+        }))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

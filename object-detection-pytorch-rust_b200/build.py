@@ -34,17 +34,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, debug_phases=False):
+    """debug_phases=True builds libdet_b200_dbg.so with the DET_MARK phase timeline compiled in (profiling only)."""
+    out = OUT.replace(".so", "_dbg.so") if debug_phases else OUT
+    if not debug_phases and not force and not needs_build():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    extra = (["-Xptxas", "-v"] if verbose else []) + (["-DDET_DEBUG_PHASES"] if debug_phases else [])
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out] + sources()
     print("[det_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(OUT)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug_phases="--debug-phases" in sys.argv))

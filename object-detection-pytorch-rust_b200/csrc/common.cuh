@@ -75,15 +75,43 @@ __device__ __forceinline__ uint32_t score_desc_key(float s) {
 }
 
 // exact greedy-NMS predicate of torchvision's CPU kernel: does kept box `a` suppress candidate `b`?
-// thr_f = float_threshold_below(double threshold).
+//     ovr = inter / (area_a + area_b - inter);  suppressed iff (double)ovr > threshold
+// thr_f = float_threshold_below(double threshold), so the comparison is (ovr > thr_f) in fp32.
+// The IEEE division is only executed for the knife-edge cases.  With t = fl(thr_f*denom) normal and thr_f normal and
+// positive (hence denom > 0, |t/(thr_f*denom) - 1| <= 2^-24):
+//   inter > fl(t*(1+2^-20))  =>  inter/denom > thr_f*(1+2^-21) >= nextafter(thr_f)  =>  fl(inter/denom) > thr_f
+//   inter < fl(t*(1-17*2^-24)) =>  inter/denom < thr_f                              =>  fl(inter/denom) <= thr_f
+// (rounding is monotone).  Everything else -- zero intersection, NaN/Inf, denormal or non-positive threshold or
+// denominator, and the band in between -- takes the exact path, so the result is bit-identical to the plain formula.
+// the exact IEEE quotient test; kept out of line so that the compiler cannot speculate the division ahead of the
+// cheap guards in nms_suppresses (it is needed only for knife-edge pairs)
+static __device__ __noinline__ bool nms_exact_ratio_gt(float inter, float denom, float thr_f) { return inter / denom > thr_f; }
+
+// NONAN: the caller guarantees that no coordinate of either box is NaN; then std::max/min and FMNMX agree (the sign
+// of a zero cannot change w, h) and the six selects become single FMNMX instructions.
+template <bool NONAN>
 __device__ __forceinline__ bool nms_suppresses(const float4 a, float area_a, const float4 b, float area_b,
                                                float thr_f) {
-    float xx1 = max_std(a.x, b.x), yy1 = max_std(a.y, b.y);
-    float xx2 = min_std(a.z, b.z), yy2 = min_std(a.w, b.w);
-    float w = max_std(0.0f, xx2 - xx1), h = max_std(0.0f, yy2 - yy1);
-    float inter = w * h;
-    float ovr = inter / (area_a + area_b - inter);
-    return ovr > thr_f;
+    float xx1, yy1, xx2, yy2, w, h;
+    if (NONAN) {
+        xx1 = fmaxf(a.x, b.x); yy1 = fmaxf(a.y, b.y);
+        xx2 = fminf(a.z, b.z); yy2 = fminf(a.w, b.w);
+        w = fmaxf(0.0f, xx2 - xx1); h = fmaxf(0.0f, yy2 - yy1);
+    } else {
+        xx1 = max_std(a.x, b.x); yy1 = max_std(a.y, b.y);
+        xx2 = min_std(a.z, b.z); yy2 = min_std(a.w, b.w);
+        w = max_std(0.0f, xx2 - xx1); h = max_std(0.0f, yy2 - yy1);
+    }
+    const float inter = w * h;
+    const float denom = area_a + area_b - inter;
+    if (inter == 0.0f)  // 0/denom is +-0 (or NaN for denom 0/NaN): suppresses only under a negative threshold
+        return (thr_f < 0.0f) && (denom == denom) && (denom != 0.0f);
+    const float t = thr_f * denom;
+    if (thr_f > 1e-30f && t > 1e-30f && t < 1e30f) {
+        if (inter > t * 1.000001f) return true;
+        if (inter < t * 0.999999f) return false;
+    }
+    return nms_exact_ratio_gt(inter, denom, thr_f);
 }
 
 // reference pairwise IoU of one pair (boxes.py:173-214), NaN-propagating min/max like torch
@@ -107,6 +135,17 @@ __device__ __forceinline__ int warp_sum(int v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// Optional phase timeline (build with -DDET_DEBUG_PHASES): block 0 / thread 0 stamps clock64() at DET_MARK(i).
+#ifdef DET_DEBUG_PHASES
+static __device__ long long g_phase_clock[32];  // one copy per translation unit (no -rdc)
+#define DET_MARK(i)                                                     \
+    do {                                                                \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clock[i] = clock64(); \
+    } while (0)
+#else
+#define DET_MARK(i) do { } while (0)
+#endif
 
 #endif  // __CUDACC__
 }  // namespace det

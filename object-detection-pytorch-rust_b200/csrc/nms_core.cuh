@@ -32,22 +32,79 @@ struct KeyLayout {
 };
 
 // ---- CTA-wide bitonic sort of n (power of two) keys in shared memory, ascending ------------------
-template <int T>
-__device__ __forceinline__ void cta_bitonic_sort(uint64_t* keys, int n) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n >> 1); t += T) {
-                const int i = 2 * t - (t & (j - 1));
-                const uint64_t a = keys[i], b = keys[i + j];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up) {
-                    keys[i] = b;
-                    keys[i + j] = a;
+// Register-resident network: thread t owns the E consecutive keys [t*E, t*E+E).  Compare-exchange distance j
+//   j < E        : inside the thread (registers only)
+//   j < 32*E     : partner is lane ^ (j/E) of the same warp (64-bit shuffles, no barrier)
+//   j >= 32*E    : partner lives in another warp -> one round trip through shared memory
+// so a 1024-key sort by 256 threads needs 6 shared-memory stages instead of 55 barrier-separated ones.
+template <int E>
+__device__ __forceinline__ void bitonic_ce_pair(uint64_t& lo, uint64_t& hi, bool up) {
+    const bool sw = (lo > hi) == up;
+    const uint64_t a = sw ? hi : lo, b = sw ? lo : hi;
+    lo = a;
+    hi = b;
+}
+
+template <int T, int E>
+__device__ void cta_bitonic_sort_reg(uint64_t* keys, int n) {
+    constexpr int LOG_E = (E == 1) ? 0 : (E == 2) ? 1 : (E == 4) ? 2 : (E == 8) ? 3 : 4;
+    constexpr int LOG_MAX = LOG_E + 8 + 1;  // T <= 512
+    const int t = threadIdx.x;
+    const int base = t * E;
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = (base + e < n) ? keys[base + e] : kSentinelKey;
+    for (int a = 1; (1 << a) <= n; ++a) {
+        const int k = 1 << a;
+#pragma unroll
+        for (int b = LOG_MAX - 1; b >= 0; --b) {
+            if (b >= a) continue;
+            const int j = 1 << b;
+            if (b < LOG_E) {  // in registers
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if ((e & j) == 0) bitonic_ce_pair<E>(v[e], v[e | j], ((base + e) & k) == 0);
+            } else if (b < LOG_E + 5) {  // inside the warp
+                const int lane_xor = j >> LOG_E;
+                const bool lower = (t & lane_xor) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, v[e], lane_xor);
+                    const bool up = ((base + e) & k) == 0;
+                    const bool keep_min = (up == lower);
+                    const bool other_smaller = other < v[e];
+                    v[e] = (keep_min == other_smaller) ? other : v[e];
                 }
+            } else {  // across warps
+#pragma unroll
+                for (int e = 0; e < E; ++e) keys[base + e] = v[e];
+                __syncthreads();
+                const bool lower = (base & j) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t other = keys[(base + e) ^ j];
+                    const bool up = ((base + e) & k) == 0;
+                    const bool keep_min = (up == lower);
+                    const bool other_smaller = other < v[e];
+                    v[e] = (keep_min == other_smaller) ? other : v[e];
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
+#pragma unroll
+    for (int e = 0; e < E; ++e) keys[base + e] = v[e];
+    __syncthreads();
+}
+
+// keys[0..n) ascending; n a power of two, n <= 16*T; the array must hold at least max(n, T) entries
+template <int T>
+__device__ __forceinline__ void cta_bitonic_sort(uint64_t* keys, int n) {
+    if (n <= T) cta_bitonic_sort_reg<T, 1>(keys, n);
+    else if (n == 2 * T) cta_bitonic_sort_reg<T, 2>(keys, n);
+    else if (n == 4 * T) cta_bitonic_sort_reg<T, 4>(keys, n);
+    else if (n == 8 * T) cta_bitonic_sort_reg<T, 8>(keys, n);
+    else cta_bitonic_sort_reg<T, 16>(keys, n);
 }
 
 __device__ __forceinline__ int next_pow2(int v) {
@@ -58,11 +115,15 @@ __device__ __forceinline__ int next_pow2(int v) {
 
 // ---- greedy suppression of one segment [s,e) by ONE WARP -------------------------------------------
 // sbox/sarea: boxes in sorted order; state: 0 candidate, 1 ignored, 2 kept; klist[s..s+nk): kept positions.
-template <typename KT>
+// Per 32-box chunk: (a) every lane tests its box against the kept list, (b) every surviving lane builds, with
+// independent IoU tests, the 32-bit row "which later survivors do I suppress", (c) the greedy order is resolved on
+// those bit rows alone (ffs / shfl / and-not), (d) kept lanes append themselves with a popc rank.
+template <typename KT, bool NONAN>
 __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t* state, KT* klist, int s, int e,
                                 float thr_f, int max_keep) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     int nk = 0;
     for (int base = s; base < e && nk < max_keep; base += 32) {
         const int p = base + lane;
@@ -74,31 +135,47 @@ __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t*
             ma = sarea[p];
         }
         bool alive = act;
-        for (int k = 0; k < nk; ++k) {
-            if (!__any_sync(FULL, alive)) break;
+        for (int k = 0; k < nk; ++k) {  // (a)
+            if ((k & 7) == 0 && !__any_sync(FULL, alive)) break;
             const int kp = (int)klist[s + k];
             const float4 kb = sbox[kp];
             const float ka = sarea[kp];
-            if (alive && nms_suppresses(kb, ka, mb, ma, thr_f)) alive = false;
+            if (alive && nms_suppresses<NONAN>(kb, ka, mb, ma, thr_f)) alive = false;
         }
-        unsigned m = __ballot_sync(FULL, alive);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            float4 kb;
-            kb.x = __shfl_sync(FULL, mb.x, l);
-            kb.y = __shfl_sync(FULL, mb.y, l);
-            kb.z = __shfl_sync(FULL, mb.z, l);
-            kb.w = __shfl_sync(FULL, mb.w, l);
-            const float ka = __shfl_sync(FULL, ma, l);
-            if (lane == l) {
-                klist[s + nk] = (KT)p;
-                state[p] = 2;
+        const unsigned am = __ballot_sync(FULL, alive);
+        // (b) every unordered pair of the chunk is tested once: lane l meets lane (l+d)&31 for d = 1..16.  If the
+        //     partner is later in the order, lane l is the suppressor (row bit); if the rotation wrapped, the partner
+        //     is the suppressor and lane l only records "killed by" (col bit).
+        unsigned row = 0, col = 0;
+        const int nchunk = min(32, e - base);
+        if (nchunk > 1) {
+#pragma unroll 4
+            for (int d = 1; d <= 16; ++d) {
+                if (d >= nchunk) break;
+                const int j = (lane + d) & 31;
+                if (!alive || !((am >> j) & 1u) || (d == 16 && lane >= 16)) continue;
+                const float4 bj = sbox[base + j];
+                const float aj = sarea[base + j];
+                if (j > lane) {
+                    if (nms_suppresses<NONAN>(mb, ma, bj, aj, thr_f)) row |= 1u << j;
+                } else {
+                    if (nms_suppresses<NONAN>(bj, aj, mb, ma, thr_f)) col |= 1u << j;
+                }
             }
-            ++nk;
-            if (nk >= max_keep) break;
-            if (alive && lane > l && nms_suppresses(kb, ka, mb, ma, thr_f)) alive = false;
-            m = __ballot_sync(FULL, alive) & ~((2u << l) - 1u);
         }
+        unsigned rem = am, keepmask = 0;  // (c)
+        while (rem) {
+            const int l = __ffs(rem) - 1;
+            keepmask |= 1u << l;
+            const unsigned killed = __shfl_sync(FULL, row, l) | __ballot_sync(FULL, (col >> l) & 1u);
+            rem &= ~(killed | (1u << l));
+        }
+        const int rank = nk + __popc(keepmask & lt_mask);  // (d)
+        if (((keepmask >> lane) & 1u) && rank < max_keep) {
+            klist[s + rank] = (KT)p;
+            state[p] = 2;
+        }
+        nk = min(nk + __popc(keepmask), max_keep);
         __syncwarp();
     }
     return nk;
@@ -106,7 +183,7 @@ __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t*
 
 // ---- greedy suppression of one segment [s,e) by a WHOLE CTA of T threads ----------------------------
 // scratch: rowbits[T * T/32], amask[T/32], s_nk[1] in shared memory.
-template <int T, typename KT>
+template <int T, typename KT, bool NONAN>
 __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* state, KT* klist, int s, int e,
                                float thr_f, int max_keep, uint32_t* rowbits, uint32_t* amask, int* s_nk) {
     constexpr int W = T / 32;
@@ -129,7 +206,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             const int kp = (int)klist[s + k];
             const float4 kb = sbox[kp];
             const float ka = sarea[kp];
-            if (alive && nms_suppresses(kb, ka, mb, ma, thr_f)) alive = false;
+            if (alive && nms_suppresses<NONAN>(kb, ka, mb, ma, thr_f)) alive = false;
         }
         const unsigned bal = __ballot_sync(FULL, alive);
         if (lane == 0) amask[wid] = bal;
@@ -144,31 +221,46 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
                     const int b = __ffs(cand) - 1;
                     cand &= cand - 1;
                     const int q = base + w2 * 32 + b;
-                    if (nms_suppresses(mb, ma, sbox[q], sarea[q], thr_f)) bits |= 1u << b;
+                    if (nms_suppresses<NONAN>(mb, ma, sbox[q], sarea[q], thr_f)) bits |= 1u << b;
                 }
                 rowbits[tid * W + w2] = bits;
             }
         }
         __syncthreads();
-        // (c) sequential resolution by warp 0: lane w owns survivor word w
+        // (c) sequential resolution by warp 0, one 32-candidate word at a time: lane w owns survivor word w; inside
+        //     the current word the greedy order is resolved on its diagonal bit rows, then the kept rows are
+        //     OR-ed into a removal mask for the later words (independent shared-memory loads).
         if (wid == 0) {
             unsigned word = (lane < W) ? amask[lane] : 0u;
             int nkl = nk;
-            while (true) {
-                const unsigned has = __ballot_sync(FULL, word != 0u);
-                if (!has) break;
-                const int f = __ffs(has) - 1;
-                const unsigned wf = __shfl_sync(FULL, word, f);
-                const int b = __ffs(wf) - 1;
-                const int c = f * 32 + b;
-                if (lane == 0) {
-                    klist[s + nkl] = (KT)(base + c);
-                    state[base + c] = 2;
+            for (int f = 0; f < W && nkl < max_keep; ++f) {
+                unsigned rem = __shfl_sync(FULL, word, f), keepmask = 0;
+                if (!rem) continue;
+                const unsigned diag = rowbits[(f * 32 + lane) * W + f];  // stale for dead lanes: only read if alive
+                while (rem) {
+                    const int b = __ffs(rem) - 1;
+                    keepmask |= 1u << b;
+                    rem &= ~(__shfl_sync(FULL, diag, b) | (1u << b));
                 }
-                ++nkl;
-                if (lane == f) word &= ~(1u << b);
-                if (nkl >= max_keep) break;
-                if (lane < W && lane >= f) word &= ~rowbits[c * W + lane];
+                if (nkl + __popc(keepmask) > max_keep) {  // keep only the first (max_keep - nkl) of them
+                    unsigned km = keepmask, trimmed = 0;
+                    for (int t = nkl; t < max_keep; ++t) {
+                        trimmed |= km & (0u - km);
+                        km &= km - 1;
+                    }
+                    keepmask = trimmed;
+                }
+                const int rank = nkl + __popc(keepmask & ((1u << lane) - 1u));
+                if ((keepmask >> lane) & 1u) {
+                    klist[s + rank] = (KT)(base + f * 32 + lane);
+                    state[base + f * 32 + lane] = 2;
+                }
+                nkl += __popc(keepmask);
+                if (lane < W && lane > f) {
+                    unsigned kill = 0;
+                    for (unsigned km = keepmask; km; km &= km - 1) kill |= rowbits[(f * 32 + __ffs(km) - 1) * W + lane];
+                    word &= ~kill;
+                }
             }
             if (lane == 0) *s_nk = nkl;
         }

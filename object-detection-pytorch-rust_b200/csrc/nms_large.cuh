@@ -294,7 +294,7 @@ large_warp_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const fl
         if (i >= total) break;
         const int4 sg = seg_small[i];
         const int64_t o = (int64_t)sg.x * mp;
-        warp_segment_nms<int32_t>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
+        warp_segment_nms<int32_t, false>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
     }
 }
 
@@ -314,7 +314,7 @@ large_cta_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const flo
         if (i >= total) break;
         const int4 sg = seg_large[i];
         const int64_t o = (int64_t)sg.x * mp;
-        cta_segment_nms<kSegThreads, int32_t>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
+        cta_segment_nms<kSegThreads, int32_t, false>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
                                               rowbits, amask, &s_nk);
     }
 }

@@ -7,7 +7,8 @@ namespace det {
 
 constexpr int kSmallThreads = 256;
 constexpr int kSmallIdxBits = 12;
-constexpr int kWarpSegMax = 64;  // segments up to this length are swept by a single warp
+constexpr int kTinySegMax = 64;   // segments up to this length: full pair bit-matrix (one u64 row per box)
+constexpr int kWarpSegMax = 192;  // segments up to this length are swept by a single warp (warps run in parallel)
 
 template <int CAP>
 struct SmallSmem {
@@ -15,15 +16,21 @@ struct SmallSmem {
     float4 sbox[CAP];
     float sarea[CAP];
     uint16_t klist[CAP];
-    uint16_t seg_s[CAP];
+    uint16_t seg_s[CAP];  // tiny segments (at most one per box)
     uint16_t seg_e[CAP];
+    uint16_t mid_s[CAP / kTinySegMax], mid_e[CAP / kTinySegMax];    // warp-swept segments (each > 64 boxes)
+    uint16_t big_s[CAP / kWarpSegMax + 1], big_e[CAP / kWarpSegMax + 1];  // CTA-swept segments (each > 192 boxes)
     uint8_t state[CAP];
-    uint32_t rowbits[kSmallThreads * (kSmallThreads / 32)];
+    uint8_t tiny_m[CAP];  // length of the tiny segment a position belongs to (0: not in a tiny segment)
+    union {               // the tiny phase finishes before the CTA-wide phase starts
+        uint64_t rowmask[CAP];
+        uint32_t rowbits[kSmallThreads * (kSmallThreads / 32)];
+    };
     uint32_t amask[kSmallThreads / 32];
     float red_max[kSmallThreads / 32];
     float red_min[kSmallThreads / 32];
     int red_flag[kSmallThreads / 32];
-    int nseg_small, nseg_large, nk_scratch, nkept, bad_cat;
+    int nseg_tiny, nseg_small, nseg_large, nk_scratch, nkept, bad_cat;
     float span;
     int fast;
 };
@@ -49,6 +56,7 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
     // reference CPU rule: boxes.numel() <= 4000 -> coordinate-offset trick (torchvision/ops/boxes.py batched_nms)
     const bool trick = (mode == DET_NMS_AUTO) ? (cnt <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
     if (tid == 0) {
+        sm.nseg_tiny = 0;
         sm.nseg_small = 0;
         sm.nseg_large = 0;
         sm.nkept = 0;
@@ -98,6 +106,7 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
         }
         __syncthreads();
     }
+    DET_MARK(4);
     const float span = sm.span;
     const bool by_cat = !trick || sm.fast;
     // ---- phase 1+2: keys, sort
@@ -112,8 +121,11 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
         sm.keys[i] = k;
     }
     __syncthreads();
+    DET_MARK(5);
     cta_bitonic_sort<kSmallThreads>(sm.keys, npad);
+    DET_MARK(6);
     // ---- phase 3: boxes in sorted order (+ offset), segment discovery
+    bool clean = true;  // no NaN coordinate seen by this thread
     for (int p = tid; p < cnt; p += kSmallThreads) {
         const uint64_t k = sm.keys[p];
         const int i = (int)KL::idx(k);
@@ -125,6 +137,9 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
         sm.sbox[p] = b;
         sm.sarea[p] = box_area(b);
         sm.state[p] = 0;
+        sm.tiny_m[p] = 0;
+        sm.rowmask[p] = 0ull;
+        clean &= (b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w);
         const uint32_t sg = KL::seg(k);
         if (p == 0 || KL::seg(sm.keys[p - 1]) != sg) {
             int lo = p + 1, hi = cnt;  // segment end = first position with a larger segment field
@@ -132,43 +147,133 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
                 const int mid = (lo + hi) >> 1;
                 if (KL::seg(sm.keys[mid]) > sg) hi = mid; else lo = mid + 1;
             }
-            if (lo - p <= kWarpSegMax) {
-                const int slot = atomicAdd(&sm.nseg_small, 1);
+            if (lo - p <= kTinySegMax) {
+                const int slot = atomicAdd(&sm.nseg_tiny, 1);
                 sm.seg_s[slot] = (uint16_t)p;
                 sm.seg_e[slot] = (uint16_t)lo;
+            } else if (lo - p <= kWarpSegMax) {
+                const int slot = atomicAdd(&sm.nseg_small, 1);
+                sm.mid_s[slot] = (uint16_t)p;
+                sm.mid_e[slot] = (uint16_t)lo;
             } else {
                 const int slot = atomicAdd(&sm.nseg_large, 1);
-                sm.seg_s[CAP - 1 - slot] = (uint16_t)p;
-                sm.seg_e[CAP - 1 - slot] = (uint16_t)lo;
+                sm.big_s[slot] = (uint16_t)p;
+                sm.big_e[slot] = (uint16_t)lo;
             }
         }
     }
-    __syncthreads();
+    const bool nonan = __syncthreads_and(clean ? 1 : 0) != 0;
+    DET_MARK(7);
+    // ---- phase 4a: tiny segments (<= 64 boxes, the common case of per-class NMS): every unordered pair of a segment
+    //      is tested exactly once with full lane utilisation -- row r meets row (r+d) mod m for d = 1..m/2 -- and a
+    //      hit sets one bit of the suppressor's u64 row; the greedy order is then resolved on the bit rows alone.
+    const int ntiny = sm.nseg_tiny;
+    if (ntiny) {
+        for (int sidx = tid; sidx < ntiny; sidx += kSmallThreads) {
+            const int s0 = (int)sm.seg_s[sidx], e0 = (int)sm.seg_e[sidx];
+            for (int q = s0; q < e0; ++q) {
+                sm.klist[q] = (uint16_t)s0;
+                sm.tiny_m[q] = (uint8_t)(e0 - s0);
+            }
+        }
+        __syncthreads();
+        DET_MARK(8);
+        for (int p = tid; p < cnt; p += kSmallThreads) {
+            const int m = (int)sm.tiny_m[p];
+            if (m < 2) continue;
+            const int s0 = (int)sm.klist[p], r = p - s0, half = m >> 1;
+            // distance-m/2 pairs (even m) are met from the lower half only
+            const int dmax = (((m & 1) == 0) && r >= half) ? half - 1 : half;
+            const float4 mb = sm.sbox[p];
+            const float ma = sm.sarea[p];
+            const float4* sb = sm.sbox + s0;
+            const float* sa = sm.sarea + s0;
+            unsigned long long* rows = reinterpret_cast<unsigned long long*>(sm.rowmask + s0);
+#pragma unroll 4
+            for (int d = 1; d <= dmax; ++d) {
+                int j = r + d;
+                j = (j >= m) ? j - m : j;
+                const float4 ob = sb[j];
+                const float oa = sa[j];
+                const bool fwd = j > r;  // the earlier box of the pair is the potential suppressor
+                const float4 ka = fwd ? mb : ob, kb = fwd ? ob : mb;
+                const float kaa = fwd ? ma : oa, kba = fwd ? oa : ma;
+                const bool hit = nonan ? nms_suppresses<true>(ka, kaa, kb, kba, thr_f)
+                                       : nms_suppresses<false>(ka, kaa, kb, kba, thr_f);
+                if (hit) atomicOr(rows + (fwd ? r : j), 1ull << (fwd ? j : r));
+            }
+        }
+        __syncthreads();
+        DET_MARK(9);
+        // resolution: only boxes whose row is non-zero can change the survivor set, so the greedy sweep visits just
+        // those (in order); the survivor mask of the segment is left in the row slot of its first box.
+        int tkept = 0;
+        for (int sidx = tid; sidx < ntiny; sidx += kSmallThreads) {
+            const int s0 = (int)sm.seg_s[sidx], m = (int)sm.seg_e[sidx] - s0;
+            uint64_t alive = (m >= 64) ? ~0ull : ((1ull << m) - 1ull);
+            uint64_t nz = 0;
+            for (int r = 0; r < m; ++r) nz |= (sm.rowmask[s0 + r] != 0ull) ? (1ull << r) : 0ull;
+            while (nz) {
+                const int r = __ffsll((long long)nz) - 1;
+                nz &= nz - 1;
+                if ((alive >> r) & 1ull) alive &= ~sm.rowmask[s0 + r];
+            }
+            int nk = __popcll(alive);
+            while (nk > max_out) {  // keep only the first max_out survivors: drop the highest set bits
+                alive &= ~(1ull << (63 - __clzll((long long)alive)));
+                --nk;
+            }
+            sm.rowmask[s0] = alive;
+            tkept += nk;
+        }
+        tkept = warp_sum(tkept);
+        if (lane == 0 && tkept) atomicAdd(&sm.nkept, tkept);
+        __syncthreads();
+    }
+    DET_MARK(10);
     // ---- phase 4: greedy suppression. short segments: one warp each, in parallel; long ones: whole CTA
     const int nsmall = sm.nseg_small, nlarge = sm.nseg_large;
     int mykept = 0;
-    for (int sidx = wid; sidx < nsmall; sidx += W)
-        mykept += warp_segment_nms<uint16_t>(sm.sbox, sm.sarea, sm.state, sm.klist, (int)sm.seg_s[sidx],
-                                             (int)sm.seg_e[sidx], thr_f, max_out);
+    for (int sidx = wid; sidx < nsmall; sidx += W) {
+        const int s0 = (int)sm.mid_s[sidx], e0 = (int)sm.mid_e[sidx];
+        mykept += nonan ? warp_segment_nms<uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0, thr_f, max_out)
+                        : warp_segment_nms<uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0, thr_f, max_out);
+    }
     if (lane == 0 && mykept) atomicAdd(&sm.nkept, mykept);
     __syncthreads();
     for (int sidx = 0; sidx < nlarge; ++sidx) {
-        const int nk = cta_segment_nms<kSmallThreads, uint16_t>(sm.sbox, sm.sarea, sm.state, sm.klist,
-                                                                (int)sm.seg_s[CAP - 1 - sidx],
-                                                                (int)sm.seg_e[CAP - 1 - sidx], thr_f, max_out,
-                                                                sm.rowbits, sm.amask, &sm.nk_scratch);
+        const int s0 = (int)sm.big_s[sidx], e0 = (int)sm.big_e[sidx];
+        const int nk = nonan ? cta_segment_nms<kSmallThreads, uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0,
+                                                                              e0, thr_f, max_out, sm.rowbits, sm.amask,
+                                                                              &sm.nk_scratch)
+                             : cta_segment_nms<kSmallThreads, uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0,
+                                                                               e0, thr_f, max_out, sm.rowbits, sm.amask,
+                                                                               &sm.nk_scratch);
         if (tid == 0) sm.nkept += nk;
         __syncthreads();
     }
     const int kept = sm.nkept;
+    DET_MARK(11);
     // ---- phase 5: output order = (descending score, index) over the kept candidates
     for (int p = tid; p < npad; p += kSmallThreads) {
         uint64_t k = kSentinelKey;
-        if (p < cnt && sm.state[p] == 2) k = KL::strip_seg(sm.keys[p]);
+        if (p < cnt) {
+            const int m = (int)sm.tiny_m[p];
+            bool is_kept;
+            if (m) {
+                const int s0 = (int)sm.klist[p];
+                is_kept = (sm.rowmask[s0] >> (p - s0)) & 1ull;
+            } else {
+                is_kept = sm.state[p] == 2;
+            }
+            if (is_kept) k = KL::strip_seg(sm.keys[p]);
+        }
         sm.keys[p] = k;
     }
     __syncthreads();
+    DET_MARK(12);
     cta_bitonic_sort<kSmallThreads>(sm.keys, npad);
+    DET_MARK(13);
     return sm.bad_cat ? -1 : kept;
 }
 

@@ -55,6 +55,7 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int img = blockIdx.x;
 
+    DET_MARK(0);
     // ---- stage this image's logits: 16-byte coalesced loads over the aligned interior of its span
     const int64_t g0 = (int64_t)img * S2 * ch, g1 = g0 + (int64_t)S2 * ch;
     const float4* head4 = reinterpret_cast<const float4*>(head);
@@ -70,6 +71,7 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
         }
     }
     __syncthreads();
+    DET_MARK(1);
     // ---- decode: boxes + confidences per predictor, class probabilities per cell (in place over the logits)
     for (int p = tid; p < P; p += kSmallThreads) {
         const int cell = p / B, bi = p - cell * B;
@@ -99,6 +101,7 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
         *q = sigmoidf_ref(*q);
     }
     __syncthreads();
+    DET_MARK(2);
     // ---- scores, threshold, order-preserving compaction (each thread owns a contiguous run of flat ids)
     const int per = (PC + kSmallThreads - 1) / kSmallThreads;
     const int f0 = min(tid * per, PC), f1 = min(f0 + per, PC);
@@ -134,6 +137,7 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
         }
     }
     __syncthreads();
+    DET_MARK(3);
     // ---- per-class NMS in shared memory
     const int cap_out = (int)min(prm.max_det, (int64_t)CAP);
     const YoloCandidates src{pbox, cscore, cflat, C};
@@ -149,6 +153,7 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
         if (det_scores) det_scores[o] = cscore[i];
     }
     if (tid == 0) det_count[img] = nout;
+    DET_MARK(15);
 }
 
 template <int CAP>
@@ -246,6 +251,12 @@ dense_decode_level_kernel(const float* __restrict__ head, int a, int c, int h, i
 }  // namespace det
 
 using namespace det;
+
+#ifdef DET_DEBUG_PHASES
+extern "C" __attribute__((visibility("default"))) int det_debug_read_phases(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, det::g_phase_clock, sizeof(long long) * 32) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 extern "C" {
 
