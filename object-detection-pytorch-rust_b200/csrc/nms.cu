@@ -13,13 +13,15 @@
 
 namespace det {
 
+constexpr int kSmallThreads = 256;
+
 template <int CAP>
 __global__ void __launch_bounds__(kSmallThreads)
 nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
                  const int64_t* __restrict__ cats, const int32_t* __restrict__ counts, int64_t m_max, float thr_f,
                  int mode, int64_t max_out, int64_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmallSmem<CAP>& sm = *reinterpret_cast<SmallSmem<CAP>*>(smem_raw);
+    SmallSmem<CAP, kSmallThreads>& sm = *reinterpret_cast<SmallSmem<CAP, kSmallThreads>*>(smem_raw);
     using KL = KeyLayout<kSmallIdxBits>;
     const int img = blockIdx.x;
     int cnt = counts ? counts[img] : (int)m_max;
@@ -27,7 +29,7 @@ nms_small_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     const int cap_out = (int)min(max_out, (int64_t)CAP);
     const GlobalCandidates src{boxes + (int64_t)img * m_max, scores + (int64_t)img * m_max,
                                cats ? cats + (int64_t)img * m_max : nullptr};
-    const int kept = small_nms_body<CAP>(sm, src, cnt, thr_f, mode, cap_out);
+    const int kept = small_nms_body<CAP, kSmallThreads>(sm, src, cnt, thr_f, mode, cap_out);
     const int nout = kept < 0 ? 0 : min(kept, cap_out);
     for (int j = threadIdx.x; j < nout; j += kSmallThreads)
         keep[(int64_t)img * max_out + j] = (int64_t)KL::idx(sm.keys[j]);
@@ -38,7 +40,7 @@ template <int CAP>
 static int launch_small(const float* boxes, const float* scores, const int64_t* cats, const int32_t* counts, int n,
                         int64_t m_max, float thr_f, int mode, int64_t max_out, int64_t* keep, int32_t* keep_counts,
                         cudaStream_t st) {
-    const size_t smem = sizeof(SmallSmem<CAP>);
+    const size_t smem = sizeof(SmallSmem<CAP, kSmallThreads>);
     cudaError_t e = cudaFuncSetAttribute(nms_small_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nms_small_kernel)");
     nms_small_kernel<CAP><<<n, kSmallThreads, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, cats,

@@ -181,7 +181,8 @@ __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t*
     return nk;
 }
 
-// ---- greedy suppression of one segment [s,e) by a WHOLE CTA of T threads ----------------------------
+// ---- greedy suppression of one segment [s,e) by a WHOLE CTA, in chunks of T boxes ---------------------
+// The CTA may have more than T threads: threads >= T only take part in the barriers.
 // scratch: rowbits[T * T/32], amask[T/32], s_nk[1] in shared memory.
 template <int T, typename KT, bool NONAN>
 __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* state, KT* klist, int s, int e,
@@ -190,9 +191,10 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int nk = 0;
+    const bool worker = tid < T;
     for (int base = s; base < e && nk < max_keep; base += T) {
         const int p = base + tid;
-        const bool act = (p < e) && (state[p] == 0);
+        const bool act = worker && (p < e) && (state[p] == 0);
         float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
         float ma = 0.f;
         if (act) {
@@ -209,7 +211,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             if (alive && nms_suppresses<NONAN>(kb, ka, mb, ma, thr_f)) alive = false;
         }
         const unsigned bal = __ballot_sync(FULL, alive);
-        if (lane == 0) amask[wid] = bal;
+        if (worker && lane == 0) amask[wid] = bal;
         __syncthreads();
         // (b) bit row of this candidate as suppressor of the later survivors of the chunk
         if (alive) {

@@ -1,36 +1,45 @@
 // Small path of the batched NMS: one CTA per image, everything (keys, sorted boxes, kept lists) in shared memory.
 // Shared by nms.cu (generic boxes from HBM) and yolo.cu (candidates produced in shared memory by the decode).
+//
+// Phases (T threads, up to CAP candidates):
+//   0  coordinate statistics for torchvision's offset trick (only when the image takes that branch)
+//   1  keys (category | descending score | index), 2  register-resident bitonic sort
+//   3  gather boxes into sorted order, discover category segments with an ordered block scan
+//   4a tiny segments (<= 64 boxes): every pair once -> u64 suppression rows -> sparse greedy resolution
+//   4b mid segments (<= 192): one warp each; 4c long segments: whole CTA (nms_core.cuh)
+//   5  re-key the kept boxes by (descending score | index) and sort again -> output order
 #pragma once
 #include "nms_core.cuh"
 
 namespace det {
 
-constexpr int kSmallThreads = 256;
 constexpr int kSmallIdxBits = 12;
-constexpr int kTinySegMax = 64;   // segments up to this length: full pair bit-matrix (one u64 row per box)
-constexpr int kWarpSegMax = 192;  // segments up to this length are swept by a single warp (warps run in parallel)
+constexpr int kTinySegMax = 64;   // full pair bit-matrix (one u64 row per box)
+constexpr int kWarpSegMax = 192;  // swept by a single warp (warps run in parallel)
+constexpr int kCtaChunk = 256;    // chunk width of the CTA-wide sweep
 
-template <int CAP>
+template <int CAP, int T>
 struct SmallSmem {
     uint64_t keys[CAP];
     float4 sbox[CAP];
     float sarea[CAP];
-    uint16_t klist[CAP];
-    uint16_t seg_s[CAP];  // tiny segments (at most one per box)
+    uint16_t klist[CAP];  // mid/long segments: kept positions; tiny segments: start position of the box's segment
+    uint16_t seg_s[CAP];  // all segments, in order (at most one per box)
     uint16_t seg_e[CAP];
-    uint16_t mid_s[CAP / kTinySegMax], mid_e[CAP / kTinySegMax];    // warp-swept segments (each > 64 boxes)
-    uint16_t big_s[CAP / kWarpSegMax + 1], big_e[CAP / kWarpSegMax + 1];  // CTA-swept segments (each > 192 boxes)
+    uint16_t mid_s[CAP / kTinySegMax], mid_e[CAP / kTinySegMax];
+    uint16_t big_s[CAP / kWarpSegMax + 1], big_e[CAP / kWarpSegMax + 1];
     uint8_t state[CAP];
     uint8_t tiny_m[CAP];  // length of the tiny segment a position belongs to (0: not in a tiny segment)
     union {               // the tiny phase finishes before the CTA-wide phase starts
         uint64_t rowmask[CAP];
-        uint32_t rowbits[kSmallThreads * (kSmallThreads / 32)];
+        uint32_t rowbits[kCtaChunk * (kCtaChunk / 32)];
     };
-    uint32_t amask[kSmallThreads / 32];
-    float red_max[kSmallThreads / 32];
-    float red_min[kSmallThreads / 32];
-    int red_flag[kSmallThreads / 32];
-    int nseg_tiny, nseg_small, nseg_large, nk_scratch, nkept, bad_cat;
+    uint32_t amask[kCtaChunk / 32];
+    float red_max[T / 32];
+    float red_min[T / 32];
+    int red_flag[T / 32];
+    int warp_heads[T / 32];
+    int nseg_small, nseg_large, nk_scratch, nkept, bad_cat;
     float span;
     int fast;
 };
@@ -45,18 +54,17 @@ struct GlobalCandidates {
     __device__ __forceinline__ int64_t cat(int i) const { return cats ? cats[i] : 0; }
 };
 
-// Greedy category-partitioned NMS of `cnt` (<= CAP) candidates by one CTA of kSmallThreads threads.
+// Greedy category-partitioned NMS of `cnt` (<= CAP) candidates by one CTA of T threads.
 // Returns (block-uniform) the number of kept candidates, or -1 if a category is outside [0, 32767).
 // On return sm.keys[0 .. kept) hold (descending-score bits | candidate index) in output order.
-template <int CAP, typename Src>
-__device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float thr_f, int mode, int max_out) {
+template <int CAP, int T, typename Src>
+__device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, float thr_f, int mode, int max_out) {
     using KL = KeyLayout<kSmallIdxBits>;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int W = kSmallThreads / 32;
+    constexpr int W = T / 32;
     // reference CPU rule: boxes.numel() <= 4000 -> coordinate-offset trick (torchvision/ops/boxes.py batched_nms)
     const bool trick = (mode == DET_NMS_AUTO) ? (cnt <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
     if (tid == 0) {
-        sm.nseg_tiny = 0;
         sm.nseg_small = 0;
         sm.nseg_large = 0;
         sm.nkept = 0;
@@ -69,7 +77,7 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
     if (trick) {
         float mx = -INFINITY, mn = INFINITY;
         int fin = 1, maxcat = 0;
-        for (int i = tid; i < cnt; i += kSmallThreads) {
+        for (int i = tid; i < cnt; i += T) {
             const float4 b = src.box(i);
             mx = max_nan(mx, max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w)));
             mn = min_nan(mn, min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w)));
@@ -111,7 +119,7 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
     const bool by_cat = !trick || sm.fast;
     // ---- phase 1+2: keys, sort
     const int npad = next_pow2(max(cnt, 2));
-    for (int i = tid; i < npad; i += kSmallThreads) {
+    for (int i = tid; i < npad; i += T) {
         uint64_t k = kSentinelKey;
         if (i < cnt) {
             const int64_t c = src.cat(i);
@@ -122,140 +130,172 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
     }
     __syncthreads();
     DET_MARK(5);
-    cta_bitonic_sort<kSmallThreads>(sm.keys, npad);
+    cta_bitonic_sort<T>(sm.keys, npad);
     DET_MARK(6);
-    // ---- phase 3: boxes in sorted order (+ offset), segment discovery
+    // ---- phase 3: boxes in sorted order (+ offset); segment heads numbered in order with a block scan, so every
+    //      segment learns its end from the next head (no search)
     bool clean = true;  // no NaN coordinate seen by this thread
-    for (int p = tid; p < cnt; p += kSmallThreads) {
-        const uint64_t k = sm.keys[p];
-        const int i = (int)KL::idx(k);
-        float4 b = src.box(i);
-        if (trick) {
-            const float off = (float)src.cat(i) * span;  // idxs.to(boxes) * (max_coordinate + 1)
-            b.x += off; b.y += off; b.z += off; b.w += off;
-        }
-        sm.sbox[p] = b;
-        sm.sarea[p] = box_area(b);
-        sm.state[p] = 0;
-        sm.tiny_m[p] = 0;
-        sm.rowmask[p] = 0ull;
-        clean &= (b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w);
-        const uint32_t sg = KL::seg(k);
-        if (p == 0 || KL::seg(sm.keys[p - 1]) != sg) {
-            int lo = p + 1, hi = cnt;  // segment end = first position with a larger segment field
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (KL::seg(sm.keys[mid]) > sg) hi = mid; else lo = mid + 1;
+    int heads_before = 0;
+    for (int p0 = 0; p0 < cnt; p0 += T) {
+        const int p = p0 + tid;
+        bool head = false;
+        if (p < cnt) {
+            const uint64_t k = sm.keys[p];
+            const int i = (int)KL::idx(k);
+            float4 b = src.box(i);
+            if (trick) {
+                const float off = (float)src.cat(i) * span;  // idxs.to(boxes) * (max_coordinate + 1)
+                b.x += off; b.y += off; b.z += off; b.w += off;
             }
-            if (lo - p <= kTinySegMax) {
-                const int slot = atomicAdd(&sm.nseg_tiny, 1);
-                sm.seg_s[slot] = (uint16_t)p;
-                sm.seg_e[slot] = (uint16_t)lo;
-            } else if (lo - p <= kWarpSegMax) {
-                const int slot = atomicAdd(&sm.nseg_small, 1);
-                sm.mid_s[slot] = (uint16_t)p;
-                sm.mid_e[slot] = (uint16_t)lo;
-            } else {
-                const int slot = atomicAdd(&sm.nseg_large, 1);
-                sm.big_s[slot] = (uint16_t)p;
-                sm.big_e[slot] = (uint16_t)lo;
-            }
+            sm.sbox[p] = b;
+            sm.sarea[p] = box_area(b);
+            sm.state[p] = 0;
+            sm.tiny_m[p] = 0;
+            sm.rowmask[p] = 0ull;
+            clean &= (b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w);
+            head = (p == 0) || (KL::seg(sm.keys[p - 1]) != KL::seg(k));
         }
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) sm.warp_heads[wid] = __popc(hb);
+        __syncthreads();
+        int before = heads_before, total = 0;
+        for (int w = 0; w < W; ++w) {
+            const int c = sm.warp_heads[w];
+            if (w < wid) before += c;
+            total += c;
+        }
+        if (head) {
+            const int slot = before + __popc(hb & ((1u << lane) - 1u));
+            sm.seg_s[slot] = (uint16_t)p;
+            if (slot > 0) sm.seg_e[slot - 1] = (uint16_t)p;
+        }
+        heads_before += total;
+        __syncthreads();
     }
+    const int nseg = heads_before;
+    if (tid == 0 && nseg > 0) sm.seg_e[nseg - 1] = (uint16_t)cnt;
     const bool nonan = __syncthreads_and(clean ? 1 : 0) != 0;
     DET_MARK(7);
-    // ---- phase 4a: tiny segments (<= 64 boxes, the common case of per-class NMS): every unordered pair of a segment
-    //      is tested exactly once with full lane utilisation -- row r meets row (r+d) mod m for d = 1..m/2 -- and a
-    //      hit sets one bit of the suppressor's u64 row; the greedy order is then resolved on the bit rows alone.
-    const int ntiny = sm.nseg_tiny;
-    if (ntiny) {
-        for (int sidx = tid; sidx < ntiny; sidx += kSmallThreads) {
-            const int s0 = (int)sm.seg_s[sidx], e0 = (int)sm.seg_e[sidx];
+    // classify: tiny segments are flagged through tiny_m, longer ones go to the mid/big work lists
+    for (int sidx = tid; sidx < nseg; sidx += T) {
+        const int s0 = (int)sm.seg_s[sidx], e0 = (int)sm.seg_e[sidx], m = e0 - s0;
+        if (m <= kTinySegMax) {
             for (int q = s0; q < e0; ++q) {
                 sm.klist[q] = (uint16_t)s0;
-                sm.tiny_m[q] = (uint8_t)(e0 - s0);
+                sm.tiny_m[q] = (uint8_t)m;
             }
+        } else if (m <= kWarpSegMax) {
+            const int slot = atomicAdd(&sm.nseg_small, 1);
+            sm.mid_s[slot] = (uint16_t)s0;
+            sm.mid_e[slot] = (uint16_t)e0;
+        } else {
+            const int slot = atomicAdd(&sm.nseg_large, 1);
+            sm.big_s[slot] = (uint16_t)s0;
+            sm.big_e[slot] = (uint16_t)e0;
         }
-        __syncthreads();
-        DET_MARK(8);
-        for (int p = tid; p < cnt; p += kSmallThreads) {
-            const int m = (int)sm.tiny_m[p];
-            if (m < 2) continue;
-            const int s0 = (int)sm.klist[p], r = p - s0, half = m >> 1;
-            // distance-m/2 pairs (even m) are met from the lower half only
-            const int dmax = (((m & 1) == 0) && r >= half) ? half - 1 : half;
-            const float4 mb = sm.sbox[p];
-            const float ma = sm.sarea[p];
-            const float4* sb = sm.sbox + s0;
-            const float* sa = sm.sarea + s0;
-            unsigned long long* rows = reinterpret_cast<unsigned long long*>(sm.rowmask + s0);
-#pragma unroll 4
-            for (int d = 1; d <= dmax; ++d) {
-                int j = r + d;
-                j = (j >= m) ? j - m : j;
-                const float4 ob = sb[j];
-                const float oa = sa[j];
-                const bool fwd = j > r;  // the earlier box of the pair is the potential suppressor
-                const float4 ka = fwd ? mb : ob, kb = fwd ? ob : mb;
-                const float kaa = fwd ? ma : oa, kba = fwd ? oa : ma;
-                const bool hit = nonan ? nms_suppresses<true>(ka, kaa, kb, kba, thr_f)
-                                       : nms_suppresses<false>(ka, kaa, kb, kba, thr_f);
-                if (hit) atomicOr(rows + (fwd ? r : j), 1ull << (fwd ? j : r));
-            }
-        }
-        __syncthreads();
-        DET_MARK(9);
-        // resolution: only boxes whose row is non-zero can change the survivor set, so the greedy sweep visits just
-        // those (in order); the survivor mask of the segment is left in the row slot of its first box.
-        int tkept = 0;
-        for (int sidx = tid; sidx < ntiny; sidx += kSmallThreads) {
-            const int s0 = (int)sm.seg_s[sidx], m = (int)sm.seg_e[sidx] - s0;
-            uint64_t alive = (m >= 64) ? ~0ull : ((1ull << m) - 1ull);
-            uint64_t nz = 0;
-            for (int r = 0; r < m; ++r) nz |= (sm.rowmask[s0 + r] != 0ull) ? (1ull << r) : 0ull;
-            while (nz) {
-                const int r = __ffsll((long long)nz) - 1;
-                nz &= nz - 1;
-                if ((alive >> r) & 1ull) alive &= ~sm.rowmask[s0 + r];
-            }
-            int nk = __popcll(alive);
-            while (nk > max_out) {  // keep only the first max_out survivors: drop the highest set bits
-                alive &= ~(1ull << (63 - __clzll((long long)alive)));
-                --nk;
-            }
-            sm.rowmask[s0] = alive;
-            tkept += nk;
-        }
-        tkept = warp_sum(tkept);
-        if (lane == 0 && tkept) atomicAdd(&sm.nkept, tkept);
-        __syncthreads();
     }
-    DET_MARK(10);
-    // ---- phase 4: greedy suppression. short segments: one warp each, in parallel; long ones: whole CTA
-    const int nsmall = sm.nseg_small, nlarge = sm.nseg_large;
-    int mykept = 0;
-    for (int sidx = wid; sidx < nsmall; sidx += W) {
-        const int s0 = (int)sm.mid_s[sidx], e0 = (int)sm.mid_e[sidx];
-        mykept += nonan ? warp_segment_nms<uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0, thr_f, max_out)
-                        : warp_segment_nms<uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0, thr_f, max_out);
-    }
-    if (lane == 0 && mykept) atomicAdd(&sm.nkept, mykept);
     __syncthreads();
+    DET_MARK(8);
+    // ---- phase 4a: tiny segments (the common case of per-class NMS): every unordered pair of a segment is tested
+    //      exactly once with full lane utilisation -- row r meets row (r+d) mod m for d = 1..m/2 -- and a hit sets one
+    //      bit of the earlier box's u64 row; the greedy order is then resolved on the bit rows alone.
+    for (int p = tid; p < cnt; p += T) {
+        const int m = (int)sm.tiny_m[p];
+        if (m < 2) continue;
+        const int s0 = (int)sm.klist[p], r = p - s0, half = m >> 1;
+        // distance-m/2 pairs (even m) are met from the lower half only
+        const int dmax = (((m & 1) == 0) && r >= half) ? half - 1 : half;
+        const float4 mb = sm.sbox[p];
+        const float ma = sm.sarea[p];
+        const float4* sb = sm.sbox + s0;
+        const float* sa = sm.sarea + s0;
+        unsigned long long* rows = reinterpret_cast<unsigned long long*>(sm.rowmask + s0);
+#pragma unroll 4
+        for (int d = 1; d <= dmax; ++d) {
+            int j = r + d;
+            j = (j >= m) ? j - m : j;
+            const float4 ob = sb[j];
+            const float oa = sa[j];
+            const bool fwd = j > r;  // the earlier box of the pair is the potential suppressor
+            const float4 ka = fwd ? mb : ob, kb = fwd ? ob : mb;
+            const float kaa = fwd ? ma : oa, kba = fwd ? oa : ma;
+            const bool hit = nonan ? nms_suppresses<true>(ka, kaa, kb, kba, thr_f)
+                                   : nms_suppresses<false>(ka, kaa, kb, kba, thr_f);
+            if (hit) {
+                const int lo_r = fwd ? r : j, hi_r = fwd ? j : r;
+                atomicOr(rows + lo_r, 1ull << hi_r);
+                // the last row of a segment is always empty (nothing comes after it): its slot collects the set of
+                // non-empty rows, which is all the resolution step has to visit
+                if (lo_r != m - 1) atomicOr(rows + (m - 1), 1ull << lo_r);
+            }
+        }
+    }
+    __syncthreads();
+    DET_MARK(9);
+    // resolution: only boxes whose row is non-zero can change the survivor set, so the greedy sweep visits just
+    // those (in order); the survivor mask of the segment is left in the row slot of its first box.
+    int tkept = 0;
+    for (int sidx = tid; sidx < nseg; sidx += T) {
+        const int s0 = (int)sm.seg_s[sidx], m = (int)sm.seg_e[sidx] - s0;
+        if (m > kTinySegMax) continue;
+        uint64_t alive = (m >= 64) ? ~0ull : ((1ull << m) - 1ull);
+        uint64_t nz = sm.rowmask[s0 + m - 1];
+        while (nz) {
+            const int r = __ffsll((long long)nz) - 1;
+            nz &= nz - 1;
+            if ((alive >> r) & 1ull) alive &= ~sm.rowmask[s0 + r];
+        }
+        int nk = __popcll(alive);
+        while (nk > max_out) {  // keep only the first max_out survivors: drop the highest set bits
+            alive &= ~(1ull << (63 - __clzll((long long)alive)));
+            --nk;
+        }
+        sm.rowmask[s0] = alive;
+        tkept += nk;
+    }
+    tkept = warp_sum(tkept);
+    if (lane == 0 && tkept) atomicAdd(&sm.nkept, tkept);
+    __syncthreads();
+    DET_MARK(10);
+    // ---- phase 4b/4c: mid segments one warp each (in parallel), long ones by the whole CTA
+    const int nsmall = sm.nseg_small, nlarge = sm.nseg_large;
+    if (nsmall) {
+        int mykept = 0;
+        for (int sidx = wid; sidx < nsmall; sidx += W) {
+            const int s0 = (int)sm.mid_s[sidx], e0 = (int)sm.mid_e[sidx];
+            mykept += nonan ? warp_segment_nms<uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0, thr_f, max_out)
+                            : warp_segment_nms<uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0, thr_f, max_out);
+        }
+        if (lane == 0 && mykept) atomicAdd(&sm.nkept, mykept);
+        __syncthreads();
+    }
+    if (nlarge) {  // the CTA-wide sweep reuses the row-mask storage: move the tiny segments' survivors into state[]
+        for (int p = tid; p < cnt; p += T) {
+            const int m = (int)sm.tiny_m[p];
+            if (m) {
+                const int s0 = (int)sm.klist[p];
+                sm.state[p] = ((sm.rowmask[s0] >> (p - s0)) & 1ull) ? 2 : 0;
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < cnt; p += T) sm.tiny_m[p] = 0;
+        __syncthreads();
+    }
     for (int sidx = 0; sidx < nlarge; ++sidx) {
         const int s0 = (int)sm.big_s[sidx], e0 = (int)sm.big_e[sidx];
-        const int nk = nonan ? cta_segment_nms<kSmallThreads, uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0,
-                                                                              e0, thr_f, max_out, sm.rowbits, sm.amask,
-                                                                              &sm.nk_scratch)
-                             : cta_segment_nms<kSmallThreads, uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0,
-                                                                               e0, thr_f, max_out, sm.rowbits, sm.amask,
-                                                                               &sm.nk_scratch);
+        const int nk = nonan ? cta_segment_nms<kCtaChunk, uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0,
+                                                                          thr_f, max_out, sm.rowbits, sm.amask,
+                                                                          &sm.nk_scratch)
+                             : cta_segment_nms<kCtaChunk, uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0,
+                                                                           thr_f, max_out, sm.rowbits, sm.amask,
+                                                                           &sm.nk_scratch);
         if (tid == 0) sm.nkept += nk;
         __syncthreads();
     }
     const int kept = sm.nkept;
     DET_MARK(11);
     // ---- phase 5: output order = (descending score, index) over the kept candidates
-    for (int p = tid; p < npad; p += kSmallThreads) {
+    for (int p = tid; p < npad; p += T) {
         uint64_t k = kSentinelKey;
         if (p < cnt) {
             const int m = (int)sm.tiny_m[p];
@@ -272,7 +312,7 @@ __device__ int small_nms_body(SmallSmem<CAP>& sm, const Src& src, int cnt, float
     }
     __syncthreads();
     DET_MARK(12);
-    cta_bitonic_sort<kSmallThreads>(sm.keys, npad);
+    cta_bitonic_sort<T>(sm.keys, npad);
     DET_MARK(13);
     return sm.bad_cat ? -1 : kept;
 }

@@ -16,14 +16,14 @@ namespace det {
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// candidates live in shared memory as (predictor << 16 | class) + score; boxes are looked up per predictor
 struct YoloCandidates {
     const float4* pbox;
     const float* cscore;
-    const uint16_t* cflat;
-    int C;
-    __device__ __forceinline__ float4 box(int i) const { return pbox[cflat[i] / C]; }
+    const uint32_t* cpc;
+    __device__ __forceinline__ float4 box(int i) const { return pbox[cpc[i] >> 16]; }
     __device__ __forceinline__ float score(int i) const { return cscore[i]; }
-    __device__ __forceinline__ int64_t cat(int i) const { return (int64_t)(cflat[i] % C); }
+    __device__ __forceinline__ int64_t cat(int i) const { return (int64_t)(cpc[i] & 0xffffu); }
 };
 
 struct YoloParams {
@@ -33,25 +33,28 @@ struct YoloParams {
     int64_t max_det;
 };
 
+constexpr int kYoloThreads = 512;
 constexpr int kYoloMaxPred = 1024;
 constexpr int kYoloMaxHead = 6144;
 
 template <int CAP>
-__global__ void __launch_bounds__(kSmallThreads)
+__global__ void __launch_bounds__(kYoloThreads, 2)
 yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict__ priors, YoloParams prm,
                        float4* __restrict__ dense_boxes, float* __restrict__ dense_conf,
                        float* __restrict__ dense_scores, int64_t* __restrict__ det_flat,
                        float4* __restrict__ det_boxes, float* __restrict__ det_scores,
                        int32_t* __restrict__ det_count) {
+    constexpr int T = kYoloThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmallSmem<CAP>& sm = *reinterpret_cast<SmallSmem<CAP>*>(smem_raw);
-    unsigned char* extra = smem_raw + ((sizeof(SmallSmem<CAP>) + 15) / 16) * 16;
+    using Smem = SmallSmem<CAP, T>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    unsigned char* extra = smem_raw + ((sizeof(Smem) + 15) / 16) * 16;
     const int S2 = prm.s * prm.s, B = prm.b, C = prm.c, ch = B * 5 + C, P = S2 * B, PC = P * C;
     float4* pbox = reinterpret_cast<float4*>(extra);
     float* cscore = reinterpret_cast<float*>(pbox + P);
     float* hs = cscore + CAP;
-    uint16_t* cflat = reinterpret_cast<uint16_t*>(hs + ((S2 * ch + 3) & ~3));
-    __shared__ int s_warp_tot[kSmallThreads / 32];
+    uint32_t* cpc = reinterpret_cast<uint32_t*>(hs + ((S2 * ch + 3) & ~3));
+    __shared__ int s_warp_tot[T / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int img = blockIdx.x;
 
@@ -59,7 +62,7 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
     // ---- stage this image's logits: 16-byte coalesced loads over the aligned interior of its span
     const int64_t g0 = (int64_t)img * S2 * ch, g1 = g0 + (int64_t)S2 * ch;
     const float4* head4 = reinterpret_cast<const float4*>(head);
-    for (int64_t v = (g0 >> 2) + tid; v < ((g1 + 3) >> 2); v += kSmallThreads) {
+    for (int64_t v = (g0 >> 2) + tid; v < ((g1 + 3) >> 2); v += T) {
         const int64_t base = v << 2;
         if (base >= g0 && base + 4 <= g1) {
             const float4 q = ld_stream(head4 + v);
@@ -72,46 +75,62 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
     }
     __syncthreads();
     DET_MARK(1);
-    // ---- decode: boxes + confidences per predictor, class probabilities per cell (in place over the logits)
-    for (int p = tid; p < P; p += kSmallThreads) {
+    // ---- transcendentals in place, one logit per thread: sigmoid for x, y, conf and the class logits, exp for w, h
+    for (int i = tid; i < S2 * ch; i += T) {
+        const int k = i % ch;
+        const float x = hs[i];
+        float y;
+        if (k < B * 5) {
+            const int comp = k % 5;
+            if (comp == 2 || comp == 3) {
+                const float cl = (x > prm.scale_clamp) ? prm.scale_clamp : x;  // torch.clamp(max=): NaN stays NaN
+                y = expf(cl);
+            } else {
+                y = sigmoidf_ref(x);
+            }
+        } else {
+            y = sigmoidf_ref(x);
+        }
+        hs[i] = y;
+    }
+    __syncthreads();
+    // ---- boxes per predictor
+    for (int p = tid; p < P; p += T) {
         const int cell = p / B, bi = p - cell * B;
         const int row = cell / prm.s, col = cell - row * prm.s;
-        float* t = hs + cell * ch + bi * 5;
+        const float* t = hs + cell * ch + bi * 5;
         const float2 pr = priors[bi];
-        const float cx = (sigmoidf_ref(t[0]) + (float)col) * prm.stride_x;
-        const float cy = (sigmoidf_ref(t[1]) + (float)row) * prm.stride_y;
-        float tw = t[2], th = t[3];
-        tw = (tw > prm.scale_clamp) ? prm.scale_clamp : tw;
-        th = (th > prm.scale_clamp) ? prm.scale_clamp : th;
-        const float w = expf(tw) * pr.x, h = expf(th) * pr.y;
+        const float cx = (t[0] + (float)col) * prm.stride_x;
+        const float cy = (t[1] + (float)row) * prm.stride_y;
+        const float w = t[2] * pr.x, h = t[3] * pr.y;
         float4 bx = make_float4(cx - 0.5f * w, cy - 0.5f * h, cx + 0.5f * w, cy + 0.5f * h);
         if (prm.clip) {  // torch clamp(min=0,max=W): NaN stays NaN
             bx.x = min_nan(max_nan(bx.x, 0.f), prm.img_w); bx.z = min_nan(max_nan(bx.z, 0.f), prm.img_w);
             bx.y = min_nan(max_nan(bx.y, 0.f), prm.img_h); bx.w = min_nan(max_nan(bx.w, 0.f), prm.img_h);
         }
         pbox[p] = bx;
-        const float conf = sigmoidf_ref(t[4]);
-        t[4] = conf;
         if (dense_boxes) dense_boxes[(int64_t)img * P + p] = bx;
-        if (dense_conf) dense_conf[(int64_t)img * P + p] = conf;
+        if (dense_conf) dense_conf[(int64_t)img * P + p] = t[4];
     }
-    for (int i = tid; i < S2 * C; i += kSmallThreads) {
-        const int cell = i / C, ci = i - cell * C;
-        float* q = hs + cell * ch + B * 5 + ci;
-        *q = sigmoidf_ref(*q);
-    }
-    __syncthreads();
     DET_MARK(2);
-    // ---- scores, threshold, order-preserving compaction (each thread owns a contiguous run of flat ids)
-    const int per = (PC + kSmallThreads - 1) / kSmallThreads;
+    // ---- scores, threshold, order-preserving compaction: each thread owns a contiguous run of flat ids
+    //      (predictor-major, class-minor) and walks it incrementally
+    const int per = (PC + T - 1) / T;
     const int f0 = min(tid * per, PC), f1 = min(f0 + per, PC);
+    const int p_start = f0 / C, c_start = f0 - p_start * C;
     int mine = 0;
-    for (int f = f0; f < f1; ++f) {
-        const int p = f / C, ci = f - p * C;
-        const int cell = p / B, bi = p - cell * B;
-        const float sc = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + ci];
-        mine += (sc > prm.score_thresh) ? 1 : 0;
-        if (dense_scores) dense_scores[(int64_t)img * PC + f] = sc;
+    {
+        int p = p_start, ci = c_start, cell = p / B, bi = p - cell * B;
+        for (int f = f0; f < f1; ++f) {
+            const float sc = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + ci];
+            mine += (sc > prm.score_thresh) ? 1 : 0;
+            if (dense_scores) dense_scores[(int64_t)img * PC + f] = sc;
+            if (++ci == C) {
+                ci = 0;
+                ++p;
+                if (++bi == B) { bi = 0; ++cell; }
+            }
+        }
     }
     int incl = mine;
     for (int o = 1; o < 32; o <<= 1) {
@@ -119,37 +138,43 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
         if (lane >= o) incl += v;
     }
     if (lane == 31) s_warp_tot[wid] = incl;
-    __syncthreads();
+    __syncthreads();  // also orders the pbox writes before the NMS reads
     int offset = incl - mine, cnt = 0;
-    for (int w = 0; w < kSmallThreads / 32; ++w) {
+    for (int w = 0; w < T / 32; ++w) {
         const int tot = s_warp_tot[w];
         if (w < wid) offset += tot;
         cnt += tot;
     }
-    for (int f = f0; f < f1; ++f) {
-        const int p = f / C, ci = f - p * C;
-        const int cell = p / B, bi = p - cell * B;
-        const float sc = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + ci];
-        if (sc > prm.score_thresh) {
-            cflat[offset] = (uint16_t)f;
-            cscore[offset] = sc;
-            ++offset;
+    {
+        int p = p_start, ci = c_start, cell = p / B, bi = p - cell * B;
+        for (int f = f0; f < f1; ++f) {
+            const float sc = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + ci];
+            if (sc > prm.score_thresh) {
+                cpc[offset] = ((uint32_t)p << 16) | (uint32_t)ci;
+                cscore[offset] = sc;
+                ++offset;
+            }
+            if (++ci == C) {
+                ci = 0;
+                ++p;
+                if (++bi == B) { bi = 0; ++cell; }
+            }
         }
     }
     __syncthreads();
     DET_MARK(3);
     // ---- per-class NMS in shared memory
     const int cap_out = (int)min(prm.max_det, (int64_t)CAP);
-    const YoloCandidates src{pbox, cscore, cflat, C};
-    const int kept = small_nms_body<CAP>(sm, src, cnt, prm.thr_f, prm.mode, cap_out);
+    const YoloCandidates src{pbox, cscore, cpc};
+    const int kept = small_nms_body<CAP, T>(sm, src, cnt, prm.thr_f, prm.mode, cap_out);
     const int nout = kept < 0 ? 0 : min(kept, cap_out);
     using KL = KeyLayout<kSmallIdxBits>;
-    for (int j = tid; j < nout; j += kSmallThreads) {
+    for (int j = tid; j < nout; j += T) {
         const int i = (int)KL::idx(sm.keys[j]);
-        const int f = cflat[i];
+        const uint32_t pc = cpc[i];
         const int64_t o = (int64_t)img * prm.max_det + j;
-        det_flat[o] = f;
-        if (det_boxes) det_boxes[o] = pbox[f / C];
+        det_flat[o] = (int64_t)(pc >> 16) * C + (int64_t)(pc & 0xffffu);
+        if (det_boxes) det_boxes[o] = pbox[pc >> 16];
         if (det_scores) det_scores[o] = cscore[i];
     }
     if (tid == 0) det_count[img] = nout;
@@ -161,11 +186,11 @@ static int launch_yolo(const float* head, const float* priors, const YoloParams&
                        float* dense_conf, float* dense_scores, int64_t* det_flat, float* det_boxes, float* det_scores,
                        int32_t* det_count, cudaStream_t st) {
     const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c, P = S2 * prm.b;
-    size_t smem = ((sizeof(SmallSmem<CAP>) + 15) / 16) * 16;
-    smem += sizeof(float4) * P + sizeof(float) * CAP + sizeof(float) * ((S2 * ch + 3) & ~3) + sizeof(uint16_t) * CAP;
+    size_t smem = ((sizeof(SmallSmem<CAP, kYoloThreads>) + 15) / 16) * 16;
+    smem += sizeof(float4) * P + sizeof(float) * CAP + sizeof(float) * ((S2 * ch + 3) & ~3) + sizeof(uint32_t) * CAP;
     cudaError_t e = cudaFuncSetAttribute(yolo_decode_nms_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(yolo_decode_nms_kernel)");
-    yolo_decode_nms_kernel<CAP><<<prm.n, kSmallThreads, smem, st>>>(
+    yolo_decode_nms_kernel<CAP><<<prm.n, kYoloThreads, smem, st>>>(
         head, reinterpret_cast<const float2*>(priors), prm, reinterpret_cast<float4*>(dense_boxes), dense_conf,
         dense_scores, det_flat, reinterpret_cast<float4*>(det_boxes), det_scores, det_count);
     DET_LAUNCH_OK("yolo_decode_nms_kernel");
