@@ -11,10 +11,9 @@
 // No reference implementation exists for either; the specification is
 // oracle/ref_torch.py (yolo_decode, yolo_select_nms, dense_decode).
 #include "nms_small.cuh"
+#include "yolo_fast.cuh"
 
 namespace det {
-
-__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // candidates live in shared memory as (predictor << 16 | class) + score; boxes are looked up per predictor
 struct YoloCandidates {
@@ -24,13 +23,6 @@ struct YoloCandidates {
     __device__ __forceinline__ float4 box(int i) const { return pbox[cpc[i] >> 16]; }
     __device__ __forceinline__ float score(int i) const { return cscore[i]; }
     __device__ __forceinline__ int64_t cat(int i) const { return (int64_t)(cpc[i] & 0xffffu); }
-};
-
-struct YoloParams {
-    int n, s, b, c;
-    float stride_x, stride_y, img_w, img_h, scale_clamp, score_thresh, thr_f;
-    int clip, mode;
-    int64_t max_det;
 };
 
 constexpr int kYoloThreads = 512;
@@ -197,6 +189,23 @@ static int launch_yolo(const float* head, const float* priors, const YoloParams&
     return DET_OK;
 }
 
+template <int MAXT, int MINB>
+static int launch_yolo_fast(const float* head, const float* priors, const YoloParams& prm, float* dense_boxes,
+                            float* dense_conf, float* dense_scores, int64_t* det_flat, float* det_boxes,
+                            float* det_scores, int32_t* det_count, cudaStream_t st) {
+    const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c, P = S2 * prm.b;
+    const FastLayout lay(S2, ch, P, prm.c);
+    const int warps = prm.c > kFastMinWarps ? prm.c : kFastMinWarps;
+    cudaError_t e = cudaFuncSetAttribute(yolo_fast_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)lay.bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(yolo_fast_kernel)");
+    yolo_fast_kernel<MAXT, MINB><<<prm.n, warps * 32, lay.bytes, st>>>(
+        head, reinterpret_cast<const float2*>(priors), prm, reinterpret_cast<float4*>(dense_boxes), dense_conf,
+        dense_scores, det_flat, reinterpret_cast<float4*>(det_boxes), det_scores, det_count);
+    DET_LAUNCH_OK("yolo_fast_kernel");
+    return DET_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense anchor head, conv layout
 // ------------------------------------------------------------------------------------------------
@@ -312,6 +321,12 @@ int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h
     prm.thr_f = float_threshold_below(iou_threshold);
     prm.clip = clip; prm.mode = mode; prm.max_det = max_det;
     cudaStream_t st = as_stream(stream);
+    // small clipped grids (BASELINE configs[0]/[1]): one warp per class, no CTA-wide sort
+    if (P <= kFastMaxP && c <= kFastMaxC && clip && FastLayout(s * s, b * 5 + c, (int)P, c).bytes <= 200 * 1024) {
+        if (c <= 20)
+            return launch_yolo_fast<640, 2>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+        return launch_yolo_fast<1024, 1>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+    }
     if (PC <= 1024)
         return launch_yolo<1024>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
     if (PC <= 2048)

@@ -79,6 +79,81 @@ class YoloGridHead:
         return r["dense_boxes"], r["dense_conf"], r["dense_scores"]
 
 
+class YoloHostPipeline:
+    """Serving loop for host-resident head tensors: `depth` slots, each with pinned host input / output buffers, device
+    buffers, its own stream and a CUDA graph [H2D copy -> det_yolo_decode_nms -> D2H copy].  Slots run on different
+    streams, so the upload of batch i+1, the kernel of batch i and the download of batch i-1 overlap (separate copy
+    engines per direction).  The producer writes a batch into ``input(slot)`` (pinned), calls ``launch(slot)`` and
+    later ``wait(slot)`` -> dict of pinned host views (flat, boxes, scores, count).  No per-step allocation."""
+
+    def __init__(self, head: "YoloGridHead", batch: int, score_thresh: float = 0.25, iou_thresh: float = 0.5,
+                 max_det: int = 300, depth: int = 3, device=None, mode: int = MODE_AUTO, use_graph: bool = True):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.head, self.batch, self.depth, self.device = head, int(batch), int(depth), dev
+        self.args = (float(score_thresh), float(iou_thresh), int(max_det), int(mode))
+        shape = (self.batch, head.S, head.S, head.B * 5 + head.C)
+        k = int(max_det)
+        # one output blob per slot so the download is a single copy: [flat i64 | boxes f32x4 | scores f32 | count i32]
+        self._sizes = (self.batch * k * 8, self.batch * k * 16, self.batch * k * 4, self.batch * 4)
+        nbytes = sum(self._sizes)
+        self.h_in = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.d_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.d_blob = [torch.empty((nbytes,), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.h_blob = [torch.empty((nbytes,), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.d_out = [self._views(b, k) for b in self.d_blob]
+        self.h_out = [self._views(b, k) for b in self.h_blob]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.graphs = [None] * depth
+        self.h2d_bytes = self.h_in[0].numel() * 4
+        self.d2h_bytes = nbytes
+        if use_graph:
+            for s in range(depth):
+                with torch.cuda.stream(self.streams[s]):
+                    self._enqueue(s)  # warm-up outside capture (function attributes, lazy init)
+                self.streams[s].synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.streams[s]):
+                    self._enqueue(s)
+                self.graphs[s] = g
+
+    def _views(self, blob, k):
+        o0, o1, o2, o3 = 0, self._sizes[0], self._sizes[0] + self._sizes[1], self._sizes[0] + self._sizes[1] + self._sizes[2]
+        return {"flat": blob[o0:o1].view(torch.int64).view(self.batch, k),
+                "boxes": blob[o1:o2].view(torch.float32).view(self.batch, k, 4),
+                "scores": blob[o2:o3].view(torch.float32).view(self.batch, k),
+                "count": blob[o3:].view(torch.int32).view(self.batch), "num_classes": self.head.C}
+
+    def _enqueue(self, s):
+        thr, iou, k, mode = self.args
+        self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+        self.head.detect(self.d_in[s], thr, iou, max_det=k, mode=mode, out=self.d_out[s])
+        self.h_blob[s].copy_(self.d_blob[s], non_blocking=True)
+
+    def input(self, slot: int) -> torch.Tensor:
+        return self.h_in[slot]
+
+    def launch(self, slot: int) -> None:
+        st = self.streams[slot]
+        if self.graphs[slot] is not None:
+            with torch.cuda.stream(st):
+                self.graphs[slot].replay()
+        else:
+            with torch.cuda.stream(st):
+                self._enqueue(slot)
+        self.done[slot].record(st)
+
+    def wait(self, slot: int):
+        self.done[slot].synchronize()
+        return self.h_out[slot]
+
+    def run(self, host_head: torch.Tensor):
+        """Convenience: one batch through slot 0, synchronously."""
+        self.h_in[0].copy_(host_head)
+        self.launch(0)
+        return self.wait(0)
+
+
 class _FusedYoloLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, head, owner, asg, gt_classes, norm):

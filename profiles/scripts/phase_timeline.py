@@ -23,10 +23,11 @@ for i in range(4):
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 32)()
 assert N.lib().det_debug_read_phases(buf) == 0
-names = {0: "start", 1: "head staged", 2: "decoded", 3: "compacted", 4: "stats", 5: "keys built", 6: "sort 1", 7: "gather/segments",
-         8: "tiny setup", 9: "tiny pair tests", 10: "tiny resolve", 11: "warp/cta segments", 12: "rekey", 13: "sort 2", 15: "output"}
+names = {0: "start", 1: "A staged+decoded", 2: "B scores/stats", 5: "C compaction (class 0)", 6: "D rank sort", 7: "E pair tests",
+         8: "F/G resolve", 3: "all classes done", 9: "keys written", 4: "merge tree", 15: "output"}
+order = [0, 1, 2, 5, 6, 7, 8, 3, 9, 4, 15]
 prev = buf[0]
-for i in sorted(names):
+for i in order:
     if buf[i]:
-        print(f"{names[i]:>20s}: +{buf[i] - prev:7d} cycles  (t={buf[i] - buf[0]})")
+        print(f"{names[i]:>26s}: +{buf[i] - prev:7d} cycles  (t={buf[i] - buf[0]})")
         prev = buf[i]

@@ -114,3 +114,69 @@ def test_dense_head_detect_three_levels(det, O):
     for i in range(2):
         want = O.batched_nms(boxes[i].cpu(), scores[i].cpu(), classes[i].cpu(), 0.5)
         assert int(cnt[i]) == want.numel() and torch.equal(keep[i, :want.numel()].cpu(), want)
+
+
+# ---- warp-per-class fast path (csrc/yolo_fast.cuh): small clipped grids ---------------------------------------------
+def _check_detect(det, O, yh, head, thr, iou, max_det=None, mode=0):
+    r = yh.detect(head.cuda(), thr, iou, max_det=max_det, return_dense=True, mode=mode)
+    gb, gs = r["dense_boxes"].cpu(), r["dense_scores"].cpu()
+    cnt, flat, kb, ks = r["count"].cpu(), r["flat"].cpu(), r["boxes"].cpu(), r["scores"].cpu()
+    for i in range(head.shape[0]):
+        wf, wb, ws, _ = O.yolo_select_nms(gb[i], gs[i], thr, iou, max_det=max_det)
+        k = int(cnt[i])
+        assert k == wf.numel(), (i, k, wf.numel())
+        assert torch.equal(flat[i, :k], wf), i
+        assert torch.equal(kb[i, :k], wb, ) or bool((torch.isnan(kb[i, :k]) == torch.isnan(wb)).all())
+        assert torch.equal(ks[i, :k], ws)
+    return r
+
+
+@pytest.mark.parametrize("S,B,C,hw,thr,iou,n", [
+    (5, 3, 7, (320, 480), 0.1, 0.45, 9),      # odd sizes, rectangular image
+    (8, 2, 32, (512, 512), 0.2, 0.5, 7),      # 128 predictors x 32 classes: the limits of the fast path
+    (3, 1, 1, (96, 96), 0.0, 0.3, 5),         # single class, every predictor a candidate
+    (7, 2, 20, (448, 448), 0.02, 0.6, 6),     # low threshold: ~98 candidates per class, per-category branch
+    (7, 2, 20, (448, 448), 0.6, 0.2, 6),      # few candidates, aggressive suppression
+    (2, 1, 3, (64, 64), 0.3, 0.5, 33),        # tiny
+])
+def test_yolo_fast_path_shapes(det, O, S, B, C, hw, thr, iou, n):
+    yh = det.YoloGridHead(S, B, C, hw)
+    head = torch.randn(n, S, S, B * 5 + C, generator=gen(S * 100 + C)) * 1.3
+    _check_detect(det, O, yh, head, thr, iou)
+    _check_detect(det, O, yh, head, thr, iou, max_det=5)
+
+
+def test_yolo_fast_path_heavy_overlap(det, O):
+    """Small w/h logits spread and centred boxes: long suppression chains inside every class."""
+    yh = det.YoloGridHead(7, 2, 20, (448, 448), priors=[[300, 300], [380, 380]])
+    head = torch.randn(12, 7, 7, 30, generator=gen(77))
+    head[..., 2:4] *= 0.05
+    head[..., 7:9] *= 0.05
+    r = _check_detect(det, O, yh, head, 0.2, 0.3)
+    assert int(r["count"].max()) < 200  # most candidates really were suppressed
+
+
+def test_yolo_fast_path_ties(det, O):
+    """Identical logits in many cells -> exactly tied scores: order must be (score desc, predictor*C+class asc)."""
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    head = torch.randn(4, 7, 7, 30, generator=gen(5))
+    head[:, :, :, 4] = 0.5    # same confidence everywhere
+    head[:, :, :, 9] = 0.5
+    head[:, :, :, 10:] = head[:, :1, :1, 10:]  # same class logits in every cell
+    _check_detect(det, O, yh, head, 0.25, 0.5)
+    _check_detect(det, O, yh, head, 0.25, 0.5, max_det=40)
+
+
+def test_yolo_fast_path_nonfinite_logits(det, O):
+    """NaN / Inf logits: NaN boxes make the offset-trick branch non-separable -> the kernel's slow exact path."""
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    head = torch.randn(6, 7, 7, 30, generator=gen(9))
+    head[0, 3, 3, 2] = float("nan")      # NaN width of one predictor
+    head[1, 0, 0, 0] = float("inf")      # sigmoid(inf) = 1: finite box
+    head[2, 6, 6, 7] = float("-inf")     # exp(-inf) = 0 width
+    head[3, 2, 2, 4] = float("nan")      # NaN confidence: its scores are NaN and never pass the threshold
+    head[4, 1, 5, 12] = float("nan")     # NaN class probability
+    head[5] *= 0.4                        # fewer candidates (<= 1000): offset-trick branch ...
+    head[5, 4, 4, 3] = float("nan")      # ... with a NaN box
+    _check_detect(det, O, yh, head, 0.25, 0.5, max_det=300)
+    _check_detect(det, O, yh, head, 0.35, 0.5)
