@@ -189,17 +189,17 @@ static int launch_yolo(const float* head, const float* priors, const YoloParams&
     return DET_OK;
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int CS, int CB, int CC>
 static int launch_yolo_fast(const float* head, const float* priors, const YoloParams& prm, float* dense_boxes,
                             float* dense_conf, float* dense_scores, int64_t* det_flat, float* det_boxes,
                             float* det_scores, int32_t* det_count, cudaStream_t st) {
     const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c, P = S2 * prm.b;
     const FastLayout lay(S2, ch, P, prm.c);
     const int warps = prm.c > kFastMinWarps ? prm.c : kFastMinWarps;
-    cudaError_t e = cudaFuncSetAttribute(yolo_fast_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(yolo_fast_kernel<MAXT, MINB, CS, CB, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)lay.bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(yolo_fast_kernel)");
-    yolo_fast_kernel<MAXT, MINB><<<prm.n, warps * 32, lay.bytes, st>>>(
+    yolo_fast_kernel<MAXT, MINB, CS, CB, CC><<<prm.n, warps * 32, lay.bytes, st>>>(
         head, reinterpret_cast<const float2*>(priors), prm, reinterpret_cast<float4*>(dense_boxes), dense_conf,
         dense_scores, det_flat, reinterpret_cast<float4*>(det_boxes), det_scores, det_count);
     DET_LAUNCH_OK("yolo_fast_kernel");
@@ -323,9 +323,11 @@ int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h
     cudaStream_t st = as_stream(stream);
     // small clipped grids (BASELINE configs[0]/[1]): one warp per class, no CTA-wide sort
     if (P <= kFastMaxP && c <= kFastMaxC && clip && FastLayout(s * s, b * 5 + c, (int)P, c).bytes <= 200 * 1024) {
+        if (s == 7 && b == 2 && c == 20)  // BASELINE configs[0]/[1]: shape folded at compile time
+            return launch_yolo_fast<640, 2, 7, 2, 20>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
         if (c <= 20)
-            return launch_yolo_fast<640, 2>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
-        return launch_yolo_fast<1024, 1>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+            return launch_yolo_fast<640, 2, 0, 0, 0>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+        return launch_yolo_fast<1024, 1, 0, 0, 0>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
     }
     if (PC <= 1024)
         return launch_yolo<1024>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);

@@ -3,17 +3,25 @@
 //
 // One CTA per image, ONE WARP PER CLASS.  A class has at most 128 candidates (one per predictor), so every
 // per-class step fits a warp and needs no block barrier:
-//   B  scores conf x class for the warp's class, threshold, candidate statistics (count, coordinate range)
+//   A  stage the image's logits (16-byte loads), sigmoid the conf / class logits in place, decode the boxes
+//   B  scores conf x class for the warp's class, threshold, class count, score histogram; one thread per predictor
+//      gathers the coordinate statistics torchvision's offset trick needs
+//   T  tier cut: only the first max_det kept detections (global score order) are output and a box can only be
+//      suppressed by higher-scored ones, so the NMS first runs on the candidates above a histogram cut holding about
+//      4/3 max_det of them; if that yields max_det kept boxes the rest cannot matter, else everything is redone
 //   C  order-preserving ballot compaction of the class's candidates
 //   D  rank-by-counting sort (score descending, predictor ascending) -> boxes (+ coordinate offset when the
 //      image takes torchvision's offset-trick branch), areas and scores in sorted order
 //   E  every unordered pair of the class tested exactly once, load-balanced over the 32 lanes; a hit sets one bit
 //      of the earlier box's suppression row (shared-memory atomicOr) and flags the row as non-empty
 //   F  greedy resolution on the bit rows alone, visiting only non-empty rows
-// then the per-class kept lists (each already in output order) are merged pairwise with binary-search ranks
-// (log2(C) levels, truncated to max_det at every level) -- no second sort -- and the detections are written.
+//   M  the kept detections of all classes are put in output order by a counting sort on a 256-bin score histogram
+//      (suffix scan -> bin-grouped placement -> rank inside the bin by direct comparison): no second sort
 // Images whose offset-trick branch cannot be swept per class (non-finite or <= -1 coordinates: only possible with
 // NaN/Inf logits here) take a slow exact path: repeated arg-max + suppression over all candidates.
+//
+// The kernel is specialised at compile time for the BASELINE shape (S=7, B=2, C=20) -- all index arithmetic folds to
+// constants -- and has a generic instantiation (CS = CB = CC = 0) that reads the shape from the parameters.
 //
 // Specification: oracle/ref_torch.py yolo_decode / yolo_select_nms (no reference
 // implementation exists); the NMS semantics are the reference's batched_nms (python/src/utils.py:96-119).
@@ -25,8 +33,7 @@ namespace det {
 constexpr int kFastMaxP = 128;
 constexpr int kFastMaxC = 32;
 constexpr int kFastMinWarps = 8;
-constexpr int kFastMaxLevels = 6;  // ceil(log2(32)) + 1 list tables
-constexpr int kFastBins = 256;      // score histogram for the top-max_det tier cut
+constexpr int kFastBins = 256;
 
 struct YoloParams {
     int n, s, b, c;
@@ -40,12 +47,13 @@ __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + e
 struct FastLayout {
     int hs_floats, pp, cls_stride, pcp;
     size_t bytes;
-    __host__ __device__ FastLayout(int s2, int ch, int p, int c) {
-        hs_floats = (s2 * ch + 3) & ~3;
-        pp = (p + 3) & ~3;
-        // per class: sbox float4[pp] | rows uint4[pp] | sarea float[pp] | skey u32[pp] | spred u8[pad16(pp)]
-        cls_stride = pp * 16 + pp * 16 + pp * 4 + pp * 4 + ((pp + 15) & ~15);
-        pcp = (p * c + 3) & ~3;
+    __host__ __device__ constexpr FastLayout(int s2, int ch, int p, int c)
+        : hs_floats((s2 * ch + 3) & ~3),
+          pp((p + 3) & ~3),
+          // per class: sbox float4[pp] | rows uint4[pp] | sarea float[pp] | skey u32[pp] | spred u8[pad16(pp)]
+          cls_stride(((p + 3) & ~3) * 40 + ((((p + 3) & ~3) + 15) & ~15)),
+          pcp((p * c + 3) & ~3),
+          bytes(0) {
         size_t cls_bytes = (size_t)cls_stride * c;
         const size_t merge_bytes = (size_t)pcp * 17 + 16;  // two u64 key buffers + one state byte per (p, c)
         if (cls_bytes < merge_bytes) cls_bytes = merge_bytes;
@@ -53,27 +61,37 @@ struct FastLayout {
     }
 };
 
-template <int MAXT, int MINB>
+// histogram bin of a score: bits in [base, 0x3F800000], `shift` chosen so that the range spans <= 256 bins
+__device__ __forceinline__ int score_bin(unsigned bits, unsigned base, int shift) {
+    return min(kFastBins - 1, (int)((bits - base) >> shift));
+}
+__device__ __forceinline__ int score_shift(unsigned base) {
+    return 0x3F800000u > base ? max(0, 32 - __clz(0x3F800000u - base) - 8) : 0;
+}
+
+template <int MAXT, int MINB, int CS, int CB, int CC>
 __global__ void __launch_bounds__(MAXT, MINB)
 yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ priors, YoloParams prm,
                  float4* __restrict__ dense_boxes, float* __restrict__ dense_conf, float* __restrict__ dense_scores,
                  int64_t* __restrict__ det_flat, float4* __restrict__ det_boxes, float* __restrict__ det_scores,
                  int32_t* __restrict__ det_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int S2 = prm.s * prm.s, B = prm.b, C = prm.c, ch = B * 5 + C, P = S2 * B, PC = P * C;
+    const int S = CS ? CS : prm.s, B = CB ? CB : prm.b, C = CC ? CC : prm.c;
+    const int S2 = S * S, ch = B * 5 + C, P = S2 * B, PC = P * C;
     const FastLayout lay(S2, ch, P, C);
     const int Pp = lay.pp;
     float* hs = reinterpret_cast<float*>(smem_raw);
     float4* pbox = reinterpret_cast<float4*>(hs + lay.hs_floats);
     unsigned char* cls_region = reinterpret_cast<unsigned char*>(pbox + Pp);
     __shared__ int s_m[kFastMaxC];
-    __shared__ float s_mx[kFastMaxC], s_mn[kFastMaxC];
-    __shared__ int s_fl[kFastMaxC];
+    __shared__ float s_mx[4], s_mn[4];
+    __shared__ int s_fl[4];
     __shared__ unsigned s_nz[kFastMaxC][4];
-    __shared__ int s_kc[kFastMaxC];
-    __shared__ int s_start[kFastMaxLevels][kFastMaxC + 1];
+    __shared__ int s_total;
     __shared__ unsigned long long s_best;
-    __shared__ __align__(16) int s_hist[kFastBins];
+    __shared__ __align__(16) int s_hist[kFastBins];   // candidates by score (tier cut)
+    __shared__ __align__(16) int s_hist2[kFastBins];  // kept detections by score (output order)
+    __shared__ int s_base[kFastBins];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, T = blockDim.x;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -95,9 +113,14 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
                 if (base + e >= g0 && base + e < g1) hs[base + e - g0] = ld_stream(head + base + e);
         }
     }
+    for (int i = tid; i < kFastBins; i += T) {
+        s_hist[i] = 0;
+        s_hist2[i] = 0;
+    }
+    if (tid == 0) s_total = 0;
     __syncthreads();
-    // transcendentals in place (sigmoid for conf and the class logits) and, by a disjoint set of threads working from
-    // the raw tx, ty, tw, th (which the in-place pass leaves alone), the predictor boxes -- one barrier for both
+    // sigmoid of conf and class logits in place and, by a disjoint set of threads working from the raw tx, ty, tw, th
+    // (which the in-place pass leaves alone), the predictor boxes -- one barrier for both
     for (int i = tid; i < S2 * ch; i += T) {
         const int cell = i / ch, k = i - cell * ch;
         if (k < B * 5) {
@@ -112,7 +135,7 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
     }
     for (int p = T - 1 - tid; p < P; p += T) {  // the last threads of the CTA have the fewest logits above
         const int cell = p / B, bi = p - cell * B;
-        const int row = cell / prm.s, col = cell - row * prm.s;
+        const int row = cell / S, col = cell - row * S;
         const float* t = hs + cell * ch + bi * 5;
         const float2 pr = priors[bi];
         const float tw = (t[2] > prm.scale_clamp) ? prm.scale_clamp : t[2];  // torch.clamp(max=): NaN stays NaN
@@ -128,15 +151,13 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         pbox[p] = bx;
         if (dense_boxes) dense_boxes[(int64_t)img * P + p] = bx;
     }
-    for (int i = tid; i < kFastBins; i += T) s_hist[i] = 0;
     __syncthreads();
     DET_MARK(1);
 
     // score histogram geometry: candidates have bits(score) in (bits(thr), bits(1.0)]; scores are >= +0
     const unsigned lo_bits = prm.score_thresh > 0.0f ? __float_as_uint(prm.score_thresh) : 0u;
-    const unsigned hi_bits = 0x3F800000u;
-    const int hshift = hi_bits > lo_bits ? max(0, 32 - __clz(hi_bits - lo_bits) - 8) : 0;
-    // ---- B: the warp's class: scores, threshold, statistics of the candidate boxes
+    const int hshift = score_shift(lo_bits);
+    // ---- B: the warp's class: scores, threshold, count, histogram
     const int c = wid;
     const bool cls_warp = c < C;
     float sc[4];
@@ -147,8 +168,7 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         pass[k] = false;
     }
     if (cls_warp) {
-        float mx = -INFINITY, mn = INFINITY;
-        int fin = 1, nonan = 1, mcount = 0;
+        int mcount = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int p = lane + 32 * k;
@@ -157,15 +177,29 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
                 sc[k] = hs[cell * ch + bi * 5 + 4] * hs[cell * ch + B * 5 + c];
                 pass[k] = sc[k] > prm.score_thresh;
                 if (dense_scores) dense_scores[(int64_t)img * PC + (int64_t)p * C + c] = sc[k];
-                if (pass[k]) {
-                    const float4 b = pbox[p];
-                    mx = max_nan(mx, max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w)));
-                    mn = min_nan(mn, min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w)));
-                    fin &= (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
-                    nonan &= (int)((b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w));
-                    ++mcount;
-                    atomicAdd(&s_hist[min(kFastBins - 1, (int)((__float_as_uint(sc[k]) - lo_bits) >> hshift))], 1);
-                }
+                if (pass[k]) atomicAdd(&s_hist[score_bin(__float_as_uint(sc[k]), lo_bits, hshift)], 1);
+            }
+            mcount += __popc(__ballot_sync(FULL, pass[k]));
+        }
+        if (lane == 0) s_m[c] = mcount;
+    }
+    // coordinate statistics over the predictors that are a candidate for at least one class: conf * max class prob
+    // passes iff some conf * prob passes (rounding is monotone); NaN probabilities never pass and are skipped by fmaxf
+    if (tid < ((P + 31) & ~31)) {
+        const int p = tid;
+        float mx = -INFINITY, mn = INFINITY;
+        int fin = 1, nonan_l = 1;
+        if (p < P) {
+            const int cell = p / B, bi = p - cell * B;
+            const float* pc = hs + cell * ch + B * 5;
+            float best = pc[0];
+            for (int q = 1; q < C; ++q) best = fmaxf(best, pc[q]);
+            if (hs[cell * ch + bi * 5 + 4] * best > prm.score_thresh) {
+                const float4 b = pbox[p];
+                mx = max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w));
+                mn = min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w));
+                fin = (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
+                nonan_l = (int)((b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w));
             }
         }
 #pragma unroll
@@ -173,23 +207,25 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
             mx = max_nan(mx, __shfl_xor_sync(FULL, mx, o));
             mn = min_nan(mn, __shfl_xor_sync(FULL, mn, o));
             fin &= __shfl_xor_sync(FULL, fin, o);
-            nonan &= __shfl_xor_sync(FULL, nonan, o);
-            mcount += __shfl_xor_sync(FULL, mcount, o);
+            nonan_l &= __shfl_xor_sync(FULL, nonan_l, o);
         }
         if (lane == 0) {
-            s_m[c] = mcount;
-            s_mx[c] = mx;
-            s_mn[c] = mn;
-            s_fl[c] = fin | (nonan << 1);
+            s_mx[wid] = mx;
+            s_mn[wid] = mn;
+            s_fl[wid] = fin | (nonan_l << 1);
         }
     }
     __syncthreads();
-    int cnt = 0, gcat = 0, gfl = 3;
+    int cnt, gcat;
+    {
+        const int mq = lane < C ? s_m[lane] : 0;
+        cnt = warp_sum(mq);
+        const unsigned has = __ballot_sync(FULL, mq > 0);
+        gcat = has ? 31 - __clz(has) : 0;
+    }
     float gmx = -INFINITY, gmn = INFINITY;
-    for (int q = 0; q < C; ++q) {
-        const int mq = s_m[q];
-        cnt += mq;
-        if (mq) gcat = q;
+    int gfl = 3;
+    for (int q = 0; q < (P + 31) / 32; ++q) {
         gmx = max_nan(gmx, s_mx[q]);
         gmn = min_nan(gmn, s_mn[q]);
         gfl &= s_fl[q];
@@ -203,10 +239,7 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
     const bool sweep_ok = (gfl & 1) && gmn > -1.0f && thr_f >= 0.0f && isfinite(far);
     const bool by_cat = !trick || sweep_ok;
     const bool nonan = (gfl & 2) != 0;
-    // ---- top-max_det tier: only the first K kept detections in global score order are output, and a candidate can
-    //      only be suppressed by higher-scored ones, so the NMS is first run on the candidates above a histogram cut
-    //      that holds about 4K/3 of them; if that already yields K kept boxes the rest cannot matter.  Otherwise
-    //      (heavy suppression) everything is redone on all candidates.  Every warp derives the cut on its own.
+    // ---- T: tier cut, derived by every warp on its own from the candidate histogram
     unsigned tier_bits = 0u;
     {
         const int target = K + K / 3 + 8;
@@ -249,218 +282,190 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
 
     if (by_cat) {
         uint64_t mykey[4];
-        int mypos[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            mykey[k] = 0ull;
-            mypos[k] = -1;
-        }
+        bool mine_kept[4];
+        unsigned base2 = 0u;
+        int shift2 = 0;
         for (int tier = tier_bits ? 0 : 1; tier < 2; ++tier) {
-        const unsigned cut_bits = tier == 0 ? tier_bits : 0u;
-        if (cls_warp) {
-            unsigned char* my = cls_region + (size_t)c * lay.cls_stride;
-            float4* sbox = reinterpret_cast<float4*>(my);
-            uint4* rows4 = reinterpret_cast<uint4*>(my + Pp * 16);
-            unsigned* rows = reinterpret_cast<unsigned*>(rows4);
-            float* sarea = reinterpret_cast<float*>(my + Pp * 32);
-            unsigned* skey = reinterpret_cast<unsigned*>(my + Pp * 36);
-            unsigned char* spred = my + Pp * 40;
-            unsigned* ckey = rows;  // unsorted candidates live in the row storage until the rows are needed
-            unsigned char* cp = reinterpret_cast<unsigned char*>(rows + Pp);
-            // ---- C: order-preserving compaction (predictor ascending)
-            if (lane < 4) s_nz[c][lane] = 0u;
-            int m = 0;
+            const unsigned cut_bits = tier == 0 ? tier_bits : 0u;
+            base2 = tier == 0 ? tier_bits : lo_bits;  // every kept score of this pass has bits >= base2
+            shift2 = score_shift(base2);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool in = pass[k] && __float_as_uint(sc[k]) >= cut_bits;
-                const unsigned bal = __ballot_sync(FULL, in);
-                if (in) {
-                    const int pos = m + __popc(bal & lt_mask);
-                    ckey[pos] = __float_as_uint(sc[k]);  // scores are >= +0: the bit patterns order like the values
-                    cp[pos] = (unsigned char)(lane + 32 * k);
+            for (int k = 0; k < 4; ++k) mine_kept[k] = false;
+            if (cls_warp) {
+                unsigned char* my = cls_region + (size_t)c * lay.cls_stride;
+                float4* sbox = reinterpret_cast<float4*>(my);
+                uint4* rows4 = reinterpret_cast<uint4*>(my + Pp * 16);
+                unsigned* rows = reinterpret_cast<unsigned*>(rows4);
+                float* sarea = reinterpret_cast<float*>(my + Pp * 32);
+                unsigned* skey = reinterpret_cast<unsigned*>(my + Pp * 36);
+                unsigned char* spred = my + Pp * 40;
+                unsigned* ckey = rows;  // unsorted candidates live in the row storage until the rows are needed
+                unsigned char* cp = reinterpret_cast<unsigned char*>(rows + Pp);
+                // ---- C: order-preserving compaction (predictor ascending)
+                if (lane < 4) s_nz[c][lane] = 0u;
+                int m = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool in = pass[k] && __float_as_uint(sc[k]) >= cut_bits;
+                    const unsigned bal = __ballot_sync(FULL, in);
+                    if (in) {
+                        const int pos = m + __popc(bal & lt_mask);
+                        ckey[pos] = __float_as_uint(sc[k]);  // scores are >= +0: bit patterns order like the values
+                        cp[pos] = (unsigned char)(lane + 32 * k);
+                    }
+                    m += __popc(bal);
                 }
-                m += __popc(bal);
-            }
-            __syncwarp();
-            DET_MARK(5);
-            // ---- D: rank by counting -> sorted order (score descending, predictor ascending)
-            const float off = trick ? (float)c * span : 0.0f;  // idxs.to(boxes) * (max_coordinate + 1)
-            for (int i0 = 0; i0 < m; i0 += 32) {
-                const int i = i0 + lane;
-                const bool has = i < m;
-                const unsigned si = has ? ckey[i] : 0u;
-                int rank = 0;
+                __syncwarp();
+                DET_MARK(5);
+                // ---- D: rank by counting -> sorted order (score descending, predictor ascending)
+                const float off = trick ? (float)c * span : 0.0f;  // idxs.to(boxes) * (max_coordinate + 1)
+                for (int i0 = 0; i0 < m; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool has = i < m;
+                    const unsigned si = has ? ckey[i] : 0u;
+                    int rank = 0;
 #pragma unroll 4
-                for (int j = 0; j < m; ++j) {
-                    const unsigned sj = ckey[j];
-                    rank += ((sj > si) || (sj == si && j < i)) ? 1 : 0;
-                }
-                if (has) {
-                    const int p = (int)cp[i];
-                    float4 b = pbox[p];
-                    if (trick) {
-                        b.x += off; b.y += off; b.z += off; b.w += off;
+                    for (int j = 0; j < m; ++j) {
+                        const unsigned sj = ckey[j];
+                        rank += ((sj > si) || (sj == si && j < i)) ? 1 : 0;
                     }
-                    sbox[rank] = b;
-                    sarea[rank] = box_area(b);
-                    skey[rank] = si;
-                    spred[rank] = (unsigned char)p;
-                }
-            }
-            __syncwarp();
-            for (int r = lane; r < m; r += 32) rows4[r] = make_uint4(0u, 0u, 0u, 0u);
-            __syncwarp();
-            DET_MARK(6);
-            // ---- E: all pairs once: item q -> (row r, distance d), partner (r + d) mod m
-            if (m >= 2) {
-                const int half = m >> 1, items = m * half;
-                const unsigned inv = half > 1 ? (0xFFFFFFFFu / (unsigned)half) + 1u : 0u;
-                const bool even = (m & 1) == 0;
-                for (int q = lane; q < items; q += 32) {
-                    const int r = half > 1 ? (int)__umulhi((unsigned)q, inv) : q;
-                    const int d = q - r * half + 1;
-                    if (even && d == half && r >= half) continue;  // distance-m/2 pairs are met from the lower half
-                    int j = r + d;
-                    j = (j >= m) ? j - m : j;
-                    const int lo = min(r, j), hi = max(r, j);
-                    const float4 ba = sbox[lo], bb = sbox[hi];
-                    const float aa = sarea[lo], ab = sarea[hi];
-                    const bool hit = nonan ? nms_suppresses<true>(ba, aa, bb, ab, thr_f)
-                                           : nms_suppresses<false>(ba, aa, bb, ab, thr_f);
-                    if (hit) {
-                        atomicOr(rows + lo * 4 + (hi >> 5), 1u << (hi & 31));
-                        atomicOr(&s_nz[c][lo >> 5], 1u << (lo & 31));
+                    if (has) {
+                        const int p = (int)cp[i];
+                        float4 b = pbox[p];
+                        if (trick) {
+                            b.x += off; b.y += off; b.z += off; b.w += off;
+                        }
+                        sbox[rank] = b;
+                        sarea[rank] = box_area(b);
+                        skey[rank] = si;
+                        spred[rank] = (unsigned char)p;
                     }
                 }
-            }
-            __syncwarp();
-            DET_MARK(7);
-            // ---- F: greedy resolution on the bit rows (uniform across the warp), only non-empty rows matter
-            unsigned alive[4];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int bits = min(32, max(0, m - 32 * w));
-                alive[w] = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
-            }
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                unsigned nzw = s_nz[c][w];
-                while (nzw) {
-                    const int b = __ffs(nzw) - 1;
-                    nzw &= nzw - 1;
-                    if ((alive[w] >> b) & 1u) {
-                        const uint4 rw = rows4[w * 32 + b];
-                        alive[0] &= ~rw.x; alive[1] &= ~rw.y; alive[2] &= ~rw.z; alive[3] &= ~rw.w;
+                __syncwarp();
+                for (int r = lane; r < m; r += 32) rows4[r] = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+                DET_MARK(6);
+                // ---- E: all pairs once: item q -> (row r, distance d), partner (r + d) mod m
+                if (m >= 2) {
+                    const int half = m >> 1, items = m * half;
+                    const unsigned inv = half > 1 ? (0xFFFFFFFFu / (unsigned)half) + 1u : 0u;
+                    const bool even = (m & 1) == 0;
+                    for (int q = lane; q < items; q += 32) {
+                        const int r = half > 1 ? (int)__umulhi((unsigned)q, inv) : q;
+                        const int d = q - r * half + 1;
+                        if (even && d == half && r >= half) continue;  // distance-m/2 pairs: from the lower half only
+                        int j = r + d;
+                        j = (j >= m) ? j - m : j;
+                        const int lo = min(r, j), hi = max(r, j);
+                        const float4 ba = sbox[lo], bb = sbox[hi];
+                        const float aa = sarea[lo], ab = sarea[hi];
+                        const bool hit = nonan ? nms_suppresses<true>(ba, aa, bb, ab, thr_f)
+                                               : nms_suppresses<false>(ba, aa, bb, ab, thr_f);
+                        if (hit) {
+                            atomicOr(rows + lo * 4 + (hi >> 5), 1u << (hi & 31));
+                            atomicOr(&s_nz[c][lo >> 5], 1u << (lo & 31));
+                        }
                     }
                 }
-            }
-            int kc = __popc(alive[0]) + __popc(alive[1]) + __popc(alive[2]) + __popc(alive[3]);
-            while (kc > K) {  // only the first K survivors of a class can reach the output
+                __syncwarp();
+                DET_MARK(7);
+                // ---- F: greedy resolution on the bit rows (uniform across the warp), only non-empty rows matter
+                unsigned alive[4];
 #pragma unroll
-                for (int w = 3; w >= 0; --w)
-                    if (alive[w]) {
-                        alive[w] &= ~(0x80000000u >> __clz(alive[w]));
-                        break;
-                    }
-                --kc;
-            }
-            // ---- G: the lane's kept keys and their ranks in the class's kept list
-            int before = 0;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int i = lane + 32 * w;
-                mypos[w] = -1;
-                if ((alive[w] >> lane) & 1u) {
-                    mypos[w] = before + __popc(alive[w] & lt_mask);
-                    mykey[w] = ((uint64_t)(~skey[i]) << 32) | (uint64_t)((unsigned)spred[i] * (unsigned)C + (unsigned)c);
+                for (int w = 0; w < 4; ++w) {
+                    const int bits = min(32, max(0, m - 32 * w));
+                    alive[w] = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
                 }
-                before += __popc(alive[w]);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    unsigned nzw = s_nz[c][w];
+                    while (nzw) {
+                        const int b = __ffs(nzw) - 1;
+                        nzw &= nzw - 1;
+                        if ((alive[w] >> b) & 1u) {
+                            const uint4 rw = rows4[w * 32 + b];
+                            alive[0] &= ~rw.x; alive[1] &= ~rw.y; alive[2] &= ~rw.z; alive[3] &= ~rw.w;
+                        }
+                    }
+                }
+                int kc = __popc(alive[0]) + __popc(alive[1]) + __popc(alive[2]) + __popc(alive[3]);
+                while (kc > K) {  // only the first K survivors of a class can reach the output
+#pragma unroll
+                    for (int w = 3; w >= 0; --w)
+                        if (alive[w]) {
+                            alive[w] &= ~(0x80000000u >> __clz(alive[w]));
+                            break;
+                        }
+                    --kc;
+                }
+                // ---- G: the lane's kept keys (descending-score bits | predictor * C + class) and their histogram
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    if ((alive[w] >> lane) & 1u) {
+                        const int i = lane + 32 * w;
+                        const unsigned sb = skey[i];
+                        mine_kept[w] = true;
+                        mykey[w] = ((uint64_t)(~sb) << 32) | (uint64_t)((unsigned)spred[i] * (unsigned)C + (unsigned)c);
+                        atomicAdd(&s_hist2[score_bin(sb, base2, shift2)], 1);
+                    }
+                }
+                if (lane == 0 && kc) atomicAdd(&s_total, kc);
+                DET_MARK(8);
             }
-            if (lane == 0) s_kc[c] = kc;
-            DET_MARK(8);
-        }
-        __syncthreads();  // every class is done with its scratch: the merge buffers may now overwrite it
-        if (tier == 0) {
-            int tk = 0;
-            for (int q = 0; q < C; ++q) tk += s_kc[q];
-            if (tk >= K) break;   // the first K kept detections all lie above the cut
-            __syncthreads();      // heavy suppression: redo on every candidate
-        }
+            __syncthreads();  // every class is done with its scratch: the merge buffers may now overwrite it
+            if (tier == 1 || s_total >= K) break;  // tier 0 sufficed: the first K kept detections lie above the cut
+            __syncthreads();                       // heavy suppression: redo on every candidate
+            for (int i = tid; i < kFastBins; i += T) s_hist2[i] = 0;
+            if (tid == 0) s_total = 0;
+            __syncthreads();
         }
         DET_MARK(3);
-        // list tables of every merge level (lengths are known without looking at the keys)
-        int levels = 0;
+        // ---- M: counting sort of the kept keys by score bin.  s_base[b] = kept keys in higher bins (they come first)
+        const int total = s_total;
         if (wid == 0) {
-            int len = lane < C ? s_kc[lane] : 0;
-            int nl = C, lev = 0;
-            while (true) {
-                int incl = len;
+            int h8[8];
+            const int4 ha = reinterpret_cast<const int4*>(s_hist2)[lane * 2], hb = reinterpret_cast<const int4*>(s_hist2)[lane * 2 + 1];
+            h8[0] = ha.x; h8[1] = ha.y; h8[2] = ha.z; h8[3] = ha.w; h8[4] = hb.x; h8[5] = hb.y; h8[6] = hb.z; h8[7] = hb.w;
+            const int mine = h8[0] + h8[1] + h8[2] + h8[3] + h8[4] + h8[5] + h8[6] + h8[7];
+            int suf = mine;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (lane < nl) s_start[lev][lane] = incl - len;
-                if (lane == nl - 1) s_start[lev][nl] = incl;
-                if (nl == 1) break;
-                const int la = __shfl_sync(FULL, len, (2 * lane) & 31), lb = __shfl_sync(FULL, len, (2 * lane + 1) & 31);
-                const int nn = (nl + 1) >> 1;
-                len = (lane < nn) ? min(la + ((2 * lane + 1 < nl) ? lb : 0), K) : 0;
-                nl = nn;
-                ++lev;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(FULL, suf, o);
+                if (lane + o < 32) suf += v;
+            }
+            int run = suf - mine;  // kept keys in the bins of higher lanes
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                s_base[lane * 8 + k] = run;
+                run += h8[k];
             }
         }
-        {
-            int nl = C;
-            while (nl > 1) {
-                nl = (nl + 1) >> 1;
-                ++levels;
-            }
-        }
-        // own class offset: exclusive prefix of s_kc
-        int off_c = 0;
-        for (int q = 0; q < c && q < C; ++q) off_c += s_kc[q];
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if (mypos[w] >= 0) buf_a[off_c + mypos[w]] = mykey[w];
         __syncthreads();
-        DET_MARK(9);
-        // ---- pairwise merges: position = index in own list + lower_bound in the partner list; keys are distinct
-        uint64_t* src = buf_a;
-        uint64_t* dst = buf_b;
-        int nl = C;
-        for (int lev = 0; lev < levels; ++lev) {
-            const int* st = s_start[lev];
-            const int* nst = s_start[lev + 1];
-            const int total = st[nl];
-            for (int e = tid; e < total; e += T) {
-                int lo = 0, hi = nl;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (st[mid] <= e) lo = mid; else hi = mid;
-                }
-                const int l = lo, partner = l ^ 1;
-                const uint64_t key = src[e];
-                int pos = e - st[l];
-                if (partner < nl) {
-                    int a = st[partner], b = st[partner + 1];
-                    const int a0 = a;
-                    while (a < b) {
-                        const int mid = (a + b) >> 1;
-                        if (src[mid] < key) a = mid + 1; else b = mid;
-                    }
-                    pos += a - a0;
-                }
-                if (pos < K) dst[nst[l >> 1] + pos] = key;
+        // bin-grouped placement (arbitrary order inside a bin): slots are handed out by counting the bin back down
+        int mybin[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            mybin[w] = 0;
+            if (mine_kept[w]) {
+                mybin[w] = score_bin(~(unsigned)(mykey[w] >> 32), base2, shift2);
+                const int slot = s_base[mybin[w]] + atomicSub(&s_hist2[mybin[w]], 1) - 1;
+                buf_a[slot] = mykey[w];
             }
-            __syncthreads();
-            uint64_t* t = src;
-            src = dst;
-            dst = t;
-            nl = (nl + 1) >> 1;
         }
-        fin_keys = src;
-        nout = min(s_start[levels][1], K);
+        __syncthreads();
+        // rank inside the bin by direct comparison (keys are distinct); only the first K positions are output
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (mine_kept[w]) {
+                const int b0 = s_base[mybin[w]], b1 = mybin[w] > 0 ? s_base[mybin[w] - 1] : total;
+                int pos = b0;
+                for (int j = b0; j < b1; ++j) pos += (buf_a[j] < mykey[w]) ? 1 : 0;
+                if (pos < K) buf_b[pos] = mykey[w];
+            }
+        }
+        __syncthreads();
+        fin_keys = buf_b;
+        nout = min(total, K);
     } else {
         // ---- slow exact path (offset trick with non-finite / <= -1 coordinates): global greedy by repeated arg-max
         unsigned char* st = reinterpret_cast<unsigned char*>(buf_b + lay.pcp);
