@@ -140,6 +140,19 @@ DET_API int det_dense_decode_level(const float* head, int n, int a, int c, int h
                            float scale_clamp, float* boxes_out, float* score_out, int64_t* class_out,
                            int64_t out_img_stride, int64_t out_offset, void* stream);
 
+/* All pyramid levels of a dense anchor head in ONE persistent launch (bulk-async-copy pipeline, csrc/dense_decode.cu).
+ * Every level shares n, a, c; level l: head (n, a*(5+c), h, w) device, anchors_wh (a,2) device, first output row
+ * out_offset.  Levels whose h*w is not a multiple of 4 (or an unaligned head) make the call fall back to one
+ * det_dense_decode_level launch per level -- same results. */
+typedef struct det_dense_level {
+    const float* head;
+    const float* anchors_wh;
+    int32_t h, w, stride, reserved;
+    int64_t out_offset;
+} det_dense_level_t;
+DET_API int det_dense_decode(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
+                     float* boxes_out, float* score_out, int64_t* class_out, int64_t out_img_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (4a) IoU target assignment -- replaces pairwise_iou + Matcher.__call__ + set_low_quality_matches_ as driven
  *      by label_and_sample_anchors, python/src/models/rpn.py:161-168 / components/matcher.py:53-120, for the

@@ -282,6 +282,97 @@ dense_decode_level_kernel(const float* __restrict__ head, int a, int c, int h, i
     }
 }
 
+
+// ---- sliced variant (hw % 4 == 0, 5 + c >= 20): the channel planes of one (image, anchor) are split into 4 slices
+// handled by 4 adjacent lanes, each lane streaming its slice with 16-byte loads over 4 consecutive positions -- 4x the
+// threads and bytes in flight of the kernel above -- then the (max, arg-max) pairs meet in a 2-step butterfly and each
+// lane finishes ONE of the 4 positions (the box logits travel through shared memory).
+constexpr int kDenseSlices = 4;
+constexpr int kDenseThreads = 256;
+
+// torch.max(dim) order on (value, class): a NaN beats everything, the first maximum / first NaN wins
+__device__ __forceinline__ bool argmax_takes(float v, int iv, float best, int ib) {
+    const bool vn = v != v, bn = best != best;
+    if (vn || bn) return vn && (!bn || iv < ib);
+    return v > best || (v == best && iv < ib);
+}
+
+__global__ void __launch_bounds__(kDenseThreads)
+dense_decode_sliced_kernel(const float* __restrict__ head, int a, int c, int hw, int w, float stride,
+                           const float2* __restrict__ anchors_wh, float scale_clamp, float4* __restrict__ boxes_out,
+                           float* __restrict__ score_out, int64_t* __restrict__ class_out, int64_t out_img_stride,
+                           int64_t out_offset) {
+    __shared__ float s_t[kDenseThreads / kDenseSlices][5][4];
+    const int nch = 5 + c, per = (nch + kDenseSlices - 1) / kDenseSlices;
+    const int groups = hw >> 2;
+    const int gt = blockIdx.x * kDenseThreads + threadIdx.x;
+    const int g = gt >> 2, sl = gt & 3;  // 4 adjacent lanes = the 4 slices of one position group
+    const int ia = blockIdx.y;           // image * a + anchor
+    const int img = ia / a, ai = ia - img * a;
+    const bool live = g < groups;
+    const int gg = live ? g : groups - 1;  // dead lanes shadow a valid group (they only take part in the shuffles)
+    const int k0 = sl * per, k1 = min(nch, k0 + per);
+    const float4* pl = reinterpret_cast<const float4*>(head + ((int64_t)ia * nch + k0) * hw) + gg;
+    const int plane4 = hw >> 2;  // float4 stride between planes
+    int k = k0;
+    if (sl == 0) {  // planes 0..4 are the box logits (per >= 5)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 q = ld_stream(pl + (int64_t)j * plane4);
+            *reinterpret_cast<float4*>(&s_t[threadIdx.x >> 2][j][0]) = q;
+        }
+        k = 5;
+    }
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bidx[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) bidx[v] = k - 5;
+    const float4* pk = pl + (int64_t)(k - k0) * plane4;
+#pragma unroll 8
+    for (; k < k1; ++k, pk += plane4) {
+        const float4 q4 = ld_stream(pk);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const bool take = (q[v] > best[v]) || (q[v] != q[v] && best[v] == best[v]);
+            best[v] = take ? q[v] : best[v];
+            bidx[v] = take ? k - 5 : bidx[v];
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < kDenseSlices; o <<= 1) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best[v], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx[v], o);
+            if (argmax_takes(ob, oi, best[v], bidx[v])) {
+                best[v] = ob;
+                bidx[v] = oi;
+            }
+        }
+    }
+    __syncwarp();  // the box logits of this group were written by its slice-0 lane (same warp)
+    // lane `sl` finishes position 4*g + sl
+    const float mybest = sl == 0 ? best[0] : sl == 1 ? best[1] : sl == 2 ? best[2] : best[3];
+    const int myidx = sl == 0 ? bidx[0] : sl == 1 ? bidx[1] : sl == 2 ? bidx[2] : bidx[3];
+    const float (*t)[4] = s_t[threadIdx.x >> 2];
+    const int pos = gg * 4 + sl;
+    const float colf = (float)(pos % w), rowf = (float)(pos / w);
+    const float cx = (sigmoidf_ref(t[0][sl]) + colf) * stride;
+    const float cy = (sigmoidf_ref(t[1][sl]) + rowf) * stride;
+    float tw = t[2][sl], th = t[3][sl];
+    tw = (tw > scale_clamp) ? scale_clamp : tw;
+    th = (th > scale_clamp) ? scale_clamp : th;
+    const float2 awh = anchors_wh[ai];
+    const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
+    if (live) {
+        const int64_t o = (int64_t)img * out_img_stride + out_offset + (int64_t)pos * a + ai;
+        st_stream(boxes_out + o, make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh));
+        st_stream(score_out + o, sigmoidf_ref(t[4][sl]) * sigmoidf_ref(mybest));
+        class_out[o] = (int64_t)myidx;
+    }
+}
+
 }  // namespace det
 
 using namespace det;
@@ -352,7 +443,11 @@ int det_dense_decode_level(const float* head, int n, int a, int c, int h, int w,
     auto awh = reinterpret_cast<const float2*>(anchors_wh);
     auto bo = reinterpret_cast<float4*>(boxes_out);
     cudaStream_t st = as_stream(stream);
-    if (hw % 4 == 0 && aligned16(head)) {
+    if (hw % 4 == 0 && aligned16(head) && 5 + c >= 5 * kDenseSlices && (int64_t)n * a <= 65535 && hw < (1 << 28)) {
+        dim3 grid((unsigned)((hw + kDenseThreads - 1) / kDenseThreads), (unsigned)(n * a));
+        dense_decode_sliced_kernel<<<grid, kDenseThreads, 0, st>>>(head, a, c, (int)hw, w, (float)stride, awh, scale_clamp,
+                                                                    bo, score_out, class_out, out_img_stride, out_offset);
+    } else if (hw % 4 == 0 && aligned16(head)) {
         dim3 grid((unsigned)((hw / 4 + 255) / 256), (unsigned)n);
         dense_decode_level_kernel<4><<<grid, 256, 0, st>>>(head, a, c, h, w, (float)stride, awh, scale_clamp, bo,
                                                            score_out, class_out, out_img_stride, out_offset);

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "det_yolo_decode_nms": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_i, c_f, c_d, c_i, c_p, c_p, c_p, c_l,
                                   c_p, c_p, c_p, c_p, c_p]),
     "det_dense_decode_level": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_p, c_p, c_p, c_l, c_l, c_p]),
+    "det_dense_decode": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_l, c_p]),
     "det_match_workspace_bytes": (c_l, [c_i, c_l, c_l]),
     "det_match_anchors": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "det_match_quality": (c_i, [c_p, c_l, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
@@ -48,6 +49,14 @@ PROTOTYPES = {
     "det_yolo_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
                             c_p, c_p]),
 }
+
+
+
+class DenseLevel(ctypes.Structure):
+    """det_dense_level_t of include/det_b200.h"""
+    _fields_ = [("head", c_p), ("anchors_wh", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_offset", c_l)]
+
 
 _lib = None
 

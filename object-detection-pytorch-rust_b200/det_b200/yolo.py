@@ -4,6 +4,7 @@ The reference has no such head; the specification 
 (oracle/ref_torch.py: yolo_decode, yolo_select_nms, dense_decode) -- parity is pinned by that oracle only.
 Arithmetic: det_yolo_decode_nms / det_dense_decode_level (csrc/yolo.cu) + det_nms_batched.
 """
+import ctypes
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -278,10 +279,24 @@ class DenseAnchorHead:
                    torch.empty((n, R), dtype=torch.float32, device=dev),
                    torch.empty((n, R), dtype=torch.int64, device=dev))
         boxes, scores, classes = out
+        anchors = self._anchors_on(dev)
+        hcs = [N.f32c(h) for h in heads]
+        na = anchors[0].shape[0]
+        if all(a.shape[0] == na for a in anchors):  # one persistent launch for the whole pyramid
+            lv = (N.DenseLevel * len(hcs))()
+            off = 0
+            for i, (hc, a, s, sz) in enumerate(zip(hcs, anchors, self.strides, sizes)):
+                assert hc.shape[1] == na * (5 + self.C), hc.shape
+                lv[i].head, lv[i].anchors_wh = hc.data_ptr(), a.data_ptr()
+                lv[i].h, lv[i].w, lv[i].stride, lv[i].reserved, lv[i].out_offset = hc.shape[2], hc.shape[3], s, 0, off
+                off += sz
+            with torch.cuda.device(dev):
+                N.call("det_dense_decode", ctypes.cast(lv, ctypes.c_void_p), len(hcs), n, na, self.C, self.scale_clamp,
+                       N.ptr(boxes), N.ptr(scores), N.ptr(classes), R, N.stream())
+            return boxes, scores, classes
         off = 0
         with torch.cuda.device(dev):
-            for h, a, s, sz in zip(heads, self._anchors_on(dev), self.strides, sizes):
-                hc = N.f32c(h)
+            for hc, a, s, sz in zip(hcs, anchors, self.strides, sizes):
                 assert hc.shape[1] == a.shape[0] * (5 + self.C), hc.shape
                 N.call("det_dense_decode_level", N.ptr(hc), n, a.shape[0], self.C, hc.shape[2], hc.shape[3], s,
                        N.ptr(a), self.scale_clamp, N.ptr(boxes), N.ptr(scores), N.ptr(classes), R, off, N.stream())

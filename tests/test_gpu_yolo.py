@@ -180,3 +180,72 @@ def test_yolo_fast_path_nonfinite_logits(det, O):
     head[5, 4, 4, 3] = float("nan")      # ... with a NaN box
     _check_detect(det, O, yh, head, 0.25, 0.5, max_det=300)
     _check_detect(det, O, yh, head, 0.35, 0.5)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_yolo_host_pipeline_matches_detect(det, O, use_graph):
+    """The serving pipeline (pinned host in -> H2D -> fused kernel -> D2H -> pinned host out, one slot per stream)
+    returns exactly what detect() returns, for every slot and across slot reuse."""
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    pipe = det.YoloHostPipeline(yh, 32, 0.25, 0.5, 300, depth=3, use_graph=use_graph)
+    heads = torch.randn(7, 32, 7, 7, 30, generator=gen(21))
+    got = []
+    for i in range(7):
+        slot = i % 3
+        if i >= 3:
+            got.append({k: v.clone() for k, v in pipe.wait(slot).items() if isinstance(v, torch.Tensor)})
+        pipe.input(slot).copy_(heads[i])
+        pipe.launch(slot)
+    for i in range(4, 7):
+        got.append({k: v.clone() for k, v in pipe.wait(i % 3).items() if isinstance(v, torch.Tensor)})
+    assert len(got) == 7
+    for i in range(7):
+        r = yh.detect(heads[i].cuda(), 0.25, 0.5, max_det=300)
+        cnt = r["count"].cpu()
+        assert torch.equal(got[i]["count"], cnt)
+        for j in range(32):
+            k = int(cnt[j])
+            assert torch.equal(got[i]["flat"][j, :k], r["flat"][j, :k].cpu())
+            assert torch.equal(got[i]["boxes"][j, :k], r["boxes"][j, :k].cpu())
+            assert torch.equal(got[i]["scores"][j, :k], r["scores"][j, :k].cpu())
+    # and against the oracle for one batch
+    r = pipe.run(heads[0])
+    d = yh.detect(heads[0].cuda(), 0.25, 0.5, return_dense=True)
+    for j in range(0, 32, 5):
+        wf, _, _, _ = O.yolo_select_nms(d["dense_boxes"][j].cpu(), d["dense_scores"][j].cpu(), 0.25, 0.5, max_det=300)
+        assert int(r["count"][j]) == wf.numel() and torch.equal(r["flat"][j, :wf.numel()], wf)
+
+
+@pytest.mark.parametrize("n,C,sizes", [
+    (3, 80, [(24, 24), (12, 12), (6, 6)]),     # every level a multiple of 4 positions: the bulk-copy pipeline
+    (2, 80, [(80, 80), (40, 40), (20, 20)]),   # BASELINE configs[3] geometry (640 px)
+    (5, 7, [(16, 12), (2, 2)]),                # few classes, tiny levels, odd class count
+    (2, 1, [(8, 8)]),                          # single class
+    (1, 80, [(20, 20), (10, 10), (5, 5)]),     # 25 positions: per-level fallback inside det_dense_decode
+])
+def test_dense_decode_all_levels_one_launch(det, O, n, C, sizes):
+    """det_dense_decode (one persistent launch, csrc/dense_decode.cu) vs the oracle, level by level."""
+    A = 3
+    strides = [8, 16, 32][:len(sizes)]
+    wh = [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]]][:len(sizes)]
+    g = gen(11)
+    heads = [torch.randn(n, A * (5 + C), h, w, generator=g) * 2 for (h, w) in sizes]
+    # arg-max corner cases: NaN class logit (NaN wins, first NaN), all -inf, exact ties (first maximum wins)
+    v = heads[0].view(n, A, 5 + C, *sizes[0])
+    v[0, 0, 5 + C // 2, 0, 0] = float("nan")
+    v[0, 1, 5:, 0, 1] = float("-inf")
+    v[0, 2, 5:, 1, 0] = 0.25
+    if C > 3:
+        v[0, 0, 5 + 1, 1, 1] = float("nan")
+        v[0, 0, 5 + 3, 1, 1] = float("nan")
+    dh = det.DenseAnchorHead(strides, wh, C)
+    gb, gs, gc = dh.decode([h.cuda() for h in heads])
+    off = 0
+    for h, s, a in zip(heads, strides, wh):
+        ob, os_, oc = O.dense_decode(h, A, C, s, torch.tensor(a, dtype=torch.float32))
+        r = ob.shape[1]
+        assert torch.equal(gc[:, off:off + r].cpu(), oc)
+        assert_boxes_close(gb[:, off:off + r].cpu(), ob, rtol=1e-5)
+        torch.testing.assert_close(gs[:, off:off + r].cpu(), os_, rtol=1e-5, atol=1e-6, equal_nan=True)
+        off += r
+    assert off == gb.shape[1]
