@@ -140,7 +140,7 @@ DET_API int det_dense_decode_level(const float* head, int n, int a, int c, int h
                            float scale_clamp, float* boxes_out, float* score_out, int64_t* class_out,
                            int64_t out_img_stride, int64_t out_offset, void* stream);
 
-/* All pyramid levels of a dense anchor head in ONE persistent launch (bulk-async-copy pipeline, csrc/dense_decode.cu).
+/* All pyramid levels of a dense anchor head in ONE launch (flat 16-byte streaming kernel, csrc/dense_decode.cu).
  * Every level shares n, a, c; level l: head (n, a*(5+c), h, w) device, anchors_wh (a,2) device, first output row
  * out_offset.  Levels whose h*w is not a multiple of 4 (or an unaligned head) make the call fall back to one
  * det_dense_decode_level launch per level -- same results. */

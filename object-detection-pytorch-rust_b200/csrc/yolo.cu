@@ -4,9 +4,7 @@
 //    image: coalesced 16-byte loads of the image's logits into shared memory, sigmoid/exp decode, conf x class
 //    scores, score threshold with an order-preserving block-scan compaction, and the per-class NMS of
 //    nms_small.cuh -- the candidates never leave shared memory.
-//  * det_dense_decode_level : dense anchor head in the conv layout (N, A*(5+C), H, W).  A thread owns 4 consecutive
-//    spatial positions: every channel plane is read with coalesced 16-byte loads, the class arg-max is kept in
-//    registers, outputs are (h, w, a)-ordered boxes / best score / best class.
+//  (the dense anchor head decode lives in dense_decode.cu)
 //
 // No reference implementation exists for either; the specification is
 // oracle/ref_torch.py (yolo_decode, yolo_select_nms, dense_decode).
@@ -206,173 +204,6 @@ static int launch_yolo_fast(const float* head, const float* priors, const YoloPa
     return DET_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// dense anchor head, conv layout
-// ------------------------------------------------------------------------------------------------
-template <int V>
-__global__ void __launch_bounds__(256)
-dense_decode_level_kernel(const float* __restrict__ head, int a, int c, int h, int w, float stride,
-                          const float2* __restrict__ anchors_wh, float scale_clamp, float4* __restrict__ boxes_out,
-                          float* __restrict__ score_out, int64_t* __restrict__ class_out, int64_t out_img_stride,
-                          int64_t out_offset) {
-    const int64_t hw = (int64_t)h * w;
-    const int64_t groups = (hw + V - 1) / V;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int img = blockIdx.y;
-    if (g >= groups) return;
-    const int64_t p0 = g * V;
-    const int nch = 5 + c;
-    float colf[V], rowf[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        colf[v] = (float)((p0 + v) % w);
-        rowf[v] = (float)((p0 + v) / w);
-    }
-    const int64_t obase = (int64_t)img * out_img_stride + out_offset;
-    for (int ai = 0; ai < a; ++ai) {
-        const float* pl = head + ((int64_t)(img * a + ai) * nch) * hw + p0;
-        float t[5][V];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            if (V == 4) {
-                const float4 q = ld_stream(reinterpret_cast<const float4*>(pl + k * hw));
-                t[k][0] = q.x; t[k][1] = q.y; t[k][2] = q.z; t[k][3] = q.w;
-            } else {
-                t[k][0] = ld_stream(pl + k * hw);
-            }
-        }
-        float best[V];
-        int bidx[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            best[v] = -INFINITY;
-            bidx[v] = 0;
-        }
-        // running arg-max over the class planes; first maximum wins, a NaN wins over everything (torch.max)
-#pragma unroll 4
-        for (int k = 0; k < c; ++k) {
-            float q[V];
-            if (V == 4) {
-                const float4 q4 = ld_stream(reinterpret_cast<const float4*>(pl + (int64_t)(5 + k) * hw));
-                q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
-            } else {
-                q[0] = ld_stream(pl + (int64_t)(5 + k) * hw);
-            }
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const bool take = (k == 0) || (q[v] > best[v]) || (q[v] != q[v] && best[v] == best[v]);
-                best[v] = take ? q[v] : best[v];
-                bidx[v] = take ? k : bidx[v];
-            }
-        }
-        const float2 awh = anchors_wh[ai];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const float cx = (sigmoidf_ref(t[0][v]) + colf[v]) * stride;
-            const float cy = (sigmoidf_ref(t[1][v]) + rowf[v]) * stride;
-            float tw = t[2][v], th = t[3][v];
-            tw = (tw > scale_clamp) ? scale_clamp : tw;
-            th = (th > scale_clamp) ? scale_clamp : th;
-            const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
-            const int64_t o = obase + (p0 + v) * a + ai;
-            boxes_out[o] = make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh);
-            score_out[o] = sigmoidf_ref(t[4][v]) * (c > 0 ? sigmoidf_ref(best[v]) : 1.0f);
-            class_out[o] = (int64_t)bidx[v];
-        }
-    }
-}
-
-
-// ---- sliced variant (hw % 4 == 0, 5 + c >= 20): the channel planes of one (image, anchor) are split into 4 slices
-// handled by 4 adjacent lanes, each lane streaming its slice with 16-byte loads over 4 consecutive positions -- 4x the
-// threads and bytes in flight of the kernel above -- then the (max, arg-max) pairs meet in a 2-step butterfly and each
-// lane finishes ONE of the 4 positions (the box logits travel through shared memory).
-constexpr int kDenseSlices = 4;
-constexpr int kDenseThreads = 256;
-
-// torch.max(dim) order on (value, class): a NaN beats everything, the first maximum / first NaN wins
-__device__ __forceinline__ bool argmax_takes(float v, int iv, float best, int ib) {
-    const bool vn = v != v, bn = best != best;
-    if (vn || bn) return vn && (!bn || iv < ib);
-    return v > best || (v == best && iv < ib);
-}
-
-__global__ void __launch_bounds__(kDenseThreads)
-dense_decode_sliced_kernel(const float* __restrict__ head, int a, int c, int hw, int w, float stride,
-                           const float2* __restrict__ anchors_wh, float scale_clamp, float4* __restrict__ boxes_out,
-                           float* __restrict__ score_out, int64_t* __restrict__ class_out, int64_t out_img_stride,
-                           int64_t out_offset) {
-    __shared__ float s_t[kDenseThreads / kDenseSlices][5][4];
-    const int nch = 5 + c, per = (nch + kDenseSlices - 1) / kDenseSlices;
-    const int groups = hw >> 2;
-    const int gt = blockIdx.x * kDenseThreads + threadIdx.x;
-    const int g = gt >> 2, sl = gt & 3;  // 4 adjacent lanes = the 4 slices of one position group
-    const int ia = blockIdx.y;           // image * a + anchor
-    const int img = ia / a, ai = ia - img * a;
-    const bool live = g < groups;
-    const int gg = live ? g : groups - 1;  // dead lanes shadow a valid group (they only take part in the shuffles)
-    const int k0 = sl * per, k1 = min(nch, k0 + per);
-    const float4* pl = reinterpret_cast<const float4*>(head + ((int64_t)ia * nch + k0) * hw) + gg;
-    const int plane4 = hw >> 2;  // float4 stride between planes
-    int k = k0;
-    if (sl == 0) {  // planes 0..4 are the box logits (per >= 5)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const float4 q = ld_stream(pl + (int64_t)j * plane4);
-            *reinterpret_cast<float4*>(&s_t[threadIdx.x >> 2][j][0]) = q;
-        }
-        k = 5;
-    }
-    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int bidx[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) bidx[v] = k - 5;
-    const float4* pk = pl + (int64_t)(k - k0) * plane4;
-#pragma unroll 8
-    for (; k < k1; ++k, pk += plane4) {
-        const float4 q4 = ld_stream(pk);
-        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const bool take = (q[v] > best[v]) || (q[v] != q[v] && best[v] == best[v]);
-            best[v] = take ? q[v] : best[v];
-            bidx[v] = take ? k - 5 : bidx[v];
-        }
-    }
-#pragma unroll
-    for (int o = 1; o < kDenseSlices; o <<= 1) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best[v], o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx[v], o);
-            if (argmax_takes(ob, oi, best[v], bidx[v])) {
-                best[v] = ob;
-                bidx[v] = oi;
-            }
-        }
-    }
-    __syncwarp();  // the box logits of this group were written by its slice-0 lane (same warp)
-    // lane `sl` finishes position 4*g + sl
-    const float mybest = sl == 0 ? best[0] : sl == 1 ? best[1] : sl == 2 ? best[2] : best[3];
-    const int myidx = sl == 0 ? bidx[0] : sl == 1 ? bidx[1] : sl == 2 ? bidx[2] : bidx[3];
-    const float (*t)[4] = s_t[threadIdx.x >> 2];
-    const int pos = gg * 4 + sl;
-    const float colf = (float)(pos % w), rowf = (float)(pos / w);
-    const float cx = (sigmoidf_ref(t[0][sl]) + colf) * stride;
-    const float cy = (sigmoidf_ref(t[1][sl]) + rowf) * stride;
-    float tw = t[2][sl], th = t[3][sl];
-    tw = (tw > scale_clamp) ? scale_clamp : tw;
-    th = (th > scale_clamp) ? scale_clamp : th;
-    const float2 awh = anchors_wh[ai];
-    const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
-    if (live) {
-        const int64_t o = (int64_t)img * out_img_stride + out_offset + (int64_t)pos * a + ai;
-        st_stream(boxes_out + o, make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh));
-        st_stream(score_out + o, sigmoidf_ref(t[4][sl]) * sigmoidf_ref(mybest));
-        class_out[o] = (int64_t)myidx;
-    }
-}
-
 }  // namespace det
 
 using namespace det;
@@ -425,39 +256,6 @@ int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h
     if (PC <= 2048)
         return launch_yolo<2048>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
     return launch_yolo<4096>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
-}
-
-int det_dense_decode_level(const float* head, int n, int a, int c, int h, int w, int stride, const float* anchors_wh,
-                           float scale_clamp, float* boxes_out, float* score_out, int64_t* class_out,
-                           int64_t out_img_stride, int64_t out_offset, void* stream) {
-    DET_CHECK_ARG(n >= 0 && a >= 1 && c >= 0 && h >= 0 && w >= 0, "bad size");
-    const int64_t hw = (int64_t)h * w;
-    if (n == 0 || hw == 0) return DET_OK;
-    DET_CHECK_ARG(head && anchors_wh && boxes_out && score_out && class_out, "null pointer");
-    DET_CHECK_ARG(out_offset >= 0 && out_img_stride >= hw * a + out_offset, "output slot out of range");
-    DET_CHECK_ARG(n <= 65535, "n > 65535");
-    if (!aligned16(boxes_out)) {
-        set_error("boxes_out must be 16-byte aligned");
-        return DET_ERR_ALIGN;
-    }
-    auto awh = reinterpret_cast<const float2*>(anchors_wh);
-    auto bo = reinterpret_cast<float4*>(boxes_out);
-    cudaStream_t st = as_stream(stream);
-    if (hw % 4 == 0 && aligned16(head) && 5 + c >= 5 * kDenseSlices && (int64_t)n * a <= 65535 && hw < (1 << 28)) {
-        dim3 grid((unsigned)((hw + kDenseThreads - 1) / kDenseThreads), (unsigned)(n * a));
-        dense_decode_sliced_kernel<<<grid, kDenseThreads, 0, st>>>(head, a, c, (int)hw, w, (float)stride, awh, scale_clamp,
-                                                                    bo, score_out, class_out, out_img_stride, out_offset);
-    } else if (hw % 4 == 0 && aligned16(head)) {
-        dim3 grid((unsigned)((hw / 4 + 255) / 256), (unsigned)n);
-        dense_decode_level_kernel<4><<<grid, 256, 0, st>>>(head, a, c, h, w, (float)stride, awh, scale_clamp, bo,
-                                                           score_out, class_out, out_img_stride, out_offset);
-    } else {
-        dim3 grid((unsigned)((hw + 255) / 256), (unsigned)n);
-        dense_decode_level_kernel<1><<<grid, 256, 0, st>>>(head, a, c, h, w, (float)stride, awh, scale_clamp, bo,
-                                                           score_out, class_out, out_img_stride, out_offset);
-    }
-    DET_LAUNCH_OK("dense_decode_level_kernel");
-    return DET_OK;
 }
 
 }  // extern "C"
