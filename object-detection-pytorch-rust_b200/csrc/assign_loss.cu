@@ -21,11 +21,12 @@ struct MatchRule {
 };
 
 __device__ __forceinline__ int8_t bucket_label(const MatchRule& r, float v) {
-    int k = 0;
+    // thresholds ascending: bucket [thr[k-1], thr[k]); static indices only, so the rule stays in the constant bank
+    int8_t lab = r.lab[0];
 #pragma unroll
     for (int i = 0; i < kMaxThresholds; ++i)
-        if (i < r.nthr && v >= r.thr[i]) k = i + 1;  // thresholds ascending: bucket [thr[k-1], thr[k])
-    return r.lab[k];
+        if (i < r.nthr && v >= r.thr[i]) lab = r.lab[i + 1];
+    return lab;
 }
 
 // IoUs are >= 0, so their bit patterns order like unsigned integers
@@ -37,121 +38,199 @@ constexpr int kMatchThreads = 256;
 constexpr int kMatchPerThread = 4;
 constexpr int kGtChunk = 512;
 
+// Block bounding box of the CTA's anchors (union of finite coordinates): a gt box that does not overlap it has zero
+// intersection -- hence IoU exactly 0 -- with every anchor of the CTA, so it is skipped as a whole ("culled").
+// Anchors are laid out (h, w, a): 1024 consecutive anchors are a few feature-map rows, and most gt boxes miss them.
+struct BlockBox {
+    float x1, y1, x2, y2;
+};
+
+__device__ __forceinline__ BlockBox block_bbox(const float4* ab, const bool* valid, float (*s_red)[4]) {
+    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (valid[k]) {  // fminf / fmaxf skip NaN coordinates: a NaN anchor never intersects anything anyway
+            x1 = fminf(x1, ab[k].x); y1 = fminf(y1, ab[k].y);
+            x2 = fmaxf(x2, ab[k].z); y2 = fmaxf(y2, ab[k].w);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o)); y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_red[wid][0] = x1; s_red[wid][1] = y1; s_red[wid][2] = x2; s_red[wid][3] = y2;
+    }
+    __syncthreads();
+    BlockBox b{INFINITY, INFINITY, -INFINITY, -INFINITY};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        b.x1 = fminf(b.x1, s_red[w][0]); b.y1 = fminf(b.y1, s_red[w][1]);
+        b.x2 = fmaxf(b.x2, s_red[w][2]); b.y2 = fmaxf(b.y2, s_red[w][3]);
+    }
+    return b;
+}
+
+// true iff the gt box certainly has zero intersection with every anchor inside `bb` (comparisons with NaN are false:
+// a NaN gt box is never culled and takes the exact path)
+__device__ __forceinline__ bool culled_by(const BlockBox& bb, const float4 g) {
+    return g.z <= bb.x1 || g.x >= bb.x2 || g.w <= bb.y1 || g.y >= bb.y2;
+}
+
+constexpr int kMatchImgs = 8;  // images walked by one CTA: its anchors and their block box stay in registers
+
 // pass 1: per anchor column max / argmax over the image's gt boxes, threshold label; per gt row max (atomics)
 __global__ void __launch_bounds__(kMatchThreads)
 match_pass1_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
-                   int64_t r, MatchRule rule, int64_t* __restrict__ matched, int8_t* __restrict__ labels,
-                   float* __restrict__ matched_iou, float* __restrict__ rowmax) {
+                   int n, int64_t r, int64_t sum_g, MatchRule rule, int64_t* __restrict__ matched,
+                   int8_t* __restrict__ labels, float* __restrict__ matched_iou, float* __restrict__ rowmax,
+                   float* __restrict__ blockmax) {
     __shared__ float4 s_gt[kGtChunk];
     __shared__ float s_area[kGtChunk];
     __shared__ float s_rmax[kGtChunk];
-    const int img = blockIdx.y;
-    const int g0 = gt_off[img], g1 = gt_off[img + 1];
-    const int G = g1 - g0;
+    __shared__ unsigned short s_list[kGtChunk];
+    __shared__ int s_nlist;
+    __shared__ float s_red[kMatchThreads / 32][4];
+    __shared__ int s_off[kMatchImgs + 1];
+    const int i0 = blockIdx.y * kMatchImgs, ni = min(kMatchImgs, n - i0);
     const int64_t base = (int64_t)blockIdx.x * (kMatchThreads * kMatchPerThread);
     float4 ab[kMatchPerThread];
-    float aa[kMatchPerThread], best[kMatchPerThread];
-    int bidx[kMatchPerThread];
+    float aa[kMatchPerThread];
+    bool valid[kMatchPerThread];
 #pragma unroll
     for (int k = 0; k < kMatchPerThread; ++k) {
         const int64_t j = base + k * kMatchThreads + threadIdx.x;
-        ab[k] = (j < r) ? anchors[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        valid[k] = j < r;
+        ab[k] = valid[k] ? anchors[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         aa[k] = box_area(ab[k]);
-        best[k] = -1.0f;  // any IoU (>= 0) beats it, so the first gt wins ties like torch.max(dim=0)
-        bidx[k] = 0;
     }
-    for (int c0 = 0; c0 < G; c0 += kGtChunk) {
-        const int cn = min(kGtChunk, G - c0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
-            const float4 b = gt[g0 + c0 + t];
-            s_gt[t] = b;
-            s_area[t] = box_area(b);
-            s_rmax[t] = 0.0f;
-        }
-        __syncthreads();
-        for (int t = 0; t < cn; ++t) {
-            const float4 gb = s_gt[t];
-            const float ga = s_area[t];
-            float rm = 0.0f;
+    if (threadIdx.x <= ni) s_off[threadIdx.x] = gt_off[i0 + threadIdx.x];
+    const BlockBox bb = block_bbox(ab, valid, s_red);  // contains a barrier: s_off is visible afterwards
+    for (int ii = 0; ii < ni; ++ii) {
+        const int img = i0 + ii;
+        const int g0 = s_off[ii], G = s_off[ii + 1] - g0;
+        float best[kMatchPerThread];
+        int bidx[kMatchPerThread];
 #pragma unroll
-            for (int k = 0; k < kMatchPerThread; ++k) {
-                const int64_t j = base + k * kMatchThreads + threadIdx.x;
-                // pairwise_iou(gt, anchors): boxes1 = gt, boxes2 = anchors (rpn.py:167)
-                const float v = (j < r) ? pair_iou(gb, ga, ab[k], aa[k]) : 0.0f;
-                if (v > best[k]) {
-                    best[k] = v;
-                    bidx[k] = c0 + t;
-                }
-                rm = fmaxf(rm, v);
+        for (int k = 0; k < kMatchPerThread; ++k) {
+            best[k] = 0.0f;  // IoUs are >= 0 and only a strictly larger one replaces the incumbent: gt 0 wins ties
+            bidx[k] = 0;     // at 0, exactly like torch.max(dim=0) on the materialised matrix
+        }
+        for (int c0 = 0; c0 < G; c0 += kGtChunk) {
+            const int cn = min(kGtChunk, G - c0);
+            __syncthreads();
+            if (threadIdx.x == 0) s_nlist = 0;
+            __syncthreads();
+            for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
+                const float4 b = gt[g0 + c0 + t];
+                s_gt[t] = b;
+                s_area[t] = box_area(b);
+                s_rmax[t] = 0.0f;
+                if (!culled_by(bb, b)) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)t;  // survivors, any order
             }
-            if (rule.allow_lq && rm > s_rmax[t]) atomic_max_nonneg(&s_rmax[t], rm);
-        }
-        __syncthreads();
-        if (rule.allow_lq)
-            for (int t = threadIdx.x; t < cn; t += kMatchThreads)
-                if (s_rmax[t] > 0.0f) atomic_max_nonneg(&rowmax[g0 + c0 + t], s_rmax[t]);
-    }
+            __syncthreads();
+            const int ns = s_nlist;
+            for (int q = 0; q < ns; ++q) {
+                const int t = (int)s_list[q];
+                const float4 gb = s_gt[t];
+                const float ga = s_area[t];
+                float rm = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMatchPerThread; ++k) {
-        const int64_t j = base + k * kMatchThreads + threadIdx.x;
-        if (j >= r) continue;
-        const int64_t o = (int64_t)img * r + j;
-        if (G == 0) {  // matcher.py:67-77: no gt -> match 0, label labels[0]
-            matched[o] = 0;
-            labels[o] = rule.lab[0];
-            if (matched_iou) matched_iou[o] = 0.0f;
-        } else {
-            matched[o] = bidx[k];
-            labels[o] = bucket_label(rule, best[k]);
-            if (matched_iou) matched_iou[o] = best[k];
+                for (int k = 0; k < kMatchPerThread; ++k) {
+                    // pairwise_iou(gt, anchors): boxes1 = gt, boxes2 = anchors (rpn.py:167)
+                    const float v = valid[k] ? pair_iou(gb, ga, ab[k], aa[k]) : 0.0f;
+                    // torch.max(dim=0): the first maximum wins -- the list is unordered, so ties go to the lower index
+                    if (v > best[k] || (v == best[k] && c0 + t < bidx[k])) {
+                        best[k] = v;
+                        bidx[k] = c0 + t;
+                    }
+                    rm = fmaxf(rm, v);
+                }
+                if (rule.allow_lq) {  // one shared-memory atomic per warp, not per thread
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+                    if ((threadIdx.x & 31) == 0 && rm > s_rmax[t]) atomic_max_nonneg(&s_rmax[t], rm);
+                }
+            }
+            __syncthreads();
+            if (rule.allow_lq)
+                for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
+                    const float m = s_rmax[t];
+                    if (m > 0.0f) atomic_max_nonneg(&rowmax[g0 + c0 + t], m);
+                    // this CTA's own maximum for gt t: pass 2 only revisits the CTAs that hold the row maximum
+                    blockmax[(int64_t)blockIdx.x * sum_g + g0 + c0 + t] = m;
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < kMatchPerThread; ++k) {
+            const int64_t j = base + k * kMatchThreads + threadIdx.x;
+            if (j >= r) continue;
+            const int64_t o = (int64_t)img * r + j;
+            if (G == 0) {  // matcher.py:67-77: no gt -> match 0, label labels[0]
+                matched[o] = 0;
+                labels[o] = rule.lab[0];
+                if (matched_iou) matched_iou[o] = 0.0f;
+            } else {
+                matched[o] = bidx[k];
+                labels[o] = bucket_label(rule, best[k]);
+                if (matched_iou) matched_iou[o] = best[k];
+            }
         }
     }
 }
 
-// pass 2 (low-quality promotion, matcher.py:96-120): label 1 wherever IoU(gt, anchor) == max over anchors for that gt
+// pass 2 (low-quality promotion, matcher.py:96-120): label 1 wherever IoU(gt, anchor) == max over anchors for that gt.
+// Only a CTA whose own maximum for a gt (recorded by pass 1) equals the row maximum can hold such an anchor; a gt whose
+// row maximum is 0 promotes EVERY anchor (the reference's `Q == rowmax` is true everywhere, matcher.py:110-113).
 __global__ void __launch_bounds__(kMatchThreads)
 match_pass2_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
-                   int64_t r, const float* __restrict__ rowmax, int8_t* __restrict__ labels) {
-    __shared__ float4 s_gt[kGtChunk];
-    __shared__ float s_area[kGtChunk];
-    __shared__ float s_rmax[kGtChunk];
-    const int img = blockIdx.y;
-    const int g0 = gt_off[img], g1 = gt_off[img + 1];
-    const int G = g1 - g0;
-    if (G == 0) return;
+                   int n, int64_t r, int64_t sum_g, const float* __restrict__ rowmax,
+                   const float* __restrict__ blockmax, int8_t* __restrict__ labels) {
+    __shared__ unsigned short s_list[kGtChunk];
+    __shared__ int s_nlist, s_all;
+    __shared__ int s_off[kMatchImgs + 1];
+    const int i0 = blockIdx.y * kMatchImgs, ni = min(kMatchImgs, n - i0);
     const int64_t base = (int64_t)blockIdx.x * (kMatchThreads * kMatchPerThread);
-    float4 ab[kMatchPerThread];
-    float aa[kMatchPerThread];
-    bool hit[kMatchPerThread];
+    if (threadIdx.x <= ni) s_off[threadIdx.x] = gt_off[i0 + threadIdx.x];
+    __syncthreads();
+    for (int ii = 0; ii < ni; ++ii) {
+        const int img = i0 + ii;
+        const int g0 = s_off[ii], G = s_off[ii + 1] - g0;
+        for (int c0 = 0; c0 < G; c0 += kGtChunk) {
+            const int cn = min(kGtChunk, G - c0);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_nlist = 0;
+                s_all = 0;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
+                const float rm = rowmax[g0 + c0 + t];
+                if (rm == 0.0f) s_all = 1;
+                else if (blockmax[(int64_t)blockIdx.x * sum_g + g0 + c0 + t] == rm)
+                    s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)t;
+            }
+            __syncthreads();
+            const int ns = s_nlist;
+            const bool all = s_all != 0;
+            if (ns == 0 && !all) continue;  // block-uniform: the usual case
 #pragma unroll
-    for (int k = 0; k < kMatchPerThread; ++k) {
-        const int64_t j = base + k * kMatchThreads + threadIdx.x;
-        ab[k] = (j < r) ? anchors[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[k] = box_area(ab[k]);
-        hit[k] = false;
-    }
-    for (int c0 = 0; c0 < G; c0 += kGtChunk) {
-        const int cn = min(kGtChunk, G - c0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
-            const float4 b = gt[g0 + c0 + t];
-            s_gt[t] = b;
-            s_area[t] = box_area(b);
-            s_rmax[t] = rowmax[g0 + c0 + t];
+            for (int k = 0; k < kMatchPerThread; ++k) {
+                const int64_t j = base + k * kMatchThreads + threadIdx.x;
+                if (j >= r) continue;
+                bool hit = all;
+                if (!hit) {
+                    const float4 ab = anchors[j];
+                    const float aa = box_area(ab);
+                    for (int q = 0; q < ns; ++q) {
+                        const int g = g0 + c0 + (int)s_list[q];
+                        const float4 gb = gt[g];
+                        hit |= (pair_iou(gb, box_area(gb), ab, aa) == rowmax[g]);
+                    }
+                }
+                if (hit) labels[(int64_t)img * r + j] = 1;
+            }
         }
-        __syncthreads();
-        for (int t = 0; t < cn; ++t) {
-            const float4 gb = s_gt[t];
-            const float ga = s_area[t], rm = s_rmax[t];
-#pragma unroll
-            for (int k = 0; k < kMatchPerThread; ++k) hit[k] |= (pair_iou(gb, ga, ab[k], aa[k]) == rm);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kMatchPerThread; ++k) {
-        const int64_t j = base + k * kMatchThreads + threadIdx.x;
-        if (j < r && hit[k]) labels[(int64_t)img * r + j] = 1;
     }
 }
 
@@ -196,42 +275,94 @@ quality_pass2_kernel(const float* __restrict__ q, int64_t g, int64_t r, const fl
 }
 
 // ---- uniform random fg/bg subsample, one CTA per image -----------------------------------------------------------
-__device__ __forceinline__ uint32_t sample_key(uint64_t seed, uint32_t img, uint32_t j) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)img << 32) | j);  // splitmix64 finaliser
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (uint32_t)(z >> 32);
+// Every anchor gets the 32-bit key mix32(j * odd + image_seed) -- a bijection of j, so keys of one image never tie --
+// and the class keeps its `want` smallest keys: a uniformly random subset, reproducible from (seed, image, anchor).
+// The want-th smallest key is found without sorting the ~50k negatives: a first pass keeps only the keys under a
+// threshold that lets about want + 4 sqrt(want) + 16 of them through (a few hundred), the exact order statistic is
+// taken among those by rank counting, and a last pass rewrites the labels.  If the threshold pass comes back with too
+// few or too many candidates (a > 4-sigma event) the CTA falls back to an exact 4 x 8-bit radix select.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
 }
+__device__ __forceinline__ uint32_t sample_key(uint32_t img_seed, uint32_t j) { return mix32(j * 0x9E3779B1u + img_seed); }
 
-constexpr int kSampleThreads = 1024;
-constexpr int kTieCap = 256;
+constexpr int kSampleThreads = 512;
+constexpr int kCandCap = 1024;
 
 struct SampleSmem {
-    int hist[2][256];
     int cnt[2];
-    unsigned prefix[2];  // selected high bits of the k-th smallest key so far
-    int remaining[2];    // rank of the threshold key inside the current bucket
-    int ties[2][kTieCap];
-    int ntie[2];
+    int ncand[2];
+    unsigned sel[2];      // the want-th smallest key of the class: keys <= sel are kept
+    unsigned prefix[2];   // radix-select fallback state
+    int remaining[2];
+    int hist[2][256];
+    unsigned ckey[2][kCandCap];
 };
 
-// cls: 0 = positive (label == 1 here: anything that is neither -1 nor bg), 1 = background (label == 0)
+// labels of one image in 16-byte granules of the GLOBAL address space (rows of odd length start unaligned): granule c
+// covers row offsets [16c - a, 16c - a + 16), a = misalignment of the row start; bytes outside the row read as -1
+struct RowView {
+    int8_t* row;
+    int64_t r;
+    int a, ngran;
+    __device__ RowView(int8_t* p, int64_t r_) : row(p), r(r_) {
+        a = (int)(reinterpret_cast<uintptr_t>(p) & 15);
+        ngran = (int)((a + r + 15) >> 4);
+    }
+    __device__ __forceinline__ int64_t first(int c) const { return (int64_t)c * 16 - a; }
+    __device__ __forceinline__ bool full(int c) const { return first(c) >= 0 && first(c) + 16 <= r; }
+    __device__ __forceinline__ void load(int c, int8_t (&v)[16]) const {
+        const int64_t lo = first(c);
+        if (full(c)) {
+            const uint4 q = *reinterpret_cast<const uint4*>(row + lo);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = (int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = (lo + k >= 0 && lo + k < r) ? row[lo + k] : (int8_t)-1;
+        }
+    }
+    __device__ __forceinline__ void store(int c, const int8_t (&v)[16]) const {
+        const int64_t lo = first(c);
+        if (full(c)) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w[k >> 2] |= (uint32_t)(uint8_t)v[k] << (8 * (k & 3));
+            *reinterpret_cast<uint4*>(row + lo) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (lo + k >= 0 && lo + k < r) row[lo + k] = v[k];
+        }
+    }
+};
+
+// cls: 0 = positive (anything that is neither -1 nor background), 1 = background (label == 0), -1 = ignored
+__device__ __forceinline__ int label_class(int8_t l) { return l == 0 ? 1 : (l == -1 ? -1 : 0); }
+
 __global__ void __launch_bounds__(kSampleThreads)
 subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float positive_fraction, uint64_t seed) {
     __shared__ SampleSmem sm;
     const int img = blockIdx.x, tid = threadIdx.x;
-    int8_t* lab = labels + (int64_t)img * r;
+    const RowView rv(labels + (int64_t)img * r, r);
+    const uint32_t img_seed = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x632BE5ABu * (uint32_t)(img + 1)));
     if (tid < 2) {
         sm.cnt[tid] = 0;
-        sm.ntie[tid] = 0;
+        sm.ncand[tid] = 0;
     }
     __syncthreads();
+    // ---- pass A: class counts
     int c0 = 0, c1 = 0;
-    for (int64_t j = tid; j < r; j += kSampleThreads) {
-        const int8_t l = lab[j];
-        c0 += (l != -1 && l != 0);
-        c1 += (l == 0);
+    for (int c = tid; c < rv.ngran; c += kSampleThreads) {
+        int8_t v[16];
+        rv.load(c, v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            c0 += (v[k] != -1 && v[k] != 0);
+            c1 += (v[k] == 0);
+        }
     }
     c0 = warp_sum(c0);
     c1 = warp_sum(c1);
@@ -248,70 +379,108 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
     const int have[2] = {npos, nneg};
     const bool need[2] = {want_pos < npos, want_neg < nneg};  // otherwise the whole class is kept
     if (!need[0] && !need[1]) return;
-    // radix select (4 x 8 bits) of the want[c]-th smallest key of each class that needs thinning
-    if (tid < 2) {
-        sm.prefix[tid] = 0;
-        sm.remaining[tid] = want[tid];  // we look for the key with rank want[c] (1-based) when want[c] > 0
+    // ---- pass B: candidates under a threshold sized for want + slack survivors
+    unsigned thr[2];
+    bool direct[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float slack = 4.0f * sqrtf((float)want[c]) + 16.0f;
+        const double p = ((double)want[c] + (double)slack) / (double)max(have[c], 1);
+        thr[c] = p >= 1.0 ? 0xffffffffu : (unsigned)(p * 4294967296.0);
+        direct[c] = need[c] && want[c] > 0 && (double)want[c] + 2.0 * slack <= (double)kCandCap;
     }
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        __syncthreads();
-        for (int t = tid; t < 512; t += kSampleThreads) (&sm.hist[0][0])[t] = 0;
-        __syncthreads();
-        const unsigned pre0 = sm.prefix[0], pre1 = sm.prefix[1];
-        const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int64_t j = tid; j < r; j += kSampleThreads) {
-            const int8_t l = lab[j];
-            if (l == -1) continue;
-            const int c = (l == 0) ? 1 : 0;
-            if (!need[c] || want[c] == 0) continue;
-            const uint32_t key = sample_key(seed, (uint32_t)img, (uint32_t)j);
-            if ((key & himask) == ((c ? pre1 : pre0) & himask)) atomicAdd(&sm.hist[c][(key >> shift) & 255], 1);
-        }
-        __syncthreads();
-        if (tid < 2 && need[tid] && want[tid] > 0) {
-            int rem = sm.remaining[tid], b = 0;
-            while (b < 255 && rem > sm.hist[tid][b]) {
-                rem -= sm.hist[tid][b];
-                ++b;
+    if (direct[0] || direct[1]) {
+        for (int c = tid; c < rv.ngran; c += kSampleThreads) {
+            int8_t v[16];
+            rv.load(c, v);
+            const int64_t j0 = rv.first(c);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int cls = label_class(v[k]);
+                if (cls < 0 || !direct[cls]) continue;
+                const unsigned key = sample_key(img_seed, (uint32_t)(j0 + k));
+                if (key <= thr[cls]) {
+                    const int slot = atomicAdd(&sm.ncand[cls], 1);
+                    if (slot < kCandCap) sm.ckey[cls][slot] = key;
+                }
             }
-            sm.remaining[tid] = rem;  // rank inside bucket b
-            sm.prefix[tid] |= (unsigned)b << shift;
         }
     }
     __syncthreads();
-    // keys < T are kept; among keys == T the `remaining` lowest indices are kept
-    const unsigned T[2] = {sm.prefix[0], sm.prefix[1]};
-    for (int64_t j = tid; j < r; j += kSampleThreads) {
-        const int8_t l = lab[j];
-        if (l == -1) continue;
-        const int c = (l == 0) ? 1 : 0;
-        if (!need[c] || want[c] == 0) continue;
-        if (sample_key(seed, (uint32_t)img, (uint32_t)j) == T[c]) {
-            const int slot = atomicAdd(&sm.ntie[c], 1);
-            if (slot < kTieCap) sm.ties[c][slot] = (int)j;
-        }
-    }
-    __syncthreads();
-    for (int64_t j = tid; j < r; j += kSampleThreads) {
-        const int8_t l = lab[j];
-        if (l == -1) continue;
-        const int c = (l == 0) ? 1 : 0;
-        if (!need[c]) continue;
-        bool keep = false;
-        if (want[c] > 0) {
-            const uint32_t key = sample_key(seed, (uint32_t)img, (uint32_t)j);
-            if (key < T[c]) keep = true;
-            else if (key == T[c]) {
+    // ---- pass C: the want-th smallest key, by rank counting among the candidates
+    bool radix[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int nc = sm.ncand[c];
+        const bool ok = direct[c] && nc >= want[c] && nc <= kCandCap;
+        radix[c] = need[c] && want[c] > 0 && !ok;
+        if (ok) {
+            for (int t = tid; t < nc; t += kSampleThreads) {
+                const unsigned key = sm.ckey[c][t];
                 int rank = 0;
-                const int nt = min(sm.ntie[c], kTieCap);
-                for (int t = 0; t < nt; ++t) rank += (sm.ties[c][t] < (int)j);
-                keep = rank < sm.remaining[c];
+                for (int q = 0; q < nc; ++q) rank += sm.ckey[c][q] < key;
+                if (rank == want[c] - 1) sm.sel[c] = key;
             }
         }
-        if (!keep) lab[j] = -1;
     }
-    (void)have;
+    if (radix[0] || radix[1]) {  // exact fallback: 4 x 8-bit radix select of the want-th smallest key
+        if (tid < 2) {
+            sm.prefix[tid] = 0;
+            sm.remaining[tid] = want[tid];
+        }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            __syncthreads();
+            for (int t = tid; t < 512; t += kSampleThreads) (&sm.hist[0][0])[t] = 0;
+            __syncthreads();
+            const unsigned pre[2] = {sm.prefix[0], sm.prefix[1]};
+            const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            for (int c = tid; c < rv.ngran; c += kSampleThreads) {
+                int8_t v[16];
+                rv.load(c, v);
+                const int64_t j0 = rv.first(c);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int cls = label_class(v[k]);
+                    if (cls < 0 || !radix[cls]) continue;
+                    const unsigned key = sample_key(img_seed, (uint32_t)(j0 + k));
+                    if ((key & himask) == (pre[cls] & himask)) atomicAdd(&sm.hist[cls][(key >> shift) & 255], 1);
+                }
+            }
+            __syncthreads();
+            if (tid < 2 && radix[tid]) {
+                int rem = sm.remaining[tid], b = 0;
+                while (b < 255 && rem > sm.hist[tid][b]) {
+                    rem -= sm.hist[tid][b];
+                    ++b;
+                }
+                sm.remaining[tid] = rem;
+                sm.prefix[tid] |= (unsigned)b << shift;
+            }
+        }
+        __syncthreads();
+        if (tid < 2 && radix[tid]) sm.sel[tid] = sm.prefix[tid];
+    }
+    __syncthreads();
+    // ---- pass D: everything of a thinned class above its selection key becomes -1
+    const unsigned sel[2] = {sm.sel[0], sm.sel[1]};
+    for (int c = tid; c < rv.ngran; c += kSampleThreads) {
+        int8_t v[16];
+        rv.load(c, v);
+        const int64_t j0 = rv.first(c);
+        bool changed = false;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int cls = label_class(v[k]);
+            if (cls < 0 || !need[cls]) continue;
+            const bool keep = want[cls] > 0 && sample_key(img_seed, (uint32_t)(j0 + k)) <= sel[cls];
+            if (!keep) {
+                v[k] = -1;
+                changed = true;
+            }
+        }
+        if (changed) rv.store(c, v);
+    }
 }
 
 // ---- fused RPN loss forward + backward ---------------------------------------------------------------------------
@@ -360,50 +529,43 @@ rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ del
     }
     float acc_cls = 0.f, acc_loc = 0.f;
     int npos = 0, nneg = 0;
-    const int64_t nquads = (total + 3) >> 2;
-    for (int64_t qd = (int64_t)blockIdx.x * kLossThreads + threadIdx.x; qd < nquads;
-         qd += (int64_t)gridDim.x * kLossThreads) {
-        const int64_t e0 = qd << 2;
-        const bool full = e0 + 4 <= total;
-        int8_t lab[4];
-        if (full) {
-            const uint32_t pk = __ldcs(reinterpret_cast<const unsigned int*>(labels + e0));
-            lab[0] = (int8_t)(pk & 255); lab[1] = (int8_t)((pk >> 8) & 255);
-            lab[2] = (int8_t)((pk >> 16) & 255); lab[3] = (int8_t)(pk >> 24);
+    // A warp owns 128 consecutive anchors per iteration.  Labels arrive as one 32-bit word per lane (4 anchors, one
+    // coalesced 128-byte load) and are re-dealt with shuffles so that in each of the 4 rounds lane l works on anchor
+    // base + 32*round + l: every gradient store of a warp is then one contiguous 128-byte (logits) or 512-byte
+    // (deltas) run of full sectors.
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
+    const int64_t warps_total = ((int64_t)gridDim.x * kLossThreads) >> 5;
+    for (int64_t base = warp_global * 128; base < total; base += warps_total * 128) {
+        const int64_t e4 = base + 4 * lane;
+        uint32_t word;
+        if (e4 + 4 <= total) {
+            word = __ldcs(reinterpret_cast<const unsigned int*>(labels + e4));
         } else {
-            for (int k = 0; k < 4; ++k) lab[k] = (e0 + k < total) ? labels[e0 + k] : (int8_t)-1;
+            word = 0xffffffffu;  // label -1: ignored
+            for (int k = 0; k < 4; ++k)
+                if (e4 + k < total) word = (word & ~(0xffu << (8 * k))) | ((uint32_t)(uint8_t)labels[e4 + k] << (8 * k));
         }
-        const bool any_valid = (lab[0] >= 0) | (lab[1] >= 0) | (lab[2] >= 0) | (lab[3] >= 0);
-        float gl[4] = {0.f, 0.f, 0.f, 0.f};
-        if (any_valid) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (lab[k] < 0) continue;
-                const int64_t e = e0 + k;
+        for (int round = 0; round < 4; ++round) {
+            const uint32_t w = __shfl_sync(0xffffffffu, word, 8 * round + (lane >> 2));
+            const int lab = (int)(int8_t)((w >> (8 * (lane & 3))) & 0xffu);
+            const int64_t e = base + 32 * round + lane;
+            if (e >= total) continue;
+            float gl = 0.f;
+            if (lab >= 0) {
                 const float x = logits[e];
-                const float y = (float)lab[k];
+                const float y = (float)lab;
                 // BCE with logits: (1-y)*x - log_sigmoid(x), log_sigmoid(x) = min(x,0) - log1p(exp(-|x|))
                 const float ls = fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
                 acc_cls += (1.f - y) * x - ls;
-                gl[k] = (1.f / (1.f + expf(-x)) - y) * gs_cls;
-                npos += lab[k] == 1;
-                nneg += lab[k] == 0;
+                gl = (1.f / (1.f + expf(-x)) - y) * gs_cls;
+                npos += lab == 1;
+                nneg += lab == 0;
             }
-        }
-        if (grad_logits) {
-            if (full) {
-                st_stream(reinterpret_cast<float4*>(grad_logits + e0), make_float4(gl[0], gl[1], gl[2], gl[3]));
-            } else {
-                for (int k = 0; k < 4; ++k)
-                    if (e0 + k < total) grad_logits[e0 + k] = gl[k];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int64_t e = e0 + k;
-            if (e >= total) break;
+            if (grad_logits) st_stream(grad_logits + e, gl);
             float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lab[k] == 1) {
+            if (lab == 1) {
                 const int64_t img = e / r, j = e - img * r;
                 const float4 g = gt[gt_off[img] + matched[e]];
                 const float4 tgt = encode_target(anchors[j], g, wt);
@@ -421,7 +583,7 @@ rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ del
     acc_cls = warp_sum(acc_cls);
     acc_loc = warp_sum(acc_loc);
     float fpos = warp_sum((float)npos), fneg = warp_sum((float)nneg);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wid = threadIdx.x >> 5;
     if (lane == 0) {
         s_part[0][wid] = acc_cls;
         s_part[1][wid] = acc_loc;
@@ -543,10 +705,12 @@ using namespace det;
 
 extern "C" {
 
+static int64_t match_blocks(int64_t r) { return (r + kMatchThreads * kMatchPerThread - 1) / (kMatchThreads * kMatchPerThread); }
+
 int64_t det_match_workspace_bytes(int n, int64_t r, int64_t sum_g) {
     (void)n;
-    (void)r;
-    return ((sum_g > 0 ? sum_g : 1) * 4 + 255) / 256 * 256;
+    // row maxima (sum_g) + per-CTA maxima (blocks x sum_g), fp32
+    return ((sum_g > 0 ? sum_g : 1) * (1 + match_blocks(r > 0 ? r : 1)) * 4 + 255) / 256 * 256;
 }
 
 int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors,
@@ -557,7 +721,7 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
     if (n == 0 || r == 0) return DET_OK;
     DET_CHECK_ARG(gt_offsets && anchors && matched_idx && labels, "null pointer");
     DET_CHECK_ARG(sum_g == 0 || gt_boxes, "null gt_boxes");
-    DET_CHECK_ARG(n <= 65535, "n > 65535");
+    DET_CHECK_ARG(n <= 65535 * kMatchImgs, "n too large");
     if (!aligned16(anchors) || (gt_boxes && !aligned16(gt_boxes))) {
         set_error("gt_boxes/anchors must be 16-byte aligned");
         return DET_ERR_ALIGN;
@@ -565,8 +729,9 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
     MatchRule rule;
     int rc = fill_rule(rule, thresholds_host, labels_host, num_thresholds, allow_low_quality);
     if (rc != DET_OK) return rc;
-    if (allow_low_quality && sum_g > 0 && (!workspace || workspace_bytes < (int64_t)sizeof(float) * sum_g)) {
-        set_error("workspace too small");
+    if (allow_low_quality && sum_g > 0 &&
+        (!workspace || workspace_bytes < (int64_t)sizeof(float) * sum_g * (1 + match_blocks(r)))) {
+        set_error("workspace too small: need %lld bytes", (long long)det_match_workspace_bytes(n, r, sum_g));
         return DET_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
@@ -575,13 +740,15 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
         cudaError_t e = cudaMemsetAsync(rowmax, 0, sizeof(float) * (size_t)sum_g, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     }
-    dim3 grid((unsigned)((r + kMatchThreads * kMatchPerThread - 1) / (kMatchThreads * kMatchPerThread)), (unsigned)n);
+    dim3 grid((unsigned)((r + kMatchThreads * kMatchPerThread - 1) / (kMatchThreads * kMatchPerThread)),
+              (unsigned)((n + kMatchImgs - 1) / kMatchImgs));
     auto g4 = reinterpret_cast<const float4*>(gt_boxes);
     auto a4 = reinterpret_cast<const float4*>(anchors);
-    match_pass1_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, r, rule, matched_idx, labels, matched_iou, rowmax);
+    match_pass1_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, n, r, sum_g, rule, matched_idx, labels, matched_iou,
+                                                       rowmax, rowmax + sum_g);
     DET_LAUNCH_OK("match_pass1_kernel");
     if (allow_low_quality && sum_g > 0) {
-        match_pass2_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, r, rowmax, labels);
+        match_pass2_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, n, r, sum_g, rowmax, rowmax + sum_g, labels);
         DET_LAUNCH_OK("match_pass2_kernel");
     }
     return DET_OK;
@@ -653,8 +820,8 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
         return DET_ERR_ALIGN;
     }
     const int64_t total = (int64_t)n * r;
-    const int64_t nquads = (total + 3) / 4;
-    int64_t blocks = (nquads + kLossThreads - 1) / kLossThreads;
+    const int64_t nwarps = (total + 127) / 128;
+    int64_t blocks = (nwarps + kLossThreads / 32 - 1) / (kLossThreads / 32);
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     rpn_loss_kernel<<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(

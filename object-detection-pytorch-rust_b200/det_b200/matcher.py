@@ -79,12 +79,13 @@ class Matcher:
         labels = torch.empty((n, r), dtype=torch.int8, device=dev)
         miou = torch.empty((n, r), dtype=torch.float32, device=dev) if return_iou else None
         if n and r:
-            ws = torch.empty((max(sum_g, 1),), dtype=torch.float32, device=dev)
+            wsb = N.fn("det_match_workspace_bytes")(n, r, sum_g)
+            ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
             thr, lab = _rule_arrays(self._inner, self.labels)
             with torch.cuda.device(dev):
                 N.call("det_match_anchors", N.ptr(table), N.ptr(offsets), n, sum_g, N.ptr(anchors), r, thr, lab,
                        len(self._inner), int(self.allow_low_quality_matches), N.ptr(matched), N.ptr(labels),
-                       N.ptr(miou), N.ptr(ws), ws.numel() * 4, N.stream())
+                       N.ptr(miou), N.ptr(ws), wsb, N.stream())
         return (matched, labels, miou) if return_iou else (matched, labels)
 
 
