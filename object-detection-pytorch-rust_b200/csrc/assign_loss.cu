@@ -77,12 +77,12 @@ __device__ __forceinline__ bool culled_by(const BlockBox& bb, const float4 g) {
     return g.z <= bb.x1 || g.x >= bb.x2 || g.w <= bb.y1 || g.y >= bb.y2;
 }
 
-constexpr int kMatchImgs = 8;  // images walked by one CTA: its anchors and their block box stay in registers
+constexpr int kMatchImgs = 8;  // at most this many images are walked by one CTA (anchors + block box stay in registers)
 
 // pass 1: per anchor column max / argmax over the image's gt boxes, threshold label; per gt row max (atomics)
 __global__ void __launch_bounds__(kMatchThreads)
 match_pass1_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
-                   int n, int64_t r, int64_t sum_g, MatchRule rule, int64_t* __restrict__ matched,
+                   int n, int imgs, int64_t r, int64_t sum_g, MatchRule rule, int64_t* __restrict__ matched,
                    int8_t* __restrict__ labels, float* __restrict__ matched_iou, float* __restrict__ rowmax,
                    float* __restrict__ blockmax) {
     __shared__ float4 s_gt[kGtChunk];
@@ -92,7 +92,7 @@ match_pass1_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt
     __shared__ int s_nlist;
     __shared__ float s_red[kMatchThreads / 32][4];
     __shared__ int s_off[kMatchImgs + 1];
-    const int i0 = blockIdx.y * kMatchImgs, ni = min(kMatchImgs, n - i0);
+    const int i0 = blockIdx.y * imgs, ni = min(imgs, n - i0);
     const int64_t base = (int64_t)blockIdx.x * (kMatchThreads * kMatchPerThread);
     float4 ab[kMatchPerThread];
     float aa[kMatchPerThread];
@@ -184,12 +184,12 @@ match_pass1_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt
 // row maximum is 0 promotes EVERY anchor (the reference's `Q == rowmax` is true everywhere, matcher.py:110-113).
 __global__ void __launch_bounds__(kMatchThreads)
 match_pass2_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
-                   int n, int64_t r, int64_t sum_g, const float* __restrict__ rowmax,
+                   int n, int imgs, int64_t r, int64_t sum_g, const float* __restrict__ rowmax,
                    const float* __restrict__ blockmax, int8_t* __restrict__ labels) {
     __shared__ unsigned short s_list[kGtChunk];
     __shared__ int s_nlist, s_all;
     __shared__ int s_off[kMatchImgs + 1];
-    const int i0 = blockIdx.y * kMatchImgs, ni = min(kMatchImgs, n - i0);
+    const int i0 = blockIdx.y * imgs, ni = min(imgs, n - i0);
     const int64_t base = (int64_t)blockIdx.x * (kMatchThreads * kMatchPerThread);
     if (threadIdx.x <= ni) s_off[threadIdx.x] = gt_off[i0 + threadIdx.x];
     __syncthreads();
@@ -721,7 +721,7 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
     if (n == 0 || r == 0) return DET_OK;
     DET_CHECK_ARG(gt_offsets && anchors && matched_idx && labels, "null pointer");
     DET_CHECK_ARG(sum_g == 0 || gt_boxes, "null gt_boxes");
-    DET_CHECK_ARG(n <= 65535 * kMatchImgs, "n too large");
+    DET_CHECK_ARG(n <= 65535, "n > 65535");
     if (!aligned16(anchors) || (gt_boxes && !aligned16(gt_boxes))) {
         set_error("gt_boxes/anchors must be 16-byte aligned");
         return DET_ERR_ALIGN;
@@ -740,15 +740,19 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
         cudaError_t e = cudaMemsetAsync(rowmax, 0, sizeof(float) * (size_t)sum_g, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     }
-    dim3 grid((unsigned)((r + kMatchThreads * kMatchPerThread - 1) / (kMatchThreads * kMatchPerThread)),
-              (unsigned)((n + kMatchImgs - 1) / kMatchImgs));
+    // images per CTA: amortise the anchor loads / block box when there are plenty of CTAs, keep one image per CTA when
+    // the grid would otherwise not fill the GPU (small anchor sets such as a 7x7 grid head)
+    const int64_t bx = match_blocks(r);
+    int imgs = (int)((bx * n) / ((int64_t)sm_count() * 16));
+    imgs = imgs < 1 ? 1 : (imgs > kMatchImgs ? kMatchImgs : imgs);
+    dim3 grid((unsigned)bx, (unsigned)((n + imgs - 1) / imgs));
     auto g4 = reinterpret_cast<const float4*>(gt_boxes);
     auto a4 = reinterpret_cast<const float4*>(anchors);
-    match_pass1_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, n, r, sum_g, rule, matched_idx, labels, matched_iou,
+    match_pass1_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, n, imgs, r, sum_g, rule, matched_idx, labels, matched_iou,
                                                        rowmax, rowmax + sum_g);
     DET_LAUNCH_OK("match_pass1_kernel");
     if (allow_low_quality && sum_g > 0) {
-        match_pass2_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, n, r, sum_g, rowmax, rowmax + sum_g, labels);
+        match_pass2_kernel<<<grid, kMatchThreads, 0, st>>>(g4, gt_offsets, a4, n, imgs, r, sum_g, rowmax, rowmax + sum_g, labels);
         DET_LAUNCH_OK("match_pass2_kernel");
     }
     return DET_OK;

@@ -39,6 +39,22 @@ def allreduce_sums_(sums: torch.Tensor) -> torch.Tensor:
     return sums
 
 
+class _Done:
+    """Stand-in work handle for the single-process case."""
+
+    def wait(self):
+        return True
+
+
+def allreduce_sums_async(sums: torch.Tensor):
+    """Same reduction, not waited for: returns a handle whose ``wait()`` makes the reduced values visible to the
+    current stream.  The loss scalars are only logged, so a training loop can wait one step late and keep the
+    collective's latency off the critical path (gradients of this path stay local to the rank)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.all_reduce(sums, op=dist.ReduceOp.SUM, async_op=True)
+    return _Done()
+
+
 def global_num_images(local_n: int, device=None) -> int:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         t = torch.tensor([local_n], dtype=torch.int64, device=device)

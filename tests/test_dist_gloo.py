@@ -50,7 +50,11 @@ def _worker(rank, world, port, out):
     sums[0] = part["cls_loss"] * (hi - lo) / n_global
     sums[1] = part["loc_loss"] * (hi - lo) / n_global
     sums[2], sums[3] = part["num_pos"], part["num_neg"]
+    late = sums.clone()
     det_b200.dist.allreduce_sums_(sums)
+    work = det_b200.dist.allreduce_sums_async(late)  # the one-step-late form used by the training loop
+    work.wait()
+    assert torch.equal(late, sums)
     if rank == 0:
         torch.save(sums, out)
     dist.barrier()
