@@ -14,6 +14,7 @@ from .yolo import YoloGridHead, DenseAnchorHead, YoloGridTrainer, YoloHostPipeli
 from .matcher import Matcher, subsample_labels_
 from .proposals import find_top_rpn_proposals, rpn_proposals_batched, add_ground_truth_to_proposals
 from .rpn import RegionProposalNetwork, Assignment, _dense_box_regression_loss
+from .roi import ROIHeads, subsample_labels
 from . import dist
 
 __all__ = [
@@ -21,5 +22,5 @@ __all__ = [
     "Box2BoxTransform", "AnchorGenerator", "generate_cell_anchors", "batched_nms", "nms", "nms_images",
     "YoloGridHead", "DenseAnchorHead", "YoloGridTrainer", "YoloHostPipeline", "Matcher", "subsample_labels_", "find_top_rpn_proposals",
     "rpn_proposals_batched", "add_ground_truth_to_proposals", "RegionProposalNetwork", "Assignment",
-    "_dense_box_regression_loss", "dist",
+    "_dense_box_regression_loss", "ROIHeads", "subsample_labels", "dist",
 ]

@@ -92,3 +92,37 @@ def test_shard_range_partitions_batch():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_subsample_labels_mirror_consumes_rng_like_the_reference():
+    """det.subsample_labels (reference python/src/utils.py:34-76) is plain torch: under the same seed it returns the
+    oracle's -- hence the reference's -- indices, on CPU tensors too (it launches no kernel of ours)."""
+    g = torch.Generator().manual_seed(3)
+    labels = torch.randint(-1, 5, (4000,), generator=g)
+    for num, frac, bg in [(256, 0.5, 0), (512, 0.25, 4), (16, 0.5, 2), (100000, 0.5, 0)]:
+        torch.manual_seed(11)
+        p1, n1 = det.subsample_labels(labels, num, frac, bg)
+        torch.manual_seed(11)
+        p2, n2 = O.subsample_labels(labels, num, frac, bg)
+        assert torch.equal(p1, p2) and torch.equal(n1, n2)
+        wp, wn = O.subsample_counts(int(((labels != -1) & (labels != bg)).sum()), int((labels == bg).sum()), num, frac)
+        assert (p1.numel(), n1.numel()) == (wp, wn)
+    e = torch.empty(0, dtype=torch.int64)
+    p, n = det.subsample_labels(e, 8, 0.5, 0)
+    assert p.numel() == 0 and n.numel() == 0
+
+
+def test_roi_heads_constructor_mirrors_reference():
+    m = det.Matcher([0.5], [0, 1], allow_low_quality_matches=False)
+    h = det.ROIHeads(num_classes=80, batch_size_per_image=512, positive_fraction=0.25, proposal_matcher=m)
+    assert (h.num_classes, h.batch_size_per_image, h.positive_fraction, h.proposal_append_gt) == (80, 512, 0.25, True)
+
+    class _MC:
+        thresholds, labels, allow_low_quality_matches = [0.5], [0, 1], False
+
+    class _RC:
+        num_classes, batch_size_per_image, positive_fraction, proposal_append_gt = 3, 64, 0.5, False
+        proposal_matcher = _MC()
+
+    b = det.ROIHeads.build(_RC())
+    assert (b.num_classes, b.batch_size_per_image, b.proposal_append_gt) == (3, 64, False)
