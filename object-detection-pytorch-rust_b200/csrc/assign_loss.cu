@@ -514,12 +514,66 @@ __device__ __forceinline__ void smooth_l1(float pred, float tgt, float beta, flo
     }
 }
 
+// GIoU loss of the box decoded from deltas `p` on anchor `a` against gt `g`, and its gradient wrt the four deltas.
+// Value: fvcore.nn.giou_loss restated (oracle/ref_torch.py giou_sum; third-party, unpinned by the reference):
+//   iou = I / (U + eps), loss = 1 - iou + (H - U) / (H + eps), I = 0 unless the boxes strictly overlap, eps = 1e-7.
+// Gradient: what autograd produces for that expression composed with Box2BoxTransform.apply_deltas
+// (box_regression.py:87-115): ties of max / min split the gradient in half, clamp(max=) passes it up to equality.
+__device__ __forceinline__ float giou_fwd_bwd(const float4 p, const float4 a, const float4 g, const CodecW wt,
+                                              float scale_clamp, float4& grad) {
+    const float eps = 1e-7f;
+    const float w = a.z - a.x, h = a.w - a.y;
+    const float cx = a.x + 0.5f * w, cy = a.y + 0.5f * h;
+    const float dx = p.x / wt.wx, dy = p.y / wt.wy;
+    const float dw_raw = p.z / wt.ww, dh_raw = p.w / wt.wh;
+    const float dw = fminf(dw_raw, scale_clamp), dh = fminf(dh_raw, scale_clamp);
+    const float pcx = dx * w + cx, pcy = dy * h + cy;
+    const float pw = expf(dw) * w, ph = expf(dh) * h;
+    const float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph, x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
+    const float ix1 = fmaxf(x1, g.x), iy1 = fmaxf(y1, g.y), ix2 = fminf(x2, g.z), iy2 = fminf(y2, g.w);
+    const bool overlap = (iy2 > iy1) && (ix2 > ix1);
+    const float I = overlap ? (ix2 - ix1) * (iy2 - iy1) : 0.0f;
+    const float A = (x2 - x1) * (y2 - y1);
+    const float U = A + (g.z - g.x) * (g.w - g.y) - I;
+    const float hx1 = fminf(x1, g.x), hy1 = fminf(y1, g.y), hx2 = fmaxf(x2, g.z), hy2 = fmaxf(y2, g.w);
+    const float H = (hx2 - hx1) * (hy2 - hy1);
+    const float iou = I / (U + eps);
+    const float loss = 1.0f - (iou - (H - U) / (H + eps));
+    // partial derivatives of the loss wrt I, A (through U) and H
+    const float ue = U + eps, he = H + eps;
+    const float dI = -(ue + I) / (ue * ue) + 1.0f / he;
+    const float dA = I / (ue * ue) - 1.0f / he;
+    const float dH = ue / (he * he);
+    auto sel = [](float v, float o, bool take_greater) {  // d max(v,o)/dv or d min(v,o)/dv
+        return v == o ? 0.5f : ((take_greater ? v > o : v < o) ? 1.0f : 0.0f);
+    };
+    float gx1 = -dA * (y2 - y1) - dH * (hy2 - hy1) * sel(x1, g.x, false);
+    float gx2 = dA * (y2 - y1) + dH * (hy2 - hy1) * sel(x2, g.z, true);
+    float gy1 = -dA * (x2 - x1) - dH * (hx2 - hx1) * sel(y1, g.y, false);
+    float gy2 = dA * (x2 - x1) + dH * (hx2 - hx1) * sel(y2, g.w, true);
+    if (overlap) {
+        gx1 -= dI * (iy2 - iy1) * sel(x1, g.x, true);
+        gx2 += dI * (iy2 - iy1) * sel(x2, g.z, false);
+        gy1 -= dI * (ix2 - ix1) * sel(y1, g.y, true);
+        gy2 += dI * (ix2 - ix1) * sel(y2, g.w, false);
+    }
+    const float gcx = gx1 + gx2, gcy = gy1 + gy2;
+    const float gpw = 0.5f * (gx2 - gx1), gph = 0.5f * (gy2 - gy1);
+    grad.x = gcx * w / wt.wx;
+    grad.y = gcy * h / wt.wy;
+    grad.z = (dw_raw <= scale_clamp) ? gpw * pw / wt.ww : 0.0f;
+    grad.w = (dh_raw <= scale_clamp) ? gph * ph / wt.wh : 0.0f;
+    return loss;
+}
+
 constexpr int kLossThreads = 256;
 
+template <bool GIOU>
 __global__ void __launch_bounds__(kLossThreads)
 rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ deltas, const int8_t* __restrict__ labels,
                 const int64_t* __restrict__ matched, const float4* __restrict__ gt, const int32_t* __restrict__ gt_off,
-                const float4* __restrict__ anchors, int64_t total, int64_t r, CodecW wt, float beta, float gs_cls,
+                const float4* __restrict__ anchors, int64_t total, int64_t r, CodecW wt, float scale_clamp,
+                float beta, float gs_cls,
                 float gs_loc, const float* __restrict__ upstream, float* __restrict__ sums,
                 float* __restrict__ grad_logits, float4* __restrict__ grad_deltas) {
     __shared__ float s_part[4][kLossThreads / 32];
@@ -568,13 +622,19 @@ rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ del
             if (lab == 1) {
                 const int64_t img = e / r, j = e - img * r;
                 const float4 g = gt[gt_off[img] + matched[e]];
-                const float4 tgt = encode_target(anchors[j], g, wt);
                 const float4 p = deltas[e];
-                float v, d;
-                smooth_l1(p.x, tgt.x, beta, v, d); acc_loc += v; gd.x = d * gs_loc;
-                smooth_l1(p.y, tgt.y, beta, v, d); acc_loc += v; gd.y = d * gs_loc;
-                smooth_l1(p.z, tgt.z, beta, v, d); acc_loc += v; gd.z = d * gs_loc;
-                smooth_l1(p.w, tgt.w, beta, v, d); acc_loc += v; gd.w = d * gs_loc;
+                if (GIOU) {
+                    float4 dd;
+                    acc_loc += giou_fwd_bwd(p, anchors[j], g, wt, scale_clamp, dd);
+                    gd = make_float4(dd.x * gs_loc, dd.y * gs_loc, dd.z * gs_loc, dd.w * gs_loc);
+                } else {
+                    const float4 tgt = encode_target(anchors[j], g, wt);
+                    float v, d;
+                    smooth_l1(p.x, tgt.x, beta, v, d); acc_loc += v; gd.x = d * gs_loc;
+                    smooth_l1(p.y, tgt.y, beta, v, d); acc_loc += v; gd.y = d * gs_loc;
+                    smooth_l1(p.z, tgt.z, beta, v, d); acc_loc += v; gd.z = d * gs_loc;
+                    smooth_l1(p.w, tgt.w, beta, v, d); acc_loc += v; gd.w = d * gs_loc;
+                }
             }
             if (grad_deltas) st_stream(grad_deltas + e, gd);
         }
@@ -809,12 +869,8 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
                  float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
                  float grad_scale_cls, float grad_scale_loc, const float* upstream, float* sums, float* grad_logits,
                  float* grad_deltas, void* stream) {
-    (void)scale_clamp;
     DET_CHECK_ARG(n >= 0 && r >= 0, "negative size");
-    if (loss_type != 0) {
-        set_error("loss_type %d (GIoU) is not implemented in this round; use smooth_l1", loss_type);
-        return DET_ERR_UNSUPPORTED;
-    }
+    DET_CHECK_ARG(loss_type == 0 || loss_type == 1, "loss_type must be 0 (smooth-L1) or 1 (GIoU)");
     if (n == 0 || r == 0) return DET_OK;
     DET_CHECK_ARG(logits && deltas && labels && matched_idx && gt_offsets && anchors && sums, "null pointer");
     if (!aligned16(deltas) || !aligned16(anchors) || !aligned16(logits) || (gt_boxes && !aligned16(gt_boxes)) ||
@@ -828,10 +884,19 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
     int64_t blocks = (nwarps + kLossThreads / 32 - 1) / (kLossThreads / 32);
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    rpn_loss_kernel<<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(
-        logits, reinterpret_cast<const float4*>(deltas), labels, matched_idx, reinterpret_cast<const float4*>(gt_boxes),
-        gt_offsets, reinterpret_cast<const float4*>(anchors), total, r, CodecW{wx, wy, ww, wh}, smooth_l1_beta,
-        grad_scale_cls, grad_scale_loc, upstream, sums, grad_logits, reinterpret_cast<float4*>(grad_deltas));
+    auto g4 = reinterpret_cast<const float4*>(gt_boxes);
+    auto a4 = reinterpret_cast<const float4*>(anchors);
+    auto d4 = reinterpret_cast<const float4*>(deltas);
+    auto gd4 = reinterpret_cast<float4*>(grad_deltas);
+    const CodecW wt{wx, wy, ww, wh};
+    if (loss_type == 1)
+        rpn_loss_kernel<true><<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(
+            logits, d4, labels, matched_idx, g4, gt_offsets, a4, total, r, wt, scale_clamp, smooth_l1_beta, grad_scale_cls,
+            grad_scale_loc, upstream, sums, grad_logits, gd4);
+    else
+        rpn_loss_kernel<false><<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(
+            logits, d4, labels, matched_idx, g4, gt_offsets, a4, total, r, wt, scale_clamp, smooth_l1_beta, grad_scale_cls,
+            grad_scale_loc, upstream, sums, grad_logits, gd4);
     DET_LAUNCH_OK("rpn_loss_kernel");
     return DET_OK;
 }

@@ -228,3 +228,39 @@ def test_forward_training_from_heads(det, O):
     (losses["cls_loss"] + losses["loc_loss"]).backward()
     assert all(t.grad is not None and torch.isfinite(t.grad).all() for t in o_g + d_g)
     assert float(losses["cls_loss"]) > 0 and all(len(p) <= 1000 for p in props)
+
+
+def test_rpn_giou_loss_forward_backward_vs_oracle(det, O):
+    """box_reg_loss_type="giou" (reference box_regression.py:159-165; fvcore giou_loss restated by the oracle --
+    third-party arithmetic, unpinned by the reference): value and gradients against autograd through the oracle."""
+    n = 3
+    torch.manual_seed(0)
+    anc, gts, labs, idxs, mboxes, logits, deltas = _rpn_loss_case(O, n, 9, 0.0)
+    deltas = deltas * 0.6
+    deltas[0, :50, 2] = 6.0  # beyond scale_clamp: the clamp must stop the gradient
+    lg = logits.clone().requires_grad_(True)
+    dl = deltas.clone().requires_grad_(True)
+    want = O.rpn_losses(anc, lg, torch.stack(labs), dl, torch.stack(mboxes), box_reg_loss_type="giou")
+    (want["cls_loss"] + 3.0 * want["loc_loss"]).backward()
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS, box_reg_loss_type="giou")
+    table = torch.cat(gts, 0).cuda()
+    off = torch.tensor([0] + list(torch.tensor([len(x) for x in gts]).cumsum(0)), dtype=torch.int32).cuda()
+    labs_t = torch.stack(labs)
+    labs_t[0, :50] = 1  # make the clamped rows foreground (matched gt index stays valid)
+    want = O.rpn_losses(anc, lg, labs_t, dl, torch.stack(mboxes), box_reg_loss_type="giou")
+    lg.grad = None
+    dl.grad = None
+    (want["cls_loss"] + 3.0 * want["loc_loss"]).backward()
+    asg = det.Assignment(labs_t.cuda(), torch.stack(idxs).cuda(), table, off)
+    glg = logits.cuda().requires_grad_(True)
+    gdl = deltas.cuda().requires_grad_(True)
+    res = rpn.fused_losses(anc.cuda(), glg, gdl, asg)
+    (res["cls_loss"] + 3.0 * res["loc_loss"]).backward()
+    torch.testing.assert_close(res["loc_loss"].cpu(), want["loc_loss"].detach(), rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(res["cls_loss"].cpu(), want["cls_loss"].detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(gdl.grad.cpu(), dl.grad, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(glg.grad.cpu(), lg.grad, rtol=1e-5, atol=1e-9)
+    assert float(gdl.grad[0, :50, 2].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        det.RegionProposalNetwork(STRIDES, SIZES, RATIOS, box_reg_loss_type="l2").fused_losses(
+            anc.cuda(), logits.cuda(), deltas.cuda(), asg)
