@@ -234,6 +234,71 @@ match_pass2_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt
     }
 }
 
+// ---- small anchor sets (r <= 128, e.g. the 98 priors of a 7x7x2 grid head): ONE WARP PER IMAGE, both passes fused.
+// Lane l owns anchors l, l+32, l+64, l+96; the image's gt boxes are broadcast loads; the row maximum of a gt is a warp
+// reduction, so the low-quality promotion (IoU == row max) is decided in the same iteration -- no workspace, no
+// second launch, no block barrier.
+constexpr int kSmallMatchWarps = 8;
+
+__global__ void __launch_bounds__(kSmallMatchWarps * 32)
+match_small_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
+                   int n, int r, MatchRule rule, int64_t* __restrict__ matched, int8_t* __restrict__ labels,
+                   float* __restrict__ matched_iou) {
+    const int lane = threadIdx.x & 31;
+    const int img = blockIdx.x * kSmallMatchWarps + (threadIdx.x >> 5);
+    if (img >= n) return;
+    float4 ab[4];
+    float aa[4], best[4];
+    int bidx[4];
+    bool valid[4], hit[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = lane + 32 * k;
+        valid[k] = j < r;
+        ab[k] = valid[k] ? anchors[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        aa[k] = box_area(ab[k]);
+        best[k] = 0.0f;  // gt 0 wins ties at IoU 0, like torch.max(dim=0)
+        bidx[k] = 0;
+        hit[k] = false;
+    }
+    const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
+    for (int t = 0; t < G; ++t) {
+        const float4 gb = gt[g0 + t];
+        const float ga = box_area(gb);
+        float v[4], rm = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = valid[k] ? pair_iou(gb, ga, ab[k], aa[k]) : 0.0f;
+            if (v[k] > best[k]) {
+                best[k] = v[k];
+                bidx[k] = t;
+            }
+            rm = fmaxf(rm, v[k]);
+        }
+        if (rule.allow_lq) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hit[k] |= (v[k] == rm);  // matcher.py:110-120 (rm == 0 promotes everything)
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = lane + 32 * k;
+        if (j >= r) continue;
+        const int64_t o = (int64_t)img * r + j;
+        if (G == 0) {  // matcher.py:67-77: no gt -> match 0, label labels[0]
+            matched[o] = 0;
+            labels[o] = rule.lab[0];
+            if (matched_iou) matched_iou[o] = 0.0f;
+        } else {
+            matched[o] = bidx[k];
+            labels[o] = hit[k] ? (int8_t)1 : bucket_label(rule, best[k]);
+            if (matched_iou) matched_iou[o] = best[k];
+        }
+    }
+}
+
 // ---- Matcher on a materialised (g, r) quality matrix ------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 quality_pass1_kernel(const float* __restrict__ q, int64_t g, int64_t r, MatchRule rule, int64_t* __restrict__ matched,
@@ -664,75 +729,143 @@ struct YoloLossParams {
     float stride_x, stride_y, lambda_coord, lambda_noobj, grad_scale;
 };
 
-__global__ void __launch_bounds__(128)
-yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labels, const int64_t* __restrict__ matched,
-                 const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
-                 const float2* __restrict__ priors, YoloLossParams prm, const float* __restrict__ upstream,
-                 float* __restrict__ sums, float* __restrict__ grad_head) {
-    __shared__ float s_part[5][4];
-    const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
-                up_cls = upstream ? upstream[2] : 1.f;
-    const int S2 = prm.s * prm.s, B = prm.b, C = prm.c, ch = B * 5 + C;
-    const int64_t cells = (int64_t)prm.n * S2;
-    const int64_t ci = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    float a_loc = 0.f, a_obj = 0.f, a_cls = 0.f, a_pos = 0.f, a_neg = 0.f;
-    if (ci < cells) {
-        const int img = (int)(ci / S2), cell = (int)(ci - (int64_t)img * S2);
-        const int row = cell / prm.s, col = cell - row * prm.s;
-        const float* t = head + ci * ch;
-        float* g = grad_head ? grad_head + ci * ch : nullptr;
-        if (g)
-            for (int k = 0; k < C; ++k) g[B * 5 + k] = 0.f;
-        for (int bi = 0; bi < B; ++bi) {
-            const int64_t p = (int64_t)img * S2 * B + (int64_t)cell * B + bi;
-            const int8_t lab = labels[p];
-            float gx = 0.f, gy = 0.f, gw = 0.f, gh = 0.f, gc = 0.f;
-            const float tc = t[bi * 5 + 4];
-            if (lab >= 0) {
-                const float y = (float)lab;
-                const float wgt = (lab == 1) ? 1.0f : prm.lambda_noobj;
-                const float ls = fminf(tc, 0.f) - log1pf(expf(-fabsf(tc)));
-                a_obj += wgt * ((1.f - y) * tc - ls);
-                gc = wgt * (1.f / (1.f + expf(-tc)) - y) * prm.grad_scale * up_obj;
-                a_pos += lab == 1;
-                a_neg += lab == 0;
-            }
-            if (lab == 1) {
-                const int64_t gi = gt_off[img] + matched[p];
-                const float4 gb = gt[gi];
-                const float2 pr = priors[bi];
-                const float bw = gb.z - gb.x, bh = gb.w - gb.y;
-                const float xs = (gb.x + 0.5f * bw) / prm.stride_x - (float)col;
-                const float ys = (gb.y + 0.5f * bh) / prm.stride_y - (float)row;
-                const float tws = logf(bw / pr.x), ths = logf(bh / pr.y);
-                const float sx = 1.f / (1.f + expf(-t[bi * 5 + 0])), sy = 1.f / (1.f + expf(-t[bi * 5 + 1]));
-                const float dx = sx - xs, dy = sy - ys, dw = t[bi * 5 + 2] - tws, dh = t[bi * 5 + 3] - ths;
-                a_loc += dx * dx + dy * dy + dw * dw + dh * dh;
-                const float k2 = 2.0f * prm.lambda_coord * prm.grad_scale * up_loc;
-                gx = k2 * dx * sx * (1.f - sx);
-                gy = k2 * dy * sy * (1.f - sy);
-                gw = k2 * dw;
-                gh = k2 * dh;
-                const int64_t cls = gt_cls[gi];
-                for (int k = 0; k < C; ++k) {
-                    const float x = t[B * 5 + k];
-                    const float y = (k == cls) ? 1.f : 0.f;
-                    const float ls = fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
-                    a_cls += (1.f - y) * x - ls;
-                    if (g) g[B * 5 + k] += (1.f / (1.f + expf(-x)) - y) * prm.grad_scale * up_cls;
-                }
-            }
-            if (g) {
-                g[bi * 5 + 0] = gx; g[bi * 5 + 1] = gy; g[bi * 5 + 2] = gw; g[bi * 5 + 3] = gh; g[bi * 5 + 4] = gc;
+// per (image, cell): loss terms and gradients, reading `t` (ch logits of the cell) and writing `g` (same layout) or not
+__device__ __forceinline__ void yolo_cell_loss(const float* t, float* g, int img, int cell, const int8_t* __restrict__ labels,
+                                               const int64_t* __restrict__ matched, const float4* __restrict__ gt,
+                                               const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
+                                               const float2* __restrict__ priors, const YoloLossParams& prm, float up_loc,
+                                               float up_obj, float up_cls, float (&acc)[5]) {
+    const int S2 = prm.s * prm.s, B = prm.b, C = prm.c;
+    const int row = cell / prm.s, col = cell - row * prm.s;
+    if (g)
+        for (int k = 0; k < C; ++k) g[B * 5 + k] = 0.f;
+    for (int bi = 0; bi < B; ++bi) {
+        const int64_t p = (int64_t)img * S2 * B + (int64_t)cell * B + bi;
+        const int8_t lab = labels[p];
+        float gx = 0.f, gy = 0.f, gw = 0.f, gh = 0.f, gc = 0.f;
+        const float tc = t[bi * 5 + 4];
+        if (lab >= 0) {
+            const float y = (float)lab;
+            const float wgt = (lab == 1) ? 1.0f : prm.lambda_noobj;
+            const float ls = fminf(tc, 0.f) - log1pf(expf(-fabsf(tc)));
+            acc[1] += wgt * ((1.f - y) * tc - ls);
+            gc = wgt * (1.f / (1.f + expf(-tc)) - y) * prm.grad_scale * up_obj;
+            acc[3] += lab == 1;
+            acc[4] += lab == 0;
+        }
+        if (lab == 1) {
+            const int64_t gi = gt_off[img] + matched[p];
+            const float4 gb = gt[gi];
+            const float2 pr = priors[bi];
+            const float bw = gb.z - gb.x, bh = gb.w - gb.y;
+            const float xs = (gb.x + 0.5f * bw) / prm.stride_x - (float)col;
+            const float ys = (gb.y + 0.5f * bh) / prm.stride_y - (float)row;
+            const float tws = logf(bw / pr.x), ths = logf(bh / pr.y);
+            const float sx = 1.f / (1.f + expf(-t[bi * 5 + 0])), sy = 1.f / (1.f + expf(-t[bi * 5 + 1]));
+            const float dx = sx - xs, dy = sy - ys, dw = t[bi * 5 + 2] - tws, dh = t[bi * 5 + 3] - ths;
+            acc[0] += dx * dx + dy * dy + dw * dw + dh * dh;
+            const float k2 = 2.0f * prm.lambda_coord * prm.grad_scale * up_loc;
+            gx = k2 * dx * sx * (1.f - sx);
+            gy = k2 * dy * sy * (1.f - sy);
+            gw = k2 * dw;
+            gh = k2 * dh;
+            const int64_t cls = gt_cls[gi];
+            for (int k = 0; k < C; ++k) {
+                const float x = t[B * 5 + k];
+                const float y = (k == cls) ? 1.f : 0.f;
+                const float ls = fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+                acc[2] += (1.f - y) * x - ls;
+                if (g) g[B * 5 + k] += (1.f / (1.f + expf(-x)) - y) * prm.grad_scale * up_cls;
             }
         }
+        if (g) {
+            g[bi * 5 + 0] = gx; g[bi * 5 + 1] = gy; g[bi * 5 + 2] = gw; g[bi * 5 + 3] = gh; g[bi * 5 + 4] = gc;
+        }
     }
-    float v[5] = {a_loc, a_obj, a_cls, a_pos, a_neg};
+}
+
+constexpr int kYoloLossThreads = 256;
+constexpr int kYoloLossTile = 5888;  // floats of head staged per CTA (and as many of gradient): 2 x 23 KB
+
+// A CTA stages the logits of `imgs` consecutive images in shared memory with coalesced 16-byte loads, one thread per
+// (image, cell) works on its cell there (a cell is 5B+C scattered floats: reading it straight from HBM wastes most of
+// every sector), and the gradient tile leaves the same way.
+__global__ void __launch_bounds__(kYoloLossThreads)
+yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labels, const int64_t* __restrict__ matched,
+                 const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
+                 const float2* __restrict__ priors, YoloLossParams prm, int imgs, const float* __restrict__ upstream,
+                 float* __restrict__ sums, float* __restrict__ grad_head) {
+    extern __shared__ __align__(16) float s_tile[];
+    __shared__ float s_part[5][kYoloLossThreads / 32];
+    const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
+                up_cls = upstream ? upstream[2] : 1.f;
+    const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c, per_img = S2 * ch;
+    const int img0 = blockIdx.x * imgs, ni = min(imgs, prm.n - img0);
+    const int count = ni * per_img;
+    const int64_t base = (int64_t)img0 * per_img;
+    float* s_in = s_tile;
+    float* s_out = s_tile + ((imgs * per_img + 3) & ~3);
+    const bool vec = ((base & 3) == 0) && ((count & 3) == 0);
+    if (vec) {
+        for (int i = threadIdx.x; i < (count >> 2); i += kYoloLossThreads)
+            reinterpret_cast<float4*>(s_in)[i] = ld_stream(reinterpret_cast<const float4*>(head + base) + i);
+    } else {
+        for (int i = threadIdx.x; i < count; i += kYoloLossThreads) s_in[i] = head[base + i];
+    }
+    __syncthreads();
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ci = threadIdx.x; ci < ni * S2; ci += kYoloLossThreads) {
+        const int li = ci / S2, cell = ci - li * S2;
+        yolo_cell_loss(s_in + (size_t)ci * ch, grad_head ? s_out + (size_t)ci * ch : nullptr, img0 + li, cell, labels,
+                       matched, gt, gt_cls, gt_off, priors, prm, up_loc, up_obj, up_cls, acc);
+    }
+    if (grad_head) {
+        __syncthreads();
+        if (vec) {
+            for (int i = threadIdx.x; i < (count >> 2); i += kYoloLossThreads)
+                st_stream(reinterpret_cast<float4*>(grad_head + base) + i, reinterpret_cast<const float4*>(s_out)[i]);
+        } else {
+            for (int i = threadIdx.x; i < count; i += kYoloLossThreads) grad_head[base + i] = s_out[i];
+        }
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        v[k] = warp_sum(v[k]);
-        if (lane == 0) s_part[k][wid] = v[k];
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) s_part[k][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float t = 0.f;
+        for (int w = 0; w < kYoloLossThreads / 32; ++w) t += s_part[threadIdx.x][w];
+        if (t != 0.f) atomicAdd(&sums[threadIdx.x], t);
+    }
+}
+
+// heads too large for the shared-memory tile: one thread per (image, cell) straight from global memory
+__global__ void __launch_bounds__(128)
+yolo_loss_direct_kernel(const float* __restrict__ head, const int8_t* __restrict__ labels,
+                        const int64_t* __restrict__ matched, const float4* __restrict__ gt,
+                        const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
+                        const float2* __restrict__ priors, YoloLossParams prm, const float* __restrict__ upstream,
+                        float* __restrict__ sums, float* __restrict__ grad_head) {
+    __shared__ float s_part[5][4];
+    const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
+                up_cls = upstream ? upstream[2] : 1.f;
+    const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c;
+    const int64_t cells = (int64_t)prm.n * S2;
+    const int64_t ci = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ci < cells) {
+        const int img = (int)(ci / S2), cell = (int)(ci - (int64_t)img * S2);
+        yolo_cell_loss(head + ci * ch, grad_head ? grad_head + ci * ch : nullptr, img, cell, labels, matched, gt, gt_cls,
+                       gt_off, priors, prm, up_loc, up_obj, up_cls, acc);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) s_part[k][wid] = v;
     }
     __syncthreads();
     if (threadIdx.x < 5) {
@@ -789,6 +922,14 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
     MatchRule rule;
     int rc = fill_rule(rule, thresholds_host, labels_host, num_thresholds, allow_low_quality);
     if (rc != DET_OK) return rc;
+    if (r <= 128) {  // one warp per image, both passes fused, no workspace
+        match_small_kernel<<<(unsigned)((n + kSmallMatchWarps - 1) / kSmallMatchWarps), kSmallMatchWarps * 32, 0,
+                             as_stream(stream)>>>(reinterpret_cast<const float4*>(gt_boxes), gt_offsets,
+                                                  reinterpret_cast<const float4*>(anchors), n, (int)r, rule, matched_idx,
+                                                  labels, matched_iou);
+        DET_LAUNCH_OK("match_small_kernel");
+        return DET_OK;
+    }
     if (allow_low_quality && sum_g > 0 &&
         (!workspace || workspace_bytes < (int64_t)sizeof(float) * sum_g * (1 + match_blocks(r)))) {
         set_error("workspace too small: need %lld bytes", (long long)det_match_workspace_bytes(n, r, sum_g));
@@ -917,10 +1058,22 @@ int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matche
     prm.stride_x = (float)((double)img_w / (double)s);
     prm.stride_y = (float)((double)img_h / (double)s);
     prm.lambda_coord = lambda_coord; prm.lambda_noobj = lambda_noobj; prm.grad_scale = grad_scale;
-    const int64_t cells = (int64_t)n * s * s;
-    yolo_loss_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, as_stream(stream)>>>(
-        head, labels, matched_idx, reinterpret_cast<const float4*>(gt_boxes), gt_classes, gt_offsets,
-        reinterpret_cast<const float2*>(priors), prm, upstream, sums, grad_head);
+    const int per_img = s * s * (b * 5 + c);
+    auto g4 = reinterpret_cast<const float4*>(gt_boxes);
+    auto p2 = reinterpret_cast<const float2*>(priors);
+    if (per_img <= kYoloLossTile) {
+        int imgs = kYoloLossTile / per_img;
+        // enough CTAs to fill the GPU first, then as many images per CTA as the tile holds
+        const int fill = (n + 2 * sm_count() - 1) / (2 * sm_count());
+        if (imgs > fill) imgs = fill < 1 ? 1 : fill;
+        const size_t smem = 2 * sizeof(float) * (size_t)((imgs * per_img + 3) & ~3);
+        yolo_loss_kernel<<<(unsigned)((n + imgs - 1) / imgs), kYoloLossThreads, smem, as_stream(stream)>>>(
+            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, imgs, upstream, sums, grad_head);
+    } else {
+        const int64_t cells = (int64_t)n * s * s;
+        yolo_loss_direct_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, as_stream(stream)>>>(
+            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, upstream, sums, grad_head);
+    }
     DET_LAUNCH_OK("yolo_loss_kernel");
     return DET_OK;
 }

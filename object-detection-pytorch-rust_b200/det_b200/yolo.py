@@ -188,6 +188,7 @@ class YoloGridTrainer:
         self.matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches)
         self.lambda_coord, self.lambda_noobj = float(lambda_coord), float(lambda_noobj)
         self._anchors = {}
+        self._scales = {}
 
     def prior_boxes(self, device) -> torch.Tensor:
         """(S*S*B,4) cell-centred prior boxes, order (row,col,b)."""
@@ -222,10 +223,17 @@ class YoloGridTrainer:
                    N.ptr(gt_classes), N.ptr(asg.gt_offsets), n, h.S, h.B, h.C, h.image_size[0], h.image_size[1],
                    N.ptr(h.priors_on(head_t.device)), self.lambda_coord, self.lambda_noobj, 1.0 / norm,
                    N.ptr(upstream), N.ptr(sums), N.ptr(grad_head), N.stream())
-        sums[0] *= self.lambda_coord / norm
-        sums[1] *= 1.0 / norm
-        sums[2] *= 1.0 / norm
-        return sums
+        return sums * self._sum_scale(norm, head_t.device)  # one launch: [lambda_coord/norm, 1/norm, 1/norm, 1, ...]
+
+    def _sum_scale(self, norm: float, device) -> torch.Tensor:
+        k = (float(norm), str(device))
+        v = self._scales.get(k)
+        if v is None:
+            if len(self._scales) > 64:
+                self._scales.clear()
+            v = torch.tensor([self.lambda_coord / norm, 1.0 / norm, 1.0 / norm, 1, 1, 1, 1, 1], dtype=torch.float32).to(device)
+            self._scales[k] = v
+        return v
 
     def loss(self, head_t: torch.Tensor, asg: YoloAssignment, gt_classes: torch.Tensor,
              normalizer: Optional[float] = None, with_grads: bool = False):
