@@ -113,6 +113,36 @@ __device__ __forceinline__ int next_pow2(int v) {
     return p;
 }
 
+// ---- warp-collective test of every lane's own box against the kept list klist[k0, k1) ------------------------------
+// The kept boxes are fetched 32 at a time, one per lane (a single round of memory latency: kept index, then box + area),
+// and handed round with shuffles -- the inner loop never waits for memory, which matters when the arrays live in HBM/L2
+// (large path) and the list is hundreds of boxes long.  Returns the lane's `alive` flag after the tests.
+template <typename KT, bool NONAN>
+__device__ __forceinline__ bool alive_after_kept(const float4* sbox, const float* sarea, const KT* klist, int k0, int k1,
+                                                 const float4 mb, float ma, bool alive, float thr_f) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int kb = k0; kb < k1; kb += 32) {
+        if (!__any_sync(FULL, alive)) break;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        float a = 0.f;
+        if (kb + lane < k1) {
+            const int kp = (int)klist[kb + lane];
+            b = sbox[kp];
+            a = sarea[kp];
+        }
+        const int cnt = min(32, k1 - kb);
+        for (int j = 0; j < cnt; ++j) {
+            if ((j & 7) == 0 && !__any_sync(FULL, alive)) break;
+            const float4 ob = make_float4(__shfl_sync(FULL, b.x, j), __shfl_sync(FULL, b.y, j), __shfl_sync(FULL, b.z, j),
+                                          __shfl_sync(FULL, b.w, j));
+            const float oa = __shfl_sync(FULL, a, j);
+            if (alive && nms_suppresses<NONAN>(ob, oa, mb, ma, thr_f)) alive = false;
+        }
+    }
+    return alive;
+}
+
 // ---- greedy suppression of one segment [s,e) by ONE WARP -------------------------------------------
 // sbox/sarea: boxes in sorted order; state: 0 candidate, 1 ignored, 2 kept; klist[s..s+nk): kept positions.
 // Per 32-box chunk: (a) every lane tests its box against the kept list, (b) every surviving lane builds, with
@@ -134,14 +164,7 @@ __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t*
             mb = sbox[p];
             ma = sarea[p];
         }
-        bool alive = act;
-        for (int k = 0; k < nk; ++k) {  // (a)
-            if ((k & 7) == 0 && !__any_sync(FULL, alive)) break;
-            const int kp = (int)klist[s + k];
-            const float4 kb = sbox[kp];
-            const float ka = sarea[kp];
-            if (alive && nms_suppresses<NONAN>(kb, ka, mb, ma, thr_f)) alive = false;
-        }
+        const bool alive = alive_after_kept<KT, NONAN>(sbox, sarea, klist, s, s + nk, mb, ma, act, thr_f);  // (a)
         const unsigned am = __ballot_sync(FULL, alive);
         // (b) every unordered pair of the chunk is tested once: lane l meets lane (l+d)&31 for d = 1..16.  If the
         //     partner is later in the order, lane l is the suppressor (row bit); if the rotation wrapped, the partner
@@ -201,15 +224,8 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             mb = sbox[p];
             ma = sarea[p];
         }
-        bool alive = act;
         // (a) against everything already kept in this segment
-        for (int k = 0; k < nk; ++k) {
-            if (!__any_sync(FULL, alive)) break;
-            const int kp = (int)klist[s + k];
-            const float4 kb = sbox[kp];
-            const float ka = sarea[kp];
-            if (alive && nms_suppresses<NONAN>(kb, ka, mb, ma, thr_f)) alive = false;
-        }
+        const bool alive = alive_after_kept<KT, NONAN>(sbox, sarea, klist, s, s + nk, mb, ma, act, thr_f);
         const unsigned bal = __ballot_sync(FULL, alive);
         if (worker && lane == 0) amask[wid] = bal;
         __syncthreads();

@@ -6,6 +6,7 @@
 // Launch sequence: [stats] -> keys -> tile sort -> log2(Mp/2048) merge passes -> gather (+segment discovery)
 //   -> warp segments (persistent, atomic work counter) -> CTA segments (persistent) -> re-key kept -> sort -> emit.
 #pragma once
+#include <cooperative_groups.h>
 #include "nms_core.cuh"
 
 namespace det {
@@ -16,6 +17,8 @@ constexpr int kSortThreads = 256;
 constexpr int kVT = kTile / kSortThreads;
 constexpr int kLargeWarpSegMax = 256;  // segments up to this length are swept by one warp
 constexpr int kSegThreads = 256;
+constexpr int kHugeSeg = 4096;     // longer segments are swept by the whole grid (cooperative kernel)
+constexpr int kHugeChunk = 512;    // positions resolved per step by the segment's leader CTA
 
 struct LargeImg {
     int32_t cnt;
@@ -25,14 +28,14 @@ struct LargeImg {
     int32_t nkept;
     int32_t bad;
     int32_t nsurv;
-    int32_t pad;
+    int32_t nonan;  // no box coordinate of the image is NaN: min/max in the predicate are single FMNMX instructions
 };
 
 struct LargeLayout {
     int n;
     int64_t m_max, mp, segcap;
     int64_t off_info, off_ctr, off_keys_a, off_keys_b, off_sbox, off_sarea, off_state, off_klist, off_seg_small,
-        off_seg_large, total;
+        off_seg_large, off_seg_huge, off_huge_nk, hugecap, total;
     LargeLayout(int n_, int64_t m_) : n(n_), m_max(m_) {
         mp = (m_max + kTile - 1) / kTile * kTile;
         segcap = mp < 32768 ? mp : 32768;
@@ -52,19 +55,23 @@ struct LargeLayout {
         off_klist = take(4 * n * mp);
         off_seg_small = take(16 * n * segcap);
         off_seg_large = take(16 * n * segcap);
+        hugecap = (int64_t)n * (mp / kHugeSeg + 1);
+        off_seg_huge = take(16 * hugecap);
+        off_huge_nk = take(8 * 3 * hugecap);
         total = o;
     }
 };
 
 struct LargeWs {
     LargeImg* info;
-    int32_t* ctr;  // [0] #small segs, [1] #large segs, [2] next small, [3] next large
+    int32_t* ctr;  // [0] #small segs, [1] #large segs, [2] next small, [3] next large, [4] #huge segs
     uint64_t *keys_a, *keys_b;
     float4* sbox;
     float* sarea;
     uint8_t* state;
     int32_t* klist;
-    int4 *seg_small, *seg_large;
+    int4 *seg_small, *seg_large, *seg_huge;
+    int2* huge_nk;  // [3][#huge]: running kept count, then the kept range of the chunk resolved in even / odd steps
     LargeWs(const LargeLayout& l, void* base) {
         char* b = static_cast<char*>(base);
         info = reinterpret_cast<LargeImg*>(b + l.off_info);
@@ -77,6 +84,8 @@ struct LargeWs {
         klist = reinterpret_cast<int32_t*>(b + l.off_klist);
         seg_small = reinterpret_cast<int4*>(b + l.off_seg_small);
         seg_large = reinterpret_cast<int4*>(b + l.off_seg_large);
+        seg_huge = reinterpret_cast<int4*>(b + l.off_seg_huge);
+        huge_nk = reinterpret_cast<int2*>(b + l.off_huge_nk);
     }
 };
 
@@ -131,7 +140,7 @@ large_stats_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__
         li.nkept = 0;
         li.bad = 0;
         li.nsurv = cnt;
-        li.pad = 0;
+        li.nonan = 1;  // cleared by the gather kernel if it meets a NaN coordinate
         info[img] = li;
     }
 }
@@ -233,14 +242,19 @@ static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStre
     return src;
 }
 
-// push segment [s,e) of image img on the short or long work list
-__device__ __forceinline__ void push_segment(int img, int s, int e, int32_t* ctr, int4* seg_small, int4* seg_large) {
+// push segment [s,e) of image img on the short, long or huge work list
+__device__ __forceinline__ void push_segment(int img, int s, int e, int32_t* ctr, int4* seg_small, int4* seg_large,
+                                             int4* seg_huge, int2* huge_nk) {
     if (e - s <= kLargeWarpSegMax) {
         const int slot = atomicAdd(&ctr[0], 1);
         seg_small[slot] = make_int4(img, s, e, 0);
-    } else {
+    } else if (e - s <= kHugeSeg) {
         const int slot = atomicAdd(&ctr[1], 1);
         seg_large[slot] = make_int4(img, s, e, 0);
+    } else {
+        const int slot = atomicAdd(&ctr[4], 1);
+        seg_huge[slot] = make_int4(img, s, e, 0);
+        huge_nk[slot] = make_int2(0, 0);
     }
 }
 
@@ -257,9 +271,9 @@ __device__ __forceinline__ int segment_end(const uint64_t* k, int p, int cnt, ui
 // ---- gather boxes into sorted order (+ coordinate offset), discover segments -------------------------
 static __global__ void __launch_bounds__(256)
 large_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats, int64_t m_max, int64_t mp,
-                    const LargeImg* __restrict__ info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
+                    LargeImg* info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
                     float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* ctr, int4* seg_small,
-                    int4* seg_large) {
+                    int4* seg_large, int4* seg_huge, int2* huge_nk) {
     const int img = blockIdx.y;
     const int p = blockIdx.x * 256 + threadIdx.x;
     const LargeImg li = info[img];
@@ -276,15 +290,16 @@ large_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict_
     sbox[(int64_t)img * mp + p] = b;
     sarea[(int64_t)img * mp + p] = box_area(b);
     state[(int64_t)img * mp + p] = 0;
+    if (!((b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w))) info[img].nonan = 0;
     const uint32_t sg = KLL::seg(key);
-    if (p == 0 || KLL::seg(k[p - 1]) != sg) push_segment(img, p, segment_end(k, p, li.cnt, sg), ctr, seg_small, seg_large);
+    if (p == 0 || KLL::seg(k[p - 1]) != sg) push_segment(img, p, segment_end(k, p, li.cnt, sg), ctr, seg_small, seg_large, seg_huge, huge_nk);
 }
 
 // ---- persistent segment kernels ---------------------------------------------------------------------------
 static __global__ void __launch_bounds__(128)
-large_warp_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const float* __restrict__ sarea,
-                           uint8_t* state, int32_t* klist, int32_t* ctr, const int4* __restrict__ seg_small,
-                           float thr_f, int max_keep) {
+large_warp_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const float4* __restrict__ sbox,
+                           const float* __restrict__ sarea, uint8_t* state, int32_t* klist, int32_t* ctr,
+                           const int4* __restrict__ seg_small, float thr_f, int max_keep) {
     const int lane = threadIdx.x & 31;
     const int total = ctr[0];
     while (true) {
@@ -294,14 +309,37 @@ large_warp_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const fl
         if (i >= total) break;
         const int4 sg = seg_small[i];
         const int64_t o = (int64_t)sg.x * mp;
-        warp_segment_nms<int32_t, false>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
+        if (info[sg.x].nonan)
+            warp_segment_nms<int32_t, true>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
+        else
+            warp_segment_nms<int32_t, false>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
     }
 }
 
+// stage boxes + areas of positions [s, e) in shared memory; returns pointers that are indexed with the GLOBAL position
+struct StagedBoxes {
+    const float4* box;
+    const float* area;
+};
+__device__ __forceinline__ StagedBoxes stage_boxes(const float4* __restrict__ sbox, const float* __restrict__ sarea, int s,
+                                                   int e, float4* sm_box, float* sm_area) {
+    for (int p = s + (int)threadIdx.x; p < e; p += (int)blockDim.x) {
+        sm_box[p - s] = sbox[p];
+        sm_area[p - s] = sarea[p];
+    }
+    __syncthreads();
+    return StagedBoxes{sm_box - s, sm_area - s};
+}
+
+// segments of 257 .. kHugeSeg boxes: one CTA each, the whole segment staged in shared memory (80 KB) so that the
+// kept-list tests and the chunk bit rows never wait for L2
 static __global__ void __launch_bounds__(kSegThreads)
-large_cta_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const float* __restrict__ sarea,
-                          uint8_t* state, int32_t* klist, int32_t* ctr, const int4* __restrict__ seg_large,
-                          float thr_f, int max_keep) {
+large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const float4* __restrict__ sbox,
+                          const float* __restrict__ sarea, uint8_t* state, int32_t* klist, int32_t* ctr,
+                          const int4* __restrict__ seg_large, float thr_f, int max_keep) {
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    float4* sm_box = reinterpret_cast<float4*>(seg_smem);
+    float* sm_area = reinterpret_cast<float*>(sm_box + kHugeSeg);
     __shared__ uint32_t rowbits[kSegThreads * (kSegThreads / 32)];
     __shared__ uint32_t amask[kSegThreads / 32];
     __shared__ int s_nk, s_next;
@@ -314,8 +352,127 @@ large_cta_segments_kernel(int64_t mp, const float4* __restrict__ sbox, const flo
         if (i >= total) break;
         const int4 sg = seg_large[i];
         const int64_t o = (int64_t)sg.x * mp;
-        cta_segment_nms<kSegThreads, int32_t, false>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
-                                              rowbits, amask, &s_nk);
+        const StagedBoxes sb = stage_boxes(sbox + o, sarea + o, sg.y, sg.z, sm_box, sm_area);
+        if (info[sg.x].nonan)
+            cta_segment_nms<kSegThreads, int32_t, true>(sb.box, sb.area, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
+                                                        rowbits, amask, &s_nk);
+        else
+            cta_segment_nms<kSegThreads, int32_t, false>(sb.box, sb.area, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
+                                                         rowbits, amask, &s_nk);
+        __syncthreads();
+    }
+}
+
+// ---- huge segments (one category with many thousands of boxes): the whole grid works on them together ----------
+// Greedy NMS in score order, kHugeChunk positions per step.  In step `it`
+//   * the segment's leader CTA first applies the kept boxes of chunk it-1 to the positions of chunk it, then resolves
+//     chunk it internally (cta_segment_nms on a shared-memory copy) and appends its survivors to the kept list;
+//   * meanwhile every other CTA (and the leaders once done) applies the kept boxes of chunk it-1 to the still-alive
+//     positions BEHIND chunk it;
+// then one grid-wide barrier.  The serial part (a 1024-box resolve) is thus hidden behind the O(kept x remaining) bulk
+// of the previous chunk, which is spread over all SMs.  All huge segments (typically one per image) advance in lock
+// step; a segment stops as soon as it has max_keep survivors.
+// huge_nk[h] = (kept so far, first kept of the newest chunk); huge_prev[h] (second int2) = the same pair one step ago.
+template <bool NONAN>
+__device__ __forceinline__ void huge_apply(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* state,
+                                           const int32_t* klist_seg, int k0, int k1, int p, int pe, float thr_f) {
+    // one position per thread of the CTA (p may be >= pe for the tail): warp-collective
+    bool alive = p < pe && state[p] == 0;
+    float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ma = 0.f;
+    if (alive) {
+        mb = sbox[p];
+        ma = sarea[p];
+    }
+    const bool was = alive;
+    alive = alive_after_kept<int32_t, NONAN>(sbox, sarea, klist_seg, k0, k1, mb, ma, alive, thr_f);
+    if (was && !alive) state[p] = 1;
+}
+
+static __global__ void __launch_bounds__(kSegThreads)
+large_huge_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const float4* __restrict__ sbox,
+                           const float* __restrict__ sarea, uint8_t* state, int32_t* klist,
+                           const int32_t* __restrict__ ctr, const int4* __restrict__ seg_huge, int2* huge_nk, float thr_f,
+                           int max_keep) {
+    namespace cg = cooperative_groups;
+    __shared__ __align__(16) float4 sm_box[kHugeChunk];
+    __shared__ float sm_area[kHugeChunk];
+    __shared__ uint32_t rowbits[kSegThreads * (kSegThreads / 32)];
+    __shared__ uint32_t amask[kSegThreads / 32];
+    __shared__ int s_nk;
+    const int nh = ctr[4];
+    if (nh == 0) return;  // grid-uniform
+    cg::grid_group grid = cg::this_grid();
+    int max_chunks = 0;
+    for (int h = 0; h < nh; ++h) {
+        const int4 sg = seg_huge[h];
+        max_chunks = max(max_chunks, (sg.z - sg.y + kHugeChunk - 1) / kHugeChunk);
+    }
+    // kept ranges are double-buffered by step parity: range[it & 1] is written by the leader in step it and read by
+    // everybody in step it + 1
+    int2* range0 = huge_nk;            // [nh]: x = kept so far (running), y unused
+    int2* ranges = huge_nk + nh;       // [2][nh]: (first, last) kept entry of the chunk resolved in that step
+    for (int it = 0; it < max_chunks; ++it) {
+        const int2* prev = ranges + ((it + 1) & 1) * nh;  // written in step it - 1
+        int2* cur = ranges + (it & 1) * nh;
+        // ---- leaders: bring chunk `it` up to date, resolve it
+        for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+            const int4 sg = seg_huge[h];
+            const int64_t o = (int64_t)sg.x * mp;
+            const int base = sg.y + it * kHugeChunk;
+            const int nk0 = range0[h].x;
+            __syncthreads();
+            if (base >= sg.z || nk0 >= max_keep) {
+                if (threadIdx.x == 0) cur[h] = make_int2(nk0, nk0);  // nothing new to apply next step
+                continue;
+            }
+            const int end = min(base + kHugeChunk, sg.z);
+            if (it > 0 && prev[h].y > prev[h].x)
+                for (int p0 = base; p0 < end; p0 += kSegThreads) {
+                    if (info[sg.x].nonan)
+                        huge_apply<true>(sbox + o, sarea + o, state + o, klist + o + sg.y, prev[h].x, prev[h].y,
+                                         p0 + (int)threadIdx.x, end, thr_f);
+                    else
+                        huge_apply<false>(sbox + o, sarea + o, state + o, klist + o + sg.y, prev[h].x, prev[h].y,
+                                          p0 + (int)threadIdx.x, end, thr_f);
+                }
+            __syncthreads();
+            const StagedBoxes sb = stage_boxes(sbox + o, sarea + o, base, end, sm_box, sm_area);
+            // kept list of the segment lives at klist[o + sg.y ...]; the chunk appends at entry nk0
+            int32_t* kl = klist + o + (sg.y + nk0 - base);
+            const int nk = info[sg.x].nonan
+                               ? cta_segment_nms<kSegThreads, int32_t, true>(sb.box, sb.area, state + o, kl, base, end, thr_f,
+                                                                             max_keep - nk0, rowbits, amask, &s_nk)
+                               : cta_segment_nms<kSegThreads, int32_t, false>(sb.box, sb.area, state + o, kl, base, end, thr_f,
+                                                                              max_keep - nk0, rowbits, amask, &s_nk);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                cur[h] = make_int2(nk0, nk0 + nk);
+                range0[h].x = nk0 + nk;
+            }
+        }
+        // ---- everybody: kept boxes of chunk it-1 against the alive positions behind chunk it
+        if (it > 0) {
+            int unit0 = 0;
+            for (int h = 0; h < nh; ++h) {
+                const int4 sg = seg_huge[h];
+                const int2 pr = prev[h];
+                const int first = sg.y + (it + 1) * kHugeChunk;
+                const int rem = sg.z - first;
+                if (rem <= 0 || pr.y <= pr.x) continue;
+                const int units = (rem + kSegThreads - 1) / kSegThreads;
+                const int64_t o = (int64_t)sg.x * mp;
+                // rotate the starting CTA from segment to segment so that short tails do not land on the same CTAs
+                const bool nn = info[sg.x].nonan != 0;
+                for (int u = (int)((blockIdx.x + gridDim.x - unit0 % gridDim.x) % gridDim.x); u < units; u += gridDim.x) {
+                    const int p = first + u * kSegThreads + (int)threadIdx.x;
+                    if (nn) huge_apply<true>(sbox + o, sarea + o, state + o, klist + o + sg.y, pr.x, pr.y, p, sg.z, thr_f);
+                    else huge_apply<false>(sbox + o, sarea + o, state + o, klist + o + sg.y, pr.x, pr.y, p, sg.z, thr_f);
+                }
+                unit0 += units;
+            }
+        }
+        grid.sync();
     }
 }
 
@@ -349,12 +506,39 @@ large_emit_kernel(int64_t mp, const LargeImg* __restrict__ info, const uint64_t*
 // runs the two persistent segment kernels over the lists built by a gather kernel
 static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float thr_f, int max_keep, cudaStream_t st) {
     const int sms = sm_count();
-    large_warp_segments_kernel<<<sms * 8, 128, 0, st>>>(lay.mp, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
+    large_warp_segments_kernel<<<sms * 8, 128, 0, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
                                                         ws.seg_small, thr_f, max_keep);
     DET_LAUNCH_OK("large_warp_segments_kernel");
-    large_cta_segments_kernel<<<sms * 2, kSegThreads, 0, st>>>(lay.mp, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
-                                                               ws.seg_large, thr_f, max_keep);
+    const int seg_smem = kHugeSeg * 20;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(large_cta_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seg_smem);
+        if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(large_cta_segments_kernel)");
+        attr_set = true;
+    }
+    large_cta_segments_kernel<<<sms * 2, kSegThreads, seg_smem, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
+                                                                      ws.seg_large, thr_f, max_keep);
     DET_LAUNCH_OK("large_cta_segments_kernel");
+    // cooperative launch: every CTA must be resident (grid barriers); it returns at once when there is no huge segment
+    static thread_local int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_huge_segments_kernel, kSegThreads, 0);
+        if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (per_sm > 4) per_sm = 4;
+    }
+    int64_t mp_arg = lay.mp;
+    const LargeImg* info_arg = ws.info;
+    const float4* sbox_arg = ws.sbox;
+    const float* sarea_arg = ws.sarea;
+    uint8_t* state_arg = ws.state;
+    int32_t* klist_arg = ws.klist;
+    const int32_t* ctr_arg = ws.ctr;
+    const int4* huge_arg = ws.seg_huge;
+    int2* nk_arg = ws.huge_nk;
+    void* args[] = {&mp_arg, &info_arg, &sbox_arg, &sarea_arg, &state_arg, &klist_arg, &ctr_arg, &huge_arg, &nk_arg, &thr_f, &max_keep};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)large_huge_segments_kernel, dim3((unsigned)(sms * per_sm)),
+                                                dim3(kSegThreads), args, 0, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(large_huge_segments_kernel)");
     return DET_OK;
 }
 
@@ -376,7 +560,7 @@ static int large_nms_run(const LargeLayout& lay, void* workspace, const float* b
     uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
     DET_LAUNCH_OK("sort_rows");
     large_gather_kernel<<<grid_e, 256, 0, st>>>(b4, cats, lay.m_max, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state,
-                                                ws.ctr, ws.seg_small, ws.seg_large);
+                                                ws.ctr, ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
     DET_LAUNCH_OK("large_gather_kernel");
     const int max_keep = (int)min(max_out, (int64_t)lay.m_max);
     int rc = run_segment_kernels(lay, ws, thr_f, max_keep, st);

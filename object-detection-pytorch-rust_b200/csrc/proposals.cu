@@ -32,7 +32,7 @@ rpn_keys_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTa
     if (i >= mp) return;
     if (i == 0) {
         LargeImg li;
-        li.cnt = (int32_t)r; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0; li.nsurv = 0; li.pad = 0;
+        li.cnt = (int32_t)r; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0; li.nsurv = 0; li.nonan = 1;  // non-finite boxes are dropped by the gather kernel
         info[img] = li;
     }
     uint64_t k = kSentinelKey;
@@ -52,7 +52,7 @@ rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ lo
                   LevelTable lt, int64_t pre_nms_topk, const int32_t* __restrict__ image_sizes, float min_size,
                   LargeImg* info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
                   float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* ctr, int4* seg_small, int4* seg_large,
-                  int32_t* __restrict__ nonfinite_flag) {
+                  int4* seg_huge, int2* huge_nk, int32_t* __restrict__ nonfinite_flag) {
     const int img = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     bool survivor = false;
@@ -78,7 +78,7 @@ rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ lo
                     sarea[(int64_t)img * mp + p] = box_area(b);
                 }
             }
-            if (rank == 0) push_segment(img, (int)p, (int)(p + take), ctr, seg_small, seg_large);
+            if (rank == 0) push_segment(img, (int)p, (int)(p + take), ctr, seg_small, seg_large, seg_huge, huge_nk);
         }
         state[(int64_t)img * mp + p] = st;
     }
@@ -199,7 +199,7 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     DET_LAUNCH_OK("sort_rows");
     rpn_gather_kernel<<<grid_e, 256, 0, st>>>(b4, logits, r, mp, lt, pre_nms_topk, image_sizes, min_box_size, ws.info,
                                               sorted, ws.sbox, ws.sarea, ws.state, ws.ctr, ws.seg_small, ws.seg_large,
-                                              nonfinite_flag);
+                                              ws.seg_huge, ws.huge_nk, nonfinite_flag);
     DET_LAUNCH_OK("rpn_gather_kernel");
     rpn_offset_kernel<<<n, 256, 0, st>>>(r, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state);
     DET_LAUNCH_OK("rpn_offset_kernel");
