@@ -230,8 +230,23 @@ def extras_train(det, dev, world, peak, quick):
             prev.wait()
 
     ms = time_region(step_grid, 30 if quick else 200)
+    if state.get("pending") is not None:
+        state["pending"].wait()
+    red = det.dist.SumsReducer(every=16)
+
+    def step_grid_cadence():
+        h = heads[state["i"] % pool]
+        state["i"] += 1
+        asg = tr.assign_packed(gtb, off, n)
+        res = tr.loss(h, asg, gtc, with_grads=True)
+        red.add(res["sums"])
+
+    ms16 = time_region(step_grid_cadence, 32 if quick else 208)
+    red.flush()
     out["train_grid_b1024"] = {"workload": "yolo7x7x30 assign+loss fwd/bwd, batch 1024/GPU", "ms_per_step": ms,
-                               "images_per_s_per_gpu": n / ms * 1e3}
+                               "images_per_s_per_gpu": n / ms * 1e3,
+                               "collective": "8-float all-reduce every step, waited for one step late",
+                               "ms_per_step_reduce_every_16": ms16, "images_per_s_per_gpu_reduce_every_16": n / ms16 * 1e3}
     # (ii) reference-native RPN form: R = 50127 anchors (FPN-18 @ 448), Matcher([0.3,0.7]), 256 samples, L1 + BCE
     rpn = det.RegionProposalNetwork([4, 8, 16, 32, 64])
     anchors = torch.cat(rpn.anchor_generator.grid_anchors([(448 // s, 448 // s) for s in (4, 8, 16, 32, 64)], dev), 0)

@@ -55,6 +55,43 @@ def allreduce_sums_async(sums: torch.Tensor):
     return _Done()
 
 
+class SumsReducer:
+    """Logging-cadence reduction of the loss/count vector: every step's local sums are accumulated on the device and
+    the accumulated vector is all-reduced (asynchronously) once every ``every`` steps.  The loss scalars are only
+    reported, never fed back into the gradients of this path, so a short training step does not have to pay a
+    collective's launch latency each iteration.  ``every=1`` is the per-step all-reduce."""
+
+    def __init__(self, every: int = 16):
+        self.every = max(1, int(every))
+        self._acc = None
+        self._steps = 0
+        self._work = None
+        self.last = None     # the most recent reduced vector (valid after the stream has passed its all-reduce)
+        self.last_steps = 0  # number of steps it covers
+
+    def add(self, sums: torch.Tensor):
+        """Account for one step; returns the reduced vector when this call completed a window, else None."""
+        if self._acc is None:
+            self._acc = torch.zeros_like(sums)
+        self._acc += sums.detach()
+        self._steps += 1
+        if self._steps < self.every:
+            return None
+        if self._work is not None:
+            self._work.wait()
+        out, self._acc = self._acc, None
+        self._work = allreduce_sums_async(out)
+        self.last, self.last_steps, self._steps = out, self.every, 0
+        return out
+
+    def flush(self):
+        """Wait for the outstanding all-reduce (end of training / before reading ``last`` on the host)."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self.last
+
+
 def global_num_images(local_n: int, device=None) -> int:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         t = torch.tensor([local_n], dtype=torch.int64, device=device)

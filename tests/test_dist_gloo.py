@@ -55,6 +55,13 @@ def _worker(rank, world, port, out):
     work = det_b200.dist.allreduce_sums_async(late)  # the one-step-late form used by the training loop
     work.wait()
     assert torch.equal(late, sums)
+    # logging-cadence reducer: 3 steps accumulated, one all-reduce
+    red = det_b200.dist.SumsReducer(every=3)
+    local = torch.full((8,), float(rank + 1))
+    assert red.add(local) is None and red.add(local) is None
+    got = red.add(local)
+    red.flush()
+    assert got is not None and torch.equal(got, torch.full((8,), 3.0 * sum(range(1, world + 1))))
     if rank == 0:
         torch.save(sums, out)
     dist.barrier()
