@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from tests.util import gen, rand_boxes
+from tests.util import gen, rand_boxes, distinct_scores
 
 pytestmark = pytest.mark.gpu
 
@@ -117,3 +117,80 @@ def test_bad_category_raises(det):
     b = torch.tensor([[0, 0, 1, 1.0]]).cuda()
     with pytest.raises(ValueError):
         det.batched_nms(b, torch.tensor([1.0]).cuda(), torch.tensor([-3]).cuda(), 0.5)
+
+
+# ---- long segments: CTA path with shared-memory staging (<= 4096) and the cooperative grid-wide path (> 4096) -------
+@pytest.mark.parametrize("m,ncat,thr,max_out", [
+    (4096, 1, 0.5, None),      # exactly the CTA-path limit
+    (4097, 1, 0.5, None),      # first huge segment
+    (9000, 1, 0.4, None),      # several 512-box leader steps, heavy suppression
+    (9000, 1, 0.7, 700),       # early stop at max_out in the middle of a leader chunk
+    (12000, 2, 0.5, None),     # two huge segments per image advancing in lock step
+    (6000, 3, 0.5, None),      # mid segments only
+])
+def test_long_segments_match_oracle(det, O, m, ncat, thr, max_out):
+    g = gen(31 + m % 7)
+    n_img = 3
+    boxes = torch.stack([rand_boxes(m, 700.0, g, 0.25) for _ in range(n_img)])
+    scores = torch.stack([distinct_scores(m, g) for _ in range(n_img)])
+    cats = torch.randint(0, ncat, (n_img, m), generator=g)
+    counts = torch.tensor([m, m - 1234, 37], dtype=torch.int32)
+    keep, kc = det.nms_images(boxes.cuda(), scores.cuda(), cats.cuda(), counts.cuda(), thr, max_out=max_out, mode=1)
+    keep, kc = keep.cpu(), kc.cpu()
+    for i in range(n_img):
+        k = int(counts[i])
+        want = O.batched_nms(boxes[i, :k], scores[i, :k], cats[i, :k], thr)
+        if max_out is not None:
+            want = want[:max_out]
+        assert int(kc[i]) == want.numel(), (i, int(kc[i]), want.numel())
+        assert torch.equal(keep[i, :want.numel()], want), i
+
+
+def test_huge_segment_with_nan_and_tied_scores(det, O):
+    """NaN coordinates switch the image to the NaN-safe predicate; exactly tied scores must come out in index order."""
+    g = gen(41)
+    m = 5200
+    boxes = rand_boxes(m, 600.0, g, 0.3)
+    boxes[17, 2] = float("nan")
+    boxes[4000, 0] = float("nan")
+    scores = torch.randint(0, 400, (m,), generator=g).float() / 400.0  # many exact ties
+    keep, kc = det.nms_images(boxes[None].cuda(), scores[None].cuda(), None, None, 0.5, mode=1)
+    want = O.nms(boxes, scores, 0.5)
+    assert int(kc[0]) == want.numel() and torch.equal(keep[0, :want.numel()].cpu(), want)
+
+
+def test_nms_properties_at_100k_boxes(det, O):
+    """BASELINE configs[4] size, where the O(M^2) oracle is out of reach: size-independent properties of greedy NMS.
+    (1) kept indices are unique, valid and in descending-score order; (2) idempotence: NMS of the kept set keeps
+    everything, in the same order; (3) no kept box is suppressed by an earlier kept box (sampled pairs);
+    (4) every dropped box of a sample is suppressed by some kept box with a higher score."""
+    g = gen(51)
+    m = 100000
+    boxes = rand_boxes(m, 1024.0, g, 0.2)
+    scores = distinct_scores(m, g)
+    cats = torch.randint(0, 3, (m,), generator=g)
+    b, s, c = boxes.cuda(), scores.cuda(), cats.cuda()
+    keep, kc = det.nms_images(b[None], s[None], c[None], None, 0.5, mode=1)
+    k = int(kc[0])
+    kept = keep[0, :k]
+    assert 0 < k < m and int(kept.min()) >= 0 and int(kept.max()) < m and kept.unique().numel() == k
+    ks = s[kept]
+    assert bool((ks[1:] < ks[:-1]).all())
+    keep2, kc2 = det.nms_images(b[kept][None], ks[None], c[kept][None], None, 0.5, mode=1)
+    assert int(kc2[0]) == k and torch.equal(keep2[0, :k], torch.arange(k, device=keep2.device))
+    # (3) on a random sample of kept boxes vs all kept boxes of the same category
+    kb, kcat = b[kept], c[kept]
+    sel = torch.randperm(k, generator=g)[:300].cuda()
+    iou = det.pairwise_iou(det.Boxes(kb[sel]), det.Boxes(kb))
+    same = kcat[sel][:, None] == kcat[None, :]
+    iou = torch.where(same, iou, torch.zeros_like(iou))
+    iou[torch.arange(sel.numel(), device=iou.device), sel] = 0
+    assert float(iou.max()) <= 0.5
+    # (4) dropped boxes: each has a same-category kept box with higher score and IoU > 0.5
+    dropped = torch.ones(m, dtype=torch.bool, device=b.device)
+    dropped[kept] = False
+    didx = dropped.nonzero()[:, 0]
+    didx = didx[torch.randperm(didx.numel(), generator=g)[:300].cuda()]
+    iou = det.pairwise_iou(det.Boxes(b[didx]), det.Boxes(kb))
+    ok = (iou > 0.5) & (c[didx][:, None] == kcat[None, :]) & (ks[None, :] > s[didx][:, None])
+    assert bool(ok.any(dim=1).all())
