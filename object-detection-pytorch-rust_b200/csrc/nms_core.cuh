@@ -205,35 +205,53 @@ __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t*
 }
 
 // ---- greedy suppression of one segment [s,e) by a WHOLE CTA, in chunks of T boxes ---------------------
-// The CTA may have more than T threads: threads >= T only take part in the barriers.
-// scratch: rowbits[T * T/32], amask[T/32], s_nk[1] in shared memory.
+// blockDim.x must be a multiple of T.  With G = blockDim.x / T > 1 the extra thread groups are helpers: every group
+// looks at the same T candidates, group g tests them against the g-th slice of the kept list (the verdicts meet in
+// `deadmask`) and builds the bit rows of the survivor words w2 = g (mod G) -- the two O(chunk x list) parts of a
+// chunk are spread over all warps of the CTA; only the order resolution (c) is serial (warp 0).
+// scratch in shared memory: rowbits[T * T/32], amask[T/32], deadmask[T/32], s_nk[1].
 template <int T, typename KT, bool NONAN>
 __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* state, KT* klist, int s, int e,
-                               float thr_f, int max_keep, uint32_t* rowbits, uint32_t* amask, int* s_nk) {
+                               float thr_f, int max_keep, uint32_t* rowbits, uint32_t* amask, uint32_t* deadmask,
+                               int* s_nk) {
     constexpr int W = T / 32;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = (int)blockDim.x / T;
+    const int gidx = tid / T, ctid = tid - gidx * T, cw = ctid >> 5;
     int nk = 0;
-    const bool worker = tid < T;
     for (int base = s; base < e && nk < max_keep; base += T) {
-        const int p = base + tid;
-        const bool act = worker && (p < e) && (state[p] == 0);
+        const int p = base + ctid;
+        const bool act = (p < e) && (state[p] == 0);
         float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
         float ma = 0.f;
         if (act) {
             mb = sbox[p];
             ma = sarea[p];
         }
-        // (a) against everything already kept in this segment
-        const bool alive = alive_after_kept<KT, NONAN>(sbox, sarea, klist, s, s + nk, mb, ma, act, thr_f);
+        // (a) against everything already kept in this segment (this group's slice of the list)
+        bool alive;
+        if (G > 1) {
+            if (tid < W) deadmask[tid] = 0u;
+            __syncthreads();
+            const int k0 = s + (int)((int64_t)nk * gidx / G), k1 = s + (int)((int64_t)nk * (gidx + 1) / G);
+            const bool mine = alive_after_kept<KT, NONAN>(sbox, sarea, klist, k0, k1, mb, ma, act, thr_f);
+            const unsigned dead = __ballot_sync(FULL, act && !mine);
+            if (lane == 0 && dead) atomicOr(&deadmask[cw], dead);
+            __syncthreads();
+            alive = act && !((deadmask[cw] >> lane) & 1u);
+        } else {
+            alive = alive_after_kept<KT, NONAN>(sbox, sarea, klist, s, s + nk, mb, ma, act, thr_f);
+        }
         const unsigned bal = __ballot_sync(FULL, alive);
-        if (worker && lane == 0) amask[wid] = bal;
+        if (gidx == 0 && lane == 0) amask[cw] = bal;
         __syncthreads();
         // (b) bit row of this candidate as suppressor of the later survivors of the chunk
         if (alive) {
-            for (int w2 = wid; w2 < W; ++w2) {
+            for (int w2 = cw; w2 < W; ++w2) {
+                if (w2 % G != gidx) continue;
                 unsigned cand = amask[w2];
-                if (w2 == wid) cand &= ~((2u << lane) - 1u);
+                if (w2 == cw) cand &= ~((2u << lane) - 1u);
                 unsigned bits = 0;
                 while (cand) {
                     const int b = __ffs(cand) - 1;
@@ -241,7 +259,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
                     const int q = base + w2 * 32 + b;
                     if (nms_suppresses<NONAN>(mb, ma, sbox[q], sarea[q], thr_f)) bits |= 1u << b;
                 }
-                rowbits[tid * W + w2] = bits;
+                rowbits[ctid * W + w2] = bits;
             }
         }
         __syncthreads();

@@ -16,7 +16,8 @@ constexpr int kTile = 2048;
 constexpr int kSortThreads = 256;
 constexpr int kVT = kTile / kSortThreads;
 constexpr int kLargeWarpSegMax = 256;  // segments up to this length are swept by one warp
-constexpr int kSegThreads = 256;
+constexpr int kSegThreads = 256;   // candidates per chunk of the CTA sweep
+constexpr int kSegCtaThreads = 1024;  // threads of the CTA that runs it: 4 groups share the list tests and bit rows
 constexpr int kHugeSeg = 4096;     // longer segments are swept by the whole grid (cooperative kernel)
 constexpr int kHugeChunk = 512;    // positions resolved per step by the segment's leader CTA
 
@@ -333,7 +334,7 @@ __device__ __forceinline__ StagedBoxes stage_boxes(const float4* __restrict__ sb
 
 // segments of 257 .. kHugeSeg boxes: one CTA each, the whole segment staged in shared memory (80 KB) so that the
 // kept-list tests and the chunk bit rows never wait for L2
-static __global__ void __launch_bounds__(kSegThreads)
+static __global__ void __launch_bounds__(kSegCtaThreads)
 large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const float4* __restrict__ sbox,
                           const float* __restrict__ sarea, uint8_t* state, int32_t* klist, int32_t* ctr,
                           const int4* __restrict__ seg_large, float thr_f, int max_keep) {
@@ -341,7 +342,7 @@ large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const f
     float4* sm_box = reinterpret_cast<float4*>(seg_smem);
     float* sm_area = reinterpret_cast<float*>(sm_box + kHugeSeg);
     __shared__ uint32_t rowbits[kSegThreads * (kSegThreads / 32)];
-    __shared__ uint32_t amask[kSegThreads / 32];
+    __shared__ uint32_t amask[kSegThreads / 32], deadmask[kSegThreads / 32];
     __shared__ int s_nk, s_next;
     const int total = ctr[1];
     while (true) {
@@ -355,10 +356,10 @@ large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const f
         const StagedBoxes sb = stage_boxes(sbox + o, sarea + o, sg.y, sg.z, sm_box, sm_area);
         if (info[sg.x].nonan)
             cta_segment_nms<kSegThreads, int32_t, true>(sb.box, sb.area, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
-                                                        rowbits, amask, &s_nk);
+                                                        rowbits, amask, deadmask, &s_nk);
         else
             cta_segment_nms<kSegThreads, int32_t, false>(sb.box, sb.area, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
-                                                         rowbits, amask, &s_nk);
+                                                         rowbits, amask, deadmask, &s_nk);
         __syncthreads();
     }
 }
@@ -389,7 +390,7 @@ __device__ __forceinline__ void huge_apply(const float4* __restrict__ sbox, cons
     if (was && !alive) state[p] = 1;
 }
 
-static __global__ void __launch_bounds__(kSegThreads)
+static __global__ void __launch_bounds__(kSegCtaThreads)
 large_huge_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const float4* __restrict__ sbox,
                            const float* __restrict__ sarea, uint8_t* state, int32_t* klist,
                            const int32_t* __restrict__ ctr, const int4* __restrict__ seg_huge, int2* huge_nk, float thr_f,
@@ -398,7 +399,7 @@ large_huge_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const 
     __shared__ __align__(16) float4 sm_box[kHugeChunk];
     __shared__ float sm_area[kHugeChunk];
     __shared__ uint32_t rowbits[kSegThreads * (kSegThreads / 32)];
-    __shared__ uint32_t amask[kSegThreads / 32];
+    __shared__ uint32_t amask[kSegThreads / 32], deadmask[kSegThreads / 32];
     __shared__ int s_nk;
     const int nh = ctr[4];
     if (nh == 0) return;  // grid-uniform
@@ -428,7 +429,7 @@ large_huge_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const 
             }
             const int end = min(base + kHugeChunk, sg.z);
             if (it > 0 && prev[h].y > prev[h].x)
-                for (int p0 = base; p0 < end; p0 += kSegThreads) {
+                for (int p0 = base; p0 < end; p0 += kSegCtaThreads) {
                     if (info[sg.x].nonan)
                         huge_apply<true>(sbox + o, sarea + o, state + o, klist + o + sg.y, prev[h].x, prev[h].y,
                                          p0 + (int)threadIdx.x, end, thr_f);
@@ -442,9 +443,9 @@ large_huge_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const 
             int32_t* kl = klist + o + (sg.y + nk0 - base);
             const int nk = info[sg.x].nonan
                                ? cta_segment_nms<kSegThreads, int32_t, true>(sb.box, sb.area, state + o, kl, base, end, thr_f,
-                                                                             max_keep - nk0, rowbits, amask, &s_nk)
+                                                                             max_keep - nk0, rowbits, amask, deadmask, &s_nk)
                                : cta_segment_nms<kSegThreads, int32_t, false>(sb.box, sb.area, state + o, kl, base, end, thr_f,
-                                                                              max_keep - nk0, rowbits, amask, &s_nk);
+                                                                              max_keep - nk0, rowbits, amask, deadmask, &s_nk);
             __syncthreads();
             if (threadIdx.x == 0) {
                 cur[h] = make_int2(nk0, nk0 + nk);
@@ -460,12 +461,12 @@ large_huge_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const 
                 const int first = sg.y + (it + 1) * kHugeChunk;
                 const int rem = sg.z - first;
                 if (rem <= 0 || pr.y <= pr.x) continue;
-                const int units = (rem + kSegThreads - 1) / kSegThreads;
+                const int units = (rem + kSegCtaThreads - 1) / kSegCtaThreads;
                 const int64_t o = (int64_t)sg.x * mp;
                 // rotate the starting CTA from segment to segment so that short tails do not land on the same CTAs
                 const bool nn = info[sg.x].nonan != 0;
                 for (int u = (int)((blockIdx.x + gridDim.x - unit0 % gridDim.x) % gridDim.x); u < units; u += gridDim.x) {
-                    const int p = first + u * kSegThreads + (int)threadIdx.x;
+                    const int p = first + u * kSegCtaThreads + (int)threadIdx.x;
                     if (nn) huge_apply<true>(sbox + o, sarea + o, state + o, klist + o + sg.y, pr.x, pr.y, p, sg.z, thr_f);
                     else huge_apply<false>(sbox + o, sarea + o, state + o, klist + o + sg.y, pr.x, pr.y, p, sg.z, thr_f);
                 }
@@ -516,13 +517,13 @@ static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float 
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(large_cta_segments_kernel)");
         attr_set = true;
     }
-    large_cta_segments_kernel<<<sms * 2, kSegThreads, seg_smem, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
+    large_cta_segments_kernel<<<sms * 2, kSegCtaThreads, seg_smem, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
                                                                       ws.seg_large, thr_f, max_keep);
     DET_LAUNCH_OK("large_cta_segments_kernel");
     // cooperative launch: every CTA must be resident (grid barriers); it returns at once when there is no huge segment
     static thread_local int per_sm = 0;
     if (per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_huge_segments_kernel, kSegThreads, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_huge_segments_kernel, kSegCtaThreads, 0);
         if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
         if (per_sm > 4) per_sm = 4;
     }
@@ -537,7 +538,7 @@ static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float 
     int2* nk_arg = ws.huge_nk;
     void* args[] = {&mp_arg, &info_arg, &sbox_arg, &sarea_arg, &state_arg, &klist_arg, &ctr_arg, &huge_arg, &nk_arg, &thr_f, &max_keep};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)large_huge_segments_kernel, dim3((unsigned)(sms * per_sm)),
-                                                dim3(kSegThreads), args, 0, st);
+                                                dim3(kSegCtaThreads), args, 0, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(large_huge_segments_kernel)");
     return DET_OK;
 }

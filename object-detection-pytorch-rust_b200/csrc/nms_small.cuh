@@ -35,6 +35,7 @@ struct SmallSmem {
         uint32_t rowbits[kCtaChunk * (kCtaChunk / 32)];
     };
     uint32_t amask[kCtaChunk / 32];
+    uint32_t deadmask[kCtaChunk / 32];
     float red_max[T / 32];
     float red_min[T / 32];
     int red_flag[T / 32];
@@ -285,10 +286,10 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
         const int s0 = (int)sm.big_s[sidx], e0 = (int)sm.big_e[sidx];
         const int nk = nonan ? cta_segment_nms<kCtaChunk, uint16_t, true>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0,
                                                                           thr_f, max_out, sm.rowbits, sm.amask,
-                                                                          &sm.nk_scratch)
+                                                                          sm.deadmask, &sm.nk_scratch)
                              : cta_segment_nms<kCtaChunk, uint16_t, false>(sm.sbox, sm.sarea, sm.state, sm.klist, s0, e0,
                                                                            thr_f, max_out, sm.rowbits, sm.amask,
-                                                                           &sm.nk_scratch);
+                                                                           sm.deadmask, &sm.nk_scratch);
         if (tid == 0) sm.nkept += nk;
         __syncthreads();
     }
