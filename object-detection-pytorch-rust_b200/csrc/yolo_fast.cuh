@@ -42,7 +42,8 @@ struct YoloParams {
     int64_t max_det;
 };
 
-__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x): __frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to the IEEE quotient 1.0f / d
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __frcp_rn(1.0f + expf(-x)); }
 
 struct FastLayout {
     int hs_floats, pp, cls_stride, pcp;
