@@ -202,6 +202,29 @@ DET_API int det_yolo_loss(const float* head, const int8_t* labels, const int64_t
                   int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
                   const float* upstream, float* sums, float* grad_head, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * (next tier) FPN level assignment + ROIAlign over a feature pyramid -- replaces
+ *      assign_boxes_to_levels / ROIPooler.forward / ROIAlign.forward,
+ *      python/src/models/modules/roi_poolers.py:103-131, :269-331, :55-72 (torchvision.ops.roi_align underneath).
+ *      Forward only in this round.
+ *      det_roi_levels: level_out[i] = clamp(floor(canonical_level + log2(sqrt(area_i)/canonical_box_size + 1e-8)),
+ *      min_level, max_level) - min_level, boxes (m,4).
+ *      det_roi_align_levels: every box samples the level `level[i]` (NULL when num_levels == 1) of image
+ *      batch_index[i]; level l: data (n, c, h, w) device fp32, spatial_scale = 1/stride.  out (m, c, out_h, out_w).
+ *      sampling_ratio <= 0: ceil(roi / bins) samples per bin; aligned != 0: half-pixel shift (ROIAlignV2).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct det_feature_level {
+    const float* data;
+    int32_t h, w;
+    float spatial_scale;
+    int32_t reserved;
+} det_feature_level_t;
+DET_API int det_roi_levels(const float* boxes, int64_t m, int min_level, int max_level, float canonical_box_size,
+                   int canonical_level, int64_t* level_out, void* stream);
+DET_API int det_roi_align_levels(const det_feature_level_t* levels_host, int num_levels, int n, int c, const float* boxes,
+                         const int32_t* batch_index, const int64_t* level, int64_t m, int out_h, int out_w,
+                         int sampling_ratio, int aligned, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,154 @@
+// FPN level assignment + ROIAlign over a feature pyramid in ONE launch.
+//
+// Replaces ROIPooler.forward (reference python/src/models/modules/roi_poolers.py:269-331): there, per level,
+// nonzero(level == l) -> gather boxes -> torchvision roi_align -> index_put_ into a zero-filled output.  Here every
+// output element (box, channel, bin) finds its own level: det_roi_levels evaluates Eqn.(1) of the FPN paper once per
+// box (roi_poolers.py:121-131), and one kernel samples all levels -- no per-level launches, no gathers, no memset.
+// The sampling arithmetic restates torchvision's roi_align (third-party, un-vendored; oracle = the installed
+// torchvision CPU kernel): `aligned` shifts by half a pixel, sampling_ratio <= 0 means ceil(roi / bins) samples.
+#include "common.cuh"
+
+namespace det {
+
+constexpr int kRoiMaxLevels = 8;
+
+struct RoiLevelDev {
+    const float* data;  // (N, C, H, W)
+    int h, w;
+    float scale;
+};
+
+struct RoiArgs {
+    RoiLevelDev lv[kRoiMaxLevels];
+    int num_levels, c, out_h, out_w, sampling_ratio, aligned;
+    int64_t m;
+    const float4* boxes;
+    const int32_t* batch_index;
+    const int64_t* level;  // may be null when num_levels == 1
+    float* out;
+};
+
+__global__ void __launch_bounds__(256)
+roi_levels_kernel(const float4* __restrict__ boxes, int64_t m, int min_level, int max_level, float canonical_box_size,
+                  float canonical_level, int64_t* __restrict__ level_out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    const float4 b = boxes[i];
+    const float size = sqrtf(box_area(b));                                       // torch.sqrt(area)
+    float lvl = floorf(canonical_level + log2f(size / canonical_box_size + 1e-8f));  // roi_poolers.py:123-125
+    lvl = fminf(fmaxf(lvl, (float)min_level), (float)max_level);                  // torch.clamp (NaN: see below)
+    if (lvl != lvl) lvl = (float)min_level;  // a NaN area would make torch's int64 cast undefined: pin it to level 0
+    level_out[i] = (int64_t)lvl - min_level;
+}
+
+// torchvision bilinear_interpolate (roi_align_common / cuda kernel)
+__device__ __forceinline__ float bilinear(const float* __restrict__ plane, int H, int W, float y, float x) {
+    if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) return 0.0f;
+    if (y <= 0.0f) y = 0.0f;
+    if (x <= 0.0f) x = 0.0f;
+    int y_low = (int)y, x_low = (int)x, y_high, x_high;
+    if (y_low >= H - 1) {
+        y_high = y_low = H - 1;
+        y = (float)y_low;
+    } else {
+        y_high = y_low + 1;
+    }
+    if (x_low >= W - 1) {
+        x_high = x_low = W - 1;
+        x = (float)x_low;
+    } else {
+        x_high = x_low + 1;
+    }
+    const float ly = y - (float)y_low, lx = x - (float)x_low, hy = 1.0f - ly, hx = 1.0f - lx;
+    const float v1 = plane[y_low * W + x_low], v2 = plane[y_low * W + x_high];
+    const float v3 = plane[y_high * W + x_low], v4 = plane[y_high * W + x_high];
+    return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+}
+
+__global__ void __launch_bounds__(256) roi_align_levels_kernel(const __grid_constant__ RoiArgs g) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int bins = g.out_h * g.out_w;
+    const int64_t total = g.m * g.c * bins;
+    if (idx >= total) return;
+    const int pw = (int)(idx % g.out_w), ph = (int)((idx / g.out_w) % g.out_h);
+    const int ch = (int)((idx / bins) % g.c);
+    const int64_t box = idx / ((int64_t)bins * g.c);
+    const int l = g.level ? (int)g.level[box] : 0;
+    const RoiLevelDev& L = g.lv[l];
+    const float4 b = g.boxes[box];
+    const float off = g.aligned ? 0.5f : 0.0f;
+    const float x1 = b.x * L.scale - off, y1 = b.y * L.scale - off;
+    float rw = b.z * L.scale - off - x1, rh = b.w * L.scale - off - y1;
+    if (!g.aligned) {  // legacy: force malformed ROIs to be 1x1
+        rw = fmaxf(rw, 1.0f);
+        rh = fmaxf(rh, 1.0f);
+    }
+    const float bin_h = rh / (float)g.out_h, bin_w = rw / (float)g.out_w;
+    const int gh = g.sampling_ratio > 0 ? g.sampling_ratio : (int)ceilf(rh / (float)g.out_h);
+    const int gw = g.sampling_ratio > 0 ? g.sampling_ratio : (int)ceilf(rw / (float)g.out_w);
+    const float count = fmaxf((float)(gh * gw), 1.0f);
+    const float* plane = L.data + ((int64_t)g.batch_index[box] * g.c + ch) * ((int64_t)L.h * L.w);
+    float acc = 0.0f;
+    for (int iy = 0; iy < gh; ++iy) {
+        const float y = y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+            const float x = x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw;
+            acc += bilinear(plane, L.h, L.w, y, x);
+        }
+    }
+    st_stream(g.out + idx, acc / count);
+}
+
+}  // namespace det
+
+using namespace det;
+
+extern "C" {
+
+int det_roi_levels(const float* boxes, int64_t m, int min_level, int max_level, float canonical_box_size,
+                   int canonical_level, int64_t* level_out, void* stream) {
+    DET_CHECK_ARG(m >= 0 && min_level <= max_level && canonical_box_size > 0.f, "bad argument");
+    if (m == 0) return DET_OK;
+    DET_CHECK_ARG(boxes && level_out, "null pointer");
+    if (!aligned16(boxes)) {
+        set_error("boxes must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    roi_levels_kernel<<<(unsigned)((m + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(boxes), m, min_level, max_level, canonical_box_size, (float)canonical_level, level_out);
+    DET_LAUNCH_OK("roi_levels_kernel");
+    return DET_OK;
+}
+
+int det_roi_align_levels(const det_feature_level_t* levels_host, int num_levels, int n, int c, const float* boxes,
+                         const int32_t* batch_index, const int64_t* level, int64_t m, int out_h, int out_w,
+                         int sampling_ratio, int aligned, float* out, void* stream) {
+    DET_CHECK_ARG(num_levels >= 1 && num_levels <= kRoiMaxLevels && n >= 0 && c >= 1 && m >= 0 && out_h >= 1 && out_w >= 1,
+                  "bad size");
+    if (m == 0) return DET_OK;
+    DET_CHECK_ARG(levels_host && boxes && batch_index && out && (level || num_levels == 1), "null pointer");
+    if (!aligned16(boxes)) {
+        set_error("boxes must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    RoiArgs g;
+    for (int l = 0; l < kRoiMaxLevels; ++l) {
+        if (l < num_levels) {
+            DET_CHECK_ARG(levels_host[l].data && levels_host[l].h >= 1 && levels_host[l].w >= 1, "bad level");
+            g.lv[l].data = levels_host[l].data; g.lv[l].h = levels_host[l].h; g.lv[l].w = levels_host[l].w;
+            g.lv[l].scale = levels_host[l].spatial_scale;
+        } else {
+            g.lv[l].data = nullptr; g.lv[l].h = 1; g.lv[l].w = 1; g.lv[l].scale = 1.f;
+        }
+    }
+    g.num_levels = num_levels; g.c = c; g.out_h = out_h; g.out_w = out_w; g.sampling_ratio = sampling_ratio;
+    g.aligned = aligned ? 1 : 0; g.m = m; g.boxes = reinterpret_cast<const float4*>(boxes);
+    g.batch_index = batch_index; g.level = num_levels > 1 ? level : nullptr; g.out = out;
+    const int64_t total = m * c * out_h * out_w;
+    DET_CHECK_ARG((total + 255) / 256 < (1ll << 31), "too many outputs");
+    roi_align_levels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(g);
+    DET_LAUNCH_OK("roi_align_levels_kernel");
+    return DET_OK;
+}
+
+}  // extern "C"

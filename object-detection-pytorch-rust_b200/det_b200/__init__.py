@@ -15,6 +15,7 @@ from .matcher import Matcher, subsample_labels_
 from .proposals import find_top_rpn_proposals, rpn_proposals_batched, add_ground_truth_to_proposals
 from .rpn import RegionProposalNetwork, Assignment, _dense_box_regression_loss
 from .roi import ROIHeads, subsample_labels
+from .roi_pool import ROIAlign, ROIPooler, assign_boxes_to_levels, convert_boxes_to_pooler_format
 from . import dist
 
 __all__ = [
@@ -22,5 +23,6 @@ __all__ = [
     "Box2BoxTransform", "AnchorGenerator", "generate_cell_anchors", "batched_nms", "nms", "nms_images",
     "YoloGridHead", "DenseAnchorHead", "YoloGridTrainer", "YoloHostPipeline", "Matcher", "subsample_labels_", "find_top_rpn_proposals",
     "rpn_proposals_batched", "add_ground_truth_to_proposals", "RegionProposalNetwork", "Assignment",
-    "_dense_box_regression_loss", "ROIHeads", "subsample_labels", "dist",
+    "_dense_box_regression_loss", "ROIHeads", "subsample_labels", "ROIAlign", "ROIPooler", "assign_boxes_to_levels",
+    "convert_boxes_to_pooler_format", "dist",
 ]

@@ -40,6 +40,8 @@ PROTOTYPES = {
                                   c_p, c_p, c_p, c_p, c_p]),
     "det_dense_decode_level": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_p, c_p, c_p, c_l, c_l, c_p]),
     "det_dense_decode": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_l, c_p]),
+    "det_roi_levels": (c_i, [c_p, c_l, c_i, c_i, c_f, c_i, c_p, c_p]),
+    "det_roi_align_levels": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "det_match_workspace_bytes": (c_l, [c_i, c_l, c_l]),
     "det_match_anchors": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "det_match_quality": (c_i, [c_p, c_l, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
@@ -56,6 +58,12 @@ class DenseLevel(ctypes.Structure):
     """det_dense_level_t of include/det_b200.h"""
     _fields_ = [("head", c_p), ("anchors_wh", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_offset", c_l)]
+
+
+class FeatureLevel(ctypes.Structure):
+    """det_feature_level_t of include/det_b200.h"""
+    _fields_ = [("data", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("spatial_scale", c_f),
+                ("reserved", ctypes.c_int32)]
 
 
 _lib = None
