@@ -65,14 +65,45 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ plane, int H
     return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
 }
 
+// One CTA per (box, group of kRoiChans channels).  The sample geometry of a box -- which feature rows / columns every
+// sample touches and with which bilinear weights -- is separable and does not depend on the channel: the CTA first
+// tabulates out_h*grid_h row taps and out_w*grid_w column taps in shared memory, then its threads walk the
+// (channel, bin) outputs of the group; every sample costs two shared-memory tap loads, 4 global loads and a few
+// multiply-adds.  Consecutive threads are consecutive output floats (fully coalesced stores) and neighbouring bins of
+// one feature plane (reads fall into the same few rows).  Boxes whose tap tables would not fit take the direct path.
+constexpr int kRoiChans = 32;
+constexpr int kRoiTaps = 128;  // per axis: out_h * grid_h (resp. out_w * grid_w) must not exceed this
+
+struct AxisTap {
+    int lo, hi;
+    float wlo, whi;  // both 0 when the sample lies outside [-1, size] (torchvision: contributes 0)
+};
+
+__device__ __forceinline__ AxisTap axis_tap(float v, int size) {
+    AxisTap t;
+    if (v < -1.0f || v > (float)size) {
+        t.lo = t.hi = 0;
+        t.wlo = t.whi = 0.0f;
+        return t;
+    }
+    if (v <= 0.0f) v = 0.0f;
+    int lo = (int)v, hi;
+    if (lo >= size - 1) {
+        hi = lo = size - 1;
+        v = (float)lo;
+    } else {
+        hi = lo + 1;
+    }
+    const float l = v - (float)lo;
+    t.lo = lo; t.hi = hi; t.wlo = 1.0f - l; t.whi = l;
+    return t;
+}
+
 __global__ void __launch_bounds__(256) roi_align_levels_kernel(const __grid_constant__ RoiArgs g) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    __shared__ AxisTap s_ty[kRoiTaps], s_tx[kRoiTaps];
+    const int64_t box = blockIdx.x;
+    const int c0 = blockIdx.y * kRoiChans, nc = min(kRoiChans, g.c - c0);
     const int bins = g.out_h * g.out_w;
-    const int64_t total = g.m * g.c * bins;
-    if (idx >= total) return;
-    const int pw = (int)(idx % g.out_w), ph = (int)((idx / g.out_w) % g.out_h);
-    const int ch = (int)((idx / bins) % g.c);
-    const int64_t box = idx / ((int64_t)bins * g.c);
     const int l = g.level ? (int)g.level[box] : 0;
     const RoiLevelDev& L = g.lv[l];
     const float4 b = g.boxes[box];
@@ -87,16 +118,57 @@ __global__ void __launch_bounds__(256) roi_align_levels_kernel(const __grid_cons
     const int gh = g.sampling_ratio > 0 ? g.sampling_ratio : (int)ceilf(rh / (float)g.out_h);
     const int gw = g.sampling_ratio > 0 ? g.sampling_ratio : (int)ceilf(rw / (float)g.out_w);
     const float count = fmaxf((float)(gh * gw), 1.0f);
-    const float* plane = L.data + ((int64_t)g.batch_index[box] * g.c + ch) * ((int64_t)L.h * L.w);
-    float acc = 0.0f;
-    for (int iy = 0; iy < gh; ++iy) {
-        const float y = y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh;
-        for (int ix = 0; ix < gw; ++ix) {
-            const float x = x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw;
-            acc += bilinear(plane, L.h, L.w, y, x);
+    const int64_t plane_sz = (int64_t)L.h * L.w;
+    const float* base = L.data + ((int64_t)g.batch_index[box] * g.c + c0) * plane_sz;
+    float* out = g.out + (box * g.c + c0) * bins;
+    const bool tabulated = gh >= 0 && gw >= 0 && g.out_h * gh <= kRoiTaps && g.out_w * gw <= kRoiTaps;  // CTA-uniform
+    if (tabulated) {
+        for (int t = threadIdx.x; t < g.out_h * gh; t += 256) {
+            const int ph = t / gh, iy = t - ph * gh;
+            AxisTap a = axis_tap(y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh, L.h);
+            a.lo *= L.w;
+            a.hi *= L.w;
+            s_ty[t] = a;
+        }
+        for (int t = threadIdx.x; t < g.out_w * gw; t += 256) {
+            const int pw = t / gw, ix = t - pw * gw;
+            s_tx[t] = axis_tap(x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw, L.w);
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < nc * bins; o += 256) {
+            const int ch = o / bins, bin = o - ch * bins;
+            const int ph = bin / g.out_w, pw = bin - ph * g.out_w;
+            const float* plane = base + (int64_t)ch * plane_sz;
+            float acc = 0.0f;
+            for (int iy = 0; iy < gh; ++iy) {
+                const AxisTap ty = s_ty[ph * gh + iy];
+                const float* r0 = plane + ty.lo;
+                const float* r1 = plane + ty.hi;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const AxisTap tx = s_tx[pw * gw + ix];
+                    // torchvision: w1*v1 + w2*v2 + w3*v3 + w4*v4 with w1 = hy*hx, w2 = hy*lx, w3 = ly*hx, w4 = ly*lx
+                    acc += ty.wlo * tx.wlo * r0[tx.lo] + ty.wlo * tx.whi * r0[tx.hi] + ty.whi * tx.wlo * r1[tx.lo] +
+                           ty.whi * tx.whi * r1[tx.hi];
+                }
+            }
+            st_stream(out + o, acc / count);
+        }
+    } else {
+        for (int o = threadIdx.x; o < nc * bins; o += 256) {
+            const int ch = o / bins, bin = o - ch * bins;
+            const int ph = bin / g.out_w, pw = bin - ph * g.out_w;
+            const float* plane = base + (int64_t)ch * plane_sz;
+            float acc = 0.0f;
+            for (int iy = 0; iy < gh; ++iy) {
+                const float y = y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const float x = x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw;
+                    acc += bilinear(plane, L.h, L.w, y, x);
+                }
+            }
+            st_stream(out + o, acc / count);
         }
     }
-    st_stream(g.out + idx, acc / count);
 }
 
 }  // namespace det
@@ -144,9 +216,9 @@ int det_roi_align_levels(const det_feature_level_t* levels_host, int num_levels,
     g.num_levels = num_levels; g.c = c; g.out_h = out_h; g.out_w = out_w; g.sampling_ratio = sampling_ratio;
     g.aligned = aligned ? 1 : 0; g.m = m; g.boxes = reinterpret_cast<const float4*>(boxes);
     g.batch_index = batch_index; g.level = num_levels > 1 ? level : nullptr; g.out = out;
-    const int64_t total = m * c * out_h * out_w;
-    DET_CHECK_ARG((total + 255) / 256 < (1ll << 31), "too many outputs");
-    roi_align_levels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(g);
+    DET_CHECK_ARG(m < (1ll << 31) && (c + kRoiChans - 1) / kRoiChans <= 65535, "too many boxes / channels");
+    dim3 grid((unsigned)m, (unsigned)((c + kRoiChans - 1) / kRoiChans));
+    roi_align_levels_kernel<<<grid, 256, 0, as_stream(stream)>>>(g);
     DET_LAUNCH_OK("roi_align_levels_kernel");
     return DET_OK;
 }
