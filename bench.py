@@ -127,7 +127,9 @@ def make_heads(pool, seed, pinned=False):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (the reference has no YOLO head; for this workload the oracle is the CPU statement)
+# CPU arm: the oracle (the reference has no YOLO head; for this workload the oracle is the CPU statement).  The path is
+# independent per image, so the CPU arm gets every host core: a pool of single-threaded worker processes, each running
+# the oracle's per-image loop on its slice of the batch (one process per core beats intra-op threads on 98-box images).
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_step(O, head, priors):
     boxes, conf, scores = O.yolo_decode(head, B, C, IMG, priors)
@@ -138,42 +140,72 @@ def cpu_step(O, head, priors):
     return kept
 
 
-def cpu_sample_size(O, priors, budget_s, steps):
-    head = torch.randn(8, S, S, B * 5 + C, generator=torch.Generator().manual_seed(1))
-    cpu_step(O, head, priors)
+_W = {}
+
+
+def _cpu_worker_init():
+    torch.set_num_threads(1)
+    from oracle import ref_torch as O
+    import det_b200
+    _W["O"], _W["priors"] = O, det_b200.YoloGridHead(S, B, C, IMG).priors
+
+
+def _cpu_worker_run(head):
+    return cpu_step(_W["O"], head, _W["priors"])
+
+
+class CpuPool:
+    """All host cores on the oracle: `cores` single-threaded processes, the batch split evenly between them."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or (os.cpu_count() or 1)
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init)
+        self.pool.map(_cpu_worker_run, [torch.randn(2, S, S, B * 5 + C) for _ in range(self.cores)])  # import + warm
+
+    def step(self, head):
+        chunks = [c for c in torch.chunk(head, self.cores) if c.shape[0]]
+        return sum(self.pool.map(_cpu_worker_run, chunks))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_images_for_budget(pool, budget_s, steps):
+    head = torch.randn(8 * pool.cores, S, S, B * 5 + C, generator=torch.Generator().manual_seed(1))
+    pool.step(head)
     t0 = time.perf_counter()
-    cpu_step(O, head, priors)
-    per_img = (time.perf_counter() - t0) / 8
-    n = int(budget_s / max(steps, 1) / max(per_img, 1e-6))
-    return max(1, min(BATCH, n))
+    pool.step(head)
+    per_img = (time.perf_counter() - t0) / head.shape[0]
+    n = int(budget_s / max(steps, 1) / max(per_img, 1e-7))
+    return max(pool.cores, min(BATCH, n))
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the CPU implementation of the same path on the host cores (rank 0 only)."""
+    """--impl reference: the CPU implementation of the same path on all host cores (rank 0 only)."""
     if rank != 0:
         return
-    from oracle import ref_torch as O
-    import det_b200
-    torch.set_num_threads(os.cpu_count() or 1)
-    priors = det_b200.YoloGridHead(S, B, C, IMG).priors
-    n_img = cpu_sample_size(O, priors, 150.0, args.steps + args.warmup)
+    pool = CpuPool()
+    n_img = cpu_images_for_budget(pool, 120.0, args.steps + args.warmup)
     heads = torch.randn(4, n_img, S, S, B * 5 + C, generator=torch.Generator().manual_seed(1))
     for w in range(args.warmup):
-        cpu_step(O, heads[w % 4], priors)
+        pool.step(heads[w % 4])
     t0 = time.perf_counter()
     for k in range(args.steps):
-        cpu_step(O, heads[k % 4], priors)
+        pool.step(heads[k % 4])
     dt = time.perf_counter() - t0
+    pool.close()
     val = n_img * args.steps / dt
-    sample = f"{n_img} of {BATCH} images per step (oracle: torch CPU decode + C greedy NMS, per-image loop)"
+    sample = (f"{n_img} of {BATCH} images per step, split over {pool.cores} single-threaded worker processes "
+              "(oracle: torch CPU decode + C greedy NMS, per-image loop)")
     print(json.dumps({
         "impl": "reference", "metric": "images/sec decode+NMS", "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": n_img, "grid": S, "boxes": B, "classes": C,
                    "score_thresh": SCORE_THR, "iou_thresh": IOU_THR, "max_det": MAX_DET},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": pool.cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -478,17 +510,22 @@ def main():
 
     cpu_baseline = None
     if rank == 0:
-        from oracle import ref_torch as O
-        torch.set_num_threads(os.cpu_count() or 1)
-        n_img = cpu_sample_size(O, yh.priors, 4.0 if args.quick else 15.0, 1)
-        sample = make_heads(1, 1)[0][:n_img]
-        cpu_step(O, sample[:4], yh.priors)
+        cpu_pool = CpuPool()
+        sample = make_heads(1, 1)[0]
+        cpu_pool.step(sample)
         t0 = time.perf_counter()
-        cpu_step(O, sample, yh.priors)
+        cpu_pool.step(sample)
+        t_batch = time.perf_counter() - t0
+        reps = max(1, min(600, int((3.0 if args.quick else 12.0) / max(t_batch, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpu_pool.step(sample)
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": n_img / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{n_img} images of the same synthetic batch, one pass ({dt:.1f} s): oracle torch-CPU "
-                                  "decode + C greedy NMS, per-image loop"}
+        cpu_pool.close()
+        cpu_baseline = {"value": reps * BATCH / dt, "unit": "images/s", "cores": cpu_pool.cores, "kind": "port",
+                        "sample": f"{reps} passes over one {BATCH}-image batch of the same synthetic distribution "
+                                  f"({dt:.1f} s), each split over {cpu_pool.cores} single-threaded worker processes: oracle "
+                                  "torch-CPU decode + C greedy NMS, per-image loop"}
         print(json.dumps({
             "metric": "images/sec decode+NMS", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
