@@ -22,6 +22,12 @@ struct MatchRule {
 
 __device__ __forceinline__ int8_t bucket_label(const MatchRule& r, float v) {
     // thresholds ascending: bucket [thr[k-1], thr[k]); static indices only, so the rule stays in the constant bank
+    if (r.nthr <= 2) {  // the reference's configurations: [0.3, 0.7] (RPN) and [0.5] (ROI heads); thr[i >= nthr] = +inf
+        int8_t lab = r.lab[0];
+        if (v >= r.thr[0]) lab = r.lab[1];
+        if (v >= r.thr[1]) lab = r.lab[2];
+        return lab;
+    }
     int8_t lab = r.lab[0];
 #pragma unroll
     for (int i = 0; i < kMaxThresholds; ++i)
@@ -38,38 +44,12 @@ constexpr int kMatchThreads = 256;
 constexpr int kMatchPerThread = 4;
 constexpr int kGtChunk = 512;
 
-// Block bounding box of the CTA's anchors (union of finite coordinates): a gt box that does not overlap it has zero
-// intersection -- hence IoU exactly 0 -- with every anchor of the CTA, so it is skipped as a whole ("culled").
-// Anchors are laid out (h, w, a): 1024 consecutive anchors are a few feature-map rows, and most gt boxes miss them.
+// Bounding box of a group of anchors (union of finite coordinates): a gt box that does not overlap it has zero
+// intersection -- hence IoU exactly 0 -- with every anchor of the group, so it is skipped as a whole ("culled").
+// Anchors are laid out (h, w, a): 128 consecutive anchors are a piece of one feature-map row, and most gt boxes miss it.
 struct BlockBox {
     float x1, y1, x2, y2;
 };
-
-__device__ __forceinline__ BlockBox block_bbox(const float4* ab, const bool* valid, float (*s_red)[4]) {
-    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (valid[k]) {  // fminf / fmaxf skip NaN coordinates: a NaN anchor never intersects anything anyway
-            x1 = fminf(x1, ab[k].x); y1 = fminf(y1, ab[k].y);
-            x2 = fmaxf(x2, ab[k].z); y2 = fmaxf(y2, ab[k].w);
-        }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o)); y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) {
-        s_red[wid][0] = x1; s_red[wid][1] = y1; s_red[wid][2] = x2; s_red[wid][3] = y2;
-    }
-    __syncthreads();
-    BlockBox b{INFINITY, INFINITY, -INFINITY, -INFINITY};
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-        b.x1 = fminf(b.x1, s_red[w][0]); b.y1 = fminf(b.y1, s_red[w][1]);
-        b.x2 = fmaxf(b.x2, s_red[w][2]); b.y2 = fmaxf(b.y2, s_red[w][3]);
-    }
-    return b;
-}
 
 // true iff the gt box certainly has zero intersection with every anchor inside `bb` (comparisons with NaN are false:
 // a NaN gt box is never culled and takes the exact path)
@@ -79,104 +59,113 @@ __device__ __forceinline__ bool culled_by(const BlockBox& bb, const float4 g) {
 
 constexpr int kMatchImgs = 8;  // at most this many images are walked by one CTA (anchors + block box stay in registers)
 
-// pass 1: per anchor column max / argmax over the image's gt boxes, threshold label; per gt row max (atomics)
+// bounding box of the 4 x 32 anchors held by a warp (finite coordinates only; NaN anchors never intersect anything)
+__device__ __forceinline__ BlockBox warp_bbox(const float4* ab, const bool* valid) {
+    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (valid[k]) {
+            x1 = fminf(x1, ab[k].x); y1 = fminf(y1, ab[k].y);
+            x2 = fmaxf(x2, ab[k].z); y2 = fmaxf(y2, ab[k].w);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o)); y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+    }
+    return BlockBox{x1, y1, x2, y2};
+}
+
+// pass 1: per anchor column max / argmax over the image's gt boxes, threshold label; per gt row max and per-CTA max.
+// Every WARP is on its own (no shared memory, no block barrier): it owns 128 consecutive anchors for up to `imgs`
+// images -- lane l holds anchors l, l+32, l+64, l+96 of them in registers (coalesced loads and stores) -- together
+// with their bounding box.  Per image the lanes first look at one gt box each (coalesced load) and vote which boxes
+// overlap the warp's bounding box at all (every other box has IoU exactly 0 with all 128 anchors); only those are
+// handed round with shuffles and evaluated, 4 IoUs per lane.  Row maxima go to `rowmax` / `blockmax` (zeroed by the
+// host) with one atomic per warp and surviving gt box.
+template <bool FULL>
+__device__ __forceinline__ void match_pass1_warp(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off,
+                                                 const float4* __restrict__ anchors, int i0, int ni, int64_t r,
+                                                 int64_t abase, const MatchRule& rule, int64_t* __restrict__ matched,
+                                                 int8_t* __restrict__ labels, float* __restrict__ matched_iou,
+                                                 float* __restrict__ rowmax, float* __restrict__ bmax) {
+    const unsigned FULLMASK = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t j0 = abase + lane;  // this lane's anchors: j0 + 32 k
+    float4 ab[4];
+    float aa[4];
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        valid[k] = FULL || (j0 + 32 * k < r);
+        ab[k] = valid[k] ? anchors[j0 + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        aa[k] = box_area(ab[k]);
+    }
+    const BlockBox wb = warp_bbox(ab, valid);
+    for (int ii = 0; ii < ni; ++ii) {
+        const int img = i0 + ii;
+        const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
+        float best[4] = {0.f, 0.f, 0.f, 0.f};  // IoUs are >= 0 and only a strictly larger one replaces the incumbent:
+        int bidx[4] = {0, 0, 0, 0};            // gt 0 wins ties at 0, exactly like torch.max(dim=0)
+        for (int t0 = 0; t0 < G; t0 += 32) {
+            float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool hit = false;
+            if (t0 + lane < G) {
+                mine = gt[g0 + t0 + lane];
+                hit = !culled_by(wb, mine);
+            }
+            unsigned todo = __ballot_sync(FULLMASK, hit);
+            while (todo) {  // ascending gt index: the first maximum wins
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float4 gb = make_float4(__shfl_sync(FULLMASK, mine.x, src), __shfl_sync(FULLMASK, mine.y, src),
+                                              __shfl_sync(FULLMASK, mine.z, src), __shfl_sync(FULLMASK, mine.w, src));
+                const float ga = box_area(gb);
+                const int t = t0 + src;
+                float rm = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // pairwise_iou(gt, anchors): boxes1 = gt, boxes2 = anchors (rpn.py:167)
+                    const float v = valid[k] ? pair_iou(gb, ga, ab[k], aa[k]) : 0.0f;
+                    if (v > best[k]) {
+                        best[k] = v;
+                        bidx[k] = t;
+                    }
+                    rm = fmaxf(rm, v);
+                }
+                if (rule.allow_lq) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(FULLMASK, rm, o));
+                    if (lane == 0 && rm > 0.0f) {
+                        atomic_max_nonneg(&rowmax[g0 + t], rm);
+                        atomic_max_nonneg(&bmax[g0 + t], rm);  // pass 2 only revisits the CTAs holding the row maximum
+                    }
+                }
+            }
+        }
+        const int64_t o = (int64_t)img * r + j0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!valid[k]) continue;
+            matched[o + 32 * k] = bidx[k];
+            labels[o + 32 * k] = G == 0 ? rule.lab[0] : bucket_label(rule, best[k]);  // matcher.py:67-77
+            if (matched_iou) matched_iou[o + 32 * k] = best[k];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMatchThreads)
 match_pass1_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
                    int n, int imgs, int64_t r, int64_t sum_g, MatchRule rule, int64_t* __restrict__ matched,
                    int8_t* __restrict__ labels, float* __restrict__ matched_iou, float* __restrict__ rowmax,
                    float* __restrict__ blockmax) {
-    __shared__ float4 s_gt[kGtChunk];
-    __shared__ float s_area[kGtChunk];
-    __shared__ float s_rmax[kGtChunk];
-    __shared__ unsigned short s_list[kGtChunk];
-    __shared__ int s_nlist;
-    __shared__ float s_red[kMatchThreads / 32][4];
-    __shared__ int s_off[kMatchImgs + 1];
     const int i0 = blockIdx.y * imgs, ni = min(imgs, n - i0);
-    const int64_t base = (int64_t)blockIdx.x * (kMatchThreads * kMatchPerThread);
-    float4 ab[kMatchPerThread];
-    float aa[kMatchPerThread];
-    bool valid[kMatchPerThread];
-#pragma unroll
-    for (int k = 0; k < kMatchPerThread; ++k) {
-        const int64_t j = base + k * kMatchThreads + threadIdx.x;
-        valid[k] = j < r;
-        ab[k] = valid[k] ? anchors[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[k] = box_area(ab[k]);
-    }
-    if (threadIdx.x <= ni) s_off[threadIdx.x] = gt_off[i0 + threadIdx.x];
-    const BlockBox bb = block_bbox(ab, valid, s_red);  // contains a barrier: s_off is visible afterwards
-    for (int ii = 0; ii < ni; ++ii) {
-        const int img = i0 + ii;
-        const int g0 = s_off[ii], G = s_off[ii + 1] - g0;
-        float best[kMatchPerThread];
-        int bidx[kMatchPerThread];
-#pragma unroll
-        for (int k = 0; k < kMatchPerThread; ++k) {
-            best[k] = 0.0f;  // IoUs are >= 0 and only a strictly larger one replaces the incumbent: gt 0 wins ties
-            bidx[k] = 0;     // at 0, exactly like torch.max(dim=0) on the materialised matrix
-        }
-        for (int c0 = 0; c0 < G; c0 += kGtChunk) {
-            const int cn = min(kGtChunk, G - c0);
-            __syncthreads();
-            if (threadIdx.x == 0) s_nlist = 0;
-            __syncthreads();
-            for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
-                const float4 b = gt[g0 + c0 + t];
-                s_gt[t] = b;
-                s_area[t] = box_area(b);
-                s_rmax[t] = 0.0f;
-                if (!culled_by(bb, b)) s_list[atomicAdd(&s_nlist, 1)] = (unsigned short)t;  // survivors, any order
-            }
-            __syncthreads();
-            const int ns = s_nlist;
-            for (int q = 0; q < ns; ++q) {
-                const int t = (int)s_list[q];
-                const float4 gb = s_gt[t];
-                const float ga = s_area[t];
-                float rm = 0.0f;
-#pragma unroll
-                for (int k = 0; k < kMatchPerThread; ++k) {
-                    // pairwise_iou(gt, anchors): boxes1 = gt, boxes2 = anchors (rpn.py:167)
-                    const float v = valid[k] ? pair_iou(gb, ga, ab[k], aa[k]) : 0.0f;
-                    // torch.max(dim=0): the first maximum wins -- the list is unordered, so ties go to the lower index
-                    if (v > best[k] || (v == best[k] && c0 + t < bidx[k])) {
-                        best[k] = v;
-                        bidx[k] = c0 + t;
-                    }
-                    rm = fmaxf(rm, v);
-                }
-                if (rule.allow_lq) {  // one shared-memory atomic per warp, not per thread
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
-                    if ((threadIdx.x & 31) == 0 && rm > s_rmax[t]) atomic_max_nonneg(&s_rmax[t], rm);
-                }
-            }
-            __syncthreads();
-            if (rule.allow_lq)
-                for (int t = threadIdx.x; t < cn; t += kMatchThreads) {
-                    const float m = s_rmax[t];
-                    if (m > 0.0f) atomic_max_nonneg(&rowmax[g0 + c0 + t], m);
-                    // this CTA's own maximum for gt t: pass 2 only revisits the CTAs that hold the row maximum
-                    blockmax[(int64_t)blockIdx.x * sum_g + g0 + c0 + t] = m;
-                }
-        }
-#pragma unroll
-        for (int k = 0; k < kMatchPerThread; ++k) {
-            const int64_t j = base + k * kMatchThreads + threadIdx.x;
-            if (j >= r) continue;
-            const int64_t o = (int64_t)img * r + j;
-            if (G == 0) {  // matcher.py:67-77: no gt -> match 0, label labels[0]
-                matched[o] = 0;
-                labels[o] = rule.lab[0];
-                if (matched_iou) matched_iou[o] = 0.0f;
-            } else {
-                matched[o] = bidx[k];
-                labels[o] = bucket_label(rule, best[k]);
-                if (matched_iou) matched_iou[o] = best[k];
-            }
-        }
-    }
+    const int64_t abase = (int64_t)blockIdx.x * (kMatchThreads * kMatchPerThread) + (int64_t)(threadIdx.x >> 5) * 128;
+    float* bmax = blockmax + (int64_t)blockIdx.x * sum_g;
+    if (abase + 128 <= r)  // warp-uniform: all 128 anchors exist
+        match_pass1_warp<true>(gt, gt_off, anchors, i0, ni, r, abase, rule, matched, labels, matched_iou, rowmax, bmax);
+    else if (abase < r)
+        match_pass1_warp<false>(gt, gt_off, anchors, i0, ni, r, abase, rule, matched, labels, matched_iou, rowmax, bmax);
 }
 
 // pass 2 (low-quality promotion, matcher.py:96-120): label 1 wherever IoU(gt, anchor) == max over anchors for that gt.
@@ -938,7 +927,7 @@ int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, int n, i
     cudaStream_t st = as_stream(stream);
     float* rowmax = static_cast<float*>(workspace);
     if (allow_low_quality && sum_g > 0) {
-        cudaError_t e = cudaMemsetAsync(rowmax, 0, sizeof(float) * (size_t)sum_g, st);
+        cudaError_t e = cudaMemsetAsync(rowmax, 0, sizeof(float) * (size_t)sum_g * (size_t)(1 + match_blocks(r)), st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     }
     // images per CTA: amortise the anchor loads / block box when there are plenty of CTAs, keep one image per CTA when
