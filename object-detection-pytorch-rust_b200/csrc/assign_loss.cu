@@ -352,6 +352,7 @@ struct SampleSmem {
     int remaining[2];
     int hist[2][256];
     unsigned ckey[2][kCandCap];
+    int cidx[2][kCandCap];  // anchor index of the candidate | its original label in the top byte
 };
 
 // labels of one image in 16-byte granules of the GLOBAL address space (rows of odd length start unaligned): granule c
@@ -366,35 +367,33 @@ struct RowView {
     }
     __device__ __forceinline__ int64_t first(int c) const { return (int64_t)c * 16 - a; }
     __device__ __forceinline__ bool full(int c) const { return first(c) >= 0 && first(c) + 16 <= r; }
-    __device__ __forceinline__ void load(int c, int8_t (&v)[16]) const {
+    // the granule as 4 little-endian words of 4 labels
+    __device__ __forceinline__ uint4 load(int c) const {
         const int64_t lo = first(c);
-        if (full(c)) {
-            const uint4 q = *reinterpret_cast<const uint4*>(row + lo);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = (int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = (lo + k >= 0 && lo + k < r) ? row[lo + k] : (int8_t)-1;
-        }
+        if (full(c)) return *reinterpret_cast<const uint4*>(row + lo);
+        uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        for (int k = 0; k < 16; ++k)
+            if (lo + k >= 0 && lo + k < r)
+                w[k >> 2] = (w[k >> 2] & ~(0xffu << (8 * (k & 3)))) | ((uint32_t)(uint8_t)row[lo + k] << (8 * (k & 3)));
+        return make_uint4(w[0], w[1], w[2], w[3]);
     }
-    __device__ __forceinline__ void store(int c, const int8_t (&v)[16]) const {
+    __device__ __forceinline__ void store(int c, const uint4 q) const {
         const int64_t lo = first(c);
         if (full(c)) {
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) w[k >> 2] |= (uint32_t)(uint8_t)v[k] << (8 * (k & 3));
-            *reinterpret_cast<uint4*>(row + lo) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(row + lo) = q;
         } else {
-#pragma unroll
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
             for (int k = 0; k < 16; ++k)
-                if (lo + k >= 0 && lo + k < r) row[lo + k] = v[k];
+                if (lo + k >= 0 && lo + k < r) row[lo + k] = (int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
         }
     }
 };
 
 // cls: 0 = positive (anything that is neither -1 nor background), 1 = background (label == 0), -1 = ignored
 __device__ __forceinline__ int label_class(int8_t l) { return l == 0 ? 1 : (l == -1 ? -1 : 0); }
+
+// per-byte masks (0xff where true) of a word of 4 labels
+__device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t pattern) { return __vcmpeq4(w, pattern); }
 
 __global__ void __launch_bounds__(kSampleThreads)
 subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float positive_fraction, uint64_t seed) {
@@ -407,19 +406,20 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
         sm.ncand[tid] = 0;
     }
     __syncthreads();
-    // ---- pass A: class counts
-    int c0 = 0, c1 = 0;
+    // ---- pass A: class counts, 4 labels per SIMD-in-word compare
+    int c_bg = 0, c_ign = 0, c_all = 0;
     for (int c = tid; c < rv.ngran; c += kSampleThreads) {
-        int8_t v[16];
-        rv.load(c, v);
+        const uint4 q = rv.load(c);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            c0 += (v[k] != -1 && v[k] != 0);
-            c1 += (v[k] == 0);
+        for (int k = 0; k < 4; ++k) {
+            c_bg += __popc(bytes_eq(w[k], 0u));
+            c_ign += __popc(bytes_eq(w[k], 0xffffffffu));
         }
+        c_all += 16;
     }
-    c0 = warp_sum(c0);
-    c1 = warp_sum(c1);
+    int c1 = warp_sum(c_bg) >> 3;                          // popc counts 8 bits per matching byte
+    int c0 = warp_sum(c_all) - c1 - (warp_sum(c_ign) >> 3);  // bytes outside the row read as -1 (ignored)
     if ((tid & 31) == 0) {
         if (c0) atomicAdd(&sm.cnt[0], c0);
         if (c1) atomicAdd(&sm.cnt[1], c1);
@@ -433,7 +433,8 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
     const int have[2] = {npos, nneg};
     const bool need[2] = {want_pos < npos, want_neg < nneg};  // otherwise the whole class is kept
     if (!need[0] && !need[1]) return;
-    // ---- pass B: candidates under a threshold sized for want + slack survivors
+    // ---- pass B: hash every label of a thinned class once; keep (key, index, label) of those under a threshold sized
+    //      for want + slack survivors
     unsigned thr[2];
     bool direct[2];
 #pragma unroll
@@ -441,34 +442,38 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
         const float slack = 4.0f * sqrtf((float)want[c]) + 16.0f;
         const double p = ((double)want[c] + (double)slack) / (double)max(have[c], 1);
         thr[c] = p >= 1.0 ? 0xffffffffu : (unsigned)(p * 4294967296.0);
-        direct[c] = need[c] && want[c] > 0 && (double)want[c] + 2.0 * slack <= (double)kCandCap;
+        direct[c] = need[c] && want[c] > 0 && (double)want[c] + 2.0 * slack <= (double)kCandCap && r < (1 << 24);
     }
     if (direct[0] || direct[1]) {
         for (int c = tid; c < rv.ngran; c += kSampleThreads) {
-            int8_t v[16];
-            rv.load(c, v);
+            const uint4 q = rv.load(c);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
             const int64_t j0 = rv.first(c);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const int cls = label_class(v[k]);
+                const int8_t l = (int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                const int cls = label_class(l);
                 if (cls < 0 || !direct[cls]) continue;
                 const unsigned key = sample_key(img_seed, (uint32_t)(j0 + k));
                 if (key <= thr[cls]) {
                     const int slot = atomicAdd(&sm.ncand[cls], 1);
-                    if (slot < kCandCap) sm.ckey[cls][slot] = key;
+                    if (slot < kCandCap) {
+                        sm.ckey[cls][slot] = key;
+                        sm.cidx[cls][slot] = (int)(j0 + k) | ((int)(uint8_t)l << 24);
+                    }
                 }
             }
         }
     }
     __syncthreads();
     // ---- pass C: the want-th smallest key, by rank counting among the candidates
-    bool radix[2];
+    bool radix[2], listed[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const int nc = sm.ncand[c];
-        const bool ok = direct[c] && nc >= want[c] && nc <= kCandCap;
-        radix[c] = need[c] && want[c] > 0 && !ok;
-        if (ok) {
+        listed[c] = direct[c] && nc >= want[c] && nc <= kCandCap;
+        radix[c] = need[c] && want[c] > 0 && !listed[c];
+        if (listed[c]) {
             for (int t = tid; t < nc; t += kSampleThreads) {
                 const unsigned key = sm.ckey[c][t];
                 int rank = 0;
@@ -490,12 +495,12 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
             const unsigned pre[2] = {sm.prefix[0], sm.prefix[1]};
             const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
             for (int c = tid; c < rv.ngran; c += kSampleThreads) {
-                int8_t v[16];
-                rv.load(c, v);
+                const uint4 q = rv.load(c);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
                 const int64_t j0 = rv.first(c);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const int cls = label_class(v[k]);
+                    const int cls = label_class((int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu));
                     if (cls < 0 || !radix[cls]) continue;
                     const unsigned key = sample_key(img_seed, (uint32_t)(j0 + k));
                     if ((key & himask) == (pre[cls] & himask)) atomicAdd(&sm.hist[cls][(key >> shift) & 255], 1);
@@ -516,24 +521,50 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
         if (tid < 2 && radix[tid]) sm.sel[tid] = sm.prefix[tid];
     }
     __syncthreads();
-    // ---- pass D: everything of a thinned class above its selection key becomes -1
+    // ---- pass D: a thinned class becomes -1 wholesale (SIMD-in-word, no hashing), except that a class that went through
+    //      the radix fallback is decided label by label; then the kept candidates of the listed classes are restored
     const unsigned sel[2] = {sm.sel[0], sm.sel[1]};
     for (int c = tid; c < rv.ngran; c += kSampleThreads) {
-        int8_t v[16];
-        rv.load(c, v);
-        const int64_t j0 = rv.first(c);
+        const uint4 q = rv.load(c);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
         bool changed = false;
+        if (!radix[0] && !radix[1]) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int cls = label_class(v[k]);
-            if (cls < 0 || !need[cls]) continue;
-            const bool keep = want[cls] > 0 && sample_key(img_seed, (uint32_t)(j0 + k)) <= sel[cls];
-            if (!keep) {
-                v[k] = -1;
-                changed = true;
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t bg = bytes_eq(w[k], 0u), ign = bytes_eq(w[k], 0xffffffffu);
+                uint32_t kill = 0u;
+                if (need[1]) kill |= bg;            // background bytes -> 0xff
+                if (need[0]) kill |= ~(bg | ign);   // positive bytes -> 0xff
+                changed |= (kill & ~ign) != 0u;
+                w[k] |= kill;
+            }
+        } else {
+            const int64_t j0 = rv.first(c);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int8_t l = (int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                const int cls = label_class(l);
+                if (cls < 0 || !need[cls]) continue;
+                // listed classes are wiped here and restored below; radix classes are decided by their key
+                const bool keep = radix[cls] && want[cls] > 0 && sample_key(img_seed, (uint32_t)(j0 + k)) <= sel[cls];
+                if (!keep) {
+                    w[k >> 2] |= 0xffu << (8 * (k & 3));
+                    changed = true;
+                }
             }
         }
-        if (changed) rv.store(c, v);
+        if (changed) rv.store(c, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+    __syncthreads();  // the wipe is complete (this CTA owns the whole row) before the survivors are written back
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (!listed[c]) continue;
+        const int nc = sm.ncand[c];
+        for (int t = tid; t < nc; t += kSampleThreads)
+            if (sm.ckey[c][t] <= sel[c]) {
+                const int packed = sm.cidx[c][t];
+                rv.row[packed & 0xffffff] = (int8_t)(packed >> 24);
+            }
     }
 }
 
