@@ -675,16 +675,19 @@ rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ del
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
     const int64_t warps_total = ((int64_t)gridDim.x * kLossThreads) >> 5;
-    for (int64_t base = warp_global * 128; base < total; base += warps_total * 128) {
+    auto load_word = [&](int64_t base) -> uint32_t {  // labels base + 4*lane .. +3 (label -1 = ignored past the end)
         const int64_t e4 = base + 4 * lane;
-        uint32_t word;
-        if (e4 + 4 <= total) {
-            word = __ldcs(reinterpret_cast<const unsigned int*>(labels + e4));
-        } else {
-            word = 0xffffffffu;  // label -1: ignored
-            for (int k = 0; k < 4; ++k)
-                if (e4 + k < total) word = (word & ~(0xffu << (8 * k))) | ((uint32_t)(uint8_t)labels[e4 + k] << (8 * k));
-        }
+        if (e4 + 4 <= total) return __ldcs(reinterpret_cast<const unsigned int*>(labels + e4));
+        uint32_t word = 0xffffffffu;
+        for (int k = 0; k < 4; ++k)
+            if (e4 + k < total) word = (word & ~(0xffu << (8 * k))) | ((uint32_t)(uint8_t)labels[e4 + k] << (8 * k));
+        return word;
+    };
+    const int64_t step = warps_total * 128;
+    uint32_t word_next = warp_global * 128 < total ? load_word(warp_global * 128) : 0xffffffffu;
+    for (int64_t base = warp_global * 128; base < total; base += step) {
+        const uint32_t word = word_next;
+        if (base + step < total) word_next = load_word(base + step);  // in flight while this block's stores are issued
 #pragma unroll
         for (int round = 0; round < 4; ++round) {
             const uint32_t w = __shfl_sync(0xffffffffu, word, 8 * round + (lane >> 2));
