@@ -89,6 +89,11 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
     __shared__ int s_fl[4];
     __shared__ unsigned s_nz[kFastMaxC][4];
     __shared__ int s_total;
+    __shared__ struct {
+        int cnt, gcat, gfl;
+        float gmx, gmn;
+        unsigned cut[2];
+    } s_img;
     __shared__ unsigned long long s_best;
     __shared__ __align__(16) int s_hist[kFastBins];   // candidates by score (tier cut)
     __shared__ __align__(16) int s_hist2[kFastBins];  // kept detections by score (output order)
@@ -217,34 +222,22 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         }
     }
     __syncthreads();
-    int cnt, gcat;
-    {
+    // ---- image-level reductions and T: the tier cuts -- warp 0 only, broadcast through shared memory
+    if (wid == 0) {
         const int mq = lane < C ? s_m[lane] : 0;
-        cnt = warp_sum(mq);
+        const int cnt_w = warp_sum(mq);
         const unsigned has = __ballot_sync(FULL, mq > 0);
-        gcat = has ? 31 - __clz(has) : 0;
-    }
-    float gmx = -INFINITY, gmn = INFINITY;
-    int gfl = 3;
-    for (int q = 0; q < (P + 31) / 32; ++q) {
-        gmx = max_nan(gmx, s_mx[q]);
-        gmn = min_nan(gmn, s_mn[q]);
-        gfl &= s_fl[q];
-    }
-    // reference CPU rule: boxes.numel() <= 4000 -> coordinate-offset trick (torchvision/ops/boxes.py batched_nms)
-    const bool trick = (prm.mode == DET_NMS_AUTO) ? (cnt <= 1000) : (prm.mode == DET_NMS_OFFSET_TRICK);
-    const float span = trick ? gmx + 1.0f : 0.0f;  // max_coordinate + torch.tensor(1).to(boxes)
-    const float thr_f = prm.thr_f;
-    // categories can be swept independently iff shifted boxes of different categories cannot intersect
-    const float far = gmx + (float)gcat * span;
-    const bool sweep_ok = (gfl & 1) && gmn > -1.0f && thr_f >= 0.0f && isfinite(far);
-    const bool by_cat = !trick || sweep_ok;
-    const bool nonan = (gfl & 2) != 0;
-    // ---- T: tier cut, derived by every warp on its own from the candidate histogram
-    unsigned tier_bits = 0u;
-    {
-        const int target = K + K / 3 + 8;
-        if (cnt > target) {
+        float gmx_w = -INFINITY, gmn_w = INFINITY;
+        int gfl_w = 3;
+        for (int q = 0; q < (P + 31) / 32; ++q) {
+            gmx_w = max_nan(gmx_w, s_mx[q]);
+            gmn_w = min_nan(gmn_w, s_mn[q]);
+            gfl_w &= s_fl[q];
+        }
+        // two nested cuts from the candidate histogram: the highest bins holding >= target candidates
+        unsigned cut[2] = {0u, 0u};
+        const int targets[2] = {K + K / 6 + 8, 2 * K + 16};
+        if (cnt_w > targets[0]) {
             int h8[8];
             const int4 ha = reinterpret_cast<const int4*>(s_hist)[lane * 2], hb = reinterpret_cast<const int4*>(s_hist)[lane * 2 + 1];
             h8[0] = ha.x; h8[1] = ha.y; h8[2] = ha.z; h8[3] = ha.w; h8[4] = hb.x; h8[5] = hb.y; h8[6] = hb.z; h8[7] = hb.w;
@@ -255,25 +248,54 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
                 const int v = __shfl_down_sync(FULL, suf, o);
                 if (lane + o < 32) suf += v;
             }
-            const unsigned reach = __ballot_sync(FULL, suf >= target);  // a prefix of lanes: lane 0 holds cnt > target
-            const int L = 31 - __clz(reach);
-            int bin = 0;
-            if (lane == L) {
-                int run = suf - mine;
-                bin = 8 * L;
 #pragma unroll
-                for (int k = 7; k >= 0; --k) {
-                    run += h8[k];
-                    if (run >= target) {
-                        bin = 8 * L + k;
-                        break;
+            for (int tq = 0; tq < 2; ++tq) {
+                const int target = targets[tq];
+                if (cnt_w <= target) continue;  // warp-uniform: this tier would hold everything
+                const unsigned reach = __ballot_sync(FULL, suf >= target);  // a prefix of lanes (lane 0: cnt > target)
+                const int L = 31 - __clz(reach);
+                int bin = 0;
+                if (lane == L) {
+                    int run = suf - mine;
+                    bin = 8 * L;
+#pragma unroll
+                    for (int k = 7; k >= 0; --k) {
+                        run += h8[k];
+                        if (run >= target) {
+                            bin = 8 * L + k;
+                            break;
+                        }
                     }
                 }
+                bin = __shfl_sync(FULL, bin, L);
+                cut[tq] = bin > 0 ? lo_bits + ((unsigned)bin << hshift) : 0u;
             }
-            bin = __shfl_sync(FULL, bin, L);
-            tier_bits = bin > 0 ? lo_bits + ((unsigned)bin << hshift) : 0u;
+        }
+        if (lane == 0) {
+            s_img.cnt = cnt_w;
+            s_img.gcat = has ? 31 - __clz(has) : 0;
+            s_img.gmx = gmx_w;
+            s_img.gmn = gmn_w;
+            s_img.gfl = gfl_w;
+            s_img.cut[0] = cut[0];
+            s_img.cut[1] = cut[1];
         }
     }
+    __syncthreads();
+    const int cnt = s_img.cnt, gcat = s_img.gcat, gfl = s_img.gfl;
+    const float gmx = s_img.gmx, gmn = s_img.gmn;
+    // reference CPU rule: boxes.numel() <= 4000 -> coordinate-offset trick (torchvision/ops/boxes.py batched_nms)
+    const bool trick = (prm.mode == DET_NMS_AUTO) ? (cnt <= 1000) : (prm.mode == DET_NMS_OFFSET_TRICK);
+    const float span = trick ? gmx + 1.0f : 0.0f;  // max_coordinate + torch.tensor(1).to(boxes)
+    const float thr_f = prm.thr_f;
+    // categories can be swept independently iff shifted boxes of different categories cannot intersect
+    const float far = gmx + (float)gcat * span;
+    const bool sweep_ok = (gfl & 1) && gmn > -1.0f && thr_f >= 0.0f && isfinite(far);
+    const bool by_cat = !trick || sweep_ok;
+    const bool nonan = (gfl & 2) != 0;
+    // tiers: NMS on the candidates above cut[0] (about 7/6 max_det of them); if that does not yield max_det survivors,
+    // above cut[1] (about 2 max_det); finally on everything.  A cut of 0 means "that tier already holds everything".
+    const unsigned tier_cut[3] = {s_img.cut[0], s_img.cut[1], 0u};
     DET_MARK(2);
 
     uint64_t* buf_a = reinterpret_cast<uint64_t*>(cls_region);
@@ -286,9 +308,10 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         bool mine_kept[4];
         unsigned base2 = 0u;
         int shift2 = 0;
-        for (int tier = tier_bits ? 0 : 1; tier < 2; ++tier) {
-            const unsigned cut_bits = tier == 0 ? tier_bits : 0u;
-            base2 = tier == 0 ? tier_bits : lo_bits;  // every kept score of this pass has bits >= base2
+        for (int tier = 0; tier < 3; ++tier) {
+            const unsigned cut_bits = tier_cut[tier];
+            if (tier < 2 && (cut_bits == 0u || cut_bits == tier_cut[tier + 1])) continue;  // same set as a later tier
+            base2 = cut_bits ? cut_bits : lo_bits;     // every kept score of this pass has bits >= base2
             shift2 = score_shift(base2);
 #pragma unroll
             for (int k = 0; k < 4; ++k) mine_kept[k] = false;
@@ -414,7 +437,7 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
                 DET_MARK(8);
             }
             __syncthreads();  // every class is done with its scratch: the merge buffers may now overwrite it
-            if (tier == 1 || s_total >= K) break;  // tier 0 sufficed: the first K kept detections lie above the cut
+            if (tier == 2 || s_total >= K) break;  // enough: the first K kept detections all lie above this cut
             __syncthreads();                       // heavy suppression: redo on every candidate
             for (int i = tid; i < kFastBins; i += T) s_hist2[i] = 0;
             if (tid == 0) s_total = 0;
