@@ -472,12 +472,15 @@ def main():
     kept = sum(int(o["count"].sum()) for o in outs) / len(outs)
     algo_bytes = BATCH * img_bytes + kept * (8 + 16 + 4) + BATCH * 4
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    # achieved = algorithmic bytes x launches / timed region: the launches of consecutive steps overlap (4 streams), so
+    # this is the GPU's sustained rate on this kernel, not one launch in isolation (22 us alone under ncu)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic("yolo_fast_kernel"), "kernel": "yolo_fast_kernel<640,2,7,2,20>",
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                "note": "3.7 MB per launch = 0.6 us at the HBM peak: one launch of 256 CTAs (one image each) is bound by "
-                        "launch latency + per-image NMS instruction issue, not by HBM; the HBM-bound kernels of this "
-                        "path (dense-head decode, loss fwd+bwd) are in extras with their own rooflines"}
+                "note": "3.7 MB per launch = 0.6 us at the HBM peak: a 256-image launch (one CTA per image) is bound by "
+                        "instruction issue of the per-image NMS (issue slots ~75 % busy with 4 launches overlapped), "
+                        "not by HBM; the HBM-bound kernels of this path (dense-head decode, loss fwd+bwd) are in "
+                        "extras with their own rooflines"}
 
     # end to end through the public API (det.YoloHostPipeline) with HOST buffers: every step uploads its batch from
     # pinned host memory, runs the fused kernel and downloads the detections; H2D / kernel / D2H of consecutive
