@@ -19,6 +19,7 @@ NVCC_FLAGS = [
     "--shared", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
+    "--threads", "0",           # the translation units are compiled in parallel
 ]
 
 
