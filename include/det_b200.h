@@ -206,7 +206,8 @@ DET_API int det_yolo_loss(const float* head, const int8_t* labels, const int64_t
  * (next tier) FPN level assignment + ROIAlign over a feature pyramid -- replaces
  *      assign_boxes_to_levels / ROIPooler.forward / ROIAlign.forward,
  *      python/src/models/modules/roi_poolers.py:103-131, :269-331, :55-72 (torchvision.ops.roi_align underneath).
- *      Forward only in this round.
+ *      det_roi_align_levels_backward: levels' `data` are the GRADIENT buffers (n, c, h, w), zeroed by the caller and
+ *      accumulated into with atomics; grad_out (m, c, out_h, out_w).
  *      det_roi_levels: level_out[i] = clamp(floor(canonical_level + log2(sqrt(area_i)/canonical_box_size + 1e-8)),
  *      min_level, max_level) - min_level, boxes (m,4).
  *      det_roi_align_levels: every box samples the level `level[i]` (NULL when num_levels == 1) of image
@@ -224,6 +225,10 @@ DET_API int det_roi_levels(const float* boxes, int64_t m, int min_level, int max
 DET_API int det_roi_align_levels(const det_feature_level_t* levels_host, int num_levels, int n, int c, const float* boxes,
                          const int32_t* batch_index, const int64_t* level, int64_t m, int out_h, int out_w,
                          int sampling_ratio, int aligned, float* out, void* stream);
+DET_API int det_roi_align_levels_backward(const det_feature_level_t* grad_levels_host, int num_levels, int n, int c,
+                                  const float* boxes, const int32_t* batch_index, const int64_t* level, int64_t m,
+                                  int out_h, int out_w, int sampling_ratio, int aligned, const float* grad_out,
+                                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -171,6 +171,85 @@ __global__ void __launch_bounds__(256) roi_align_levels_kernel(const __grid_cons
     }
 }
 
+// Backward of the pyramid ROIAlign: grad_input[level] (N, C, H, W; zeroed by the caller) += the bilinear weights of
+// every sample times grad_out / count -- the transpose of the forward gather, so the same tap tables drive 4 atomic
+// adds per sample (what autograd does through torchvision's roi_align backward).
+struct RoiGradArgs {
+    float* grad[kRoiMaxLevels];  // (N, C, H, W) per level
+    int h[kRoiMaxLevels], w[kRoiMaxLevels];
+    float scale[kRoiMaxLevels];
+    int num_levels, c, out_h, out_w, sampling_ratio, aligned;
+    const float4* boxes;
+    const int32_t* batch_index;
+    const int64_t* level;
+    const float* grad_out;  // (M, C, out_h, out_w)
+};
+
+__global__ void __launch_bounds__(256) roi_align_levels_backward_kernel(const __grid_constant__ RoiGradArgs g) {
+    __shared__ AxisTap s_ty[kRoiTaps], s_tx[kRoiTaps];
+    const int64_t box = blockIdx.x;
+    const int c0 = blockIdx.y * kRoiChans, nc = min(kRoiChans, g.c - c0);
+    const int bins = g.out_h * g.out_w;
+    const int l = g.level ? (int)g.level[box] : 0;
+    const int H = g.h[l], W = g.w[l];
+    const float scale = g.scale[l];
+    const float4 b = g.boxes[box];
+    const float off = g.aligned ? 0.5f : 0.0f;
+    const float x1 = b.x * scale - off, y1 = b.y * scale - off;
+    float rw = b.z * scale - off - x1, rh = b.w * scale - off - y1;
+    if (!g.aligned) {
+        rw = fmaxf(rw, 1.0f);
+        rh = fmaxf(rh, 1.0f);
+    }
+    const float bin_h = rh / (float)g.out_h, bin_w = rw / (float)g.out_w;
+    const int gh = g.sampling_ratio > 0 ? g.sampling_ratio : (int)ceilf(rh / (float)g.out_h);
+    const int gw = g.sampling_ratio > 0 ? g.sampling_ratio : (int)ceilf(rw / (float)g.out_w);
+    const float count = fmaxf((float)(gh * gw), 1.0f);
+    const int64_t plane_sz = (int64_t)H * W;
+    float* base = g.grad[l] + ((int64_t)g.batch_index[box] * g.c + c0) * plane_sz;
+    const float* go = g.grad_out + (box * g.c + c0) * bins;
+    const bool tabulated = gh >= 0 && gw >= 0 && g.out_h * gh <= kRoiTaps && g.out_w * gw <= kRoiTaps;  // CTA-uniform
+    if (tabulated) {
+        for (int t = threadIdx.x; t < g.out_h * gh; t += 256) {
+            const int ph = t / gh, iy = t - ph * gh;
+            AxisTap a = axis_tap(y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh, H);
+            a.lo *= W;
+            a.hi *= W;
+            s_ty[t] = a;
+        }
+        for (int t = threadIdx.x; t < g.out_w * gw; t += 256) {
+            const int pw = t / gw, ix = t - pw * gw;
+            s_tx[t] = axis_tap(x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw, W);
+        }
+        __syncthreads();
+    }
+    for (int o = threadIdx.x; o < nc * bins; o += 256) {
+        const int ch = o / bins, bin = o - ch * bins;
+        const int ph = bin / g.out_w, pw = bin - ph * g.out_w;
+        float* plane = base + (int64_t)ch * plane_sz;
+        const float gv = go[o] / count;
+        for (int iy = 0; iy < gh; ++iy) {
+            AxisTap ty;
+            if (tabulated) {
+                ty = s_ty[ph * gh + iy];
+            } else {
+                ty = axis_tap(y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh, H);
+                ty.lo *= W;
+                ty.hi *= W;
+            }
+            for (int ix = 0; ix < gw; ++ix) {
+                const AxisTap tx = tabulated ? s_tx[pw * gw + ix]
+                                             : axis_tap(x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw, W);
+                const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+                if (w1 != 0.0f) atomicAdd(plane + ty.lo + tx.lo, w1 * gv);
+                if (w2 != 0.0f) atomicAdd(plane + ty.lo + tx.hi, w2 * gv);
+                if (w3 != 0.0f) atomicAdd(plane + ty.hi + tx.lo, w3 * gv);
+                if (w4 != 0.0f) atomicAdd(plane + ty.hi + tx.hi, w4 * gv);
+            }
+        }
+    }
+}
+
 }  // namespace det
 
 using namespace det;
@@ -220,6 +299,38 @@ int det_roi_align_levels(const det_feature_level_t* levels_host, int num_levels,
     dim3 grid((unsigned)m, (unsigned)((c + kRoiChans - 1) / kRoiChans));
     roi_align_levels_kernel<<<grid, 256, 0, as_stream(stream)>>>(g);
     DET_LAUNCH_OK("roi_align_levels_kernel");
+    return DET_OK;
+}
+
+int det_roi_align_levels_backward(const det_feature_level_t* grad_levels_host, int num_levels, int n, int c,
+                                  const float* boxes, const int32_t* batch_index, const int64_t* level, int64_t m,
+                                  int out_h, int out_w, int sampling_ratio, int aligned, const float* grad_out,
+                                  void* stream) {
+    DET_CHECK_ARG(num_levels >= 1 && num_levels <= kRoiMaxLevels && n >= 0 && c >= 1 && m >= 0 && out_h >= 1 && out_w >= 1,
+                  "bad size");
+    if (m == 0) return DET_OK;
+    DET_CHECK_ARG(grad_levels_host && boxes && batch_index && grad_out && (level || num_levels == 1), "null pointer");
+    if (!aligned16(boxes)) {
+        set_error("boxes must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    RoiGradArgs g;
+    for (int l = 0; l < kRoiMaxLevels; ++l) {
+        if (l < num_levels) {
+            DET_CHECK_ARG(grad_levels_host[l].data && grad_levels_host[l].h >= 1 && grad_levels_host[l].w >= 1, "bad level");
+            g.grad[l] = const_cast<float*>(grad_levels_host[l].data);  // the level's GRADIENT buffer, accumulated into
+            g.h[l] = grad_levels_host[l].h; g.w[l] = grad_levels_host[l].w; g.scale[l] = grad_levels_host[l].spatial_scale;
+        } else {
+            g.grad[l] = nullptr; g.h[l] = 1; g.w[l] = 1; g.scale[l] = 1.f;
+        }
+    }
+    g.num_levels = num_levels; g.c = c; g.out_h = out_h; g.out_w = out_w; g.sampling_ratio = sampling_ratio;
+    g.aligned = aligned ? 1 : 0; g.boxes = reinterpret_cast<const float4*>(boxes); g.batch_index = batch_index;
+    g.level = num_levels > 1 ? level : nullptr; g.grad_out = grad_out;
+    DET_CHECK_ARG(m < (1ll << 31) && (c + kRoiChans - 1) / kRoiChans <= 65535, "too many boxes / channels");
+    dim3 grid((unsigned)m, (unsigned)((c + kRoiChans - 1) / kRoiChans));
+    roi_align_levels_backward_kernel<<<grid, 256, 0, as_stream(stream)>>>(g);
+    DET_LAUNCH_OK("roi_align_levels_backward_kernel");
     return DET_OK;
 }
 

@@ -1,5 +1,6 @@
 """FPN level assignment + ROIAlign -- drop-in for ``assign_boxes_to_levels``, ``convert_boxes_to_pooler_format``,
-``ROIAlign`` and ``ROIPooler`` of the reference (python/src/models/modules/roi_poolers.py:15-331), forward pass.
+``ROIAlign`` and ``ROIPooler`` of the reference (python/src/models/modules/roi_poolers.py:15-331), forward and
+backward (gradients flow to the feature maps, as through torchvision's roi_align).
 
 The reference loops over the pyramid levels with nonzero / gather / torchvision ``roi_align`` / ``index_put_``; here
 one kernel computes every box's level (det_roi_levels) and one kernel samples all levels (det_roi_align_levels).
@@ -37,28 +38,60 @@ def assign_boxes_to_levels(box_lists: Sequence, min_level: int, max_level: int, 
     return out
 
 
+def _level_table(tensors, scales):
+    lv = (N.FeatureLevel * len(tensors))()
+    for i, (f, s) in enumerate(zip(tensors, scales)):
+        lv[i].data, lv[i].h, lv[i].w, lv[i].spatial_scale, lv[i].reserved = f.data_ptr(), f.shape[2], f.shape[3], float(s), 0
+    return lv
+
+
+class _RoiAlignLevels(torch.autograd.Function):
+    """forward: det_roi_align_levels; backward: det_roi_align_levels_backward (gradients w.r.t. the feature maps)."""
+
+    @staticmethod
+    def forward(ctx, boxes, batch_index, level, scales, output_size, sampling_ratio, aligned, *feats):
+        n, c = feats[0].shape[0], feats[0].shape[1]
+        m = boxes.shape[0]
+        out = torch.empty((m, c, output_size[0], output_size[1]), dtype=torch.float32, device=boxes.device)
+        if m:
+            lv = _level_table(feats, scales)
+            with torch.cuda.device(boxes.device):
+                N.call("det_roi_align_levels", ctypes.cast(lv, ctypes.c_void_p), len(feats), n, c, N.ptr(boxes),
+                       N.ptr(batch_index), N.ptr(level), m, int(output_size[0]), int(output_size[1]), int(sampling_ratio),
+                       int(bool(aligned)), N.ptr(out), N.stream())
+        ctx.save_for_backward(boxes, batch_index, level if level is not None else torch.empty(0, device=boxes.device))
+        ctx.meta = (scales, output_size, sampling_ratio, aligned, [tuple(f.shape) for f in feats], level is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        boxes, batch_index, level = ctx.saved_tensors
+        scales, output_size, sampling_ratio, aligned, shapes, has_level = ctx.meta
+        grads = [torch.zeros(sh, dtype=torch.float32, device=boxes.device) for sh in shapes]
+        m = boxes.shape[0]
+        if m:
+            go = grad_out.contiguous().float()
+            lv = _level_table(grads, scales)
+            with torch.cuda.device(boxes.device):
+                N.call("det_roi_align_levels_backward", ctypes.cast(lv, ctypes.c_void_p), len(grads), shapes[0][0],
+                       shapes[0][1], N.ptr(boxes), N.ptr(batch_index), N.ptr(level if has_level else None), m,
+                       int(output_size[0]), int(output_size[1]), int(sampling_ratio), int(bool(aligned)), N.ptr(go),
+                       N.stream())
+        return (None, None, None, None, None, None, None) + tuple(grads)
+
+
 def _roi_align_levels(features: List[torch.Tensor], scales: Sequence[float], boxes: torch.Tensor,
                       batch_index: torch.Tensor, level, output_size: Tuple[int, int], sampling_ratio: int,
                       aligned: bool) -> torch.Tensor:
     N.require_cuda(boxes, *features)
-    feats = [N.f32c(f) for f in features]
+    feats = [f.to(torch.float32).contiguous() for f in features]  # keeps the autograd graph of the feature maps
     n, c = feats[0].shape[0], feats[0].shape[1]
     for f in feats:
         assert f.dim() == 4 and f.shape[0] == n and f.shape[1] == c, "feature maps must share batch and channels"
     b = N.f32c(boxes)
     bi = batch_index.to(torch.int32).contiguous()
-    m = b.shape[0]
-    out = torch.empty((m, c, output_size[0], output_size[1]), dtype=torch.float32, device=b.device)
-    if m == 0:
-        return out
-    lv = (N.FeatureLevel * len(feats))()
-    for i, (f, s) in enumerate(zip(feats, scales)):
-        lv[i].data, lv[i].h, lv[i].w, lv[i].spatial_scale, lv[i].reserved = f.data_ptr(), f.shape[2], f.shape[3], float(s), 0
-    with torch.cuda.device(b.device):
-        N.call("det_roi_align_levels", ctypes.cast(lv, ctypes.c_void_p), len(feats), n, c, N.ptr(b), N.ptr(bi),
-               N.ptr(level), m, int(output_size[0]), int(output_size[1]), int(sampling_ratio), int(bool(aligned)),
-               N.ptr(out), N.stream())
-    return out
+    return _RoiAlignLevels.apply(b, bi, level, tuple(float(s) for s in scales), tuple(output_size), int(sampling_ratio),
+                                 bool(aligned), *feats)
 
 
 class ROIAlign:

@@ -98,3 +98,26 @@ def test_roi_align_single_level_and_edges(det):
     assert empty.shape == (0, 8, 7, 7)
     with pytest.raises(ValueError):
         det.ROIPooler([0.25], 0, 7, "Bilinear")
+
+
+@pytest.mark.parametrize("ptype,sampling_ratio", [("ROIAlignV2", 0), ("ROIAlign", 2)])
+def test_roi_pooler_backward_matches_torchvision_cpu(det, ptype, sampling_ratio):
+    """Gradients w.r.t. every pyramid level against autograd through torchvision's CPU roi_align (atomics: 1e-5)."""
+    g = gen(21)
+    n_img, C = 2, 10
+    strides = [4, 8, 16, 32]
+    feats = [torch.randn(n_img, C, 224 // s, 224 // s, generator=g) for s in strides]
+    scales = [1.0 / s for s in strides]
+    box_lists = _boxes(n_img, 40, g, frame=224.0)
+    weight = torch.randn(sum(b.shape[0] for b in box_lists), C, 7, 7, generator=g)
+    cpu_feats = [f.clone().requires_grad_(True) for f in feats]
+    want = ref_pooler(cpu_feats, scales, box_lists, (7, 7), sampling_ratio, ptype == "ROIAlignV2", 2, 5)
+    (want * weight).sum().backward()
+    gpu_feats = [f.cuda().requires_grad_(True) for f in feats]
+    pooler = det.ROIPooler(scales, sampling_ratio, 7, ptype)
+    got = pooler(gpu_feats, [det.Boxes(b.cuda()) for b in box_lists])
+    (got * weight.cuda()).sum().backward()
+    torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+    for gf, cf in zip(gpu_feats, cpu_feats):
+        assert gf.grad is not None
+        torch.testing.assert_close(gf.grad.cpu(), cf.grad, rtol=1e-4, atol=1e-5)
