@@ -227,6 +227,32 @@ def time_region(fn, iters, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+def time_graph(fns, iters, warm=2):
+    """ms per call of the callables `fns` (one step each, e.g. one per input set of a pool) replayed from ONE CUDA graph:
+    launch overhead of the Python/ctypes layer is outside the timed region, the kernels and their order are not."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # lazy initialisation (function attributes, allocations) before the capture
+        for f in fns:
+            f()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for f in fns:
+            f()
+    for _ in range(warm):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (iters * len(fns))
+
+
 def synth_gt(n, seed, dev):
     g = torch.Generator().manual_seed(seed)
     counts = torch.randint(1, 17, (n,), generator=g)
@@ -375,6 +401,31 @@ def extras_dense(det, dev, peak, quick):
                                               "algorithmic_bytes": nms_bytes, "achieved_gbs": nms_bytes / ms_n / 1e6,
                                               "note": "all 25200 boxes of every image, 80 categories, top-1000 kept; "
                                                       "sort + greedy sweep is latency/FP32-ALU-bound, not HBM-bound"}})
+        # the detector's inference path (configs[3]): decode -> score threshold -> per-class NMS -> top 300, fused
+        # (det_dense_detect: streaming select kernel + one-CTA-per-image NMS kernel; no dense output)
+        thr, max_det, cap = 0.1, 300, 2048
+        res = {}
+        for gate in (False, True):
+            ws = torch.empty((det._native.fn("det_dense_detect_workspace_bytes")(n, cap),), dtype=torch.uint8, device=dev)
+            r = dh.detect_thresholded(heads[0], thr, 0.5, max_det=max_det, cand_cap=cap, gate=gate, check=True, workspace=ws)
+            fns = [(lambda hs=hs_: dh.detect_thresholded(hs, thr, 0.5, max_det=max_det, cand_cap=cap, gate=gate,
+                                                         check=False, out=r, workspace=ws)) for hs_ in heads]
+            ms = time_graph(fns, 3 if quick else 10)
+            res[gate] = (ms, float(r["count"].float().mean()))
+        k_mean = res[False][1]
+        det_bytes = n * (4 * R * (5 + C80) + (36 * k_mean + 4))
+        entry["detect_thresholded"] = {
+            "workload": f"decode + score>{thr} + per-class NMS (IoU 0.5) + top {max_det}, batch {n}: det_dense_detect "
+                        "(2 launches per batch)",
+            "kept_per_image": k_mean,
+            "ms_streaming": res[False][0], "images_per_s_streaming": n / res[False][0] * 1e3,
+            "roofline": {"bound": "hbm", "achieved": det_bytes / res[False][0] / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": det_bytes / res[False][0] / 1e6 / peak, "algorithmic_bytes": det_bytes,
+                         "formula": "N * (4*R*(5+C) read + (36*K + 4) written), R=25200, C=80, K = kept per image; "
+                                    "both kernels (select + NMS) inside the timed region, gate off (whole head streamed)"},
+            "ms_gated": res[True][0], "images_per_s_gated": n / res[True][0] * 1e3,
+            "gated_note": "objectness plane first; class/box planes of 4-position groups that cannot pass are never "
+                          "read (exact: score <= sigmoid(obj)); fewer bytes than the formula, so no roofline claim"}
         out[f"dense_head_25200x80_b{n}"] = entry
         del heads, outbuf
         torch.cuda.empty_cache()

@@ -153,6 +153,25 @@ typedef struct det_dense_level {
 DET_API int det_dense_decode(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
                      float* boxes_out, float* score_out, int64_t* class_out, int64_t out_img_stride, void* stream);
 
+/* Dense anchor head as a detector runs it (BASELINE configs[3]): decode -> score > score_thresh -> per-class NMS ->
+ * top max_det, two launches for the whole batch and no dense output.  Specification: oracle/ref_torch.py
+ * dense_select_nms over dense_decode (own), i.e. per image
+ *     cand = nonzero(score > score_thresh);  keep = batched_nms(boxes[cand], score[cand], class[cand], iou)[:max_det]
+ * with batched_nms = python/src/utils.py:96-119 (`mode` as in det_nms_batched).
+ *   det_idx (n,max_det) int64 = row of the detection in the (level,h,w,a) order of det_dense_decode,
+ *   det_boxes (n,max_det,4), det_scores (n,max_det), det_classes (n,max_det) int64, det_count (n) int32,
+ *   by descending score, ties by lower row.
+ *   cand_cap (<= 4096): capacity of the per-image candidate list.  An image with more candidates gets
+ *   det_count = -1 and *overflow_flag (device int32, may be NULL; written by the call) = 1 -- nothing is guessed.
+ *   gate != 0: read the objectness plane first and skip the class/box planes of positions that cannot pass
+ *   (exact: score <= sigmoid(objectness)); gate == 0 streams the whole head.
+ *   limits: every level h*w % 4 == 0 and 16-byte aligned heads (else DET_ERR_UNSUPPORTED). */
+DET_API int64_t det_dense_detect_workspace_bytes(int n, int64_t cand_cap);
+DET_API int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
+                     float score_thresh, double iou_threshold, int mode, int gate, int64_t cand_cap, int64_t max_det,
+                     int64_t* det_idx, float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
+                     int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (4a) IoU target assignment -- replaces pairwise_iou + Matcher.__call__ + set_low_quality_matches_ as driven
  *      by label_and_sample_anchors, python/src/models/rpn.py:161-168 / components/matcher.py:53-120, for the

@@ -15,11 +15,21 @@
 // instructions each and only two 87 KB stages fit, so it lost to plain loads and was removed.
 //
 // Specification: oracle/ref_torch.py dense_decode (own; SURVEY.md section 8 row a15 -- no reference implementation).
-#include "common.cuh"
+//
+// det_dense_detect (BASELINE configs[3] as a detector runs it: decode -> score threshold -> per-class NMS -> top
+// max_det) uses the same streaming kernel in SELECT mode: nothing dense is written, a position whose score passes the
+// threshold appends (box, score, class, row index) to its image's candidate list; `dense_detect_nms_kernel` (one CTA
+// per image, nms_small.cuh) then orders the list by row index (= the order torch.nonzero gives the oracle, which
+// decides ties), runs the exact greedy NMS and writes the detections.  GATED select reads the objectness plane first
+// and skips the other 84 planes of a thread's 4 positions when sigmoid(obj) <= thresh for all of them -- exact, since
+// score = sigmoid(obj) * sigmoid(best) <= sigmoid(obj) in fp32 (a factor <= 1 cannot round a product upwards).
+#include "nms_core.cuh"
+#include "nms_small.cuh"
 
 namespace det {
 
 constexpr int kMaxLevels = 8;
+constexpr int kModeDense = 0, kModeSelect = 1, kModeSelectGated = 2;
 
 struct DenseLevelDev {
     const float* head;
@@ -43,8 +53,17 @@ struct FlatArgs {
     float4* boxes_out;
     float* score_out;
     int64_t* class_out;
+    // SELECT modes: per-image candidate lists of capacity cand_cap (row index inside the image, box, score, class)
+    float score_thresh;
+    int cand_cap;
+    int32_t* cand_count;
+    float4* cand_box;
+    float* cand_score;
+    int32_t* cand_cls;
+    int32_t* cand_id;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const __grid_constant__ FlatArgs g) {
     const long long gt = (long long)blockIdx.x * kFlatThreads + threadIdx.x;
     if (gt >= g.thread_begin[g.num_levels]) return;
@@ -63,6 +82,14 @@ __global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const _
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int bidx[4] = {0, 0, 0, 0};
     const float4* pk = pl + (int64_t)5 * plane4;
+    if (MODE == kModeSelectGated) {
+        const float4 q = ld_stream(pl + (int64_t)4 * plane4);
+        const float thr = g.score_thresh;
+        // `!(x > thr)` also holds for NaN: a NaN objectness gives a NaN score, which is no candidate either
+        if (!(sigmoidf_dd(q.x) > thr) && !(sigmoidf_dd(q.y) > thr) && !(sigmoidf_dd(q.z) > thr) &&
+            !(sigmoidf_dd(q.w) > thr))
+            return;
+    }
     int k = 0;
     for (; k + 8 <= C; k += 8) {
         float4 q[8];
@@ -115,11 +142,106 @@ __global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const _
         const float tw = (t[2][v] > g.scale_clamp) ? g.scale_clamp : t[2][v];  // torch.clamp(max=): NaN stays NaN
         const float th = (t[3][v] > g.scale_clamp) ? g.scale_clamp : t[3][v];
         const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
-        const int64_t o = obase + (int64_t)pos * A + ai;
-        st_stream(g.boxes_out + o, make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh));
-        st_stream(g.score_out + o, sigmoidf_dd(t[4][v]) * (C > 0 ? sigmoidf_dd(best[v]) : 1.0f));
-        g.class_out[o] = (int64_t)(C > 0 ? bidx[v] : 0);
+        const float4 box = make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh);
+        const float score = sigmoidf_dd(t[4][v]) * (C > 0 ? sigmoidf_dd(best[v]) : 1.0f);
+        if (MODE == kModeDense) {
+            const int64_t o = obase + (int64_t)pos * A + ai;
+            st_stream(g.boxes_out + o, box);
+            st_stream(g.score_out + o, score);
+            g.class_out[o] = (int64_t)(C > 0 ? bidx[v] : 0);
+        } else if (score > g.score_thresh) {
+            const int slot = atomicAdd(g.cand_count + img, 1);  // ~2 % of the positions get here
+            if (slot < g.cand_cap) {
+                const int64_t o = (int64_t)img * g.cand_cap + slot;
+                g.cand_box[o] = box;
+                g.cand_score[o] = score;
+                g.cand_cls[o] = C > 0 ? bidx[v] : 0;
+                g.cand_id[o] = (int32_t)(L.out_offset + (int64_t)pos * A + ai);
+            }
+        }
     }
+}
+
+// ---- NMS over the candidate lists: one CTA per image ---------------------------------------------------------------
+constexpr int kDetectThreads = 256;
+
+template <int CAP>
+struct DetectSmem {
+    SmallSmem<CAP, kDetectThreads> nms;
+    uint16_t perm[CAP];  // i-th candidate in row-index order -> slot in the image's list
+};
+
+struct ListCandidates {
+    const float4* boxes;
+    const float* scores;
+    const int32_t* cls;
+    const uint16_t* perm;  // null: identity
+    __device__ __forceinline__ int slot(int i) const { return perm ? (int)perm[i] : i; }
+    __device__ __forceinline__ float4 box(int i) const { return boxes[slot(i)]; }
+    __device__ __forceinline__ float score(int i) const { return scores[slot(i)]; }
+    __device__ __forceinline__ int64_t cat(int i) const { return (int64_t)cls[slot(i)]; }
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(kDetectThreads)
+dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __restrict__ cand_box,
+                        const float* __restrict__ cand_score, const int32_t* __restrict__ cand_cls,
+                        const int32_t* __restrict__ cand_id, int cand_cap, float thr_f, int mode, int64_t max_det,
+                        int64_t* __restrict__ det_idx, float4* __restrict__ det_boxes, float* __restrict__ det_scores,
+                        int64_t* __restrict__ det_classes, int32_t* __restrict__ det_count,
+                        int32_t* __restrict__ overflow_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DetectSmem<CAP>& sm = *reinterpret_cast<DetectSmem<CAP>*>(smem_raw);
+    using KL = KeyLayout<kSmallIdxBits>;
+    constexpr int T = kDetectThreads;
+    const int img = blockIdx.x, tid = threadIdx.x;
+    DET_MARK(0);
+    const int cnt = cand_count[img];
+    if (cnt > cand_cap) {  // the list is incomplete: report, do not guess
+        if (tid == 0) {
+            det_count[img] = -1;
+            if (overflow_flag) atomicExch(overflow_flag, 1);
+        }
+        return;
+    }
+    const int64_t base = (int64_t)img * cand_cap;
+    // The list was filled in arrival order, the oracle's candidates come in row order (torch.nonzero).  The order
+    // only matters where two scores tie, so the first attempt uses the list as it is and looks for ties -- inside a
+    // category segment (small_nms_body flags them) and between neighbours of the final list; only then the slots are
+    // sorted by row index and the image is redone.
+    const int npad = next_pow2(max(cnt, 2));
+    const int cap_out = (int)min(max_det, (int64_t)CAP);
+    ListCandidates src{cand_box + base, cand_score + base, cand_cls + base, nullptr};
+    int kept;
+    for (bool presort = false;; presort = true) {
+        if (presort) {
+            for (int i = tid; i < npad; i += T)
+                sm.nms.keys[i] = (i < cnt) ? (((uint64_t)(uint32_t)cand_id[base + i] << kSmallIdxBits) | (uint64_t)i) : kSentinelKey;
+            __syncthreads();
+            cta_bitonic_sort<T>(sm.nms.keys, npad);
+            for (int i = tid; i < cnt; i += T) sm.perm[i] = (uint16_t)(sm.nms.keys[i] & ((1u << kSmallIdxBits) - 1u));
+            __syncthreads();
+            src.perm = sm.perm;
+        }
+        DET_MARK(1);
+        kept = small_nms_body<CAP, T>(sm.nms, src, cnt, thr_f, mode, cap_out);
+        if (presort) break;
+        int tie = sm.nms.tie;
+        for (int j = tid; j + 1 < kept; j += T)
+            tie |= ((sm.nms.keys[j] ^ sm.nms.keys[j + 1]) >> KL::kScoreShift) == 0 ? 1 : 0;
+        if (!__syncthreads_or(tie)) break;
+    }
+    const int nout = kept < 0 ? 0 : min(kept, cap_out);
+    for (int j = tid; j < nout; j += T) {
+        const int slot = src.slot((int)KL::idx(sm.nms.keys[j]));
+        const int64_t o = (int64_t)img * max_det + j;
+        det_idx[o] = (int64_t)cand_id[base + slot];
+        det_boxes[o] = cand_box[base + slot];
+        det_scores[o] = cand_score[base + slot];
+        det_classes[o] = (int64_t)cand_cls[base + slot];
+    }
+    if (tid == 0) det_count[img] = kept < 0 ? -1 : nout;
+    DET_MARK(14);
 }
 
 // ---- fallback for levels whose h*w is not a multiple of 4 (or an unaligned head): one thread per position, scalar loads
@@ -201,11 +323,47 @@ dense_decode_level_kernel(const float* __restrict__ head, int a, int c, int h, i
 
 using namespace det;
 
+struct SelectArgs {
+    int mode;  // kModeSelect / kModeSelectGated
+    float score_thresh;
+    int cand_cap;
+    int32_t* cand_count;
+    float4* cand_box;
+    float* cand_score;
+    int32_t* cand_cls;
+    int32_t* cand_id;
+};
+
+template <int CAP>
+static int launch_detect_nms(const SelectArgs& sel, int n, float thr_f, int mode, int64_t max_det, int64_t* det_idx,
+                             float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
+                             int32_t* overflow_flag, cudaStream_t st) {
+    const size_t smem = sizeof(DetectSmem<CAP>);
+    cudaError_t e = cudaFuncSetAttribute(dense_detect_nms_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dense_detect_nms_kernel)");
+    dense_detect_nms_kernel<CAP><<<n, kDetectThreads, smem, st>>>(
+        sel.cand_count, sel.cand_box, sel.cand_score, sel.cand_cls, sel.cand_id, sel.cand_cap, thr_f, mode, max_det,
+        det_idx, reinterpret_cast<float4*>(det_boxes), det_scores, det_classes, det_count, overflow_flag);
+    DET_LAUNCH_OK("dense_detect_nms_kernel");
+    return DET_OK;
+}
+
 extern "C" {
 
+#ifdef DET_DEBUG_PHASES
+__attribute__((visibility("default"))) int det_debug_read_phases_dense(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, det::g_phase_clock, sizeof(long long) * 32) == cudaSuccess ? 0 : -4;
+}
+#endif
+
 static int launch_flat(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
-                       float* boxes_out, float* score_out, int64_t* class_out, int64_t out_img_stride, cudaStream_t st) {
+                       float* boxes_out, float* score_out, int64_t* class_out, int64_t out_img_stride, cudaStream_t st,
+                       const SelectArgs* sel = nullptr) {
     FlatArgs f;
+    f.score_thresh = sel ? sel->score_thresh : 0.f; f.cand_cap = sel ? sel->cand_cap : 0;
+    f.cand_count = sel ? sel->cand_count : nullptr; f.cand_box = sel ? sel->cand_box : nullptr;
+    f.cand_score = sel ? sel->cand_score : nullptr; f.cand_cls = sel ? sel->cand_cls : nullptr;
+    f.cand_id = sel ? sel->cand_id : nullptr;
     f.num_levels = num_levels; f.n = n; f.a = a; f.c = c; f.scale_clamp = scale_clamp; f.out_img_stride = out_img_stride;
     f.boxes_out = reinterpret_cast<float4*>(boxes_out); f.score_out = score_out; f.class_out = class_out;
     long long tb = 0;
@@ -228,10 +386,14 @@ static int launch_flat(const det_dense_level_t* levels_host, int num_levels, int
     if (tb == 0) return DET_OK;
     const long long blocks = (tb + kFlatThreads - 1) / kFlatThreads;
     DET_CHECK_ARG(blocks < (1ll << 31), "too many positions");
-    dense_decode_flat_kernel<<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    if (!sel) dense_decode_flat_kernel<kModeDense><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    else if (sel->mode == kModeSelectGated) dense_decode_flat_kernel<kModeSelectGated><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    else dense_decode_flat_kernel<kModeSelect><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
     DET_LAUNCH_OK("dense_decode_flat_kernel");
     return DET_OK;
 }
+
+static inline int64_t align16_i64(int64_t v) { return (v + 15) & ~(int64_t)15; }
 
 static bool level_is_flat(const float* head, int64_t hw) { return hw % 4 == 0 && aligned16(head) && hw < (1ll << 30); }
 
@@ -285,6 +447,81 @@ int det_dense_decode(const det_dense_level_t* levels_host, int num_levels, int n
         if (rc != DET_OK) return rc;
     }
     return DET_OK;
+}
+
+int64_t det_dense_detect_workspace_bytes(int n, int64_t cand_cap) {
+    if (n <= 0 || cand_cap <= 0) return 256;
+    return align16_i64(4 * ((int64_t)n + 4)) + (int64_t)n * cand_cap * (16 + 4 + 4 + 4);
+}
+
+int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
+                     float score_thresh, double iou_threshold, int mode, int gate, int64_t cand_cap, int64_t max_det,
+                     int64_t* det_idx, float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
+                     int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream) {
+    DET_CHECK_ARG(num_levels >= 0 && n >= 0 && a >= 1 && c >= 0, "bad size");
+    DET_CHECK_ARG(mode >= DET_NMS_AUTO && mode <= DET_NMS_OFFSET_TRICK, "unknown mode");
+    DET_CHECK_ARG(cand_cap >= 1 && cand_cap <= 4096, "cand_cap must be in [1, 4096]");
+    DET_CHECK_ARG(max_det >= 1, "max_det must be positive");
+    if (n == 0) return DET_OK;
+    DET_CHECK_ARG(det_idx && det_boxes && det_scores && det_classes && det_count, "null output");
+    DET_CHECK_ARG(num_levels <= kMaxLevels, "too many levels");
+    DET_CHECK_ARG(num_levels == 0 || levels_host, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (!aligned16(det_boxes)) {
+        set_error("det_boxes must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    int64_t rows = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const det_dense_level_t& L = levels_host[l];
+        DET_CHECK_ARG(L.head && L.anchors_wh && L.h >= 0 && L.w >= 0 && L.out_offset >= 0, "bad level");
+        if (!level_is_flat(L.head, (int64_t)L.h * L.w)) {
+            set_error("det_dense_detect needs h*w %% 4 == 0 and 16-byte aligned heads (level %d: %d x %d)", l, L.h, L.w);
+            return DET_ERR_UNSUPPORTED;
+        }
+        rows = L.out_offset + (int64_t)L.h * L.w * a > rows ? L.out_offset + (int64_t)L.h * L.w * a : rows;
+    }
+    DET_CHECK_ARG(rows < (1ll << 31), "too many rows per image");
+    const int64_t need = det_dense_detect_workspace_bytes(n, cand_cap);
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %lld bytes", (long long)need);
+        return DET_ERR_WORKSPACE;
+    }
+    if (!aligned16(workspace)) {
+        set_error("workspace must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    SelectArgs sel;
+    sel.mode = gate ? kModeSelectGated : kModeSelect;
+    sel.score_thresh = score_thresh;
+    sel.cand_cap = (int)cand_cap;
+    sel.cand_count = reinterpret_cast<int32_t*>(w);
+    w += align16_i64(4 * ((int64_t)n + 4));
+    sel.cand_box = reinterpret_cast<float4*>(w);
+    w += (int64_t)n * cand_cap * 16;
+    sel.cand_score = reinterpret_cast<float*>(w);
+    w += (int64_t)n * cand_cap * 4;
+    sel.cand_cls = reinterpret_cast<int32_t*>(w);
+    w += (int64_t)n * cand_cap * 4;
+    sel.cand_id = reinterpret_cast<int32_t*>(w);
+    cudaError_t e = cudaMemsetAsync(sel.cand_count, 0, sizeof(int32_t) * (size_t)n, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    if (overflow_flag) {
+        e = cudaMemsetAsync(overflow_flag, 0, sizeof(int32_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    }
+    int rc = launch_flat(levels_host, num_levels, n, a, c, scale_clamp, nullptr, nullptr, nullptr, rows, st, &sel);
+    if (rc != DET_OK) return rc;
+    const float thr_f = float_threshold_below(iou_threshold);
+    if (cand_cap <= 1024)
+        return launch_detect_nms<1024>(sel, n, thr_f, mode, max_det, det_idx, det_boxes, det_scores, det_classes,
+                                       det_count, overflow_flag, st);
+    if (cand_cap <= 2048)
+        return launch_detect_nms<2048>(sel, n, thr_f, mode, max_det, det_idx, det_boxes, det_scores, det_classes,
+                                       det_count, overflow_flag, st);
+    return launch_detect_nms<4096>(sel, n, thr_f, mode, max_det, det_idx, det_boxes, det_scores, det_classes, det_count,
+                                   overflow_flag, st);
 }
 
 }  // extern "C"

@@ -43,7 +43,10 @@ struct SmallSmem {
     int nseg_small, nseg_large, nk_scratch, nkept, bad_cat;
     float span;
     int fast;
+    int tie;  // two candidates of one segment share their score: their order was decided by the candidate index
 };
+
+constexpr int kCrossMax = 256;  // offset trick: most boxes that may reach into a lower category's coordinate range
 
 // candidate source for boxes that live in HBM as (boxes, scores, categories) rows of one image
 struct GlobalCandidates {
@@ -72,6 +75,8 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
         sm.bad_cat = 0;
         sm.span = 0.f;
         sm.fast = 1;
+        sm.tie = 0;
+        sm.nk_scratch = 0;
     }
     __syncthreads();
     // ---- phase 0: coordinate statistics for the offset trick
@@ -80,10 +85,13 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
         int fin = 1, maxcat = 0;
         for (int i = tid; i < cnt; i += T) {
             const float4 b = src.box(i);
+            const int64_t c = src.cat(i);
+            sm.sbox[i] = b;  // raw copies for the cross-category check below (phase 3 overwrites them)
+            sm.seg_s[i] = (uint16_t)min(max(c, (int64_t)0), (int64_t)65535);
             mx = max_nan(mx, max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w)));
             mn = min_nan(mn, min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w)));
             fin &= (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
-            maxcat = max(maxcat, (int)src.cat(i));
+            maxcat = max(maxcat, (int)c);
         }
         for (int o = 16; o > 0; o >>= 1) {
             mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -109,11 +117,52 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
             const float span = gmx + 1.0f;  // max_coordinate + torch.tensor(1).to(boxes)
             sm.span = span;
             // categories can be swept independently iff shifted boxes of different categories cannot intersect:
-            // all coordinates finite and > -1, shifted coordinates finite, non-negative threshold
+            // all coordinates finite, shifted coordinates finite, non-negative threshold, and either every coordinate
+            // > -1 (then category c lives in [c*span - 1, (c+1)*span - 1)) or -- checked next, fast == 2 -- no actual
+            // pair of boxes of different categories with a positive intersection
             const float far = gmx + (float)gcat * span;
-            sm.fast = (gfin && gmn > -1.0f && thr_f >= 0.0f && isfinite(far)) ? 1 : 0;
+            const bool base = gfin && thr_f >= 0.0f && isfinite(far);
+            sm.fast = !base ? 0 : (gmn > -1.0f) ? 1 : (gmx > -1.0f && gcat < 65535) ? 2 : 0;
+            sm.red_max[0] = far;
         }
         __syncthreads();
+        if (sm.fast == 2) {
+            // A box Q of category q can reach a box P of a lower category only if BOTH its x1 and y1 lie below
+            // -1 (+ a margin of ~30 ulp of the largest shifted coordinate for the fp32 roundings of the shifts):
+            // otherwise fl(P.x2 + p*span) <= fl(Q.x1 + q*span) for every P (or the same in y).  Such boxes (top-left
+            // corner, partly outside the frame) are few: test them against every box of a lower category with the
+            // shifted coordinates exactly as phase 3 computes them.
+            const float span = sm.span, lim = -1.0f + sm.red_max[0] * 4e-6f;
+            for (int i = tid; i < cnt; i += T) {
+                const float4 b = sm.sbox[i];
+                if (sm.seg_s[i] >= 1 && b.x < lim && b.y < lim) {
+                    const int slot = atomicAdd(&sm.nk_scratch, 1);
+                    if (slot < kCrossMax) sm.klist[slot] = (uint16_t)i;
+                }
+            }
+            __syncthreads();
+            const int na = sm.nk_scratch;
+            int cross = (na > kCrossMax) ? 1 : 0;
+            if (!cross) {
+                for (int w = tid; w < na * cnt; w += T) {
+                    const int a = w / cnt, i = w - a * cnt;
+                    const int iq = (int)sm.klist[a];
+                    const int cq = (int)sm.seg_s[iq], cp = (int)sm.seg_s[i];
+                    if (cp >= cq) continue;
+                    const float oq = (float)cq * span, op = (float)cp * span;
+                    const float4 q = sm.sbox[iq], pb = sm.sbox[i];
+                    const float ww = fminf(q.z + oq, pb.z + op) - fmaxf(q.x + oq, pb.x + op);
+                    const float hh = fminf(q.w + oq, pb.w + op) - fmaxf(q.y + oq, pb.y + op);
+                    cross |= (ww > 0.0f && hh > 0.0f) ? 1 : 0;
+                }
+            }
+            cross = __syncthreads_or(cross);
+            if (tid == 0) {
+                sm.fast = cross ? 0 : 1;
+                sm.nk_scratch = 0;
+            }
+            __syncthreads();
+        }
     }
     DET_MARK(4);
     const float span = sm.span;
@@ -155,6 +204,7 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
             sm.rowmask[p] = 0ull;
             clean &= (b.x == b.x) && (b.y == b.y) && (b.z == b.z) && (b.w == b.w);
             head = (p == 0) || (KL::seg(sm.keys[p - 1]) != KL::seg(k));
+            if (!head && ((sm.keys[p - 1] ^ k) >> KL::kScoreShift) == 0) sm.tie = 1;
         }
         const unsigned hb = __ballot_sync(0xffffffffu, head);
         if (lane == 0) sm.warp_heads[wid] = __popc(hb);

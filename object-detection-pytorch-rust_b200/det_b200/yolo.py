@@ -311,6 +311,84 @@ class DenseAnchorHead:
                 off += sz
         return boxes, scores, classes
 
+    def _levels(self, heads: List[torch.Tensor]):
+        """(det_dense_level_t array, contiguous heads, n, A, R) for heads that share the anchor count."""
+        dev = heads[0].device
+        anchors = self._anchors_on(dev)
+        hcs = [N.f32c(h) for h in heads]
+        na = anchors[0].shape[0]
+        assert all(a.shape[0] == na for a in anchors), "levels must share the anchor count"
+        lv = (N.DenseLevel * len(hcs))()
+        off = 0
+        for i, (hc, a, s) in enumerate(zip(hcs, anchors, self.strides)):
+            assert hc.shape[1] == na * (5 + self.C), hc.shape
+            lv[i].head, lv[i].anchors_wh = hc.data_ptr(), a.data_ptr()
+            lv[i].h, lv[i].w, lv[i].stride, lv[i].reserved, lv[i].out_offset = hc.shape[2], hc.shape[3], s, 0, off
+            off += hc.shape[2] * hc.shape[3] * na
+        return lv, hcs, heads[0].shape[0], na, off
+
+    def fused_ok(self, heads: List[torch.Tensor]) -> bool:
+        """det_dense_detect's documented limits: equal anchor counts, every level h*w % 4 == 0."""
+        na = self.anchors[0].shape[0]
+        return all(a.shape[0] == na for a in self.anchors) and all((h.shape[2] * h.shape[3]) % 4 == 0 for h in heads)
+
+    def detect_thresholded(self, heads: List[torch.Tensor], score_thresh: float, iou_thresh: float = 0.5,
+                           max_det: int = 300, cand_cap: int = 1024, gate: bool = True, mode: int = MODE_AUTO,
+                           check: bool = True, out=None, workspace: Optional[torch.Tensor] = None):
+        """The detector's inference path: decode -> score > score_thresh -> per-class NMS -> top max_det
+        (oracle/ref_torch.py dense_select_nms over dense_decode).  Two launches for the batch (det_dense_detect);
+        nothing dense is written.  Returns a dict: idx (N,max_det) int64 rows in decode() order, boxes, scores,
+        classes int64, count (N) int32 (rows past count are undefined).
+
+        cand_cap (<= 4096) bounds the per-image candidate list.  With check=True (one 4-byte read-back) an image that
+        overflows it -- or a pyramid outside det_dense_detect's limits -- is redone exactly by the unfused GPU path
+        (decode + det_nms_batched); with check=False overflowing images carry count = -1 and `overflow` is set."""
+        N.require_cuda(*heads)
+        dev = heads[0].device
+        n = heads[0].shape[0]
+        max_det = int(max_det)
+        if not self.fused_ok(heads) or cand_cap > 4096:
+            return self._detect_thresholded_unfused(heads, score_thresh, iou_thresh, max_det, mode)
+        if out is None:
+            out = {"idx": torch.empty((n, max_det), dtype=torch.int64, device=dev),
+                   "boxes": torch.empty((n, max_det, 4), dtype=torch.float32, device=dev),
+                   "scores": torch.empty((n, max_det), dtype=torch.float32, device=dev),
+                   "classes": torch.empty((n, max_det), dtype=torch.int64, device=dev),
+                   "count": torch.empty((n,), dtype=torch.int32, device=dev),
+                   "overflow": torch.empty((1,), dtype=torch.int32, device=dev)}
+        if n == 0:
+            return out
+        lv, hcs, _, na, _ = self._levels(heads)
+        wsb = N.fn("det_dense_detect_workspace_bytes")(n, int(cand_cap))
+        if workspace is None or workspace.numel() < wsb:
+            workspace = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.call("det_dense_detect", ctypes.cast(lv, ctypes.c_void_p), len(hcs), n, na, self.C, self.scale_clamp,
+                   float(score_thresh), float(iou_thresh), int(mode), 1 if gate else 0, int(cand_cap), max_det,
+                   N.ptr(out["idx"]), N.ptr(out["boxes"]), N.ptr(out["scores"]), N.ptr(out["classes"]),
+                   N.ptr(out["count"]), N.ptr(out["overflow"]), N.ptr(workspace), wsb, N.stream())
+        if check and int(out["overflow"].item()) != 0:
+            return self._detect_thresholded_unfused(heads, score_thresh, iou_thresh, max_det, mode)
+        return out
+
+    def _detect_thresholded_unfused(self, heads, score_thresh, iou_thresh, max_det, mode):
+        """Same contract through decode() + det_nms_batched (any candidate count up to 131071 per image)."""
+        boxes, scores, classes = self.decode(heads)
+        n, R = scores.shape
+        mask = scores > score_thresh
+        counts = mask.sum(dim=1).to(torch.int32)
+        # stable partition: candidates first, in row order
+        order = torch.sort((~mask).to(torch.uint8), dim=1, stable=True).indices
+        m = max(int(counts.max().item()) if n else 0, 1)
+        sel = order[:, :m]
+        cb = torch.gather(boxes, 1, sel[..., None].expand(-1, -1, 4)).contiguous()
+        cs, cc = torch.gather(scores, 1, sel).contiguous(), torch.gather(classes, 1, sel).contiguous()
+        keep, cnt = nms_images(cb, cs, cc, counts, iou_thresh, max_det, mode)
+        kk = keep.clamp(0, m - 1)
+        return {"idx": torch.gather(sel, 1, kk), "boxes": torch.gather(cb, 1, kk[..., None].expand(-1, -1, 4)),
+                "scores": torch.gather(cs, 1, kk), "classes": torch.gather(cc, 1, kk), "count": cnt,
+                "overflow": torch.zeros((1,), dtype=torch.int32, device=scores.device)}
+
     def detect(self, heads: List[torch.Tensor], iou_thresh: float = 0.5, max_det: Optional[int] = None,
                mode: int = MODE_AUTO):
         """decode + per-class NMS over all R boxes of every image: (boxes, scores, classes, keep (N,max_det),

@@ -517,6 +517,19 @@ def dense_decode(head: torch.Tensor, num_anchors: int, num_classes: int, stride:
     return boxes, score.permute(0, 2, 3, 1).reshape(n, -1), cidx.permute(0, 2, 3, 1).reshape(n, -1)
 
 
+def dense_select_nms(boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Tensor, score_thresh: float,
+                     iou_thresh: float, max_det: Optional[int] = None):
+    """Inference selection of ONE image of a dense anchor head (own specification; the NMS is the reference's
+    batched_nms, python/src/utils.py:96-119): candidates = rows with score > score_thresh in row order,
+    keep = batched_nms(...)[:max_det].  Returns (rows int64, boxes, scores, classes) by descending score."""
+    cand = torch.nonzero(scores > score_thresh, as_tuple=True)[0]
+    cb, cs, cc = boxes[cand], scores[cand], classes[cand]
+    keep = batched_nms(cb, cs, cc, iou_thresh)
+    if max_det is not None:
+        keep = keep[:max_det]
+    return cand[keep], cb[keep], cs[keep], cc[keep]
+
+
 def yolo_grid_anchors(S: int, image_hw: Tuple[int, int], priors: torch.Tensor) -> torch.Tensor:
     """Prior boxes of the S*S*B predictors (cell-centred), order (row,col,b); used for IoU target assignment."""
     H, W = image_hw

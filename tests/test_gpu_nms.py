@@ -194,3 +194,45 @@ def test_nms_properties_at_100k_boxes(det, O):
     iou = det.pairwise_iou(det.Boxes(b[didx]), det.Boxes(kb))
     ok = (iou > 0.5) & (c[didx][:, None] == kcat[None, :]) & (ks[None, :] > s[didx][:, None])
     assert bool(ok.any(dim=1).all())
+
+
+# ---- offset trick with coordinates below -1: categories are swept independently only if no pair of boxes of different
+#      categories intersects after the shift (nms_small.cuh phase 0) ------------------------------------------------------
+@pytest.mark.parametrize("n,ncat,seed", [(300, 80, 0), (900, 20, 1), (1000, 80, 2), (64, 2, 3), (700, 3, 4)])
+def test_offset_trick_with_negative_coordinates(det, O, n, ncat, seed):
+    g = gen(100 + seed)
+    b = rand_boxes(n, 640.0, g, wh_frac=0.4) - 120.0  # a good share of the boxes starts left of / above the frame
+    s = torch.rand(n, generator=g)
+    c = torch.randint(0, ncat, (n,), generator=g)
+    for thr in (0.5, 0.05):
+        want = O.batched_nms(b, s, c, thr)
+        got = det.batched_nms(b.cuda(), s.cuda(), c.cuda(), thr).cpu()
+        assert torch.equal(got, want)
+
+
+def test_offset_trick_cross_category_suppression_is_reproduced(det, O):
+    """torchvision's trick lets a top-left box of category c+1 overlap a bottom-right box of category c: the shifted
+    boxes really intersect and the lower-scored one is suppressed ACROSS categories.  The library must do the same."""
+    g = gen(7)
+    b = rand_boxes(200, 400.0, g)
+    s = torch.rand(200, generator=g) * 0.5
+    c = torch.randint(0, 4, (200,), generator=g)
+    mx = 500.0
+    b[0] = torch.tensor([mx - 60, mx - 60, mx, mx]); c[0] = 0; s[0] = 0.9      # holds the global maximum coordinate
+    b[1] = torch.tensor([-55.0, -55.0, 8.0, 8.0]); c[1] = 1; s[1] = 0.8        # shifted by span = mx + 1 it meets box 0
+    want = O.batched_nms(b, s, c, 0.05)
+    assert 1 not in want.tolist() and 0 in want.tolist()  # suppressed across categories in the reference semantics
+    got = det.batched_nms(b.cuda(), s.cuda(), c.cuda(), 0.05).cpu()
+    assert torch.equal(got, want)
+    # the same boxes per category (forced branch) keep box 1
+    kk, kc = det.nms_images(b[None].cuda(), s[None].cuda(), c[None].cuda(), None, 0.05, None, 1)
+    assert 1 in kk[0, :int(kc)].tolist()
+
+
+def test_offset_trick_many_corner_boxes_take_the_exact_slow_path(det, O):
+    g = gen(8)
+    n = 600
+    b = rand_boxes(n, 300.0, g) - 200.0  # most boxes have x1, y1 < -1: more than kCrossMax candidates
+    s = torch.rand(n, generator=g)
+    c = torch.randint(0, 10, (n,), generator=g)
+    assert torch.equal(det.batched_nms(b.cuda(), s.cuda(), c.cuda(), 0.4).cpu(), O.batched_nms(b, s, c, 0.4))
