@@ -139,9 +139,11 @@ __device__ __forceinline__ int warp_sum(int v) {
 // Optional phase timeline (build with -DDET_DEBUG_PHASES): block 0 / thread 0 stamps clock64() at DET_MARK(i).
 #ifdef DET_DEBUG_PHASES
 static __device__ long long g_phase_clock[32];  // one copy per translation unit (no -rdc)
+static __device__ long long g_phase_block[64][16];  // the same stamps for the first 64 blocks (marks 0..15)
 #define DET_MARK(i)                                                     \
     do {                                                                \
         if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clock[i] = clock64(); \
+        if (blockIdx.x < 64 && threadIdx.x == 0) g_phase_block[blockIdx.x][(i) & 15] = clock64(); \
     } while (0)
 #else
 #define DET_MARK(i) do { } while (0)

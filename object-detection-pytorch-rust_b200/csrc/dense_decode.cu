@@ -63,10 +63,17 @@ struct FlatArgs {
     int32_t* cand_id;
 };
 
+constexpr int kCountStride = 32;  // one 128-byte line per image counter: same-line atomics serialise in L2
+
 template <int MODE>
 __global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const __grid_constant__ FlatArgs g) {
-    const long long gt = (long long)blockIdx.x * kFlatThreads + threadIdx.x;
-    if (gt >= g.thread_begin[g.num_levels]) return;
+    long long gt = (long long)blockIdx.x * kFlatThreads + threadIdx.x;
+    bool active = gt < g.thread_begin[g.num_levels];
+    if (MODE == kModeDense) {
+        if (!active) return;
+    } else if (!active) {
+        gt = 0;  // SELECT: every lane reaches the warp-collective append below
+    }
     int l = 0;
 #pragma unroll
     for (int q = 1; q < kMaxLevels; ++q)
@@ -79,96 +86,139 @@ __global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const _
     const int img = ia / A, ai = ia - img * A;
     const int plane4 = groups;  // float4 stride between planes
     const float4* pl = reinterpret_cast<const float4*>(L.head + (int64_t)ia * nch * L.hw) + grp;
-    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int bidx[4] = {0, 0, 0, 0};
     const float4* pk = pl + (int64_t)5 * plane4;
-    if (MODE == kModeSelectGated) {
+    if (MODE == kModeSelectGated && active) {
         const float4 q = ld_stream(pl + (int64_t)4 * plane4);
         const float thr = g.score_thresh;
         // `!(x > thr)` also holds for NaN: a NaN objectness gives a NaN score, which is no candidate either
         if (!(sigmoidf_dd(q.x) > thr) && !(sigmoidf_dd(q.y) > thr) && !(sigmoidf_dd(q.z) > thr) &&
             !(sigmoidf_dd(q.w) > thr))
-            return;
+            active = false;
     }
-    int k = 0;
-    for (; k + 8 <= C; k += 8) {
-        float4 q[8];
+    float4 box[4];
+    float score[4];
+    int bidx[4] = {0, 0, 0, 0};
+    if (active) {
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int k = 0;
+        for (; k + 8 <= C; k += 8) {
+            float4 q[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = ld_stream(pk + (int64_t)(k + i) * plane4);
+            for (int i = 0; i < 8; ++i) q[i] = ld_stream(pk + (int64_t)(k + i) * plane4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            bidx[0] = (q[i].x > best[0]) ? k + i : bidx[0]; best[0] = max_nan(best[0], q[i].x);
-            bidx[1] = (q[i].y > best[1]) ? k + i : bidx[1]; best[1] = max_nan(best[1], q[i].y);
-            bidx[2] = (q[i].z > best[2]) ? k + i : bidx[2]; best[2] = max_nan(best[2], q[i].z);
-            bidx[3] = (q[i].w > best[3]) ? k + i : bidx[3]; best[3] = max_nan(best[3], q[i].w);
+            for (int i = 0; i < 8; ++i) {
+                bidx[0] = (q[i].x > best[0]) ? k + i : bidx[0]; best[0] = max_nan(best[0], q[i].x);
+                bidx[1] = (q[i].y > best[1]) ? k + i : bidx[1]; best[1] = max_nan(best[1], q[i].y);
+                bidx[2] = (q[i].z > best[2]) ? k + i : bidx[2]; best[2] = max_nan(best[2], q[i].z);
+                bidx[3] = (q[i].w > best[3]) ? k + i : bidx[3]; best[3] = max_nan(best[3], q[i].w);
+            }
+        }
+        for (; k < C; ++k) {
+            const float4 q = ld_stream(pk + (int64_t)k * plane4);
+            bidx[0] = (q.x > best[0]) ? k : bidx[0]; best[0] = max_nan(best[0], q.x);
+            bidx[1] = (q.y > best[1]) ? k : bidx[1]; best[1] = max_nan(best[1], q.y);
+            bidx[2] = (q.z > best[2]) ? k : bidx[2]; best[2] = max_nan(best[2], q.z);
+            bidx[3] = (q.w > best[3]) ? k : bidx[3]; best[3] = max_nan(best[3], q.w);
+        }
+        // the running max is NaN-propagating and `q > max` is false once it is NaN: a NaN column is finished by an
+        // exact rescan (torch.max: the first NaN wins)
+        if (best[0] != best[0] || best[1] != best[1] || best[2] != best[2] || best[3] != best[3]) {
+            bool found[4] = {false, false, false, false};
+            for (int j = 0; j < C; ++j) {
+                const float4 q4 = pk[(int64_t)j * plane4];
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (q[v] != q[v] && !found[v]) {
+                        found[v] = true;
+                        bidx[v] = j;
+                    }
+            }
+        }
+        float t[5][4];  // box logits last: they would only occupy registers during the class loop
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 q = ld_stream(pl + (int64_t)j * plane4);
+            t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+        }
+        const float2 awh = L.anchors_wh[ai];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int pos = grp * 4 + v;
+            const int row = pos / L.w, colx = pos - row * L.w;
+            const float cx = (sigmoidf_dd(t[0][v]) + (float)colx) * L.stride;
+            const float cy = (sigmoidf_dd(t[1][v]) + (float)row) * L.stride;
+            const float tw = (t[2][v] > g.scale_clamp) ? g.scale_clamp : t[2][v];  // torch.clamp(max=): NaN stays NaN
+            const float th = (t[3][v] > g.scale_clamp) ? g.scale_clamp : t[3][v];
+            const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
+            box[v] = make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh);
+            score[v] = sigmoidf_dd(t[4][v]) * (C > 0 ? sigmoidf_dd(best[v]) : 1.0f);
         }
     }
-    for (; k < C; ++k) {
-        const float4 q = ld_stream(pk + (int64_t)k * plane4);
-        bidx[0] = (q.x > best[0]) ? k : bidx[0]; best[0] = max_nan(best[0], q.x);
-        bidx[1] = (q.y > best[1]) ? k : bidx[1]; best[1] = max_nan(best[1], q.y);
-        bidx[2] = (q.z > best[2]) ? k : bidx[2]; best[2] = max_nan(best[2], q.z);
-        bidx[3] = (q.w > best[3]) ? k : bidx[3]; best[3] = max_nan(best[3], q.w);
-    }
-    // the running max is NaN-propagating and `q > max` is false once it is NaN: a NaN column is finished by an exact
-    // rescan (torch.max: the first NaN wins)
-    if (best[0] != best[0] || best[1] != best[1] || best[2] != best[2] || best[3] != best[3]) {
-        bool found[4] = {false, false, false, false};
-        for (int j = 0; j < C; ++j) {
-            const float4 q4 = pk[(int64_t)j * plane4];
-            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    if (MODE == kModeDense) {
+        const int64_t obase = (int64_t)img * g.out_img_stride + L.out_offset;
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-                if (q[v] != q[v] && !found[v]) {
-                    found[v] = true;
-                    bidx[v] = j;
-                }
-        }
-    }
-    float t[5][4];  // box logits last: they would only occupy registers during the class loop
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const float4 q = ld_stream(pl + (int64_t)j * plane4);
-        t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
-    }
-    const float2 awh = L.anchors_wh[ai];
-    const int64_t obase = (int64_t)img * g.out_img_stride + L.out_offset;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const int pos = grp * 4 + v;
-        const int row = pos / L.w, colx = pos - row * L.w;
-        const float cx = (sigmoidf_dd(t[0][v]) + (float)colx) * L.stride;
-        const float cy = (sigmoidf_dd(t[1][v]) + (float)row) * L.stride;
-        const float tw = (t[2][v] > g.scale_clamp) ? g.scale_clamp : t[2][v];  // torch.clamp(max=): NaN stays NaN
-        const float th = (t[3][v] > g.scale_clamp) ? g.scale_clamp : t[3][v];
-        const float bw = expf(tw) * awh.x, bh = expf(th) * awh.y;
-        const float4 box = make_float4(cx - 0.5f * bw, cy - 0.5f * bh, cx + 0.5f * bw, cy + 0.5f * bh);
-        const float score = sigmoidf_dd(t[4][v]) * (C > 0 ? sigmoidf_dd(best[v]) : 1.0f);
-        if (MODE == kModeDense) {
-            const int64_t o = obase + (int64_t)pos * A + ai;
-            st_stream(g.boxes_out + o, box);
-            st_stream(g.score_out + o, score);
+        for (int v = 0; v < 4; ++v) {
+            const int64_t o = obase + (int64_t)(grp * 4 + v) * A + ai;
+            st_stream(g.boxes_out + o, box[v]);
+            st_stream(g.score_out + o, score[v]);
             g.class_out[o] = (int64_t)(C > 0 ? bidx[v] : 0);
-        } else if (score > g.score_thresh) {
-            const int slot = atomicAdd(g.cand_count + img, 1);  // ~2 % of the positions get here
+        }
+    } else {
+        // append the passing positions to the image's candidate list: one atomic per warp when the warp works on one
+        // image (almost always), slots dealt with a shuffle scan.  The list order is arbitrary; the NMS kernel
+        // restores row order where it matters (ties).
+        unsigned pass = 0;
+        if (active) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) pass |= (score[v] > g.score_thresh) ? (1u << v) : 0u;
+        }
+        const int my = __popc(pass);
+        const int lane = threadIdx.x & 31;
+        const int img0 = __shfl_sync(0xffffffffu, img, 0);
+        int slot = 0;
+        if (__all_sync(0xffffffffu, img == img0)) {
+            int incl = my;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += (lane >= o) ? up : 0;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(g.cand_count + (int64_t)img0 * kCountStride, total);
+                slot = __shfl_sync(0xffffffffu, base, 0) + incl - my;
+            }
+        } else if (my) {
+            slot = atomicAdd(g.cand_count + (int64_t)img * kCountStride, my);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (!((pass >> v) & 1u)) continue;
             if (slot < g.cand_cap) {
                 const int64_t o = (int64_t)img * g.cand_cap + slot;
-                g.cand_box[o] = box;
-                g.cand_score[o] = score;
+                g.cand_box[o] = box[v];
+                g.cand_score[o] = score[v];
                 g.cand_cls[o] = C > 0 ? bidx[v] : 0;
-                g.cand_id[o] = (int32_t)(L.out_offset + (int64_t)pos * A + ai);
+                g.cand_id[o] = (int32_t)(L.out_offset + (int64_t)(grp * 4 + v) * A + ai);
             }
+            ++slot;
         }
     }
 }
 
 // ---- NMS over the candidate lists: one CTA per image ---------------------------------------------------------------
-constexpr int kDetectThreads = 256;
-
-template <int CAP>
+// T = 256 threads (several CTAs per SM) for large batches; 512 when there are no more images than SMs, where the
+// latency of the single CTA that owns an image is all that counts.
+template <int CAP, int T>
 struct DetectSmem {
-    SmallSmem<CAP, kDetectThreads> nms;
-    uint16_t perm[CAP];  // i-th candidate in row-index order -> slot in the image's list
+    SmallSmem<CAP, T> nms;
+    uint16_t perm[CAP];  // i-th candidate handed to the NMS -> slot in the image's list
+    uint32_t hist[256];
+    FullStats full;
+    uint32_t sel_prefix;
+    int sel_want, sub_count;
 };
 
 struct ListCandidates {
@@ -182,8 +232,8 @@ struct ListCandidates {
     __device__ __forceinline__ int64_t cat(int i) const { return (int64_t)cls[slot(i)]; }
 };
 
-template <int CAP>
-__global__ void __launch_bounds__(kDetectThreads)
+template <int CAP, int T>
+__global__ void __launch_bounds__(T, 512 / T)
 dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __restrict__ cand_box,
                         const float* __restrict__ cand_score, const int32_t* __restrict__ cand_cls,
                         const int32_t* __restrict__ cand_id, int cand_cap, float thr_f, int mode, int64_t max_det,
@@ -191,12 +241,11 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
                         int64_t* __restrict__ det_classes, int32_t* __restrict__ det_count,
                         int32_t* __restrict__ overflow_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DetectSmem<CAP>& sm = *reinterpret_cast<DetectSmem<CAP>*>(smem_raw);
+    DetectSmem<CAP, T>& sm = *reinterpret_cast<DetectSmem<CAP, T>*>(smem_raw);
     using KL = KeyLayout<kSmallIdxBits>;
-    constexpr int T = kDetectThreads;
     const int img = blockIdx.x, tid = threadIdx.x;
     DET_MARK(0);
-    const int cnt = cand_count[img];
+    const int cnt = cand_count[(int64_t)img * kCountStride];
     if (cnt > cand_cap) {  // the list is incomplete: report, do not guess
         if (tid == 0) {
             det_count[img] = -1;
@@ -205,31 +254,154 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
         return;
     }
     const int64_t base = (int64_t)img * cand_cap;
-    // The list was filled in arrival order, the oracle's candidates come in row order (torch.nonzero).  The order
-    // only matters where two scores tie, so the first attempt uses the list as it is and looks for ties -- inside a
-    // category segment (small_nms_body flags them) and between neighbours of the final list; only then the slots are
-    // sorted by row index and the image is redone.
-    const int npad = next_pow2(max(cnt, 2));
     const int cap_out = (int)min(max_det, (int64_t)CAP);
+    const int lane = tid & 31, wid = tid >> 5;
     ListCandidates src{cand_box + base, cand_score + base, cand_cls + base, nullptr};
-    int kept;
-    for (bool presort = false;; presort = true) {
-        if (presort) {
-            for (int i = tid; i < npad; i += T)
-                sm.nms.keys[i] = (i < cnt) ? (((uint64_t)(uint32_t)cand_id[base + i] << kSmallIdxBits) | (uint64_t)i) : kSentinelKey;
+    int kept = 0;
+    // Tier cut: only the first max_det detections are wanted and a box can only be suppressed by a better-scored
+    // one, so the NMS first runs on the ~1.25 * max_det best candidates (every score above a 16-bit radix cut, ties
+    // with the cut included).  max_det survivors there are the answer; otherwise everything is swept.  The
+    // reference's branch rule and the offset trick's span are defined on ALL candidates: FullStats carries them.
+    const int want_sub = cap_out + (cap_out >> 2) + 32;
+    for (int tier = (cnt >= want_sub + (want_sub >> 1)) ? 0 : 1; tier < 2; ++tier) {
+        int m = cnt;
+        const FullStats* fs = nullptr;
+        if (tier == 0) {
+            float mx = -INFINITY, mn = INFINITY;
+            int fin = 1, maxcat = 0;
+            uint32_t* skey = reinterpret_cast<uint32_t*>(sm.nms.sarea);
+            for (int i = tid; i < cnt; i += T) {
+                const float4 b = cand_box[base + i];
+                mx = max_nan(mx, max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w)));
+                mn = min_nan(mn, min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w)));
+                fin &= (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
+                maxcat = max(maxcat, cand_cls[base + i]);
+                skey[i] = score_desc_key(cand_score[base + i]);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                fin &= __shfl_xor_sync(0xffffffffu, fin, o);
+                maxcat = max(maxcat, __shfl_xor_sync(0xffffffffu, maxcat, o));
+            }
+            if (lane == 0) {
+                sm.nms.red_max[wid] = mx;
+                sm.nms.red_min[wid] = mn;
+                sm.nms.red_flag[wid] = fin | (maxcat << 1);
+            }
+            if (tid == 0) {
+                sm.sel_prefix = 0u;
+                sm.sel_want = want_sub;
+                sm.sub_count = 0;
+            }
             __syncthreads();
-            cta_bitonic_sort<T>(sm.nms.keys, npad);
-            for (int i = tid; i < cnt; i += T) sm.perm[i] = (uint16_t)(sm.nms.keys[i] & ((1u << kSmallIdxBits) - 1u));
+            if (tid == 0) {
+                float gmx = sm.nms.red_max[0], gmn = sm.nms.red_min[0];
+                int gfin = sm.nms.red_flag[0] & 1, gcat = sm.nms.red_flag[0] >> 1;
+                for (int w = 1; w < T / 32; ++w) {
+                    gmx = max_nan(gmx, sm.nms.red_max[w]);
+                    gmn = min_nan(gmn, sm.nms.red_min[w]);
+                    gfin &= sm.nms.red_flag[w] & 1;
+                    gcat = max(gcat, sm.nms.red_flag[w] >> 1);
+                }
+                sm.full.count = cnt; sm.full.mx = gmx; sm.full.mn = gmn; sm.full.fin = gfin; sm.full.maxcat = gcat;
+            }
+            // radix select on the two upper bytes of the descending-score keys: the bin of the want_sub-th best
+            for (int shift = 24; shift >= 16; shift -= 8) {
+                for (int b = tid; b < 256; b += T) sm.hist[b] = 0u;
+                __syncthreads();
+                const uint32_t prefix = sm.sel_prefix, himask = (shift == 24) ? 0u : 0xff000000u;
+                for (int i = tid; i < cnt; i += T)
+                    if ((skey[i] & himask) == prefix) atomicAdd(&sm.hist[(skey[i] >> shift) & 255u], 1u);
+                __syncthreads();
+                if (wid == 0) {
+                    uint32_t c8[8], tot = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        c8[q] = sm.hist[lane * 8 + q];
+                        tot += c8[q];
+                    }
+                    uint32_t incl = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                        incl += (lane >= o) ? up : 0u;
+                    }
+                    const uint32_t want = (uint32_t)sm.sel_want, before = incl - tot;
+                    if (before < want && want <= incl) {  // exactly one lane (want <= number of matching keys)
+                        uint32_t run = before;
+                        int q = 0;
+                        for (; q < 7 && run + c8[q] < want; ++q) run += c8[q];
+                        sm.sel_prefix = prefix | ((uint32_t)(lane * 8 + q) << shift);
+                        sm.sel_want = (int)(want - run);
+                    }
+                }
+                __syncthreads();
+            }
+            const uint32_t cut = sm.sel_prefix | 0xffffu;  // every key of the chosen 16-bit bin and all better ones
+            for (int i0 = 0; i0 < cnt; i0 += T) {
+                const int i = i0 + tid;
+                const bool in = i < cnt && skey[i] <= cut;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                int pos = 0;
+                if (lane == 0 && bal) pos = atomicAdd(&sm.sub_count, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (in) sm.perm[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+            }
             __syncthreads();
+            m = sm.sub_count;
+            fs = &sm.full;
             src.perm = sm.perm;
+        } else {
+            src.perm = nullptr;
         }
-        DET_MARK(1);
-        kept = small_nms_body<CAP, T>(sm.nms, src, cnt, thr_f, mode, cap_out);
-        if (presort) break;
-        int tie = sm.nms.tie;
-        for (int j = tid; j + 1 < kept; j += T)
-            tie |= ((sm.nms.keys[j] ^ sm.nms.keys[j + 1]) >> KL::kScoreShift) == 0 ? 1 : 0;
-        if (!__syncthreads_or(tie)) break;
+        // The list was filled in arrival order, the oracle's candidates come in row order (torch.nonzero).  The order
+        // only matters where two scores tie, so the first attempt uses the list as it is and looks for ties: inside a
+        // category segment (small_nms_body flags them) they may have changed the outcome and the image is redone with
+        // the slots in row order (rare); ties of different segments only meet in the final list, where each run of
+        // equal scores is put into row order by the thread that owns its first entry.
+        const int npad = next_pow2(max(m, 2));
+        for (bool presort = false;; presort = true) {
+            if (presort) {
+                for (int i = tid; i < npad; i += T) {
+                    const int slot = (i < m) ? src.slot(i) : 0;
+                    sm.nms.keys[i] = (i < m) ? (((uint64_t)(uint32_t)cand_id[base + slot] << kSmallIdxBits) | (uint64_t)slot)
+                                             : kSentinelKey;
+                }
+                __syncthreads();
+                cta_bitonic_sort<T>(sm.nms.keys, npad);
+                for (int i = tid; i < m; i += T) sm.perm[i] = (uint16_t)(sm.nms.keys[i] & ((1u << kSmallIdxBits) - 1u));
+                __syncthreads();
+                src.perm = sm.perm;
+            }
+            DET_MARK(1);
+            kept = small_nms_body<CAP, T>(sm.nms, src, m, thr_f, mode, cap_out, fs);
+            if (presort) break;
+            int redo = sm.nms.tie;
+            if (!redo) {
+                for (int j = tid; j + 1 < kept; j += T) {
+                    const uint64_t sc = sm.nms.keys[j] >> KL::kScoreShift;
+                    if ((sm.nms.keys[j + 1] >> KL::kScoreShift) != sc) continue;
+                    if (j > 0 && (sm.nms.keys[j - 1] >> KL::kScoreShift) == sc) continue;  // not the head of the run
+                    int len = 2;
+                    while (j + len < kept && (sm.nms.keys[j + len] >> KL::kScoreShift) == sc) ++len;
+                    if (len > 16) {
+                        redo = 1;
+                        break;
+                    }
+                    for (int a = 0; a + 1 < len; ++a)  // selection sort by row index; only this thread writes the run
+                        for (int b = a + 1; b < len; ++b) {
+                            const uint64_t ka = sm.nms.keys[j + a], kb = sm.nms.keys[j + b];
+                            if (cand_id[base + src.slot((int)KL::idx(kb))] < cand_id[base + src.slot((int)KL::idx(ka))]) {
+                                sm.nms.keys[j + a] = kb;
+                                sm.nms.keys[j + b] = ka;
+                            }
+                        }
+                }
+            }
+            if (!__syncthreads_or(redo)) break;
+        }
+        if (kept < 0 || kept >= cap_out) break;  // bad category, or the tier already holds max_det survivors
     }
     const int nout = kept < 0 ? 0 : min(kept, cap_out);
     for (int j = tid; j < nout; j += T) {
@@ -334,18 +506,29 @@ struct SelectArgs {
     int32_t* cand_id;
 };
 
-template <int CAP>
-static int launch_detect_nms(const SelectArgs& sel, int n, float thr_f, int mode, int64_t max_det, int64_t* det_idx,
-                             float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
-                             int32_t* overflow_flag, cudaStream_t st) {
-    const size_t smem = sizeof(DetectSmem<CAP>);
-    cudaError_t e = cudaFuncSetAttribute(dense_detect_nms_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int CAP, int T>
+static int launch_detect_nms_t(const SelectArgs& sel, int n, float thr_f, int mode, int64_t max_det, int64_t* det_idx,
+                               float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
+                               int32_t* overflow_flag, cudaStream_t st) {
+    const size_t smem = sizeof(DetectSmem<CAP, T>);
+    cudaError_t e = cudaFuncSetAttribute(dense_detect_nms_kernel<CAP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dense_detect_nms_kernel)");
-    dense_detect_nms_kernel<CAP><<<n, kDetectThreads, smem, st>>>(
+    dense_detect_nms_kernel<CAP, T><<<n, T, smem, st>>>(
         sel.cand_count, sel.cand_box, sel.cand_score, sel.cand_cls, sel.cand_id, sel.cand_cap, thr_f, mode, max_det,
         det_idx, reinterpret_cast<float4*>(det_boxes), det_scores, det_classes, det_count, overflow_flag);
     DET_LAUNCH_OK("dense_detect_nms_kernel");
     return DET_OK;
+}
+
+template <int CAP>
+static int launch_detect_nms(const SelectArgs& sel, int n, float thr_f, int mode, int64_t max_det, int64_t* det_idx,
+                             float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
+                             int32_t* overflow_flag, cudaStream_t st) {
+    if (n <= sm_count())
+        return launch_detect_nms_t<CAP, 512>(sel, n, thr_f, mode, max_det, det_idx, det_boxes, det_scores, det_classes,
+                                             det_count, overflow_flag, st);
+    return launch_detect_nms_t<CAP, 256>(sel, n, thr_f, mode, max_det, det_idx, det_boxes, det_scores, det_classes,
+                                         det_count, overflow_flag, st);
 }
 
 extern "C" {
@@ -353,6 +536,9 @@ extern "C" {
 #ifdef DET_DEBUG_PHASES
 __attribute__((visibility("default"))) int det_debug_read_phases_dense(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, det::g_phase_clock, sizeof(long long) * 32) == cudaSuccess ? 0 : -4;
+}
+__attribute__((visibility("default"))) int det_debug_read_phase_blocks_dense(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, det::g_phase_block, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -4;
 }
 #endif
 
@@ -393,7 +579,6 @@ static int launch_flat(const det_dense_level_t* levels_host, int num_levels, int
     return DET_OK;
 }
 
-static inline int64_t align16_i64(int64_t v) { return (v + 15) & ~(int64_t)15; }
 
 static bool level_is_flat(const float* head, int64_t hw) { return hw % 4 == 0 && aligned16(head) && hw < (1ll << 30); }
 
@@ -451,7 +636,7 @@ int det_dense_decode(const det_dense_level_t* levels_host, int num_levels, int n
 
 int64_t det_dense_detect_workspace_bytes(int n, int64_t cand_cap) {
     if (n <= 0 || cand_cap <= 0) return 256;
-    return align16_i64(4 * ((int64_t)n + 4)) + (int64_t)n * cand_cap * (16 + 4 + 4 + 4);
+    return (int64_t)n * kCountStride * 4 + (int64_t)n * cand_cap * (16 + 4 + 4 + 4);
 }
 
 int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
@@ -497,7 +682,7 @@ int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n
     sel.score_thresh = score_thresh;
     sel.cand_cap = (int)cand_cap;
     sel.cand_count = reinterpret_cast<int32_t*>(w);
-    w += align16_i64(4 * ((int64_t)n + 4));
+    w += (int64_t)n * kCountStride * 4;
     sel.cand_box = reinterpret_cast<float4*>(w);
     w += (int64_t)n * cand_cap * 16;
     sel.cand_score = reinterpret_cast<float*>(w);
@@ -505,7 +690,7 @@ int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n
     sel.cand_cls = reinterpret_cast<int32_t*>(w);
     w += (int64_t)n * cand_cap * 4;
     sel.cand_id = reinterpret_cast<int32_t*>(w);
-    cudaError_t e = cudaMemsetAsync(sel.cand_count, 0, sizeof(int32_t) * (size_t)n, st);
+    cudaError_t e = cudaMemsetAsync(sel.cand_count, 0, sizeof(int32_t) * (size_t)n * kCountStride, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     if (overflow_flag) {
         e = cudaMemsetAsync(overflow_flag, 0, sizeof(int32_t), st);

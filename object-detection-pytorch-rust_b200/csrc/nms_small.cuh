@@ -44,9 +44,14 @@ struct SmallSmem {
     float span;
     int fast;
     int tie;  // two candidates of one segment share their score: their order was decided by the candidate index
+    // offset trick with coordinates below -1: categories joined by an intersecting pair of shifted boxes
+    int nnode, nedge;
+    uint16_t node_cat[64], node_lab[64];
+    uint32_t edges[64];  // (lower category << 16) | higher category
 };
 
 constexpr int kCrossMax = 256;  // offset trick: most boxes that may reach into a lower category's coordinate range
+constexpr int kCrossNodes = 64;
 
 // candidate source for boxes that live in HBM as (boxes, scores, categories) rows of one image
 struct GlobalCandidates {
@@ -58,16 +63,25 @@ struct GlobalCandidates {
     __device__ __forceinline__ int64_t cat(int i) const { return cats ? cats[i] : 0; }
 };
 
+// Statistics of a superset of the candidates handed to small_nms_body (the caller sweeps only a best-scored subset):
+// the reference's branch rule (count <= 1000 -> offset trick) and the trick's span are defined on the full set.
+struct FullStats {
+    int count;
+    float mx, mn;
+    int fin, maxcat;
+};
+
 // Greedy category-partitioned NMS of `cnt` (<= CAP) candidates by one CTA of T threads.
 // Returns (block-uniform) the number of kept candidates, or -1 if a category is outside [0, 32767).
 // On return sm.keys[0 .. kept) hold (descending-score bits | candidate index) in output order.
 template <int CAP, int T, typename Src>
-__device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, float thr_f, int mode, int max_out) {
+__device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, float thr_f, int mode, int max_out,
+                              const FullStats* full = nullptr) {
     using KL = KeyLayout<kSmallIdxBits>;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int W = T / 32;
     // reference CPU rule: boxes.numel() <= 4000 -> coordinate-offset trick (torchvision/ops/boxes.py batched_nms)
-    const bool trick = (mode == DET_NMS_AUTO) ? (cnt <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
+    const bool trick = (mode == DET_NMS_AUTO) ? ((full ? full->count : cnt) <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
     if (tid == 0) {
         sm.nseg_small = 0;
         sm.nseg_large = 0;
@@ -77,7 +91,10 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
         sm.fast = 1;
         sm.tie = 0;
         sm.nk_scratch = 0;
+        sm.nnode = 0;
+        sm.nedge = 0;
     }
+    if (tid < kCrossNodes) sm.edges[tid] = 0u;  // 0 is no edge (lower < higher): a reserved, unwritten slot matches nothing
     __syncthreads();
     // ---- phase 0: coordinate statistics for the offset trick
     if (trick) {
@@ -114,6 +131,9 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
                 gfin &= sm.red_flag[w] & 1;
                 gcat = max(gcat, sm.red_flag[w] >> 1);
             }
+            if (full) {
+                gmx = full->mx; gmn = full->mn; gfin = full->fin; gcat = full->maxcat;
+            }
             const float span = gmx + 1.0f;  // max_coordinate + torch.tensor(1).to(boxes)
             sm.span = span;
             // categories can be swept independently iff shifted boxes of different categories cannot intersect:
@@ -131,7 +151,9 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
             // -1 (+ a margin of ~30 ulp of the largest shifted coordinate for the fp32 roundings of the shifts):
             // otherwise fl(P.x2 + p*span) <= fl(Q.x1 + q*span) for every P (or the same in y).  Such boxes (top-left
             // corner, partly outside the frame) are few: test them against every box of a lower category with the
-            // shifted coordinates exactly as phase 3 computes them.
+            // shifted coordinates exactly as phase 3 computes them.  Every intersecting pair joins its two categories;
+            // the connected components of that graph are closed under suppression (boxes of different components
+            // have IoU 0), so each component is swept as ONE segment and the result equals the sweep over everything.
             const float span = sm.span, lim = -1.0f + sm.red_max[0] * 4e-6f;
             for (int i = tid; i < cnt; i += T) {
                 const float4 b = sm.sbox[i];
@@ -142,8 +164,7 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
             }
             __syncthreads();
             const int na = sm.nk_scratch;
-            int cross = (na > kCrossMax) ? 1 : 0;
-            if (!cross) {
+            if (na <= kCrossMax) {
                 for (int w = tid; w < na * cnt; w += T) {
                     const int a = w / cnt, i = w - a * cnt;
                     const int iq = (int)sm.klist[a];
@@ -153,12 +174,45 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
                     const float4 q = sm.sbox[iq], pb = sm.sbox[i];
                     const float ww = fminf(q.z + oq, pb.z + op) - fmaxf(q.x + oq, pb.x + op);
                     const float hh = fminf(q.w + oq, pb.w + op) - fmaxf(q.y + oq, pb.y + op);
-                    cross |= (ww > 0.0f && hh > 0.0f) ? 1 : 0;
+                    if (ww > 0.0f && hh > 0.0f) {
+                        const uint32_t e = ((uint32_t)cp << 16) | (uint32_t)cq;
+                        bool seen = false;  // the same pair of categories is usually hit many times
+                        const int ne = min(*(volatile int*)&sm.nedge, kCrossNodes);
+                        for (int k = 0; k < ne; ++k) seen |= (((volatile uint32_t*)sm.edges)[k] == e);
+                        if (!seen) {
+                            const int slot = atomicAdd(&sm.nedge, 1);
+                            if (slot < kCrossNodes) sm.edges[slot] = e;
+                        }
+                    }
                 }
             }
-            cross = __syncthreads_or(cross);
+            __syncthreads();
             if (tid == 0) {
-                sm.fast = cross ? 0 : 1;
+                int ok = (na <= kCrossMax && sm.nedge <= kCrossNodes) ? 1 : 0;
+                int nn = 0;
+                for (int k = 0; ok && k < sm.nedge; ++k) {  // label propagation over a handful of edges
+                    const int u = (int)(sm.edges[k] >> 16), v = (int)(sm.edges[k] & 0xffffu);
+                    int lu = -1, lv = -1;
+                    for (int q = 0; q < nn; ++q) {
+                        if (sm.node_cat[q] == u) lu = sm.node_lab[q];
+                        if (sm.node_cat[q] == v) lv = sm.node_lab[q];
+                    }
+                    if (lu < 0) {
+                        if (nn == kCrossNodes) { ok = 0; break; }
+                        sm.node_cat[nn] = (uint16_t)u; sm.node_lab[nn] = (uint16_t)u; lu = u; ++nn;
+                    }
+                    if (lv < 0) {
+                        if (nn == kCrossNodes) { ok = 0; break; }
+                        sm.node_cat[nn] = (uint16_t)v; sm.node_lab[nn] = (uint16_t)v; lv = v; ++nn;
+                    }
+                    if (lu != lv) {
+                        const int lo = min(lu, lv), hi = max(lu, lv);
+                        for (int q = 0; q < nn; ++q)
+                            if (sm.node_lab[q] == hi) sm.node_lab[q] = (uint16_t)lo;
+                    }
+                }
+                sm.nnode = ok ? nn : 0;
+                sm.fast = ok;
                 sm.nk_scratch = 0;
             }
             __syncthreads();
@@ -167,6 +221,7 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
     DET_MARK(4);
     const float span = sm.span;
     const bool by_cat = !trick || sm.fast;
+    const int nnode = (trick && sm.fast) ? sm.nnode : 0;
     // ---- phase 1+2: keys, sort
     const int npad = next_pow2(max(cnt, 2));
     for (int i = tid; i < npad; i += T) {
@@ -174,7 +229,10 @@ __device__ int small_nms_body(SmallSmem<CAP, T>& sm, const Src& src, int cnt, fl
         if (i < cnt) {
             const int64_t c = src.cat(i);
             if (c < 0 || c >= (1 << kSegBits) - 1) sm.bad_cat = 1;
-            k = KL::make(by_cat ? (uint32_t)(c & ((1 << kSegBits) - 1)) : 0u, src.score(i), (uint32_t)i);
+            uint32_t seg = by_cat ? (uint32_t)(c & ((1 << kSegBits) - 1)) : 0u;
+            for (int q = 0; q < nnode; ++q)  // categories joined by an intersecting pair share a segment
+                if ((uint32_t)sm.node_cat[q] == seg) seg = (uint32_t)sm.node_lab[q];
+            k = KL::make(seg, src.score(i), (uint32_t)i);
         }
         sm.keys[i] = k;
     }

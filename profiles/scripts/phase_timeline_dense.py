@@ -27,6 +27,9 @@ for thr, cap in ((0.1, 2048), (0.25, 1024)):
     for _ in range(3):
         r = dh.detect_thresholded(hs, thr, 0.5, max_det=300, cand_cap=cap, check=False)
     torch.cuda.synchronize()
+    cnts = (torch.cat([x.flatten(1) for x in dh.decode(hs)[1:2]], 1) > thr).sum(1).cpu()
+    r = dh.detect_thresholded(hs, thr, 0.5, max_det=300, cand_cap=cap, check=False)
+    torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 32)()
     assert N.lib().det_debug_read_phases_dense(buf) == 0
     print(f"thr {thr} cap {cap}: kept {float(r['count'].float().mean())}")
@@ -35,3 +38,15 @@ for thr, cap in ((0.1, 2048), (0.25, 1024)):
         if buf[i]:
             print(f"{names[i]:>22s}: +{buf[i] - prev:8d} cycles  (t={buf[i] - buf[0]})")
             prev = buf[i]
+    blk = (ctypes.c_longlong * (64 * 16))()
+    assert N.lib().det_debug_read_phase_blocks_dense(blk) == 0
+    tot = [(blk[b * 16 + 14] - blk[b * 16 + 0], b) for b in range(n)]
+    print("per-image CTA cycles:", sorted(t for t, _ in tot))
+    _, worst = max(tot)
+    print(f"slowest CTA {worst}: candidates {int(cnts[worst])}")
+    prev = blk[worst * 16]
+    for i in order:
+        v = blk[worst * 16 + i]
+        if v:
+            print(f"{names[i]:>22s}: +{v - prev:8d} cycles")
+            prev = v

@@ -62,6 +62,41 @@ def test_dense_detect_parity(det, O, gate, image, n, bias, thr, cap, max_det):
     check_against_oracle(dh, O, heads, r, thr, 0.5, max_det)
 
 
+@pytest.mark.parametrize("bias,thr,iou,max_det,cap", [
+    (0.0, 0.3, 0.5, 100, 4096),    # tier cut succeeds: the best ~160 candidates yield 100 survivors (per-category branch)
+    (0.0, 0.3, 0.01, 100, 4096),   # heavy suppression: the tier falls short and everything is swept
+    (-2.5, 0.2, 0.5, 100, 1024),   # <= 1000 candidates: offset-trick branch with the full set's span
+    (-2.5, 0.2, 0.02, 100, 1024),  # the same, tier falls short
+    (1.0, 0.3, 0.3, 50, 4096),
+    (0.0, 0.3, 0.5, 1, 4096),
+])
+def test_dense_detect_tier_cut(det, O, bias, thr, iou, max_det, cap):
+    """Only max_det detections are wanted: the kernel first sweeps the ~1.25 * max_det best candidates (exact)."""
+    C = 80
+    dh = det.DenseAnchorHead(STRIDES, WH, C)
+    heads = [h.cuda() for h in make_heads(4, 256, C, 77, bias)]
+    r = dh.detect_thresholded(heads, thr, iou, max_det=max_det, cand_cap=cap, check=False)
+    assert int(r["overflow"].item()) == 0
+    n_cand = (dh.decode(heads)[1] > thr).sum(1)
+    assert int(n_cand.min()) >= 3 * (max_det + max_det // 4 + 32) // 2 + 1, n_cand.tolist()  # the tier path runs
+    check_against_oracle(dh, O, heads, r, thr, iou, max_det)
+
+
+def test_dense_detect_tier_cut_with_quantised_scores(det, O):
+    """Scores on a coarse grid: many ties inside segments, across segments and at the tier's radix cut."""
+    C = 8
+    dh = det.DenseAnchorHead(STRIDES, WH, C)
+    heads = make_heads(3, 256, C, 31, 0.0)
+    for h in heads:
+        v = h.view(3, 3, 5 + C, h.shape[2], h.shape[3])
+        v[:, :, 4:] = (v[:, :, 4:] * 2).round() / 2  # objectness and class logits in steps of 0.5
+    hg = [h.cuda() for h in heads]
+    for max_det in (20, 150):
+        r = dh.detect_thresholded(hg, 0.3, 0.5, max_det=max_det, cand_cap=4096, check=False)
+        assert int(r["overflow"].item()) == 0
+        check_against_oracle(dh, O, hg, r, 0.3, 0.5, max_det)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_dense_detect_modes_and_few_classes(det, O, mode):
     C = 3
