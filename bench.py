@@ -399,8 +399,9 @@ def extras_dense(det, dev, peak, quick):
             entry.update({"ms_nms": ms_n, "images_per_s_decode_plus_nms": n / (ms_d + ms_n) * 1e3,
                           "nms_25200_boxes": {"ms_per_image": ms_n / n, "kept_per_image": k_tot / n,
                                               "algorithmic_bytes": nms_bytes, "achieved_gbs": nms_bytes / ms_n / 1e6,
-                                              "note": "all 25200 boxes of every image, 80 categories, top-1000 kept; "
-                                                      "sort + greedy sweep is latency/FP32-ALU-bound, not HBM-bound"}})
+                                              "note": "all 25200 boxes of every image handed to det_nms_batched, 80 "
+                                                      "categories, top-1000 kept: the top-k tier sweeps the ~1300 "
+                                                      "best-scored boxes first (exact); latency-bound, not HBM-bound"}})
         # the detector's inference path (configs[3]): decode -> score threshold -> per-class NMS -> top 300, fused
         # (det_dense_detect: streaming select kernel + one-CTA-per-image NMS kernel; no dense output)
         thr, max_det, cap = 0.1, 300, 2048

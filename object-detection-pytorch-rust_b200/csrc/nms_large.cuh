@@ -8,6 +8,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "nms_core.cuh"
+#include "nms_list.cuh"
 
 namespace det {
 
@@ -20,6 +21,8 @@ constexpr int kSegThreads = 256;   // candidates per chunk of the CTA sweep
 constexpr int kSegCtaThreads = 1024;  // threads of the CTA that runs it: 4 groups share the list tests and bit rows
 constexpr int kHugeSeg = 4096;     // longer segments are swept by the whole grid (cooperative kernel)
 constexpr int kHugeChunk = 512;    // positions resolved per step by the segment's leader CTA
+constexpr int kTierCap = 4096;     // top-k tier: capacity of an image's candidate list
+constexpr int kTierMaxWant = 3072; // ... and the largest tier size tried (1.25 * max_out + 32)
 
 struct LargeImg {
     int32_t cnt;
@@ -30,6 +33,8 @@ struct LargeImg {
     int32_t bad;
     int32_t nsurv;
     int32_t nonan;  // no box coordinate of the image is NaN: min/max in the predicate are single FMNMX instructions
+    int32_t skip;   // the top-k tier already produced this image's output: nothing to do, nothing to write
+    int32_t pad_[7];
 };
 
 struct LargeLayout {
@@ -37,6 +42,7 @@ struct LargeLayout {
     int64_t m_max, mp, segcap;
     int64_t off_info, off_ctr, off_keys_a, off_keys_b, off_sbox, off_sarea, off_state, off_klist, off_seg_small,
         off_seg_large, off_seg_huge, off_huge_nk, hugecap, total;
+    int64_t off_tier_count, off_tier_box, off_tier_score, off_tier_cls, off_tier_id, off_tier_full, off_tier_todo;
     LargeLayout(int n_, int64_t m_) : n(n_), m_max(m_) {
         mp = (m_max + kTile - 1) / kTile * kTile;
         segcap = mp < 32768 ? mp : 32768;
@@ -59,6 +65,14 @@ struct LargeLayout {
         hugecap = (int64_t)n * (mp / kHugeSeg + 1);
         off_seg_huge = take(16 * hugecap);
         off_huge_nk = take(8 * 3 * hugecap);
+        // top-k tier (max_out << boxes): candidate lists of the best-scored boxes of each image
+        off_tier_count = take((int64_t)n * kCountStride * 4);
+        off_tier_box = take((int64_t)16 * n * kTierCap);
+        off_tier_score = take((int64_t)4 * n * kTierCap);
+        off_tier_cls = take((int64_t)4 * n * kTierCap);
+        off_tier_id = take((int64_t)4 * n * kTierCap);
+        off_tier_full = take((int64_t)sizeof(FullStats) * n);
+        off_tier_todo = take((int64_t)4 * n);
         total = o;
     }
 };
@@ -73,6 +87,10 @@ struct LargeWs {
     int32_t* klist;
     int4 *seg_small, *seg_large, *seg_huge;
     int2* huge_nk;  // [3][#huge]: running kept count, then the kept range of the chunk resolved in even / odd steps
+    int32_t *tier_count, *tier_cls, *tier_id, *tier_todo;
+    float4* tier_box;
+    float* tier_score;
+    FullStats* tier_full;
     LargeWs(const LargeLayout& l, void* base) {
         char* b = static_cast<char*>(base);
         info = reinterpret_cast<LargeImg*>(b + l.off_info);
@@ -87,6 +105,13 @@ struct LargeWs {
         seg_large = reinterpret_cast<int4*>(b + l.off_seg_large);
         seg_huge = reinterpret_cast<int4*>(b + l.off_seg_huge);
         huge_nk = reinterpret_cast<int2*>(b + l.off_huge_nk);
+        tier_count = reinterpret_cast<int32_t*>(b + l.off_tier_count);
+        tier_box = reinterpret_cast<float4*>(b + l.off_tier_box);
+        tier_score = reinterpret_cast<float*>(b + l.off_tier_score);
+        tier_cls = reinterpret_cast<int32_t*>(b + l.off_tier_cls);
+        tier_id = reinterpret_cast<int32_t*>(b + l.off_tier_id);
+        tier_full = reinterpret_cast<FullStats*>(b + l.off_tier_full);
+        tier_todo = reinterpret_cast<int32_t*>(b + l.off_tier_todo);
     }
 };
 
@@ -95,12 +120,15 @@ using KLL = KeyLayout<kLargeIdxBits>;
 // ---- per-image mode + coordinate statistics ------------------------------------------------------
 static __global__ void __launch_bounds__(256)
 large_stats_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats,
-                   const int32_t* __restrict__ counts, int64_t m_max, float thr_f, int mode, LargeImg* info) {
+                   const int32_t* __restrict__ counts, int64_t m_max, float thr_f, int mode, LargeImg* info,
+                   const int32_t* __restrict__ todo = nullptr) {
     __shared__ float r_max[8], r_min[8];
     __shared__ int r_flag[8];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int cnt = counts ? counts[img] : (int)m_max;
     cnt = max(0, min(cnt, (int)m_max));
+    const bool skip = todo && todo[img] == 0;  // the top-k tier has written this image's result
+    if (skip) cnt = 0;
     const bool trick = (mode == DET_NMS_AUTO) ? (cnt <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
     float mx = -INFINITY, mn = INFINITY;
     int fin = 1, maxcat = 0;
@@ -142,7 +170,144 @@ large_stats_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__
         li.bad = 0;
         li.nsurv = cnt;
         li.nonan = 1;  // cleared by the gather kernel if it meets a NaN coordinate
+        li.skip = skip ? 1 : 0;
         info[img] = li;
+    }
+}
+
+// ---- top-k tier: the best-scored `want` boxes of an image -> candidate list ----------------------------------------------
+// Only max_out survivors are wanted and a box can only be suppressed by a better-scored one, so when max_out is a small
+// part of the image the NMS first runs on the want = 1.25 * max_out + 32 best boxes (list_nms_kernel, nms_list.cuh);
+// max_out survivors there are exactly the first max_out of the full result.  The cut is the want-th best score to 24
+// bits (three radix passes); every box at or above it joins the list, so ties never straddle the cut.  The reference's
+// branch rule and the offset trick's span are defined on the whole image: FullStats.  tier_count = -1 hands the
+// image to the full path (too few boxes for a tier, a category outside the key range, or a list overflow).
+static __global__ void __launch_bounds__(1024)
+large_topk_select_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                         const int64_t* __restrict__ cats, const int32_t* __restrict__ counts, int64_t m_max, int mode,
+                         int want, int32_t* __restrict__ tier_count, float4* __restrict__ cand_box,
+                         float* __restrict__ cand_score, int32_t* __restrict__ cand_cls, int32_t* __restrict__ cand_id,
+                         FullStats* __restrict__ full) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_want, s_n, s_bad;
+    __shared__ float r_max[32], r_min[32];
+    __shared__ int r_flag[32];
+    constexpr int T = 1024;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int cnt = counts ? counts[img] : (int)m_max;
+    cnt = max(0, min(cnt, (int)m_max));
+    int32_t* my_count = tier_count + (int64_t)img * kCountStride;
+    if (cnt < want + (want >> 1)) {
+        if (tid == 0) *my_count = -1;
+        return;
+    }
+    const float* sc = scores + (int64_t)img * m_max;
+    const float4* bx = boxes + (int64_t)img * m_max;
+    const int64_t* ct = cats ? cats + (int64_t)img * m_max : nullptr;
+    if (tid == 0) {
+        s_prefix = 0u;
+        s_want = want;
+        s_n = 0;
+        s_bad = 0;
+    }
+    for (int shift = 24; shift >= 8; shift -= 8) {
+        for (int b = tid; b < 256; b += T) hist[b] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < cnt; i += T) {
+            const uint32_t key = score_desc_key(sc[i]);
+            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t c8[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                c8[q] = hist[lane * 8 + q];
+                tot += c8[q];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += (lane >= o) ? up : 0u;
+            }
+            const uint32_t w = (uint32_t)s_want, before = incl - tot;
+            if (before < w && w <= incl) {
+                uint32_t run = before;
+                int q = 0;
+                for (; q < 7 && run + c8[q] < w; ++q) run += c8[q];
+                s_prefix = prefix | ((uint32_t)(lane * 8 + q) << shift);
+                s_want = (int)(w - run);
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t cut = s_prefix | 0xffu;
+    // statistics of the whole image, needed only where the offset trick applies
+    const bool trick = (mode == DET_NMS_AUTO) ? (cnt <= 1000) : (mode == DET_NMS_OFFSET_TRICK);
+    float mx = -INFINITY, mn = INFINITY;
+    int fin = 1, maxcat = 0;
+    if (trick) {
+        for (int i = tid; i < cnt; i += T) {
+            const float4 b = bx[i];
+            mx = max_nan(mx, max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w)));
+            mn = min_nan(mn, min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w)));
+            fin &= (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
+        }
+    }
+    // compaction; every category of the image is looked at (one outside the key range makes the result -1)
+    int bad = 0;
+    for (int i0 = 0; i0 < cnt; i0 += T) {
+        const int i = i0 + tid;
+        bool in = false;
+        int64_t c = 0;
+        float s = 0.f;
+        if (i < cnt) {
+            c = ct ? ct[i] : 0;
+            bad |= (c < 0 || c >= (1 << kSegBits) - 1) ? 1 : 0;
+            maxcat = max(maxcat, (int)min(max(c, (int64_t)0), (int64_t)65535));
+            s = sc[i];
+            in = score_desc_key(s) <= cut;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        int pos = 0;
+        if (lane == 0 && bal) pos = atomicAdd(&s_n, __popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+        if (in && pos < kTierCap) {
+            const int64_t o = (int64_t)img * kTierCap + pos;
+            cand_box[o] = bx[i];
+            cand_score[o] = s;
+            cand_cls[o] = (int32_t)c;
+            cand_id[o] = i;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        fin &= __shfl_xor_sync(0xffffffffu, fin, o);
+        maxcat = max(maxcat, __shfl_xor_sync(0xffffffffu, maxcat, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) {
+        r_max[wid] = mx;
+        r_min[wid] = mn;
+        r_flag[wid] = fin | (maxcat << 1);
+        if (bad) s_bad = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < T / 32; ++w) {
+            mx = max_nan(mx, r_max[w]);
+            mn = min_nan(mn, r_min[w]);
+            fin &= r_flag[w] & 1;
+            maxcat = max(maxcat, r_flag[w] >> 1);
+        }
+        FullStats f;
+        f.count = cnt; f.mx = mx; f.mn = mn; f.fin = fin; f.maxcat = maxcat;
+        full[img] = f;
+        *my_count = (s_bad || s_n > kTierCap) ? -1 : s_n;
     }
 }
 
@@ -154,6 +319,7 @@ large_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= mp) return;
     const LargeImg li = info[img];
+    if (li.skip) return;
     uint64_t k = kSentinelKey;
     if (i < li.cnt) {
         const int64_t c = cats ? cats[(int64_t)img * m_max + i] : 0;
@@ -165,8 +331,10 @@ large_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
 }
 
 // ---- sort: 2048-key tiles in shared memory, then merge-path passes ------------------------------------
-static __global__ void __launch_bounds__(kSortThreads) sort_tiles_kernel(uint64_t* __restrict__ keys, int64_t mp) {
+static __global__ void __launch_bounds__(kSortThreads)
+sort_tiles_kernel(uint64_t* __restrict__ keys, int64_t mp, const LargeImg* __restrict__ info) {
     __shared__ uint64_t s[kTile];
+    if (info && info[blockIdx.y].skip) return;  // nobody reads this image's keys
     uint64_t* g = keys + (int64_t)blockIdx.y * mp + (int64_t)blockIdx.x * kTile;
 #pragma unroll
     for (int v = 0; v < kVT; ++v) s[threadIdx.x + v * kSortThreads] = g[threadIdx.x + v * kSortThreads];
@@ -188,9 +356,11 @@ __device__ __forceinline__ int64_t merge_path(P A, int64_t na, P B, int64_t nb, 
 }
 
 static __global__ void __launch_bounds__(kSortThreads)
-merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t mp, int64_t width) {
+merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t mp, int64_t width,
+                  const LargeImg* __restrict__ info) {
     __shared__ uint64_t s[kTile];
     __shared__ int64_t s_cut[2];
+    if (info && info[blockIdx.y].skip) return;
     const uint64_t* kin = in + (int64_t)blockIdx.y * mp;
     uint64_t* kout = out + (int64_t)blockIdx.y * mp;
     const int64_t out0 = (int64_t)blockIdx.x * kTile;
@@ -230,12 +400,13 @@ merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, i
 }
 
 // sorts every image's row of mp keys ascending; returns the buffer that holds the result
-static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStream_t st) {
+static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStream_t st,
+                           const LargeImg* info = nullptr) {
     dim3 grid((unsigned)(mp / kTile), (unsigned)n);
-    sort_tiles_kernel<<<grid, kSortThreads, 0, st>>>(a, mp);
+    sort_tiles_kernel<<<grid, kSortThreads, 0, st>>>(a, mp, info);
     uint64_t *src = a, *dst = b;
     for (int64_t width = kTile; width < mp; width *= 2) {
-        merge_pass_kernel<<<grid, kSortThreads, 0, st>>>(src, dst, mp, width);
+        merge_pass_kernel<<<grid, kSortThreads, 0, st>>>(src, dst, mp, width, info);
         uint64_t* t = src;
         src = dst;
         dst = t;
@@ -483,6 +654,7 @@ large_rekey_kernel(int64_t mp, LargeImg* info, const uint64_t* __restrict__ keys
                    uint64_t* __restrict__ keys_out) {
     const int img = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (info[img].skip) return;
     const int cnt = info[img].cnt;
     bool kept = false;
     if (p < mp) {
@@ -499,9 +671,29 @@ large_emit_kernel(int64_t mp, const LargeImg* __restrict__ info, const uint64_t*
     const int img = blockIdx.y;
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const LargeImg li = info[img];
+    if (li.skip) return;
     const int64_t nout = li.bad ? 0 : min((int64_t)li.nkept, max_out);
     if (j < nout) keep[(int64_t)img * max_out + j] = (int64_t)KLL::idx(keys[(int64_t)img * mp + j]);
     if (j == 0) keep_counts[img] = li.bad ? -1 : (int32_t)nout;
+}
+
+static int launch_list_nms_ext(const int32_t* tier_count, const float4* box, const float* score, const int32_t* cls,
+                               const int32_t* id, int n, float thr_f, int mode, int64_t max_out, int64_t* keep,
+                               int32_t* keep_counts, const FullStats* full, int32_t* todo, cudaStream_t st) {
+    constexpr int T = 512;  // 180 KB of shared memory per CTA: one CTA per SM either way
+    const size_t smem = sizeof(DetectSmem<kTierCap, T>);
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(dense_detect_nms_kernel<kTierCap, T>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(list nms)");
+        attr_set = true;
+    }
+    dense_detect_nms_kernel<kTierCap, T><<<n, T, smem, st>>>(tier_count, box, score, cls, id, kTierCap, thr_f, mode,
+                                                             max_out, keep, nullptr, nullptr, nullptr, keep_counts,
+                                                             nullptr, full, todo);
+    DET_LAUNCH_OK("list_nms_kernel(ext)");
+    return DET_OK;
 }
 
 // runs the two persistent segment kernels over the lists built by a gather kernel
@@ -552,12 +744,25 @@ static int large_nms_run(const LargeLayout& lay, void* workspace, const float* b
     auto b4 = reinterpret_cast<const float4*>(boxes);
     cudaError_t e = cudaMemsetAsync(ws.ctr, 0, 64, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    large_stats_kernel<<<n, 256, 0, st>>>(b4, cats, counts, lay.m_max, thr_f, mode, ws.info);
+    // top-k tier: when max_out is a small part of the image, sweep the best-scored boxes first (see
+    // large_topk_select_kernel); images that get their max_out survivors there skip everything below
+    const int64_t want = max_out + (max_out >> 2) + 32;
+    const int32_t* todo = nullptr;
+    if (max_out >= 1 && want <= kTierMaxWant && want + (want >> 1) <= lay.m_max) {
+        large_topk_select_kernel<<<n, 1024, 0, st>>>(b4, scores, cats, counts, lay.m_max, mode, (int)want, ws.tier_count,
+                                                     ws.tier_box, ws.tier_score, ws.tier_cls, ws.tier_id, ws.tier_full);
+        DET_LAUNCH_OK("large_topk_select_kernel");
+        const int rc = launch_list_nms_ext(ws.tier_count, ws.tier_box, ws.tier_score, ws.tier_cls, ws.tier_id, n, thr_f,
+                                           mode, max_out, keep, keep_counts, ws.tier_full, ws.tier_todo, st);
+        if (rc != DET_OK) return rc;
+        todo = ws.tier_todo;
+    }
+    large_stats_kernel<<<n, 256, 0, st>>>(b4, cats, counts, lay.m_max, thr_f, mode, ws.info, todo);
     DET_LAUNCH_OK("large_stats_kernel");
     dim3 grid_e((unsigned)((mp + 255) / 256), (unsigned)n);
     large_keys_kernel<<<grid_e, 256, 0, st>>>(scores, cats, lay.m_max, mp, ws.info, ws.keys_a);
     DET_LAUNCH_OK("large_keys_kernel");
-    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st);
+    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st, ws.info);
     uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
     DET_LAUNCH_OK("sort_rows");
     large_gather_kernel<<<grid_e, 256, 0, st>>>(b4, cats, lay.m_max, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state,
@@ -568,7 +773,7 @@ static int large_nms_run(const LargeLayout& lay, void* workspace, const float* b
     if (rc != DET_OK) return rc;
     large_rekey_kernel<<<grid_e, 256, 0, st>>>(mp, ws.info, sorted, ws.state, other);
     DET_LAUNCH_OK("large_rekey_kernel");
-    uint64_t* final_keys = sort_rows(other, sorted, n, mp, st);
+    uint64_t* final_keys = sort_rows(other, sorted, n, mp, st, ws.info);
     DET_LAUNCH_OK("sort_rows(2)");
     dim3 grid_o((unsigned)((min(max_out, lay.m_max) + 255) / 256), (unsigned)n);
     large_emit_kernel<<<grid_o, 256, 0, st>>>(mp, ws.info, final_keys, max_out, keep, keep_counts);

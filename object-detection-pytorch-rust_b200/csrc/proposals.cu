@@ -32,7 +32,7 @@ rpn_keys_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTa
     if (i >= mp) return;
     if (i == 0) {
         LargeImg li;
-        li.cnt = (int32_t)r; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0; li.nsurv = 0; li.nonan = 1;  // non-finite boxes are dropped by the gather kernel
+        li.cnt = (int32_t)r; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0; li.nsurv = 0; li.nonan = 1; li.skip = 0;  // non-finite boxes are dropped by the gather kernel
         info[img] = li;
     }
     uint64_t k = kSentinelKey;

@@ -236,3 +236,45 @@ def test_offset_trick_many_corner_boxes_take_the_exact_slow_path(det, O):
     s = torch.rand(n, generator=g)
     c = torch.randint(0, 10, (n,), generator=g)
     assert torch.equal(det.batched_nms(b.cuda(), s.cuda(), c.cuda(), 0.4).cpu(), O.batched_nms(b, s, c, 0.4))
+
+
+# ---- top-k tier of the large path: max_out << boxes (nms_large.cuh large_topk_select_kernel + nms_list.cuh) ------------
+@pytest.mark.parametrize("m,ncat,max_out,thr,ties", [
+    (5000, 80, 100, 0.5, False), (25200, 80, 1000, 0.5, False), (25200, 1, 300, 0.5, False),
+    (8000, 20, 200, 0.5, True),      # quantised scores: ties inside segments, across them and at the radix cut
+    (6000, 1, 500, 0.05, False),     # heavy suppression: the tier falls short, the full path takes over
+    (5000, 3, 2400, 0.5, False),     # the largest tier (want = 3032)
+])
+def test_large_path_topk_tier(det, O, m, ncat, max_out, thr, ties):
+    n = 3
+    counts = [m, m // 2 + 7, max_out + 5]  # the last image is too small for a tier
+    bs, ss, cs = [], [], []
+    for i in range(n):
+        b, s, c = _case(m, ncat, seed=1000 + m + i, ties=ties)
+        bs.append(b); ss.append(s); cs.append(c)
+    keep, cnt = det.nms_images(torch.stack(bs).cuda(), torch.stack(ss).cuda(), torch.stack(cs).cuda(),
+                               torch.tensor(counts, dtype=torch.int32).cuda(), thr, max_out)
+    for i in range(n):
+        k = counts[i]
+        want = O.batched_nms(bs[i][:k], ss[i][:k], cs[i][:k], thr)[:max_out]
+        assert int(cnt[i]) == want.numel()
+        assert torch.equal(keep[i, :want.numel()].cpu(), want)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_large_path_topk_tier_forced_branches(det, mode):
+    """Forced per-category / offset-trick branches: top-k result == the first max_out of the library's full result."""
+    b, s, c = _case(7000, 12, seed=5)
+    b = b - 100.0  # coordinates below -1: the trick's cross-category handling with the full image's span
+    args = (b[None].cuda(), s[None].cuda(), c[None].cuda(), None, 0.5)
+    full, fc = det.nms_images(*args, None, mode)
+    top, tc = det.nms_images(*args, 150, mode)
+    assert int(tc) == 150 and int(fc) >= 150 and torch.equal(top[0, :150], full[0, :150])
+
+
+def test_large_path_topk_tier_bad_category_anywhere_is_reported(det):
+    b, s, c = _case(6000, 5, seed=6)
+    s[4000] = -1.0   # far below the tier's cut
+    c[4000] = 40000  # outside the key range
+    keep, cnt = det.nms_images(b[None].cuda(), s[None].cuda(), c[None].cuda(), None, 0.5, 100)
+    assert int(cnt) == -1
