@@ -356,7 +356,7 @@ __device__ __forceinline__ int64_t merge_path(P A, int64_t na, P B, int64_t nb, 
 }
 
 static __global__ void __launch_bounds__(kSortThreads)
-merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t mp, int64_t width,
+merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t mp, int64_t len, int64_t width,
                   const LargeImg* __restrict__ info) {
     __shared__ uint64_t s[kTile];
     __shared__ int64_t s_cut[2];
@@ -365,9 +365,9 @@ merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, i
     uint64_t* kout = out + (int64_t)blockIdx.y * mp;
     const int64_t out0 = (int64_t)blockIdx.x * kTile;
     const int64_t lo = out0 / (2 * width) * (2 * width);
-    const int64_t a_len = min(width, mp - lo);
+    const int64_t a_len = min(width, len - lo);
     const int64_t b_lo = lo + a_len;
-    const int64_t b_len = max((int64_t)0, min(width, mp - b_lo));
+    const int64_t b_len = max((int64_t)0, min(width, len - b_lo));
     const uint64_t* A = kin + lo;
     const uint64_t* B = kin + b_lo;
     const int64_t d0 = out0 - lo, d1 = min(d0 + (int64_t)kTile, a_len + b_len);
@@ -399,14 +399,16 @@ merge_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, i
         if (diag + v < total) kout[out0 + diag + v] = r[v];
 }
 
-// sorts every image's row of mp keys ascending; returns the buffer that holds the result
+// sorts the first `len` keys (a multiple of kTile; default: all mp) of every image's row ascending; rows are mp keys
+// apart; returns the buffer that holds the result
 static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStream_t st,
-                           const LargeImg* info = nullptr) {
-    dim3 grid((unsigned)(mp / kTile), (unsigned)n);
+                           const LargeImg* info = nullptr, int64_t len = 0) {
+    if (len <= 0) len = mp;
+    dim3 grid((unsigned)(len / kTile), (unsigned)n);
     sort_tiles_kernel<<<grid, kSortThreads, 0, st>>>(a, mp, info);
     uint64_t *src = a, *dst = b;
-    for (int64_t width = kTile; width < mp; width *= 2) {
-        merge_pass_kernel<<<grid, kSortThreads, 0, st>>>(src, dst, mp, width, info);
+    for (int64_t width = kTile; width < len; width *= 2) {
+        merge_pass_kernel<<<grid, kSortThreads, 0, st>>>(src, dst, mp, len, width, info);
         uint64_t* t = src;
         src = dst;
         dst = t;
@@ -415,9 +417,11 @@ static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStre
 }
 
 // push segment [s,e) of image img on the short, long or huge work list
+// warp_max: longest segment handed to a single warp.  A lone warp needs > 100 us for 256 boxes (latency-bound), which
+// is right when there are thousands of segments and wrong when there are a few hundred (RPN levels): those go to CTAs.
 __device__ __forceinline__ void push_segment(int img, int s, int e, int32_t* ctr, int4* seg_small, int4* seg_large,
-                                             int4* seg_huge, int2* huge_nk) {
-    if (e - s <= kLargeWarpSegMax) {
+                                             int4* seg_huge, int2* huge_nk, int warp_max = kLargeWarpSegMax) {
+    if (e - s <= warp_max) {
         const int slot = atomicAdd(&ctr[0], 1);
         seg_small[slot] = make_int4(img, s, e, 0);
     } else if (e - s <= kHugeSeg) {

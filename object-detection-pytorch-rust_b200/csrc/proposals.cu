@@ -6,11 +6,13 @@
 //   of every level with the finite / clip / min-size filters fused in -> per-(image, level) greedy NMS (nms_core.cuh)
 //   -> re-key kept by (descending logit | index) -> sort -> emit the first post_nms_topk boxes + logits per image.
 // No host synchronisation; the "training diverged" condition (models/utils.py:79-84) is reported through a device flag.
+#include <algorithm>
 #include "nms_large.cuh"
 
 namespace det {
 
 constexpr int kMaxLevels = 16;
+constexpr int kRpnWarpSegMax = 32;  // at most 16 segments per image: longer ones are swept by whole CTAs
 struct LevelTable {
     int num_levels;
     int64_t off[kMaxLevels + 1];
@@ -51,8 +53,7 @@ static __global__ void __launch_bounds__(256)
 rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ logits, int64_t r, int64_t mp,
                   LevelTable lt, int64_t pre_nms_topk, const int32_t* __restrict__ image_sizes, float min_size,
                   LargeImg* info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
-                  float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* ctr, int4* seg_small, int4* seg_large,
-                  int4* seg_huge, int2* huge_nk, int32_t* __restrict__ nonfinite_flag) {
+                  float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* __restrict__ nonfinite_flag) {
     const int img = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     bool survivor = false;
@@ -78,7 +79,6 @@ rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ lo
                     sarea[(int64_t)img * mp + p] = box_area(b);
                 }
             }
-            if (rank == 0) push_segment(img, (int)p, (int)(p + take), ctr, seg_small, seg_large, seg_huge, huge_nk);
         }
         state[(int64_t)img * mp + p] = st;
     }
@@ -114,6 +114,133 @@ rpn_offset_kernel(int64_t r, int64_t mp, const LargeImg* __restrict__ info, cons
             sbox[(int64_t)img * mp + p] = b;
             sarea[(int64_t)img * mp + p] = box_area(b);
         }
+}
+
+// ---- tier cut --------------------------------------------------------------------------------------------------------------
+// Only post_nms_topk proposals are wanted and a box can only be suppressed by a better-scored box of its level, so the
+// per-level sweeps first run on the candidates above a global score cut -- the (1.25 * post_nms_topk + 32)-th best
+// logit among the image's valid candidates, found exactly with a 4-pass radix select; ties with the cut are included.
+// Inside a level the candidates are sorted by logit, so "above the cut" is a PREFIX of the level's segment.  If the
+// prefixes yield post_nms_topk survivors, those are exactly the first post_nms_topk of the full result; otherwise
+// rpn_tier_check_kernel resets the image and queues its full segments for a second run of the segment kernels.
+// pass 0: decide + push prefixes (or full segments when a tier is not worth it);  pass 1: check + push full segments.
+static __global__ void __launch_bounds__(1024)
+rpn_tier_kernel(int pass, int64_t r, int64_t mp, LevelTable lt, int64_t pre_nms_topk, int64_t post_nms_topk,
+                LargeImg* info, const uint64_t* __restrict__ keys, uint8_t* __restrict__ state, int32_t* ctr,
+                int4* seg_small, int4* seg_large, int4* seg_huge, int2* huge_nk) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_want, s_kept;
+    constexpr int T = 1024;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t* k = keys + (int64_t)img * mp;
+    uint8_t* stt = state + (int64_t)img * mp;
+    const int want = (int)min(post_nms_topk + (post_nms_topk >> 2) + 32, (int64_t)1 << 30);
+    if (pass == 1) {
+        if (!info[img].pad_[0]) return;  // no tier was cut for this image: its full segments have been swept
+        if (tid == 0) s_kept = 0;
+        __syncthreads();
+        int kept = 0;
+        for (int l = 0; l < lt.num_levels; ++l) {
+            const int64_t s0 = lt.off[l], take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
+            for (int64_t p = s0 + tid; p < s0 + take; p += T) kept += stt[p] == 2 ? 1 : 0;
+        }
+        kept = warp_sum(kept);
+        if (lane == 0 && kept) atomicAdd(&s_kept, kept);
+        __syncthreads();
+        if (s_kept >= post_nms_topk) return;
+        for (int l = 0; l < lt.num_levels; ++l) {  // fell short: forget the prefix sweep, queue the full segments
+            const int64_t s0 = lt.off[l], take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
+            for (int64_t p = s0 + tid; p < s0 + take; p += T)
+                if (stt[p] == 2) stt[p] = 0;
+            if (tid == 0 && take > 0) push_segment(img, (int)s0, (int)(s0 + take), ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax);
+        }
+        return;
+    }
+    const bool tier = info[img].nsurv >= want + (want >> 1);
+    if (tid == 0) info[img].pad_[0] = tier ? 1 : 0;
+    if (!tier) {
+        if (tid < lt.num_levels) {
+            const int64_t s0 = lt.off[tid], take = min(lt.off[tid + 1] - lt.off[tid], pre_nms_topk);
+            if (take > 0) push_segment(img, (int)s0, (int)(s0 + take), ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax);
+        }
+        return;
+    }
+    if (tid == 0) {
+        s_prefix = 0u;
+        s_want = want;
+    }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += T) hist[b] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+        for (int l = 0; l < lt.num_levels; ++l) {
+            const int64_t s0 = lt.off[l], take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
+            for (int64_t p = s0 + tid; p < s0 + take; p += T) {
+                if (stt[p] != 0) continue;
+                const uint32_t key = (uint32_t)(k[p] >> KLL::kScoreShift);
+                if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        }
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t c8[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                c8[q] = hist[lane * 8 + q];
+                tot += c8[q];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += (lane >= o) ? up : 0u;
+            }
+            const uint32_t w = (uint32_t)s_want, before = incl - tot;
+            if (before < w && w <= incl) {
+                uint32_t run = before;
+                int q = 0;
+                for (; q < 7 && run + c8[q] < w; ++q) run += c8[q];
+                s_prefix = prefix | ((uint32_t)(lane * 8 + q) << shift);
+                s_want = (int)(w - run);
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t cut = s_prefix;  // exact descending-logit key of the want-th best valid candidate
+    if (tid < lt.num_levels) {
+        const int64_t s0 = lt.off[tid], take = min(lt.off[tid + 1] - lt.off[tid], pre_nms_topk);
+        int64_t lo = s0, hi = s0 + take;  // first position of the level whose key is worse than the cut
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((uint32_t)(k[mid] >> KLL::kScoreShift) > cut) hi = mid; else lo = mid + 1;
+        }
+        if (lo > s0) push_segment(img, (int)s0, (int)lo, ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax);
+    }
+}
+
+// kept candidates -> output keys (descending logit | index), COMPACTED to the front of the row: at most
+// min(sum of the levels' top-k, levels * post_nms_topk) boxes survive, so the output sort only touches a few tiles
+static __global__ void __launch_bounds__(256)
+rpn_rekey_compact_kernel(int64_t r, int64_t mp, LargeImg* info, const uint64_t* __restrict__ keys,
+                         const uint8_t* __restrict__ state, uint64_t* __restrict__ keys_out) {
+    const int img = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool kept = (p < r) && state[(int64_t)img * mp + p] == 2;
+    const unsigned bal = __ballot_sync(0xffffffffu, kept);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&info[img].nkept, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (kept) keys_out[(int64_t)img * mp + base + __popc(bal & ((1u << lane) - 1u))] = KLL::strip_seg(keys[(int64_t)img * mp + p]);
+}
+
+static __global__ void __launch_bounds__(256)
+rpn_pad_kernel(int64_t mp, int64_t len, const LargeImg* __restrict__ info, uint64_t* __restrict__ keys_out) {
+    const int img = blockIdx.y;
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j < len && j >= info[img].nkept) keys_out[(int64_t)img * mp + j] = kSentinelKey;
 }
 
 static __global__ void __launch_bounds__(256)
@@ -198,16 +325,33 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
     DET_LAUNCH_OK("sort_rows");
     rpn_gather_kernel<<<grid_e, 256, 0, st>>>(b4, logits, r, mp, lt, pre_nms_topk, image_sizes, min_box_size, ws.info,
-                                              sorted, ws.sbox, ws.sarea, ws.state, ws.ctr, ws.seg_small, ws.seg_large,
-                                              ws.seg_huge, ws.huge_nk, nonfinite_flag);
+                                              sorted, ws.sbox, ws.sarea, ws.state, nonfinite_flag);
     DET_LAUNCH_OK("rpn_gather_kernel");
     rpn_offset_kernel<<<n, 256, 0, st>>>(r, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state);
     DET_LAUNCH_OK("rpn_offset_kernel");
+    DET_CHECK_ARG(num_levels <= 32, "levels");
+    rpn_tier_kernel<<<n, 1024, 0, st>>>(0, r, mp, lt, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
+                                        ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
+    DET_LAUNCH_OK("rpn_tier_kernel");
     int rc = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
     if (rc != DET_OK) return rc;
-    large_rekey_kernel<<<grid_e, 256, 0, st>>>(mp, ws.info, sorted, ws.state, other);
-    DET_LAUNCH_OK("large_rekey_kernel");
-    uint64_t* final_keys = sort_rows(other, sorted, n, mp, st);
+    // images whose tier fell short of post_nms_topk survivors are swept again in full (usually none: empty lists)
+    e = cudaMemsetAsync(ws.ctr, 0, 64, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    rpn_tier_kernel<<<n, 1024, 0, st>>>(1, r, mp, lt, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
+                                        ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
+    DET_LAUNCH_OK("rpn_tier_kernel(check)");
+    rc = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
+    if (rc != DET_OK) return rc;
+    int64_t kept_bound = 0;
+    for (int l = 0; l < num_levels; ++l) kept_bound += std::min({level_sizes_host[l], pre_nms_topk, post_nms_topk});
+    const int64_t len2 = std::min(mp, (kept_bound + kTile - 1) / kTile * kTile);
+    rpn_rekey_compact_kernel<<<grid_e, 256, 0, st>>>(r, mp, ws.info, sorted, ws.state, other);
+    DET_LAUNCH_OK("rpn_rekey_compact_kernel");
+    dim3 grid_p((unsigned)((len2 + 255) / 256), (unsigned)n);
+    rpn_pad_kernel<<<grid_p, 256, 0, st>>>(mp, len2, ws.info, other);
+    DET_LAUNCH_OK("rpn_pad_kernel");
+    uint64_t* final_keys = sort_rows(other, sorted, n, mp, st, nullptr, len2);
     DET_LAUNCH_OK("sort_rows(2)");
     dim3 grid_o((unsigned)((min(post_nms_topk, r) + 255) / 256), (unsigned)n);
     rpn_emit_kernel<<<grid_o, 256, 0, st>>>(b4, logits, r, mp, ws.info, final_keys, image_sizes, post_nms_topk,

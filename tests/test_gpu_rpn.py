@@ -113,3 +113,22 @@ def test_forward_eval_from_heads(det, O):
     for i in range(2):
         assert torch.equal(props[i].proposal_boxes.tensor.cpu(), want[i][0])
         assert torch.equal(props[i].objectness_logits.cpu(), want[i][1])
+
+
+@pytest.mark.parametrize("nms_thresh,pre,post", [(0.7, 2000, 300), (0.05, 2000, 300), (0.3, 4000, 1000), (0.7, 1000, 50)])
+def test_find_top_rpn_proposals_tier_cut(det, O, nms_thresh, pre, post):
+    """post_nms_topk << candidates: the per-level sweeps first run above a global score cut (exact); with a low NMS
+    threshold the cut falls short and the full segments are swept in a second pass."""
+    g = gen(int(nms_thresh * 100) + post)
+    n = 3
+    obj, dlt = _heads(n, 448, g, 0.3)
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, 448)
+    sizes = [(448, 448), (400, 448), (448, 300)]
+    want = O.find_top_rpn_proposals(props, lg, sizes, nms_thresh, pre, post, 0.0, False)
+    got = det.find_top_rpn_proposals([p.cuda() for p in props], [l.cuda() for l in lg], sizes, nms_thresh, pre, post,
+                                     0.0, False)
+    for i in range(n):
+        wb, ws = want[i]
+        assert len(got[i]) == wb.shape[0], (i, len(got[i]), wb.shape[0])
+        assert torch.equal(got[i].objectness_logits.cpu(), ws)
+        assert torch.equal(got[i].proposal_boxes.tensor.cpu(), wb)
