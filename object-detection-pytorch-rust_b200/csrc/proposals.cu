@@ -2,9 +2,10 @@
 //
 // Replaces find_top_rpn_proposals (python/src/models/utils.py:9-109), which sorts every level fully, gathers, and then
 // loops over the images in Python with >= 4 host synchronisations each.  Here:
-//   keys (level | descending logit | anchor index) -> one segmented sort per image -> gather of the first pre_nms_topk
-//   of every level with the finite / clip / min-size filters fused in -> per-(image, level) greedy NMS (nms_core.cuh)
-//   -> re-key kept by (descending logit | index) -> sort -> emit the first post_nms_topk boxes + logits per image.
+//   per-level radix select of the pre_nms_topk best keys (level | descending logit | anchor index) into a compact row
+//   -> sort of that row only -> gather with the finite / clip / min-size filters fused in -> tier cut: per-(image,
+//   level) greedy NMS (nms_core.cuh) above a global score cut first, full segments only if that falls short of
+//   post_nms_topk -> kept keys (descending logit | index) compacted -> sort of a few tiles -> emit boxes + logits.
 // No host synchronisation; the "training diverged" condition (models/utils.py:79-84) is reported through a device flag.
 #include <algorithm>
 #include "nms_large.cuh"
@@ -26,20 +27,106 @@ __device__ __forceinline__ int level_of(const LevelTable& t, int64_t i) {
     return l;
 }
 
-static __global__ void __launch_bounds__(256)
-rpn_keys_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LargeImg* info,
-                uint64_t* __restrict__ keys) {
-    const int img = blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= mp) return;
-    if (i == 0) {
+// ---- per-level top-k by radix select ---------------------------------------------------------------------------------------
+// The reference sorts every level fully and narrows to pre_nms_topk (models/utils.py:56-58).  Here the pre_nms_topk
+// best keys (level | descending logit | anchor index -- unique, so "best k" is exact and stable) of every level are
+// found with a radix select (4 byte-passes over the logit bits; the index bits only when equal logits straddle the
+// cut) and written, in arrival order, to a compact row [coff[l], coff[l] + take_l) per level.  Only that row -- a few
+// tiles instead of all R keys -- is sorted afterwards.  One CTA per image.
+static __global__ void __launch_bounds__(1024)
+rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LevelTable ct, int64_t len1,
+                  LargeImg* info, uint64_t* __restrict__ keys) {
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_want, s_slot, s_done;
+    constexpr int T = 1024;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* lg = logits + (int64_t)img * r;
+    uint64_t* out = keys + (int64_t)img * mp;
+    if (tid == 0) {
         LargeImg li;
-        li.cnt = (int32_t)r; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0; li.nsurv = 0; li.nonan = 1; li.skip = 0;  // non-finite boxes are dropped by the gather kernel
+        li.cnt = (int32_t)ct.off[ct.num_levels]; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0;
+        li.nsurv = 0; li.nonan = 1; li.skip = 0;  // non-finite boxes are dropped by the gather kernel
+        for (int q = 0; q < 7; ++q) li.pad_[q] = 0;
         info[img] = li;
     }
-    uint64_t k = kSentinelKey;
-    if (i < r) k = KLL::make((uint32_t)level_of(lt, i), logits[(int64_t)img * r + i], (uint32_t)i);
-    keys[(int64_t)img * mp + i] = k;
+    for (int64_t j = ct.off[ct.num_levels] + tid; j < len1; j += T) out[j] = kSentinelKey;
+    for (int l = 0; l < lt.num_levels; ++l) {
+        const int64_t i0 = lt.off[l], size = lt.off[l + 1] - i0;
+        const int take = (int)(ct.off[l + 1] - ct.off[l]);
+        if (take == 0) continue;
+        unsigned long long cut = ~0ull;  // take == size: everything
+        if (take < size) {
+            // keys without the level field, shifted left by 7: bits 24..55 = logit, 7..23 = index; selected byte by
+            // byte from the top (the four logit bytes first)
+            if (tid == 0) {
+                s_prefix = 0ull;
+                s_want = take;
+                s_done = 0;
+            }
+            for (int shift = 48; shift >= 0; shift -= 8) {
+                for (int b = tid; b < 256; b += T) hist[b] = 0u;
+                __syncthreads();
+                if (s_done) break;
+                const unsigned long long prefix = s_prefix;
+                const unsigned long long himask = (shift == 48) ? 0ull : (~0ull << (shift + 8));
+                for (int64_t i = tid; i < size; i += T) {
+                    const unsigned long long key = KLL::strip_seg(KLL::make(0u, lg[i0 + i], (uint32_t)(i0 + i))) << 7;
+                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255ull], 1u);
+                }
+                __syncthreads();
+                if (wid == 0) {
+                    uint32_t c8[8], tot = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        c8[q] = hist[lane * 8 + q];
+                        tot += c8[q];
+                    }
+                    uint32_t incl = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                        incl += (lane >= o) ? up : 0u;
+                    }
+                    const uint32_t w = (uint32_t)s_want, before = incl - tot;
+                    if (before < w && w <= incl) {
+                        uint32_t run = before;
+                        int q = 0;
+                        for (; q < 7 && run + c8[q] < w; ++q) run += c8[q];
+                        unsigned long long np = prefix | ((unsigned long long)(lane * 8 + q) << shift);
+                        // the whole bin is wanted: every key that shares the prefix so far is in; stop here
+                        if (run + c8[q] == w) {
+                            np |= (shift == 0) ? 0ull : ((1ull << shift) - 1ull);
+                            s_done = 1;
+                        }
+                        s_prefix = np;
+                        s_want = (int)(w - run);
+                    }
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+            cut = s_prefix;
+        }
+        if (tid == 0) s_slot = 0;
+        __syncthreads();
+        const uint64_t lvl = (uint64_t)l << KLL::kSegShift;
+        for (int64_t base = 0; base < size; base += T) {
+            const int64_t i = base + tid;
+            unsigned long long key = 0;
+            bool in = false;
+            if (i < size) {
+                key = KLL::strip_seg(KLL::make(0u, lg[i0 + i], (uint32_t)(i0 + i)));
+                in = (key << 7) <= cut;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            int pos = 0;
+            if (lane == 0 && bal) pos = atomicAdd(&s_slot, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+            if (in && pos < take) out[ct.off[l] + pos] = lvl | key;
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ float4 clip_box(float4 b, float w, float h) {
@@ -50,14 +137,14 @@ __device__ __forceinline__ float4 clip_box(float4 b, float w, float h) {
 }
 
 static __global__ void __launch_bounds__(256)
-rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ logits, int64_t r, int64_t mp,
+rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ logits, int64_t r, int64_t rc, int64_t mp,
                   LevelTable lt, int64_t pre_nms_topk, const int32_t* __restrict__ image_sizes, float min_size,
                   LargeImg* info, const uint64_t* __restrict__ keys, float4* __restrict__ sbox,
                   float* __restrict__ sarea, uint8_t* __restrict__ state, int32_t* __restrict__ nonfinite_flag) {
     const int img = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     bool survivor = false;
-    if (p < r) {
+    if (p < rc) {  // lt is the COMPACT level table here: level l occupies [lt.off[l], lt.off[l+1]) of the sorted row
         const uint64_t key = keys[(int64_t)img * mp + p];
         const int64_t i = KLL::idx(key);
         const int l = (int)KLL::seg(key);
@@ -318,35 +405,44 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     auto b4 = reinterpret_cast<const float4*>(boxes);
     cudaError_t e = cudaMemsetAsync(ws.ctr, 0, 64, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    dim3 grid_e((unsigned)((mp + 255) / 256), (unsigned)n);
-    rpn_keys_kernel<<<grid_e, 256, 0, st>>>(logits, r, mp, lt, ws.info, ws.keys_a);
-    DET_LAUNCH_OK("rpn_keys_kernel");
-    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st);
+    // compact level table: level l keeps its best take_l = min(size_l, pre_nms_topk) keys at [coff[l], coff[l+1])
+    LevelTable ct;
+    ct.num_levels = num_levels;
+    int64_t rc = 0;
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        ct.off[l] = rc;
+        if (l < num_levels) rc += std::min(level_sizes_host[l], pre_nms_topk);
+    }
+    const int64_t len1 = (rc + kTile - 1) / kTile * kTile;  // <= mp
+    rpn_select_kernel<<<n, 1024, 0, st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a);
+    DET_LAUNCH_OK("rpn_select_kernel");
+    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st, nullptr, len1);
     uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
     DET_LAUNCH_OK("sort_rows");
-    rpn_gather_kernel<<<grid_e, 256, 0, st>>>(b4, logits, r, mp, lt, pre_nms_topk, image_sizes, min_box_size, ws.info,
+    dim3 grid_e((unsigned)((len1 + 255) / 256), (unsigned)n);
+    rpn_gather_kernel<<<grid_e, 256, 0, st>>>(b4, logits, r, rc, mp, ct, pre_nms_topk, image_sizes, min_box_size, ws.info,
                                               sorted, ws.sbox, ws.sarea, ws.state, nonfinite_flag);
     DET_LAUNCH_OK("rpn_gather_kernel");
-    rpn_offset_kernel<<<n, 256, 0, st>>>(r, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state);
+    rpn_offset_kernel<<<n, 256, 0, st>>>(rc, mp, ws.info, sorted, ws.sbox, ws.sarea, ws.state);
     DET_LAUNCH_OK("rpn_offset_kernel");
     DET_CHECK_ARG(num_levels <= 32, "levels");
-    rpn_tier_kernel<<<n, 1024, 0, st>>>(0, r, mp, lt, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
+    rpn_tier_kernel<<<n, 1024, 0, st>>>(0, rc, mp, ct, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
                                         ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
     DET_LAUNCH_OK("rpn_tier_kernel");
-    int rc = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
-    if (rc != DET_OK) return rc;
+    int status = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
+    if (status != DET_OK) return status;
     // images whose tier fell short of post_nms_topk survivors are swept again in full (usually none: empty lists)
     e = cudaMemsetAsync(ws.ctr, 0, 64, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    rpn_tier_kernel<<<n, 1024, 0, st>>>(1, r, mp, lt, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
+    rpn_tier_kernel<<<n, 1024, 0, st>>>(1, rc, mp, ct, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
                                         ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
     DET_LAUNCH_OK("rpn_tier_kernel(check)");
-    rc = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
-    if (rc != DET_OK) return rc;
+    status = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
+    if (status != DET_OK) return status;
     int64_t kept_bound = 0;
     for (int l = 0; l < num_levels; ++l) kept_bound += std::min({level_sizes_host[l], pre_nms_topk, post_nms_topk});
     const int64_t len2 = std::min(mp, (kept_bound + kTile - 1) / kTile * kTile);
-    rpn_rekey_compact_kernel<<<grid_e, 256, 0, st>>>(r, mp, ws.info, sorted, ws.state, other);
+    rpn_rekey_compact_kernel<<<grid_e, 256, 0, st>>>(rc, mp, ws.info, sorted, ws.state, other);
     DET_LAUNCH_OK("rpn_rekey_compact_kernel");
     dim3 grid_p((unsigned)((len2 + 255) / 256), (unsigned)n);
     rpn_pad_kernel<<<grid_p, 256, 0, st>>>(mp, len2, ws.info, other);

@@ -132,3 +132,20 @@ def test_find_top_rpn_proposals_tier_cut(det, O, nms_thresh, pre, post):
         assert len(got[i]) == wb.shape[0], (i, len(got[i]), wb.shape[0])
         assert torch.equal(got[i].objectness_logits.cpu(), ws)
         assert torch.equal(got[i].proposal_boxes.tensor.cpu(), wb)
+
+
+def test_find_top_rpn_proposals_equal_logits_straddle_the_topk_cut(det, O):
+    """Quantised logits: the per-level radix select has to go on into the index bits (stable order, lower index first)."""
+    g = gen(123)
+    n = 2
+    obj, dlt = _heads(n, 224, g, 0.3)
+    obj = [(o * 2).round() / 2 for o in obj]
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, 224)
+    sizes = [(224, 224), (200, 224)]
+    for pre, post in ((100, 40), (700, 300), (3000, 1000)):
+        want = O.find_top_rpn_proposals(props, lg, sizes, 0.7, pre, post, 0.0, False)
+        got = det.find_top_rpn_proposals([p.cuda() for p in props], [l.cuda() for l in lg], sizes, 0.7, pre, post, 0.0,
+                                         False)
+        for i in range(n):
+            assert torch.equal(got[i].objectness_logits.cpu(), want[i][1])
+            assert torch.equal(got[i].proposal_boxes.tensor.cpu(), want[i][0])
