@@ -62,7 +62,7 @@ struct LargeLayout {
         off_klist = take(4 * n * mp);
         off_seg_small = take(16 * n * segcap);
         off_seg_large = take(16 * n * segcap);
-        hugecap = (int64_t)n * (mp / kHugeSeg + 1);
+        hugecap = (int64_t)n * (mp / kHugeSeg + 1 > 16 ? mp / kHugeSeg + 1 : 16);  // RPN: up to 16 levels per image
         off_seg_huge = take(16 * hugecap);
         off_huge_nk = take(8 * 3 * hugecap);
         // top-k tier (max_out << boxes): candidate lists of the best-scored boxes of each image
@@ -420,11 +420,12 @@ static uint64_t* sort_rows(uint64_t* a, uint64_t* b, int n, int64_t mp, cudaStre
 // warp_max: longest segment handed to a single warp.  A lone warp needs > 100 us for 256 boxes (latency-bound), which
 // is right when there are thousands of segments and wrong when there are a few hundred (RPN levels): those go to CTAs.
 __device__ __forceinline__ void push_segment(int img, int s, int e, int32_t* ctr, int4* seg_small, int4* seg_large,
-                                             int4* seg_huge, int2* huge_nk, int warp_max = kLargeWarpSegMax) {
+                                             int4* seg_huge, int2* huge_nk, int warp_max = kLargeWarpSegMax,
+                                             int cta_max = kHugeSeg) {
     if (e - s <= warp_max) {
         const int slot = atomicAdd(&ctr[0], 1);
         seg_small[slot] = make_int4(img, s, e, 0);
-    } else if (e - s <= kHugeSeg) {
+    } else if (e - s <= cta_max) {
         const int slot = atomicAdd(&ctr[1], 1);
         seg_large[slot] = make_int4(img, s, e, 0);
     } else {

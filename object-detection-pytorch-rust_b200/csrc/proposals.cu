@@ -13,7 +13,9 @@
 namespace det {
 
 constexpr int kMaxLevels = 16;
-constexpr int kRpnWarpSegMax = 32;  // at most 16 segments per image: longer ones are swept by whole CTAs
+constexpr int kRpnWarpSegMax = 32;  // at most 16 segments per image: longer ones are swept by whole CTAs,
+constexpr int kRpnCtaSegMax = kHugeSeg;  // (routing segments > 512 to the grid-wide kernel was measured slower:
+                                         //  0.69 vs 0.57 ms per 64 images -- its grid barriers cost more than they save)
 struct LevelTable {
     int num_levels;
     int64_t off[kMaxLevels + 1];
@@ -240,7 +242,7 @@ rpn_tier_kernel(int pass, int64_t r, int64_t mp, LevelTable lt, int64_t pre_nms_
             const int64_t s0 = lt.off[l], take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
             for (int64_t p = s0 + tid; p < s0 + take; p += T)
                 if (stt[p] == 2) stt[p] = 0;
-            if (tid == 0 && take > 0) push_segment(img, (int)s0, (int)(s0 + take), ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax);
+            if (tid == 0 && take > 0) push_segment(img, (int)s0, (int)(s0 + take), ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax, kRpnCtaSegMax);
         }
         return;
     }
@@ -249,7 +251,7 @@ rpn_tier_kernel(int pass, int64_t r, int64_t mp, LevelTable lt, int64_t pre_nms_
     if (!tier) {
         if (tid < lt.num_levels) {
             const int64_t s0 = lt.off[tid], take = min(lt.off[tid + 1] - lt.off[tid], pre_nms_topk);
-            if (take > 0) push_segment(img, (int)s0, (int)(s0 + take), ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax);
+            if (take > 0) push_segment(img, (int)s0, (int)(s0 + take), ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax, kRpnCtaSegMax);
         }
         return;
     }
@@ -302,7 +304,7 @@ rpn_tier_kernel(int pass, int64_t r, int64_t mp, LevelTable lt, int64_t pre_nms_
             const int64_t mid = (lo + hi) >> 1;
             if ((uint32_t)(k[mid] >> KLL::kScoreShift) > cut) hi = mid; else lo = mid + 1;
         }
-        if (lo > s0) push_segment(img, (int)s0, (int)lo, ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax);
+        if (lo > s0) push_segment(img, (int)s0, (int)lo, ctr, seg_small, seg_large, seg_huge, huge_nk, kRpnWarpSegMax, kRpnCtaSegMax);
     }
 }
 
