@@ -43,3 +43,22 @@ def test_no_torch_types_in_the_abi():
     assert "torch" not in text.lower().replace("pytorch-rust", "").replace("python/src", "").replace("torchvision", "") \
         or "at::" not in text
     assert "at::Tensor" not in text and "#include <torch" not in text
+
+
+def test_dense_detect_queries_and_argument_checks_need_no_gpu():
+    """Pure size query + argument validation of det_dense_detect: rejected before any CUDA call is made."""
+    import ctypes
+    from det_b200 import _native as N
+    wsb = N.fn("det_dense_detect_workspace_bytes")
+    assert wsb(0, 1024) == 256
+    assert wsb(32, 2048) == 32 * 128 + 32 * 2048 * 28          # padded counters + (box, score, class, row) lists
+    assert N.fn("det_nms_workspace_bytes")(32, 25200) > wsb(32, 4096)   # the large path carries the top-k tier's lists
+    f = N.fn("det_dense_detect")
+    null = ctypes.c_void_p(0)
+    args = lambda cap, max_det, mode: (null, 0, 4, 3, 80, 4.0, 0.1, 0.5, mode, 1, cap, max_det, null, null, null, null,
+                                       null, null, null, 0, null)
+    assert f(*args(5000, 300, 0)) == -1     # cand_cap > 4096
+    assert f(*args(1024, 0, 0)) == -1       # max_det < 1
+    assert f(*args(1024, 300, 7)) == -1     # unknown NMS mode
+    assert f(*args(1024, 300, 0)) == -1     # null outputs
+    assert b"null output" in N.fn("det_last_error")()
