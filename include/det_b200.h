@@ -85,6 +85,21 @@ DET_API int det_rpn_decode_level(const float* objectness, const float* deltas, i
                          float scale_clamp, float* logits_out, float* boxes_out, int64_t out_img_stride,
                          int64_t out_offset, void* stream);
 
+/* All pyramid levels of the RPN head in ONE launch (csrc/box_ops.cu rpn_decode_flat_kernel: a warp per 128-position
+ * tile, outputs staged in shared memory and written as contiguous spans).  Every level shares n and a; level l:
+ * objectness (n,a,h,w), deltas (n,a*4,h,w), cell_anchors (a,4), first output row out_offset.  Levels whose h*w is not
+ * a multiple of 4, unaligned heads or a > 4 fall back to one det_rpn_decode_level launch per level -- same results. */
+typedef struct det_rpn_level {
+    const float* objectness;
+    const float* deltas;
+    const float* cell_anchors;
+    int32_t h, w, stride, reserved;
+    int64_t out_offset;
+} det_rpn_level_t;
+DET_API int det_rpn_decode(const det_rpn_level_t* levels_host, int num_levels, int n, int a, float offset, float wx, float wy,
+                   float ww, float wh, float scale_clamp, float* logits_out, float* boxes_out, int64_t out_img_stride,
+                   void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (3) batched, category-partitioned NMS -- replaces batched_nms, python/src/utils.py:96 (and through it
  *     torchvision.ops.batched_nms / nms), for a whole batch of images in one call.

@@ -225,6 +225,94 @@ rpn_decode_level_kernel(const float* __restrict__ obj, const float* __restrict__
     }
 }
 
+
+// ---- all pyramid levels in ONE launch, outputs staged through shared memory --------------------------------------------
+// One warp owns a tile of 128 consecutive positions of one (level, image): every lane loads its 4 positions of the A
+// objectness planes and 4A delta planes with 16-byte loads (5A independent loads in flight), decodes, and parks the
+// results in the warp's shared-memory slab in output order (position-major, anchor-minor); the warp then writes the
+// slab -- one contiguous span of 128*A boxes and logits -- with fully coalesced stores.  Small levels ride along with
+// the big one instead of paying their own launch, ramp and tail.
+constexpr int kRpnFlatMaxLevels = 8;
+constexpr int kRpnFlatMaxA = 4;
+constexpr int kRpnTilePos = 128;
+constexpr int kRpnFlatWarps = 8;
+
+struct RpnLevelDev {
+    const float* obj;
+    const float* deltas;
+    const float4* cell;
+    int w, hw, tiles;  // tiles of 128 positions per image
+    float stride_unused;
+    int stride;
+    int64_t out_offset;
+};
+
+struct RpnFlatArgs {
+    RpnLevelDev lv[kRpnFlatMaxLevels];
+    long long tile_begin[kRpnFlatMaxLevels + 1];  // first flat tile of each level
+    int num_levels, n, a;
+    float offset, scale_clamp;
+    CodecWeights wt;
+    int64_t out_img_stride;
+    float* logits_out;
+    float4* boxes_out;
+};
+
+__global__ void __launch_bounds__(kRpnFlatWarps * 32) rpn_decode_flat_kernel(const __grid_constant__ RpnFlatArgs g) {
+    extern __shared__ __align__(16) unsigned char rpn_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * kRpnFlatWarps + wid;
+    if (tile >= g.tile_begin[g.num_levels]) return;  // warp-uniform
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < kRpnFlatMaxLevels; ++q)
+        if (q < g.num_levels && tile >= g.tile_begin[q]) l = q;
+    const RpnLevelDev& L = g.lv[l];
+    const int A = g.a;
+    const long long local = tile - g.tile_begin[l];
+    const int img = (int)(local / L.tiles), t = (int)(local - (long long)img * L.tiles);
+    const int pos0 = t * kRpnTilePos, npos = min(kRpnTilePos, L.hw - pos0);
+    float4* s_box = reinterpret_cast<float4*>(rpn_smem) + (size_t)wid * kRpnTilePos * A;
+    float* s_log = reinterpret_cast<float*>(reinterpret_cast<float4*>(rpn_smem) + (size_t)kRpnFlatWarps * kRpnTilePos * A) +
+                   (size_t)wid * kRpnTilePos * A;
+    const int p0 = pos0 + lane * 4;
+    if (lane * 4 < npos) {  // hw % 4 == 0: a lane's 4 positions are all inside or all outside
+        const float* obj_img = L.obj + (int64_t)img * A * L.hw + p0;
+        const float* del_img = L.deltas + (int64_t)img * A * 4 * L.hw + p0;
+        float sx[4], sy[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int p = p0 + v;
+            sx[v] = grid_shift(p % L.w, L.stride, g.offset);
+            sy[v] = grid_shift(p / L.w, L.stride, g.offset);
+        }
+        for (int ai = 0; ai < A; ++ai) {
+            const float4 l4 = ld_stream(reinterpret_cast<const float4*>(obj_img + (int64_t)ai * L.hw));
+            float4 q[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[c] = ld_stream(reinterpret_cast<const float4*>(del_img + (int64_t)(ai * 4 + c) * L.hw));
+            const float lg[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float d0[4] = {q[0].x, q[0].y, q[0].z, q[0].w}, d1[4] = {q[1].x, q[1].y, q[1].z, q[1].w};
+            const float d2[4] = {q[2].x, q[2].y, q[2].z, q[2].w}, d3[4] = {q[3].x, q[3].y, q[3].z, q[3].w};
+            const float4 ca = L.cell[ai];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float4 anchor = make_float4(sx[v] + ca.x, sy[v] + ca.y, sx[v] + ca.z, sy[v] + ca.w);
+                const int o = (lane * 4 + v) * A + ai;
+                s_box[o] = decode_delta(anchor, make_float4(d0[v], d1[v], d2[v], d3[v]), g.wt, g.scale_clamp);
+                s_log[o] = lg[v];
+            }
+        }
+    }
+    __syncwarp();
+    const int64_t obase = (int64_t)img * g.out_img_stride + L.out_offset + (int64_t)pos0 * A;
+    const int total = npos * A;
+    for (int i = lane; i < total; i += 32) {
+        st_stream(g.boxes_out + obase + i, s_box[i]);
+        st_stream(g.logits_out + obase + i, s_log[i]);
+    }
+}
+
 }  // namespace det
 
 using namespace det;
@@ -343,6 +431,57 @@ int det_rpn_decode_level(const float* objectness, const float* deltas, int n, in
                                                          scale_clamp, logits_out, bo, out_img_stride, out_offset);
     }
     DET_LAUNCH_OK("rpn_decode_level_kernel");
+    return DET_OK;
+}
+
+int det_rpn_decode(const det_rpn_level_t* levels_host, int num_levels, int n, int a, float offset, float wx, float wy,
+                   float ww, float wh, float scale_clamp, float* logits_out, float* boxes_out, int64_t out_img_stride,
+                   void* stream) {
+    DET_CHECK_ARG(num_levels >= 0 && n >= 0 && a >= 1 && a <= kMaxCellAnchors, "bad size (a <= 16)");
+    if (num_levels == 0 || n == 0) return DET_OK;
+    DET_CHECK_ARG(levels_host && logits_out && boxes_out, "null pointer");
+    const bool flat_ok = a <= kRpnFlatMaxA && aligned16(boxes_out);
+    RpnFlatArgs f;
+    f.num_levels = 0; f.n = n; f.a = a; f.offset = offset; f.scale_clamp = scale_clamp;
+    f.wt = CodecWeights{wx, wy, ww, wh};
+    f.out_img_stride = out_img_stride; f.logits_out = logits_out; f.boxes_out = reinterpret_cast<float4*>(boxes_out);
+    long long tb = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const det_rpn_level_t& L = levels_host[l];
+        DET_CHECK_ARG(L.objectness && L.deltas && L.cell_anchors && L.h >= 0 && L.w >= 0 && L.out_offset >= 0, "bad level");
+        const int64_t hw = (int64_t)L.h * L.w;
+        DET_CHECK_ARG(out_img_stride >= L.out_offset + hw * a, "output slot out of range");
+        const bool flat = flat_ok && f.num_levels < kRpnFlatMaxLevels && hw % 4 == 0 && hw < (1ll << 30) &&
+                          aligned16(L.objectness) && aligned16(L.deltas) && aligned16(L.cell_anchors);
+        if (!flat) {  // this level takes its own launch: same results
+            const int rc = det_rpn_decode_level(L.objectness, L.deltas, n, a, L.h, L.w, L.stride, offset, L.cell_anchors, wx,
+                                                wy, ww, wh, scale_clamp, logits_out, boxes_out, out_img_stride,
+                                                L.out_offset, stream);
+            if (rc != DET_OK) return rc;
+            continue;
+        }
+        RpnLevelDev& D = f.lv[f.num_levels];
+        f.tile_begin[f.num_levels] = tb;
+        D.obj = L.objectness; D.deltas = L.deltas; D.cell = reinterpret_cast<const float4*>(L.cell_anchors);
+        D.w = L.w > 0 ? L.w : 1; D.hw = L.h * L.w; D.tiles = (D.hw + kRpnTilePos - 1) / kRpnTilePos;
+        D.stride = L.stride; D.stride_unused = 0.f; D.out_offset = L.out_offset;
+        tb += (long long)n * D.tiles;
+        ++f.num_levels;
+    }
+    for (int l = f.num_levels; l < kRpnFlatMaxLevels; ++l) {
+        RpnLevelDev& D = f.lv[l];
+        D.obj = nullptr; D.deltas = nullptr; D.cell = nullptr; D.w = 1; D.hw = 0; D.tiles = 1; D.stride = 0;
+        D.stride_unused = 0.f; D.out_offset = 0;
+    }
+    for (int l = f.num_levels; l <= kRpnFlatMaxLevels; ++l) f.tile_begin[l] = tb;
+    if (tb == 0) return DET_OK;
+    const long long blocks = (tb + kRpnFlatWarps - 1) / kRpnFlatWarps;
+    DET_CHECK_ARG(blocks < (1ll << 31), "too many positions");
+    const size_t smem = (size_t)kRpnFlatWarps * kRpnTilePos * a * (sizeof(float4) + sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(rpn_decode_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rpn_decode_flat_kernel)");
+    rpn_decode_flat_kernel<<<(unsigned)blocks, kRpnFlatWarps * 32, smem, as_stream(stream)>>>(f);
+    DET_LAUNCH_OK("rpn_decode_flat_kernel");
     return DET_OK;
 }
 

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "det_grid_anchors": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     "det_rpn_decode_level": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_f, c_f, c_f, c_f, c_f, c_p, c_p,
                                    c_l, c_l, c_p]),
+    "det_rpn_decode": (c_i, [c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_l, c_p]),
     "det_nms_workspace_bytes": (c_l, [c_i, c_l]),
     "det_nms_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_l, c_d, c_i, c_l, c_p, c_p, c_p, c_l, c_p]),
     "det_rpn_proposals_workspace_bytes": (c_l, [c_i, c_l]),
@@ -61,6 +62,12 @@ PROTOTYPES = {
 class DenseLevel(ctypes.Structure):
     """det_dense_level_t of include/det_b200.h"""
     _fields_ = [("head", c_p), ("anchors_wh", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_offset", c_l)]
+
+
+class RpnLevel(ctypes.Structure):
+    """det_rpn_level_t of include/det_b200.h"""
+    _fields_ = [("objectness", c_p), ("deltas", c_p), ("cell_anchors", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_offset", c_l)]
 
 

@@ -8,6 +8,8 @@ NCHW outputs.  Two API levels:
 import math
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
+import ctypes
+
 import torch
 
 from . import _native as N
@@ -104,11 +106,25 @@ class RegionProposalNetwork:
         R = sum(sizes)
         logits = torch.empty((n, R), dtype=torch.float32, device=dev)
         boxes = torch.empty((n, R, 4), dtype=torch.float32, device=dev)
-        off = 0
         w = self.box2box_transform.weights
+        ocs, dcs = [N.f32c(o) for o in pred_objectness], [N.f32c(d) for d in pred_deltas]
+        na = ocs[0].shape[1]
+        if all(o.shape[1] == na for o in ocs):  # one launch for the whole pyramid (det_rpn_decode)
+            lv = (N.RpnLevel * len(ocs))()
+            off = 0
+            for i, (oc, dc, cell, stride, sz) in enumerate(zip(ocs, dcs, cells, self.anchor_generator.strides, sizes)):
+                assert dc.shape[1] == na * 4 and na == cell.shape[0]
+                lv[i].objectness, lv[i].deltas, lv[i].cell_anchors = oc.data_ptr(), dc.data_ptr(), cell.data_ptr()
+                lv[i].h, lv[i].w, lv[i].stride, lv[i].reserved, lv[i].out_offset = oc.shape[2], oc.shape[3], int(stride), 0, off
+                off += sz
+            with torch.cuda.device(dev):
+                N.call("det_rpn_decode", ctypes.cast(lv, ctypes.c_void_p), len(ocs), n, na,
+                       float(self.anchor_generator.offset), *w, self.box2box_transform.scale_clamp, N.ptr(logits),
+                       N.ptr(boxes), R, N.stream())
+            return logits, boxes, sizes
+        off = 0
         with torch.cuda.device(dev):
-            for o, d, cell, stride, sz in zip(pred_objectness, pred_deltas, cells, self.anchor_generator.strides, sizes):
-                oc, dc = N.f32c(o), N.f32c(d)
+            for oc, dc, cell, stride, sz in zip(ocs, dcs, cells, self.anchor_generator.strides, sizes):
                 a, h, wd = oc.shape[1], oc.shape[2], oc.shape[3]
                 assert dc.shape[1] == a * 4 and a == cell.shape[0]
                 N.call("det_rpn_decode_level", N.ptr(oc), N.ptr(dc), n, a, h, wd, int(stride),

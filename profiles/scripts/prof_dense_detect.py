@@ -15,6 +15,7 @@ wh = [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90
 dh = det.DenseAnchorHead(strides, wh, C)
 peak, _ = load_peaks()
 dev = torch.device("cuda")
+torch.zeros(1, device=dev)
 for n in ns:
     g = torch.Generator(device=dev).manual_seed(3)
     pool = 1 if once else (2 if n > 64 else 4)
