@@ -751,7 +751,10 @@ static int large_nms_run(const LargeLayout& lay, void* workspace, const float* b
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     // top-k tier: when max_out is a small part of the image, sweep the best-scored boxes first (see
     // large_topk_select_kernel); images that get their max_out survivors there skip everything below
-    const int64_t want = max_out + (max_out >> 2) + 32;
+    // the list holds twice the first tier (capped): list_nms_kernel sweeps the best 1.25 * max_out + 32 of it first and
+    // the whole list if those fall short (low survival, e.g. one category), before an image goes to the full path
+    const int64_t tier1 = max_out + (max_out >> 2) + 32;
+    const int64_t want = tier1 * 2 < kTierMaxWant ? tier1 * 2 : (tier1 < kTierMaxWant ? kTierMaxWant : tier1);
     const int32_t* todo = nullptr;
     if (max_out >= 1 && want <= kTierMaxWant && want + (want >> 1) <= lay.m_max) {
         large_topk_select_kernel<<<n, 1024, 0, st>>>(b4, scores, cats, counts, lay.m_max, mode, (int)want, ws.tier_count,

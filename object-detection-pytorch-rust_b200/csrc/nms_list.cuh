@@ -71,7 +71,7 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
     // with the cut included).  max_det survivors there are the answer; otherwise everything is swept.  The
     // reference's branch rule and the offset trick's span are defined on ALL candidates: FullStats carries them.
     const int want_sub = cap_out + (cap_out >> 2) + 32;
-    for (int tier = (!ext_full && cnt >= want_sub + (want_sub >> 1)) ? 0 : 1; tier < 2; ++tier) {
+    for (int tier = (cnt >= want_sub + (want_sub >> 1)) ? 0 : 1; tier < 2; ++tier) {
         int m = cnt;
         const FullStats* fs = ext_full ? ext_full + img : nullptr;
         if (tier == 0) {
@@ -158,7 +158,7 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
             }
             __syncthreads();
             m = sm.sub_count;
-            fs = &sm.full;
+            if (!ext_full) fs = &sm.full;  // external tier: the statistics of the whole image came with the list
             src.perm = sm.perm;
         } else {
             src.perm = nullptr;
