@@ -341,12 +341,27 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 }
 __device__ __forceinline__ uint32_t sample_key(uint32_t img_seed, uint32_t j) { return mix32(j * 0x9E3779B1u + img_seed); }
 
+// b-bit bijection (odd multiplies and right xor-shifts are invertible mod 2^b): k -> a pseudo-random permutation of
+// [0, 2^b).  Walking k = 0, 1, 2, ... and keeping the first `want` indices that fall inside the row and carry the class
+// label IS a uniformly random `want`-subset of the class -- in O(want / density) steps instead of one hash per anchor.
+// Used for a DENSE class (the background of an RPN image: ~98 % of the anchors, 128-256 wanted).
+__device__ __forceinline__ uint32_t perm_bits(uint32_t k, uint32_t s0, int b) {
+    const uint32_t mask = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+    const int h = (b + 1) >> 1;
+    uint32_t x = (k * 0x9E3779B1u + s0) & mask;
+    x ^= x >> h; x = (x * 0x7FEB352Du) & mask;
+    x ^= x >> h; x = (x * 0x846CA68Bu) & mask;
+    x ^= x >> h;
+    return x;
+}
+
 constexpr int kSampleThreads = 512;
 constexpr int kCandCap = 1024;
 
 struct SampleSmem {
     int cnt[2];
     int ncand[2];
+    int walk_total, walk_warp[kSampleThreads / 32];
     unsigned sel[2];      // the want-th smallest key of the class: keys <= sel are kept
     unsigned prefix[2];   // radix-select fallback state
     int remaining[2];
@@ -444,6 +459,15 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
         thr[c] = p >= 1.0 ? 0xffffffffu : (unsigned)(p * 4294967296.0);
         direct[c] = need[c] && want[c] > 0 && (double)want[c] + 2.0 * slack <= (double)kCandCap && r < (1 << 24);
     }
+    // a dense class is sampled by walking a random permutation of the row instead of hashing every anchor
+    bool walk[2];
+    int pbits = 1;
+    while ((1ll << pbits) < r) ++pbits;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        walk[c] = need[c] && want[c] > 0 && want[c] <= kCandCap && r < (1 << 24) && (int64_t)have[c] * 8 >= r;
+        if (walk[c]) direct[c] = false;
+    }
     if (direct[0] || direct[1]) {
         for (int c = tid; c < rv.ngran; c += kSampleThreads) {
             const uint4 q = rv.load(c);
@@ -466,14 +490,51 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
         }
     }
     __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (!walk[c]) continue;
+        const uint32_t s0 = mix32(img_seed + 0x51ED270Bu * (uint32_t)(c + 1));
+        const int lane = tid & 31, wid = tid >> 5;
+        int total = 0;  // accepted so far (block-uniform)
+        for (uint32_t k0 = 0; total < want[c] && k0 < (1u << pbits); k0 += kSampleThreads) {
+            const uint32_t j = perm_bits(k0 + (uint32_t)tid, s0, pbits);
+            int8_t l = -1;
+            bool ok = false;
+            if ((int64_t)j < r) {
+                l = rv.row[j];
+                ok = label_class(l) == c;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) sm.walk_warp[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, round_total = 0;
+            for (int w = 0; w < kSampleThreads / 32; ++w) {
+                const int v = sm.walk_warp[w];
+                before += (w < wid) ? v : 0;
+                round_total += v;
+            }
+            const int slot = total + before + __popc(bal & ((1u << lane) - 1u));  // rank in walk order
+            if (ok && slot < want[c]) {
+                sm.ckey[c][slot] = 0u;
+                sm.cidx[c][slot] = (int)j | ((int)(uint8_t)l << 24);
+            }
+            total += round_total;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            sm.ncand[c] = want[c];
+            sm.sel[c] = 0u;  // every listed candidate (key 0) is restored after the wholesale wipe
+        }
+    }
+    __syncthreads();
     // ---- pass C: the want-th smallest key, by rank counting among the candidates
     bool radix[2], listed[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const int nc = sm.ncand[c];
-        listed[c] = direct[c] && nc >= want[c] && nc <= kCandCap;
+        listed[c] = walk[c] || (direct[c] && nc >= want[c] && nc <= kCandCap);
         radix[c] = need[c] && want[c] > 0 && !listed[c];
-        if (listed[c]) {
+        if (listed[c] && !walk[c]) {
             for (int t = tid; t < nc; t += kSampleThreads) {
                 const unsigned key = sm.ckey[c][t];
                 int rank = 0;

@@ -109,6 +109,42 @@ def test_device_subsample_counts_and_uniformity(det, O):
     assert abs(float(frac.mean()) - 128 / 300) < 1e-6 and float(frac.min()) > 0.25 and float(frac.max()) < 0.6
 
 
+def test_device_subsample_dense_class_walks_a_permutation(det, O):
+    """A class that holds >= 1/8 of the anchors (RPN background) is sampled by walking a pseudo-random permutation of the
+    row: exact counts, subset of the class, reproducible, and uniform over the class."""
+    g = gen(9)
+    n, r = 4, 2048
+    lab = torch.full((n, r), -1, dtype=torch.int8)
+    npos, nneg = [10, 700, 0, 300], [1500, 1300, 2048, 256]
+    for i in range(n):
+        perm = torch.randperm(r, generator=g)
+        lab[i, perm[:npos[i]]] = 1
+        lab[i, perm[npos[i]:npos[i] + nneg[i]]] = 0
+    out = det.subsample_labels_(lab.cuda().clone(), 256, 0.5, seed=5).cpu()
+    for i in range(n):
+        wp, wn = O.subsample_counts(npos[i], nneg[i], 256, 0.5)
+        assert int((out[i] == 1).sum()) == wp and int((out[i] == 0).sum()) == wn, i
+        assert bool(((out[i] == 1) <= (lab[i] == 1)).all()) and bool(((out[i] == 0) <= (lab[i] == 0)).all())
+    again = det.subsample_labels_(lab.cuda().clone(), 256, 0.5, seed=5).cpu()
+    assert torch.equal(out, again)
+    hits = torch.zeros(r)
+    row = lab[0:1].cuda()  # 1500 negatives, 246 kept
+    trials = 300
+    for s in range(trials):
+        hits += (det.subsample_labels_(row.clone(), 256, 0.5, seed=1000 + s)[0].cpu() == 0).float()
+    frac = hits[lab[0] == 0] / trials
+    p = 246 / 1500
+    assert abs(float(frac.mean()) - p) < 1e-6
+    assert float(frac.min()) > p - 0.1 and float(frac.max()) < p + 0.1  # +-4.7 sigma of a binomial(300, p) frequency
+    # pairs of anchors are not tied together: neighbouring negatives are kept together ~ p^2 of the time
+    neg = torch.nonzero(lab[0] == 0, as_tuple=True)[0]
+    both = 0
+    for s in range(trials):
+        o = det.subsample_labels_(row.clone(), 256, 0.5, seed=5000 + s)[0].cpu()
+        both += int(((o[neg[:-1]] == 0) & (o[neg[1:]] == 0)).sum())
+    assert abs(both / (trials * (neg.numel() - 1)) - p * p) < 0.01
+
+
 def _rpn_loss_case(O, n, seed, beta=0.0):
     g = gen(seed)
     anc = _anchors(O)
