@@ -264,6 +264,25 @@ DET_API int det_roi_align_levels_backward(const det_feature_level_t* grad_levels
                                   int out_h, int out_w, int sampling_ratio, int aligned, const float* grad_out,
                                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * (e) the training path's one collective over NVLink peer memory instead of NCCL: SUM of the `width`-float loss/count
+ *     vector (the sums the reference logs per step, python/src/models/rpn.py:216-220, 238-241) over `world` ranks.
+ *     Every rank owns a buffer of slots * world * 16 floats that is mapped into every peer (symmetric memory);
+ *     peers_dev = device array of the `world` buffer base pointers as seen from this rank.
+ *     publish: store this rank's vector + the step stamp into record [slot][rank] of every peer's buffer.
+ *     collect: wait until all `world` records of [slot] in the LOCAL buffer carry `stamp`, write their sum (rank
+ *     order) to out.  A wait longer than timeout_ns writes NaN and sets *error_flag (may be NULL) -- never hangs.
+ *     Issue publish(t), collect(t - 1) in stream order with slots >= 4 (csrc/peer.cu explains the slot reuse).
+ * ---------------------------------------------------------------------------------------------------------- */
+DET_API int det_peer_sums_publish(const float* sums, int width, int rank, int world, const void* peers_dev, int slots,
+                          int slot, uint32_t stamp, void* stream);
+DET_API int det_peer_sums_collect(float* out, int width, int world, const float* local_buf, int slots, int slot,
+                          uint32_t stamp, int64_t timeout_ns, int32_t* error_flag, void* stream);
+/* both in one launch per training step: publish step `stamp` (slot stamp % slots), then collect step stamp - lag into
+ * out (nothing is collected while stamp <= lag). */
+DET_API int det_peer_sums_exchange(const float* sums, float* out, int width, int rank, int world, const void* peers_dev,
+                           int slots, uint32_t stamp, uint32_t lag, int64_t timeout_ns, int32_t* error_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,9 @@ PROTOTYPES = {
     "det_dense_detect_workspace_bytes": (c_l, [c_i, c_l]),
     "det_dense_detect": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_d, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p,
                                c_p, c_l, c_p]),
+    "det_peer_sums_publish": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_p]),
+    "det_peer_sums_collect": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_l, c_p, c_p]),
+    "det_peer_sums_exchange": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.c_uint32, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_roi_levels": (c_i, [c_p, c_l, c_i, c_i, c_f, c_i, c_p, c_p]),
     "det_roi_align_levels": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "det_roi_align_levels_backward": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),

@@ -145,6 +145,46 @@ def test_device_subsample_dense_class_walks_a_permutation(det, O):
     assert abs(both / (trials * (neg.numel() - 1)) - p * p) < 0.01
 
 
+def test_peer_sums_protocol_on_one_gpu(det):
+    """det_peer_sums_publish / collect (csrc/peer.cu) with two VIRTUAL ranks whose "peer" buffers live on one GPU: every
+    rank's record lands in every buffer, the sum is taken in rank order, stamps gate the read, a missing peer times out
+    with NaN + error flag instead of hanging."""
+    import det_b200._native as N
+    dev = torch.device("cuda")
+    world, slots, width = 2, 8, 8
+    bufs = [torch.zeros(slots * world * 16, device=dev) for _ in range(world)]
+    peers = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    g = gen(4)
+    for step in range(1, 20):
+        vecs = [torch.randn(width, generator=g).to(dev) for _ in range(world)]
+        for r in range(world):
+            N.call("det_peer_sums_publish", N.ptr(vecs[r]), width, r, world, N.ptr(peers), slots, step % slots, step,
+                   N.stream())
+        for r in range(world):
+            out = torch.empty(width, device=dev)
+            N.call("det_peer_sums_collect", N.ptr(out), width, world, N.ptr(bufs[r]), slots, step % slots, step,
+                   10 ** 9, N.ptr(err), N.stream())
+            assert torch.equal(out, vecs[0] + vecs[1])  # rank order, fp32: bitwise the same on every rank
+    assert int(err.item()) == 0
+    # rank 1 never publishes step 20: the collect gives up after 20 ms
+    N.call("det_peer_sums_publish", N.ptr(vecs[0]), width, 0, world, N.ptr(peers), slots, 20 % slots, 20, N.stream())
+    out = torch.zeros(width, device=dev)
+    N.call("det_peer_sums_collect", N.ptr(out), width, world, N.ptr(bufs[0]), slots, 20 % slots, 20, 20_000_000,
+           N.ptr(err), N.stream())
+    assert int(err.item()) == 1 and bool(torch.isnan(out).all())
+    # the single-process PeerSums wrapper (world 1) returns what was published, one step late
+    ps = det.dist.PeerSums(dev)
+    a, b = torch.arange(8.0, device=dev), torch.ones(8, device=dev)
+    ps.publish(a); ps.publish(b)
+    assert torch.equal(ps.collect(), a) and torch.equal(ps.collect(), b)
+    ps.check()
+    px = det.dist.PeerSums(dev)  # one launch per step: publish(t) + collect(t - 1)
+    assert px.exchange(a) is None
+    assert torch.equal(px.exchange(b), a) and torch.equal(px.exchange(a + b), b) and torch.equal(px.flush(), a + b)
+    px.check()
+
+
 def _rpn_loss_case(O, n, seed, beta=0.0):
     g = gen(seed)
     anc = _anchors(O)
