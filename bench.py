@@ -306,6 +306,26 @@ def extras_train(det, dev, world, peak, quick):
                                "images_per_s_per_gpu": n / ms * 1e3,
                                "collective": "8-float all-reduce every step, waited for one step late",
                                "ms_per_step_reduce_every_16": ms16, "images_per_s_per_gpu_reduce_every_16": n / ms16 * 1e3}
+    # the same all-reduce every step through NVLink peer memory (det_b200.dist.PeerSums, csrc/peer.cu): one tiny launch
+    # per step publishes this step's sums into every peer's symmetric buffer and collects the previous step's
+    try:
+        ps = det.dist.PeerSums(dev)
+
+        def step_grid_peer():
+            h = heads[state["i"] % pool]
+            state["i"] += 1
+            asg = tr.assign_packed(gtb, off, n)
+            res = tr.loss(h, asg, gtc, with_grads=True)
+            ps.exchange(res["sums"])
+
+        ms_p = time_region(step_grid_peer, 30 if quick else 200)
+        ps.flush()
+        ps.check()
+        out["train_grid_b1024"].update({"ms_per_step_peer_exchange": ms_p, "images_per_s_per_gpu_peer_exchange": n / ms_p * 1e3,
+                                        "peer_exchange": "det_peer_sums_exchange: P2P stores into every rank's symmetric "
+                                                         "buffer + step stamps, no NCCL launch"})
+    except Exception as e:  # noqa: BLE001
+        out["train_grid_b1024"]["peer_exchange_error"] = f"{type(e).__name__}: {e}"
     # (ii) reference-native RPN form: R = 50127 anchors (FPN-18 @ 448), Matcher([0.3,0.7]), 256 samples, L1 + BCE
     rpn = det.RegionProposalNetwork([4, 8, 16, 32, 64])
     anchors = torch.cat(rpn.anchor_generator.grid_anchors([(448 // s, 448 // s) for s in (4, 8, 16, 32, 64)], dev), 0)
