@@ -278,6 +278,22 @@ DET_API int det_peer_sums_publish(const float* sums, int width, int rank, int wo
                           int slot, uint32_t stamp, void* stream);
 DET_API int det_peer_sums_collect(float* out, int width, int world, const float* local_buf, int slots, int slot,
                           uint32_t stamp, int64_t timeout_ns, int32_t* error_flag, void* stream);
+/* compute + collective in ONE kernel: det_yolo_loss whose last CTA publishes the batch's sums (the raw `sums` vector,
+ * `width` <= 8 floats) as step `stamp` and collects step stamp - lag into `out`.  done_counter: device int32, zero
+ * before the first use (the kernel resets it). */
+typedef struct det_peer_ctx {
+    const void* peers_dev;
+    float* out;
+    int32_t* error_flag;
+    int32_t* done_counter;
+    int64_t timeout_ns;
+    int32_t width, rank, world, slots;
+    uint32_t stamp, lag;
+} det_peer_ctx_t;
+DET_API int det_yolo_loss_peer(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
+                       const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
+                       int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
+                       const float* upstream, float* sums, float* grad_head, const det_peer_ctx_t* peer, void* stream);
 /* both in one launch per training step: publish step `stamp` (slot stamp % slots), then collect step stamp - lag into
  * out (nothing is collected while stamp <= lag). */
 DET_API int det_peer_sums_exchange(const float* sums, float* out, int width, int rank, int world, const void* peers_dev,

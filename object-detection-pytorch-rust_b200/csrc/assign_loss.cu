@@ -9,6 +9,7 @@
 // The (G,R) IoU matrix, the (N,R,4) matched-gt tensor and the (N,R,4) target-delta tensor of the reference are
 // never materialised: IoUs are recomputed from the box tables, targets are encoded on the fly for positives only.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace det {
 
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__(kYoloLossThreads)
 yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labels, const int64_t* __restrict__ matched,
                  const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
                  const float2* __restrict__ priors, YoloLossParams prm, int imgs, const float* __restrict__ upstream,
-                 float* __restrict__ sums, float* __restrict__ grad_head) {
+                 float* __restrict__ sums, float* __restrict__ grad_head, const PeerCtxDev peer) {
     extern __shared__ __align__(16) float s_tile[];
     __shared__ float s_part[5][kYoloLossThreads / 32];
     const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
@@ -924,6 +925,9 @@ yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labe
         for (int w = 0; w < kYoloLossThreads / 32; ++w) t += s_part[threadIdx.x][w];
         if (t != 0.f) atomicAdd(&sums[threadIdx.x], t);
     }
+    // compute + collective in one kernel: the last CTA publishes the batch's sums into every peer's buffer over NVLink
+    // and collects the previous step's world sum (peer.cuh)
+    if (peer.enabled) peer_exchange_from_last_cta(peer, sums);
 }
 
 // heads too large for the shared-memory tile: one thread per (image, cell) straight from global memory
@@ -1126,10 +1130,11 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
     return DET_OK;
 }
 
-int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
-                  const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
-                  int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                  const float* upstream, float* sums, float* grad_head, void* stream) {
+static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
+                          const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
+                          int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
+                          const float* upstream, float* sums, float* grad_head, void* stream,
+                          const det_peer_ctx_t* peer) {
     DET_CHECK_ARG(n >= 0 && s >= 1 && b >= 1 && c >= 0, "bad size");
     if (n == 0) return DET_OK;
     DET_CHECK_ARG(head && labels && matched_idx && gt_offsets && priors && sums, "null pointer");
@@ -1145,6 +1150,21 @@ int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matche
     const int per_img = s * s * (b * 5 + c);
     auto g4 = reinterpret_cast<const float4*>(gt_boxes);
     auto p2 = reinterpret_cast<const float2*>(priors);
+    PeerCtxDev pc;
+    pc.enabled = 0;
+    if (peer) {
+        DET_CHECK_ARG(peer->peers_dev && peer->out && peer->done_counter, "peer context: null pointer");
+        DET_CHECK_ARG(peer->width >= 1 && peer->width <= 8, "peer context: width must be in [1, 8] (the sums vector)");
+        DET_CHECK_ARG(peer->world >= 1 && peer->world <= kPeerMaxWorld && peer->rank >= 0 && peer->rank < peer->world,
+                      "peer context: bad rank / world");
+        DET_CHECK_ARG(peer->slots >= 4 && peer->lag >= 1 && (int)peer->lag <= peer->slots - 3 && peer->timeout_ns > 0,
+                      "peer context: slots >= 4, 1 <= lag <= slots - 3");
+        DET_CHECK_ARG(per_img <= kYoloLossTile, "peer context: only the shared-memory-tile kernel publishes");
+        pc.peers = reinterpret_cast<float* const*>(peer->peers_dev); pc.out = peer->out;
+        pc.error_flag = peer->error_flag; pc.done_counter = peer->done_counter; pc.timeout_ns = peer->timeout_ns;
+        pc.width = peer->width; pc.rank = peer->rank; pc.world = peer->world; pc.slots = peer->slots;
+        pc.stamp = peer->stamp; pc.lag = peer->lag; pc.enabled = 1;
+    }
     if (per_img <= kYoloLossTile) {
         int imgs = kYoloLossTile / per_img;
         // enough CTAs to fill the GPU first, then as many images per CTA as the tile holds
@@ -1152,7 +1172,7 @@ int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matche
         if (imgs > fill) imgs = fill < 1 ? 1 : fill;
         const size_t smem = 2 * sizeof(float) * (size_t)((imgs * per_img + 3) & ~3);
         yolo_loss_kernel<<<(unsigned)((n + imgs - 1) / imgs), kYoloLossThreads, smem, as_stream(stream)>>>(
-            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, imgs, upstream, sums, grad_head);
+            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, imgs, upstream, sums, grad_head, pc);
     } else {
         const int64_t cells = (int64_t)n * s * s;
         yolo_loss_direct_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, as_stream(stream)>>>(
@@ -1160,6 +1180,24 @@ int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matche
     }
     DET_LAUNCH_OK("yolo_loss_kernel");
     return DET_OK;
+}
+
+int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
+                  const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
+                  int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
+                  const float* upstream, float* sums, float* grad_head, void* stream) {
+    return yolo_loss_impl(head, labels, matched_idx, gt_boxes, gt_classes, gt_offsets, n, s, b, c, img_h, img_w, priors,
+                          lambda_coord, lambda_noobj, grad_scale, upstream, sums, grad_head, stream, nullptr);
+}
+
+int det_yolo_loss_peer(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
+                       const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
+                       int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
+                       const float* upstream, float* sums, float* grad_head, const det_peer_ctx_t* peer, void* stream) {
+    DET_CHECK_ARG(peer, "null peer context");
+    DET_CHECK_ARG(n >= 1, "the publishing kernel needs a non-empty batch");
+    return yolo_loss_impl(head, labels, matched_idx, gt_boxes, gt_classes, gt_offsets, n, s, b, c, img_h, img_w, priors,
+                          lambda_coord, lambda_noobj, grad_scale, upstream, sums, grad_head, stream, peer);
 }
 
 }  // extern "C"

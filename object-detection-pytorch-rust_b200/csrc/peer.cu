@@ -12,63 +12,9 @@
 // stamp in place; a spin that outlasts `timeout_ns` (a dead peer) writes NaNs, raises *error_flag and returns instead
 // of hanging the GPU.  Slot reuse is safe for slots >= 4 when every rank issues publish(t), collect(t-1) in stream
 // order: a rank can only run ahead of a peer by collecting, which needs that peer's publish.
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace det {
-
-constexpr int kPeerRecordWords = 16;
-constexpr int kPeerStampWord = 15;
-constexpr int kPeerMaxWidth = 12;
-constexpr int kPeerMaxWorld = 32;
-
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-__device__ __forceinline__ void peer_publish(const float* __restrict__ sums, int width, int rank, int world,
-                                             float* const* __restrict__ peers, int slot, uint32_t stamp) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    float* rec = peers[r] + ((int64_t)slot * world + rank) * kPeerRecordWords;
-    for (int i = 0; i < width; ++i) rec[i] = sums[i];
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t*>(rec + kPeerStampWord) = stamp;
-}
-
-__device__ __forceinline__ void peer_collect(float* __restrict__ out, int width, int world, const float* __restrict__ local,
-                                             int slot, uint32_t stamp, long long timeout_ns,
-                                             int32_t* __restrict__ error_flag) {
-    __shared__ float s_val[kPeerMaxWorld][kPeerMaxWidth];
-    __shared__ int s_bad;
-    const int r = threadIdx.x;
-    if (r == 0) s_bad = 0;
-    __syncwarp();
-    if (r < world) {
-        const float* rec = local + ((int64_t)slot * world + r) * kPeerRecordWords;
-        const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(rec + kPeerStampWord);
-        const unsigned long long t0 = global_timer_ns();
-        bool ok = true;
-        while (*flag != stamp) {
-            if ((long long)(global_timer_ns() - t0) > timeout_ns) {
-                ok = false;
-                break;
-            }
-            __nanosleep(200);
-        }
-        __threadfence_system();
-        for (int i = 0; i < width; ++i) s_val[r][i] = ok ? *reinterpret_cast<const volatile float*>(rec + i) : NAN;
-        if (!ok) s_bad = 1;
-    }
-    __syncwarp();
-    if (r < width) {
-        float acc = 0.0f;
-        for (int q = 0; q < world; ++q) acc += s_val[q][r];  // rank order: the same bits on every rank
-        out[r] = acc;
-    }
-    if (r == 0 && s_bad && error_flag) *error_flag = 1;
-}
 
 __global__ void __launch_bounds__(32)
 peer_sums_publish_kernel(const float* __restrict__ sums, int width, int rank, int world, float* const* __restrict__ peers,

@@ -1,0 +1,98 @@
+// Device side of the peer-memory exchange (see peer.cu for the protocol): shared by the stand-alone kernels of peer.cu and
+// by the loss kernels that publish their sums from their last CTA (assign_loss.cu).
+#pragma once
+#include "common.cuh"
+
+namespace det {
+
+constexpr int kPeerRecordWords = 16;
+constexpr int kPeerStampWord = 15;
+constexpr int kPeerMaxWidth = 12;
+constexpr int kPeerMaxWorld = 32;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void peer_publish(const float* __restrict__ sums, int width, int rank, int world,
+                                             float* const* __restrict__ peers, int slot, uint32_t stamp) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    float* rec = peers[r] + ((int64_t)slot * world + rank) * kPeerRecordWords;
+    for (int i = 0; i < width; ++i) rec[i] = sums[i];
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(rec + kPeerStampWord) = stamp;
+}
+
+__device__ __forceinline__ void peer_collect(float* __restrict__ out, int width, int world, const float* __restrict__ local,
+                                             int slot, uint32_t stamp, long long timeout_ns,
+                                             int32_t* __restrict__ error_flag) {
+    __shared__ float s_val[kPeerMaxWorld][kPeerMaxWidth];
+    __shared__ int s_bad;
+    const int r = threadIdx.x;
+    if (r == 0) s_bad = 0;
+    __syncwarp();
+    if (r < world) {
+        const float* rec = local + ((int64_t)slot * world + r) * kPeerRecordWords;
+        const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(rec + kPeerStampWord);
+        const unsigned long long t0 = global_timer_ns();
+        bool ok = true;
+        while (*flag != stamp) {
+            if ((long long)(global_timer_ns() - t0) > timeout_ns) {
+                ok = false;
+                break;
+            }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+        for (int i = 0; i < width; ++i) s_val[r][i] = ok ? *reinterpret_cast<const volatile float*>(rec + i) : NAN;
+        if (!ok) s_bad = 1;
+    }
+    __syncwarp();
+    if (r < width) {
+        float acc = 0.0f;
+        for (int q = 0; q < world; ++q) acc += s_val[q][r];  // rank order: the same bits on every rank
+        out[r] = acc;
+    }
+    if (r == 0 && s_bad && error_flag) *error_flag = 1;
+}
+
+// launch parameters of a fused publish + collect (mirrors det_peer_ctx_t; enabled == 0: nothing to do)
+struct PeerCtxDev {
+    float* const* peers;
+    float* out;
+    int32_t* error_flag;
+    int32_t* done_counter;
+    long long timeout_ns;
+    int width, rank, world, slots;
+    uint32_t stamp, lag;
+    int enabled;
+};
+
+// Called by EVERY CTA of a kernel after its atomicAdd()s into `sums`: the CTA that arrives last sees the final sums,
+// publishes them as step `stamp` and collects step `stamp - lag` (warp 0).  The counter resets itself.
+__device__ __forceinline__ void peer_exchange_from_last_cta(const PeerCtxDev& pc, const float* sums) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(pc.done_counter, 1);
+        s_last = (ticket == (int)(gridDim.x * gridDim.y) - 1) ? 1 : 0;
+        if (s_last) *pc.done_counter = 0;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    __shared__ float s_sums[kPeerMaxWidth];
+    if ((int)threadIdx.x < pc.width) s_sums[threadIdx.x] = __ldcg(sums + threadIdx.x);  // final values live in L2
+    __syncwarp();
+    peer_publish(s_sums, pc.width, pc.rank, pc.world, pc.peers, (int)(pc.stamp % (uint32_t)pc.slots), pc.stamp);
+    __syncwarp();
+    if (pc.stamp > pc.lag)
+        peer_collect(pc.out, pc.width, pc.world, pc.peers[pc.rank], (int)((pc.stamp - pc.lag) % (uint32_t)pc.slots),
+                     pc.stamp - pc.lag, pc.timeout_ns, pc.error_flag);
+}
+
+}  // namespace det

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "det_peer_sums_publish": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_p]),
     "det_peer_sums_collect": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_peer_sums_exchange": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.c_uint32, ctypes.c_uint32, c_l, c_p, c_p]),
+    "det_yolo_loss_peer": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
+                                 c_p, c_p, c_p]),
     "det_roi_levels": (c_i, [c_p, c_l, c_i, c_i, c_f, c_i, c_p, c_p]),
     "det_roi_align_levels": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "det_roi_align_levels_backward": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
@@ -72,6 +74,13 @@ class RpnLevel(ctypes.Structure):
     """det_rpn_level_t of include/det_b200.h"""
     _fields_ = [("objectness", c_p), ("deltas", c_p), ("cell_anchors", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_offset", c_l)]
+
+
+class PeerCtx(ctypes.Structure):
+    """det_peer_ctx_t of include/det_b200.h"""
+    _fields_ = [("peers_dev", c_p), ("out", c_p), ("error_flag", c_p), ("done_counter", c_p), ("timeout_ns", c_l),
+                ("width", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("slots", ctypes.c_int32),
+                ("stamp", ctypes.c_uint32), ("lag", ctypes.c_uint32)]
 
 
 class FeatureLevel(ctypes.Structure):

@@ -170,6 +170,25 @@ class PeerSums:
         self._collected = self.step
         return out if self.step > 1 else None
 
+    def fused_ctx(self):
+        """Context for a kernel that publishes from its own last CTA (det_yolo_loss_peer): advances the step like
+        exchange() and returns (det_peer_ctx_t, out) -- `out` receives the previous step's world sum of the RAW sums
+        vector (None on the first step), valid in stream order after that kernel."""
+        N = self._N
+        assert self._collected == self.step, "do not mix the fused path with publish() / collect()"
+        if not hasattr(self, "_done"):
+            self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.step += 1
+        out = self._out[self.step & 1]
+        ctx = N.PeerCtx()
+        ctx.peers_dev, ctx.out = self.peers.data_ptr(), out.data_ptr()
+        ctx.error_flag, ctx.done_counter = self.error.data_ptr(), self._done.data_ptr()
+        ctx.timeout_ns = self.timeout_ns
+        ctx.width, ctx.rank, ctx.world, ctx.slots = self.width, self.rank, self.world, self.SLOTS
+        ctx.stamp, ctx.lag = self.step & 0xffffffff, 1
+        self._collected = self.step
+        return ctx, (out if self.step > 1 else None)
+
     def flush(self) -> torch.Tensor:
         """World sum of the latest published vector (end of training / before logging the last step)."""
         N = self._N

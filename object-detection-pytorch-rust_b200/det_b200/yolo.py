@@ -214,15 +214,22 @@ class YoloGridTrainer:
         matched, labels = self.matcher.match_packed(gt_table, gt_offsets, n, self.prior_boxes(gt_table.device))
         return YoloAssignment(labels, matched, gt_table, gt_offsets)
 
-    def _run_loss(self, head_t, asg, gt_classes, norm, upstream, grad_head):
+    def _run_loss(self, head_t, asg, gt_classes, norm, upstream, grad_head, peer=None):
         h = self.head
         n = head_t.shape[0]
         sums = torch.zeros((8,), dtype=torch.float32, device=head_t.device)
+        self._world_prev = None
         with torch.cuda.device(head_t.device):
-            N.call("det_yolo_loss", N.ptr(head_t), N.ptr(asg.labels), N.ptr(asg.matched), N.ptr(asg.gt_table),
-                   N.ptr(gt_classes), N.ptr(asg.gt_offsets), n, h.S, h.B, h.C, h.image_size[0], h.image_size[1],
-                   N.ptr(h.priors_on(head_t.device)), self.lambda_coord, self.lambda_noobj, 1.0 / norm,
-                   N.ptr(upstream), N.ptr(sums), N.ptr(grad_head), N.stream())
+            args = (N.ptr(head_t), N.ptr(asg.labels), N.ptr(asg.matched), N.ptr(asg.gt_table),
+                    N.ptr(gt_classes), N.ptr(asg.gt_offsets), n, h.S, h.B, h.C, h.image_size[0], h.image_size[1],
+                    N.ptr(h.priors_on(head_t.device)), self.lambda_coord, self.lambda_noobj, 1.0 / norm,
+                    N.ptr(upstream), N.ptr(sums), N.ptr(grad_head))
+            if peer is None:
+                N.call("det_yolo_loss", *args, N.stream())
+            else:  # the loss kernel's last CTA publishes the sums to every rank and collects the previous step's
+                ctx, prev = peer.fused_ctx()
+                N.call("det_yolo_loss_peer", *args, ctypes.byref(ctx), N.stream())
+                self._world_prev = prev
         return sums * self._sum_scale(norm, head_t.device)  # one launch: [lambda_coord/norm, 1/norm, 1/norm, 1, ...]
 
     def _sum_scale(self, norm: float, device) -> torch.Tensor:
@@ -236,10 +243,12 @@ class YoloGridTrainer:
         return v
 
     def loss(self, head_t: torch.Tensor, asg: YoloAssignment, gt_classes: torch.Tensor,
-             normalizer: Optional[float] = None, with_grads: bool = False):
+             normalizer: Optional[float] = None, with_grads: bool = False, peer=None):
         """head (N,S,S,B*5+C) fp32; gt_classes (sum_G,) int64 packed like asg.gt_table.  Returns {"loc_loss",
         "obj_loss","cls_loss","num_pos","num_neg"} (autograd-connected) and, with_grads=True, "grad_head" from the same
-        launch (fused forward+backward)."""
+        launch (fused forward+backward).  peer (det_b200.dist.PeerSums, with_grads only): the same launch also publishes
+        the sums to every rank over NVLink peer memory and returns "world_sums_prev", the all-rank sum of the PREVIOUS
+        step's scaled sums (None on the first step) -- compute + collective in one kernel, no NCCL call."""
         N.require_cuda(head_t, gt_classes)
         ht = head_t.contiguous()
         assert ht.dtype == torch.float32
@@ -247,13 +256,16 @@ class YoloGridTrainer:
         norm = float(ht.shape[0] if normalizer is None else normalizer)
         if with_grads:
             gh = torch.empty_like(ht)
-            sums = self._run_loss(ht.detach(), asg, gc, norm, None, gh)
+            sums = self._run_loss(ht.detach(), asg, gc, norm, None, gh, peer)
         else:
             sums = _FusedYoloLoss.apply(ht, self, asg, gc, norm)
         out = {"loc_loss": sums[0], "obj_loss": sums[1], "cls_loss": sums[2], "num_pos": sums[3].detach(),
                "num_neg": sums[4].detach(), "sums": sums}
         if with_grads:
             out["grad_head"] = gh
+            if peer is not None:
+                prev = self._world_prev
+                out["world_sums_prev"] = None if prev is None else prev * self._sum_scale(norm, ht.device)
         return out
 
 

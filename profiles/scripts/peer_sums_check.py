@@ -64,6 +64,12 @@ def step_peer():
     res = tr.loss(h, tr.assign_packed(gtb, off, n), gtc, with_grads=True)
     ps2.exchange(res["sums"])
 
+ps3 = det.dist.PeerSums(dev)
+
+def step_fused():
+    h = heads[st["i"] % 24]; st["i"] += 1
+    tr.loss(h, tr.assign_packed(gtb, off, n), gtc, with_grads=True, peer=ps3)
+
 def step_none():
     h = heads[st["i"] % 24]; st["i"] += 1
     tr.loss(h, tr.assign_packed(gtb, off, n), gtc, with_grads=True)
@@ -75,11 +81,23 @@ ps2 = det.dist.PeerSums(dev)
 ms_peer = time_region(step_peer, 300)
 ps2.flush(); ps2.check()
 dist.barrier()
+# fused: numerically the same as an NCCL all-reduce of the previous step's sums
+prev_local = None
+for i in range(5):
+    res = tr.loss(heads[i], tr.assign_packed(gtb, off, n), gtc, with_grads=True, peer=ps3)
+    if prev_local is not None:
+        want = prev_local.clone(); dist.all_reduce(want)
+        ok &= bool(torch.allclose(res["world_sums_prev"], want, rtol=1e-5, atol=1e-5))
+    prev_local = res["sums"].clone()
+dist.barrier()
+ms_fused = time_region(step_fused, 300)
+ps3.flush(); ps3.check()
+dist.barrier()
 ms_none = time_region(step_none, 300)
-t = torch.tensor([ms_nccl, ms_peer, ms_none], device=dev)
+t = torch.tensor([ms_nccl, ms_peer, ms_none, ms_fused], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"world": world, "sums_equal_nccl_and_bitwise_equal_across_ranks": ok,
                       "ms_step_nccl_allreduce": round(float(t[0]), 5), "ms_step_peer_exchange": round(float(t[1]), 5),
-                      "ms_step_no_collective": round(float(t[2]), 5)}), flush=True)
+                      "ms_step_fused_in_loss_kernel": round(float(t[3]), 5), "ms_step_no_collective": round(float(t[2]), 5)}), flush=True)
 dist.destroy_process_group()

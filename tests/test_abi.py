@@ -62,3 +62,17 @@ def test_dense_detect_queries_and_argument_checks_need_no_gpu():
     assert f(*args(1024, 300, 7)) == -1     # unknown NMS mode
     assert f(*args(1024, 300, 0)) == -1     # null outputs
     assert b"null output" in N.fn("det_last_error")()
+
+
+def test_peer_sums_argument_checks_need_no_gpu():
+    import ctypes
+    from det_b200 import _native as N
+    one = ctypes.c_void_p(16)  # never dereferenced: every call below is rejected by the argument checks
+    pub, col, exc = N.fn("det_peer_sums_publish"), N.fn("det_peer_sums_collect"), N.fn("det_peer_sums_exchange")
+    assert pub(one, 13, 0, 2, one, 8, 0, 1, None) == -1          # width > 12
+    assert pub(one, 8, 2, 2, one, 8, 0, 1, None) == -1           # rank >= world
+    assert pub(one, 8, 0, 2, one, 8, 8, 1, None) == -1           # slot >= slots
+    assert col(one, 8, 33, one, 8, 0, 1, 10 ** 9, None, None) == -1   # world > 32
+    assert col(one, 8, 2, one, 8, 0, 1, 0, None, None) == -1          # timeout must be positive
+    assert exc(one, one, 8, 0, 2, one, 3, 1, 1, 10 ** 9, None, None) == -1   # slots < 4
+    assert exc(one, one, 8, 0, 2, one, 8, 1, 6, 10 ** 9, None, None) == -1   # lag > slots - 3

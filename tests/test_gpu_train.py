@@ -185,6 +185,37 @@ def test_peer_sums_protocol_on_one_gpu(det):
     px.check()
 
 
+def test_yolo_loss_publishes_from_its_last_cta(det):
+    """det_yolo_loss_peer (world 1): same losses and gradients as det_yolo_loss, and "world_sums_prev" of step t is the
+    sums vector of step t - 1 -- published and collected by the loss kernel's own last CTA."""
+    dev = torch.device("cuda")
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    tr = det.YoloGridTrainer(yh)
+    g = gen(12)
+    n = 300
+    gts = [torch.cat([xy, xy + wh], 1) for xy, wh in
+           ((torch.rand(k, 2, generator=g) * 300, torch.rand(k, 2, generator=g) * 100 + 8)
+            for k in torch.randint(1, 6, (n,), generator=g).tolist())]
+    gtc = torch.cat([torch.randint(0, 20, (b.shape[0],), generator=g) for b in gts]).to(dev)
+    off = torch.tensor([0] + [b.shape[0] for b in gts]).cumsum(0).to(torch.int32).to(dev)
+    gtb = torch.cat(gts).to(dev)
+    asg = tr.assign_packed(gtb, off, n)
+    ps = det.dist.PeerSums(dev)
+    prev = None
+    for step in range(6):
+        head = torch.randn(n, 7, 7, 30, generator=g).to(dev)
+        want = tr.loss(head, asg, gtc, with_grads=True)
+        got = tr.loss(head, asg, gtc, with_grads=True, peer=ps)
+        assert torch.equal(got["grad_head"], want["grad_head"])
+        torch.testing.assert_close(got["sums"], want["sums"], rtol=1e-5, atol=1e-6)  # atomics: order of the CTAs
+        if step == 0:
+            assert got["world_sums_prev"] is None
+        else:
+            assert torch.equal(got["world_sums_prev"], prev)
+        prev = got["sums"].clone()
+    ps.check()
+
+
 def _rpn_loss_case(O, n, seed, beta=0.0):
     g = gen(seed)
     anc = _anchors(O)
