@@ -321,6 +321,21 @@ def extras_train(det, dev, world, peak, quick):
         ms_p = time_region(step_grid_peer, 30 if quick else 200)
         ps.flush()
         ps.check()
+        ps2 = det.dist.PeerSums(dev)
+
+        def step_grid_fused():
+            h = heads[state["i"] % pool]
+            state["i"] += 1
+            asg = tr.assign_packed(gtb, off, n)
+            tr.loss(h, asg, gtc, with_grads=True, peer=ps2)  # the loss kernel's last CTA does the exchange
+
+        ms_f = time_region(step_grid_fused, 30 if quick else 200)
+        ps2.flush()
+        ps2.check()
+        out["train_grid_b1024"].update({"ms_per_step_fused_peer_exchange": ms_f,
+                                        "images_per_s_per_gpu_fused_peer_exchange": n / ms_f * 1e3,
+                                        "fused_peer_exchange": "det_yolo_loss_peer: the loss kernel's last CTA publishes the "
+                                                               "sums to every rank and collects the previous step's world sum"})
         out["train_grid_b1024"].update({"ms_per_step_peer_exchange": ms_p, "images_per_s_per_gpu_peer_exchange": n / ms_p * 1e3,
                                         "peer_exchange": "det_peer_sums_exchange: P2P stores into every rank's symmetric "
                                                          "buffer + step stamps, no NCCL launch"})
