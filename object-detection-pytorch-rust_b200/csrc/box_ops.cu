@@ -242,7 +242,6 @@ struct RpnLevelDev {
     const float* deltas;
     const float4* cell;
     int w, hw, tiles;  // tiles of 128 positions per image
-    float stride_unused;
     int stride;
     int64_t out_offset;
 };
@@ -464,14 +463,14 @@ int det_rpn_decode(const det_rpn_level_t* levels_host, int num_levels, int n, in
         f.tile_begin[f.num_levels] = tb;
         D.obj = L.objectness; D.deltas = L.deltas; D.cell = reinterpret_cast<const float4*>(L.cell_anchors);
         D.w = L.w > 0 ? L.w : 1; D.hw = L.h * L.w; D.tiles = (D.hw + kRpnTilePos - 1) / kRpnTilePos;
-        D.stride = L.stride; D.stride_unused = 0.f; D.out_offset = L.out_offset;
+        D.stride = L.stride; D.out_offset = L.out_offset;
         tb += (long long)n * D.tiles;
         ++f.num_levels;
     }
     for (int l = f.num_levels; l < kRpnFlatMaxLevels; ++l) {
         RpnLevelDev& D = f.lv[l];
         D.obj = nullptr; D.deltas = nullptr; D.cell = nullptr; D.w = 1; D.hw = 0; D.tiles = 1; D.stride = 0;
-        D.stride_unused = 0.f; D.out_offset = 0;
+        D.out_offset = 0;
     }
     for (int l = f.num_levels; l <= kRpnFlatMaxLevels; ++l) f.tile_begin[l] = tb;
     if (tb == 0) return DET_OK;
