@@ -575,10 +575,17 @@ def main():
     # steps overlap on the pipeline's per-slot streams.  The timed region ends when the last result is on the host.
     e2e_steps = max(3, min(args.steps, 2000))
     depth = 4
-    pipe = det.YoloHostPipeline(yh, BATCH, SCORE_THR, IOU_THR, MAX_DET, depth=depth, device=dev)
     host_src = make_heads(depth, 100 + rank)
-    for s_ in range(depth):
-        pipe.input(s_).copy_(host_src[s_])
+
+    def make_pipe(index_dtype):
+        p_ = det.YoloHostPipeline(yh, BATCH, SCORE_THR, IOU_THR, MAX_DET, depth=depth, device=dev, index_dtype=index_dtype)
+        for s_ in range(depth):
+            p_.input(s_).copy_(host_src[s_])
+        return p_
+
+    # detection indices travel as int32 (same values as the int64 `flat` of detect(); 4 of 28 bytes per detection less
+    # on the PCIe download, which is what bounds this number); the int64 wire format is timed once below for reference
+    pipe = make_pipe(torch.int32)
 
     def e2e_run(k):
         seen = 0
@@ -609,8 +616,18 @@ def main():
            "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
            "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall_ms / e2e_steps,
            "segments_ms_per_step": [m / e2e_steps for m in seg_ms],
-           "api": f"det_b200.YoloHostPipeline(depth={depth}): pinned host in -> H2D -> det_yolo_decode_nms -> D2H -> "
-                  "pinned host out, one CUDA graph per slot, slots on separate streams"}
+           "api": f"det_b200.YoloHostPipeline(depth={depth}, index_dtype=int32): pinned host in -> H2D -> "
+                  "det_yolo_decode_nms_i32 -> D2H -> pinned host out, one CUDA graph per slot, slots on separate streams"}
+    pipe = make_pipe(torch.int64)
+    e2e_run(2 * depth)
+    barrier(world)
+    e0.record()
+    e2e_run(e2e_steps)
+    e1.record()
+    barrier(world)
+    ms64 = max_over_ranks(max(e0.elapsed_time(e1), 0.0), world, dev)
+    e2e["int64_indices"] = {"value": world * BATCH * e2e_steps / (ms64 * 1e-3), "d2h_bytes_per_step": pipe.d2h_bytes,
+                            "ms_per_step": ms64 / e2e_steps}
 
     extras = {}
     if not args.no_extras:

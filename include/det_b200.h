@@ -149,6 +149,13 @@ DET_API int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, i
                         float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
                         int64_t* det_flat, float* det_boxes, float* det_scores, int32_t* det_count, void* stream);
 
+/* the same call with 32-bit detection indices (same values; p*c <= 4096 always fits): the serving wire format of
+ * det_b200.YoloHostPipeline -- 4 bytes less per detection to move over PCIe. */
+DET_API int det_yolo_decode_nms_i32(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
+                            float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
+                            float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
+                            int32_t* det_flat32, float* det_boxes, float* det_scores, int32_t* det_count, void* stream);
+
 /* dense anchor head (YOLOv3-style, NCHW): head (n, a*(5+c), h, w) -> boxes (n,h*w*a,4), best score, best class.
  * anchors_wh (a,2) device.  Output slots as in det_rpn_decode_level. */
 DET_API int det_dense_decode_level(const float* head, int n, int a, int c, int h, int w, int stride, const float* anchors_wh,

@@ -163,7 +163,9 @@ yolo_decode_nms_kernel(const float* __restrict__ head, const float2* __restrict_
         const int i = (int)KL::idx(sm.keys[j]);
         const uint32_t pc = cpc[i];
         const int64_t o = (int64_t)img * prm.max_det + j;
-        det_flat[o] = (int64_t)(pc >> 16) * C + (int64_t)(pc & 0xffffu);
+        const int64_t flat = (int64_t)(pc >> 16) * C + (int64_t)(pc & 0xffffu);
+        if (prm.flat32) reinterpret_cast<int32_t*>(det_flat)[o] = (int32_t)flat;
+        else det_flat[o] = flat;
         if (det_boxes) det_boxes[o] = pbox[pc >> 16];
         if (det_scores) det_scores[o] = cscore[i];
     }
@@ -216,10 +218,11 @@ extern "C" __attribute__((visibility("default"))) int det_debug_read_phases(long
 
 extern "C" {
 
-int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
-                        float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
-                        float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
-                        int64_t* det_flat, float* det_boxes, float* det_scores, int32_t* det_count, void* stream) {
+static int yolo_decode_nms_impl(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
+                                float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
+                                float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
+                                int64_t* det_flat, float* det_boxes, float* det_scores, int32_t* det_count, void* stream,
+                                int flat32) {
     DET_CHECK_ARG(n >= 0 && s >= 1 && b >= 1 && c >= 1 && max_det >= 1, "bad size");
     DET_CHECK_ARG(mode >= DET_NMS_AUTO && mode <= DET_NMS_OFFSET_TRICK, "unknown mode");
     if (n == 0) return DET_OK;
@@ -241,7 +244,7 @@ int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h
     prm.img_w = (float)img_w; prm.img_h = (float)img_h;
     prm.scale_clamp = scale_clamp; prm.score_thresh = score_thresh;
     prm.thr_f = float_threshold_below(iou_threshold);
-    prm.clip = clip; prm.mode = mode; prm.max_det = max_det;
+    prm.clip = clip; prm.mode = mode; prm.max_det = max_det; prm.flat32 = flat32;
     cudaStream_t st = as_stream(stream);
     // small clipped grids (BASELINE configs[0]/[1]): one warp per class, no CTA-wide sort
     if (P <= kFastMaxP && c <= kFastMaxC && clip && FastLayout(s * s, b * 5 + c, (int)P, c).bytes <= 200 * 1024) {
@@ -256,6 +259,24 @@ int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h
     if (PC <= 2048)
         return launch_yolo<2048>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
     return launch_yolo<4096>(head, priors, prm, dense_boxes, dense_conf, dense_scores, det_flat, det_boxes, det_scores, det_count, st);
+}
+
+int det_yolo_decode_nms(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
+                        float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
+                        float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
+                        int64_t* det_flat, float* det_boxes, float* det_scores, int32_t* det_count, void* stream) {
+    return yolo_decode_nms_impl(head, n, s, b, c, img_h, img_w, priors, scale_clamp, clip, score_thresh, iou_threshold, mode,
+                                dense_boxes, dense_conf, dense_scores, max_det, det_flat, det_boxes, det_scores, det_count,
+                                stream, 0);
+}
+
+int det_yolo_decode_nms_i32(const float* head, int n, int s, int b, int c, int img_h, int img_w, const float* priors,
+                            float scale_clamp, int clip, float score_thresh, double iou_threshold, int mode,
+                            float* dense_boxes, float* dense_conf, float* dense_scores, int64_t max_det,
+                            int32_t* det_flat32, float* det_boxes, float* det_scores, int32_t* det_count, void* stream) {
+    return yolo_decode_nms_impl(head, n, s, b, c, img_h, img_w, priors, scale_clamp, clip, score_thresh, iou_threshold, mode,
+                                dense_boxes, dense_conf, dense_scores, max_det, reinterpret_cast<int64_t*>(det_flat32),
+                                det_boxes, det_scores, det_count, stream, 1);
 }
 
 }  // extern "C"

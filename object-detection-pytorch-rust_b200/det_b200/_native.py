@@ -39,6 +39,8 @@ PROTOTYPES = {
                                 c_p]),
     "det_yolo_decode_nms": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_i, c_f, c_d, c_i, c_p, c_p, c_p, c_l,
                                   c_p, c_p, c_p, c_p, c_p]),
+    "det_yolo_decode_nms_i32": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_i, c_f, c_d, c_i, c_p, c_p, c_p, c_l,
+                                      c_p, c_p, c_p, c_p, c_p]),
     "det_dense_decode_level": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_p, c_p, c_p, c_l, c_l, c_p]),
     "det_dense_decode": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_l, c_p]),
     "det_dense_detect_workspace_bytes": (c_l, [c_i, c_l]),

@@ -44,11 +44,13 @@ class YoloGridHead:
         return self._dev_priors[k]
 
     def detect(self, head: torch.Tensor, score_thresh: float = 0.25, iou_thresh: float = 0.5,
-               max_det: Optional[int] = None, return_dense: bool = False, mode: int = MODE_AUTO, out=None):
+               max_det: Optional[int] = None, return_dense: bool = False, mode: int = MODE_AUTO, out=None,
+               index_dtype: torch.dtype = torch.int64):
         """head (N,S,S,B*5+C) -> dict(flat (N,K) int64 = predictor*C+class, boxes (N,K,4), scores (N,K),
         count (N) int32) with K = max_det padding, by descending score; one launch, no host synchronisation.
         With return_dense the decoded boxes/conf/scores of every predictor are written too.
-        `out` may carry a dict returned by an earlier call with the same shapes to reuse its buffers."""
+        `out` may carry a dict returned by an earlier call with the same shapes to reuse its buffers.
+        index_dtype=torch.int32 writes the same `flat` values as 32-bit integers (det_yolo_decode_nms_i32)."""
         N.require_cuda(head)
         h = N.f32c(head)
         n = h.shape[0]
@@ -57,7 +59,7 @@ class YoloGridHead:
         max_det = P * C if max_det is None else int(max_det)
         dev = h.device
         if out is None:
-            out = {"flat": torch.empty((n, max_det), dtype=torch.int64, device=dev),
+            out = {"flat": torch.empty((n, max_det), dtype=index_dtype, device=dev),
                    "boxes": torch.empty((n, max_det, 4), dtype=torch.float32, device=dev),
                    "scores": torch.empty((n, max_det), dtype=torch.float32, device=dev),
                    "count": torch.empty((n,), dtype=torch.int32, device=dev), "num_classes": C}
@@ -65,9 +67,11 @@ class YoloGridHead:
                 out.update(dense_boxes=torch.empty((n, P, 4), dtype=torch.float32, device=dev),
                            dense_conf=torch.empty((n, P), dtype=torch.float32, device=dev),
                            dense_scores=torch.empty((n, P, C), dtype=torch.float32, device=dev))
+        assert out["flat"].dtype in (torch.int64, torch.int32)
         if n:
             with torch.cuda.device(dev):
-                N.call("det_yolo_decode_nms", N.ptr(h), n, self.S, self.B, C, self.image_size[0], self.image_size[1],
+                N.call("det_yolo_decode_nms" if out["flat"].dtype == torch.int64 else "det_yolo_decode_nms_i32",
+                       N.ptr(h), n, self.S, self.B, C, self.image_size[0], self.image_size[1],
                        N.ptr(self.priors_on(dev)), self.scale_clamp, int(self.clip), float(score_thresh),
                        float(iou_thresh), int(mode), N.ptr(out.get("dense_boxes")), N.ptr(out.get("dense_conf")),
                        N.ptr(out.get("dense_scores")), max_det, N.ptr(out["flat"]), N.ptr(out["boxes"]),
@@ -88,14 +92,18 @@ class YoloHostPipeline:
     later ``wait(slot)`` -> dict of pinned host views (flat, boxes, scores, count).  No per-step allocation."""
 
     def __init__(self, head: "YoloGridHead", batch: int, score_thresh: float = 0.25, iou_thresh: float = 0.5,
-                 max_det: int = 300, depth: int = 3, device=None, mode: int = MODE_AUTO, use_graph: bool = True):
+                 max_det: int = 300, depth: int = 3, device=None, mode: int = MODE_AUTO, use_graph: bool = True,
+                 index_dtype: torch.dtype = torch.int64):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.head, self.batch, self.depth, self.device = head, int(batch), int(depth), dev
         self.args = (float(score_thresh), float(iou_thresh), int(max_det), int(mode))
         shape = (self.batch, head.S, head.S, head.B * 5 + head.C)
         k = int(max_det)
-        # one output blob per slot so the download is a single copy: [flat i64 | boxes f32x4 | scores f32 | count i32]
-        self._sizes = (self.batch * k * 8, self.batch * k * 16, self.batch * k * 4, self.batch * 4)
+        assert index_dtype in (torch.int64, torch.int32)
+        self.index_dtype = index_dtype  # int32: the same indices, 4 bytes less per detection on the PCIe download
+        isz = 8 if index_dtype == torch.int64 else 4
+        # one output blob per slot so the download is a single copy: [flat i64/i32 | boxes f32x4 | scores f32 | count i32]
+        self._sizes = (self.batch * k * isz, self.batch * k * 16, self.batch * k * 4, self.batch * 4)
         nbytes = sum(self._sizes)
         self.h_in = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.d_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(depth)]
@@ -120,7 +128,7 @@ class YoloHostPipeline:
 
     def _views(self, blob, k):
         o0, o1, o2, o3 = 0, self._sizes[0], self._sizes[0] + self._sizes[1], self._sizes[0] + self._sizes[1] + self._sizes[2]
-        return {"flat": blob[o0:o1].view(torch.int64).view(self.batch, k),
+        return {"flat": blob[o0:o1].view(self.index_dtype).view(self.batch, k),
                 "boxes": blob[o1:o2].view(torch.float32).view(self.batch, k, 4),
                 "scores": blob[o2:o3].view(torch.float32).view(self.batch, k),
                 "count": blob[o3:].view(torch.int32).view(self.batch), "num_classes": self.head.C}

@@ -182,12 +182,12 @@ def test_yolo_fast_path_nonfinite_logits(det, O):
     _check_detect(det, O, yh, head, 0.35, 0.5)
 
 
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_yolo_host_pipeline_matches_detect(det, O, use_graph):
+@pytest.mark.parametrize("use_graph,index_dtype", [(True, torch.int64), (False, torch.int64), (True, torch.int32)])
+def test_yolo_host_pipeline_matches_detect(det, O, use_graph, index_dtype):
     """The serving pipeline (pinned host in -> H2D -> fused kernel -> D2H -> pinned host out, one slot per stream)
     returns exactly what detect() returns, for every slot and across slot reuse."""
     yh = det.YoloGridHead(7, 2, 20, (448, 448))
-    pipe = det.YoloHostPipeline(yh, 32, 0.25, 0.5, 300, depth=3, use_graph=use_graph)
+    pipe = det.YoloHostPipeline(yh, 32, 0.25, 0.5, 300, depth=3, use_graph=use_graph, index_dtype=index_dtype)
     heads = torch.randn(7, 32, 7, 7, 30, generator=gen(21))
     got = []
     for i in range(7):
@@ -205,7 +205,8 @@ def test_yolo_host_pipeline_matches_detect(det, O, use_graph):
         assert torch.equal(got[i]["count"], cnt)
         for j in range(32):
             k = int(cnt[j])
-            assert torch.equal(got[i]["flat"][j, :k], r["flat"][j, :k].cpu())
+            assert got[i]["flat"].dtype == index_dtype
+            assert torch.equal(got[i]["flat"][j, :k].long(), r["flat"][j, :k].cpu())
             assert torch.equal(got[i]["boxes"][j, :k], r["boxes"][j, :k].cpu())
             assert torch.equal(got[i]["scores"][j, :k], r["scores"][j, :k].cpu())
     # and against the oracle for one batch
@@ -213,7 +214,7 @@ def test_yolo_host_pipeline_matches_detect(det, O, use_graph):
     d = yh.detect(heads[0].cuda(), 0.25, 0.5, return_dense=True)
     for j in range(0, 32, 5):
         wf, _, _, _ = O.yolo_select_nms(d["dense_boxes"][j].cpu(), d["dense_scores"][j].cpu(), 0.25, 0.5, max_det=300)
-        assert int(r["count"][j]) == wf.numel() and torch.equal(r["flat"][j, :wf.numel()], wf)
+        assert int(r["count"][j]) == wf.numel() and torch.equal(r["flat"][j, :wf.numel()].long(), wf)
 
 
 @pytest.mark.parametrize("n,C,sizes", [
