@@ -336,6 +336,19 @@ def extras_train(det, dev, world, peak, quick):
                                         "images_per_s_per_gpu_fused_peer_exchange": n / ms_f * 1e3,
                                         "fused_peer_exchange": "det_yolo_loss_peer: the loss kernel's last CTA publishes the "
                                                                "sums to every rank and collects the previous step's world sum"})
+        # the whole step (assignment, loss fwd+bwd with the fused all-reduce, scaling) replayed from a CUDA graph: the
+        # 4 launches of an 80 us step are launch-bound from Python; the step counter of the exchange lives on the device
+        ps3 = det.dist.PeerSums(dev, graph_safe=True)
+
+        def graph_step(h):
+            tr.loss(h, tr.assign_packed(gtb, off, n), gtc, with_grads=True, peer=ps3)
+
+        ms_g = time_graph([(lambda h=h_: graph_step(h)) for h_ in heads], 5 if quick else 20)
+        ps3.flush()
+        ps3.check()
+        out["train_grid_b1024"].update({"ms_per_step_graph_fused_peer_exchange": ms_g,
+                                        "images_per_s_per_gpu_graph_fused_peer_exchange": n / ms_g * 1e3,
+                                        "graph": f"{pool} steps per CUDA graph replay, all-reduce every step inside the loss kernel"})
         out["train_grid_b1024"].update({"ms_per_step_peer_exchange": ms_p, "images_per_s_per_gpu_peer_exchange": n / ms_p * 1e3,
                                         "peer_exchange": "det_peer_sums_exchange: P2P stores into every rank's symmetric "
                                                          "buffer + step stamps, no NCCL launch"})

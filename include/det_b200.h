@@ -287,7 +287,7 @@ DET_API int det_peer_sums_collect(float* out, int width, int world, const float*
                           uint32_t stamp, int64_t timeout_ns, int32_t* error_flag, void* stream);
 /* compute + collective in ONE kernel: det_yolo_loss whose last CTA publishes the batch's sums (the raw `sums` vector,
  * `width` <= 8 floats) as step `stamp` and collects step stamp - lag into `out`.  done_counter: device int32, zero
- * before the first use (the kernel resets it). */
+ * before the first use (the kernel resets it).  The out buffer of step t must stay untouched until step t + 1's. */
 typedef struct det_peer_ctx {
     const void* peers_dev;
     float* out;
@@ -296,6 +296,8 @@ typedef struct det_peer_ctx {
     int64_t timeout_ns;
     int32_t width, rank, world, slots;
     uint32_t stamp, lag;
+    uint32_t* stamp_counter; /* device, may be NULL.  Non-NULL: the kernel stamps with ++(*stamp_counter) and ignores
+                                `stamp`, so a captured CUDA graph can be replayed (same number of replays on every rank) */
 } det_peer_ctx_t;
 DET_API int det_yolo_loss_peer(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                        const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,

@@ -1152,6 +1152,7 @@ static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t
     auto p2 = reinterpret_cast<const float2*>(priors);
     PeerCtxDev pc;
     pc.enabled = 0;
+    pc.stamp_counter = nullptr;
     if (peer) {
         DET_CHECK_ARG(peer->peers_dev && peer->out && peer->done_counter, "peer context: null pointer");
         DET_CHECK_ARG(peer->width >= 1 && peer->width <= 8, "peer context: width must be in [1, 8] (the sums vector)");
@@ -1163,7 +1164,7 @@ static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t
         pc.peers = reinterpret_cast<float* const*>(peer->peers_dev); pc.out = peer->out;
         pc.error_flag = peer->error_flag; pc.done_counter = peer->done_counter; pc.timeout_ns = peer->timeout_ns;
         pc.width = peer->width; pc.rank = peer->rank; pc.world = peer->world; pc.slots = peer->slots;
-        pc.stamp = peer->stamp; pc.lag = peer->lag; pc.enabled = 1;
+        pc.stamp = peer->stamp; pc.lag = peer->lag; pc.stamp_counter = peer->stamp_counter; pc.enabled = 1;
     }
     if (per_img <= kYoloLossTile) {
         int imgs = kYoloLossTile / per_img;

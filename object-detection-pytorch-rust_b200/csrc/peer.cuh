@@ -68,6 +68,7 @@ struct PeerCtxDev {
     long long timeout_ns;
     int width, rank, world, slots;
     uint32_t stamp, lag;
+    uint32_t* stamp_counter;  // non-null: the step stamp is ++(*stamp_counter) instead of `stamp` (CUDA-graph replays)
     int enabled;
 };
 
@@ -87,12 +88,20 @@ __device__ __forceinline__ void peer_exchange_from_last_cta(const PeerCtxDev& pc
     __threadfence();
     __shared__ float s_sums[kPeerMaxWidth];
     if ((int)threadIdx.x < pc.width) s_sums[threadIdx.x] = __ldcg(sums + threadIdx.x);  // final values live in L2
+    uint32_t stamp = pc.stamp;
+    if (pc.stamp_counter) {  // a replayed graph cannot change its kernel arguments: the step lives on the device
+        if (threadIdx.x == 0) {
+            stamp = *pc.stamp_counter + 1u;
+            *pc.stamp_counter = stamp;
+        }
+        stamp = __shfl_sync(0xffffffffu, stamp, 0);
+    }
     __syncwarp();
-    peer_publish(s_sums, pc.width, pc.rank, pc.world, pc.peers, (int)(pc.stamp % (uint32_t)pc.slots), pc.stamp);
+    peer_publish(s_sums, pc.width, pc.rank, pc.world, pc.peers, (int)(stamp % (uint32_t)pc.slots), stamp);
     __syncwarp();
-    if (pc.stamp > pc.lag)
-        peer_collect(pc.out, pc.width, pc.world, pc.peers[pc.rank], (int)((pc.stamp - pc.lag) % (uint32_t)pc.slots),
-                     pc.stamp - pc.lag, pc.timeout_ns, pc.error_flag);
+    if (stamp > pc.lag)
+        peer_collect(pc.out, pc.width, pc.world, pc.peers[pc.rank], (int)((stamp - pc.lag) % (uint32_t)pc.slots),
+                     stamp - pc.lag, pc.timeout_ns, pc.error_flag);
 }
 
 }  // namespace det

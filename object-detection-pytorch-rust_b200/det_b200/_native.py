@@ -82,7 +82,7 @@ class PeerCtx(ctypes.Structure):
     """det_peer_ctx_t of include/det_b200.h"""
     _fields_ = [("peers_dev", c_p), ("out", c_p), ("error_flag", c_p), ("done_counter", c_p), ("timeout_ns", c_l),
                 ("width", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("slots", ctypes.c_int32),
-                ("stamp", ctypes.c_uint32), ("lag", ctypes.c_uint32)]
+                ("stamp", ctypes.c_uint32), ("lag", ctypes.c_uint32), ("stamp_counter", c_p)]
 
 
 class FeatureLevel(ctypes.Structure):

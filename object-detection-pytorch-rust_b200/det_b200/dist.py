@@ -103,8 +103,11 @@ class PeerSums:
     SLOTS = 8
     RECORD = 16
 
-    def __init__(self, device, width: int = 8, timeout_s: float = 5.0):
+    def __init__(self, device, width: int = 8, timeout_s: float = 5.0, graph_safe: bool = False):
+        """graph_safe=True keeps the step counter on the device (fused path only: det_yolo_loss_peer increments it), so the
+        training step can be captured in a CUDA graph and replayed -- every rank must replay the same number of times."""
         from . import _native as N
+        self._device_stamps = bool(graph_safe)
         self._N = N
         self.device = torch.device(device)
         self.width = int(width)
@@ -173,29 +176,43 @@ class PeerSums:
     def fused_ctx(self):
         """Context for a kernel that publishes from its own last CTA (det_yolo_loss_peer): advances the step like
         exchange() and returns (det_peer_ctx_t, out) -- `out` receives the previous step's world sum of the RAW sums
-        vector (None on the first step), valid in stream order after that kernel."""
+        vector (None on the first step), valid in stream order after that kernel.
+        With graph_safe=True (constructor) the step counter lives on the device and `out` is a single buffer that every
+        step overwrites (zeros after the first step)."""
         N = self._N
         assert self._collected == self.step, "do not mix the fused path with publish() / collect()"
         if not hasattr(self, "_done"):
             self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.step += 1
-        out = self._out[self.step & 1]
+            self._stamp_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         ctx = N.PeerCtx()
-        ctx.peers_dev, ctx.out = self.peers.data_ptr(), out.data_ptr()
+        ctx.peers_dev = self.peers.data_ptr()
         ctx.error_flag, ctx.done_counter = self.error.data_ptr(), self._done.data_ptr()
         ctx.timeout_ns = self.timeout_ns
         ctx.width, ctx.rank, ctx.world, ctx.slots = self.width, self.rank, self.world, self.SLOTS
-        ctx.stamp, ctx.lag = self.step & 0xffffffff, 1
+        ctx.lag = 1
+        if self._device_stamps:
+            out = self._out[0]
+            ctx.out, ctx.stamp, ctx.stamp_counter = out.data_ptr(), 0, self._stamp_dev.data_ptr()
+            return ctx, out
+        assert not torch.cuda.is_current_stream_capturing(), "capture needs PeerSums(..., graph_safe=True)"
+        self.step += 1
+        out = self._out[self.step & 1]
+        ctx.out, ctx.stamp, ctx.stamp_counter = out.data_ptr(), self.step & 0xffffffff, None
         self._collected = self.step
         return ctx, (out if self.step > 1 else None)
 
     def flush(self) -> torch.Tensor:
         """World sum of the latest published vector (end of training / before logging the last step)."""
         N = self._N
-        out = self._out[(self.step + 1) & 1]
+        step = self.step
+        if self._device_stamps and hasattr(self, "_stamp_dev"):  # the step counter lives on the device (graph replays)
+            step = int(self._stamp_dev.item())
+        if step == 0:
+            return torch.zeros(self.width, dtype=torch.float32, device=self.device)
+        out = self._out[1] if self._device_stamps else self._out[(step + 1) & 1]
         with torch.cuda.device(self.device):
             N.call("det_peer_sums_collect", N.ptr(out), self.width, self.world, N.ptr(self.buf), self.SLOTS,
-                   self.step % self.SLOTS, self.step & 0xffffffff, self.timeout_ns, N.ptr(self.error), N.stream())
+                   step % self.SLOTS, step & 0xffffffff, self.timeout_ns, N.ptr(self.error), N.stream())
         return out
 
     def check(self):

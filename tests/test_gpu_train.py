@@ -216,6 +216,43 @@ def test_yolo_loss_publishes_from_its_last_cta(det):
     ps.check()
 
 
+def test_fused_exchange_replays_from_a_cuda_graph(det):
+    """PeerSums(graph_safe=True): the step stamp lives on the device, so a captured training step can be replayed; after
+    every replay the collected vector is the sums of the previous replay."""
+    dev = torch.device("cuda")
+    yh = det.YoloGridHead(7, 2, 20, (448, 448))
+    tr = det.YoloGridTrainer(yh)
+    g = gen(13)
+    n = 64
+    gts = [torch.tensor([[10.0 + i, 20.0, 120.0 + i, 200.0]]) for i in range(n)]
+    gtc = torch.randint(0, 20, (n,), generator=g).to(dev)
+    off = torch.arange(n + 1, dtype=torch.int32).to(dev)
+    gtb = torch.cat(gts).to(dev)
+    head = torch.randn(n, 7, 7, 30, generator=g).to(dev)
+    ps = det.dist.PeerSums(dev, graph_safe=True)
+    res = {}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        res = tr.loss(head, tr.assign_packed(gtb, off, n), gtc, with_grads=True, peer=ps)  # stamp 1 (eager warm-up)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        res = tr.loss(head, tr.assign_packed(gtb, off, n), gtc, with_grads=True, peer=ps)
+    want = tr.loss(head, tr.assign_packed(gtb, off, n), gtc, with_grads=True)["sums"]
+    for rep in range(4):
+        head.mul_(1.0 + 0.1 * rep)  # new inputs in place: the graph reads the same buffers
+        expect_prev = want.clone()
+        want = tr.loss(head, tr.assign_packed(gtb, off, n), gtc, with_grads=True)["sums"].clone()
+        graph.replay()
+        torch.cuda.synchronize()
+        torch.testing.assert_close(res["sums"], want, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(res["world_sums_prev"], expect_prev, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ps.flush() * tr._sum_scale(float(n), dev), want, rtol=1e-5, atol=1e-6)
+    ps.check()
+
+
 def _rpn_loss_case(O, n, seed, beta=0.0):
     g = gen(seed)
     anc = _anchors(O)
