@@ -309,6 +309,7 @@ def extras_train(det, dev, world, peak, quick):
     # the same all-reduce every step through NVLink peer memory (det_b200.dist.PeerSums, csrc/peer.cu): one tiny launch
     # per step publishes this step's sums into every peer's symmetric buffer and collects the previous step's
     try:
+        barrier(world)  # the exchange kernels wait for their peers on the device: start the sections together
         ps = det.dist.PeerSums(dev)
 
         def step_grid_peer():
@@ -321,6 +322,7 @@ def extras_train(det, dev, world, peak, quick):
         ms_p = time_region(step_grid_peer, 30 if quick else 200)
         ps.flush()
         ps.check()
+        barrier(world)
         ps2 = det.dist.PeerSums(dev)
 
         def step_grid_fused():
@@ -338,6 +340,7 @@ def extras_train(det, dev, world, peak, quick):
                                                                "sums to every rank and collects the previous step's world sum"})
         # the whole step (assignment, loss fwd+bwd with the fused all-reduce, scaling) replayed from a CUDA graph: the
         # 4 launches of an 80 us step are launch-bound from Python; the step counter of the exchange lives on the device
+        barrier(world)
         ps3 = det.dist.PeerSums(dev, graph_safe=True)
 
         def graph_step(h):
@@ -441,7 +444,7 @@ def extras_dense(det, dev, peak, quick):
             def step_nms():
                 det.nms_images(boxes, scores, classes, None, 0.5, 1000)
 
-            ms_n = time_region(step_nms, 3 if quick else 10)
+            ms_n = time_graph([step_nms], 3 if quick else 20)  # ~20 launches per call: replayed from a CUDA graph
             k_tot = int(cnt.sum())
             nms_bytes = n * 28 * R + 8 * k_tot + 8 * n
             entry.update({"ms_nms": ms_n, "images_per_s_decode_plus_nms": n / (ms_d + ms_n) * 1e3,

@@ -103,7 +103,7 @@ class PeerSums:
     SLOTS = 8
     RECORD = 16
 
-    def __init__(self, device, width: int = 8, timeout_s: float = 5.0, graph_safe: bool = False):
+    def __init__(self, device, width: int = 8, timeout_s: float = 20.0, graph_safe: bool = False):
         """graph_safe=True keeps the step counter on the device (fused path only: det_yolo_loss_peer increments it), so the
         training step can be captured in a CUDA graph and replayed -- every rank must replay the same number of times."""
         from . import _native as N
