@@ -14,7 +14,10 @@ L2, CUDA-graph replay in which consecutive, independent batches rotate over 4 st
 overlaps the head of the next); `e2e` goes through the public Python API with pinned host buffers, H2D + D2H inside the timed
 region; `roofline` is the fused kernel's algorithmic bytes / measured launch time against MEASURED_PEAKS.json;
 `cpu_baseline` is the CPU oracle (torch CPU ops + C greedy NMS) on a bounded sample; `extras` carries the training
-step (assignment + loss fwd/bwd, BASELINE configs[2]) and the dense-head decode+NMS (configs[3]).
+step (assignment + loss fwd/bwd, BASELINE configs[2]: Python loop with an NCCL all-reduce, with the all-reduce over
+NVLink peer memory -- separate kernel, fused into the loss kernel, and the whole step replayed from a CUDA graph) and the
+dense-head decode / decode+threshold+NMS with their rooflines (configs[3]).  The e2e pipeline moves the detection
+indices as int32 (same values as detect()'s int64 `flat`); `e2e.int64_indices` is the int64 wire format.
 """
 import argparse
 import json
