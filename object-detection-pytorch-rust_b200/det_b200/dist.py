@@ -98,7 +98,9 @@ class PeerSums:
     every peer's symmetric buffer; ``collect()`` returns the world's sum of the PREVIOUS publish (one step late, so
     the peers' stores have normally arrived and the tiny kernel does not spin).  Two ~2 us launches per step instead
     of ~55 us of NCCL launch: what a 81 us training step needs to scale.  Single process: the same kernels on a
-    plain buffer (world 1)."""
+    plain buffer (world 1).  One instance serves ONE stream of steps: every rank must issue the same sequence of
+    publish / collect / exchange / fused launches on a single stream (the slots and the fused path's arrival counter are
+    not shared between concurrent launches)."""
 
     SLOTS = 8
     RECORD = 16

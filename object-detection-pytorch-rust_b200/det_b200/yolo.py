@@ -262,6 +262,7 @@ class YoloGridTrainer:
         assert ht.dtype == torch.float32
         gc = gt_classes.to(torch.int64).contiguous()
         norm = float(ht.shape[0] if normalizer is None else normalizer)
+        assert peer is None or with_grads, "the fused all-reduce rides on the fused forward+backward launch (with_grads=True)"
         if with_grads:
             gh = torch.empty_like(ht)
             sums = self._run_loss(ht.detach(), asg, gc, norm, None, gh, peer)
