@@ -32,15 +32,15 @@ __device__ __forceinline__ int level_of(const LevelTable& t, int64_t i) {
 // ---- per-level top-k by radix select ---------------------------------------------------------------------------------------
 // The reference sorts every level fully and narrows to pre_nms_topk (models/utils.py:56-58).  Here the pre_nms_topk
 // best keys (level | descending logit | anchor index -- unique, so "best k" is exact and stable) of every level are
-// found with a radix select (4 byte-passes over the logit bits; the index bits only when equal logits straddle the
-// cut) and written, in arrival order, to a compact row [coff[l], coff[l] + take_l) per level.  Only that row -- a few
+// found with a radix select (4 byte-passes over the 32-bit logit keys; when equal logits straddle the cut the lower
+// anchor indices win, ranked in index order) and written, in arrival order, to a compact row [coff[l], coff[l] + take_l) per level.  Only that row -- a few
 // tiles instead of all R keys -- is sorted afterwards.  One CTA per image.
 static __global__ void __launch_bounds__(1024)
 rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LevelTable ct, int64_t len1,
                   LargeImg* info, uint64_t* __restrict__ keys) {
     __shared__ uint32_t hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ int s_want, s_slot, s_done;
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_want, s_slot, s_done, s_warp[32];
     constexpr int T = 1024;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* lg = logits + (int64_t)img * r;
@@ -57,24 +57,26 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
         const int64_t i0 = lt.off[l], size = lt.off[l + 1] - i0;
         const int take = (int)(ct.off[l + 1] - ct.off[l]);
         if (take == 0) continue;
-        unsigned long long cut = ~0ull;  // take == size: everything
+        // cut: keys with score key < cut are in; in tie mode those == cut only while `tie_want` lasts (index order),
+        // otherwise every key <= cut is in
+        uint32_t cut = 0xffffffffu;
+        bool tie_mode = false;
+        int tie_want = 0;
         if (take < size) {
-            // keys without the level field, shifted left by 7: bits 24..55 = logit, 7..23 = index; selected byte by
-            // byte from the top (the four logit bytes first)
+            // radix select of the take-th best 32-bit descending-logit key, one byte per pass
             if (tid == 0) {
-                s_prefix = 0ull;
+                s_prefix = 0u;
                 s_want = take;
                 s_done = 0;
             }
-            for (int shift = 48; shift >= 0; shift -= 8) {
+            for (int shift = 24; shift >= 0; shift -= 8) {
                 for (int b = tid; b < 256; b += T) hist[b] = 0u;
                 __syncthreads();
                 if (s_done) break;
-                const unsigned long long prefix = s_prefix;
-                const unsigned long long himask = (shift == 48) ? 0ull : (~0ull << (shift + 8));
+                const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
                 for (int64_t i = tid; i < size; i += T) {
-                    const unsigned long long key = KLL::strip_seg(KLL::make(0u, lg[i0 + i], (uint32_t)(i0 + i))) << 7;
-                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255ull], 1u);
+                    const uint32_t key = score_desc_key(lg[i0 + i]);
+                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                 }
                 __syncthreads();
                 if (wid == 0) {
@@ -95,10 +97,9 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
                         uint32_t run = before;
                         int q = 0;
                         for (; q < 7 && run + c8[q] < w; ++q) run += c8[q];
-                        unsigned long long np = prefix | ((unsigned long long)(lane * 8 + q) << shift);
-                        // the whole bin is wanted: every key that shares the prefix so far is in; stop here
-                        if (run + c8[q] == w) {
-                            np |= (shift == 0) ? 0ull : ((1ull << shift) - 1ull);
+                        uint32_t np = prefix | ((uint32_t)(lane * 8 + q) << shift);
+                        if (run + c8[q] == w) {  // the whole bin is wanted: everything that shares the prefix is in
+                            np |= (shift == 0) ? 0u : ((1u << shift) - 1u);
                             s_done = 1;
                         }
                         s_prefix = np;
@@ -109,23 +110,44 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
             }
             __syncthreads();
             cut = s_prefix;
+            // not done after the last byte: several anchors share the cut logit and only s_want of them fit -- the
+            // reference's stable sort keeps the lower indices
+            tie_mode = s_done == 0;
+            tie_want = s_want;
         }
         if (tid == 0) s_slot = 0;
         __syncthreads();
         const uint64_t lvl = (uint64_t)l << KLL::kSegShift;
+        int tie_seen = 0;  // equal-logit anchors already passed, in index order (block-uniform)
         for (int64_t base = 0; base < size; base += T) {
             const int64_t i = base + tid;
-            unsigned long long key = 0;
-            bool in = false;
+            uint32_t k32 = 0xffffffffu;
+            bool in = false, eq = false;
             if (i < size) {
-                key = KLL::strip_seg(KLL::make(0u, lg[i0 + i], (uint32_t)(i0 + i)));
-                in = (key << 7) <= cut;
+                k32 = score_desc_key(lg[i0 + i]);
+                in = tie_mode ? (k32 < cut) : (k32 <= cut);
+                eq = tie_mode && k32 == cut;
+            }
+            if (tie_mode) {  // block-uniform branch: rank the equal keys of this step in index order
+                const unsigned be = __ballot_sync(0xffffffffu, eq);
+                if (lane == 0) s_warp[wid] = __popc(be);
+                __syncthreads();
+                int before = tie_seen, total = 0;
+                for (int w = 0; w < T / 32; ++w) {
+                    const int v = s_warp[w];
+                    before += (w < wid) ? v : 0;
+                    total += v;
+                }
+                if (eq && before + __popc(be & ((1u << lane) - 1u)) < tie_want) in = true;
+                tie_seen += total;
+                __syncthreads();
             }
             const unsigned bal = __ballot_sync(0xffffffffu, in);
             int pos = 0;
             if (lane == 0 && bal) pos = atomicAdd(&s_slot, __popc(bal));
             pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-            if (in && pos < take) out[ct.off[l] + pos] = lvl | key;
+            if (in && pos < take)
+                out[ct.off[l] + pos] = lvl | ((uint64_t)k32 << KLL::kScoreShift) | (uint64_t)(uint32_t)(i0 + i);
         }
         __syncthreads();
     }
