@@ -69,3 +69,23 @@ def test_find_top_rpn_proposals(R):
     b = R.find_top_rpn_proposals([p.clone() for p in props], logits, sizes, 0.7, 1000, 300, 1.0, False)
     for (ab, as_), bi in zip(a, b):
         assert torch.equal(ab, bi.proposal_boxes.tensor) and torch.equal(as_, bi.objectness_logits)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_dense_select_nms_is_the_reference_batched_nms_on_the_thresholded_rows(R, seed):
+    """oracle.dense_select_nms (the spec of det_dense_detect's selection stage) = rows with score > thr, in row order,
+    through the REFERENCE's batched_nms, cut at max_det -- including negative coordinates (boxes sticking out of the
+    frame), where torchvision's coordinate-offset trick can suppress across categories."""
+    g = gen(400 + seed)
+    n = [300, 1500, 5000, 900][seed]
+    b = rand_boxes(n, 640.0, g, 0.3) - 60.0
+    s = torch.rand(n, generator=g)
+    if seed % 2:
+        s = (s * 64).round() / 64  # ties: row order decides
+    c = torch.randint(0, 80, (n,), generator=g)
+    thr, iou, max_det = 0.4, 0.5, 200
+    rows, bb, ss, cc = O.dense_select_nms(b, s, c, thr, iou, max_det)
+    cand = torch.nonzero(s > thr, as_tuple=True)[0]
+    keep = R.batched_nms(b[cand], s[cand], c[cand], iou)[:max_det]
+    assert torch.equal(rows, cand[keep])
+    assert torch.equal(bb, b[cand][keep]) and torch.equal(ss, s[cand][keep]) and torch.equal(cc, c[cand][keep])
