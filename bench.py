@@ -593,7 +593,7 @@ def main():
     # pinned host memory, runs the fused kernel and downloads the detections; H2D / kernel / D2H of consecutive
     # steps overlap on the pipeline's per-slot streams.  The timed region ends when the last result is on the host.
     e2e_steps = max(3, min(args.steps, 2000))
-    depth = 4
+    depth = int(os.environ.get("DET_E2E_DEPTH", "8"))  # pipeline slots (streams / graphs in flight)
     host_src = make_heads(depth, 100 + rank)
 
     def make_pipe(index_dtype):
