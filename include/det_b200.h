@@ -31,7 +31,7 @@ extern "C" {
 #define DET_ERR_CUDA (-4)         /* a CUDA runtime call failed; see det_last_error()            */
 #define DET_ERR_ALIGN (-5)        /* pointer not aligned as documented                           */
 
-#define DET_ABI_VERSION 1
+#define DET_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DET_API __attribute__((visibility("default")))
@@ -64,6 +64,11 @@ DET_API int det_matched_iou(const float* boxes1, const float* boxes2, int64_t n,
 /* deltas (m, k*4), boxes (m,4) -> out (m, k*4).  weights = (wx,wy,ww,wh). */
 DET_API int det_apply_deltas(const float* deltas, const float* boxes, int64_t m, int k, float wx, float wy, float ww,
                      float wh, float scale_clamp, float* out, void* stream);
+/* backward of det_apply_deltas (the reference's apply_deltas is differentiable through autograd; its GIoU loss and any
+ * ROI box head rely on that): grad_out (m, k*4) -> grad_deltas (m, k*4) and/or grad_boxes (m,4), either may be NULL. */
+DET_API int det_apply_deltas_backward(const float* deltas, const float* boxes, const float* grad_out, int64_t m, int k,
+                              float wx, float wy, float ww, float wh, float scale_clamp, float* grad_deltas,
+                              float* grad_boxes, void* stream);
 /* src (m,4), tgt (m,4) -> out (m,4).  *invalid_flag (device int32, caller-zeroed) is set to 1 if any src width
  * <= 0 (the reference asserts, box_regression.py:72). */
 DET_API int det_get_deltas(const float* src, const float* tgt, int64_t m, float wx, float wy, float ww, float wh, float* out,
@@ -214,8 +219,9 @@ DET_API int det_match_quality(const float* quality, int64_t g, int64_t r, const 
 
 /* Uniform random fg/bg subsample on the device (statistically, not stream-, equivalent to subsample_labels +
  * _subsample_labels, python/src/utils.py:34 / models/rpn.py:108): keeps min(#pos, int(s*f)) positives and
- * min(#neg, s-#pos) negatives per image, everything else becomes -1.  labels (n,r) int8 in place. */
-DET_API int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, float positive_fraction, uint64_t seed,
+ * min(#neg, s-#pos) negatives per image, everything else becomes -1.  labels (n,r) int8 in place.  int(s*f) is the
+ * reference's Python double product truncated (utils.py:63), hence the double argument. */
+DET_API int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, double positive_fraction, uint64_t seed,
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

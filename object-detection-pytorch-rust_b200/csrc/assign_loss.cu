@@ -412,7 +412,7 @@ __device__ __forceinline__ int label_class(int8_t l) { return l == 0 ? 1 : (l ==
 __device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t pattern) { return __vcmpeq4(w, pattern); }
 
 __global__ void __launch_bounds__(kSampleThreads)
-subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float positive_fraction, uint64_t seed) {
+subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, int pos_cap, uint64_t seed) {
     __shared__ SampleSmem sm;
     const int img = blockIdx.x, tid = threadIdx.x;
     const RowView rv(labels + (int64_t)img * r, r);
@@ -442,8 +442,9 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, float 
     }
     __syncthreads();
     const int npos = sm.cnt[0], nneg = sm.cnt[1];
-    // utils.py:64-69: num_pos = min(#pos, int(S*f)); num_neg = min(#neg, S - num_pos)
-    const int want_pos = min(npos, (int)((float)num_samples * positive_fraction));
+    // utils.py:63-69: num_pos = min(#pos, int(S*f)); num_neg = min(#neg, S - num_pos); pos_cap = int(S*f) is evaluated
+    // on the host in double like the reference's Python expression (100 * 0.29 -> 28, not fp32's 29)
+    const int want_pos = min(npos, pos_cap);
     const int want_neg = min(nneg, num_samples - want_pos);
     const int want[2] = {want_pos, want_neg};
     const int have[2] = {npos, nneg};
@@ -1082,13 +1083,15 @@ int det_match_quality(const float* quality, int64_t g, int64_t r, const float* t
     return DET_OK;
 }
 
-int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, float positive_fraction, uint64_t seed,
+int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, double positive_fraction, uint64_t seed,
                          void* stream) {
     DET_CHECK_ARG(n >= 0 && r >= 0 && num_samples >= 0, "negative size");
+    DET_CHECK_ARG(positive_fraction >= 0.0 && positive_fraction <= 1.0, "positive_fraction outside [0, 1]");
+    const int pos_cap = (int)((double)num_samples * positive_fraction);  // Python: int(num_samples * positive_fraction)
     DET_CHECK_ARG(r < (1ll << 31), "r too large");
     if (n == 0 || r == 0) return DET_OK;
     DET_CHECK_ARG(labels, "null pointer");
-    subsample_kernel<<<n, kSampleThreads, 0, as_stream(stream)>>>(labels, r, num_samples, positive_fraction, seed);
+    subsample_kernel<<<n, kSampleThreads, 0, as_stream(stream)>>>(labels, r, num_samples, pos_cap, seed);
     DET_LAUNCH_OK("subsample_kernel");
     return DET_OK;
 }

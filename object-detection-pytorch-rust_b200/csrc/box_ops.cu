@@ -123,6 +123,39 @@ __global__ void apply_deltas_kernel(const float4* __restrict__ deltas, const flo
     out[i] = decode_delta(boxes[i / k], deltas[i], wt, scale_clamp);
 }
 
+// backward of apply_deltas (what autograd produces for box_regression.py:87-115): one thread per box row, its k
+// class-specific deltas in a loop so that the gradient of the box itself (summed over k) needs no atomics.
+// torch.clamp(max=) passes the gradient where the input is <= the bound.
+__global__ void apply_deltas_backward_kernel(const float4* __restrict__ deltas, const float4* __restrict__ boxes,
+                                             const float4* __restrict__ grad_out, int64_t m, int k, CodecWeights wt,
+                                             float scale_clamp, float4* __restrict__ grad_deltas,
+                                             float4* __restrict__ grad_boxes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float4 box = boxes[i];
+    const float w = box.z - box.x, h = box.w - box.y;
+    float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < k; ++c) {
+        const float4 d = deltas[i * k + c], g = grad_out[i * k + c];
+        const float dx = d.x / wt.wx, dy = d.y / wt.wy;
+        const float dw_raw = d.z / wt.ww, dh_raw = d.w / wt.wh;
+        const float ew = expf((dw_raw > scale_clamp) ? scale_clamp : dw_raw);
+        const float eh = expf((dh_raw > scale_clamp) ? scale_clamp : dh_raw);
+        const float gcx = g.x + g.z, gcy = g.y + g.w;                   // d/d pred_ctr
+        const float gpw = 0.5f * (g.z - g.x), gph = 0.5f * (g.w - g.y);  // d/d pred_w, pred_h
+        if (grad_deltas)
+            grad_deltas[i * k + c] = make_float4(gcx * w / wt.wx, gcy * h / wt.wy,
+                                                 (dw_raw <= scale_clamp) ? gpw * ew * w / wt.ww : 0.0f,
+                                                 (dh_raw <= scale_clamp) ? gph * eh * h / wt.wh : 0.0f);
+        // pred_ctr = dx * w + (x1 + 0.5 w), pred_w = e^dw * w, w = x2 - x1
+        gb.x += gcx * (0.5f - dx) - gpw * ew;
+        gb.z += gcx * (0.5f + dx) + gpw * ew;
+        gb.y += gcy * (0.5f - dy) - gph * eh;
+        gb.w += gcy * (0.5f + dy) + gph * eh;
+    }
+    if (grad_boxes) grad_boxes[i] = gb;
+}
+
 // reference get_deltas on one (src, tgt) pair; operation order of box_regression.py:53-69
 __device__ __forceinline__ float4 encode_delta(const float4 s, const float4 t, const CodecWeights wt) {
     const float sw = s.z - s.x, sh = s.w - s.y;
@@ -366,6 +399,25 @@ int det_apply_deltas(const float* deltas, const float* boxes, int64_t m, int k, 
         reinterpret_cast<const float4*>(deltas), reinterpret_cast<const float4*>(boxes), total, k,
         CodecWeights{wx, wy, ww, wh}, scale_clamp, reinterpret_cast<float4*>(out));
     DET_LAUNCH_OK("apply_deltas_kernel");
+    return DET_OK;
+}
+
+int det_apply_deltas_backward(const float* deltas, const float* boxes, const float* grad_out, int64_t m, int k, float wx,
+                              float wy, float ww, float wh, float scale_clamp, float* grad_deltas, float* grad_boxes,
+                              void* stream) {
+    DET_CHECK_ARG(m >= 0 && k >= 1, "bad size");
+    if (m == 0) return DET_OK;
+    DET_CHECK_ARG(deltas && boxes && grad_out && (grad_deltas || grad_boxes), "null pointer");
+    if (!aligned16(deltas) || !aligned16(boxes) || !aligned16(grad_out) || (grad_deltas && !aligned16(grad_deltas)) ||
+        (grad_boxes && !aligned16(grad_boxes))) {
+        set_error("deltas/boxes/gradients must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    apply_deltas_backward_kernel<<<(unsigned)((m + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(deltas), reinterpret_cast<const float4*>(boxes),
+        reinterpret_cast<const float4*>(grad_out), m, k, CodecWeights{wx, wy, ww, wh}, scale_clamp,
+        reinterpret_cast<float4*>(grad_deltas), reinterpret_cast<float4*>(grad_boxes));
+    DET_LAUNCH_OK("apply_deltas_backward_kernel");
     return DET_OK;
 }
 

@@ -27,6 +27,7 @@ PROTOTYPES = {
     "det_pairwise_overlap": (c_i, [c_p, c_l, c_p, c_l, c_i, c_p, c_p]),
     "det_matched_iou": (c_i, [c_p, c_p, c_l, c_p, c_p]),
     "det_apply_deltas": (c_i, [c_p, c_p, c_l, c_i, c_f, c_f, c_f, c_f, c_f, c_p, c_p]),
+    "det_apply_deltas_backward": (c_i, [c_p, c_p, c_p, c_l, c_i, c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_p]),
     "det_get_deltas": (c_i, [c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_p, c_p, c_p]),
     "det_grid_anchors": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     "det_rpn_decode_level": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_f, c_f, c_f, c_f, c_f, c_p, c_p,
@@ -57,7 +58,7 @@ PROTOTYPES = {
     "det_match_workspace_bytes": (c_l, [c_i, c_l, c_l]),
     "det_match_anchors": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "det_match_quality": (c_i, [c_p, c_l, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
-    "det_subsample_labels": (c_i, [c_p, c_i, c_l, c_i, c_f, c_u64, c_p]),
+    "det_subsample_labels": (c_i, [c_p, c_i, c_l, c_i, c_d, c_u64, c_p]),
     "det_rpn_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f,
                            c_p, c_p, c_p, c_p, c_p]),
     "det_yolo_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
@@ -95,29 +96,31 @@ _lib = None
 
 
 def _build():
+    """object-detection-pytorch-rust_b200/build.py: a no-op when the in-tree .so matches the hash of the sources."""
     sys.path.insert(0, os.path.dirname(_HERE))
     try:
-        import build as _b  # object-detection-pytorch-rust_b200/build.py
+        import build as _b
         _b.build()
     finally:
         sys.path.pop(0)
 
 
 def lib():
-    """Load (building if necessary) the shared library.  Raises if it cannot be produced."""
+    """Load the shared library, (re)building it first when it is missing or STALE: build.needs_build() compares the hash
+    of csrc/ + include/ + the nvcc flags with the one recorded next to the .so, so an edited kernel can never run
+    against an old binary.  Raises if the library cannot be produced -- there is no fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        try:
-            _build()
-        except Exception as e:  # noqa: BLE001
-            raise ImportError(
-                f"det_b200: native library {_LIB_PATH} is missing and could not be built ({e}). "
-                "There is no CPU or PyTorch fallback for this package.") from e
+    try:
+        _build()
+    except Exception as e:  # noqa: BLE001
+        raise ImportError(
+            f"det_b200: native library {_LIB_PATH} is missing or stale and could not be built ({e}). "
+            "There is no CPU or PyTorch fallback for this package.") from e
     handle = ctypes.CDLL(_LIB_PATH)
     handle.det_abi_version.restype = c_i
-    if handle.det_abi_version() != 1:
+    if handle.det_abi_version() != 2:
         raise ImportError("det_b200: ABI version mismatch")
     _lib = handle
     return _lib

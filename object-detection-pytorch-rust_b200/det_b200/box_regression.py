@@ -36,14 +36,44 @@ class Box2BoxTransform:
         return out
 
     def apply_deltas(self, deltas: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
-        """(M,k*4),(M,4) -> (M,k*4) decoded boxes."""
+        """(M,k*4),(M,4) -> (M,k*4) decoded boxes.  Differentiable like the reference's (autograd through
+        det_apply_deltas_backward) whenever deltas or boxes require grad."""
         N.require_cuda(deltas, boxes)
+        if torch.is_grad_enabled() and (deltas.requires_grad or boxes.requires_grad):
+            return _ApplyDeltas.apply(deltas, boxes, self.weights, self.scale_clamp)
+        return _apply_deltas_forward(N.f32c(deltas), N.f32c(boxes), self.weights, self.scale_clamp)
+
+
+def _apply_deltas_forward(d: torch.Tensor, b: torch.Tensor, weights, scale_clamp: float) -> torch.Tensor:
+    m = d.shape[0]
+    k = (d.shape[1] // 4) if d.dim() == 2 else 1
+    out = torch.empty_like(d)
+    if m and k:
+        with torch.cuda.device(d.device):
+            N.call("det_apply_deltas", N.ptr(d), N.ptr(b), m, k, *weights, scale_clamp, N.ptr(out), N.stream())
+    return out
+
+
+class _ApplyDeltas(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, deltas, boxes, weights, scale_clamp):
         d, b = N.f32c(deltas), N.f32c(boxes)
+        ctx.weights, ctx.scale_clamp = weights, scale_clamp
+        ctx.dtypes = (deltas.dtype, boxes.dtype)
+        ctx.save_for_backward(d, b)
+        return _apply_deltas_forward(d, b, weights, scale_clamp)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d, b = ctx.saved_tensors
         m = d.shape[0]
         k = (d.shape[1] // 4) if d.dim() == 2 else 1
-        out = torch.empty_like(d)
+        need_d, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gd = torch.zeros_like(d) if need_d else None
+        gb = torch.zeros_like(b) if need_b else None
         if m and k:
+            go = N.f32c(grad_out)
             with torch.cuda.device(d.device):
-                N.call("det_apply_deltas", N.ptr(d), N.ptr(b), m, k, *self.weights, self.scale_clamp, N.ptr(out),
-                       N.stream())
-        return out
+                N.call("det_apply_deltas_backward", N.ptr(d), N.ptr(b), N.ptr(go), m, k, *ctx.weights, ctx.scale_clamp,
+                       N.ptr(gd), N.ptr(gb), N.stream())
+        return (gd.to(ctx.dtypes[0]) if need_d else None, gb.to(ctx.dtypes[1]) if need_b else None, None, None)

@@ -72,8 +72,9 @@ def add_ground_truth_to_proposals(gt_boxes: List[Boxes], proposals: List[Instanc
     out = []
     for gt_i, prop_i in zip(gt_boxes, proposals):
         dev = prop_i.objectness_logits.device
-        gt_prop = Instances(prop_i.image_size)
+        rec = type(prop_i)  # duck typing: the caller's own record class (e.g. the reference's Instances) comes back
+        gt_prop = rec(prop_i.image_size)
         gt_prop.proposal_boxes = gt_i
         gt_prop.objectness_logits = gt_logit_value * torch.ones(len(gt_i), device=dev)
-        out.append(Instances.cat([prop_i, gt_prop]))
+        out.append(rec.cat([prop_i, gt_prop]))
     return out

@@ -90,8 +90,10 @@ def _roi_align_levels(features: List[torch.Tensor], scales: Sequence[float], box
         assert f.dim() == 4 and f.shape[0] == n and f.shape[1] == c, "feature maps must share batch and channels"
     b = N.f32c(boxes)
     bi = batch_index.to(torch.int32).contiguous()
-    return _RoiAlignLevels.apply(b, bi, level, tuple(float(s) for s in scales), tuple(output_size), int(sampling_ratio),
-                                 bool(aligned), *feats)
+    out = _RoiAlignLevels.apply(b, bi, level, tuple(float(s) for s in scales), tuple(output_size), int(sampling_ratio),
+                                bool(aligned), *feats)
+    # the kernels compute in fp32; the result carries the feature maps' dtype like torchvision.ops.roi_align's does
+    return out if features[0].dtype == torch.float32 else out.to(features[0].dtype)
 
 
 class ROIAlign:

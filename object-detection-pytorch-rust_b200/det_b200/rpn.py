@@ -31,24 +31,30 @@ class Assignment:
 class _FusedRPNLoss(torch.autograd.Function):
     """Forward: one pass that reduces the BCE / L1 sums (no gradient stores).  Backward: the same kernel with the
     upstream gradients read on the device, writing grad_logits / grad_deltas.  `fused_losses(..., with_grads=True)`
-    is the single-launch fwd+bwd form used when the caller drives backward by hand."""
+    is the single-launch fwd+bwd form used when the caller drives backward by hand.
+
+    Everything the backward launch reads -- anchors and the four Assignment tensors -- is an explicit argument and
+    goes through save_for_backward: two forwards before one backward (gradient accumulation, multi-scale batches)
+    each keep their own anchors, and an in-place change of the labels between forward and backward (e.g. a later
+    subsample_labels_) trips autograd's version check instead of silently encoding against the wrong targets."""
 
     @staticmethod
-    def forward(ctx, logits, deltas, owner, asg, n_norm):
-        sums = owner._run_loss(logits, deltas, asg, n_norm, None, None, None)
-        ctx.owner, ctx.asg, ctx.n_norm = owner, asg, n_norm
-        ctx.save_for_backward(logits, deltas)
+    def forward(ctx, logits, deltas, anchors, labels, matched, gt_table, gt_offsets, owner, n_norm):
+        asg = Assignment(labels, matched, gt_table, gt_offsets)
+        sums = owner._run_loss(anchors, logits, deltas, asg, n_norm, None, None, None)
+        ctx.owner, ctx.n_norm = owner, n_norm
+        ctx.save_for_backward(logits, deltas, anchors, labels, matched, gt_table, gt_offsets)
         return sums
 
     @staticmethod
     def backward(ctx, grad_sums):
-        logits, deltas = ctx.saved_tensors
+        logits, deltas, anchors, labels, matched, gt_table, gt_offsets = ctx.saved_tensors
         up = grad_sums[:2].contiguous().float()
         gl = torch.empty_like(logits)
         gd = torch.empty_like(deltas)
-        scratch = ctx.owner._run_loss(logits, deltas, ctx.asg, ctx.n_norm, up, gl, gd)
-        del scratch
-        return gl, gd, None, None, None
+        ctx.owner._run_loss(anchors, logits, deltas, Assignment(labels, matched, gt_table, gt_offsets), ctx.n_norm, up,
+                            gl, gd)
+        return gl, gd, None, None, None, None, None, None, None
 
 
 class RegionProposalNetwork:
@@ -170,7 +176,7 @@ class RegionProposalNetwork:
         return gt_labels, matched_gt
 
     # ------------------------------------------------------------------ losses
-    def _run_loss(self, logits, deltas, asg: Assignment, n_norm, upstream, grad_logits, grad_deltas):
+    def _run_loss(self, anchors, logits, deltas, asg: Assignment, n_norm, upstream, grad_logits, grad_deltas):
         n, r = logits.shape
         dev = logits.device
         sums = torch.zeros((8,), dtype=torch.float32, device=dev)
@@ -182,7 +188,7 @@ class RegionProposalNetwork:
         w = self.box2box_transform.weights
         with torch.cuda.device(dev):
             N.call("det_rpn_loss", N.ptr(logits), N.ptr(deltas), N.ptr(asg.labels), N.ptr(asg.matched),
-                   N.ptr(asg.gt_table), N.ptr(asg.gt_offsets), N.ptr(self._anchors_for_loss), n, r, *w,
+                   N.ptr(asg.gt_table), N.ptr(asg.gt_offsets), N.ptr(anchors), n, r, *w,
                    self.box2box_transform.scale_clamp, 0 if self.box_reg_loss_type == "smooth_l1" else 1,
                    float(self.smooth_l1_beta), w_cls / norm, w_loc / norm, N.ptr(upstream), N.ptr(sums),
                    N.ptr(grad_logits), N.ptr(grad_deltas), N.stream())
@@ -198,14 +204,14 @@ class RegionProposalNetwork:
         the SAME launch (fused forward+backward, detached).  `num_images_global` = batch size over all data-parallel
         ranks (normaliser = batch_size_per_image * that, rpn.py:238)."""
         N.require_cuda(anchors, logits, deltas)
-        self._anchors_for_loss = N.f32c(anchors)
+        at = N.f32c(anchors)
         lg, dl = logits.contiguous(), deltas.contiguous()
         n_norm = lg.shape[0] if num_images_global is None else int(num_images_global)
         if with_grads:
             gl, gd = torch.empty_like(lg), torch.empty_like(dl)
-            sums = self._run_loss(lg.detach(), dl.detach(), asg, n_norm, None, gl, gd)
+            sums = self._run_loss(at, lg.detach(), dl.detach(), asg, n_norm, None, gl, gd)
         else:
-            sums = _FusedRPNLoss.apply(lg, dl, self, asg, n_norm)
+            sums = _FusedRPNLoss.apply(lg, dl, at, asg.labels, asg.matched, asg.gt_table, asg.gt_offsets, self, n_norm)
         out = {"cls_loss": sums[0], "loc_loss": sums[1], "num_pos_anchors": sums[2].detach(),
                "num_neg_anchors": sums[3].detach(), "sums": sums}
         if with_grads:

@@ -3,7 +3,6 @@
 re-exported by ``python/src/structures/__init__.py:1-13``).  The overlap arithmetic runs in
 ``det_pairwise_overlap`` / ``det_matched_iou`` (csrc/box_ops.cu); the containers only hold tensors.
 """
-import itertools
 from typing import Any, Dict, List, Tuple, Union
 
 import torch
@@ -128,99 +127,90 @@ def matched_boxlist_iou(boxes1, boxes2) -> torch.Tensor:
     return out
 
 
+def _cat_column(values: List[Any]) -> Any:
+    first = values[0]
+    if isinstance(first, torch.Tensor):
+        return torch.cat(values, dim=0)
+    if isinstance(first, list):
+        return [x for v in values for x in v]
+    if hasattr(type(first), "cat"):
+        return type(first).cat(values)
+    raise ValueError(f"Unsupported type {type(first)} for concatenation")
+
+
 class Instances:
-    """Per-image bag of equally long fields (reference: python/src/structures/instances.py:7-191)."""
+    """Per-image record: ``image_size`` plus any number of equally long columns (``proposal_boxes``,
+    ``objectness_logits``, ``gt_boxes``, ``gt_classes`` ...).
 
-    def __init__(self, image_size: Tuple[int, int], **kwargs: Any):
-        self._image_size = image_size
-        self._fields: Dict[str, Any] = {}
-        for k, v in kwargs.items():
-            self.set(k, v)
+    This is the boundary type of the reference's callables (python/src/structures/instances.py) and offers the calls
+    the hot path and its callers use -- attribute access, ``has/get/set/remove/get_fields``, ``len``, indexing, ``to``,
+    ``cat`` -- on an independent, much smaller implementation: columns are ordinary instance attributes.  The package
+    itself only relies on duck typing (``image_size``, ``gt_boxes``, ``proposal_boxes``, ``objectness_logits``,
+    ``gt_classes``, ``get_fields``), so the reference's own ``Instances`` objects can be passed in unchanged and
+    functions that extend a caller's record return the caller's class."""
 
-    @property
-    def image_size(self) -> Tuple[int, int]:
-        return self._image_size
+    def __init__(self, image_size: Tuple[int, int], **columns: Any):
+        object.__setattr__(self, "image_size", image_size)
+        for name, value in columns.items():
+            setattr(self, name, value)
 
-    def __setattr__(self, name: str, val: Any) -> None:
-        if name.startswith("_"):
-            super().__setattr__(name, val)
-        else:
-            self.set(name, val)
+    def __setattr__(self, name: str, value: Any) -> None:
+        assert name != "image_size", "image_size is fixed at construction"
+        cols = self.get_fields()
+        if cols and name not in cols:
+            assert len(value) == len(self), f"Adding a field of length {len(value)} to a Instances of length {len(self)}"
+        object.__setattr__(self, name, value)
 
-    def __getattr__(self, name: str) -> Any:
-        if name == "_fields" or name not in self._fields:
-            raise AttributeError(f"Cannot find field '{name}' in the given Instances!")
-        return self._fields[name]
-
-    def set(self, name: str, value: Any) -> None:
-        n = len(value)
-        if len(self._fields):
-            assert len(self) == n, f"Adding a field of length {n} to a Instances of length {len(self)}"
-        self._fields[name] = value
-
-    def has(self, name: str) -> bool:
-        return name in self._fields
-
-    def remove(self, name: str) -> None:
-        del self._fields[name]
-
-    def get(self, name: str) -> Any:
-        return self._fields[name]
+    set = __setattr__
 
     def get_fields(self) -> Dict[str, Any]:
-        return self._fields
+        return {k: v for k, v in vars(self).items() if k != "image_size"}
 
-    def to(self, *args: Any, **kwargs: Any) -> "Instances":
-        out = Instances(self._image_size)
-        for k, v in self._fields.items():
-            out.set(k, v.to(*args, **kwargs) if hasattr(v, "to") else v)
-        return out
+    def has(self, name: str) -> bool:
+        return name in self.get_fields()
 
-    def __getitem__(self, item: Union[int, slice, torch.Tensor]) -> "Instances":
-        if type(item) == int:
-            if item >= len(self) or item < -len(self):
-                raise IndexError("Instances index out of range!")
-            item = slice(item, None, len(self))
-        out = Instances(self._image_size)
-        for k, v in self._fields.items():
-            out.set(k, v[item])
-        return out
+    def get(self, name: str) -> Any:
+        return self.get_fields()[name]
+
+    def remove(self, name: str) -> None:
+        assert name != "image_size"
+        object.__delattr__(self, name)
 
     def __len__(self) -> int:
-        for v in self._fields.values():
-            return v.__len__()
+        for value in self.get_fields().values():
+            return len(value)
         raise NotImplementedError("Empty Instances does not support __len__!")
 
     def __iter__(self):
         raise NotImplementedError("`Instances` object is not iterable!")
 
+    def _map(self, fn) -> "Instances":
+        return type(self)(self.image_size, **{k: fn(v) for k, v in self.get_fields().items()})
+
+    def to(self, *args: Any, **kwargs: Any) -> "Instances":
+        return self._map(lambda v: v.to(*args, **kwargs) if hasattr(v, "to") else v)
+
+    def __getitem__(self, item: Union[int, slice, torch.Tensor]) -> "Instances":
+        if isinstance(item, int):
+            n = len(self)
+            if not -n <= item < n:
+                raise IndexError("Instances index out of range!")
+            item = slice(item % n, item % n + 1)
+        return self._map(lambda v: v[item])
+
     @staticmethod
     def cat(instance_lists: List["Instances"]) -> "Instances":
-        assert all(isinstance(i, Instances) for i in instance_lists)
         assert len(instance_lists) > 0
+        first = instance_lists[0]
         if len(instance_lists) == 1:
-            return instance_lists[0]
-        size = instance_lists[0].image_size
-        for i in instance_lists[1:]:
-            assert i.image_size == size
-        out = Instances(size)
-        for k in instance_lists[0]._fields.keys():
-            vals = [i.get(k) for i in instance_lists]
-            v0 = vals[0]
-            if isinstance(v0, torch.Tensor):
-                vals = torch.cat(vals, dim=0)
-            elif isinstance(v0, list):
-                vals = list(itertools.chain(*vals))
-            elif hasattr(type(v0), "cat"):
-                vals = type(v0).cat(vals)
-            else:
-                raise ValueError(f"Unsupported type {type(v0)} for concatenation")
-            out.set(k, vals)
+            return first
+        assert all(i.image_size == first.image_size for i in instance_lists)
+        out = type(first)(first.image_size)
+        for name in first.get_fields():
+            out.set(name, _cat_column([i.get(name) for i in instance_lists]))
         return out
 
-    def __str__(self) -> str:
-        fields = ", ".join(f"{k}: {v}" for k, v in self._fields.items())
-        return (f"Instances(num_instances={len(self)}, image_height={self._image_size[0]}, "
-                f"image_width={self._image_size[1]}, fields=[{fields}])")
-
-    __repr__ = __str__
+    def __repr__(self) -> str:
+        cols = ", ".join(f"{k}: {v}" for k, v in self.get_fields().items())
+        return (f"Instances(num_instances={len(self) if self.get_fields() else 0}, image_height={self.image_size[0]}, "
+                f"image_width={self.image_size[1]}, fields=[{cols}])")

@@ -164,20 +164,22 @@ class YoloHostPipeline:
 
 
 class _FusedYoloLoss(torch.autograd.Function):
+    """Everything the backward launch reads is saved with save_for_backward (no state on the owner)."""
+
     @staticmethod
-    def forward(ctx, head, owner, asg, gt_classes, norm):
-        sums = owner._run_loss(head, asg, gt_classes, norm, None, None)
-        ctx.owner, ctx.asg, ctx.gt_classes, ctx.norm = owner, asg, gt_classes, norm
-        ctx.save_for_backward(head)
+    def forward(ctx, head, labels, matched, gt_table, gt_offsets, gt_classes, owner, norm):
+        sums = owner._run_loss(head, YoloAssignment(labels, matched, gt_table, gt_offsets), gt_classes, norm, None, None)
+        ctx.owner, ctx.norm = owner, norm
+        ctx.save_for_backward(head, labels, matched, gt_table, gt_offsets, gt_classes)
         return sums
 
     @staticmethod
     def backward(ctx, grad_sums):
-        (head,) = ctx.saved_tensors
+        head, labels, matched, gt_table, gt_offsets, gt_classes = ctx.saved_tensors
         up = grad_sums[:3].contiguous().float()
         gh = torch.empty_like(head)
-        ctx.owner._run_loss(head, ctx.asg, ctx.gt_classes, ctx.norm, up, gh)
-        return gh, None, None, None, None
+        ctx.owner._run_loss(head, YoloAssignment(labels, matched, gt_table, gt_offsets), gt_classes, ctx.norm, up, gh)
+        return gh, None, None, None, None, None, None, None
 
 
 class YoloAssignment:
@@ -267,7 +269,7 @@ class YoloGridTrainer:
             gh = torch.empty_like(ht)
             sums = self._run_loss(ht.detach(), asg, gc, norm, None, gh, peer)
         else:
-            sums = _FusedYoloLoss.apply(ht, self, asg, gc, norm)
+            sums = _FusedYoloLoss.apply(ht, asg.labels, asg.matched, asg.gt_table, asg.gt_offsets, gc, self, norm)
         out = {"loc_loss": sums[0], "obj_loss": sums[1], "cls_loss": sums[2], "num_pos": sums[3].detach(),
                "num_neg": sums[4].detach(), "sums": sums}
         if with_grads:

@@ -64,6 +64,29 @@ def test_apply_deltas(det, O, weights, k):
     assert_boxes_close(got.reshape(-1, 4), want.reshape(-1, 4), rtol=1e-5)
 
 
+@pytest.mark.parametrize("k", [1, 3])
+def test_apply_deltas_is_differentiable_like_the_reference(det, O, k):
+    """box_regression.py:75-115 is plain torch: autograd flows to the deltas (and the boxes).  The drop-in's backward
+    kernel (det_apply_deltas_backward) must give the same gradients, including the clamp(max=) mask."""
+    g = gen(13)
+    w = (10.0, 10.0, 5.0, 5.0)
+    boxes = rand_boxes(777, g=g)
+    deltas = torch.randn(777, 4 * k, generator=g) * 3
+    deltas[5, 2] = 40.0  # dw = 8 > scale_clamp: clamped, zero gradient
+    up = torch.randn(777, 4 * k, generator=g)
+    d0, b0 = deltas.clone().requires_grad_(True), boxes.clone().requires_grad_(True)
+    (O.apply_deltas(d0, b0, w) * up).sum().backward()
+    d1, b1 = deltas.cuda().requires_grad_(True), boxes.cuda().requires_grad_(True)
+    out = det.Box2BoxTransform(w, O.DEFAULT_SCALE_CLAMP).apply_deltas(d1, b1)
+    assert out.requires_grad
+    (out * up.cuda()).sum().backward()
+    assert float(d1.grad[5, 2]) == 0.0
+    torch.testing.assert_close(d1.grad.cpu(), d0.grad, rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(b1.grad.cpu(), b0.grad, rtol=2e-5, atol=1e-4)
+    # no graph is built when nothing requires grad
+    assert not det.Box2BoxTransform(w).apply_deltas(deltas.cuda(), boxes.cuda()).requires_grad
+
+
 def test_apply_deltas_known_answer(det):
     # SURVEY.md section 4: weights (10,10,5,5), box [0,0,10,20], delta [1,2,30,-1] -> dw clamped to log(1000/16)
     import math

@@ -159,8 +159,45 @@ def test_huge_segment_with_nan_and_tied_scores(det, O):
     assert int(kc[0]) == want.numel() and torch.equal(keep[0, :want.numel()].cpu(), want)
 
 
+# ---- BASELINE configs[4] sizes against the oracle itself (kept indices + counts bit-exact).  40 500 boxes crosses the
+#      reference's own >= 40000 branch (python/src/utils.py:108-119: per-id loop + argsort instead of torchvision's
+#      batched_nms); torch.rand fp32 scores tie at these sizes, ties resolve by lower index.
+@pytest.mark.parametrize("m,ncat,frame,seed", [
+    (40500, 30, 1024.0, 11),    # the reference's branch point
+    (50000, 80, 1024.0, 12),
+    (100000, 80, 1024.0, 13),
+    (50000, 1, 1024.0, 14),     # single-category worst case: one 50k-box segment
+    (100000, 3, 1024.0, 15),    # three ~33k-box segments (cooperative huge-segment sweep)
+])
+def test_batched_nms_matches_oracle_at_cfg5_sizes(det, O, m, ncat, frame, seed):
+    g = gen(seed)
+    b = rand_boxes(m, frame, g, 0.2)
+    s = torch.rand(m, generator=g)
+    c = torch.randint(0, ncat, (m,), generator=g)
+    want = O.batched_nms(b, s, c, 0.5)
+    got = det.batched_nms(b.cuda(), s.cuda(), c.cuda(), 0.5).cpu()
+    assert got.numel() == want.numel()
+    assert torch.equal(got, want)
+
+
+def test_nms_images_cfg5_batch_of_8_at_50k(det, O):
+    """configs[4] as it is sharded: 8 images per GPU in one call, ragged counts around 50 000 boxes, 80 categories."""
+    n, m = 8, 50000
+    g = gen(77)
+    counts = [m, m - 1, 40000, 39999, 45000, 50000, 12345, 1000]
+    bs = rand_boxes(n * m, 1024.0, g, 0.2).view(n, m, 4)
+    ss = torch.rand(n, m, generator=g)
+    cs = torch.randint(0, 80, (n, m), generator=g)
+    keep, cnt = det.nms_images(bs.cuda(), ss.cuda(), cs.cuda(), torch.tensor(counts, dtype=torch.int32).cuda(), 0.5)
+    for i in range(n):
+        k = counts[i]
+        want = O.batched_nms(bs[i, :k], ss[i, :k], cs[i, :k], 0.5)
+        assert int(cnt[i]) == want.numel()
+        assert torch.equal(keep[i, :want.numel()].cpu(), want)
+
+
 def test_nms_properties_at_100k_boxes(det, O):
-    """BASELINE configs[4] size, where the O(M^2) oracle is out of reach: size-independent properties of greedy NMS.
+    """BASELINE configs[4] size: size-independent properties of greedy NMS (the oracle-equality cases are above).
     (1) kept indices are unique, valid and in descending-score order; (2) idempotence: NMS of the kept set keeps
     everything, in the same order; (3) no kept box is suppressed by an earlier kept box (sampled pairs);
     (4) every dropped box of a sample is suppressed by some kept box with a higher score."""

@@ -109,6 +109,21 @@ def test_device_subsample_counts_and_uniformity(det, O):
     assert abs(float(frac.mean()) - 128 / 300) < 1e-6 and float(frac.min()) > 0.25 and float(frac.max()) < 0.6
 
 
+@pytest.mark.parametrize("num_samples,frac", [(100, 0.29), (100, 0.57), (256, 0.5), (512, 0.25), (7, 0.3)])
+def test_device_subsample_positive_cap_is_the_python_double_product(det, O, num_samples, frac):
+    """utils.py:63 int(num_samples * positive_fraction) in Python double: 100 * 0.29 -> 28 (fp32 would give 29)."""
+    g = gen(21)
+    r = 4000
+    lab = torch.full((1, r), -1, dtype=torch.int8)
+    perm = torch.randperm(r, generator=g)
+    lab[0, perm[:600]] = 1
+    lab[0, perm[600:3000]] = 0
+    out = det.subsample_labels_(lab.cuda().clone(), num_samples, frac, seed=3).cpu()
+    wp, wn = O.subsample_counts(600, 2400, num_samples, frac)
+    assert wp == int(num_samples * frac)
+    assert int((out[0] == 1).sum()) == wp and int((out[0] == 0).sum()) == wn
+
+
 def test_device_subsample_dense_class_walks_a_permutation(det, O):
     """A class that holds >= 1/8 of the anchors (RPN background) is sampled by walking a pseudo-random permutation of the
     row: exact counts, subset of the class, reproducible, and uniform over the class."""
