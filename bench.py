@@ -9,15 +9,19 @@ Primary workload (BASELINE.json configs[1]): YOLO-style 7x7x(2*5+20) head, batch
 threshold 0.25, per-class NMS IoU 0.5, top-300 detections per image.  A step = one batch through the fused
 decode+NMS kernel.  Weak scaling: every rank owns its own batches, no collective on the inference path.
 
-Prints ONE JSON line (rank 0).  `value` is device-timed (inputs resident in HBM, rotating over a pool larger than
-L2, CUDA-graph replay in which consecutive, independent batches rotate over 4 streams so that the tail of one launch
-overlaps the head of the next); `e2e` goes through the public Python API with pinned host buffers, H2D + D2H inside the timed
-region; `roofline` is the fused kernel's algorithmic bytes / measured launch time against MEASURED_PEAKS.json;
-`cpu_baseline` is the CPU oracle (torch CPU ops + C greedy NMS) on a bounded sample; `extras` carries the training
-step (assignment + loss fwd/bwd, BASELINE configs[2]: Python loop with an NCCL all-reduce, with the all-reduce over
-NVLink peer memory -- separate kernel, fused into the loss kernel, and the whole step replayed from a CUDA graph) and the
-dense-head decode / decode+threshold+NMS with their rooflines (configs[3]).  The e2e pipeline moves the detection
-indices as int32 (same values as detect()'s int64 `flat`); `e2e.int64_indices` is the int64 wire format.
+Prints ONE JSON line (rank 0).  `value` is device-timed: inputs resident in HBM and rotating over a pool larger than L2,
+one CUDA graph = one pass over the pool (one kernel launch per step, on a single stream unless --lanes > 1), and the timed
+region is a whole number of graph replays covering at least --steps steps and at least --min-ms milliseconds, so
+`--steps 20` exercises exactly the launch path `--steps 20000` does (`timing.timed_steps` is the number actually timed,
+`ms_per_step` their mean).  `e2e` goes through the public Python API with pinned host buffers, H2D + D2H inside the timed
+region (same rule: at least --steps steps and --min-ms ms per segment, median of three segments).  `roofline` is the
+fused kernel's algorithmic bytes / measured launch time against MEASURED_PEAKS.json, `roofline.others` the fractions of
+the HBM-bound kernels of the path.  `cpu_baseline` is the CPU oracle (torch CPU ops + C greedy NMS) on a bounded sample.
+`extras` carries the detail: the training step (assignment + loss fwd/bwd, BASELINE configs[2]), the dense head
+(configs[3]) and pairwise IoU (configs[4]) with their rooflines; `train` (printed last, mirrored in `e2e`) is the compact
+per-N training summary, with `peer_equals_nccl` = the NVLink peer-memory all-reduce checked against NCCL on the real
+ranks.  The e2e pipeline moves the detection indices as int32 (same values as detect()'s int64 `flat`);
+`e2e.int64_indices` is the int64 wire format.
 """
 import argparse
 import json
@@ -207,8 +211,8 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "images/sec decode+NMS", "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": n_img, "grid": S, "boxes": B, "classes": C,
-                   "score_thresh": SCORE_THR, "iou_thresh": IOU_THR, "max_det": MAX_DET},
+        "config": bench_config(),
+        "timing": {"images_per_step": n_img},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": pool.cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -369,7 +373,6 @@ def extras_train(det, dev, world, peak, quick):
     logits = torch.randn(nb, R, device=dev)
     deltas = torch.randn(nb, R, 4, device=dev) * 0.5
     gl, gd = torch.empty_like(logits), torch.empty_like(deltas)
-    rpn._anchors_for_loss = anchors
     st = {"seed": 0}
 
     def step_assign():
@@ -379,7 +382,7 @@ def extras_train(det, dev, world, peak, quick):
         st["asg"] = det.Assignment(labels, matched, gtb2, off2)
 
     def step_loss():
-        sums = rpn._run_loss(logits, deltas, st["asg"], nb * world, None, gl, gd)
+        sums = rpn._run_loss(anchors, logits, deltas, st["asg"], nb * world, None, gl, gd)
         prev = st.get("pending")
         st["pending"] = det.dist.allreduce_sums_async(sums)
         if prev is not None:
@@ -394,7 +397,8 @@ def extras_train(det, dev, world, peak, quick):
     assign_bytes = nb * 9 * R + 16 * tot2
     out["train_rpn_r50127"] = {
         "workload": f"RPN form R=50127, batch {nb}/GPU: match+subsample, fused loss fwd+bwd (+8-float allreduce)",
-        "ms_assign": ms_a, "ms_loss_fwd_bwd": ms_l, "images_per_s_per_gpu": nb / (ms_a + ms_l) * 1e3,
+        "ms_assign": ms_a, "ms_loss_fwd_bwd": ms_l, "ms_step": ms_a + ms_l, "batch": nb,
+        "images_per_s_per_gpu": nb / (ms_a + ms_l) * 1e3, "images_per_s_total": world * nb / (ms_a + ms_l) * 1e3,
         "loss_roofline": {"bound": "hbm", "achieved": loss_moved / ms_l / 1e6, "peak": peak, "unit": "GB/s",
                           "frac": loss_moved / ms_l / 1e6 / peak, "algorithmic_bytes": loss_moved,
                           "formula": "N*(21R) + sampled rows: label read + grad_logits/grad_deltas written everywhere, "
@@ -488,16 +492,121 @@ def extras_dense(det, dev, peak, quick):
     return out
 
 
+def extras_iou(det, dev, peak, quick):
+    """pairwise IoU (reference structures/boxes.py:193) at M = 20 000 x 20 000 (BASELINE configs[4]: the largest materialised
+    matrix of the sweep, 1.6 GB written)."""
+    m = 4000 if quick else 20000
+    g = torch.Generator().manual_seed(4)
+    xy = torch.rand(2 * m, 2, generator=g) * 0.8 * 1024
+    wh = torch.rand(2 * m, 2, generator=g) * 0.2 * 1024 + 1
+    bx = torch.cat([xy, xy + wh], 1).to(dev)
+    b1, b2 = det.Boxes(bx[:m]), det.Boxes(bx[m:])
+    det.pairwise_iou(b1, b2)
+    ms = time_region(lambda: det.pairwise_iou(b1, b2), 3 if quick else 10, warm=2)  # allocates its (M,M) output per call
+    nbytes = 16 * (m + m) + 4 * m * m
+    return {"pairwise_iou": {"workload": f"pairwise_iou {m} x {m} boxes, matrix materialised", "ms": ms,
+                             "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                          "frac": nbytes / ms / 1e6 / peak, "algorithmic_bytes": nbytes,
+                                          "formula": "16(N+M) + 4NM (SURVEY 8d)",
+                                          "traffic": load_traffic(f"pairwise_overlap_kernel_m{m}")},
+                             "pair_ious_per_s": m * m / ms * 1e3}}
+
+
+def _r(x, nd=4):
+    return None if x is None else round(float(x), nd)
+
+
+def train_summary(extras, world):
+    """Compact training-side numbers (BASELINE metric "loss fwd/bwd at 1/2/4/8 B200"): printed LAST in the JSON line and
+    mirrored into e2e so that the driver's retained fields carry them.  Weak scaling: 1024 images per GPU per step."""
+    out = {"scaling": "weak", "images_per_gpu_per_step": 1024, "n_gpus": world}
+    r = extras.get("train_rpn_r50127")
+    if r:
+        out["rpn_r50127"] = {"ms_step": _r(r.get("ms_step")), "ms_assign": _r(r.get("ms_assign")),
+                             "ms_loss": _r(r.get("ms_loss_fwd_bwd")), "img_s_total": _r(r.get("images_per_s_total"), 0),
+                             "assign_frac": _r(r["assign_roofline"]["frac"], 3), "loss_frac": _r(r["loss_roofline"]["frac"], 3),
+                             "batch": r.get("batch")}
+    g = extras.get("train_grid_b1024")
+    if g:
+        out["grid7x7x30"] = {"ms_nccl": _r(g.get("ms_per_step")), "ms_peer": _r(g.get("ms_per_step_peer_exchange")),
+                            "ms_fused_peer": _r(g.get("ms_per_step_fused_peer_exchange")),
+                            "ms_graph_fused_peer": _r(g.get("ms_per_step_graph_fused_peer_exchange"))}
+        best = min(v for v in out["grid7x7x30"].values() if v)
+        out["grid7x7x30"]["img_s_total_best"] = round(world * 1024 / best * 1e3)
+    return out
+
+
+def others_summary(extras):
+    """roofline fractions of the HBM-bound kernels of the path (each measured in extras with its byte formula)."""
+    out = {}
+    for n in (32, 256):
+        e = extras.get(f"dense_head_25200x80_b{n}")
+        if e:
+            out[f"dense_detect_b{n}"] = _r(e["detect_thresholded"]["roofline"]["frac"], 3)
+            out[f"dense_decode_b{n}"] = _r(e["decode_roofline"]["frac"], 3)
+    r = extras.get("train_rpn_r50127")
+    if r:
+        out["rpn_loss_fwd_bwd"] = _r(r["loss_roofline"]["frac"], 3)
+        out["rpn_assign"] = _r(r["assign_roofline"]["frac"], 3)
+    p = extras.get("pairwise_iou")
+    if p:
+        out["pairwise_iou_20k"] = _r(p["roofline"]["frac"], 3)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
+def bench_config():
+    """The workload description both arms print (identical keys and values: the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu_per_step": BATCH, "grid": S, "boxes": B, "classes": C,
+            "image": list(IMG), "score_thresh": SCORE_THR, "iou_thresh": IOU_THR, "max_det": MAX_DET}
+
+
+def all_ranks_max_int(v, world, dev):
+    if world > 1:
+        t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return int(t.item())
+    return int(v)
+
+
+def peer_equals_nccl(det, dev, world):
+    """PeerSums (NVLink peer-memory SUM, csrc/peer.cu) against NCCL's all_reduce of the same vectors, on the real ranks:
+    three exchanged steps + the flush.  Equal means bitwise or within 1e-6 relative (the summation order may differ)."""
+    ps = det.dist.PeerSums(dev)
+    rank = ps.rank
+    ok = True
+    vecs = [torch.arange(8, dtype=torch.float32, device=dev) * (0.37 + step) + (rank + 1) * 1.25 + step for step in range(4)]
+    want = []
+    for v in vecs:
+        w = v.clone()
+        det.dist.allreduce_sums_(w)
+        want.append(w)
+    got = []
+    for v in vecs:
+        prev = ps.exchange(v)
+        if prev is not None:
+            got.append(prev.clone())
+    got.append(ps.flush().clone())
+    ps.check()
+    for g_, w_ in zip(got, want):
+        ok = ok and bool(torch.equal(g_, w_) or torch.allclose(g_, w_, rtol=1e-6, atol=0.0))
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    return bool(int(flag.item()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--quick", action="store_true", help="smaller extras / CPU sample (CI)")
-    ap.add_argument("--lanes", type=int, default=4, help="streams the independent steps rotate over inside the graph (1-4)")
+    ap.add_argument("--lanes", type=int, default=1,
+                    help="streams the independent steps rotate over inside the graph (1 = the caller's single stream)")
+    ap.add_argument("--min-ms", type=float, default=60.0, help="lower bound of every timed region (whole graph replays)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -520,23 +629,23 @@ def main():
     img_bytes = S * S * (B * 5 + C) * 4
     pool = L2_BYTES // (BATCH * img_bytes) + 8  # rotating pool of input batches larger than L2
     heads = make_heads(pool, 1 + rank).to(dev)
-    outs = [yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET) for i in range(4)]
+    n_out = 4
+    outs = [yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET) for i in range(n_out)]
     torch.cuda.synchronize()
 
-    # CUDA graph with one launch per pool entry (launch-bound loop -> graph replay)
-    graph = torch.cuda.CUDAGraph()
+    # ONE CUDA graph = one pass over the pool: `pool` launches of the fused kernel, one per step, each on its own input
+    # batch (the pool is larger than L2), outputs rotating over 4 buffers.  The timed region is a whole number of
+    # replays of that graph, however few --steps asks for: the launch path is the same for --steps 20 and --steps 20000.
+    n_lanes = max(1, min(4, args.lanes))
+    lanes = [torch.cuda.Stream() for _ in range(n_lanes - 1)]
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for i in range(3):
-            yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+            yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % n_out])
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    # Consecutive steps are independent batches (own inputs, outputs rotating over 4 buffers): inside the graph they
-    # rotate over up to four streams (one per output buffer), so the tail of one launch (256 CTAs on 148 SMs leave 40 SMs half empty) overlaps
-    # the head of the next instead of idling.  One kernel launch per step either way.
-    n_lanes = max(1, min(4, args.lanes))
-    lanes = [torch.cuda.Stream() for _ in range(n_lanes - 1)]
+    graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         cap = torch.cuda.current_stream()
         for st_ in lanes:
@@ -544,55 +653,54 @@ def main():
         for i in range(pool):
             lane = i % n_lanes
             if lane == 0:
-                yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+                yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % n_out])
             else:
                 with torch.cuda.stream(lanes[lane - 1]):
-                    yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
+                    yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % n_out])
         for st_ in lanes:
             cap.wait_stream(st_)
-    launches = {"n": 0}
 
-    def run_steps(k):
-        full, rem = divmod(k, pool)
-        for _ in range(full):
-            graph.replay()
-        for i in range(rem):
-            yh.detect(heads[i], SCORE_THR, IOU_THR, max_det=MAX_DET, out=outs[i % 4])
-        launches["n"] += k
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(2, -(-args.warmup // pool))):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(2):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    est_replay_ms = max(e0.elapsed_time(e1) / 2, 1e-3)
+    replays = max(-(-args.steps // pool), int(math.ceil(args.min_ms / est_replay_ms)))
+    replays = all_ranks_max_int(replays, world, dev)
+    timed_steps = replays * pool
 
-    run_steps(args.warmup)
     sampler = ClockSampler(local)
     barrier(world)
     sampler.start()
-    launches["n"] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run_steps(args.steps)
+    for _ in range(replays):
+        graph.replay()
     e1.record()
     barrier(world)
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    ms_step = ms_total / args.steps
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    ms_step = ms_total / timed_steps
+    value = world * BATCH * timed_steps / (ms_total * 1e-3)
 
     # algorithmic bytes of one launch: logits read + kept detections written (fused: no decode hand-off)
     kept = sum(int(o["count"].sum()) for o in outs) / len(outs)
     algo_bytes = BATCH * img_bytes + kept * (8 + 16 + 4) + BATCH * 4
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
-    # achieved = algorithmic bytes x launches / timed region: the launches of consecutive steps overlap (4 streams), so
-    # this is the GPU's sustained rate on this kernel, not one launch in isolation (22 us alone under ncu)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic("yolo_fast_kernel"), "kernel": "yolo_fast_kernel<640,2,7,2,20>",
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                "note": "3.7 MB per launch = 0.6 us at the HBM peak: a 256-image launch (one CTA per image) is bound by "
-                        "instruction issue of the per-image NMS (issue slots ~75 % busy with 4 launches overlapped), "
-                        "not by HBM; the HBM-bound kernels of this path (dense-head decode, loss fwd+bwd) are in "
-                        "extras with their own rooflines"}
+                "note": "3.7 MB per launch = 0.6 us at the HBM peak: a 256-image launch is bound by launch latency and "
+                        "instruction issue of the per-image NMS, not by HBM; the HBM-bound kernels of this path "
+                        "(dense-head decode+NMS, loss fwd+bwd, assignment, pairwise IoU) are in `others`"}
 
     # end to end through the public API (det.YoloHostPipeline) with HOST buffers: every step uploads its batch from
     # pinned host memory, runs the fused kernel and downloads the detections; H2D / kernel / D2H of consecutive
     # steps overlap on the pipeline's per-slot streams.  The timed region ends when the last result is on the host.
-    e2e_steps = max(3, min(args.steps, 2000))
     depth = int(os.environ.get("DET_E2E_DEPTH", "8"))  # pipeline slots (streams / graphs in flight)
     host_src = make_heads(depth, 100 + rank)
 
@@ -617,7 +725,12 @@ def main():
             seen += int(pipe.wait(i % depth)["count"][0])
         return seen
 
-    e2e_run(2 * depth)
+    e2e_run(4 * depth)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_run(8 * depth)
+    est_step_ms = max((time.perf_counter() - t0) * 1e3 / (8 * depth), 1e-3)
+    e2e_steps = all_ranks_max_int(max(args.steps, int(math.ceil(args.min_ms / est_step_ms))), world, dev)
     # three back-to-back segments, the median is reported (host-side jitter on a shared box shows up as one slow segment)
     seg_ms, seg_wall = [], []
     for _ in range(3):
@@ -647,16 +760,28 @@ def main():
     ms64 = max_over_ranks(max(e0.elapsed_time(e1), 0.0), world, dev)
     e2e["int64_indices"] = {"value": world * BATCH * e2e_steps / (ms64 * 1e-3), "d2h_bytes_per_step": pipe.d2h_bytes,
                             "ms_per_step": ms64 / e2e_steps}
+    del pipe
 
-    extras = {}
+    extras, train, others = {}, {}, {}
     if not args.no_extras:
+        try:
+            train["peer_equals_nccl"] = peer_equals_nccl(det, dev, world)
+        except Exception as e:  # noqa: BLE001
+            train["peer_equals_nccl"] = False
+            train["peer_error"] = f"{type(e).__name__}: {e}"[:160]
         try:
             extras.update(extras_train(det, dev, world, peak, args.quick))
             if world == 1 or rank == 0:
                 extras.update(extras_dense(det, dev, peak, args.quick))
+                extras.update(extras_iou(det, dev, peak, args.quick))
         except Exception as e:  # noqa: BLE001
             extras["error"] = f"{type(e).__name__}: {e}"
         barrier(world)
+        train.update(train_summary(extras, world))
+        others = others_summary(extras)
+        e2e["peer_equals_nccl"] = train["peer_equals_nccl"]
+        e2e["train"] = train
+    roofline["others"] = others
 
     cpu_baseline = None
     if rank == 0:
@@ -676,17 +801,23 @@ def main():
                         "sample": f"{reps} passes over one {BATCH}-image batch of the same synthetic distribution "
                                   f"({dt:.1f} s), each split over {cpu_pool.cores} single-threaded worker processes: oracle "
                                   "torch-CPU decode + C greedy NMS, per-image loop"}
-        print(json.dumps({
+        lane_txt = ("all on the caller's single stream" if n_lanes == 1 else
+                    f"consecutive (independent) batches rotate over {n_lanes} streams inside the graph")
+        line = {
             "metric": "images/sec decode+NMS", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": BATCH, "grid": S, "boxes": B, "classes": C,
-                       "image": list(IMG), "score_thresh": SCORE_THR, "iou_thresh": IOU_THR, "max_det": MAX_DET,
+            "config": bench_config(),
+            "timing": {"timed_steps": timed_steps, "timed_ms": ms_total, "graph_replays": replays,
+                       "steps_per_replay": pool, "lanes": n_lanes,
+                       "launch": f"CUDA graph replay: one graph = {pool} launches (one kernel per step), {lane_txt}; the "
+                                 f"timed region is {replays} whole replays (>= --steps and >= {args.min_ms:.0f} ms)",
                        "l2": f"inputs rotate over a pool of {pool} batches = {pool * BATCH * img_bytes / 2**20:.0f} MiB "
-                             "> 126 MiB L2", "launch": "CUDA graph replay, one kernel per step; consecutive (independent) batches alternate between two streams inside the graph"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "extras": extras,
-        }))
+                             "> 126 MiB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": timed_steps, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "extras": extras, "train": train,
+        }
+        print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
