@@ -364,51 +364,97 @@ def extras_train(det, dev, world, peak, quick):
                                                          "buffer + step stamps, no NCCL launch"})
     except Exception as e:  # noqa: BLE001
         out["train_grid_b1024"]["peer_exchange_error"] = f"{type(e).__name__}: {e}"
-    # (ii) reference-native RPN form: R = 50127 anchors (FPN-18 @ 448), Matcher([0.3,0.7]), 256 samples, L1 + BCE
-    rpn = det.RegionProposalNetwork([4, 8, 16, 32, 64])
-    anchors = torch.cat(rpn.anchor_generator.grid_anchors([(448 // s, 448 // s) for s in (4, 8, 16, 32, 64)], dev), 0)
+    # (ii) reference-native RPN form: R = 50127 anchors (FPN-18 @ 448), Matcher([0.3,0.7]), 256 samples, L1 + BCE, from the
+    #      head convolutions' own NCHW outputs: det_match_grid (2 launches) -> det_subsample_labels_grid ->
+    #      det_rpn_loss_sampled (forward + backward into persistent NCHW gradient buffers) -- 4 launches per step.
+    strides = (4, 8, 16, 32, 64)
+    rpn = det.RegionProposalNetwork(list(strides))
+    hw = [(448 // s, 448 // s) for s in strides]
+    anchors = torch.cat(rpn.anchor_generator.grid_anchors(hw, dev), 0)
+    grid = rpn.anchor_generator.grid_layout(hw)
     R = anchors.shape[0]
     nb = 256 if quick else 1024
     gtb2, _, off2, tot2 = synth_gt(nb, 3, dev)
-    logits = torch.randn(nb, R, device=dev)
-    deltas = torch.randn(nb, R, 4, device=dev) * 0.5
-    gl, gd = torch.empty_like(logits), torch.empty_like(deltas)
-    st = {"seed": 0}
+    obj = [torch.randn(nb, 3, h, w, device=dev) for h, w in hw]
+    dlt = [torch.randn(nb, 12, h, w, device=dev) * 0.5 for h, w in hw]
+    g_obj, g_dlt = [torch.zeros_like(o) for o in obj], [torch.zeros_like(d) for d in dlt]
+    st = {"seed": 0, "prev": None}
+    m = rpn.anchor_matcher
 
-    def step_assign():
-        matched, labels = rpn.anchor_matcher.match_packed(gtb2, off2, nb, anchors)
+    def assign_only():
+        matched, labels, stats = m.match_packed(gtb2, off2, nb, anchors, grid=grid, with_stats=True)
+        return matched, labels, stats
+
+    def sample_only(matched, labels, stats):
         st["seed"] += 1
-        det.subsample_labels_(labels, 256, 0.5, st["seed"])
-        st["asg"] = det.Assignment(labels, matched, gtb2, off2)
+        _, samples, counts = det.subsample_labels_(labels, 256, 0.5, st["seed"], stats=stats, return_samples=True)
+        return det.Assignment(labels, matched, gtb2, off2, samples, counts)
 
-    def step_loss():
-        sums = rpn._run_loss(anchors, logits, deltas, st["asg"], nb * world, None, gl, gd)
+    def loss_only(asg):
+        sums = rpn._run_sampled(anchors, obj, dlt, asg, nb * world, None, (g_obj, g_dlt), st["prev"])
+        st["prev"] = (asg.samples, asg.sample_count)
+        return sums
+
+    def step_full():
+        sums = loss_only(sample_only(*assign_only()))
         prev = st.get("pending")
-        st["pending"] = det.dist.allreduce_sums_async(sums)
+        st["pending"] = det.dist.allreduce_sums_async(sums)  # waited for one step late: the scalars are only logged
         if prev is not None:
             prev.wait()
 
-    ms_a = time_region(step_assign, 5 if quick else 20)
-    ms_l = time_region(step_loss, 5 if quick else 20)
+    it = 5 if quick else 20
+    ms_step = time_region(step_full, it)
+    if st.get("pending") is not None:
+        st["pending"].wait()
+    ms_match = time_region(lambda: st.__setitem__("mls", assign_only()), it)
+    asg0 = sample_only(*st["mls"])
+    ms_loss = time_region(lambda: loss_only(asg0), it)
+    # the same step replayed from a CUDA graph (two steps per graph: the persistent gradient buffers' clear lists ping-pong)
+    ms_graph = None
+    try:
+        keep = []
+
+        def graph_step():
+            asg = sample_only(*assign_only())
+            keep.append(asg)
+            loss_only(asg)
+
+        ms_graph = time_graph([graph_step, graph_step], 3 if quick else 10)
+    except Exception as e:  # noqa: BLE001
+        out["train_rpn_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+    # the dense-output forms for their rooflines: assignment writes 9R bytes per image (labels + matched), the dense
+    # fused loss writes both gradient tensors in full
+    ms_assign_generic = time_region(lambda: m.match_packed(gtb2, off2, nb, anchors), it)
+    logits = torch.randn(nb, R, device=dev)
+    deltas = torch.randn(nb, R, 4, device=dev) * 0.5
+    gl, gd = torch.empty_like(logits), torch.empty_like(deltas)
+    ms_loss_dense = time_region(lambda: rpn._run_loss(anchors, logits, deltas, asg0, nb * world, None, gl, gd), it)
+    del logits, deltas, gl, gd
     loss_bytes = nb * (49 * R) + 16 * tot2 + 20  # SURVEY 8d formula: every input read once, both gradients written
-    # what the fused kernel has to move: labels (1 B) read and both gradient tensors (4 + 16 B) written for every
+    # what the dense fused kernel has to move: labels (1 B) read and both gradient tensors (4 + 16 B) written for every
     # anchor; logits only where label >= 0, deltas / matched index / gt only for positives (<= 256 sampled per image)
     loss_moved = nb * (21 * R) + nb * 256 * 4 + nb * 128 * (16 + 8 + 16)
     assign_bytes = nb * 9 * R + 16 * tot2
     out["train_rpn_r50127"] = {
-        "workload": f"RPN form R=50127, batch {nb}/GPU: match+subsample, fused loss fwd+bwd (+8-float allreduce)",
-        "ms_assign": ms_a, "ms_loss_fwd_bwd": ms_l, "ms_step": ms_a + ms_l, "batch": nb,
-        "images_per_s_per_gpu": nb / (ms_a + ms_l) * 1e3, "images_per_s_total": world * nb / (ms_a + ms_l) * 1e3,
-        "loss_roofline": {"bound": "hbm", "achieved": loss_moved / ms_l / 1e6, "peak": peak, "unit": "GB/s",
-                          "frac": loss_moved / ms_l / 1e6 / peak, "algorithmic_bytes": loss_moved,
+        "workload": f"RPN form R=50127, batch {nb}/GPU, NCHW head tensors: grid match + subsample + sampled loss fwd+bwd "
+                    "(persistent NCHW gradient buffers) + 8-float NCCL all-reduce every step (waited one step late)",
+        "ms_step": ms_step, "ms_assign": ms_match, "ms_loss_fwd_bwd": ms_loss, "ms_step_graph_no_collective": ms_graph,
+        "batch": nb, "launches_per_step": 4,
+        "images_per_s_per_gpu": nb / ms_step * 1e3, "images_per_s_total": world * nb / ms_step * 1e3,
+        "ms_assign_generic_anchors": ms_assign_generic, "ms_loss_dense_fwd_bwd": ms_loss_dense,
+        "loss_roofline": {"bound": "hbm", "achieved": loss_moved / ms_loss_dense / 1e6, "peak": peak, "unit": "GB/s",
+                          "frac": loss_moved / ms_loss_dense / 1e6 / peak, "algorithmic_bytes": loss_moved,
+                          "kernel": "rpn_loss_kernel (dense gradients, det_rpn_loss)",
                           "formula": "N*(21R) + sampled rows: label read + grad_logits/grad_deltas written everywhere, "
                                      "logits/deltas/targets only where sampled",
-                          "survey_formula_bytes": loss_bytes, "survey_formula_gbs": loss_bytes / ms_l / 1e6,
+                          "survey_formula_bytes": loss_bytes, "survey_formula_gbs": loss_bytes / ms_loss_dense / 1e6,
                           "note": "the SURVEY 8d figure (49R+16G+20) counts reads the fused kernel skips, so it exceeds "
-                                  "the HBM peak; frac uses the bytes actually required"},
-        "assign_roofline": {"bound": "hbm", "achieved": assign_bytes / ms_a / 1e6, "peak": peak, "unit": "GB/s",
-                            "frac": assign_bytes / ms_a / 1e6 / peak, "algorithmic_bytes": assign_bytes,
-                            "note": "IoU ALU-bound: 16 gt x 50127 anchors x 2 passes per image"},
+                                  "the HBM peak; frac uses the bytes actually required.  The training step itself uses "
+                                  "the sampled kernel (ms_loss_fwd_bwd), which moves O(samples) bytes"},
+        "assign_roofline": {"bound": "hbm", "achieved": assign_bytes / ms_match / 1e6, "peak": peak, "unit": "GB/s",
+                            "frac": assign_bytes / ms_match / 1e6 / peak, "algorithmic_bytes": assign_bytes,
+                            "kernel": "match_rowmax_kernel + match_grid_kernel (det_match_grid)",
+                            "formula": "N*9R + 16G: labels int8 + matched int64 written, gt read (SURVEY 8d)"},
     }
     return out
 
@@ -523,7 +569,8 @@ def train_summary(extras, world):
     r = extras.get("train_rpn_r50127")
     if r:
         out["rpn_r50127"] = {"ms_step": _r(r.get("ms_step")), "ms_assign": _r(r.get("ms_assign")),
-                             "ms_loss": _r(r.get("ms_loss_fwd_bwd")), "img_s_total": _r(r.get("images_per_s_total"), 0),
+                             "ms_loss": _r(r.get("ms_loss_fwd_bwd")), "ms_graph": _r(r.get("ms_step_graph_no_collective")),
+                             "img_s_total": _r(r.get("images_per_s_total"), 0),
                              "assign_frac": _r(r["assign_roofline"]["frac"], 3), "loss_frac": _r(r["loss_roofline"]["frac"], 3),
                              "batch": r.get("batch")}
     g = extras.get("train_grid_b1024")

@@ -212,6 +212,26 @@ DET_API int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, 
                       int64_t r, const float* thresholds_host, const int32_t* labels_host, int num_thresholds,
                       int allow_low_quality, int64_t* matched_idx, int8_t* labels, float* matched_iou,
                       void* workspace, int64_t workspace_bytes, void* stream);
+/* The same assignment for GRID anchors -- the (R,4) table AnchorGenerator.forward produces
+ * (python/src/models/modules/anchor_generators.py:158-179: per level h*w positions x `a` cell anchors, order (h,w,a),
+ * levels concatenated) -- in ONE streaming pass (csrc/assign_grid.cu): a gt-centric kernel evaluates every row maximum on
+ * the closed-form window of anchors that can overlap the box, then one anchor-centric kernel (8 x 4 position tiles per
+ * warp) writes labels and matched indices including the low-quality promotion.  Results are bit-identical to
+ * det_match_anchors.  levels_host[l] = {h, w, stride, 0, first_row}; rows must be consecutive and sum to r;
+ * a in {1, 3, 9}, num_levels * a <= 32, num_levels <= 8 (else DET_ERR_UNSUPPORTED: use det_match_anchors).
+ * Optional per-image statistics for det_subsample_labels_grid (both NULL to skip): stats (n,4) int32 = {#positives,
+ * #ignored (label -1), 0, 0} (written by the call), pos_list (n, list_cap) int32 = anchor row | label << 24 of the
+ * first list_cap positives in arrival order (needs r < 2^24). */
+typedef struct det_anchor_level {
+    int32_t h, w, stride, reserved;
+    int64_t first_row;
+} det_anchor_level_t;
+DET_API int64_t det_match_grid_workspace_bytes(int n, int64_t sum_g);
+DET_API int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors,
+                   int64_t r, const det_anchor_level_t* levels_host, int num_levels, int a,
+                   const float* thresholds_host, const int32_t* labels_host, int num_thresholds, int allow_low_quality,
+                   int64_t* matched_idx, int8_t* labels, float* matched_iou, int32_t* stats, int32_t* pos_list,
+                   int list_cap, void* workspace, int64_t workspace_bytes, void* stream);
 /* Matcher on a materialised quality matrix (g,r) -- Matcher.__call__, matcher.py:53. */
 DET_API int det_match_quality(const float* quality, int64_t g, int64_t r, const float* thresholds_host,
                       const int32_t* labels_host, int num_thresholds, int allow_low_quality, int64_t* matched_idx,
@@ -224,12 +244,26 @@ DET_API int det_match_quality(const float* quality, int64_t g, int64_t r, const 
 DET_API int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, double positive_fraction, uint64_t seed,
                          void* stream);
 
+/* det_subsample_labels driven by det_match_grid's statistics: same result bit for bit (same hash keys, same
+ * permutation walk), but the label row is never read in full -- positives are ranked from pos_list, negatives found by
+ * the walk, the row is overwritten with -1 and the survivors written back.  Images outside the fast path's
+ * preconditions (positives not sparse, negatives not dense or not thinned, list overflow) run det_subsample_labels'
+ * code.  Optional sample list for det_rpn_loss_sampled (both NULL to skip): samples (n, sample_cap) int32 = anchor row |
+ * label << 24 of every anchor whose final label is not -1, sample_count (n) int32. */
+DET_API int det_subsample_labels_grid(int8_t* labels, int n, int64_t r, int num_samples, double positive_fraction,
+                              uint64_t seed, const int32_t* stats, const int32_t* pos_list, int list_cap,
+                              int32_t* samples, int32_t* sample_count, int sample_cap, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (4b) fused RPN loss forward + backward -- replaces losses + _dense_box_regression_loss + get_deltas,
  *      python/src/models/rpn.py:187-244, components/box_regression.py:128-168, :33-73, and autograd's backward.
  *      logits (n,r), deltas (n,r,4), labels (n,r) int8, matched_idx (n,r) int64, gt as above, anchors (r,4).
  *      loss_type 0 = smooth-L1(beta) (beta<1e-5 -> L1), 1 = GIoU.
- *      sums (8) fp32, caller-zeroed: [0]=objectness BCE sum, [1]=localisation sum, [2]=#pos, [3]=#neg.
+ *      accumulators: 16 floats of device scratch owned by the caller, ZERO BEFORE THE FIRST CALL; every launch leaves
+ *      them zero again (the kernel's last CTA re-arms them), so no memset surrounds the call.  One buffer per stream.
+ *      sums_out (8) fp32, written by that last CTA: [0] = objectness BCE sum * grad_scale_cls, [1] = localisation sum *
+ *      grad_scale_loc -- with grad_scale_x = loss_weight_x / (batch_size_per_image * n_global) these ARE the reference's
+ *      weighted, normalised losses (rpn.py:238-243) -- [2] = #pos, [3] = #neg, rest 0.
  *      grad_logits (n,r) / grad_deltas (n,r,4): d(sum)/d(input) * grad_scale_{cls,loc} [* upstream[0|1]];
  *      NULL to skip backward.  upstream: device float[2] (d total / d cls_loss, d total / d loc_loss) or NULL (= 1),
  *      read by the kernel so an autograd backward needs no host synchronisation.
@@ -237,17 +271,48 @@ DET_API int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_sampl
 DET_API int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
                  const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r, float wx,
                  float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
-                 float grad_scale_cls, float grad_scale_loc, const float* upstream, float* sums, float* grad_logits,
-                 float* grad_deltas, void* stream);
+                 float grad_scale_cls, float grad_scale_loc, const float* upstream, float* accumulators, float* sums_out,
+                 float* grad_logits, float* grad_deltas, void* stream);
+
+/* The same loss on the SAMPLED anchors only (the labels of everything else are -1 and contribute nothing, rpn.py:222-236),
+ * reading the head where the convolutions left it and writing the gradients in the same layout -- O(samples) traffic
+ * instead of O(r), no layout change (rpn.py:270-284), no (n,r) label sweep.
+ *   layout: num_levels >= 1: levels_host[l] = per-level NCHW planes objectness (n,a,h,w), deltas (n,a*4,h,w) (channel =
+ *   a*4 + component, rpn.py:278-280) and their gradient planes (all NULL to skip backward); the *_flat pointers are
+ *   ignored.  num_levels == 0: logits_flat (n,r), deltas_flat (n,r,4), grad_*_flat or NULL.
+ *   samples / sample_count / sample_cap: from det_subsample_labels_grid.  matched_idx (n,r) from det_match_grid.
+ *   Gradient buffers are NOT swept: zero them once (cudaMemset) -- or keep them persistent and pass the PREVIOUS step's
+ *   sample list as clear_samples / clear_count (NULL, NULL otherwise): those entries are reset to zero first.
+ *   accumulators: 8 floats of device scratch, zero before the first call (the kernel re-arms them).
+ *   sums_out (8): [0] = objectness BCE sum * scale_cls, [1] = localisation sum * scale_loc, [2] = #pos, [3] = #neg, rest 0
+ *   -- written by the kernel's last CTA, so no memset and no scaling op surround the call.  Gradients are
+ *   d(sum)/d(input) * scale_{cls,loc} [* upstream[0|1]]. */
+typedef struct det_head_level {
+    const float* objectness;
+    const float* deltas;
+    float* grad_objectness;
+    float* grad_deltas;
+    int32_t h, w;
+} det_head_level_t;
+DET_API int det_rpn_loss_sampled(const det_head_level_t* levels_host, int num_levels, int a, const float* logits_flat,
+                         const float* deltas_flat, float* grad_logits_flat, float* grad_deltas_flat,
+                         const int32_t* samples, const int32_t* sample_count, int sample_cap,
+                         const int32_t* clear_samples, const int32_t* clear_count, const int64_t* matched_idx,
+                         const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r,
+                         float wx, float wy, float ww, float wh, float scale_clamp, int loss_type,
+                         float smooth_l1_beta, float scale_cls, float scale_loc, const float* upstream,
+                         float* accumulators, float* sums_out, void* stream);
 
 /* YOLO-grid fused loss forward + backward (own specification: oracle/ref_torch.py yolo_loss).
  * head (n,s,s,b*5+c); labels (n,p) int8; matched_idx (n,p) int64; gt_classes (sum_g) int64.
- * sums (8): [0]=loc, [1]=obj, [2]=cls, [3]=#pos, [4]=#neg.  grad_head same shape as head (fully written) or NULL.
+ * accumulators: as for det_rpn_loss.  sums_out (8): [0] = lambda_coord * loc * grad_scale, [1] = obj * grad_scale,
+ * [2] = cls * grad_scale, [3] = #pos, [4] = #neg, rest 0 (grad_scale = 1 / normaliser: the reported losses).
+ * grad_head same shape as head (fully written) or NULL.
  * grad = d(lambda_coord*loc + obj + cls)/d(head) * grad_scale [* upstream[0..2] per term], upstream device float[3] or NULL. */
 DET_API int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                   const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                   int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                  const float* upstream, float* sums, float* grad_head, void* stream);
+                  const float* upstream, float* accumulators, float* sums_out, float* grad_head, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (next tier) FPN level assignment + ROIAlign over a feature pyramid -- replaces
@@ -291,9 +356,9 @@ DET_API int det_peer_sums_publish(const float* sums, int width, int rank, int wo
                           int slot, uint32_t stamp, void* stream);
 DET_API int det_peer_sums_collect(float* out, int width, int world, const float* local_buf, int slots, int slot,
                           uint32_t stamp, int64_t timeout_ns, int32_t* error_flag, void* stream);
-/* compute + collective in ONE kernel: det_yolo_loss whose last CTA publishes the batch's sums (the raw `sums` vector,
- * `width` <= 8 floats) as step `stamp` and collects step stamp - lag into `out`.  done_counter: device int32, zero
- * before the first use (the kernel resets it).  The out buffer of step t must stay untouched until step t + 1's. */
+/* compute + collective in ONE kernel: det_yolo_loss whose last CTA publishes the batch's finished `sums_out` vector
+ * (`width` <= 8 floats) as step `stamp` and collects step stamp - lag into `out`.  done_counter is unused since ABI 2
+ * (the accumulators carry the arrival ticket).  The out buffer of step t must stay untouched until step t + 1's. */
 typedef struct det_peer_ctx {
     const void* peers_dev;
     float* out;
@@ -308,7 +373,8 @@ typedef struct det_peer_ctx {
 DET_API int det_yolo_loss_peer(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                        const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                        int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                       const float* upstream, float* sums, float* grad_head, const det_peer_ctx_t* peer, void* stream);
+                       const float* upstream, float* accumulators, float* sums_out, float* grad_head,
+                       const det_peer_ctx_t* peer, void* stream);
 /* both in one launch per training step: publish step `stamp` (slot stamp % slots), then collect step stamp - lag into
  * out (nothing is collected while stamp <= lag). */
 DET_API int det_peer_sums_exchange(const float* sums, float* out, int width, int rank, int world, const void* peers_dev,

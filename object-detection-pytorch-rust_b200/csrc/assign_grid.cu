@@ -23,6 +23,7 @@
 // Anchor coordinates are always READ from the caller's (R, 4) table (802 KB, L2-resident): every IoU is the same fp32
 // expression on the same bits as in the generic kernels, the grid layout only organises the work.
 #include "common.cuh"
+#include "peer.cuh"
 #include "assign.cuh"
 
 namespace det {
@@ -312,7 +313,7 @@ rpn_loss_sampled_kernel(HeadLayoutDev hl, const int32_t* __restrict__ samples, c
                         float scale_cls, float scale_loc, const float* __restrict__ upstream, float* __restrict__ acc,
                         int32_t* __restrict__ ticket, float* __restrict__ sums_out, int write_grads) {
     __shared__ float s_part[4][kSampledThreads / 32];
-    __shared__ int s_last;
+    __shared__ float s_fin[8];
     const int img = blockIdx.x;
     float gs_cls = scale_cls, gs_loc = scale_loc;
     if (upstream) {
@@ -405,21 +406,8 @@ rpn_loss_sampled_kernel(HeadLayoutDev hl, const int32_t* __restrict__ samples, c
         if (t != 0.f) atomicAdd(&acc[threadIdx.x], t);
     }
     // last CTA: sums_out = [cls * scale_cls, loc * scale_loc, #pos, #neg, 0...], accumulators and ticket re-armed
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int tk = atomicAdd(ticket, 1);
-        s_last = (tk == (int)gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x < 8) {
-        __threadfence();
-        const float v = threadIdx.x < 4 ? __ldcg(acc + threadIdx.x) : 0.0f;
-        const float sc = threadIdx.x == 0 ? scale_cls : (threadIdx.x == 1 ? scale_loc : 1.0f);
-        sums_out[threadIdx.x] = v * sc;
-        if (threadIdx.x < 4) acc[threadIdx.x] = 0.0f;
-        if (threadIdx.x == 0) *ticket = 0;
-    }
+    if (last_cta_arrives(ticket))
+        finalize_sums(acc, sums_out, s_fin, [&](int i) { return i == 0 ? scale_cls : (i == 1 ? scale_loc : 1.0f); });
 }
 
 static int fill_layout(GridLayoutDev& lay, const det_anchor_level_t* levels_host, int num_levels, int a, int64_t r) {
@@ -578,7 +566,7 @@ int det_rpn_loss_sampled(const det_head_level_t* levels_host, int num_levels, in
     const CodecW wt{wx, wy, ww, wh};
     auto g4 = reinterpret_cast<const float4*>(gt_boxes);
     auto a4 = reinterpret_cast<const float4*>(anchors);
-    int32_t* ticket = reinterpret_cast<int32_t*>(accumulators + 4);
+    int32_t* ticket = reinterpret_cast<int32_t*>(accumulators + 8);
     if (loss_type == 1)
         rpn_loss_sampled_kernel<true><<<n, kSampledThreads, 0, as_stream(stream)>>>(
             hl, samples, sample_count, sample_cap, clear_samples, clear_count, matched_idx, g4, gt_offsets, a4, r, wt,

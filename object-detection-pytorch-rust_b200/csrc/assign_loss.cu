@@ -324,12 +324,55 @@ struct SampleSmem {
     int cidx[2][kCandCap];  // anchor index of the candidate | its original label in the top byte
 };
 
-__global__ void __launch_bounds__(kSampleThreads)
-subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, int pos_cap, uint64_t seed) {
-    __shared__ SampleSmem sm;
-    const int img = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ uint32_t image_seed(uint64_t seed, int img) {
+    return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x632BE5ABu * (uint32_t)(img + 1)));
+}
+
+// class c of one image sampled by walking a pseudo-random permutation of the row (block-wide, all threads call it):
+// the first `want` hits, in walk order, land in sm.cidx[c][0..want) with key 0
+__device__ __forceinline__ void walk_class(SampleSmem& sm, const RowView& rv, int c, int want, uint32_t img_seed, int pbits) {
+    const int tid = threadIdx.x;
+    const int64_t r = rv.r;
+    const uint32_t s0 = mix32(img_seed + 0x51ED270Bu * (uint32_t)(c + 1));
+    const int lane = tid & 31, wid = tid >> 5;
+    int total = 0;  // accepted so far (block-uniform)
+    for (uint32_t k0 = 0; total < want && k0 < (1u << pbits); k0 += kSampleThreads) {
+        const uint32_t j = perm_bits(k0 + (uint32_t)tid, s0, pbits);
+        int8_t l = -1;
+        bool ok = false;
+        if ((int64_t)j < r) {
+            l = rv.row[j];
+            ok = label_class(l) == c;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) sm.walk_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, round_total = 0;
+        for (int w = 0; w < kSampleThreads / 32; ++w) {
+            const int v = sm.walk_warp[w];
+            before += (w < wid) ? v : 0;
+            round_total += v;
+        }
+        const int slot = total + before + __popc(bal & ((1u << lane) - 1u));  // rank in walk order
+        if (ok && slot < want) {
+            sm.ckey[c][slot] = 0u;
+            sm.cidx[c][slot] = (int)j | ((int)(uint8_t)l << 24);
+        }
+        total += round_total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        sm.ncand[c] = want;
+        sm.sel[c] = 0u;  // every listed candidate (key 0) is restored after the wholesale wipe
+    }
+}
+
+// one image of det_subsample_labels (block-wide; every thread of the CTA calls it)
+__device__ void subsample_image(SampleSmem& sm, int8_t* __restrict__ labels, int img, int64_t r, int num_samples, int pos_cap,
+                                uint64_t seed) {
+    const int tid = threadIdx.x;
     const RowView rv(labels + (int64_t)img * r, r);
-    const uint32_t img_seed = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x632BE5ABu * (uint32_t)(img + 1)));
+    const uint32_t img_seed = image_seed(seed, img);
     if (tid < 2) {
         sm.cnt[tid] = 0;
         sm.ncand[tid] = 0;
@@ -406,41 +449,8 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, int po
     }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (!walk[c]) continue;
-        const uint32_t s0 = mix32(img_seed + 0x51ED270Bu * (uint32_t)(c + 1));
-        const int lane = tid & 31, wid = tid >> 5;
-        int total = 0;  // accepted so far (block-uniform)
-        for (uint32_t k0 = 0; total < want[c] && k0 < (1u << pbits); k0 += kSampleThreads) {
-            const uint32_t j = perm_bits(k0 + (uint32_t)tid, s0, pbits);
-            int8_t l = -1;
-            bool ok = false;
-            if ((int64_t)j < r) {
-                l = rv.row[j];
-                ok = label_class(l) == c;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if (lane == 0) sm.walk_warp[wid] = __popc(bal);
-            __syncthreads();
-            int before = 0, round_total = 0;
-            for (int w = 0; w < kSampleThreads / 32; ++w) {
-                const int v = sm.walk_warp[w];
-                before += (w < wid) ? v : 0;
-                round_total += v;
-            }
-            const int slot = total + before + __popc(bal & ((1u << lane) - 1u));  // rank in walk order
-            if (ok && slot < want[c]) {
-                sm.ckey[c][slot] = 0u;
-                sm.cidx[c][slot] = (int)j | ((int)(uint8_t)l << 24);
-            }
-            total += round_total;
-            __syncthreads();
-        }
-        if (tid == 0) {
-            sm.ncand[c] = want[c];
-            sm.sel[c] = 0u;  // every listed candidate (key 0) is restored after the wholesale wipe
-        }
-    }
+    for (int c = 0; c < 2; ++c)
+        if (walk[c]) walk_class(sm, rv, c, want[c], img_seed, pbits);
     __syncthreads();
     // ---- pass C: the want-th smallest key, by rank counting among the candidates
     bool radix[2], listed[2];
@@ -544,6 +554,95 @@ subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, int po
     }
 }
 
+__global__ void __launch_bounds__(kSampleThreads)
+subsample_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, int pos_cap, uint64_t seed) {
+    __shared__ SampleSmem sm;
+    subsample_image(sm, labels, blockIdx.x, r, num_samples, pos_cap, seed);
+}
+
+// The same subsample driven by what det_match_grid already knows about the image -- #positives, #ignored and the list of
+// positives -- so that the label row is never read in full: positives are ranked by their hash keys straight from the
+// list, negatives are found by the permutation walk (O(wanted) random reads), the row is overwritten with -1 (a pure
+// streaming store) and the <= num_samples survivors are written back.  Identical result to det_subsample_labels (same
+// keys, same walk); images outside the fast path's preconditions take that kernel's code.  Also emits the image's sample
+// list (anchor row | label << 24) for the sampled loss.
+__global__ void __launch_bounds__(kSampleThreads)
+subsample_stats_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, int pos_cap, uint64_t seed,
+                       const int32_t* __restrict__ stats, const int32_t* __restrict__ pos_list, int list_cap,
+                       int32_t* __restrict__ samples, int32_t* __restrict__ sample_count, int sample_cap) {
+    __shared__ SampleSmem sm;
+    __shared__ int s_nout;
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int npos = stats[img * 4 + 0], nign = stats[img * 4 + 1];
+    const int64_t nneg64 = r - npos - nign;
+    const int nneg = (int)nneg64;
+    const int want_pos = min(npos, pos_cap);
+    const int want_neg = min(nneg, num_samples - want_pos);
+    int8_t* row = labels + (int64_t)img * r;
+    const bool fast = r < (1 << 24) && npos <= min(list_cap, kCandCap) && (int64_t)npos * 8 < r &&  // sparse positives
+                      want_neg < nneg && want_neg <= kCandCap && (int64_t)nneg * 8 >= r;            // dense, thinned negatives
+    if (tid == 0) s_nout = 0;
+    if (!fast) {
+        subsample_image(sm, labels, img, r, num_samples, pos_cap, seed);
+        __syncthreads();
+        if (samples) {  // rare: rebuild the list from the finished row
+            for (int64_t j = tid; j < r; j += kSampleThreads) {
+                const int8_t l = row[j];
+                if (l != -1) {
+                    const int slot = atomicAdd(&s_nout, 1);
+                    if (slot < sample_cap) samples[(int64_t)img * sample_cap + slot] = (int)j | ((int)(uint8_t)l << 24);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sample_count[img] = min(s_nout, sample_cap);
+        }
+        return;
+    }
+    const RowView rv(row, r);
+    const uint32_t img_seed = image_seed(seed, img);
+    int pbits = 1;
+    while ((1ll << pbits) < r) ++pbits;
+    // positives: the want_pos smallest keys of the list (keys are a bijection of the anchor index: no ties)
+    for (int t = tid; t < npos; t += kSampleThreads) {
+        const int packed = pos_list[(int64_t)img * list_cap + t];
+        sm.cidx[0][t] = packed;
+        sm.ckey[0][t] = sample_key(img_seed, (uint32_t)(packed & 0xffffff));
+    }
+    __syncthreads();
+    if (want_pos < npos) {
+        for (int t = tid; t < npos; t += kSampleThreads) {
+            const unsigned key = sm.ckey[0][t];
+            int rank = 0;
+            for (int q = 0; q < npos; ++q) rank += sm.ckey[0][q] < key;
+            if (rank >= want_pos) sm.cidx[0][t] = -1;  // dropped
+        }
+    }
+    if (want_neg > 0) walk_class(sm, rv, 1, want_neg, img_seed, pbits);  // has block barriers inside
+    __syncthreads();
+    // the row becomes -1 wholesale ...
+    const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int c = tid; c < rv.ngran; c += kSampleThreads) rv.store(c, ones);
+    __syncthreads();
+    // ... and the survivors come back
+    for (int t = tid; t < npos; t += kSampleThreads) {
+        const int packed = sm.cidx[0][t];
+        if (packed == -1) continue;
+        row[packed & 0xffffff] = (int8_t)(packed >> 24);
+        if (samples) {
+            const int slot = atomicAdd(&s_nout, 1);
+            if (slot < sample_cap) samples[(int64_t)img * sample_cap + slot] = packed;
+        }
+    }
+    __syncthreads();
+    const int kept_pos = s_nout;
+    for (int t = tid; t < want_neg; t += kSampleThreads) {
+        const int packed = sm.cidx[1][t];
+        row[packed & 0xffffff] = (int8_t)(packed >> 24);
+        if (samples && kept_pos + t < sample_cap) samples[(int64_t)img * sample_cap + kept_pos + t] = packed;
+    }
+    if (samples && tid == 0) sample_count[img] = min(samples ? kept_pos + want_neg : 0, sample_cap);
+}
+
 // ---- fused RPN loss forward + backward ---------------------------------------------------------------------------
 constexpr int kLossThreads = 256;
 
@@ -553,9 +652,11 @@ rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ del
                 const int64_t* __restrict__ matched, const float4* __restrict__ gt, const int32_t* __restrict__ gt_off,
                 const float4* __restrict__ anchors, int64_t total, int64_t r, CodecW wt, float scale_clamp,
                 float beta, float gs_cls,
-                float gs_loc, const float* __restrict__ upstream, float* __restrict__ sums,
+                float gs_loc, const float* __restrict__ upstream, float* __restrict__ acc, float* __restrict__ sums_out,
                 float* __restrict__ grad_logits, float4* __restrict__ grad_deltas) {
     __shared__ float s_part[4][kLossThreads / 32];
+    __shared__ float s_fin[8];
+    const float scale_cls = gs_cls, scale_loc = gs_loc;  // the reported losses are not multiplied by the upstream gradient
     if (upstream) {
         gs_cls *= upstream[0];
         gs_loc *= upstream[1];
@@ -636,8 +737,11 @@ rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ del
     if (threadIdx.x < 4) {
         float t = 0.f;
         for (int w = 0; w < kLossThreads / 32; ++w) t += s_part[threadIdx.x][w];
-        if (t != 0.f) atomicAdd(&sums[threadIdx.x], t);
+        if (t != 0.f) atomicAdd(&acc[threadIdx.x], t);
     }
+    // the last CTA turns the accumulators into the weighted, normalised losses (rpn.py:238-243) and re-arms them
+    if (last_cta_arrives(reinterpret_cast<int32_t*>(acc + 8)))
+        finalize_sums(acc, sums_out, s_fin, [&](int i) { return i == 0 ? scale_cls : (i == 1 ? scale_loc : 1.0f); });
 }
 
 // ---- fused YOLO-grid loss forward + backward: one thread per (image, cell) -----------------------------------------
@@ -711,9 +815,11 @@ __global__ void __launch_bounds__(kYoloLossThreads)
 yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labels, const int64_t* __restrict__ matched,
                  const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
                  const float2* __restrict__ priors, YoloLossParams prm, int imgs, const float* __restrict__ upstream,
-                 float* __restrict__ sums, float* __restrict__ grad_head, const PeerCtxDev peer) {
+                 float* __restrict__ gacc, float* __restrict__ sums_out, float* __restrict__ grad_head,
+                 const PeerCtxDev peer) {
     extern __shared__ __align__(16) float s_tile[];
     __shared__ float s_part[5][kYoloLossThreads / 32];
+    __shared__ float s_fin[8];
     const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
                 up_cls = upstream ? upstream[2] : 1.f;
     const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c, per_img = S2 * ch;
@@ -755,11 +861,16 @@ yolo_loss_kernel(const float* __restrict__ head, const int8_t* __restrict__ labe
     if (threadIdx.x < 5) {
         float t = 0.f;
         for (int w = 0; w < kYoloLossThreads / 32; ++w) t += s_part[threadIdx.x][w];
-        if (t != 0.f) atomicAdd(&sums[threadIdx.x], t);
+        if (t != 0.f) atomicAdd(&gacc[threadIdx.x], t);
     }
-    // compute + collective in one kernel: the last CTA publishes the batch's sums into every peer's buffer over NVLink
-    // and collects the previous step's world sum (peer.cuh)
-    if (peer.enabled) peer_exchange_from_last_cta(peer, sums);
+    // The last CTA scales the accumulators into the reported losses [lambda_coord * loc, obj, cls] * grad_scale (counts
+    // unscaled) and re-arms them.  Compute + collective in one kernel: it then publishes that vector into every peer's
+    // buffer over NVLink and collects the previous step's world sum (peer.cuh).
+    if (last_cta_arrives(reinterpret_cast<int32_t*>(gacc + 8))) {
+        const float gs = prm.grad_scale, lc = prm.lambda_coord;
+        finalize_sums(gacc, sums_out, s_fin, [&](int i) { return i == 0 ? lc * gs : (i < 3 ? gs : 1.0f); });
+        if (peer.enabled) peer_exchange_warp0(peer, s_fin);
+    }
 }
 
 // heads too large for the shared-memory tile: one thread per (image, cell) straight from global memory
@@ -768,8 +879,9 @@ yolo_loss_direct_kernel(const float* __restrict__ head, const int8_t* __restrict
                         const int64_t* __restrict__ matched, const float4* __restrict__ gt,
                         const int64_t* __restrict__ gt_cls, const int32_t* __restrict__ gt_off,
                         const float2* __restrict__ priors, YoloLossParams prm, const float* __restrict__ upstream,
-                        float* __restrict__ sums, float* __restrict__ grad_head) {
+                        float* __restrict__ gacc, float* __restrict__ sums_out, float* __restrict__ grad_head) {
     __shared__ float s_part[5][4];
+    __shared__ float s_fin[8];
     const float up_loc = upstream ? upstream[0] : 1.f, up_obj = upstream ? upstream[1] : 1.f,
                 up_cls = upstream ? upstream[2] : 1.f;
     const int S2 = prm.s * prm.s, ch = prm.b * 5 + prm.c;
@@ -790,7 +902,11 @@ yolo_loss_direct_kernel(const float* __restrict__ head, const int8_t* __restrict
     __syncthreads();
     if (threadIdx.x < 5) {
         const float t = s_part[threadIdx.x][0] + s_part[threadIdx.x][1] + s_part[threadIdx.x][2] + s_part[threadIdx.x][3];
-        if (t != 0.f) atomicAdd(&sums[threadIdx.x], t);
+        if (t != 0.f) atomicAdd(&gacc[threadIdx.x], t);
+    }
+    if (last_cta_arrives(reinterpret_cast<int32_t*>(gacc + 8))) {
+        const float gs = prm.grad_scale, lc = prm.lambda_coord;
+        finalize_sums(gacc, sums_out, s_fin, [&](int i) { return i == 0 ? lc * gs : (i < 3 ? gs : 1.0f); });
     }
 }
 
@@ -909,15 +1025,37 @@ int det_subsample_labels(int8_t* labels, int n, int64_t r, int num_samples, doub
     return DET_OK;
 }
 
+int det_subsample_labels_grid(int8_t* labels, int n, int64_t r, int num_samples, double positive_fraction, uint64_t seed,
+                              const int32_t* stats, const int32_t* pos_list, int list_cap, int32_t* samples,
+                              int32_t* sample_count, int sample_cap, void* stream) {
+    DET_CHECK_ARG(n >= 0 && r >= 0 && num_samples >= 0, "negative size");
+    DET_CHECK_ARG(r < (1ll << 31), "r too large");
+    DET_CHECK_ARG(positive_fraction >= 0.0 && positive_fraction <= 1.0, "positive_fraction outside [0, 1]");
+    if (n == 0 || r == 0) return DET_OK;
+    DET_CHECK_ARG(labels && stats && pos_list && list_cap >= 1, "null pointer");
+    DET_CHECK_ARG((samples == nullptr) == (sample_count == nullptr) && (!samples || sample_cap >= 1), "bad sample list");
+    DET_CHECK_ARG(!samples || r < (1 << 24), "sample lists pack the anchor row in 24 bits");
+    const int pos_cap = (int)((double)num_samples * positive_fraction);
+    subsample_stats_kernel<<<n, kSampleThreads, 0, as_stream(stream)>>>(labels, r, num_samples, pos_cap, seed, stats, pos_list,
+                                                                        list_cap, samples, sample_count, sample_cap);
+    DET_LAUNCH_OK("subsample_stats_kernel");
+    return DET_OK;
+}
+
 int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
                  const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r, float wx,
                  float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
-                 float grad_scale_cls, float grad_scale_loc, const float* upstream, float* sums, float* grad_logits,
-                 float* grad_deltas, void* stream) {
+                 float grad_scale_cls, float grad_scale_loc, const float* upstream, float* accumulators, float* sums_out,
+                 float* grad_logits, float* grad_deltas, void* stream) {
     DET_CHECK_ARG(n >= 0 && r >= 0, "negative size");
     DET_CHECK_ARG(loss_type == 0 || loss_type == 1, "loss_type must be 0 (smooth-L1) or 1 (GIoU)");
-    if (n == 0 || r == 0) return DET_OK;
-    DET_CHECK_ARG(logits && deltas && labels && matched_idx && gt_offsets && anchors && sums, "null pointer");
+    DET_CHECK_ARG(accumulators && sums_out, "null accumulators / sums_out");
+    if (n == 0 || r == 0) {
+        cudaError_t e = cudaMemsetAsync(sums_out, 0, 8 * sizeof(float), as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        return DET_OK;
+    }
+    DET_CHECK_ARG(logits && deltas && labels && matched_idx && gt_offsets && anchors, "null pointer");
     if (!aligned16(deltas) || !aligned16(anchors) || !aligned16(logits) || (gt_boxes && !aligned16(gt_boxes)) ||
         (grad_logits && !aligned16(grad_logits)) || (grad_deltas && !aligned16(grad_deltas)) ||
         (reinterpret_cast<uintptr_t>(labels) & 3u)) {
@@ -937,11 +1075,11 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
     if (loss_type == 1)
         rpn_loss_kernel<true><<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(
             logits, d4, labels, matched_idx, g4, gt_offsets, a4, total, r, wt, scale_clamp, smooth_l1_beta, grad_scale_cls,
-            grad_scale_loc, upstream, sums, grad_logits, gd4);
+            grad_scale_loc, upstream, accumulators, sums_out, grad_logits, gd4);
     else
         rpn_loss_kernel<false><<<(unsigned)blocks, kLossThreads, 0, as_stream(stream)>>>(
             logits, d4, labels, matched_idx, g4, gt_offsets, a4, total, r, wt, scale_clamp, smooth_l1_beta, grad_scale_cls,
-            grad_scale_loc, upstream, sums, grad_logits, gd4);
+            grad_scale_loc, upstream, accumulators, sums_out, grad_logits, gd4);
     DET_LAUNCH_OK("rpn_loss_kernel");
     return DET_OK;
 }
@@ -949,11 +1087,16 @@ int det_rpn_loss(const float* logits, const float* deltas, const int8_t* labels,
 static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                           const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                           int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                          const float* upstream, float* sums, float* grad_head, void* stream,
+                          const float* upstream, float* accumulators, float* sums_out, float* grad_head, void* stream,
                           const det_peer_ctx_t* peer) {
     DET_CHECK_ARG(n >= 0 && s >= 1 && b >= 1 && c >= 0, "bad size");
-    if (n == 0) return DET_OK;
-    DET_CHECK_ARG(head && labels && matched_idx && gt_offsets && priors && sums, "null pointer");
+    DET_CHECK_ARG(accumulators && sums_out, "null accumulators / sums_out");
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(sums_out, 0, 8 * sizeof(float), as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        return DET_OK;
+    }
+    DET_CHECK_ARG(head && labels && matched_idx && gt_offsets && priors, "null pointer");
     if (gt_boxes && !aligned16(gt_boxes)) {
         set_error("gt_boxes must be 16-byte aligned");
         return DET_ERR_ALIGN;
@@ -970,7 +1113,7 @@ static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t
     pc.enabled = 0;
     pc.stamp_counter = nullptr;
     if (peer) {
-        DET_CHECK_ARG(peer->peers_dev && peer->out && peer->done_counter, "peer context: null pointer");
+        DET_CHECK_ARG(peer->peers_dev && peer->out, "peer context: null pointer");
         DET_CHECK_ARG(peer->width >= 1 && peer->width <= 8, "peer context: width must be in [1, 8] (the sums vector)");
         DET_CHECK_ARG(peer->world >= 1 && peer->world <= kPeerMaxWorld && peer->rank >= 0 && peer->rank < peer->world,
                       "peer context: bad rank / world");
@@ -978,7 +1121,7 @@ static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t
                       "peer context: slots >= 4, 1 <= lag <= slots - 3");
         DET_CHECK_ARG(per_img <= kYoloLossTile, "peer context: only the shared-memory-tile kernel publishes");
         pc.peers = reinterpret_cast<float* const*>(peer->peers_dev); pc.out = peer->out;
-        pc.error_flag = peer->error_flag; pc.done_counter = peer->done_counter; pc.timeout_ns = peer->timeout_ns;
+        pc.error_flag = peer->error_flag; pc.timeout_ns = peer->timeout_ns;
         pc.width = peer->width; pc.rank = peer->rank; pc.world = peer->world; pc.slots = peer->slots;
         pc.stamp = peer->stamp; pc.lag = peer->lag; pc.stamp_counter = peer->stamp_counter; pc.enabled = 1;
     }
@@ -989,11 +1132,11 @@ static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t
         if (imgs > fill) imgs = fill < 1 ? 1 : fill;
         const size_t smem = 2 * sizeof(float) * (size_t)((imgs * per_img + 3) & ~3);
         yolo_loss_kernel<<<(unsigned)((n + imgs - 1) / imgs), kYoloLossThreads, smem, as_stream(stream)>>>(
-            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, imgs, upstream, sums, grad_head, pc);
+            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, imgs, upstream, accumulators, sums_out, grad_head, pc);
     } else {
         const int64_t cells = (int64_t)n * s * s;
         yolo_loss_direct_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, as_stream(stream)>>>(
-            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, upstream, sums, grad_head);
+            head, labels, matched_idx, g4, gt_classes, gt_offsets, p2, prm, upstream, accumulators, sums_out, grad_head);
     }
     DET_LAUNCH_OK("yolo_loss_kernel");
     return DET_OK;
@@ -1002,19 +1145,21 @@ static int yolo_loss_impl(const float* head, const int8_t* labels, const int64_t
 int det_yolo_loss(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                   const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                   int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                  const float* upstream, float* sums, float* grad_head, void* stream) {
+                  const float* upstream, float* accumulators, float* sums_out, float* grad_head, void* stream) {
     return yolo_loss_impl(head, labels, matched_idx, gt_boxes, gt_classes, gt_offsets, n, s, b, c, img_h, img_w, priors,
-                          lambda_coord, lambda_noobj, grad_scale, upstream, sums, grad_head, stream, nullptr);
+                          lambda_coord, lambda_noobj, grad_scale, upstream, accumulators, sums_out, grad_head, stream,
+                          nullptr);
 }
 
 int det_yolo_loss_peer(const float* head, const int8_t* labels, const int64_t* matched_idx, const float* gt_boxes,
                        const int64_t* gt_classes, const int32_t* gt_offsets, int n, int s, int b, int c, int img_h,
                        int img_w, const float* priors, float lambda_coord, float lambda_noobj, float grad_scale,
-                       const float* upstream, float* sums, float* grad_head, const det_peer_ctx_t* peer, void* stream) {
+                       const float* upstream, float* accumulators, float* sums_out, float* grad_head,
+                       const det_peer_ctx_t* peer, void* stream) {
     DET_CHECK_ARG(peer, "null peer context");
     DET_CHECK_ARG(n >= 1, "the publishing kernel needs a non-empty batch");
     return yolo_loss_impl(head, labels, matched_idx, gt_boxes, gt_classes, gt_offsets, n, s, b, c, img_h, img_w, priors,
-                          lambda_coord, lambda_noobj, grad_scale, upstream, sums, grad_head, stream, peer);
+                          lambda_coord, lambda_noobj, grad_scale, upstream, accumulators, sums_out, grad_head, stream, peer);
 }
 
 }  // extern "C"

@@ -64,7 +64,6 @@ struct PeerCtxDev {
     float* const* peers;
     float* out;
     int32_t* error_flag;
-    int32_t* done_counter;
     long long timeout_ns;
     int width, rank, world, slots;
     uint32_t stamp, lag;
@@ -72,22 +71,41 @@ struct PeerCtxDev {
     int enabled;
 };
 
-// Called by EVERY CTA of a kernel after its atomicAdd()s into `sums`: the CTA that arrives last sees the final sums,
-// publishes them as step `stamp` and collects step `stamp - lag` (warp 0).  The counter resets itself.
-__device__ __forceinline__ void peer_exchange_from_last_cta(const PeerCtxDev& pc, const float* sums) {
+// Called by EVERY CTA of a kernel after its atomicAdd()s into the accumulators `acc`: the CTA that arrives last (all of
+// its threads get `true`) sees the final values in L2.  `ticket` is a device int32 that is zero before the first launch;
+// the last CTA re-arms it.
+__device__ __forceinline__ bool last_cta_arrives(int32_t* ticket) {
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int ticket = atomicAdd(pc.done_counter, 1);
-        s_last = (ticket == (int)(gridDim.x * gridDim.y) - 1) ? 1 : 0;
-        if (s_last) *pc.done_counter = 0;
+        const int t = atomicAdd(ticket, 1);
+        s_last = (t == (int)(gridDim.x * gridDim.y) - 1) ? 1 : 0;
+        if (s_last) *ticket = 0;
     }
     __syncthreads();
-    if (!s_last || threadIdx.x >= 32) return;
-    __threadfence();
-    __shared__ float s_sums[kPeerMaxWidth];
-    if ((int)threadIdx.x < pc.width) s_sums[threadIdx.x] = __ldcg(sums + threadIdx.x);  // final values live in L2
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// Last CTA only, every thread calls it (blockDim.x >= 32): out[i] = acc[i] * scale(i) for i < 8, accumulators re-zeroed --
+// so the launch needs neither a memset before nor a scaling op after it.  The finished vector is also left in
+// `s_fin` (shared, 8 floats) for a peer exchange that may follow.
+template <typename ScaleFn>
+__device__ __forceinline__ void finalize_sums(float* __restrict__ acc, float* __restrict__ out, float* s_fin, ScaleFn scale) {
+    if (threadIdx.x < 8) {
+        const float v = __ldcg(acc + threadIdx.x) * scale((int)threadIdx.x);
+        out[threadIdx.x] = v;
+        s_fin[threadIdx.x] = v;
+        acc[threadIdx.x] = 0.0f;
+    }
+    __syncthreads();
+}
+
+// Last CTA only: warp 0 publishes the finished vector `s_vals` (shared memory) as this step's record into every peer's
+// buffer over NVLink and collects step `stamp - lag` (compute + collective in one kernel).
+__device__ __forceinline__ void peer_exchange_warp0(const PeerCtxDev& pc, const float* s_vals) {
+    if (threadIdx.x >= 32) return;
     uint32_t stamp = pc.stamp;
     if (pc.stamp_counter) {  // a replayed graph cannot change its kernel arguments: the step lives on the device
         if (threadIdx.x == 0) {
@@ -97,7 +115,7 @@ __device__ __forceinline__ void peer_exchange_from_last_cta(const PeerCtxDev& pc
         stamp = __shfl_sync(0xffffffffu, stamp, 0);
     }
     __syncwarp();
-    peer_publish(s_sums, pc.width, pc.rank, pc.world, pc.peers, (int)(stamp % (uint32_t)pc.slots), stamp);
+    peer_publish(s_vals, pc.width, pc.rank, pc.world, pc.peers, (int)(stamp % (uint32_t)pc.slots), stamp);
     __syncwarp();
     if (stamp > pc.lag)
         peer_collect(pc.out, pc.width, pc.world, pc.peers[pc.rank], (int)((stamp - pc.lag) % (uint32_t)pc.slots),

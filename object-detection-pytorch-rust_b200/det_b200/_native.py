@@ -51,18 +51,24 @@ PROTOTYPES = {
     "det_peer_sums_collect": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_peer_sums_exchange": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.c_uint32, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_yolo_loss_peer": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
-                                 c_p, c_p, c_p]),
+                                 c_p, c_p, c_p, c_p]),
     "det_roi_levels": (c_i, [c_p, c_l, c_i, c_i, c_f, c_i, c_p, c_p]),
     "det_roi_align_levels": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "det_roi_align_levels_backward": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "det_match_workspace_bytes": (c_l, [c_i, c_l, c_l]),
     "det_match_anchors": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
+    "det_match_grid_workspace_bytes": (c_l, [c_i, c_l]),
+    "det_match_grid": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p,
+                             c_i, c_p, c_l, c_p]),
+    "det_subsample_labels_grid": (c_i, [c_p, c_i, c_l, c_i, c_d, c_u64, c_p, c_p, c_i, c_p, c_p, c_i, c_p]),
+    "det_rpn_loss_sampled": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i,
+                                   c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p]),
     "det_match_quality": (c_i, [c_p, c_l, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "det_subsample_labels": (c_i, [c_p, c_i, c_l, c_i, c_d, c_u64, c_p]),
     "det_rpn_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f,
-                           c_p, c_p, c_p, c_p, c_p]),
+                           c_p, c_p, c_p, c_p, c_p, c_p]),
     "det_yolo_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
-                            c_p, c_p]),
+                            c_p, c_p, c_p]),
 }
 
 
@@ -77,6 +83,18 @@ class RpnLevel(ctypes.Structure):
     """det_rpn_level_t of include/det_b200.h"""
     _fields_ = [("objectness", c_p), ("deltas", c_p), ("cell_anchors", c_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_offset", c_l)]
+
+
+class AnchorLevel(ctypes.Structure):
+    """det_anchor_level_t of include/det_b200.h"""
+    _fields_ = [("h", ctypes.c_int32), ("w", ctypes.c_int32), ("stride", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("first_row", c_l)]
+
+
+class HeadLevel(ctypes.Structure):
+    """det_head_level_t of include/det_b200.h"""
+    _fields_ = [("objectness", c_p), ("deltas", c_p), ("grad_objectness", c_p), ("grad_deltas", c_p),
+                ("h", ctypes.c_int32), ("w", ctypes.c_int32)]
 
 
 class PeerCtx(ctypes.Structure):
@@ -169,6 +187,20 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise RuntimeError("det_b200 runs on CUDA tensors only (there is no CPU fallback); got a "
                                f"{t.device.type} tensor")
+
+
+_accumulators = {}
+
+
+def accumulators(device) -> torch.Tensor:
+    """The 16-float scratch the loss kernels accumulate into (include/det_b200.h: zero before the first call, re-armed by
+    every launch): one per (device, stream), created once -- no per-step memset."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    t = _accumulators.get(key)
+    if t is None:
+        t = torch.zeros((16,), dtype=torch.float32, device=device)
+        _accumulators[key] = t
+    return t
 
 
 def f32c(t):

@@ -77,8 +77,16 @@ class AnchorGenerator:
                 if t.numel():
                     N.call("det_grid_anchors", N.ptr(cell), a, int(h), int(w), int(stride), float(self.offset),
                            N.ptr(t), N.stream())
+                t._det_grid = (int(h), int(w), int(stride), int(a))  # layout tag read by the grid matcher (never guessed)
                 out.append(t)
         return out
+
+    def grid_layout(self, grid_sizes: List[Tuple[int, int]]):
+        """(levels, a) for Matcher.match_packed(grid=...), or None when the levels differ in anchors per position."""
+        na = self.num_anchors
+        if len(set(na)) != 1:
+            return None
+        return [(int(h), int(w), int(s)) for (h, w), s in zip(grid_sizes, self.strides)], na[0]
 
     def forward(self, features: List[torch.Tensor]) -> List[Boxes]:
         N.require_cuda(*features)

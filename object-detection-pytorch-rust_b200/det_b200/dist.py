@@ -183,12 +183,11 @@ class PeerSums:
         step overwrites (zeros after the first step)."""
         N = self._N
         assert self._collected == self.step, "do not mix the fused path with publish() / collect()"
-        if not hasattr(self, "_done"):
-            self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if not hasattr(self, "_stamp_dev"):
             self._stamp_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         ctx = N.PeerCtx()
         ctx.peers_dev = self.peers.data_ptr()
-        ctx.error_flag, ctx.done_counter = self.error.data_ptr(), self._done.data_ptr()
+        ctx.error_flag, ctx.done_counter = self.error.data_ptr(), None  # the ticket lives in the loss accumulators
         ctx.timeout_ns = self.timeout_ns
         ctx.width, ctx.rank, ctx.world, ctx.slots = self.width, self.rank, self.world, self.SLOTS
         ctx.lag = 1

@@ -22,10 +22,13 @@ from .structures import Boxes, Instances
 
 class Assignment:
     """Result of the batched target assignment: labels (N,R) int8, matched (N,R) int64 indices into each image's own
-    gt boxes, the packed gt table (sum_G,4) and its int32 offsets (N+1)."""
+    gt boxes, the packed gt table (sum_G,4) and its int32 offsets (N+1).  After a grid assignment with sampling it
+    also carries the per-image sample lists (N,S) int32 (anchor row | label << 24) + counts (N) int32 that the sampled
+    loss (det_rpn_loss_sampled) works from."""
 
-    def __init__(self, labels, matched, gt_table, gt_offsets):
+    def __init__(self, labels, matched, gt_table, gt_offsets, samples=None, sample_count=None):
         self.labels, self.matched, self.gt_table, self.gt_offsets = labels, matched, gt_table, gt_offsets
+        self.samples, self.sample_count = samples, sample_count
 
 
 class _FusedRPNLoss(torch.autograd.Function):
@@ -57,6 +60,32 @@ class _FusedRPNLoss(torch.autograd.Function):
         return gl, gd, None, None, None, None, None, None, None
 
 
+class _SampledRPNLoss(torch.autograd.Function):
+    """det_rpn_loss_sampled behind autograd: forward reduces the sums from the NCHW head tensors, backward re-launches
+    the kernel with the upstream gradients read on the device and scatters into zero-initialised NCHW gradients."""
+
+    @staticmethod
+    def forward(ctx, owner, n_norm, nl, anchors, labels, matched, gt_table, gt_offsets, samples, sample_count, *heads):
+        obj = [h.contiguous() for h in heads[:nl]]
+        dlt = [h.contiguous() for h in heads[nl:]]
+        asg = Assignment(labels, matched, gt_table, gt_offsets, samples, sample_count)
+        sums = owner._run_sampled(anchors, obj, dlt, asg, n_norm, None, None)
+        ctx.owner, ctx.n_norm, ctx.nl = owner, n_norm, nl
+        ctx.save_for_backward(anchors, labels, matched, gt_table, gt_offsets, samples, sample_count, *obj, *dlt)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        anchors, labels, matched, gt_table, gt_offsets, samples, sample_count = ctx.saved_tensors[:7]
+        heads = ctx.saved_tensors[7:]
+        obj, dlt = list(heads[:ctx.nl]), list(heads[ctx.nl:])
+        up = grad_sums[:2].contiguous().float()
+        g_obj, g_dlt = [torch.zeros_like(o) for o in obj], [torch.zeros_like(d) for d in dlt]
+        asg = Assignment(labels, matched, gt_table, gt_offsets, samples, sample_count)
+        ctx.owner._run_sampled(anchors, obj, dlt, asg, ctx.n_norm, up, (g_obj, g_dlt))
+        return (None,) * 10 + tuple(g_obj) + tuple(g_dlt)
+
+
 class RegionProposalNetwork:
     def __init__(self, strides: Sequence[int], anchor_sizes=((32,), (64,), (128,), (256,), (512,)),
                  aspect_ratios=((0.5, 1.0, 2.0),), anchor_offset: float = 0.0,
@@ -82,6 +111,7 @@ class RegionProposalNetwork:
         self.head = head
         self.training = False
         self._sample_seed = 0
+        self._anchor_cache = {}
 
     @classmethod
     def build(cls, conf, input_shapes):
@@ -151,23 +181,46 @@ class RegionProposalNetwork:
 
     # ------------------------------------------------------------------ assignment
     def assign(self, anchors: torch.Tensor, gt_boxes: List[torch.Tensor], sample: bool = True,
-               seed: Optional[int] = None) -> Assignment:
-        """Batched IoU -> Matcher -> (optional) device fg/bg subsample; no (G,R) matrix, no per-image loop."""
+               seed: Optional[int] = None, grid=None) -> Assignment:
+        """Batched IoU -> Matcher -> (optional) device fg/bg subsample; no (G,R) matrix, no per-image loop.
+        grid = AnchorGenerator.grid_layout(feature sizes) when `anchors` is that generator's table: one-pass grid
+        matcher + O(samples) subsample, and the Assignment carries the sample lists for `sampled_losses`."""
         gts = [g.tensor if isinstance(g, Boxes) else g for g in gt_boxes]
-        matched, labels, table, offsets = self.anchor_matcher.match_boxes(gts, anchors)
+        use_grid = grid is not None
+        res = self.anchor_matcher.match_boxes(gts, anchors, grid=grid, with_stats=use_grid and sample)
+        if use_grid and sample:
+            matched, labels, stats, table, offsets = res
+        else:
+            (matched, labels, table, offsets), stats = res, None
+        samples = counts = None
         if sample:
             if seed is None:
                 self._sample_seed += 1
                 seed = self._sample_seed
-            subsample_labels_(labels, self.batch_size_per_image, self.positive_fraction, seed)
-        return Assignment(labels, matched, table, offsets)
+            if stats is not None:
+                _, samples, counts = subsample_labels_(labels, self.batch_size_per_image, self.positive_fraction, seed,
+                                                       stats=stats, return_samples=True)
+            else:
+                subsample_labels_(labels, self.batch_size_per_image, self.positive_fraction, seed)
+        return Assignment(labels, matched, table, offsets, samples, counts)
+
+    @staticmethod
+    def _grid_of(level_tensors) -> Optional[tuple]:
+        """(levels, a) if every per-level anchor tensor carries AnchorGenerator's layout tag, else None."""
+        tags = [getattr(t, "_det_grid", None) for t in level_tensors]
+        if any(t is None for t in tags) or len({t[3] for t in tags}) != 1:
+            return None
+        if any(t[0] * t[1] * t[3] != x.shape[0] for t, x in zip(tags, level_tensors)):
+            return None
+        return [(t[0], t[1], t[2]) for t in tags], tags[0][3]
 
     @torch.no_grad()
     def label_and_sample_anchors(self, anchors: List[Boxes], gt_instances: List[Instances]):
         """Reference signature (rpn.py:132): -> (list of int8[R] labels, list of (R,4) matched gt boxes)."""
-        at = Boxes.cat(anchors).tensor
+        level_tensors = [a.tensor if isinstance(a, Boxes) else a for a in anchors]
+        at = level_tensors[0] if len(level_tensors) == 1 else torch.cat(level_tensors, 0)
         gt_boxes = [x.gt_boxes for x in gt_instances]
-        asg = self.assign(at, gt_boxes, sample=True)
+        asg = self.assign(at, gt_boxes, sample=True, grid=self._grid_of(level_tensors))
         gt_labels, matched_gt = [], []
         for i, g in enumerate(gt_boxes):
             gt_labels.append(asg.labels[i])
@@ -176,26 +229,93 @@ class RegionProposalNetwork:
         return gt_labels, matched_gt
 
     # ------------------------------------------------------------------ losses
-    def _run_loss(self, anchors, logits, deltas, asg: Assignment, n_norm, upstream, grad_logits, grad_deltas):
-        n, r = logits.shape
-        dev = logits.device
-        sums = torch.zeros((8,), dtype=torch.float32, device=dev)
+    def _loss_scales(self, n_norm):
+        """(loss_type, w_cls / norm, w_loc / norm) with norm = batch_size_per_image * N_global (rpn.py:238-243)."""
         if self.box_reg_loss_type not in ("smooth_l1", "giou"):
             raise ValueError(f"Invalid dense box regression loss type '{self.box_reg_loss_type}'")
         norm = float(self.batch_size_per_image * n_norm)
-        w_cls = float(getattr(self.loss_weight, "cls_loss", self.loss_weight[0] if isinstance(self.loss_weight, (tuple, list)) else 1.0))
-        w_loc = float(getattr(self.loss_weight, "loc_loss", self.loss_weight[1] if isinstance(self.loss_weight, (tuple, list)) else 1.0))
+        lw = self.loss_weight
+        w_cls = float(getattr(lw, "cls_loss", lw[0] if isinstance(lw, (tuple, list)) else 1.0))
+        w_loc = float(getattr(lw, "loc_loss", lw[1] if isinstance(lw, (tuple, list)) else 1.0))
+        return (0 if self.box_reg_loss_type == "smooth_l1" else 1), w_cls / norm, w_loc / norm
+
+    def _run_loss(self, anchors, logits, deltas, asg: Assignment, n_norm, upstream, grad_logits, grad_deltas):
+        """One launch of the dense fused kernel: returns sums (8) = [cls_loss, loc_loss, #pos, #neg, 0...] already
+        weighted and normalised (the kernel's last CTA does it: no memset before, no scaling op after)."""
+        n, r = logits.shape
+        dev = logits.device
+        loss_type, s_cls, s_loc = self._loss_scales(n_norm)
         w = self.box2box_transform.weights
         with torch.cuda.device(dev):
+            sums = torch.empty((8,), dtype=torch.float32, device=dev)
             N.call("det_rpn_loss", N.ptr(logits), N.ptr(deltas), N.ptr(asg.labels), N.ptr(asg.matched),
                    N.ptr(asg.gt_table), N.ptr(asg.gt_offsets), N.ptr(anchors), n, r, *w,
-                   self.box2box_transform.scale_clamp, 0 if self.box_reg_loss_type == "smooth_l1" else 1,
-                   float(self.smooth_l1_beta), w_cls / norm, w_loc / norm, N.ptr(upstream), N.ptr(sums),
-                   N.ptr(grad_logits), N.ptr(grad_deltas), N.stream())
-        # [0] cls sum, [1] loc sum -> weighted, normalised losses in place (rpn.py:238-243)
-        sums[0] *= w_cls / norm
-        sums[1] *= w_loc / norm
+                   self.box2box_transform.scale_clamp, loss_type, float(self.smooth_l1_beta), s_cls, s_loc,
+                   N.ptr(upstream), N.ptr(N.accumulators(dev)), N.ptr(sums), N.ptr(grad_logits), N.ptr(grad_deltas),
+                   N.stream())
         return sums
+
+    # ------------------------------------------------------------------ sampled losses on the conv-layout head
+    def _run_sampled(self, anchors, obj, dlt, asg: Assignment, n_norm, upstream, grads, clear=None):
+        """det_rpn_loss_sampled on per-level NCHW head tensors (obj[l] (N,A,H,W), dlt[l] (N,A*4,H,W)) -- or, with
+        dlt.dim() == 3, on flat (N,R) / (N,R,4) tensors.  grads = (list of grad_obj, list of grad_dlt) buffers the
+        kernel scatters into (None: forward only); clear = (samples, counts) of the previous step for persistent
+        buffers.  Returns sums (8) like _run_loss."""
+        assert asg.samples is not None, "sampled losses need an Assignment from assign(..., grid=...) with sampling"
+        flat = isinstance(obj, torch.Tensor)
+        dev = (obj if flat else obj[0]).device
+        n = (obj if flat else obj[0]).shape[0]
+        r = anchors.shape[0]
+        loss_type, s_cls, s_loc = self._loss_scales(n_norm)
+        w = self.box2box_transform.weights
+        cs, cc = (None, None) if clear is None else clear
+        with torch.cuda.device(dev):
+            sums = torch.empty((8,), dtype=torch.float32, device=dev)
+            if flat:
+                lv, nl, a = None, 0, 1
+                ptrs = (N.ptr(obj), N.ptr(dlt), N.ptr(grads[0] if grads else None), N.ptr(grads[1] if grads else None))
+            else:
+                a = obj[0].shape[1]
+                lv = (N.HeadLevel * len(obj))()
+                for i, (o, d) in enumerate(zip(obj, dlt)):
+                    assert o.shape[1] == a and d.shape[1] == 4 * a and o.is_contiguous() and d.is_contiguous()
+                    lv[i].objectness, lv[i].deltas = o.data_ptr(), d.data_ptr()
+                    lv[i].grad_objectness = grads[0][i].data_ptr() if grads else None
+                    lv[i].grad_deltas = grads[1][i].data_ptr() if grads else None
+                    lv[i].h, lv[i].w = o.shape[2], o.shape[3]
+                nl = len(obj)
+                ptrs = (None, None, None, None)
+                lv = ctypes.cast(lv, ctypes.c_void_p)
+            N.call("det_rpn_loss_sampled", lv, nl, a, *ptrs, N.ptr(asg.samples), N.ptr(asg.sample_count),
+                   asg.samples.shape[1], N.ptr(cs), N.ptr(cc), N.ptr(asg.matched), N.ptr(asg.gt_table),
+                   N.ptr(asg.gt_offsets), N.ptr(anchors), n, r, *w, self.box2box_transform.scale_clamp, loss_type,
+                   float(self.smooth_l1_beta), s_cls, s_loc, N.ptr(upstream), N.ptr(N.accumulators(dev)), N.ptr(sums),
+                   N.stream())
+        return sums
+
+    def sampled_losses(self, anchors: torch.Tensor, pred_objectness: List[torch.Tensor], pred_deltas: List[torch.Tensor],
+                       asg: Assignment, num_images_global: Optional[int] = None, grad_buffers=None,
+                       clear_previous=None):
+        """The RPN losses straight from the head convolutions' NCHW outputs (per level (N,A,Hi,Wi) / (N,A*4,Hi,Wi)), on
+        the sampled anchors only: no layout change (rpn.py:270-284), no dense label sweep, O(samples) traffic.
+
+        Default: autograd-connected {"cls_loss", "loc_loss", ...}; backward re-launches the kernel, which scatters the
+        gradients into zero-initialised NCHW tensors (exactly what the head convolutions' backward takes).
+        grad_buffers=(list grad_obj, list grad_dlt): fused forward+backward in ONE launch into caller-owned buffers --
+        zeroed by the caller, or persistent with clear_previous=(samples, counts) of the step that last wrote them."""
+        N.require_cuda(anchors, *pred_objectness, *pred_deltas)
+        at = N.f32c(anchors)
+        n_norm = pred_objectness[0].shape[0] if num_images_global is None else int(num_images_global)
+        if grad_buffers is not None:
+            obj = [o.detach().contiguous() for o in pred_objectness]
+            dlt = [d.detach().contiguous() for d in pred_deltas]
+            sums = self._run_sampled(at, obj, dlt, asg, n_norm, None, grad_buffers, clear_previous)
+        else:
+            nl = len(pred_objectness)
+            sums = _SampledRPNLoss.apply(self, n_norm, nl, at, asg.labels, asg.matched, asg.gt_table, asg.gt_offsets,
+                                         asg.samples, asg.sample_count, *pred_objectness, *pred_deltas)
+        return {"cls_loss": sums[0], "loc_loss": sums[1], "num_pos_anchors": sums[2].detach(),
+                "num_neg_anchors": sums[3].detach(), "sums": sums}
 
     def fused_losses(self, anchors: torch.Tensor, logits: torch.Tensor, deltas: torch.Tensor, asg: Assignment,
                      num_images_global: Optional[int] = None, with_grads: bool = False):
@@ -252,6 +372,19 @@ class RegionProposalNetwork:
                                      self.pre_nms_topk[self.training], self.post_nms_topk[self.training],
                                      self.min_box_size)
 
+    def _cached_anchors(self, feats_hw, device):
+        """Per-level anchors + their concatenation for these feature sizes: a pure function of the shapes
+        (anchor_generators.py:212-225 recomputes them every forward), so they are generated once per shape."""
+        key = (tuple(feats_hw), str(device))
+        hit = self._anchor_cache.get(key)
+        if hit is None:
+            if len(self._anchor_cache) > 16:
+                self._anchor_cache.clear()
+            levels = self.anchor_generator.grid_anchors(feats_hw, device)
+            hit = (levels, levels[0] if len(levels) == 1 else torch.cat(levels, 0))
+            self._anchor_cache[key] = hit
+        return hit
+
     def forward(self, images, features: Dict[str, torch.Tensor] = None, gt_instances: Optional[List[Instances]] = None,
                 head_outputs=None):
         """`forward` of the reference (rpn.py:246) from the head outputs: (objectness list, deltas list) in the conv
@@ -261,17 +394,24 @@ class RegionProposalNetwork:
             head_outputs = self.head(features)
         obj, dlt = head_outputs
         image_sizes = images.image_sizes if hasattr(images, "image_sizes") else images
-        feats_hw = [tuple(o.shape[-2:]) for o in obj]
-        anchors = self.anchor_generator.grid_anchors(feats_hw, obj[0].device)
-        n = obj[0].shape[0]
-        logits = [o.permute(0, 2, 3, 1).reshape(n, -1) for o in obj]
-        deltas = [d.view(n, -1, 4, d.shape[-2], d.shape[-1]).permute(0, 3, 4, 1, 2).reshape(n, -1, 4) for d in dlt]
+        feats_hw = [tuple(int(v) for v in o.shape[-2:]) for o in obj]
+        anchors, anchors_cat = self._cached_anchors(feats_hw, obj[0].device)
         losses = {}
         if self.training:
+            # grid matcher -> O(samples) subsample -> sampled loss reading the NCHW head in place: the reference's
+            # layout change (rpn.py:270-284) is never materialised and only library kernels of this package launch
             assert gt_instances is not None, "RPN requires gt_instances in training!"
-            at = torch.cat(anchors, 0)
-            asg = self.assign(at, [x.gt_boxes for x in gt_instances])
-            res = self.fused_losses(at, torch.cat(logits, 1), torch.cat(deltas, 1), asg)
+            at = anchors_cat
+            grid = self.anchor_generator.grid_layout(feats_hw)
+            if grid is not None and all(o.dtype == torch.float32 for o in obj):
+                asg = self.assign(at, [x.gt_boxes for x in gt_instances], grid=grid)
+                res = self.sampled_losses(at, list(obj), list(dlt), asg)
+            else:  # levels with different anchor counts: generic matcher + dense loss on re-laid-out tensors
+                n = obj[0].shape[0]
+                logits = [o.permute(0, 2, 3, 1).reshape(n, -1) for o in obj]
+                deltas = [d.view(n, -1, 4, d.shape[-2], d.shape[-1]).permute(0, 3, 4, 1, 2).reshape(n, -1, 4) for d in dlt]
+                asg = self.assign(at, [x.gt_boxes for x in gt_instances])
+                res = self.fused_losses(at, torch.cat(logits, 1), torch.cat(deltas, 1), asg)
             losses = {"cls_loss": res["cls_loss"], "loc_loss": res["loc_loss"]}
         sizes = torch.tensor([[int(h), int(w)] for h, w in image_sizes], dtype=torch.int32).to(obj[0].device)
         ob, os_, cnt, flag = self.proposals_from_heads(obj, dlt, sizes)

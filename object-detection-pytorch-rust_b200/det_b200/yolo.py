@@ -198,7 +198,6 @@ class YoloGridTrainer:
         self.matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches)
         self.lambda_coord, self.lambda_noobj = float(lambda_coord), float(lambda_noobj)
         self._anchors = {}
-        self._scales = {}
 
     def prior_boxes(self, device) -> torch.Tensor:
         """(S*S*B,4) cell-centred prior boxes, order (row,col,b)."""
@@ -225,32 +224,25 @@ class YoloGridTrainer:
         return YoloAssignment(labels, matched, gt_table, gt_offsets)
 
     def _run_loss(self, head_t, asg, gt_classes, norm, upstream, grad_head, peer=None):
+        """One launch: returns sums (8) = [lambda_coord * loc, obj, cls] / norm, #pos, #neg, 0... -- scaled by the
+        kernel's last CTA (no memset before, no scaling op after the launch)."""
         h = self.head
         n = head_t.shape[0]
-        sums = torch.zeros((8,), dtype=torch.float32, device=head_t.device)
+        dev = head_t.device
         self._world_prev = None
-        with torch.cuda.device(head_t.device):
+        with torch.cuda.device(dev):
+            sums = torch.empty((8,), dtype=torch.float32, device=dev)
             args = (N.ptr(head_t), N.ptr(asg.labels), N.ptr(asg.matched), N.ptr(asg.gt_table),
                     N.ptr(gt_classes), N.ptr(asg.gt_offsets), n, h.S, h.B, h.C, h.image_size[0], h.image_size[1],
-                    N.ptr(h.priors_on(head_t.device)), self.lambda_coord, self.lambda_noobj, 1.0 / norm,
-                    N.ptr(upstream), N.ptr(sums), N.ptr(grad_head))
+                    N.ptr(h.priors_on(dev)), self.lambda_coord, self.lambda_noobj, 1.0 / norm,
+                    N.ptr(upstream), N.ptr(N.accumulators(dev)), N.ptr(sums), N.ptr(grad_head))
             if peer is None:
                 N.call("det_yolo_loss", *args, N.stream())
             else:  # the loss kernel's last CTA publishes the sums to every rank and collects the previous step's
                 ctx, prev = peer.fused_ctx()
                 N.call("det_yolo_loss_peer", *args, ctypes.byref(ctx), N.stream())
                 self._world_prev = prev
-        return sums * self._sum_scale(norm, head_t.device)  # one launch: [lambda_coord/norm, 1/norm, 1/norm, 1, ...]
-
-    def _sum_scale(self, norm: float, device) -> torch.Tensor:
-        k = (float(norm), str(device))
-        v = self._scales.get(k)
-        if v is None:
-            if len(self._scales) > 64:
-                self._scales.clear()
-            v = torch.tensor([self.lambda_coord / norm, 1.0 / norm, 1.0 / norm, 1, 1, 1, 1, 1], dtype=torch.float32).to(device)
-            self._scales[k] = v
-        return v
+        return sums
 
     def loss(self, head_t: torch.Tensor, asg: YoloAssignment, gt_classes: torch.Tensor,
              normalizer: Optional[float] = None, with_grads: bool = False, peer=None):
@@ -276,7 +268,7 @@ class YoloGridTrainer:
             out["grad_head"] = gh
             if peer is not None:
                 prev = self._world_prev
-                out["world_sums_prev"] = None if prev is None else prev * self._sum_scale(norm, ht.device)
+                out["world_sums_prev"] = prev  # already the world sum of the previous step's reported (scaled) sums
         return out
 
 
