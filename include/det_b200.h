@@ -214,10 +214,10 @@ DET_API int det_match_anchors(const float* gt_boxes, const int32_t* gt_offsets, 
                       void* workspace, int64_t workspace_bytes, void* stream);
 /* The same assignment for GRID anchors -- the (R,4) table AnchorGenerator.forward produces
  * (python/src/models/modules/anchor_generators.py:158-179: per level h*w positions x `a` cell anchors, order (h,w,a),
- * levels concatenated) -- in ONE streaming pass (csrc/assign_grid.cu): a gt-centric kernel evaluates every row maximum on
- * the closed-form window of anchors that can overlap the box, then one anchor-centric kernel (8 x 4 position tiles per
- * warp) writes labels and matched indices including the low-quality promotion.  Results are bit-identical to
- * det_match_anchors.  levels_host[l] = {h, w, stride, 0, first_row}; rows must be consecutive and sum to r;
+ * levels concatenated) -- in ONE streaming pass (csrc/assign_grid.cu): a gt-centric kernel marks the 8 x 4-position tiles
+ * each box can overlap and evaluates every row maximum on the closed-form window where it can be attained, then one
+ * anchor-centric kernel (a tile per warp) writes labels and matched indices including the low-quality promotion.
+ * Results are bit-identical to det_match_anchors.  levels_host[l] = {h, w, stride, 0, first_row}; rows must be consecutive and sum to r;
  * a in {1, 3, 9}, num_levels * a <= 32, num_levels <= 8 (else DET_ERR_UNSUPPORTED: use det_match_anchors).
  * Optional per-image statistics for det_subsample_labels_grid (both NULL to skip): stats (n,4) int32 = {#positives,
  * #ignored (label -1), 0, 0} (written by the call), pos_list (n, list_cap) int32 = anchor row | label << 24 of the
@@ -226,7 +226,7 @@ typedef struct det_anchor_level {
     int32_t h, w, stride, reserved;
     int64_t first_row;
 } det_anchor_level_t;
-DET_API int64_t det_match_grid_workspace_bytes(int n, int64_t sum_g);
+DET_API int64_t det_match_grid_workspace_bytes(int n, int64_t sum_g, const det_anchor_level_t* levels_host, int num_levels);
 DET_API int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors,
                    int64_t r, const det_anchor_level_t* levels_host, int num_levels, int a,
                    const float* thresholds_host, const int32_t* labels_host, int num_thresholds, int allow_low_quality,

@@ -48,12 +48,47 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// ---- K1: row maximum of pairwise_iou(gt, anchors) for every gt box, one warp per box ----------------------------------
+// ---- K1: one warp per gt box: (1) marks the tiles of its image the box can overlap (bit `t` of mask[img][tile] for the
+// image's t-th box, t < 32), (2) the row maximum of pairwise_iou(gt, anchors).
 // stats (4 int32 per image: #positives, #ignored, 2 spare) are zeroed here for match_grid_kernel, which follows on the
-// same stream (saves a memset launch).
+// same stream; flags / mask are zeroed by the host's memset before the launch.
+constexpr int kFlagPromoteAll = 1;  // some gt of the image has row maximum 0: `Q == rowmax` holds for EVERY anchor
+constexpr int kFlagManyGt = 2;      // more than 32 gt boxes: the tile masks do not cover the image, cull on the fly
+
+__device__ __forceinline__ int gt_image(const int32_t* __restrict__ gt_off, int n, int t) {
+    int lo = 0, hi = n;  // the image with gt_off[img] <= t < gt_off[img + 1] (empty images are skipped by construction)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (gt_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// positions x in [0, w) whose anchor [a_lo + x s, a_hi + x s] can reach the interval (g_lo, g_hi), one position of margin
+__device__ __forceinline__ void reach_window(float g_lo, float g_hi, float a_lo, float a_hi, float s, int w, int& lo, int& hi) {
+    const float f_lo = floorf((g_lo - a_hi) / s) - 1.0f, f_hi = ceilf((g_hi - a_lo) / s) + 1.0f;
+    lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)w);
+    hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), -1.0f);
+}
+
+// positions whose overlap with (g_lo, g_hi) along one axis can be the LARGEST: with centre offset d the overlap is
+// min(a_len, g_len, (a_len + g_len)/2 - |d|): constant on the plateau |d| <= |g_len - a_len| / 2 and strictly smaller
+// by at least one stride for every further position.  IoU grows with the overlap of either axis, so a row maximum (and
+// every anchor that EQUALS it) lies on plateau x plateau; two positions of margin absorb the rounding of the coordinates.
+__device__ __forceinline__ void plateau_window(float g_lo, float g_hi, float a_lo, float a_hi, float s, int w, int& lo, int& hi) {
+    const float gc = 0.5f * (g_lo + g_hi), ac = 0.5f * (a_lo + a_hi);
+    const float half = 0.5f * fabsf((g_hi - g_lo) - (a_hi - a_lo));
+    const float f_lo = floorf((gc - ac - half) / s) - 2.0f, f_hi = ceilf((gc - ac + half) / s) + 2.0f;
+    lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)w);
+    hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), -1.0f);
+}
+
 __global__ void __launch_bounds__(256)
-match_rowmax_kernel(const float4* __restrict__ gt, int64_t sum_g, const float4* __restrict__ anchors, GridLayoutDev lay,
-                    float* __restrict__ rowmax, int32_t* __restrict__ stats, int stats_words) {
+match_rowmax_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, int n, int64_t sum_g,
+                    const float4* __restrict__ anchors, GridLayoutDev lay, int want_rowmax, float* __restrict__ rowmax,
+                    int32_t* __restrict__ flags, uint32_t* __restrict__ mask, int32_t* __restrict__ stats,
+                    int stats_words) {
+    const unsigned FULLMASK = 0xffffffffu;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (stats && tid < stats_words) stats[tid] = 0;
     const int64_t t = tid >> 5;
@@ -71,44 +106,71 @@ match_rowmax_kernel(const float4* __restrict__ gt, int64_t sum_g, const float4* 
         // IoU <= min(area) / max(area); anything doubtful (degenerate or non-finite boxes) is never pruned
         bound = (finite && ga > 0.0f && aa > 0.0f && isfinite(aa)) ? fminf(ga, aa) / fmaxf(ga, aa) : INFINITY;
     }
+    // ---- (1) tile marks
+    const int img = gt_image(gt_off, n, (int)t);
+    const int tl = (int)t - gt_off[img];
+    if (tl >= 32) {
+        if (lane == 0 && tl == 32) atomicOr(&flags[img], kFlagManyGt);
+    } else {
+        for (int l = 0; l < lay.nlev; ++l) {
+            const GridLevelDev L = lay.lv[l];
+            // union of the level's cell anchors at position (0, 0)
+            float ux1 = INFINITY, uy1 = INFINITY, ux2 = -INFINITY, uy2 = -INFINITY;
+            for (int a = 0; a < A; ++a) {
+                ux1 = fminf(ux1, __shfl_sync(FULLMASK, ab0.x, l * A + a)); uy1 = fminf(uy1, __shfl_sync(FULLMASK, ab0.y, l * A + a));
+                ux2 = fmaxf(ux2, __shfl_sync(FULLMASK, ab0.z, l * A + a)); uy2 = fmaxf(uy2, __shfl_sync(FULLMASK, ab0.w, l * A + a));
+            }
+            int x_lo = 0, x_hi = L.w - 1, y_lo = 0, y_hi = L.h - 1;
+            if (finite && isfinite(ux1) && isfinite(uy1) && isfinite(ux2) && isfinite(uy2)) {
+                reach_window(gb.x, gb.z, ux1, ux2, (float)L.stride, L.w, x_lo, x_hi);
+                reach_window(gb.y, gb.w, uy1, uy2, (float)L.stride, L.h, y_lo, y_hi);
+            }
+            if (x_lo > x_hi || y_lo > y_hi) continue;
+            const int tx_lo = x_lo / kTileW, tx_n = x_hi / kTileW - tx_lo + 1;
+            const int ty_lo = y_lo / kTileH, ty_n = y_hi / kTileH - ty_lo + 1;
+            uint32_t* __restrict__ row = mask + (int64_t)img * lay.tiles_total + L.first_tile;
+            for (int k = lane; k < tx_n * ty_n; k += 32)
+                atomicOr(&row[(ty_lo + k / tx_n) * L.tiles_x + tx_lo + k % tx_n], 1u << tl);
+        }
+    }
+    if (!want_rowmax) return;
+    // ---- (2) row maximum
     float best = 0.0f;
-    unsigned pending = __ballot_sync(0xffffffffu, lane < P);
+    unsigned pending = __ballot_sync(FULLMASK, lane < P);
     while (pending) {
         // the pending pair with the largest bound
         const float mine = ((pending >> lane) & 1u) ? bound : -1.0f;
         const float bmax = warp_max(mine);
         if (bmax * 1.0001f < best) break;  // no remaining pair can reach (let alone equal) the maximum found so far
-        const int src = __ffs(__ballot_sync(0xffffffffu, mine == bmax)) - 1;
+        const int src = __ffs(__ballot_sync(FULLMASK, mine == bmax)) - 1;
         pending &= ~(1u << src);
-        const float4 a0 = make_float4(__shfl_sync(0xffffffffu, ab0.x, src), __shfl_sync(0xffffffffu, ab0.y, src),
-                                      __shfl_sync(0xffffffffu, ab0.z, src), __shfl_sync(0xffffffffu, ab0.w, src));
+        const float4 a0 = make_float4(__shfl_sync(FULLMASK, ab0.x, src), __shfl_sync(FULLMASK, ab0.y, src),
+                                      __shfl_sync(FULLMASK, ab0.z, src), __shfl_sync(FULLMASK, ab0.w, src));
         const GridLevelDev L = lay.lv[src / A];
         const int a = src % A;
-        // anchor at (y, x) = a0 + (x, y) * stride up to rounding: it can only intersect gb if
-        //   a0.x + x s < gb.z  and  a0.z + x s > gb.x  (same in y); one position of margin on each side
         int x_lo = 0, x_hi = L.w - 1, y_lo = 0, y_hi = L.h - 1;
-        if (finite) {
-            const float s = (float)L.stride;
-            const float fx_lo = floorf((gb.x - a0.z) / s) - 1.0f, fx_hi = ceilf((gb.z - a0.x) / s) + 1.0f;
-            const float fy_lo = floorf((gb.y - a0.w) / s) - 1.0f, fy_hi = ceilf((gb.w - a0.y) / s) + 1.0f;
-            x_lo = (int)fminf(fmaxf(fx_lo, 0.0f), (float)L.w);
-            x_hi = (int)fmaxf(fminf(fx_hi, (float)(L.w - 1)), -1.0f);
-            y_lo = (int)fminf(fmaxf(fy_lo, 0.0f), (float)L.h);
-            y_hi = (int)fmaxf(fminf(fy_hi, (float)(L.h - 1)), -1.0f);
+        if (finite && ga > 0.0f && isfinite(a0.x) && isfinite(a0.y) && isfinite(a0.z) && isfinite(a0.w) &&
+            a0.z > a0.x && a0.w > a0.y) {
+            plateau_window(gb.x, gb.z, a0.x, a0.z, (float)L.stride, L.w, x_lo, x_hi);
+            plateau_window(gb.y, gb.w, a0.y, a0.w, (float)L.stride, L.h, y_lo, y_hi);
         }
-        const int wx = x_hi - x_lo + 1, wy = y_hi - y_lo + 1;
         float v = 0.0f;
-        if (wx > 0 && wy > 0) {
-            const int nwin = wx * wy;
-            for (int k = lane; k < nwin; k += 32) {
-                const int y = y_lo + k / wx, x = x_lo + k % wx;
-                const float4 ab = anchors[L.first_row + ((int64_t)y * L.w + x) * A + a];
+        // the lanes sweep the window as an 8 x 4 patch (no integer division, 32-bit row arithmetic: r < 2^31 / 16)
+        const float4* __restrict__ lvl = anchors + L.first_row + a;
+        const int lx = lane & 7, ly = lane >> 3;
+        for (int y = y_lo + ly; y <= y_hi; y += 4) {
+            const int rowbase = y * L.w;
+            for (int x = x_lo + lx; x <= x_hi; x += 8) {
+                const float4 ab = lvl[(rowbase + x) * A];
                 v = fmaxf(v, pair_iou(gb, ga, ab, box_area(ab)));  // same expression as match_grid_kernel
             }
         }
         best = fmaxf(best, warp_max(v));
     }
-    if (lane == 0) rowmax[t] = best;
+    if (lane == 0) {
+        rowmax[t] = best;
+        if (best == 0.0f) atomicOr(&flags[img], kFlagPromoteAll);
+    }
 }
 
 // ---- K2: labels + matched index of every anchor, one pass -------------------------------------------------------------
@@ -120,12 +182,32 @@ __device__ __forceinline__ bool tile_culls(const TileBox& bb, const float4 g) {
     return g.z <= bb.x1 || g.x >= bb.x2 || g.w <= bb.y1 || g.y >= bb.y2;
 }
 
+// one gt box against the A anchors of this lane.  Lanes without a position hold all-zero anchors: their IoUs are 0, which
+// never beats the initial best and is never stored.  hits: bit a set iff some IoU of anchor a equalled its gt's row maximum.
+template <int A>
+__device__ __forceinline__ void match_one(const float4 gb, float rm, int t, const float4 (&ab)[A], const float (&aa)[A],
+                                          float (&best)[A], int (&bidx)[A], unsigned& hits) {
+    const float ga = box_area(gb);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        // pairwise_iou(gt, anchors): boxes1 = gt, boxes2 = anchors (rpn.py:167).  (The quotient stays behind the
+        // `inter > 0` branch: evaluated unconditionally, 0 / x takes the division's slow path -- measured 25 % slower.)
+        const float v = pair_iou(gb, ga, ab[a], aa[a]);
+        if (v > best[a]) {
+            best[a] = v;
+            bidx[a] = t;
+        }
+        hits |= (v == rm) ? (1u << a) : 0u;  // matcher.py:110-120; skipped pairs have v = 0 and could only match rm = 0
+    }
+}
+
 template <int A, bool DENSE>
-__global__ void __launch_bounds__(kGridWarps * 32)
+__global__ void __launch_bounds__(kGridWarps * 32, A <= 3 ? 4 : 2)
 match_grid_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
                   int n, int imgs, int64_t r, GridLayoutDev lay, MatchRule rule, const float* __restrict__ rowmax,
-                  int64_t* __restrict__ matched, int8_t* __restrict__ labels, float* __restrict__ matched_iou,
-                  int32_t* __restrict__ stats, int32_t* __restrict__ pos_list, int list_cap) {
+                  const int32_t* __restrict__ flags, const uint32_t* __restrict__ mask, int64_t* __restrict__ matched,
+                  int8_t* __restrict__ labels, float* __restrict__ matched_iou, int32_t* __restrict__ stats,
+                  int32_t* __restrict__ pos_list, int list_cap) {
     const unsigned FULLMASK = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int T = blockIdx.x * kGridWarps + (threadIdx.x >> 5);
@@ -141,100 +223,139 @@ match_grid_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_
     const int64_t row0 = L.first_row + ((int64_t)y * L.w + x) * A;  // this lane's A anchors are consecutive rows
     float4 ab[A];
     float aa[A];
-    TileBox bb{INFINITY, INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         ab[a] = valid ? anchors[row0 + a] : make_float4(0.f, 0.f, 0.f, 0.f);
         aa[a] = box_area(ab[a]);
-        if (valid) {  // fminf / fmaxf drop NaN coordinates: a NaN anchor intersects nothing
-            bb.x1 = fminf(bb.x1, ab[a].x); bb.y1 = fminf(bb.y1, ab[a].y);
-            bb.x2 = fmaxf(bb.x2, ab[a].z); bb.y2 = fmaxf(bb.y2, ab[a].w);
-        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bb.x1 = fminf(bb.x1, __shfl_xor_sync(FULLMASK, bb.x1, o)); bb.y1 = fminf(bb.y1, __shfl_xor_sync(FULLMASK, bb.y1, o));
-        bb.x2 = fmaxf(bb.x2, __shfl_xor_sync(FULLMASK, bb.x2, o)); bb.y2 = fmaxf(bb.y2, __shfl_xor_sync(FULLMASK, bb.y2, o));
-    }
+    const int nvalid = __popc(__ballot_sync(FULLMASK, valid));
+    const int lab_none = rule.lab[0];  // label of an anchor that overlaps no gt box (IoU 0): bucket (-inf, thr[0])
+    const float thr0 = rule.thr[0], thr1 = rule.thr[1];  // the reference's rules have one or two thresholds (thr[i >= nthr] = +inf)
+    const int lab1 = rule.lab[1], lab2 = rule.lab[2];
     const int i0 = blockIdx.y * imgs, ni = min(imgs, n - i0);
+    // the image's flags and this tile's gt mask are prefetched one image ahead
+    int fl_next = flags[i0], g0_next = gt_off[i0];
+    unsigned mk_next = mask[(int64_t)i0 * lay.tiles_total + T];
     for (int ii = 0; ii < ni; ++ii) {
         const int img = i0 + ii;
-        const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
+        const int fl = fl_next, g0 = g0_next;
+        unsigned todo = mk_next;
+        if (ii + 1 < ni) {
+            fl_next = flags[img + 1];
+            g0_next = gt_off[img + 1];
+            mk_next = mask[(int64_t)(img + 1) * lay.tiles_total + T];
+        }
+        const bool promote_all = rule.allow_lq && (fl & kFlagPromoteAll);
+        const int64_t o = (int64_t)img * r + row0;
+        if (todo == 0u && !(fl & kFlagManyGt) && !promote_all) {
+            // no gt box reaches this tile (the usual case on the fine levels; also an image without gt,
+            // matcher.py:67-77): every anchor has IoU 0 with every box -- match 0, the label of the lowest bucket
+            if (DENSE && valid) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    matched[o + a] = 0;
+                    labels[o + a] = (int8_t)lab_none;
+                    if (matched_iou) matched_iou[o + a] = 0.0f;
+                }
+            }
+            // (a rule whose lowest bucket is positive makes positives dense: the list overflows by construction and the
+            //  sampler takes its generic path, so untouched tiles only count)
+            if (stats && lab_none != 0 && lane == 0) atomicAdd(&stats[img * 4 + (lab_none == -1 ? 1 : 0)], nvalid * A);
+            continue;
+        }
+        // a touched tile: the image has gt boxes (an image without any has an empty mask and no flag)
         float best[A];
         int bidx[A];
-        bool hit[A];
+        unsigned hits = 0u;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             best[a] = 0.0f;  // IoUs are >= 0 and only a strictly larger one replaces the incumbent: gt 0 wins ties at 0,
             bidx[a] = 0;     // exactly like torch.max(dim=0)
-            hit[a] = false;
         }
-        bool promote_all = false;  // a gt whose row maximum is 0 promotes EVERY anchor (`Q == rowmax` holds everywhere)
-        for (int t0 = 0; t0 < G; t0 += 32) {
-            float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-            float rm_mine = 1.0f;
-            bool over = false;
-            if (t0 + lane < G) {
-                mine = gt[g0 + t0 + lane];
-                over = !tile_culls(bb, mine);
-                if (rule.allow_lq) rm_mine = rowmax[g0 + t0 + lane];
-            }
-            if (rule.allow_lq) promote_all |= __any_sync(FULLMASK, rm_mine == 0.0f);
-            unsigned todo = __ballot_sync(FULLMASK, over);
+        if (!(fl & kFlagManyGt)) {
             while (todo) {  // ascending gt index: the first maximum wins
-                const int src = __ffs(todo) - 1;
+                const int t = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const float4 gb = make_float4(__shfl_sync(FULLMASK, mine.x, src), __shfl_sync(FULLMASK, mine.y, src),
-                                              __shfl_sync(FULLMASK, mine.z, src), __shfl_sync(FULLMASK, mine.w, src));
-                const float rm = __shfl_sync(FULLMASK, rm_mine, src);
-                const float ga = box_area(gb);
-                const int t = t0 + src;
+                const float4 gb = gt[g0 + t];  // warp-uniform address: one broadcast load
+                const float rm = rule.allow_lq ? rowmax[g0 + t] : -1.0f;
+                match_one<A>(gb, rm, t, ab, aa, best, bidx, hits);
+            }
+        } else {  // more than 32 boxes: cull against the tile's bounding box on the fly (rare: the box is rebuilt here)
+            TileBox bb{INFINITY, INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    // pairwise_iou(gt, anchors): boxes1 = gt, boxes2 = anchors (rpn.py:167)
-                    const float v = valid ? pair_iou(gb, ga, ab[a], aa[a]) : 0.0f;
-                    if (v > best[a]) {
-                        best[a] = v;
-                        bidx[a] = t;
-                    }
-                    hit[a] |= (v == rm);  // matcher.py:110-120; culled pairs have v = 0 and only match rm = 0 (promote_all)
+            for (int a = 0; a < A; ++a)
+                if (valid) {  // fminf / fmaxf drop NaN coordinates: a NaN anchor intersects nothing
+                    bb.x1 = fminf(bb.x1, ab[a].x); bb.y1 = fminf(bb.y1, ab[a].y);
+                    bb.x2 = fmaxf(bb.x2, ab[a].z); bb.y2 = fmaxf(bb.y2, ab[a].w);
+                }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                bb.x1 = fminf(bb.x1, __shfl_xor_sync(FULLMASK, bb.x1, o2)); bb.y1 = fminf(bb.y1, __shfl_xor_sync(FULLMASK, bb.y1, o2));
+                bb.x2 = fmaxf(bb.x2, __shfl_xor_sync(FULLMASK, bb.x2, o2)); bb.y2 = fmaxf(bb.y2, __shfl_xor_sync(FULLMASK, bb.y2, o2));
+            }
+            const int G = gt_off[img + 1] - g0;
+            for (int t0 = 0; t0 < G; t0 += 32) {
+                float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+                float rm_mine = -1.0f;
+                bool over = false;
+                if (t0 + lane < G) {
+                    mine = gt[g0 + t0 + lane];
+                    over = !tile_culls(bb, mine);
+                    if (rule.allow_lq) rm_mine = rowmax[g0 + t0 + lane];
+                }
+                unsigned td = __ballot_sync(FULLMASK, over);
+                while (td) {
+                    const int src = __ffs(td) - 1;
+                    td &= td - 1;
+                    const float4 gb = make_float4(__shfl_sync(FULLMASK, mine.x, src), __shfl_sync(FULLMASK, mine.y, src),
+                                                  __shfl_sync(FULLMASK, mine.z, src), __shfl_sync(FULLMASK, mine.w, src));
+                    match_one<A>(gb, __shfl_sync(FULLMASK, rm_mine, src), t0 + src, ab, aa, best, bidx, hits);
                 }
             }
         }
-        int8_t lab[A];
-        int npos = 0, nign = 0;
+        if (promote_all) hits = 0xffffffffu;
+        if (!rule.allow_lq) hits = 0u;
+        int lab[A];
+        int my_pos = 0, my_ign = 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
-            lab[a] = (G == 0) ? rule.lab[0]  // matcher.py:67-77: no gt -> match 0, label labels[0]
-                              : ((rule.allow_lq && (hit[a] || promote_all)) ? (int8_t)1 : bucket_label(rule, best[a]));
-            npos += valid && lab[a] != 0 && lab[a] != -1;
-            nign += valid && lab[a] == -1;
+            int lb;
+            if (rule.nthr <= 2) {
+                lb = lab_none;
+                if (best[a] >= thr0) lb = lab1;
+                if (best[a] >= thr1) lb = lab2;
+            } else {
+                lb = bucket_label(rule, best[a]);
+            }
+            if ((hits >> a) & 1u) lb = 1;
+            lab[a] = lb;
+            my_pos += valid && lb != 0 && lb != -1;
+            my_ign += valid && lb == -1;
         }
+        const int tot_pos = stats ? __reduce_add_sync(FULLMASK, my_pos) : 0;
+        const int tot_ign = stats ? __reduce_add_sync(FULLMASK, my_ign) : 0;
         if (DENSE && valid) {
-            const int64_t o = (int64_t)img * r + row0;
 #pragma unroll
             for (int a = 0; a < A; ++a) {
                 matched[o + a] = bidx[a];
-                labels[o + a] = lab[a];
+                labels[o + a] = (int8_t)lab[a];
                 if (matched_iou) matched_iou[o + a] = best[a];
             }
         }
         if (stats) {
             // warp-aggregated: one atomic per warp and image for each counter that is non-zero (both are rare)
-            const unsigned pm = __ballot_sync(FULLMASK, npos > 0);
-            const int tot_ign = warp_sum(nign);
-            if (pm) {
-                int incl = npos;  // inclusive scan of the per-lane positive counts
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int up = __shfl_up_sync(FULLMASK, incl, o);
-                    if (lane >= o) incl += up;
-                }
-                const int total = __shfl_sync(FULLMASK, incl, 31);
+            if (tot_pos) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&stats[img * 4 + 0], total);
-                base = __shfl_sync(FULLMASK, base, 0) + incl - npos;
+                if (lane == 0) base = atomicAdd(&stats[img * 4 + 0], tot_pos);
                 if (pos_list) {
+                    // list slot: positives of lower lanes first, then this lane's in anchor order
+                    int before = 0;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        const bool is_pos = valid && lab[a] != 0 && lab[a] != -1;
+                        before += __popc(__ballot_sync(FULLMASK, is_pos) & ((1u << lane) - 1u));
+                    }
+                    base = __shfl_sync(FULLMASK, base, 0) + before;
 #pragma unroll
                     for (int a = 0; a < A; ++a)
                         if (valid && lab[a] != 0 && lab[a] != -1) {
@@ -447,9 +568,16 @@ using namespace det;
 
 extern "C" {
 
-int64_t det_match_grid_workspace_bytes(int n, int64_t sum_g) {
-    (void)n;
-    return ((sum_g > 0 ? sum_g : 1) * 4 + 255) / 256 * 256;  // row maxima, fp32
+static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+// workspace: row maxima (sum_g fp32) | per-image flags (n int32) | tile masks (n x tiles uint32)
+int64_t det_match_grid_workspace_bytes(int n, int64_t sum_g, const det_anchor_level_t* levels_host, int num_levels) {
+    int64_t tiles = 0;
+    for (int l = 0; levels_host && l < num_levels; ++l)
+        tiles += (int64_t)((levels_host[l].w + kTileW - 1) / kTileW) * ((levels_host[l].h + kTileH - 1) / kTileH);
+    if (tiles < 1) tiles = 1;
+    return align256((sum_g > 0 ? sum_g : 1) * 4) + align256((int64_t)(n > 0 ? n : 1) * 4) +
+           align256((int64_t)(n > 0 ? n : 1) * tiles * 4);
 }
 
 int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors, int64_t r,
@@ -462,6 +590,7 @@ int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int6
     DET_CHECK_ARG(gt_offsets && anchors && matched_idx && labels, "null pointer");
     DET_CHECK_ARG(sum_g == 0 || gt_boxes, "null gt_boxes");
     DET_CHECK_ARG(n <= 65535, "n > 65535");
+    DET_CHECK_ARG(r < (1ll << 27) && sum_g < (1ll << 31), "r must be below 2^27");
     DET_CHECK_ARG(!pos_list || (stats && list_cap >= 1 && r < (1 << 24)), "pos_list needs stats, list_cap >= 1, r < 2^24");
     if (!aligned16(anchors) || (gt_boxes && !aligned16(gt_boxes))) {
         set_error("gt_boxes/anchors must be 16-byte aligned");
@@ -477,19 +606,27 @@ int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int6
         set_error("det_match_grid: anchors per position must be 1, 3 or 9 (use det_match_anchors otherwise)");
         return DET_ERR_UNSUPPORTED;
     }
-    if (allow_low_quality && sum_g > 0 && (!workspace || workspace_bytes < (int64_t)sizeof(float) * sum_g)) {
-        set_error("workspace too small: need %lld bytes", (long long)det_match_grid_workspace_bytes(n, sum_g));
+    const int64_t off_flags = align256((sum_g > 0 ? sum_g : 1) * 4);
+    const int64_t off_mask = off_flags + align256((int64_t)n * 4);
+    const int64_t need = off_mask + align256((int64_t)n * lay.tiles_total * 4);
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %lld bytes", (long long)need);
         return DET_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    float* rowmax = static_cast<float*>(workspace);
+    char* ws = static_cast<char*>(workspace);
+    float* rowmax = reinterpret_cast<float*>(ws);
+    int32_t* flags = reinterpret_cast<int32_t*>(ws + off_flags);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(ws + off_mask);
+    cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(need - off_flags), st);  // flags + masks in one sweep
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     auto g4 = reinterpret_cast<const float4*>(gt_boxes);
     auto a4 = reinterpret_cast<const float4*>(anchors);
     const int stats_words = stats ? n * 4 : 0;
-    const int64_t k1_threads = (allow_low_quality ? sum_g * 32 : 0) > stats_words ? sum_g * 32 : stats_words;
+    const int64_t k1_threads = sum_g * 32 > stats_words ? sum_g * 32 : stats_words;
     if (k1_threads > 0) {
         match_rowmax_kernel<<<(unsigned)((k1_threads + 255) / 256), 256, 0, st>>>(
-            g4, allow_low_quality ? sum_g : 0, a4, lay, rowmax, stats, stats_words);
+            g4, gt_offsets, n, sum_g, a4, lay, allow_low_quality ? 1 : 0, rowmax, flags, mask, stats, stats_words);
         DET_LAUNCH_OK("match_rowmax_kernel");
     }
     // images per CTA: amortise the anchor loads and the tile box while keeping >= 8 CTAs per SM in flight
@@ -499,8 +636,8 @@ int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int6
     dim3 grid((unsigned)bx, (unsigned)((n + imgs - 1) / imgs));
 #define DET_LAUNCH_GRID(AA)                                                                                              \
     match_grid_kernel<AA, true><<<grid, kGridWarps * 32, 0, st>>>(g4, gt_offsets, a4, n, imgs, r, lay, rule, rowmax,      \
-                                                                  matched_idx, labels, matched_iou, stats, pos_list,     \
-                                                                  list_cap)
+                                                                  flags, mask, matched_idx, labels, matched_iou, stats,  \
+                                                                  pos_list, list_cap)
     if (a == 1) DET_LAUNCH_GRID(1);
     else if (a == 3) DET_LAUNCH_GRID(3);
     else DET_LAUNCH_GRID(9);

@@ -57,7 +57,7 @@ PROTOTYPES = {
     "det_roi_align_levels_backward": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "det_match_workspace_bytes": (c_l, [c_i, c_l, c_l]),
     "det_match_anchors": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
-    "det_match_grid_workspace_bytes": (c_l, [c_i, c_l]),
+    "det_match_grid_workspace_bytes": (c_l, [c_i, c_l, c_p, c_i]),
     "det_match_grid": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p,
                              c_i, c_p, c_l, c_p]),
     "det_subsample_labels_grid": (c_i, [c_p, c_i, c_l, c_i, c_d, c_u64, c_p, c_p, c_i, c_p, c_p, c_i, c_p]),

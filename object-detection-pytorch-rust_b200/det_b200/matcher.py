@@ -95,7 +95,7 @@ class Matcher:
                 for i, (h, w, stride) in enumerate(levels):
                     lv[i].h, lv[i].w, lv[i].stride, lv[i].reserved, lv[i].first_row = int(h), int(w), int(stride), 0, row
                     row += int(h) * int(w) * a
-                wsb = N.fn("det_match_grid_workspace_bytes")(n, sum_g)
+                wsb = N.fn("det_match_grid_workspace_bytes")(n, sum_g, ctypes.cast(lv, ctypes.c_void_p), len(levels))
                 ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
                 if with_stats and r < (1 << 24):
                     stats = MatchStats(torch.empty((n, 4), dtype=torch.int32, device=dev),

@@ -32,6 +32,7 @@ print(f"total warp-instructions {tot_i}, samples {tot_s}")
 print("-- by instructions")
 for f, l, s, i, sm in sorted(agg, key=lambda a: -a[3])[:top]:
     print(f"{100 * i / tot_i:5.1f}% inst {100 * sm / tot_s:5.1f}% samp  {f}:{l}  {s}")
-print("-- by stall samples")
-for f, l, s, i, sm in sorted(agg, key=lambda a: -a[4])[:top]:
-    print(f"{100 * sm / tot_s:5.1f}% samp {100 * i / tot_i:5.1f}% inst  {f}:{l}  {s}")
+if len(sys.argv) > 3:
+    print("-- by stall samples")
+    for f, l, s, i, sm in sorted(agg, key=lambda a: -a[4])[:top]:
+        print(f"{100 * sm / tot_s:5.1f}% samp {100 * i / tot_i:5.1f}% inst  {f}:{l}  {s}")
