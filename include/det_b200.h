@@ -274,13 +274,32 @@ DET_API int det_rpn_loss(const float* logits, const float* deltas, const int8_t*
                  float grad_scale_cls, float grad_scale_loc, const float* upstream, float* accumulators, float* sums_out,
                  float* grad_logits, float* grad_deltas, void* stream);
 
+/* Sample-list-only ("lazy") assignment for GRID anchors: label_and_sample_anchors (rpn.py:132-185) reduced to what the
+ * losses read -- per image the <= num_samples sampled anchors (anchor row | label << 24), the matched gt index of each
+ * and their number -- without computing, writing or reading anything for the other ~R anchors.  Positives are found from
+ * the gt side (closed-form windows where IoU >= the lowest positive threshold, or IoU == the row maximum, can occur),
+ * negatives by the sampler's permutation walk, which labels only the anchors it visits; every label is the same fp32
+ * arithmetic as det_match_grid, so the lists equal det_match_grid + det_subsample_labels_grid's as sets whenever that
+ * sampler walks too (dense, thinned negatives -- any realistic image).  Images whose positives are dense (a gt with row
+ * maximum 0 promotes every anchor, matcher.py:110-113) are labelled in full into scratch_labels (n, r) int8 (device
+ * scratch, otherwise untouched).  labels_host[0] must be 0 or -1.  samples / sample_gt (n, sample_cap) int32,
+ * sample_count (n) int32.  Feed them to det_rpn_loss_sampled (matched_idx = NULL). */
+DET_API int64_t det_assign_sampled_workspace_bytes(int n, int64_t sum_g, int list_cap);
+DET_API int det_assign_sampled(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors,
+                       int64_t r, const det_anchor_level_t* levels_host, int num_levels, int a,
+                       const float* thresholds_host, const int32_t* labels_host, int num_thresholds,
+                       int allow_low_quality, int num_samples, double positive_fraction, uint64_t seed,
+                       int8_t* scratch_labels, int32_t* samples, int32_t* sample_gt, int32_t* sample_count,
+                       int sample_cap, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* The same loss on the SAMPLED anchors only (the labels of everything else are -1 and contribute nothing, rpn.py:222-236),
  * reading the head where the convolutions left it and writing the gradients in the same layout -- O(samples) traffic
  * instead of O(r), no layout change (rpn.py:270-284), no (n,r) label sweep.
  *   layout: num_levels >= 1: levels_host[l] = per-level NCHW planes objectness (n,a,h,w), deltas (n,a*4,h,w) (channel =
  *   a*4 + component, rpn.py:278-280) and their gradient planes (all NULL to skip backward); the *_flat pointers are
  *   ignored.  num_levels == 0: logits_flat (n,r), deltas_flat (n,r,4), grad_*_flat or NULL.
- *   samples / sample_count / sample_cap: from det_subsample_labels_grid.  matched_idx (n,r) from det_match_grid.
+ *   samples / sample_count / sample_cap: from det_subsample_labels_grid, with matched_idx (n,r) from det_match_grid and
+ *   sample_gt = NULL -- or from det_assign_sampled, with its sample_gt (n, sample_cap) and matched_idx = NULL.
  *   Gradient buffers are NOT swept: zero them once (cudaMemset) -- or keep them persistent and pass the PREVIOUS step's
  *   sample list as clear_samples / clear_count (NULL, NULL otherwise): those entries are reset to zero first.
  *   accumulators: 8 floats of device scratch, zero before the first call (the kernel re-arms them).
@@ -298,7 +317,8 @@ DET_API int det_rpn_loss_sampled(const det_head_level_t* levels_host, int num_le
                          const float* deltas_flat, float* grad_logits_flat, float* grad_deltas_flat,
                          const int32_t* samples, const int32_t* sample_count, int sample_cap,
                          const int32_t* clear_samples, const int32_t* clear_count, const int64_t* matched_idx,
-                         const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r,
+                         const int32_t* sample_gt, const float* gt_boxes, const int32_t* gt_offsets, const float* anchors,
+                         int n, int64_t r,
                          float wx, float wy, float ww, float wh, float scale_clamp, int loss_type,
                          float smooth_l1_beta, float scale_cls, float scale_loc, const float* upstream,
                          float* accumulators, float* sums_out, void* stream);

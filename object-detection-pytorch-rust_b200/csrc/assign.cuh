@@ -176,6 +176,37 @@ __device__ __forceinline__ float giou_fwd_bwd(const float4 p, const float4 a, co
     return loss;
 }
 
+// ---- one anchor against all gt boxes of its image (the sample-list-only assignment of assign_grid.cu and its sampler)
+struct Verdict {
+    float best;
+    int argmax;   // first gt attaining the column maximum (torch.max(dim=0))
+    int first_q;  // first gt that makes the anchor a candidate (IoU >= tau or IoU == its row maximum); -1: none
+    bool hit;     // low-quality promotion (matcher.py:110-120)
+};
+
+__device__ __forceinline__ Verdict anchor_verdict(const float4 ab, const float4* __restrict__ gt, const float* __restrict__ rowmax,
+                                                  int g0, int G, float tau, bool allow_lq) {
+    Verdict v{0.0f, 0, -1, false};
+    const float aa = box_area(ab);
+    for (int t = 0; t < G; ++t) {
+        const float4 gb = gt[g0 + t];
+        const float q = pair_iou(gb, box_area(gb), ab, aa);
+        if (q > v.best) {
+            v.best = q;
+            v.argmax = t;
+        }
+        const bool lq = allow_lq && q == rowmax[g0 + t];
+        v.hit |= lq;
+        if (v.first_q < 0 && (q >= tau || lq)) v.first_q = t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int verdict_label(const MatchRule& rule, const Verdict& v, int G) {
+    if (G == 0) return rule.lab[0];
+    return v.hit ? 1 : (int)bucket_label(rule, v.best);
+}
+
 #endif  // __CUDACC__
 
 static inline int fill_rule(MatchRule& rule, const float* thresholds_host, const int32_t* labels_host, int num_thresholds,

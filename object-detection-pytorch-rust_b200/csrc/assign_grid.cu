@@ -109,7 +109,9 @@ match_rowmax_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ g
     // ---- (1) tile marks
     const int img = gt_image(gt_off, n, (int)t);
     const int tl = (int)t - gt_off[img];
-    if (tl >= 32) {
+    if (!mask) {
+        // sample-list-only assignment (assign_candidates_kernel follows): no tile kernel, no masks
+    } else if (tl >= 32) {
         if (lane == 0 && tl == 32) atomicOr(&flags[img], kFlagManyGt);
     } else {
         for (int l = 0; l < lay.nlev; ++l) {
@@ -170,6 +172,111 @@ match_rowmax_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ g
     if (lane == 0) {
         rowmax[t] = best;
         if (best == 0.0f) atomicOr(&flags[img], kFlagPromoteAll);
+    }
+}
+
+// ---- sample-list-only assignment ("lazy"): the training step needs the <= num_samples sampled anchors of an image, not
+// the labels of all R.  Positives are found from the gt side -- an anchor is positive only if its IoU with SOME gt box g
+// reaches the lowest threshold of a positive bucket, or equals g's row maximum -- on closed-form windows around g;
+// negatives are drawn by the sampler, which labels the few hundred anchors its permutation walk visits on the fly.
+// Every label comes from anchor_verdict(), the same arithmetic as match_grid_kernel.
+// positions whose overlap with the gt along one axis can be at least ov_min (centre offset |d| <= (a_len + g_len)/2 - ov_min)
+__device__ __forceinline__ void overlap_window(float g_lo, float g_hi, float a_lo, float a_hi, float ov_min, float s, int w,
+                                               int& lo, int& hi) {
+    const float gc = 0.5f * (g_lo + g_hi), ac = 0.5f * (a_lo + a_hi);
+    const float half = 0.5f * ((g_hi - g_lo) + (a_hi - a_lo)) - ov_min;
+    if (!(half >= 0.0f)) {
+        lo = 0;
+        hi = -1;
+        return;
+    }
+    const float f_lo = floorf((gc - ac - half) / s) - 2.0f, f_hi = ceilf((gc - ac + half) / s) + 2.0f;
+    lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)w);
+    hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), -1.0f);
+}
+
+// one warp per gt box (row maxima are final: match_rowmax_kernel ran before).  Appends the image's positives
+// (anchor row | label << 24, matched gt) to pos_list / pos_gt; stats[img*4+0] counts them.  An anchor that several boxes
+// nominate is emitted by the first of them only (Verdict::first_q).
+__global__ void __launch_bounds__(256)
+assign_candidates_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, int n, int64_t sum_g,
+                         const float4* __restrict__ anchors, GridLayoutDev lay, MatchRule rule, float tau,
+                         const float* __restrict__ rowmax, const int32_t* __restrict__ flags, int32_t* __restrict__ stats,
+                         int32_t* __restrict__ pos_list, int32_t* __restrict__ pos_gt, int list_cap) {
+    const unsigned FULLMASK = 0xffffffffu;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= sum_g) return;
+    const int lane = threadIdx.x & 31;
+    const int img = gt_image(gt_off, n, (int)t);
+    if (rule.allow_lq && (flags[img] & kFlagPromoteAll)) return;  // every anchor is positive: the sampler's dense path
+    const int g0 = gt_off[img], G = gt_off[img + 1] - g0, tl = (int)t - g0;
+    const float4 gb = gt[t];
+    const float ga = box_area(gb);
+    const float rm = rule.allow_lq ? rowmax[t] : -1.0f;
+    const bool finite = isfinite(gb.x) && isfinite(gb.y) && isfinite(gb.z) && isfinite(gb.w) && ga > 0.0f;
+    const int A = lay.a, P = lay.nlev * A;
+    for (int p = 0; p < P; ++p) {
+        const GridLevelDev L = lay.lv[p / A];
+        const int a = p % A;
+        const float4 a0 = anchors[L.first_row + a];
+        const float aa = box_area(a0);
+        int x_lo = 0, x_hi = L.w - 1, y_lo = 0, y_hi = L.h - 1;
+        if (finite && aa > 0.0f && isfinite(aa) && a0.z > a0.x && a0.w > a0.y) {
+            const float bound = fminf(ga, aa) / fmaxf(ga, aa) * 1.0001f;  // IoU <= min(area) / max(area)
+            const bool by_tau = bound >= tau, by_rm = rule.allow_lq && bound >= rm;
+            if (!by_tau && !by_rm) continue;
+            // IoU >= tau needs inter >= tau * max(area), hence an x overlap of at least that over the largest possible y
+            // overlap min(a_h, g_h) (and vice versa); IoU == row max lies on the plateau windows (match_rowmax_kernel)
+            const float need = tau * fmaxf(ga, aa) * 0.9999f;
+            int xa = 0, xb = -1, ya = 0, yb = -1, xc = 0, xd = -1, yc = 0, yd = -1;
+            if (by_tau) {
+                overlap_window(gb.x, gb.z, a0.x, a0.z, need / fminf(a0.w - a0.y, gb.w - gb.y), (float)L.stride, L.w, xa, xb);
+                overlap_window(gb.y, gb.w, a0.y, a0.w, need / fminf(a0.z - a0.x, gb.z - gb.x), (float)L.stride, L.h, ya, yb);
+            }
+            if (by_rm) {
+                plateau_window(gb.x, gb.z, a0.x, a0.z, (float)L.stride, L.w, xc, xd);
+                plateau_window(gb.y, gb.w, a0.y, a0.w, (float)L.stride, L.h, yc, yd);
+            }
+            const bool e1 = xa > xb || ya > yb, e2 = xc > xd || yc > yd;
+            if (e1 && e2) continue;
+            x_lo = e1 ? xc : (e2 ? xa : min(xa, xc)); x_hi = e1 ? xd : (e2 ? xb : max(xb, xd));
+            y_lo = e1 ? yc : (e2 ? ya : min(ya, yc)); y_hi = e1 ? yd : (e2 ? yb : max(yb, yd));
+        }
+        const float4* __restrict__ lvl = anchors + L.first_row + a;
+        const int lx = lane & 7, ly = lane >> 3;
+        // warp-uniform trip counts (the verdict loop below shuffles nothing, but the list append is warp-aggregated)
+        for (int yy = y_lo; yy <= y_hi; yy += 4) {
+            for (int xx = x_lo; xx <= x_hi; xx += 8) {
+                const int y = yy + ly, x = xx + lx;
+                const bool in = y <= y_hi && x <= x_hi;
+                bool emit = false;
+                int packed = 0, mgt = 0;
+                if (in) {
+                    const int row = (y * L.w + x) * A;
+                    const float4 ab = lvl[row];
+                    const float v = pair_iou(gb, ga, ab, box_area(ab));
+                    if (v >= tau || (rule.allow_lq && v == rm)) {
+                        const Verdict vd = anchor_verdict(ab, gt, rowmax, g0, G, tau, rule.allow_lq != 0);
+                        const int lb = verdict_label(rule, vd, G);
+                        if (vd.first_q == tl && lb != 0 && lb != -1) {
+                            emit = true;
+                            packed = (int)(L.first_row + a + row) | ((int)(uint8_t)lb << 24);
+                            mgt = vd.argmax;
+                        }
+                    }
+                }
+                const unsigned em = __ballot_sync(FULLMASK, emit);
+                if (em) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&stats[img * 4 + 0], __popc(em));
+                    base = __shfl_sync(FULLMASK, base, 0) + __popc(em & ((1u << lane) - 1u));
+                    if (emit && base < list_cap) {
+                        pos_list[(int64_t)img * list_cap + base] = packed;
+                        pos_gt[(int64_t)img * list_cap + base] = mgt;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -429,7 +536,7 @@ __global__ void __launch_bounds__(kSampledThreads)
 rpn_loss_sampled_kernel(HeadLayoutDev hl, const int32_t* __restrict__ samples, const int32_t* __restrict__ sample_count,
                         int sample_cap, const int32_t* __restrict__ clear_samples,
                         const int32_t* __restrict__ clear_count, const int64_t* __restrict__ matched,
-                        const float4* __restrict__ gt, const int32_t* __restrict__ gt_off,
+                        const int32_t* __restrict__ sample_gt, const float4* __restrict__ gt, const int32_t* __restrict__ gt_off,
                         const float4* __restrict__ anchors, int64_t r, CodecW wt, float scale_clamp, float beta,
                         float scale_cls, float scale_loc, const float* __restrict__ upstream, float* __restrict__ acc,
                         int32_t* __restrict__ ticket, float* __restrict__ sums_out, int write_grads) {
@@ -477,7 +584,8 @@ rpn_loss_sampled_kernel(HeadLayoutDev hl, const int32_t* __restrict__ samples, c
         nneg += lab == 0;
         if (write_grads) L.g_obj[ad.obj] = (1.f / (1.f + expf(-x)) - yv) * gs_cls;
         if (lab == 1) {
-            const float4 g = gt[gt_off[img] + matched[(int64_t)img * r + j]];
+            const int64_t mg = sample_gt ? (int64_t)sample_gt[(int64_t)img * sample_cap + k] : matched[(int64_t)img * r + j];
+            const float4 g = gt[gt_off[img] + mg];
             float4 p;
             if (ad.dlt_step == 1) {
                 p = *reinterpret_cast<const float4*>(L.dlt + ad.dlt);
@@ -566,6 +674,13 @@ static int fill_layout(GridLayoutDev& lay, const det_anchor_level_t* levels_host
 
 using namespace det;
 
+// assign_loss.cu (the samplers live next to subsample_image)
+int launch_subsample_lazy(const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r,
+                          const MatchRule& rule, float tau, const float* rowmax, const int32_t* flags, const int32_t* stats,
+                          const int32_t* pos_list, const int32_t* pos_gt, int list_cap, int num_samples,
+                          double positive_fraction, uint64_t seed, int8_t* scratch, int32_t* samples, int32_t* sample_gt,
+                          int32_t* sample_count, int sample_cap, cudaStream_t st);
+
 extern "C" {
 
 static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
@@ -646,11 +761,83 @@ int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int6
     return DET_OK;
 }
 
+int64_t det_assign_sampled_workspace_bytes(int n, int64_t sum_g, int list_cap) {
+    const int64_t nn = n > 0 ? n : 1, cap = list_cap > 0 ? list_cap : 1;
+    return align256((sum_g > 0 ? sum_g : 1) * 4) + align256(nn * 4) + align256(nn * 16) + 2 * align256(nn * cap * 4);
+}
+
+int det_assign_sampled(const float* gt_boxes, const int32_t* gt_offsets, int n, int64_t sum_g, const float* anchors,
+                       int64_t r, const det_anchor_level_t* levels_host, int num_levels, int a,
+                       const float* thresholds_host, const int32_t* labels_host, int num_thresholds, int allow_low_quality,
+                       int num_samples, double positive_fraction, uint64_t seed, int8_t* scratch_labels, int32_t* samples,
+                       int32_t* sample_gt, int32_t* sample_count, int sample_cap, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
+    DET_CHECK_ARG(n >= 0 && r >= 0 && sum_g >= 0 && num_samples >= 0 && sample_cap >= 1, "bad size");
+    DET_CHECK_ARG(positive_fraction >= 0.0 && positive_fraction <= 1.0, "positive_fraction outside [0, 1]");
+    if (n == 0) return DET_OK;
+    DET_CHECK_ARG(gt_offsets && anchors && scratch_labels && samples && sample_gt && sample_count, "null pointer");
+    DET_CHECK_ARG(sum_g == 0 || gt_boxes, "null gt_boxes");
+    DET_CHECK_ARG(r >= 1 && r < (1 << 24) && sum_g < (1ll << 31) && n <= 65535, "1 <= r < 2^24, n <= 65535");
+    if (!aligned16(anchors) || (gt_boxes && !aligned16(gt_boxes))) {
+        set_error("gt_boxes/anchors must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    MatchRule rule;
+    int rc = fill_rule(rule, thresholds_host, labels_host, num_thresholds, allow_low_quality);
+    if (rc != DET_OK) return rc;
+    if (rule.lab[0] != 0 && rule.lab[0] != -1) {
+        set_error("det_assign_sampled: the lowest bucket must not be positive (labels[0] in {0, -1})");
+        return DET_ERR_UNSUPPORTED;
+    }
+    // the lowest IoU that can make an anchor positive through the threshold rule
+    float tau = INFINITY;
+    for (int i = num_thresholds; i >= 1; --i)
+        if (rule.lab[i] != 0 && rule.lab[i] != -1) tau = rule.thr[i - 1];
+    GridLayoutDev lay;
+    rc = fill_layout(lay, levels_host, num_levels, a, r);
+    if (rc != DET_OK) return rc;
+    const int list_cap = 1024;
+    const int64_t off_flags = align256((sum_g > 0 ? sum_g : 1) * 4);
+    const int64_t off_stats = off_flags + align256((int64_t)n * 4);
+    const int64_t off_list = off_stats + align256((int64_t)n * 16);
+    const int64_t off_gt = off_list + align256((int64_t)n * list_cap * 4);
+    const int64_t need = off_gt + align256((int64_t)n * list_cap * 4);
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %lld bytes", (long long)need);
+        return DET_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    char* ws = static_cast<char*>(workspace);
+    float* rowmax = reinterpret_cast<float*>(ws);
+    int32_t* flags = reinterpret_cast<int32_t*>(ws + off_flags);
+    int32_t* stats = reinterpret_cast<int32_t*>(ws + off_stats);
+    int32_t* pos_list = reinterpret_cast<int32_t*>(ws + off_list);
+    int32_t* pos_gt = reinterpret_cast<int32_t*>(ws + off_gt);
+    cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(off_list - off_flags), st);  // flags + stats
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    auto g4 = reinterpret_cast<const float4*>(gt_boxes);
+    auto a4 = reinterpret_cast<const float4*>(anchors);
+    if (sum_g > 0) {
+        const unsigned blocks = (unsigned)((sum_g * 32 + 255) / 256);
+        if (allow_low_quality) {
+            match_rowmax_kernel<<<blocks, 256, 0, st>>>(g4, gt_offsets, n, sum_g, a4, lay, 1, rowmax, flags, nullptr, nullptr, 0);
+            DET_LAUNCH_OK("match_rowmax_kernel");
+        }
+        assign_candidates_kernel<<<blocks, 256, 0, st>>>(g4, gt_offsets, n, sum_g, a4, lay, rule, tau, rowmax, flags, stats,
+                                                         pos_list, pos_gt, list_cap);
+        DET_LAUNCH_OK("assign_candidates_kernel");
+    }
+    return launch_subsample_lazy(gt_boxes, gt_offsets, anchors, n, r, rule, tau, rowmax, flags, stats, pos_list, pos_gt,
+                                 list_cap, num_samples, positive_fraction, seed, scratch_labels, samples, sample_gt,
+                                 sample_count, sample_cap, st);
+}
+
 int det_rpn_loss_sampled(const det_head_level_t* levels_host, int num_levels, int a, const float* logits_flat,
                          const float* deltas_flat, float* grad_logits_flat, float* grad_deltas_flat,
                          const int32_t* samples, const int32_t* sample_count, int sample_cap,
                          const int32_t* clear_samples, const int32_t* clear_count, const int64_t* matched_idx,
-                         const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r, float wx,
+                         const int32_t* sample_gt, const float* gt_boxes, const int32_t* gt_offsets, const float* anchors,
+                         int n, int64_t r, float wx,
                          float wy, float ww, float wh, float scale_clamp, int loss_type, float smooth_l1_beta,
                          float scale_cls, float scale_loc, const float* upstream, float* accumulators, float* sums_out,
                          void* stream) {
@@ -662,7 +849,7 @@ int det_rpn_loss_sampled(const det_head_level_t* levels_host, int num_levels, in
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
         return DET_OK;
     }
-    DET_CHECK_ARG(samples && sample_count && matched_idx && gt_offsets && anchors, "null pointer");
+    DET_CHECK_ARG(samples && sample_count && (matched_idx || sample_gt) && gt_offsets && anchors, "null pointer");
     DET_CHECK_ARG(r < (1 << 24), "r must be below 2^24 (sample entries pack the anchor row in 24 bits)");
     DET_CHECK_ARG((clear_samples == nullptr) == (clear_count == nullptr), "clear_samples and clear_count go together");
     if (!aligned16(anchors) || (gt_boxes && !aligned16(gt_boxes))) {
@@ -706,11 +893,11 @@ int det_rpn_loss_sampled(const det_head_level_t* levels_host, int num_levels, in
     int32_t* ticket = reinterpret_cast<int32_t*>(accumulators + 8);
     if (loss_type == 1)
         rpn_loss_sampled_kernel<true><<<n, kSampledThreads, 0, as_stream(stream)>>>(
-            hl, samples, sample_count, sample_cap, clear_samples, clear_count, matched_idx, g4, gt_offsets, a4, r, wt,
+            hl, samples, sample_count, sample_cap, clear_samples, clear_count, matched_idx, sample_gt, g4, gt_offsets, a4, r, wt,
             scale_clamp, smooth_l1_beta, scale_cls, scale_loc, upstream, accumulators, ticket, sums_out, write_grads);
     else
         rpn_loss_sampled_kernel<false><<<n, kSampledThreads, 0, as_stream(stream)>>>(
-            hl, samples, sample_count, sample_cap, clear_samples, clear_count, matched_idx, g4, gt_offsets, a4, r, wt,
+            hl, samples, sample_count, sample_cap, clear_samples, clear_count, matched_idx, sample_gt, g4, gt_offsets, a4, r, wt,
             scale_clamp, smooth_l1_beta, scale_cls, scale_loc, upstream, accumulators, ticket, sums_out, write_grads);
     DET_LAUNCH_OK("rpn_loss_sampled_kernel");
     return DET_OK;

@@ -644,6 +644,115 @@ subsample_stats_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, 
 }
 
 // ---- fused RPN loss forward + backward ---------------------------------------------------------------------------
+// The sampler of the sample-list-only assignment (assign_grid.cu): nothing dense exists for the image.  Positives come from
+// assign_candidates_kernel's list (ranked by their hash keys when there are too many, exactly like the other samplers);
+// negatives are found by the same permutation walk, each visited anchor labelled on the fly by anchor_verdict() -- the
+// walk accepts the first `want` anchors whose label is 0 and simply ends after a full cycle if the image has fewer, which
+// is min(#neg, S - #pos) without ever counting the negatives.  Output: the sample list (anchor row | label << 24), the
+// matched gt of every sample and the count.  Images whose positives are dense (a gt with row maximum 0 promotes every
+// anchor; list overflow) are labelled in full into `scratch` (n, r) int8 and go through subsample_image().
+__global__ void __launch_bounds__(kSampleThreads)
+subsample_lazy_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
+                      int64_t r, MatchRule rule, float tau, const float* __restrict__ rowmax,
+                      const int32_t* __restrict__ flags, const int32_t* __restrict__ stats,
+                      const int32_t* __restrict__ pos_list, const int32_t* __restrict__ pos_gt, int list_cap,
+                      int num_samples, int pos_cap, uint64_t seed, int8_t* __restrict__ scratch,
+                      int32_t* __restrict__ samples, int32_t* __restrict__ sample_gt, int32_t* __restrict__ sample_count,
+                      int sample_cap) {
+    __shared__ SampleSmem sm;
+    __shared__ int s_nout;
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
+    const bool lq = rule.allow_lq != 0;
+    const int npos = stats[img * 4 + 0];
+    const bool dense = (lq && (flags[img] & 1)) || npos > min(list_cap, kCandCap) || r >= (1 << 24);
+    if (tid == 0) s_nout = 0;
+    __syncthreads();
+    if (dense) {
+        int8_t* row = scratch + (int64_t)img * r;
+        for (int64_t j = tid; j < r; j += kSampleThreads) {
+            const Verdict v = anchor_verdict(anchors[j], gt, rowmax, g0, G, tau, lq);
+            row[j] = (int8_t)((lq && (flags[img] & 1) && G > 0) ? 1 : verdict_label(rule, v, G));
+        }
+        __syncthreads();
+        subsample_image(sm, scratch, img, r, num_samples, pos_cap, seed);
+        __syncthreads();
+        for (int64_t j = tid; j < r; j += kSampleThreads) {
+            const int8_t l = row[j];
+            if (l == -1) continue;
+            const int slot = atomicAdd(&s_nout, 1);
+            if (slot < sample_cap) {
+                samples[(int64_t)img * sample_cap + slot] = (int)j | ((int)(uint8_t)l << 24);
+                sample_gt[(int64_t)img * sample_cap + slot] =
+                    (l == 0) ? 0 : anchor_verdict(anchors[j], gt, rowmax, g0, G, tau, lq).argmax;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sample_count[img] = min(s_nout, sample_cap);
+        return;
+    }
+    const uint32_t img_seed = image_seed(seed, img);
+    int pbits = 1;
+    while ((1ll << pbits) < r) ++pbits;
+    const int want_pos = min(npos, pos_cap);
+    const int want_neg_max = num_samples - want_pos;  // min(#neg, .) falls out of the walk
+    // positives: the want_pos smallest keys of the list (keys are a bijection of the anchor index: no ties)
+    for (int t = tid; t < npos; t += kSampleThreads) {
+        const int packed = pos_list[(int64_t)img * list_cap + t];
+        sm.cidx[0][t] = packed;
+        sm.ckey[0][t] = sample_key(img_seed, (uint32_t)(packed & 0xffffff));
+    }
+    __syncthreads();
+    for (int t = tid; t < npos; t += kSampleThreads) {
+        bool keep = true;
+        if (want_pos < npos) {
+            const unsigned key = sm.ckey[0][t];
+            int rank = 0;
+            for (int q = 0; q < npos; ++q) rank += sm.ckey[0][q] < key;
+            keep = rank < want_pos;
+        }
+        if (keep) {
+            const int slot = atomicAdd(&s_nout, 1);
+            if (slot < sample_cap) {
+                samples[(int64_t)img * sample_cap + slot] = sm.cidx[0][t];
+                sample_gt[(int64_t)img * sample_cap + slot] = pos_gt[(int64_t)img * list_cap + t];
+            }
+        }
+    }
+    __syncthreads();
+    const int kept_pos = s_nout;
+    // negatives: walk_class() with the label evaluated on the fly (same permutation, same acceptance order)
+    const int want = min(want_neg_max, kCandCap);
+    int total = 0;
+    if (want > 0) {
+        const uint32_t s0 = mix32(img_seed + 0x51ED270Bu * 2u);
+        const int lane = tid & 31, wid = tid >> 5;
+        for (uint32_t k0 = 0; total < want && k0 < (1u << pbits); k0 += kSampleThreads) {
+            const uint32_t j = perm_bits(k0 + (uint32_t)tid, s0, pbits);
+            bool ok = false;
+            if ((int64_t)j < r)
+                ok = verdict_label(rule, anchor_verdict(anchors[j], gt, rowmax, g0, G, tau, lq), G) == 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) sm.walk_warp[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, round_total = 0;
+            for (int w = 0; w < kSampleThreads / 32; ++w) {
+                const int v = sm.walk_warp[w];
+                before += (w < wid) ? v : 0;
+                round_total += v;
+            }
+            const int slot = total + before + __popc(bal & ((1u << lane) - 1u));  // rank in walk order
+            if (ok && slot < want && kept_pos + slot < sample_cap) {
+                samples[(int64_t)img * sample_cap + kept_pos + slot] = (int)j;  // label 0
+                sample_gt[(int64_t)img * sample_cap + kept_pos + slot] = 0;
+            }
+            total += round_total;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) sample_count[img] = min(kept_pos + min(total, want), sample_cap);
+}
+
 constexpr int kLossThreads = 256;
 
 template <bool GIOU>
@@ -913,6 +1022,21 @@ yolo_loss_direct_kernel(const float* __restrict__ head, const int8_t* __restrict
 }  // namespace det
 
 using namespace det;
+
+// second half of det_assign_sampled (assign_grid.cu launches the gt-centric kernels and then calls this)
+int launch_subsample_lazy(const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int n, int64_t r,
+                          const MatchRule& rule, float tau, const float* rowmax, const int32_t* flags, const int32_t* stats,
+                          const int32_t* pos_list, const int32_t* pos_gt, int list_cap, int num_samples,
+                          double positive_fraction, uint64_t seed, int8_t* scratch, int32_t* samples, int32_t* sample_gt,
+                          int32_t* sample_count, int sample_cap, cudaStream_t st) {
+    const int pos_cap = (int)((double)num_samples * positive_fraction);
+    subsample_lazy_kernel<<<n, kSampleThreads, 0, st>>>(
+        reinterpret_cast<const float4*>(gt_boxes), gt_offsets, reinterpret_cast<const float4*>(anchors), r, rule, tau, rowmax,
+        flags, stats, pos_list, pos_gt, list_cap, num_samples, pos_cap, seed, scratch, samples, sample_gt, sample_count,
+        sample_cap);
+    DET_LAUNCH_OK("subsample_lazy_kernel");
+    return DET_OK;
+}
 
 extern "C" {
 

@@ -61,8 +61,11 @@ PROTOTYPES = {
     "det_match_grid": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p,
                              c_i, c_p, c_l, c_p]),
     "det_subsample_labels_grid": (c_i, [c_p, c_i, c_l, c_i, c_d, c_u64, c_p, c_p, c_i, c_p, c_p, c_i, c_p]),
-    "det_rpn_loss_sampled": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i,
-                                   c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p]),
+    "det_rpn_loss_sampled": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                   c_i, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p]),
+    "det_assign_sampled_workspace_bytes": (c_l, [c_i, c_l, c_i]),
+    "det_assign_sampled": (c_i, [c_p, c_p, c_i, c_l, c_p, c_l, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_d, c_u64, c_p, c_p,
+                                 c_p, c_p, c_i, c_p, c_l, c_p]),
     "det_match_quality": (c_i, [c_p, c_l, c_l, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "det_subsample_labels": (c_i, [c_p, c_i, c_l, c_i, c_d, c_u64, c_p]),
     "det_rpn_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f,

@@ -61,16 +61,21 @@ class Matcher:
         [, matched IoU (N,R)] [, MatchStats], and the packed gt table (sum_G,4) + int32 offsets (N+1) used by the loss
         kernel.  grid / with_stats: see match_packed."""
         N.require_cuda(anchors, *gt_boxes)
-        dev = anchors.device
         a = N.f32c(anchors)
-        n, r = len(gt_boxes), a.shape[0]
-        sizes = [int(g.shape[0]) for g in gt_boxes]
-        table = N.f32c(torch.cat([g.reshape(-1, 4) for g in gt_boxes], dim=0)) if n else a.new_zeros((0, 4))
+        table, offsets = self.pack_gt(gt_boxes, anchors.device)
+        return self.match_packed(table, offsets, len(gt_boxes), a, return_iou, grid, with_stats) + (table, offsets)
+
+    @staticmethod
+    def pack_gt(gt_boxes: Sequence[torch.Tensor], device):
+        """list of (G_i,4) tensors -> packed (sum_G,4) fp32 table + int32 offsets (N+1) on `device`."""
+        n = len(gt_boxes)
+        table = (N.f32c(torch.cat([g.reshape(-1, 4) for g in gt_boxes], dim=0)) if n
+                 else torch.zeros((0, 4), dtype=torch.float32, device=device))
         off_host = [0]
-        for s in sizes:
-            off_host.append(off_host[-1] + s)
-        offsets = torch.tensor(off_host, dtype=torch.int32).to(dev, non_blocking=True)
-        return self.match_packed(table, offsets, n, a, return_iou, grid, with_stats) + (table, offsets)
+        for g in gt_boxes:
+            off_host.append(off_host[-1] + int(g.shape[0]))
+        offsets = torch.tensor(off_host, dtype=torch.int32).to(device, non_blocking=True)
+        return table, offsets
 
     def match_packed(self, table: torch.Tensor, offsets: torch.Tensor, n: int, anchors: torch.Tensor,
                      return_iou: bool = False, grid=None, with_stats: bool = False):

@@ -24,11 +24,12 @@ class Assignment:
     """Result of the batched target assignment: labels (N,R) int8, matched (N,R) int64 indices into each image's own
     gt boxes, the packed gt table (sum_G,4) and its int32 offsets (N+1).  After a grid assignment with sampling it
     also carries the per-image sample lists (N,S) int32 (anchor row | label << 24) + counts (N) int32 that the sampled
-    loss (det_rpn_loss_sampled) works from."""
+    loss (det_rpn_loss_sampled) works from.  A sample-list-only assignment (assign_sampled) has labels = matched = None
+    and sample_gt (N,S) int32 = the matched gt index of every sample instead."""
 
-    def __init__(self, labels, matched, gt_table, gt_offsets, samples=None, sample_count=None):
+    def __init__(self, labels, matched, gt_table, gt_offsets, samples=None, sample_count=None, sample_gt=None):
         self.labels, self.matched, self.gt_table, self.gt_offsets = labels, matched, gt_table, gt_offsets
-        self.samples, self.sample_count = samples, sample_count
+        self.samples, self.sample_count, self.sample_gt = samples, sample_count, sample_gt
 
 
 class _FusedRPNLoss(torch.autograd.Function):
@@ -65,23 +66,23 @@ class _SampledRPNLoss(torch.autograd.Function):
     the kernel with the upstream gradients read on the device and scatters into zero-initialised NCHW gradients."""
 
     @staticmethod
-    def forward(ctx, owner, n_norm, nl, anchors, labels, matched, gt_table, gt_offsets, samples, sample_count, *heads):
+    def forward(ctx, owner, n_norm, nl, anchors, matched, sample_gt, gt_table, gt_offsets, samples, sample_count, *heads):
         obj = [h.contiguous() for h in heads[:nl]]
         dlt = [h.contiguous() for h in heads[nl:]]
-        asg = Assignment(labels, matched, gt_table, gt_offsets, samples, sample_count)
+        asg = Assignment(None, matched, gt_table, gt_offsets, samples, sample_count, sample_gt)
         sums = owner._run_sampled(anchors, obj, dlt, asg, n_norm, None, None)
         ctx.owner, ctx.n_norm, ctx.nl = owner, n_norm, nl
-        ctx.save_for_backward(anchors, labels, matched, gt_table, gt_offsets, samples, sample_count, *obj, *dlt)
+        ctx.save_for_backward(anchors, matched, sample_gt, gt_table, gt_offsets, samples, sample_count, *obj, *dlt)
         return sums
 
     @staticmethod
     def backward(ctx, grad_sums):
-        anchors, labels, matched, gt_table, gt_offsets, samples, sample_count = ctx.saved_tensors[:7]
+        anchors, matched, sample_gt, gt_table, gt_offsets, samples, sample_count = ctx.saved_tensors[:7]
         heads = ctx.saved_tensors[7:]
         obj, dlt = list(heads[:ctx.nl]), list(heads[ctx.nl:])
         up = grad_sums[:2].contiguous().float()
         g_obj, g_dlt = [torch.zeros_like(o) for o in obj], [torch.zeros_like(d) for d in dlt]
-        asg = Assignment(labels, matched, gt_table, gt_offsets, samples, sample_count)
+        asg = Assignment(None, matched, gt_table, gt_offsets, samples, sample_count, sample_gt)
         ctx.owner._run_sampled(anchors, obj, dlt, asg, ctx.n_norm, up, (g_obj, g_dlt))
         return (None,) * 10 + tuple(g_obj) + tuple(g_dlt)
 
@@ -204,6 +205,42 @@ class RegionProposalNetwork:
                 subsample_labels_(labels, self.batch_size_per_image, self.positive_fraction, seed)
         return Assignment(labels, matched, table, offsets, samples, counts)
 
+    def assign_sampled(self, anchors: torch.Tensor, gt_table: torch.Tensor, gt_offsets: torch.Tensor, n: int, grid,
+                       seed: Optional[int] = None) -> Assignment:
+        """label_and_sample_anchors reduced to what the losses read (det_assign_sampled): the sampled anchors of every
+        image, their labels and matched gt -- nothing is computed or written for the other anchors.  gt_table (sum_G,4)
+        + int32 gt_offsets (n+1) as in Matcher.match_packed; grid = AnchorGenerator.grid_layout(...)."""
+        N.require_cuda(anchors, gt_table, gt_offsets)
+        from .matcher import _rule_arrays, grid_supported
+        m = self.anchor_matcher
+        r, sum_g = anchors.shape[0], gt_table.shape[0]
+        assert grid is not None and grid_supported(grid, r) and m.labels[0] in (0, -1) and r < (1 << 24)
+        if seed is None:
+            self._sample_seed += 1
+            seed = self._sample_seed
+        dev = anchors.device
+        levels, a = grid
+        lv = (N.AnchorLevel * len(levels))()
+        row = 0
+        for i, (h, w, stride) in enumerate(levels):
+            lv[i].h, lv[i].w, lv[i].stride, lv[i].reserved, lv[i].first_row = int(h), int(w), int(stride), 0, row
+            row += int(h) * int(w) * a
+        cap = max(int(self.batch_size_per_image), 1)
+        thr, lab = _rule_arrays(m._inner, m.labels)
+        with torch.cuda.device(dev):
+            samples = torch.empty((n, cap), dtype=torch.int32, device=dev)
+            sample_gt = torch.empty((n, cap), dtype=torch.int32, device=dev)
+            counts = torch.empty((n,), dtype=torch.int32, device=dev)
+            scratch = torch.empty((n, r), dtype=torch.int8, device=dev)  # only written for images with dense positives
+            wsb = N.fn("det_assign_sampled_workspace_bytes")(n, sum_g, 1024)
+            ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+            N.call("det_assign_sampled", N.ptr(gt_table), N.ptr(gt_offsets), n, sum_g, N.ptr(anchors), r,
+                   ctypes.cast(lv, ctypes.c_void_p), len(levels), int(a), thr, lab, len(m._inner),
+                   int(m.allow_low_quality_matches), int(self.batch_size_per_image), float(self.positive_fraction),
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, N.ptr(scratch), N.ptr(samples), N.ptr(sample_gt), N.ptr(counts), cap,
+                   N.ptr(ws), wsb, N.stream())
+        return Assignment(None, None, gt_table, gt_offsets, samples, counts, sample_gt)
+
     @staticmethod
     def _grid_of(level_tensors) -> Optional[tuple]:
         """(levels, a) if every per-level anchor tensor carries AnchorGenerator's layout tag, else None."""
@@ -287,7 +324,7 @@ class RegionProposalNetwork:
                 ptrs = (None, None, None, None)
                 lv = ctypes.cast(lv, ctypes.c_void_p)
             N.call("det_rpn_loss_sampled", lv, nl, a, *ptrs, N.ptr(asg.samples), N.ptr(asg.sample_count),
-                   asg.samples.shape[1], N.ptr(cs), N.ptr(cc), N.ptr(asg.matched), N.ptr(asg.gt_table),
+                   asg.samples.shape[1], N.ptr(cs), N.ptr(cc), N.ptr(asg.matched), N.ptr(asg.sample_gt), N.ptr(asg.gt_table),
                    N.ptr(asg.gt_offsets), N.ptr(anchors), n, r, *w, self.box2box_transform.scale_clamp, loss_type,
                    float(self.smooth_l1_beta), s_cls, s_loc, N.ptr(upstream), N.ptr(N.accumulators(dev)), N.ptr(sums),
                    N.stream())
@@ -312,7 +349,7 @@ class RegionProposalNetwork:
             sums = self._run_sampled(at, obj, dlt, asg, n_norm, None, grad_buffers, clear_previous)
         else:
             nl = len(pred_objectness)
-            sums = _SampledRPNLoss.apply(self, n_norm, nl, at, asg.labels, asg.matched, asg.gt_table, asg.gt_offsets,
+            sums = _SampledRPNLoss.apply(self, n_norm, nl, at, asg.matched, asg.sample_gt, asg.gt_table, asg.gt_offsets,
                                          asg.samples, asg.sample_count, *pred_objectness, *pred_deltas)
         return {"cls_loss": sums[0], "loc_loss": sums[1], "num_pos_anchors": sums[2].detach(),
                 "num_neg_anchors": sums[3].detach(), "sums": sums}
@@ -403,8 +440,12 @@ class RegionProposalNetwork:
             assert gt_instances is not None, "RPN requires gt_instances in training!"
             at = anchors_cat
             grid = self.anchor_generator.grid_layout(feats_hw)
-            if grid is not None and all(o.dtype == torch.float32 for o in obj):
-                asg = self.assign(at, [x.gt_boxes for x in gt_instances], grid=grid)
+            from .matcher import grid_supported
+            if (grid is not None and grid_supported(grid, at.shape[0]) and self.anchor_matcher.labels[0] in (0, -1)
+                    and all(o.dtype == torch.float32 for o in obj)):
+                gts = [x.gt_boxes.tensor if isinstance(x.gt_boxes, Boxes) else x.gt_boxes for x in gt_instances]
+                table, offsets = self.anchor_matcher.pack_gt(gts, at.device)
+                asg = self.assign_sampled(at, table, offsets, len(gts), grid)
                 res = self.sampled_losses(at, list(obj), list(dlt), asg)
             else:  # levels with different anchor counts: generic matcher + dense loss on re-laid-out tensors
                 n = obj[0].shape[0]

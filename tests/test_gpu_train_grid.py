@@ -268,3 +268,80 @@ def test_forward_training_launches_match_the_oracle_losses(det, O):
     torch.testing.assert_close(losses["loc_loss"].detach().cpu(), want["loc_loss"].detach(), rtol=1e-5, atol=1e-7)
     for a, b in zip(o_g + d_g, o_c + d_c):
         torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-9)
+
+
+def _sample_sets(samples, counts, gt_idx=None):
+    out = []
+    for i in range(samples.shape[0]):
+        k = int(counts[i])
+        row = samples[i, :k].cpu()
+        order = (row & 0xffffff).argsort()
+        rec = [(row & 0xffffff)[order], (row >> 24).to(torch.int8)[order]]
+        if gt_idx is not None:
+            rec.append(gt_idx[i, :k].cpu()[order])
+        out.append(rec)
+    return out
+
+
+@pytest.mark.parametrize("num_samples,frac", [(256, 0.5), (64, 0.25)])
+def test_sample_list_only_assignment_equals_the_dense_one(det, O, num_samples, frac):
+    """det_assign_sampled (nothing dense is computed) picks exactly the anchors det_match_grid +
+    det_subsample_labels_grid pick, with the same labels and the same matched gt -- including images without gt, with a
+    gt off the image / of zero area (every anchor promoted: dense path), with > 32 gts and with hundreds of positives."""
+    g = gen(61)
+    rpn, hw, levels, at, grid = _pyramid(det, 448)
+    rpn.batch_size_per_image, rpn.positive_fraction = num_samples, frac
+    gts = _gts(12, g)
+    gts[0] = torch.zeros(0, 4)
+    gts[1] = torch.cat([gts[1], torch.tensor([[-500.0, -500.0, -400.0, -450.0]])])   # row maximum 0: everything positive
+    gts[2] = torch.cat([gts[2], torch.tensor([[50.0, 60.0, 50.0, 90.0]])])           # zero area
+    gts[3] = rand_boxes(70, 448.0, g)                                                # > 32 gts
+    gts[4] = rand_boxes(300, 448.0, g, 0.5)                                          # positives overflow the list
+    gts[5] = rand_boxes(3, 448.0, g, 0.02)                                           # tiny boxes: low-quality matches only
+    gts[6] = torch.cat([gts[6], gts[6][:2]])                                         # duplicated gts
+    dev_gts = [b.cuda() for b in gts]
+    for seed in (3, 4):
+        dense = rpn.assign(at, dev_gts, seed=seed, grid=grid)
+        table, off = rpn.anchor_matcher.pack_gt(dev_gts, at.device)
+        lazy = rpn.assign_sampled(at, table, off, len(gts), grid, seed=seed)
+        assert lazy.labels is None and lazy.matched is None
+        assert torch.equal(lazy.sample_count, dense.sample_count)
+        want = _sample_sets(dense.samples, dense.sample_count)
+        got = _sample_sets(lazy.samples, lazy.sample_count, lazy.sample_gt)
+        for i in range(len(gts)):
+            assert torch.equal(got[i][0], want[i][0]) and torch.equal(got[i][1], want[i][1]), i
+            rows = got[i][0].long()
+            pos = got[i][1] == 1
+            assert torch.equal(got[i][2][pos].long(), dense.matched[i].cpu()[rows][pos]), i
+            # and the dense labels agree with the lists
+            lab = dense.labels[i].cpu()
+            assert torch.equal(lab[rows], got[i][1]) and int((lab != -1).sum()) == rows.numel()
+
+
+def test_sample_list_only_assignment_feeds_the_same_losses(det):
+    g = gen(62)
+    n, img = 4, 224
+    rpn = det.RegionProposalNetwork(STRIDES, SIZES, RATIOS)
+    hw = [(img // s, img // s) for s in STRIDES]
+    at = torch.cat(rpn.anchor_generator.grid_anchors(hw, torch.device("cuda")), 0)
+    grid = rpn.anchor_generator.grid_layout(hw)
+    gts = [b.cuda() for b in _gts(n, g, float(img))]
+    obj, dlt = _heads(n, img, g, 0.3)
+    obj, dlt = [o.cuda() for o in obj], [d.cuda() for d in dlt]
+    dense = rpn.assign(at, gts, seed=8, grid=grid)
+    table, off = rpn.anchor_matcher.pack_gt(gts, at.device)
+    lazy = rpn.assign_sampled(at, table, off, n, grid, seed=8)
+    ga, gb = ([torch.zeros_like(o) for o in obj], [torch.zeros_like(d) for d in dlt]), \
+             ([torch.zeros_like(o) for o in obj], [torch.zeros_like(d) for d in dlt])
+    ra = rpn.sampled_losses(at, obj, dlt, dense, grad_buffers=ga)
+    rb = rpn.sampled_losses(at, obj, dlt, lazy, grad_buffers=gb)
+    torch.testing.assert_close(ra["sums"][:4], rb["sums"][:4], rtol=1e-6, atol=1e-8)
+    for x, y in zip(ga[0] + ga[1], gb[0] + gb[1]):
+        assert torch.equal(x, y)
+    # autograd form on the lazy assignment
+    o_g = [o.clone().requires_grad_(True) for o in obj]
+    d_g = [d.clone().requires_grad_(True) for d in dlt]
+    res = rpn.sampled_losses(at, o_g, d_g, lazy)
+    (res["cls_loss"] + res["loc_loss"]).backward()
+    for x, y in zip(o_g + d_g, gb[0] + gb[1]):
+        assert torch.equal(x.grad, y)
