@@ -365,8 +365,9 @@ def extras_train(det, dev, world, peak, quick):
     except Exception as e:  # noqa: BLE001
         out["train_grid_b1024"]["peer_exchange_error"] = f"{type(e).__name__}: {e}"
     # (ii) reference-native RPN form: R = 50127 anchors (FPN-18 @ 448), Matcher([0.3,0.7]), 256 samples, L1 + BCE, from the
-    #      head convolutions' own NCHW outputs: det_match_grid (2 launches) -> det_subsample_labels_grid ->
-    #      det_rpn_loss_sampled (forward + backward into persistent NCHW gradient buffers) -- 4 launches per step.
+    #      head convolutions' own NCHW outputs.  The step = det_assign_sampled (row maxima -> gt-centric positive search ->
+    #      sampler that labels the negatives it draws) + det_rpn_loss_sampled (forward + backward into persistent NCHW
+    #      gradient buffers); the dense-label form (det_match_grid -> det_subsample_labels_grid -> loss) is timed beside it.
     strides = (4, 8, 16, 32, 64)
     rpn = det.RegionProposalNetwork(list(strides))
     hw = [(448 // s, 448 // s) for s in strides]
@@ -395,17 +396,32 @@ def extras_train(det, dev, world, peak, quick):
         st["prev"] = (asg.samples, asg.sample_count)
         return sums
 
-    def step_full():
-        sums = loss_only(sample_only(*assign_only()))
-        prev = st.get("pending")
-        st["pending"] = det.dist.allreduce_sums_async(sums)  # waited for one step late: the scalars are only logged
-        if prev is not None:
-            prev.wait()
+    def assign_lazy():
+        # what forward(training) runs: det_assign_sampled -- only the sampled anchors are labelled (rpn.py:132-185 reduced
+        # to what `losses` reads), nothing of size R is written
+        st["seed"] += 1
+        return rpn.assign_sampled(anchors, gtb2, off2, nb, grid, seed=st["seed"])
+
+    def step_with(assign_fn):
+        def step():
+            sums = loss_only(assign_fn())
+            prev = st.get("pending")
+            st["pending"] = det.dist.allreduce_sums_async(sums)  # waited for one step late: the scalars are only logged
+            if prev is not None:
+                prev.wait()
+        return step
+
+    def drain():
+        if st.get("pending") is not None:
+            st["pending"].wait()
+            st["pending"] = None
 
     it = 5 if quick else 20
-    ms_step = time_region(step_full, it)
-    if st.get("pending") is not None:
-        st["pending"].wait()
+    ms_step_dense = time_region(step_with(lambda: sample_only(*assign_only())), it)
+    drain()
+    ms_step = time_region(step_with(assign_lazy), it)
+    drain()
+    ms_assign_lazy = time_region(assign_lazy, it)
     ms_match = time_region(lambda: st.__setitem__("mls", assign_only()), it)
     asg0 = sample_only(*st["mls"])
     ms_loss = time_region(lambda: loss_only(asg0), it)
@@ -415,7 +431,7 @@ def extras_train(det, dev, world, peak, quick):
         keep = []
 
         def graph_step():
-            asg = sample_only(*assign_only())
+            asg = assign_lazy()
             keep.append(asg)
             loss_only(asg)
 
@@ -436,10 +452,15 @@ def extras_train(det, dev, world, peak, quick):
     loss_moved = nb * (21 * R) + nb * 256 * 4 + nb * 128 * (16 + 8 + 16)
     assign_bytes = nb * 9 * R + 16 * tot2
     out["train_rpn_r50127"] = {
-        "workload": f"RPN form R=50127, batch {nb}/GPU, NCHW head tensors: grid match + subsample + sampled loss fwd+bwd "
-                    "(persistent NCHW gradient buffers) + 8-float NCCL all-reduce every step (waited one step late)",
-        "ms_step": ms_step, "ms_assign": ms_match, "ms_loss_fwd_bwd": ms_loss, "ms_step_graph_no_collective": ms_graph,
-        "batch": nb, "launches_per_step": 4,
+        "workload": f"RPN form R=50127, batch {nb}/GPU, NCHW head tensors: sample-list assignment (det_assign_sampled) + "
+                    "sampled loss fwd+bwd (persistent NCHW gradient buffers) + 8-float NCCL all-reduce every step (waited "
+                    "one step late) -- the launches of RegionProposalNetwork.forward(training)",
+        "ms_step": ms_step, "ms_assign_sampled": ms_assign_lazy, "ms_assign": ms_match, "ms_loss_fwd_bwd": ms_loss,
+        "ms_step_graph_no_collective": ms_graph,
+        "ms_step_dense_labels": ms_step_dense,
+        "dense_labels_note": "ms_step_dense_labels / ms_assign: the same step with det_match_grid writing labels + matched "
+                             "index of ALL anchors (the reference signature of label_and_sample_anchors) + subsample",
+        "batch": nb,
         "images_per_s_per_gpu": nb / ms_step * 1e3, "images_per_s_total": world * nb / ms_step * 1e3,
         "ms_assign_generic_anchors": ms_assign_generic, "ms_loss_dense_fwd_bwd": ms_loss_dense,
         "loss_roofline": {"bound": "hbm", "achieved": loss_moved / ms_loss_dense / 1e6, "peak": peak, "unit": "GB/s",
@@ -568,7 +589,8 @@ def train_summary(extras, world):
     out = {"scaling": "weak", "images_per_gpu_per_step": 1024, "n_gpus": world}
     r = extras.get("train_rpn_r50127")
     if r:
-        out["rpn_r50127"] = {"ms_step": _r(r.get("ms_step")), "ms_assign": _r(r.get("ms_assign")),
+        out["rpn_r50127"] = {"ms_step": _r(r.get("ms_step")), "ms_step_dense_labels": _r(r.get("ms_step_dense_labels")),
+                             "ms_assign_sampled": _r(r.get("ms_assign_sampled")), "ms_assign": _r(r.get("ms_assign")),
                              "ms_loss": _r(r.get("ms_loss_fwd_bwd")), "ms_graph": _r(r.get("ms_step_graph_no_collective")),
                              "img_s_total": _r(r.get("images_per_s_total"), 0),
                              "assign_frac": _r(r["assign_roofline"]["frac"], 3), "loss_frac": _r(r["loss_roofline"]["frac"], 3),
