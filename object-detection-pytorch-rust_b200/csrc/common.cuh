@@ -37,8 +37,35 @@ static inline float float_threshold_below(double thr) {
     return f;
 }
 
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
+// A kernel launched through launch_pdl() may become resident while the previous kernel of its stream is still draining:
+// its CTAs take SM slots as they free up and park in pdl_wait() -- which returns once the previous grid has completed and
+// its memory is visible -- so the launch gap and the ramp of the next launch overlap the tail of this one.  In-stream
+// semantics are unchanged as long as a kernel touches global memory only after pdl_wait().  pdl_trigger() (first
+// statement of a kernel) lets the NEXT launch_pdl() kernel in the stream start that early; after a kernel that never
+// triggers (any foreign kernel, a copy) the launch simply behaves like <<<>>>.  The edges survive stream capture.
+bool pdl_enabled();  // core.cu: false when DET_NO_PDL=1 is set in the environment (A/B measurements)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers -----------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // std::max / std::min NaN behaviour (what torchvision's CPU NMS evaluates): (a<b)?b:a and (b<a)?b:a
 __device__ __forceinline__ float max_std(float a, float b) { return (a < b) ? b : a; }

@@ -199,10 +199,10 @@ static int launch_yolo_fast(const float* head, const float* priors, const YoloPa
     cudaError_t e = cudaFuncSetAttribute(yolo_fast_kernel<MAXT, MINB, CS, CB, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)lay.bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(yolo_fast_kernel)");
-    yolo_fast_kernel<MAXT, MINB, CS, CB, CC><<<prm.n, warps * 32, lay.bytes, st>>>(
-        head, reinterpret_cast<const float2*>(priors), prm, reinterpret_cast<float4*>(dense_boxes), dense_conf,
-        dense_scores, det_flat, reinterpret_cast<float4*>(det_boxes), det_scores, det_count);
-    DET_LAUNCH_OK("yolo_fast_kernel");
+    e = launch_pdl(yolo_fast_kernel<MAXT, MINB, CS, CB, CC>, dim3(prm.n), dim3(warps * 32), lay.bytes, st, head,
+                   reinterpret_cast<const float2*>(priors), prm, reinterpret_cast<float4*>(dense_boxes), dense_conf,
+                   dense_scores, det_flat, reinterpret_cast<float4*>(det_boxes), det_scores, det_count);
+    if (e != cudaSuccess) return cuda_fail(e, "yolo_fast_kernel");
     return DET_OK;
 }
 

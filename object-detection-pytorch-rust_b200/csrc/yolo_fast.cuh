@@ -89,10 +89,10 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
     __shared__ float s_mx[4], s_mn[4];
     __shared__ int s_fl[4];
     __shared__ unsigned s_nz[kFastMaxC][4];
+    __shared__ __align__(16) int4 s_work[kFastMaxC];  // per class: candidates, 32-item chunks of pair tests, 2^32/half
     __shared__ int s_total;
     __shared__ struct {
-        int cnt, gcat, gfl;
-        float gmx, gmn;
+        int cnt, gcat;
         unsigned cut[2];
     } s_img;
     __shared__ unsigned long long s_best;
@@ -105,58 +105,41 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
     const int img = blockIdx.x;
     const int K = (int)min(prm.max_det, (int64_t)PC);
 
-    DET_MARK(0);
-    // ---- A: stage this image's logits with 16-byte coalesced loads over the aligned interior of its span
-    const int64_t g0 = (int64_t)img * S2 * ch, g1 = g0 + (int64_t)S2 * ch;
-    const float4* head4 = reinterpret_cast<const float4*>(head);
-    for (int64_t v = (g0 >> 2) + tid; v < ((g1 + 3) >> 2); v += T) {
-        const int64_t base = v << 2;
-        if (base >= g0 && base + 4 <= g1) {
-            const float4 q = ld_stream(head4 + v);
-            float* d = hs + (base - g0);
-            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
-        } else {
-            for (int e = 0; e < 4; ++e)
-                if (base + e >= g0 && base + e < g1) hs[base + e - g0] = ld_stream(head + base + e);
-        }
-    }
+    pdl_trigger();  // the next launch of this stream may take SM slots as they free up (it parks in its own pdl_wait)
     for (int i = tid; i < kFastBins; i += T) {
         s_hist[i] = 0;
         s_hist2[i] = 0;
     }
     if (tid == 0) s_total = 0;
-    __syncthreads();
-    // sigmoid of conf and class logits in place and, by a disjoint set of threads working from the raw tx, ty, tw, th
-    // (which the in-place pass leaves alone), the predictor boxes -- one barrier for both
-    for (int i = tid; i < S2 * ch; i += T) {
-        const int cell = i / ch, k = i - cell * ch;
+    pdl_wait();     // everything earlier in the stream is complete and visible from here on
+    DET_MARK(0);
+    // ---- A: stage this image's logits with 16-byte coalesced loads over the aligned interior of its span; every value is
+    // transformed on its way into shared memory -- sigmoid for tx, ty, conf and the class logits, exp(min(t, clamp)) for
+    // tw, th -- so nothing is staged raw and the box assembly below is a handful of multiply-adds
+    const int64_t g0 = (int64_t)img * S2 * ch, g1 = g0 + (int64_t)S2 * ch;
+    const float4* head4 = reinterpret_cast<const float4*>(head);
+    auto activate = [&](int e, float x) -> float {  // e = element index inside the image (cell-major, channel-minor)
+        const int cell = e / ch, k = e - cell * ch;
         if (k < B * 5) {
             const int bi = k / 5, comp = k - bi * 5;
-            if (comp != 4) continue;
-            const float y = sigmoidf_ref(hs[i]);
-            hs[i] = y;
-            if (dense_conf) dense_conf[(int64_t)img * P + cell * B + bi] = y;
+            if (comp == 2 || comp == 3) return expf((x > prm.scale_clamp) ? prm.scale_clamp : x);  // clamp(max=): NaN stays
+            const float y = sigmoidf_ref(x);
+            if (comp == 4 && dense_conf) dense_conf[(int64_t)img * P + cell * B + bi] = y;
+            return y;
+        }
+        return sigmoidf_ref(x);
+    };
+    for (int64_t v = (g0 >> 2) + tid; v < ((g1 + 3) >> 2); v += T) {
+        const int64_t base = v << 2;
+        const int e0 = (int)(base - g0);
+        if (base >= g0 && base + 4 <= g1) {
+            const float4 q = ld_stream(head4 + v);
+            float* d = hs + e0;
+            d[0] = activate(e0, q.x); d[1] = activate(e0 + 1, q.y); d[2] = activate(e0 + 2, q.z); d[3] = activate(e0 + 3, q.w);
         } else {
-            hs[i] = sigmoidf_ref(hs[i]);
+            for (int e = 0; e < 4; ++e)
+                if (base + e >= g0 && base + e < g1) hs[e0 + e] = activate(e0 + e, ld_stream(head + base + e));
         }
-    }
-    for (int p = T - 1 - tid; p < P; p += T) {  // the last threads of the CTA have the fewest logits above
-        const int cell = p / B, bi = p - cell * B;
-        const int row = cell / S, col = cell - row * S;
-        const float* t = hs + cell * ch + bi * 5;
-        const float2 pr = priors[bi];
-        const float tw = (t[2] > prm.scale_clamp) ? prm.scale_clamp : t[2];  // torch.clamp(max=): NaN stays NaN
-        const float th = (t[3] > prm.scale_clamp) ? prm.scale_clamp : t[3];
-        const float cx = (sigmoidf_ref(t[0]) + (float)col) * prm.stride_x;
-        const float cy = (sigmoidf_ref(t[1]) + (float)row) * prm.stride_y;
-        const float w = expf(tw) * pr.x, h = expf(th) * pr.y;
-        float4 bx = make_float4(cx - 0.5f * w, cy - 0.5f * h, cx + 0.5f * w, cy + 0.5f * h);
-        if (prm.clip) {  // torch clamp(min=0,max=W): NaN stays NaN
-            bx.x = min_nan(max_nan(bx.x, 0.f), prm.img_w); bx.z = min_nan(max_nan(bx.z, 0.f), prm.img_w);
-            bx.y = min_nan(max_nan(bx.y, 0.f), prm.img_h); bx.w = min_nan(max_nan(bx.w, 0.f), prm.img_h);
-        }
-        pbox[p] = bx;
-        if (dense_boxes) dense_boxes[(int64_t)img * P + p] = bx;
     }
     __syncthreads();
     DET_MARK(1);
@@ -190,19 +173,36 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         }
         if (lane == 0) s_m[c] = mcount;
     }
-    // coordinate statistics over the predictors that are a candidate for at least one class: conf * max class prob
-    // passes iff some conf * prob passes (rounding is monotone); NaN probabilities never pass and are skipped by fmaxf
-    if (tid < ((P + 31) & ~31)) {
-        const int p = tid;
+    __syncthreads();
+    // ---- image-level work, two groups of warps side by side:
+    //  * warp 0 -- class counts and T: the tier cuts from the candidate histogram
+    //  * the next ceil(P/32) warps -- one thread per predictor: box assembly, and the coordinate statistics torchvision's
+    //    offset trick needs over the predictors that are a candidate for at least one class (conf * max class prob passes
+    //    iff some conf * prob passes: rounding is monotone; NaN probabilities never pass and are skipped by fmaxf)
+    const int stat_w0 = (T >> 5) > (P + 31) / 32 ? 1 : 0;  // first statistics warp (warp 0 joins in when the CTA is small)
+    if (wid >= stat_w0 && wid < stat_w0 + (P + 31) / 32) {
+        const int p = tid - 32 * stat_w0;
         float mx = -INFINITY, mn = INFINITY;
         int fin = 1, nonan_l = 1;
         if (p < P) {
             const int cell = p / B, bi = p - cell * B;
+            const int row = cell / S, col = cell - row * S;
+            const float* t = hs + cell * ch + bi * 5;
+            const float2 pr = priors[bi];
+            const float cx = (t[0] + (float)col) * prm.stride_x;
+            const float cy = (t[1] + (float)row) * prm.stride_y;
+            const float w = t[2] * pr.x, h = t[3] * pr.y;
+            float4 b = make_float4(cx - 0.5f * w, cy - 0.5f * h, cx + 0.5f * w, cy + 0.5f * h);
+            if (prm.clip) {  // torch clamp(min=0,max=W): NaN stays NaN
+                b.x = min_nan(max_nan(b.x, 0.f), prm.img_w); b.z = min_nan(max_nan(b.z, 0.f), prm.img_w);
+                b.y = min_nan(max_nan(b.y, 0.f), prm.img_h); b.w = min_nan(max_nan(b.w, 0.f), prm.img_h);
+            }
+            pbox[p] = b;
+            if (dense_boxes) dense_boxes[(int64_t)img * P + p] = b;
             const float* pc = hs + cell * ch + B * 5;
             float best = pc[0];
             for (int q = 1; q < C; ++q) best = fmaxf(best, pc[q]);
-            if (hs[cell * ch + bi * 5 + 4] * best > prm.score_thresh) {
-                const float4 b = pbox[p];
+            if (t[4] * best > prm.score_thresh) {
                 mx = max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w));
                 mn = min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w));
                 fin = (int)(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w));
@@ -217,24 +217,15 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
             nonan_l &= __shfl_xor_sync(FULL, nonan_l, o);
         }
         if (lane == 0) {
-            s_mx[wid] = mx;
-            s_mn[wid] = mn;
-            s_fl[wid] = fin | (nonan_l << 1);
+            s_mx[wid - stat_w0] = mx;
+            s_mn[wid - stat_w0] = mn;
+            s_fl[wid - stat_w0] = fin | (nonan_l << 1);
         }
     }
-    __syncthreads();
-    // ---- image-level reductions and T: the tier cuts -- warp 0 only, broadcast through shared memory
     if (wid == 0) {
         const int mq = lane < C ? s_m[lane] : 0;
         const int cnt_w = warp_sum(mq);
         const unsigned has = __ballot_sync(FULL, mq > 0);
-        float gmx_w = -INFINITY, gmn_w = INFINITY;
-        int gfl_w = 3;
-        for (int q = 0; q < (P + 31) / 32; ++q) {
-            gmx_w = max_nan(gmx_w, s_mx[q]);
-            gmn_w = min_nan(gmn_w, s_mn[q]);
-            gfl_w &= s_fl[q];
-        }
         // two nested cuts from the candidate histogram: the highest bins holding >= target candidates
         unsigned cut[2] = {0u, 0u};
         const int targets[2] = {K + K / 6 + 8, 2 * K + 16};
@@ -275,16 +266,19 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         if (lane == 0) {
             s_img.cnt = cnt_w;
             s_img.gcat = has ? 31 - __clz(has) : 0;
-            s_img.gmx = gmx_w;
-            s_img.gmn = gmn_w;
-            s_img.gfl = gfl_w;
             s_img.cut[0] = cut[0];
             s_img.cut[1] = cut[1];
         }
     }
     __syncthreads();
-    const int cnt = s_img.cnt, gcat = s_img.gcat, gfl = s_img.gfl;
-    const float gmx = s_img.gmx, gmn = s_img.gmn;
+    float gmx = -INFINITY, gmn = INFINITY;
+    int gfl = 3;
+    for (int q = 0; q < (P + 31) / 32; ++q) {
+        gmx = max_nan(gmx, s_mx[q]);
+        gmn = min_nan(gmn, s_mn[q]);
+        gfl &= s_fl[q];
+    }
+    const int cnt = s_img.cnt, gcat = s_img.gcat;
     // reference CPU rule: boxes.numel() <= 4000 -> coordinate-offset trick (torchvision/ops/boxes.py batched_nms)
     const bool trick = (prm.mode == DET_NMS_AUTO) ? (cnt <= 1000) : (prm.mode == DET_NMS_OFFSET_TRICK);
     const float span = trick ? gmx + 1.0f : 0.0f;  // max_coordinate + torch.tensor(1).to(boxes)
@@ -316,19 +310,18 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
             shift2 = score_shift(base2);
 #pragma unroll
             for (int k = 0; k < 4; ++k) mine_kept[k] = false;
+            unsigned char* my = cls_region + (size_t)(cls_warp ? c : 0) * lay.cls_stride;
+            unsigned* skey = reinterpret_cast<unsigned*>(my + Pp * 36);
+            unsigned char* spred = my + Pp * 40;
+            int m = 0;
             if (cls_warp) {
-                unsigned char* my = cls_region + (size_t)c * lay.cls_stride;
                 float4* sbox = reinterpret_cast<float4*>(my);
                 uint4* rows4 = reinterpret_cast<uint4*>(my + Pp * 16);
                 unsigned* rows = reinterpret_cast<unsigned*>(rows4);
                 float* sarea = reinterpret_cast<float*>(my + Pp * 32);
-                unsigned* skey = reinterpret_cast<unsigned*>(my + Pp * 36);
-                unsigned char* spred = my + Pp * 40;
                 unsigned* ckey = rows;  // unsorted candidates live in the row storage until the rows are needed
                 unsigned char* cp = reinterpret_cast<unsigned char*>(rows + Pp);
                 // ---- C: order-preserving compaction (predictor ascending)
-                if (lane < 4) s_nz[c][lane] = 0u;
-                int m = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const bool in = pass[k] && __float_as_uint(sc[k]) >= cut_bits;
@@ -368,32 +361,64 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
                 }
                 __syncwarp();
                 for (int r = lane; r < m; r += 32) rows4[r] = make_uint4(0u, 0u, 0u, 0u);
-                __syncwarp();
+                if (lane < 4) s_nz[c][lane] = 0u;
+                if (lane == 0) {
+                    // the class's pair items (m * floor(m/2), see E) in chunks of 32 for the CTA-wide sweep below
+                    const int half = m >> 1;
+                    s_work[c] = make_int4(m, m >= 2 ? (m * half + 31) >> 5 : 0,
+                                          half > 1 ? (int)((0xFFFFFFFFu / (unsigned)half) + 1u) : 0, 0);
+                }
                 DET_MARK(6);
-                // ---- E: all pairs once: item q -> (row r, distance d), partner (r + d) mod m
-                if (m >= 2) {
-                    const int half = m >> 1, items = m * half;
-                    const unsigned inv = half > 1 ? (0xFFFFFFFFu / (unsigned)half) + 1u : 0u;
-                    const bool even = (m & 1) == 0;
-                    for (int q = lane; q < items; q += 32) {
-                        const int r = half > 1 ? (int)__umulhi((unsigned)q, inv) : q;
-                        const int d = q - r * half + 1;
-                        if (even && d == half && r >= half) continue;  // distance-m/2 pairs: from the lower half only
-                        int j = r + d;
-                        j = (j >= m) ? j - m : j;
-                        const int lo = min(r, j), hi = max(r, j);
-                        const float4 ba = sbox[lo], bb = sbox[hi];
-                        const float aa = sarea[lo], ab = sarea[hi];
-                        const bool hit = nonan ? nms_suppresses<true>(ba, aa, bb, ab, thr_f)
-                                               : nms_suppresses<false>(ba, aa, bb, ab, thr_f);
-                        if (hit) {
-                            atomicOr(rows + lo * 4 + (hi >> 5), 1u << (hi & 31));
-                            atomicOr(&s_nz[c][lo >> 5], 1u << (lo & 31));
-                        }
+            } else if (wid < kFastMaxC && lane == 0) {
+                s_work[wid] = make_int4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            // ---- E: every unordered pair of every class exactly once.  A class of m candidates has m * floor(m/2) items
+            // (item q -> row r = q / half, distance d = q % half + 1, partner (r + d) mod m), cut into chunks of 32; the
+            // chunks of ALL classes are dealt round-robin to the warps of the CTA, so a class with many candidates no
+            // longer holds up the image (the classes' sizes differ by 2-3x and the work is quadratic in them).
+            {
+                const int nw = T >> 5;
+                const int4 wk = lane < C ? s_work[lane] : make_int4(0, 0, 0, 0);
+                int incl = wk.y;  // inclusive scan of the chunk counts over the classes (lane = class)
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int chunks = __shfl_sync(FULL, incl, 31);
+                for (int g = wid; g < chunks; g += nw) {
+                    const int cls = __popc(__ballot_sync(FULL, incl <= g));  // classes that end at or before chunk g
+                    const int first = __shfl_sync(FULL, incl - wk.y, cls);
+                    const int mm = __shfl_sync(FULL, wk.x, cls);
+                    const unsigned inv = (unsigned)__shfl_sync(FULL, wk.z, cls);
+                    const int half = mm >> 1, items = mm * half;
+                    const int q = ((g - first) << 5) + lane;
+                    if (q >= items) continue;
+                    unsigned char* cm = cls_region + (size_t)cls * lay.cls_stride;
+                    const float4* cbox = reinterpret_cast<const float4*>(cm);
+                    unsigned* crows = reinterpret_cast<unsigned*>(cm + Pp * 16);
+                    const float* carea = reinterpret_cast<const float*>(cm + Pp * 32);
+                    const int r = half > 1 ? (int)__umulhi((unsigned)q, inv) : q;
+                    const int d = q - r * half + 1;
+                    if (((mm & 1) == 0) && d == half && r >= half) continue;  // distance-m/2 pairs: from the lower half only
+                    int j = r + d;
+                    j = (j >= mm) ? j - mm : j;
+                    const int lo = min(r, j), hi = max(r, j);
+                    const float4 ba = cbox[lo], bb = cbox[hi];
+                    const float aa = carea[lo], ab = carea[hi];
+                    const bool hit = nonan ? nms_suppresses<true>(ba, aa, bb, ab, thr_f)
+                                           : nms_suppresses<false>(ba, aa, bb, ab, thr_f);
+                    if (hit) {
+                        atomicOr(crows + lo * 4 + (hi >> 5), 1u << (hi & 31));
+                        atomicOr(&s_nz[cls][lo >> 5], 1u << (lo & 31));
                     }
                 }
-                __syncwarp();
-                DET_MARK(7);
+            }
+            __syncthreads();
+            DET_MARK(7);
+            if (cls_warp) {
+                const uint4* rows4 = reinterpret_cast<const uint4*>(my + Pp * 16);
                 // ---- F: greedy resolution on the bit rows (uniform across the warp), only non-empty rows matter
                 unsigned alive[4];
 #pragma unroll
@@ -467,26 +492,24 @@ yolo_fast_kernel(const float* __restrict__ head, const float2* __restrict__ prio
         }
         __syncthreads();
         // bin-grouped placement (arbitrary order inside a bin): slots are handed out by counting the bin back down
-        int mybin[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            mybin[w] = 0;
             if (mine_kept[w]) {
-                mybin[w] = score_bin(~(unsigned)(mykey[w] >> 32), base2, shift2);
-                const int slot = s_base[mybin[w]] + atomicSub(&s_hist2[mybin[w]], 1) - 1;
+                const int bin = score_bin(~(unsigned)(mykey[w] >> 32), base2, shift2);
+                const int slot = s_base[bin] + atomicSub(&s_hist2[bin], 1) - 1;
                 buf_a[slot] = mykey[w];
             }
         }
         __syncthreads();
-        // rank inside the bin by direct comparison (keys are distinct); only the first K positions are output
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            if (mine_kept[w]) {
-                const int b0 = s_base[mybin[w]], b1 = mybin[w] > 0 ? s_base[mybin[w] - 1] : total;
-                int pos = b0;
-                for (int j = b0; j < b1; ++j) pos += (buf_a[j] < mykey[w]) ? 1 : 0;
-                if (pos < K) buf_b[pos] = mykey[w];
-            }
+        // rank inside the bin by direct comparison (keys are distinct); only the first K positions are output.  One
+        // thread per SLOT: the lanes of a warp hold neighbouring bins, so their scans have similar lengths
+        for (int t = tid; t < total; t += T) {
+            const uint64_t key = buf_a[t];
+            const int bin = score_bin(~(unsigned)(key >> 32), base2, shift2);
+            const int b0 = s_base[bin], b1 = bin > 0 ? s_base[bin - 1] : total;
+            int pos = b0;
+            for (int j = b0; j < b1; ++j) pos += (buf_a[j] < key) ? 1 : 0;
+            if (pos < K) buf_b[pos] = key;
         }
         __syncthreads();
         fin_keys = buf_b;
