@@ -31,7 +31,7 @@ extern "C" {
 #define DET_ERR_CUDA (-4)         /* a CUDA runtime call failed; see det_last_error()            */
 #define DET_ERR_ALIGN (-5)        /* pointer not aligned as documented                           */
 
-#define DET_ABI_VERSION 2
+#define DET_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DET_API __attribute__((visibility("default")))
@@ -198,6 +198,23 @@ DET_API int det_dense_detect(const det_dense_level_t* levels_host, int num_level
                      float score_thresh, double iou_threshold, int mode, int gate, int64_t cand_cap, int64_t max_det,
                      int64_t* det_idx, float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
                      int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Row-ordered candidate compaction and the final gather of the UNFUSED detector path (det_dense_decode ->
+ * det_threshold_compact -> det_nms_batched -> det_gather_detections): the exact route for images that overflow
+ * det_dense_detect's candidate list and for pyramids outside its limits.  Same specification as det_dense_detect
+ * (oracle/ref_torch.py dense_select_nms): cand = nonzero(score > score_thresh) in row order.
+ *   boxes (n,r,4), scores (n,r), classes (n,r) int64 or NULL -> cand_rows (n,cap) int64 (row of every candidate),
+ *   cand_boxes (n,cap,4), cand_scores (n,cap), cand_classes (n,cap) int64, cand_counts (n) int32 = min(#candidates, cap).
+ * det_gather_detections: keep (n,max_det) int64 indices into an image's candidate list + keep_counts (n) (the outputs of
+ *   det_nms_batched) -> det_idx (original rows; the candidate index when cand_rows is NULL), det_boxes, det_scores,
+ *   det_classes, each (n,max_det[,4]); entries past keep_counts stay untouched. */
+DET_API int det_threshold_compact(const float* boxes, const float* scores, const int64_t* classes, int n, int64_t r,
+                          float score_thresh, int64_t cap, int64_t* cand_rows, float* cand_boxes, float* cand_scores,
+                          int64_t* cand_classes, int32_t* cand_counts, void* stream);
+DET_API int det_gather_detections(const int64_t* keep, const int32_t* keep_counts, int n, int64_t max_det,
+                          const int64_t* cand_rows, const float* cand_boxes, const float* cand_scores,
+                          const int64_t* cand_classes, int64_t cap, int64_t* det_idx, float* det_boxes, float* det_scores,
+                          int64_t* det_classes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (4a) IoU target assignment -- replaces pairwise_iou + Matcher.__call__ + set_low_quality_matches_ as driven

@@ -74,16 +74,17 @@ __device__ __forceinline__ void reach_window(float g_lo, float g_hi, float a_lo,
 // positions whose overlap with (g_lo, g_hi) along one axis can be the LARGEST: with centre offset d the overlap is
 // min(a_len, g_len, (a_len + g_len)/2 - |d|): constant on the plateau |d| <= |g_len - a_len| / 2 and strictly smaller
 // by at least one stride for every further position.  IoU grows with the overlap of either axis, so a row maximum (and
-// every anchor that EQUALS it) lies on plateau x plateau; two positions of margin absorb the rounding of the coordinates.
+// every anchor that EQUALS it) lies on plateau x plateau.  floor / ceil already round outwards; one more position of margin
+// absorbs the rounding of the quotient (anchor coordinates are x * stride + offset: exact in fp32 at these sizes).
 __device__ __forceinline__ void plateau_window(float g_lo, float g_hi, float a_lo, float a_hi, float s, int w, int& lo, int& hi) {
     const float gc = 0.5f * (g_lo + g_hi), ac = 0.5f * (a_lo + a_hi);
     const float half = 0.5f * fabsf((g_hi - g_lo) - (a_hi - a_lo));
-    const float f_lo = floorf((gc - ac - half) / s) - 2.0f, f_hi = ceilf((gc - ac + half) / s) + 2.0f;
+    const float f_lo = floorf((gc - ac - half) / s) - 1.0f, f_hi = ceilf((gc - ac + half) / s) + 1.0f;
     lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)w);
     hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), -1.0f);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 10)
 match_rowmax_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, int n, int64_t sum_g,
                     const float4* __restrict__ anchors, GridLayoutDev lay, int want_rowmax, float* __restrict__ rowmax,
                     int32_t* __restrict__ flags, uint32_t* __restrict__ mask, int32_t* __restrict__ stats,
@@ -136,7 +137,19 @@ match_rowmax_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ g
         }
     }
     if (!want_rowmax) return;
-    // ---- (2) row maximum
+    // ---- (2) row maximum.  Lane p prepares pair p's plateau window once (the divisions run side by side instead of one
+    // pair after the other); the sweep below fetches the window of the pair it works on with shuffles.
+    int wx_lo = 0, wx_hi = -1, wy_lo = 0, wy_hi = -1;
+    if (lane < P) {
+        const GridLevelDev Lp = lay.lv[lane / A];
+        wx_hi = Lp.w - 1;
+        wy_hi = Lp.h - 1;
+        if (finite && ga > 0.0f && isfinite(ab0.x) && isfinite(ab0.y) && isfinite(ab0.z) && isfinite(ab0.w) &&
+            ab0.z > ab0.x && ab0.w > ab0.y) {
+            plateau_window(gb.x, gb.z, ab0.x, ab0.z, (float)Lp.stride, Lp.w, wx_lo, wx_hi);
+            plateau_window(gb.y, gb.w, ab0.y, ab0.w, (float)Lp.stride, Lp.h, wy_lo, wy_hi);
+        }
+    }
     float best = 0.0f;
     unsigned pending = __ballot_sync(FULLMASK, lane < P);
     while (pending) {
@@ -146,16 +159,10 @@ match_rowmax_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ g
         if (bmax * 1.0001f < best) break;  // no remaining pair can reach (let alone equal) the maximum found so far
         const int src = __ffs(__ballot_sync(FULLMASK, mine == bmax)) - 1;
         pending &= ~(1u << src);
-        const float4 a0 = make_float4(__shfl_sync(FULLMASK, ab0.x, src), __shfl_sync(FULLMASK, ab0.y, src),
-                                      __shfl_sync(FULLMASK, ab0.z, src), __shfl_sync(FULLMASK, ab0.w, src));
+        const int x_lo = __shfl_sync(FULLMASK, wx_lo, src), x_hi = __shfl_sync(FULLMASK, wx_hi, src);
+        const int y_lo = __shfl_sync(FULLMASK, wy_lo, src), y_hi = __shfl_sync(FULLMASK, wy_hi, src);
         const GridLevelDev L = lay.lv[src / A];
         const int a = src % A;
-        int x_lo = 0, x_hi = L.w - 1, y_lo = 0, y_hi = L.h - 1;
-        if (finite && ga > 0.0f && isfinite(a0.x) && isfinite(a0.y) && isfinite(a0.z) && isfinite(a0.w) &&
-            a0.z > a0.x && a0.w > a0.y) {
-            plateau_window(gb.x, gb.z, a0.x, a0.z, (float)L.stride, L.w, x_lo, x_hi);
-            plateau_window(gb.y, gb.w, a0.y, a0.w, (float)L.stride, L.h, y_lo, y_hi);
-        }
         float v = 0.0f;
         // the lanes sweep the window as an 8 x 4 patch (no integer division, 32-bit row arithmetic: r < 2^31 / 16)
         const float4* __restrict__ lvl = anchors + L.first_row + a;
@@ -190,7 +197,7 @@ __device__ __forceinline__ void overlap_window(float g_lo, float g_hi, float a_l
         hi = -1;
         return;
     }
-    const float f_lo = floorf((gc - ac - half) / s) - 2.0f, f_hi = ceilf((gc - ac + half) / s) + 2.0f;
+    const float f_lo = floorf((gc - ac - half) / s) - 1.0f, f_hi = ceilf((gc - ac + half) / s) + 1.0f;
     lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)w);
     hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), -1.0f);
 }
@@ -198,33 +205,41 @@ __device__ __forceinline__ void overlap_window(float g_lo, float g_hi, float a_l
 // one warp per gt box (row maxima are final: match_rowmax_kernel ran before).  Appends the image's positives
 // (anchor row | label << 24, matched gt) to pos_list / pos_gt; stats[img*4+0] counts them.  An anchor that several boxes
 // nominate is emitted by the first of them only (Verdict::first_q).
-__global__ void __launch_bounds__(256)
+constexpr int kCandWarps = 4;   // warps (gt boxes) per CTA of match_rowmax_kernel / assign_candidates_kernel: small CTAs even
+                                // out the very different amounts of work per box
+constexpr int kHitCap = 128;    // nominated anchors buffered per warp before their verdicts are evaluated
+
+__global__ void __launch_bounds__(kCandWarps * 32, 10)
 assign_candidates_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, int n, int64_t sum_g,
                          const float4* __restrict__ anchors, GridLayoutDev lay, MatchRule rule, float tau,
                          const float* __restrict__ rowmax, const int32_t* __restrict__ flags, int32_t* __restrict__ stats,
                          int32_t* __restrict__ pos_list, int32_t* __restrict__ pos_gt, int list_cap) {
+    __shared__ int s_hits[kCandWarps][kHitCap];
     const unsigned FULLMASK = 0xffffffffu;
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= sum_g) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int img = gt_image(gt_off, n, (int)t);
     if (rule.allow_lq && (flags[img] & kFlagPromoteAll)) return;  // every anchor is positive: the sampler's dense path
     const int g0 = gt_off[img], G = gt_off[img + 1] - g0, tl = (int)t - g0;
     const float4 gb = gt[t];
     const float ga = box_area(gb);
-    const float rm = rule.allow_lq ? rowmax[t] : -1.0f;
+    const bool lq = rule.allow_lq != 0;
+    const float rm = lq ? rowmax[t] : -1.0f;
     const bool finite = isfinite(gb.x) && isfinite(gb.y) && isfinite(gb.z) && isfinite(gb.w) && ga > 0.0f;
     const int A = lay.a, P = lay.nlev * A;
-    for (int p = 0; p < P; ++p) {
-        const GridLevelDev L = lay.lv[p / A];
-        const int a = p % A;
-        const float4 a0 = anchors[L.first_row + a];
+    // lane p prepares the window of (level, cell anchor) pair p: the positions whose IoU with this box can reach tau
+    // or equal the row maximum (empty for most pairs).  All the divisions of the 15 pairs run side by side.
+    int wx_lo = 0, wx_hi = -1, wy_lo = 0, wy_hi = -1;
+    if (lane < P) {
+        const GridLevelDev L = lay.lv[lane / A];
+        const float4 a0 = anchors[L.first_row + lane % A];
         const float aa = box_area(a0);
-        int x_lo = 0, x_hi = L.w - 1, y_lo = 0, y_hi = L.h - 1;
+        wx_hi = L.w - 1;
+        wy_hi = L.h - 1;  // anything doubtful (degenerate or non-finite boxes) sweeps the whole level
         if (finite && aa > 0.0f && isfinite(aa) && a0.z > a0.x && a0.w > a0.y) {
             const float bound = fminf(ga, aa) / fmaxf(ga, aa) * 1.0001f;  // IoU <= min(area) / max(area)
-            const bool by_tau = bound >= tau, by_rm = rule.allow_lq && bound >= rm;
-            if (!by_tau && !by_rm) continue;
+            const bool by_tau = bound >= tau, by_rm = lq && bound >= rm;
             // IoU >= tau needs inter >= tau * max(area), hence an x overlap of at least that over the largest possible y
             // overlap min(a_h, g_h) (and vice versa); IoU == row max lies on the plateau windows (match_rowmax_kernel)
             const float need = tau * fmaxf(ga, aa) * 0.9999f;
@@ -238,46 +253,77 @@ assign_candidates_kernel(const float4* __restrict__ gt, const int32_t* __restric
                 plateau_window(gb.y, gb.w, a0.y, a0.w, (float)L.stride, L.h, yc, yd);
             }
             const bool e1 = xa > xb || ya > yb, e2 = xc > xd || yc > yd;
-            if (e1 && e2) continue;
-            x_lo = e1 ? xc : (e2 ? xa : min(xa, xc)); x_hi = e1 ? xd : (e2 ? xb : max(xb, xd));
-            y_lo = e1 ? yc : (e2 ? ya : min(ya, yc)); y_hi = e1 ? yd : (e2 ? yb : max(yb, yd));
+            wx_lo = e1 ? xc : (e2 ? xa : min(xa, xc)); wx_hi = e1 ? xd : (e2 ? xb : max(xb, xd));
+            wy_lo = e1 ? yc : (e2 ? ya : min(ya, yc)); wy_hi = e1 ? yd : (e2 ? yb : max(yb, yd));
+            if (e1 && e2) {
+                wx_lo = 0;
+                wx_hi = -1;
+            }
         }
-        const float4* __restrict__ lvl = anchors + L.first_row + a;
-        const int lx = lane & 7, ly = lane >> 3;
-        // warp-uniform trip counts (the verdict loop below shuffles nothing, but the list append is warp-aggregated)
+    }
+    // Nominated anchors (IoU >= tau or == row maximum) are only buffered during the sweep; their verdicts -- one loop
+    // over all gt boxes of the image each -- are evaluated 32 at a time with every lane busy.
+    int nh = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        for (int h0 = 0; h0 < nh; h0 += 32) {
+            const bool has = h0 + lane < nh;
+            bool emit = false;
+            int packed = 0, mgt = 0;
+            if (has) {
+                const int row = s_hits[wid][h0 + lane];
+                const Verdict vd = anchor_verdict(anchors[row], gt, rowmax, g0, G, tau, lq);
+                const int lb = verdict_label(rule, vd, G);
+                if (vd.first_q == tl && lb != 0 && lb != -1) {  // an anchor several boxes nominate: the first one emits
+                    emit = true;
+                    packed = row | ((int)(uint8_t)lb << 24);
+                    mgt = vd.argmax;
+                }
+            }
+            const unsigned em = __ballot_sync(FULLMASK, emit);
+            if (em) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&stats[img * 4 + 0], __popc(em));
+                base = __shfl_sync(FULLMASK, base, 0) + __popc(em & ((1u << lane) - 1u));
+                if (emit && base < list_cap) {
+                    pos_list[(int64_t)img * list_cap + base] = packed;
+                    pos_gt[(int64_t)img * list_cap + base] = mgt;
+                }
+            }
+        }
+        __syncwarp();
+        nh = 0;
+    };
+    const int lx = lane & 7, ly = lane >> 3;
+    for (int p = 0; p < P; ++p) {
+        const int x_lo = __shfl_sync(FULLMASK, wx_lo, p), x_hi = __shfl_sync(FULLMASK, wx_hi, p);
+        const int y_lo = __shfl_sync(FULLMASK, wy_lo, p), y_hi = __shfl_sync(FULLMASK, wy_hi, p);
+        if (x_lo > x_hi || y_lo > y_hi) continue;  // warp-uniform
+        const GridLevelDev L = lay.lv[p / A];
+        const int a = p % A;
+        const int row_a = (int)L.first_row + a;
+        const float4* __restrict__ lvl = anchors + row_a;
         for (int yy = y_lo; yy <= y_hi; yy += 4) {
             for (int xx = x_lo; xx <= x_hi; xx += 8) {
                 const int y = yy + ly, x = xx + lx;
-                const bool in = y <= y_hi && x <= x_hi;
-                bool emit = false;
-                int packed = 0, mgt = 0;
-                if (in) {
-                    const int row = (y * L.w + x) * A;
+                bool hit = false;
+                int row = 0;
+                if (y <= y_hi && x <= x_hi) {
+                    row = (y * L.w + x) * A;
                     const float4 ab = lvl[row];
                     const float v = pair_iou(gb, ga, ab, box_area(ab));
-                    if (v >= tau || (rule.allow_lq && v == rm)) {
-                        const Verdict vd = anchor_verdict(ab, gt, rowmax, g0, G, tau, rule.allow_lq != 0);
-                        const int lb = verdict_label(rule, vd, G);
-                        if (vd.first_q == tl && lb != 0 && lb != -1) {
-                            emit = true;
-                            packed = (int)(L.first_row + a + row) | ((int)(uint8_t)lb << 24);
-                            mgt = vd.argmax;
-                        }
-                    }
+                    hit = v >= tau || (lq && v == rm);
                 }
-                const unsigned em = __ballot_sync(FULLMASK, emit);
-                if (em) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&stats[img * 4 + 0], __popc(em));
-                    base = __shfl_sync(FULLMASK, base, 0) + __popc(em & ((1u << lane) - 1u));
-                    if (emit && base < list_cap) {
-                        pos_list[(int64_t)img * list_cap + base] = packed;
-                        pos_gt[(int64_t)img * list_cap + base] = mgt;
-                    }
+                const unsigned bal = __ballot_sync(FULLMASK, hit);
+                if (bal) {
+                    if (nh + __popc(bal) > kHitCap) flush();
+                    if (hit) s_hits[wid][nh + __popc(bal & ((1u << lane) - 1u))] = row_a + row;
+                    nh += __popc(bal);
                 }
             }
         }
     }
+    flush();
 }
 
 // ---- K2: labels + matched index of every anchor, one pass -------------------------------------------------------------
@@ -529,7 +575,7 @@ __device__ __forceinline__ HeadAddr head_addr(const HeadLayoutDev& hl, int img, 
     return ad;
 }
 
-constexpr int kSampledThreads = 128;
+constexpr int kSampledThreads = 256;  // one thread per sample (batch_size_per_image = 256): every gather is in flight at once
 
 template <bool GIOU>
 __global__ void __launch_bounds__(kSampledThreads)
@@ -740,7 +786,7 @@ int det_match_grid(const float* gt_boxes, const int32_t* gt_offsets, int n, int6
     const int stats_words = stats ? n * 4 : 0;
     const int64_t k1_threads = sum_g * 32 > stats_words ? sum_g * 32 : stats_words;
     if (k1_threads > 0) {
-        match_rowmax_kernel<<<(unsigned)((k1_threads + 255) / 256), 256, 0, st>>>(
+        match_rowmax_kernel<<<(unsigned)((k1_threads + 127) / 128), 128, 0, st>>>(
             g4, gt_offsets, n, sum_g, a4, lay, allow_low_quality ? 1 : 0, rowmax, flags, mask, stats, stats_words);
         DET_LAUNCH_OK("match_rowmax_kernel");
     }
@@ -818,12 +864,12 @@ int det_assign_sampled(const float* gt_boxes, const int32_t* gt_offsets, int n, 
     auto g4 = reinterpret_cast<const float4*>(gt_boxes);
     auto a4 = reinterpret_cast<const float4*>(anchors);
     if (sum_g > 0) {
-        const unsigned blocks = (unsigned)((sum_g * 32 + 255) / 256);
+        const unsigned blocks = (unsigned)((sum_g + kCandWarps - 1) / kCandWarps);
         if (allow_low_quality) {
-            match_rowmax_kernel<<<blocks, 256, 0, st>>>(g4, gt_offsets, n, sum_g, a4, lay, 1, rowmax, flags, nullptr, nullptr, 0);
+            match_rowmax_kernel<<<blocks, 128, 0, st>>>(g4, gt_offsets, n, sum_g, a4, lay, 1, rowmax, flags, nullptr, nullptr, 0);
             DET_LAUNCH_OK("match_rowmax_kernel");
         }
-        assign_candidates_kernel<<<blocks, 256, 0, st>>>(g4, gt_offsets, n, sum_g, a4, lay, rule, tau, rowmax, flags, stats,
+        assign_candidates_kernel<<<blocks, kCandWarps * 32, 0, st>>>(g4, gt_offsets, n, sum_g, a4, lay, rule, tau, rowmax, flags, stats,
                                                          pos_list, pos_gt, list_cap);
         DET_LAUNCH_OK("assign_candidates_kernel");
     }

@@ -66,6 +66,7 @@ struct FlatArgs {
 
 template <int MODE>
 __global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const __grid_constant__ FlatArgs g) {
+    if (MODE != kModeDense) pdl_trigger();  // det_dense_detect: the NMS kernel's CTAs may move in as SM slots free up
     long long gt = (long long)blockIdx.x * kFlatThreads + threadIdx.x;
     bool active = gt < g.thread_begin[g.num_levels];
     if (MODE == kModeDense) {
@@ -282,7 +283,70 @@ dense_decode_level_kernel(const float* __restrict__ head, int a, int c, int h, i
 }
 
 
+// ---- candidate compaction / final gather for the unfused detector path (any candidate count: the overflow route of
+// det_dense_detect and pyramids outside its limits).  One CTA per image walks the image's rows in order; a block-wide
+// ballot scan keeps the candidates (score > thr) in ROW ORDER, which is what torch.nonzero gives the oracle.
+constexpr int kCompactThreads = 512;
+
+__global__ void __launch_bounds__(kCompactThreads)
+threshold_compact_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                         const int64_t* __restrict__ classes, int64_t r, float thr, int64_t cap,
+                         int64_t* __restrict__ out_rows, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                         int64_t* __restrict__ out_classes, int32_t* __restrict__ out_counts) {
+    __shared__ int s_warp[kCompactThreads / 32];
+    __shared__ int s_base;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t in0 = (int64_t)img * r, out0 = (int64_t)img * cap;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t j0 = 0; j0 < r; j0 += kCompactThreads) {
+        const int64_t j = j0 + tid;
+        const float sc = j < r ? scores[in0 + j] : 0.0f;
+        const bool pass = j < r && sc > thr;  // NaN never passes (torch: nan > thr is False)
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = s_base, total = 0;
+#pragma unroll
+        for (int w = 0; w < kCompactThreads / 32; ++w) {
+            const int v = s_warp[w];
+            before += w < wid ? v : 0;
+            total += v;
+        }
+        const int64_t slot = before + __popc(bal & ((1u << lane) - 1u));
+        if (pass && slot < cap) {
+            out_rows[out0 + slot] = j;
+            out_boxes[out0 + slot] = boxes[in0 + j];
+            out_scores[out0 + slot] = sc;
+            out_classes[out0 + slot] = classes ? classes[in0 + j] : 0;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+    }
+    __syncthreads();
+    if (tid == 0) out_counts[img] = (int32_t)(s_base < cap ? s_base : cap);
+}
+
+__global__ void gather_detections_kernel(const int64_t* __restrict__ keep, const int32_t* __restrict__ keep_counts,
+                                         int64_t max_det, const int64_t* __restrict__ rows,
+                                         const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                         const int64_t* __restrict__ classes, int64_t cap, int64_t n,
+                                         int64_t* __restrict__ det_idx, float4* __restrict__ det_boxes,
+                                         float* __restrict__ det_scores, int64_t* __restrict__ det_classes) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * max_det) return;
+    const int64_t img = t / max_det, j = t - img * max_det;
+    if (j >= keep_counts[img]) return;  // rows past the count stay undefined, as in det_dense_detect
+    const int64_t k = keep[t];
+    const int64_t src = img * cap + k;
+    det_idx[t] = rows ? rows[src] : k;
+    det_boxes[t] = boxes[src];
+    det_scores[t] = scores[src];
+    det_classes[t] = classes ? classes[src] : 0;
+}
+
 }  // namespace det
+
 
 using namespace det;
 
@@ -304,10 +368,11 @@ static int launch_detect_nms_t(const SelectArgs& sel, int n, float thr_f, int mo
     const size_t smem = sizeof(DetectSmem<CAP, T>);
     cudaError_t e = cudaFuncSetAttribute(dense_detect_nms_kernel<CAP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dense_detect_nms_kernel)");
-    dense_detect_nms_kernel<CAP, T><<<n, T, smem, st>>>(
-        sel.cand_count, sel.cand_box, sel.cand_score, sel.cand_cls, sel.cand_id, sel.cand_cap, thr_f, mode, max_det,
-        det_idx, reinterpret_cast<float4*>(det_boxes), det_scores, det_classes, det_count, overflow_flag);
-    DET_LAUNCH_OK("dense_detect_nms_kernel");
+    // programmatic dependent launch: the CTAs take their SM slots while the select kernel drains (see common.cuh)
+    e = launch_pdl(dense_detect_nms_kernel<CAP, T>, dim3(n), dim3(T), smem, st, sel.cand_count, sel.cand_box, sel.cand_score,
+                   sel.cand_cls, sel.cand_id, sel.cand_cap, thr_f, mode, max_det, det_idx,
+                   reinterpret_cast<float4*>(det_boxes), det_scores, det_classes, det_count, overflow_flag, nullptr, nullptr);
+    if (e != cudaSuccess) return cuda_fail(e, "dense_detect_nms_kernel");
     return DET_OK;
 }
 
@@ -498,6 +563,42 @@ int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n
                                        det_count, overflow_flag, st);
     return launch_detect_nms<4096>(sel, n, thr_f, mode, max_det, det_idx, det_boxes, det_scores, det_classes, det_count,
                                    overflow_flag, st);
+}
+
+int det_threshold_compact(const float* boxes, const float* scores, const int64_t* classes, int n, int64_t r,
+                          float score_thresh, int64_t cap, int64_t* cand_rows, float* cand_boxes, float* cand_scores,
+                          int64_t* cand_classes, int32_t* cand_counts, void* stream) {
+    DET_CHECK_ARG(n >= 0 && r >= 0 && cap >= 1, "bad size");
+    if (n == 0) return DET_OK;
+    DET_CHECK_ARG(boxes && scores && cand_rows && cand_boxes && cand_scores && cand_classes && cand_counts, "null pointer");
+    if (!aligned16(boxes) || !aligned16(cand_boxes)) {
+        set_error("boxes / cand_boxes must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    threshold_compact_kernel<<<n, kCompactThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(boxes), scores, classes, r, score_thresh, cap, cand_rows,
+        reinterpret_cast<float4*>(cand_boxes), cand_scores, cand_classes, cand_counts);
+    DET_LAUNCH_OK("threshold_compact_kernel");
+    return DET_OK;
+}
+
+int det_gather_detections(const int64_t* keep, const int32_t* keep_counts, int n, int64_t max_det, const int64_t* cand_rows,
+                          const float* cand_boxes, const float* cand_scores, const int64_t* cand_classes, int64_t cap,
+                          int64_t* det_idx, float* det_boxes, float* det_scores, int64_t* det_classes, void* stream) {
+    DET_CHECK_ARG(n >= 0 && max_det >= 1 && cap >= 1, "bad size");
+    if (n == 0) return DET_OK;
+    DET_CHECK_ARG(keep && keep_counts && cand_boxes && cand_scores && det_idx && det_boxes && det_scores && det_classes,
+                  "null pointer");
+    if (!aligned16(cand_boxes) || !aligned16(det_boxes)) {
+        set_error("cand_boxes / det_boxes must be 16-byte aligned");
+        return DET_ERR_ALIGN;
+    }
+    const int64_t total = (int64_t)n * max_det;
+    gather_detections_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+        keep, keep_counts, max_det, cand_rows, reinterpret_cast<const float4*>(cand_boxes), cand_scores, cand_classes, cap, n,
+        det_idx, reinterpret_cast<float4*>(det_boxes), det_scores, det_classes);
+    DET_LAUNCH_OK("gather_detections_kernel");
+    return DET_OK;
 }
 
 }  // extern "C"

@@ -48,6 +48,7 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
     DetectSmem<CAP, T>& sm = *reinterpret_cast<DetectSmem<CAP, T>*>(smem_raw);
     using KL = KeyLayout<kSmallIdxBits>;
     const int img = blockIdx.x, tid = threadIdx.x;
+    pdl_wait();  // no-op unless launched with launch_pdl (det_dense_detect): the candidate lists are complete from here
     DET_MARK(0);
     const int cnt = cand_count[(int64_t)img * kCountStride];
     if (ext_full) {  // external tier: a negative count means "no usable list", the full path takes the image

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "det_dense_detect_workspace_bytes": (c_l, [c_i, c_l]),
     "det_dense_detect": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_d, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p,
                                c_p, c_l, c_p]),
+    "det_threshold_compact": (c_i, [c_p, c_p, c_p, c_i, c_l, c_f, c_l, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "det_gather_detections": (c_i, [c_p, c_p, c_i, c_l, c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_p]),
     "det_peer_sums_publish": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_p]),
     "det_peer_sums_collect": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_peer_sums_exchange": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.c_uint32, ctypes.c_uint32, c_l, c_p, c_p]),
@@ -141,7 +143,7 @@ def lib():
             "There is no CPU or PyTorch fallback for this package.") from e
     handle = ctypes.CDLL(_LIB_PATH)
     handle.det_abi_version.restype = c_i
-    if handle.det_abi_version() != 2:
+    if handle.det_abi_version() != 3:
         raise ImportError("det_b200: ABI version mismatch")
     _lib = handle
     return _lib

@@ -387,22 +387,35 @@ class DenseAnchorHead:
         return out
 
     def _detect_thresholded_unfused(self, heads, score_thresh, iou_thresh, max_det, mode):
-        """Same contract through decode() + det_nms_batched (any candidate count up to 131071 per image)."""
+        """Same contract through det_dense_decode -> det_threshold_compact (row-ordered candidates) -> det_nms_batched ->
+        det_gather_detections: any candidate count up to 131071 per image, library kernels only, no host sync."""
         boxes, scores, classes = self.decode(heads)
         n, R = scores.shape
-        mask = scores > score_thresh
-        counts = mask.sum(dim=1).to(torch.int32)
-        # stable partition: candidates first, in row order
-        order = torch.sort((~mask).to(torch.uint8), dim=1, stable=True).indices
-        m = max(int(counts.max().item()) if n else 0, 1)
-        sel = order[:, :m]
-        cb = torch.gather(boxes, 1, sel[..., None].expand(-1, -1, 4)).contiguous()
-        cs, cc = torch.gather(scores, 1, sel).contiguous(), torch.gather(classes, 1, sel).contiguous()
+        dev = scores.device
+        cap = max(int(R), 1)
+        rows = torch.empty((n, cap), dtype=torch.int64, device=dev)
+        cb = torch.empty((n, cap, 4), dtype=torch.float32, device=dev)
+        cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
+        cc = torch.empty((n, cap), dtype=torch.int64, device=dev)
+        counts = torch.empty((n,), dtype=torch.int32, device=dev)
+        out = {"idx": torch.empty((n, max_det), dtype=torch.int64, device=dev),
+               "boxes": torch.empty((n, max_det, 4), dtype=torch.float32, device=dev),
+               "scores": torch.empty((n, max_det), dtype=torch.float32, device=dev),
+               "classes": torch.empty((n, max_det), dtype=torch.int64, device=dev),
+               "overflow": torch.zeros((1,), dtype=torch.int32, device=dev)}
+        if n == 0 or R == 0:
+            out["count"] = torch.zeros((n,), dtype=torch.int32, device=dev)
+            return out
+        with torch.cuda.device(dev):
+            N.call("det_threshold_compact", N.ptr(boxes), N.ptr(scores), N.ptr(classes), n, R, float(score_thresh), cap,
+                   N.ptr(rows), N.ptr(cb), N.ptr(cs), N.ptr(cc), N.ptr(counts), N.stream())
         keep, cnt = nms_images(cb, cs, cc, counts, iou_thresh, max_det, mode)
-        kk = keep.clamp(0, m - 1)
-        return {"idx": torch.gather(sel, 1, kk), "boxes": torch.gather(cb, 1, kk[..., None].expand(-1, -1, 4)),
-                "scores": torch.gather(cs, 1, kk), "classes": torch.gather(cc, 1, kk), "count": cnt,
-                "overflow": torch.zeros((1,), dtype=torch.int32, device=scores.device)}
+        with torch.cuda.device(dev):
+            N.call("det_gather_detections", N.ptr(keep), N.ptr(cnt), n, max_det, N.ptr(rows), N.ptr(cb), N.ptr(cs),
+                   N.ptr(cc), cap, N.ptr(out["idx"]), N.ptr(out["boxes"]), N.ptr(out["scores"]), N.ptr(out["classes"]),
+                   N.stream())
+        out["count"] = cnt
+        return out
 
     def detect(self, heads: List[torch.Tensor], iou_thresh: float = 0.5, max_det: Optional[int] = None,
                mode: int = MODE_AUTO):

@@ -1,0 +1,12 @@
+#!/bin/bash
+# quick A/B of the training side: parity tests, then the per-kernel times of the sample-list training step (ncu launch list)
+python -m pytest tests/test_gpu_train_grid.py tests/test_gpu_train.py tests/test_gpu_determinism.py -m gpu -x -q 2>&1 | tail -2
+python profiles/scripts/prof_train_lazy.py 1024 3 > /dev/null 2>&1 || echo "plain run failed"
+ncu --metrics gpu__time_duration.sum --clock-control none --csv python profiles/scripts/prof_train_lazy.py 1024 3 2>/dev/null | python -c "
+import csv,sys
+rows=[r for r in csv.reader(sys.stdin) if len(r)>10 and r[0].isdigit()]
+last={}
+for r in rows:
+    name=r[4].split('(')[0][-40:]; last.setdefault(name,[]).append(float(r[-1]))
+for k,v in last.items():
+    if 'det::' in k or 'rpn_loss' in k or 'match' in k: print(k, [round(x/1000,1) for x in v[-3:]])"

@@ -31,7 +31,7 @@ def test_argument_counts_match_header():
 
 def test_abi_version_and_pure_queries():
     from det_b200 import _native as N
-    assert N.fn("det_abi_version")() == 2
+    assert N.fn("det_abi_version")() == 3
     assert N.fn("det_nms_workspace_bytes")(4, 1000) == 256
     assert N.fn("det_nms_workspace_bytes")(2, 25200) > 2 * 25200 * 40
     assert N.fn("det_rpn_proposals_workspace_bytes")(1, 50127) > 50127 * 40

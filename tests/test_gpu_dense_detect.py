@@ -207,3 +207,49 @@ def test_dense_detect_full_size_properties(det):
         iou = det.pairwise_iou(det.Boxes(bx), det.Boxes(bx))
         same = (cl[:, None] == cl[None, :]) & ~torch.eye(k, dtype=torch.bool, device=bx.device)
         assert float((iou * same).max()) <= 0.5 + 1e-6
+
+
+def test_threshold_compact_and_gather_kernels(det):
+    """det_threshold_compact keeps the candidates in row order (torch.nonzero order), det_gather_detections maps kept
+    candidate indices back to rows; NaN scores never pass; a cap below the candidate count truncates in row order."""
+    import det_b200._native as N
+    g = gen(21)
+    n, R = 5, 3001
+    boxes = torch.rand(n, R, 4, generator=g).cuda()
+    scores = torch.rand(n, R, generator=g)
+    scores[1] = 0.0                      # an image without candidates
+    scores[2, ::7] = float("nan")
+    scores = scores.cuda()
+    classes = torch.randint(0, 80, (n, R), generator=g).cuda()
+    for cap in (R, 100):
+        rows = torch.full((n, cap), -1, dtype=torch.int64, device="cuda")
+        cb = torch.zeros((n, cap, 4), device="cuda")
+        cs = torch.zeros((n, cap), device="cuda")
+        cc = torch.zeros((n, cap), dtype=torch.int64, device="cuda")
+        cnt = torch.zeros((n,), dtype=torch.int32, device="cuda")
+        N.call("det_threshold_compact", N.ptr(boxes), N.ptr(scores), N.ptr(classes), n, R, 0.6, cap, N.ptr(rows), N.ptr(cb),
+               N.ptr(cs), N.ptr(cc), N.ptr(cnt), N.stream())
+        for i in range(n):
+            want = torch.nonzero(scores[i] > 0.6, as_tuple=True)[0][:cap]
+            k = want.numel()
+            assert int(cnt[i]) == k
+            assert torch.equal(rows[i, :k], want) and torch.equal(cb[i, :k], boxes[i, want])
+            assert torch.equal(cs[i, :k], scores[i, want]) and torch.equal(cc[i, :k], classes[i, want])
+    # gather: keep = the first few candidates reversed
+    max_det = 8
+    keep = torch.zeros((n, max_det), dtype=torch.int64, device="cuda")
+    kc = torch.minimum(cnt, torch.tensor(max_det, dtype=torch.int32, device="cuda")).to(torch.int32)
+    for i in range(n):
+        k = int(kc[i])
+        keep[i, :k] = torch.arange(k - 1, -1, -1, device="cuda")
+    out_idx = torch.full((n, max_det), -7, dtype=torch.int64, device="cuda")
+    ob = torch.zeros((n, max_det, 4), device="cuda")
+    os_ = torch.zeros((n, max_det), device="cuda")
+    oc = torch.zeros((n, max_det), dtype=torch.int64, device="cuda")
+    N.call("det_gather_detections", N.ptr(keep), N.ptr(kc), n, max_det, N.ptr(rows), N.ptr(cb), N.ptr(cs), N.ptr(cc), cap,
+           N.ptr(out_idx), N.ptr(ob), N.ptr(os_), N.ptr(oc), N.stream())
+    for i in range(n):
+        k = int(kc[i])
+        assert torch.equal(out_idx[i, :k], rows[i, :k].flip(0)) and torch.equal(ob[i, :k], cb[i, :k].flip(0))
+        assert torch.equal(os_[i, :k], cs[i, :k].flip(0)) and torch.equal(oc[i, :k], cc[i, :k].flip(0))
+        assert bool((out_idx[i, k:] == -7).all())
