@@ -80,8 +80,11 @@ __device__ __forceinline__ void plateau_window(float g_lo, float g_hi, float a_l
     const float gc = 0.5f * (g_lo + g_hi), ac = 0.5f * (a_lo + a_hi);
     const float half = 0.5f * fabsf((g_hi - g_lo) - (a_hi - a_lo));
     const float f_lo = floorf((gc - ac - half) / s) - 1.0f, f_hi = ceilf((gc - ac + half) / s) + 1.0f;
-    lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)w);
-    hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), -1.0f);
+    // A plateau that lies beyond the feature map (a gt box sticking out of the image) is clamped ONTO the map, not cut
+    // away: the overlap falls off monotonically with the distance from the plateau, so the best position that exists is
+    // the border one.
+    lo = (int)fminf(fmaxf(f_lo, 0.0f), (float)(w - 1));
+    hi = (int)fmaxf(fminf(f_hi, (float)(w - 1)), 0.0f);
 }
 
 __global__ void __launch_bounds__(128, 10)

@@ -417,15 +417,17 @@ __device__ void subsample_image(SampleSmem& sm, int8_t* __restrict__ labels, int
         thr[c] = p >= 1.0 ? 0xffffffffu : (unsigned)(p * 4294967296.0);
         direct[c] = need[c] && want[c] > 0 && (double)want[c] + 2.0 * slack <= (double)kCandCap && r < (1 << 24);
     }
-    // a dense class is sampled by walking a random permutation of the row instead of hashing every anchor
+    // The background class is sampled by walking a random permutation of the row instead of hashing every anchor (it is
+    // the dense class of every workload on this path: O(want / density) steps; a sparse one just takes up to one full
+    // cycle, which is what hashing the row costs).  The rule is fixed per CLASS, not per density, so that the samplers
+    // that never see the whole row -- subsample_stats_kernel, subsample_lazy_kernel -- draw the very same samples:
+    // positives always by their hash keys, negatives always by the walk.
     bool walk[2];
     int pbits = 1;
     while ((1ll << pbits) < r) ++pbits;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        walk[c] = need[c] && want[c] > 0 && want[c] <= kCandCap && r < (1 << 24) && (int64_t)have[c] * 8 >= r;
-        if (walk[c]) direct[c] = false;
-    }
+    walk[0] = false;
+    walk[1] = need[1] && want[1] > 0 && want[1] <= kCandCap && r < (1 << 24);
+    if (walk[1]) direct[1] = false;
     if (direct[0] || direct[1]) {
         for (int c = tid; c < rv.ngran; c += kSampleThreads) {
             const uint4 q = rv.load(c);
@@ -579,8 +581,8 @@ subsample_stats_kernel(int8_t* __restrict__ labels, int64_t r, int num_samples, 
     const int want_pos = min(npos, pos_cap);
     const int want_neg = min(nneg, num_samples - want_pos);
     int8_t* row = labels + (int64_t)img * r;
-    const bool fast = r < (1 << 24) && npos <= min(list_cap, kCandCap) && (int64_t)npos * 8 < r &&  // sparse positives
-                      want_neg < nneg && want_neg <= kCandCap && (int64_t)nneg * 8 >= r;            // dense, thinned negatives
+    const bool fast = r < (1 << 24) && npos <= min(list_cap, kCandCap) &&  // the positives are all on the list
+                      want_neg < nneg && want_neg <= kCandCap;             // thinned negatives (same rule as subsample_image)
     if (tid == 0) s_nout = 0;
     if (!fast) {
         subsample_image(sm, labels, img, r, num_samples, pos_cap, seed);
@@ -665,7 +667,8 @@ subsample_lazy_kernel(const float4* __restrict__ gt, const int32_t* __restrict__
     const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
     const bool lq = rule.allow_lq != 0;
     const int npos = stats[img * 4 + 0];
-    const bool dense = (lq && (flags[img] & 1)) || npos > min(list_cap, kCandCap) || r >= (1 << 24);
+    const bool dense = (lq && (flags[img] & 1)) || npos > min(list_cap, kCandCap) || r >= (1 << 24) ||
+                       num_samples > kCandCap;  // (more samples than the walk's buffer: subsample_image's exact paths)
     if (tid == 0) s_nout = 0;
     __syncthreads();
     if (dense) {

@@ -345,3 +345,47 @@ def test_sample_list_only_assignment_feeds_the_same_losses(det):
     (res["cls_loss"] + res["loc_loss"]).backward()
     for x, y in zip(o_g + d_g, gb[0] + gb[1]):
         assert torch.equal(x.grad, y)
+
+
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("DET_STRESS_SEEDS", "24")))))
+def test_window_logic_stress_random_pyramids(det, seed):
+    """The closed-form windows of the grid kernels (reach / plateau / overlap windows, one position of margin) against the
+    brute-force generic matcher on random pyramids: strides, anchor sizes, aspect ratios, anchor offset 0 or 0.5,
+    non-square ragged feature maps, and gt boxes from sub-pixel to larger than the image, partly outside it.  The dense
+    grid matcher must equal det_match_anchors bit for bit; the sample-list assignment must equal the dense one."""
+    g = gen(1000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    nlev = ri(1, 4)
+    s0 = [2, 4, 8][ri(0, 2)]
+    strides = [s0 * (2 ** l) for l in range(nlev)]
+    base = float(torch.rand(1, generator=g)) * 24 + 8
+    sizes = [[base * (2 ** l)] for l in range(nlev)]
+    ratios = [[[0.5, 1.0, 2.0], [1.0], [0.33, 1.0, 3.0]][ri(0, 2)]]
+    offset = [0.0, 0.5][ri(0, 1)]
+    H, W = ri(40, 260), ri(40, 260)
+    rpn = det.RegionProposalNetwork(strides, sizes, ratios, anchor_offset=offset)
+    hw = [(-(-H // s), -(-W // s)) for s in strides]
+    at = torch.cat(rpn.anchor_generator.grid_anchors(hw, torch.device("cuda")), 0)
+    grid = rpn.anchor_generator.grid_layout(hw)
+    n = 6
+    gts = []
+    for i in range(n):
+        k = ri(0, 12)
+        scale = [2.0, 20.0, 80.0, 400.0][ri(0, 3)]
+        xy = torch.rand(k, 2, generator=g) * torch.tensor([W * 1.2, H * 1.2]) - torch.tensor([W * 0.1, H * 0.1])
+        wh = torch.rand(k, 2, generator=g) * scale + 0.05
+        gts.append(torch.cat([xy, xy + wh], 1).cuda())
+    dense = rpn.assign(at, gts, sample=False, grid=grid)
+    generic = rpn.assign(at, gts, sample=False)
+    assert torch.equal(dense.labels, generic.labels) and torch.equal(dense.matched, generic.matched)
+    rpn.batch_size_per_image = 64
+    d2 = rpn.assign(at, gts, seed=5, grid=grid)
+    table, off = rpn.anchor_matcher.pack_gt(gts, at.device)
+    lazy = rpn.assign_sampled(at, table, off, n, grid, seed=5)
+    assert torch.equal(lazy.sample_count, d2.sample_count)
+    want = _sample_sets(d2.samples, d2.sample_count)
+    got = _sample_sets(lazy.samples, lazy.sample_count, lazy.sample_gt)
+    for i in range(n):
+        assert torch.equal(got[i][0], want[i][0]) and torch.equal(got[i][1], want[i][1]), i
+        rows, pos = got[i][0].long(), got[i][1] == 1
+        assert torch.equal(got[i][2][pos].long(), d2.matched[i].cpu()[rows][pos]), i
