@@ -253,3 +253,26 @@ def test_threshold_compact_and_gather_kernels(det):
         assert torch.equal(out_idx[i, :k], rows[i, :k].flip(0)) and torch.equal(ob[i, :k], cb[i, :k].flip(0))
         assert torch.equal(os_[i, :k], cs[i, :k].flip(0)) and torch.equal(oc[i, :k], cc[i, :k].flip(0))
         assert bool((out_idx[i, k:] == -7).all())
+
+
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("DET_STRESS_SEEDS", "12")))))
+def test_dense_detect_stress_random_heads(det, O, seed):
+    """Random dense heads through det_dense_detect: image size, classes, objectness bias (from nothing to thousands of
+    candidates per image), thresholds, max_det, candidate cap, gate on/off, quantised logits (ties), NMS branch: rows, counts,
+    boxes, scores and classes bit-exact against the oracle on the decoded values; overflowing images take the exact route."""
+    g = gen(11000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    rf = lambda lo, hi: float(torch.rand(1, generator=g)) * (hi - lo) + lo
+    image = 32 * ri(2, 8)
+    C = [1, 3, 20, 80][ri(0, 3)]
+    n = ri(1, 5)
+    dh = det.DenseAnchorHead(STRIDES, WH, C)
+    heads = make_heads(n, image, C, 500 + seed, rf(-5.0, 0.5))
+    if ri(0, 2) == 0:
+        heads = [(h * 4).round() / 4 for h in heads]
+    heads = [h.cuda() for h in heads]
+    thr, iou = rf(0.02, 0.5), rf(0.2, 0.8)
+    max_det = [1, 30, 300, 1000][ri(0, 3)]
+    cap = [256, 1024, 4096][ri(0, 2)]
+    r = dh.detect_thresholded(heads, thr, iou, max_det=max_det, cand_cap=cap, gate=bool(ri(0, 1)), check=True)
+    check_against_oracle(dh, O, heads, r, thr, iou, max_det)

@@ -315,3 +315,41 @@ def test_large_path_topk_tier_bad_category_anywhere_is_reported(det):
     c[4000] = 40000  # outside the key range
     keep, cnt = det.nms_images(b[None].cuda(), s[None].cuda(), c[None].cuda(), None, 0.5, 100)
     assert int(cnt) == -1
+
+
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("DET_STRESS_SEEDS", "16")))))
+def test_nms_images_stress_random_batches(det, O, seed):
+    """Random batches through det_nms_batched: image counts around every path boundary (warp / CTA / large path, the
+    1000-box branch rule), 1..200 categories with skewed sizes, frames from crowded to empty, negative coordinates, quantised
+    coordinates and scores (ties), an occasional NaN / degenerate box, random max_out: kept indices and counts bit-exact."""
+    g = gen(9000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    rf = lambda lo, hi: float(torch.rand(1, generator=g)) * (hi - lo) + lo
+    n_img = ri(1, 5)
+    m = [40, 300, 1100, 4200, 6000][ri(0, 4)]
+    ncat = [1, 2, 7, 80, 200][ri(0, 4)]
+    frame = [60.0, 300.0, 2000.0][ri(0, 2)]
+    boxes = torch.stack([rand_boxes(m, frame, g, rf(0.05, 0.6)) for _ in range(n_img)]) - (frame * 0.3 if ri(0, 2) == 0 else 0.0)
+    if ri(0, 1):
+        boxes = boxes.round()
+    scores = torch.rand(n_img, m, generator=g)
+    if ri(0, 2) == 0:
+        scores = (scores * 32).round() / 32
+    cats = (torch.rand(n_img, m, generator=g) ** [1.0, 3.0][ri(0, 1)] * ncat).long().clamp(max=ncat - 1)  # skewed sizes
+    if ri(0, 3) == 0:
+        boxes[0, ri(0, m - 1), ri(0, 3)] = float("nan")
+    if ri(0, 3) == 0:
+        j = ri(0, m - 1)
+        boxes[0, j, 2:] = boxes[0, j, :2]  # zero-area box
+    counts = torch.tensor([[m, ri(0, m), min(m, 1000), min(m, 1001), ri(0, m)][i] for i in range(n_img)], dtype=torch.int32)
+    thr = rf(0.1, 0.9)
+    max_out = [None, 1, 100, 1000][ri(0, 3)]
+    keep, kc = det.nms_images(boxes.cuda(), scores.cuda(), cats.cuda(), counts.cuda(), thr, max_out)
+    keep, kc = keep.cpu(), kc.cpu()
+    for i in range(n_img):
+        k = int(counts[i])
+        want = O.batched_nms(boxes[i, :k], scores[i, :k], cats[i, :k], thr)
+        if max_out is not None:
+            want = want[:max_out]
+        assert int(kc[i]) == want.numel(), (i, int(kc[i]), want.numel())
+        assert torch.equal(keep[i, :want.numel()], want), i

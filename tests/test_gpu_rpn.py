@@ -149,3 +149,33 @@ def test_find_top_rpn_proposals_equal_logits_straddle_the_topk_cut(det, O):
         for i in range(n):
             assert torch.equal(got[i].objectness_logits.cpu(), want[i][1])
             assert torch.equal(got[i].proposal_boxes.tensor.cpu(), want[i][0])
+
+
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("DET_STRESS_SEEDS", "12")))))
+def test_find_top_rpn_proposals_stress(det, O, seed):
+    """Random proposal-selection problems: pyramid size, delta scale (tiny to image-sized boxes), pre/post top-k around the
+    level sizes, NMS threshold, min box size, ragged image sizes, quantised logits (ties at the cuts) and an occasional
+    non-finite proposal in eval mode: kept boxes, logits and counts bit-exact on identical inputs."""
+    g = gen(13000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    rf = lambda lo, hi: float(torch.rand(1, generator=g)) * (hi - lo) + lo
+    img = 64 * ri(1, 5)
+    n = ri(1, 4)
+    obj, dlt = _heads(n, img, g, rf(0.05, 1.5))
+    if ri(0, 2) == 0:
+        obj = [(o * 2).round() / 2 for o in obj]
+    anchors, lg, dl, props = _oracle_decode(O, obj, dlt, img)
+    if ri(0, 3) == 0:
+        props[ri(0, len(props) - 1)][0, 0, ri(0, 3)] = float("inf")
+    pre = [5, 60, 1000, 12000][ri(0, 3)]
+    post = [1, 20, 300, 2000][ri(0, 3)]
+    thr = rf(0.3, 0.9)
+    min_size = [0.0, 0.0, 4.0, 20.0][ri(0, 3)]
+    sizes = [(img - ri(0, 30), img - ri(0, 30)) for _ in range(n)]
+    want = O.find_top_rpn_proposals([p.clone() for p in props], lg, sizes, thr, pre, post, min_size, False)
+    got = det.find_top_rpn_proposals([p.cuda() for p in props], [l.cuda() for l in lg], sizes, thr, pre, post, min_size, False)
+    for i in range(n):
+        wb, ws = want[i]
+        assert len(got[i]) == wb.shape[0], (i, len(got[i]), wb.shape[0])
+        assert torch.equal(got[i].objectness_logits.cpu(), ws), i
+        assert torch.equal(got[i].proposal_boxes.tensor.cpu(), wb), i

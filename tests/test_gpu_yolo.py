@@ -117,12 +117,38 @@ def test_dense_head_detect_three_levels(det, O):
 
 
 # ---- warp-per-class fast path (csrc/yolo_fast.cuh): small clipped grids ---------------------------------------------
+def _select_nms_forced(O, boxes, scores, thr, iou, max_det, mode):
+    """yolo_select_nms with one branch of the reference's batched_nms forced (det_nms_batched's `mode`): 1 = per category
+    (torchvision's vanilla loop), 2 = coordinate-offset trick.  Built from the oracle's own primitives."""
+    C = scores.shape[1]
+    pi, ci = torch.nonzero(scores > thr, as_tuple=True)
+    cb, cs = boxes[pi].float(), scores[pi, ci]
+    if cb.numel() == 0:
+        keep = torch.empty((0,), dtype=torch.int64)
+    elif mode == 2:
+        span = cb.max() + torch.tensor(1).to(cb)
+        keep = O.nms(cb + (ci.to(cb) * span)[:, None], cs, iou)
+    else:
+        hit = torch.zeros_like(cs, dtype=torch.bool)
+        for c in torch.unique(ci):
+            members = torch.nonzero(ci == c, as_tuple=True)[0]
+            hit[members[O.nms(cb[members], cs[members], iou)]] = True
+        kept = torch.nonzero(hit, as_tuple=True)[0]
+        keep = kept[O.stable_desc_order(cs[kept])]
+    if max_det is not None:
+        keep = keep[:max_det]
+    return (pi[keep] * C + ci[keep]), cb[keep], cs[keep], ci[keep]
+
+
 def _check_detect(det, O, yh, head, thr, iou, max_det=None, mode=0):
     r = yh.detect(head.cuda(), thr, iou, max_det=max_det, return_dense=True, mode=mode)
     gb, gs = r["dense_boxes"].cpu(), r["dense_scores"].cpu()
     cnt, flat, kb, ks = r["count"].cpu(), r["flat"].cpu(), r["boxes"].cpu(), r["scores"].cpu()
     for i in range(head.shape[0]):
-        wf, wb, ws, _ = O.yolo_select_nms(gb[i], gs[i], thr, iou, max_det=max_det)
+        if mode == 0:
+            wf, wb, ws, _ = O.yolo_select_nms(gb[i], gs[i], thr, iou, max_det=max_det)
+        else:
+            wf, wb, ws, _ = _select_nms_forced(O, gb[i], gs[i], thr, iou, max_det, mode)
         k = int(cnt[i])
         assert k == wf.numel(), (i, k, wf.numel())
         assert torch.equal(flat[i, :k], wf), i
@@ -250,3 +276,32 @@ def test_dense_decode_all_levels_one_launch(det, O, n, C, sizes):
         torch.testing.assert_close(gs[:, off:off + r].cpu(), os_, rtol=1e-5, atol=1e-6, equal_nan=True)
         off += r
     assert off == gb.shape[1]
+
+
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("DET_STRESS_SEEDS", "16")))))
+def test_yolo_fused_kernel_stress_random_shapes(det, O, seed):
+    """Random grid shapes (fast path and generic kernel), logit scales, thresholds, max_det, clip on/off, NMS branch forced or
+    automatic, occasional ties and non-finite logits: kept ids, counts, boxes and scores bit-exact against the oracle NMS on
+    the GPU's own decoded values (every tier of the tier cut, the slow exact path and the merge are hit across the seeds)."""
+    g = gen(7000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    rf = lambda lo, hi: float(torch.rand(1, generator=g)) * (hi - lo) + lo
+    S, B = ri(1, 9), ri(1, 3)
+    C = [1, 3, 20, 32, 7][ri(0, 4)]
+    if S * S * B * C > 4096:
+        C = max(1, 4096 // (S * S * B))
+    hw = (32 * ri(2, 16), 32 * ri(2, 16))
+    clip = ri(0, 3) > 0
+    yh = det.YoloGridHead(S, B, C, hw, clip=clip)
+    n = ri(1, 12)
+    head = torch.randn(n, S, S, B * 5 + C, generator=g) * rf(0.3, 2.5)
+    head[..., 4::5][..., :B] += rf(-2.0, 2.0)                     # confidence bias: from nearly nothing to everything passing
+    if ri(0, 3) == 0:                                             # ties: identical cells
+        head[:, :, :, :] = head[:, :1, :1, :]
+    if ri(0, 4) == 0:
+        head.view(-1)[ri(0, head.numel() - 1)] = float("nan")
+    if ri(0, 6) == 0:
+        head.view(-1)[ri(0, head.numel() - 1)] = float("inf")
+    thr, iou = rf(0.0, 0.6), rf(0.05, 0.9)
+    max_det = [None, 1, 5, 50, 300][ri(0, 4)]
+    _check_detect(det, O, yh, head, thr, iou, max_det=max_det, mode=ri(0, 2))
