@@ -438,6 +438,25 @@ def extras_train(det, dev, world, peak, quick):
         ms_graph = time_graph([graph_step, graph_step], 3 if quick else 10)
     except Exception as e:  # noqa: BLE001
         out["train_rpn_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+    # ... and with the step's all-reduce inside the graph: det_peer_sums_exchange_dev (NVLink peer memory, step stamp on the
+    # device) publishes this step's sums to every rank and collects the previous step's world sum -- a per-step collective
+    # without an NCCL launch, which is what lets the replayed step scale
+    ms_graph_peer = None
+    try:
+        barrier(world)
+        psr = det.dist.PeerSums(dev, graph_safe=True)
+
+        def graph_step_peer():
+            asg = assign_lazy()
+            keep.append(asg)
+            psr.exchange(loss_only(asg))
+
+        ms_graph_peer = time_graph([graph_step_peer, graph_step_peer], 3 if quick else 10)
+        psr.flush()
+        psr.check()
+        barrier(world)
+    except Exception as e:  # noqa: BLE001
+        out["train_rpn_graph_peer_error"] = f"{type(e).__name__}: {e}"[:200]
     # the dense-output forms for their rooflines: assignment writes 9R bytes per image (labels + matched), the dense
     # fused loss writes both gradient tensors in full
     ms_assign_generic = time_region(lambda: m.match_packed(gtb2, off2, nb, anchors), it)
@@ -457,6 +476,8 @@ def extras_train(det, dev, world, peak, quick):
                     "one step late) -- the launches of RegionProposalNetwork.forward(training)",
         "ms_step": ms_step, "ms_assign_sampled": ms_assign_lazy, "ms_assign": ms_match, "ms_loss_fwd_bwd": ms_loss,
         "ms_step_graph_no_collective": ms_graph,
+        "ms_step_graph_peer_allreduce": ms_graph_peer,
+        "images_per_s_total_graph_peer_allreduce": (world * nb / ms_graph_peer * 1e3) if ms_graph_peer else None,
         "ms_step_dense_labels": ms_step_dense,
         "dense_labels_note": "ms_step_dense_labels / ms_assign: the same step with det_match_grid writing labels + matched "
                              "index of ALL anchors (the reference signature of label_and_sample_anchors) + subsample",
@@ -592,7 +613,9 @@ def train_summary(extras, world):
         out["rpn_r50127"] = {"ms_step": _r(r.get("ms_step")), "ms_step_dense_labels": _r(r.get("ms_step_dense_labels")),
                              "ms_assign_sampled": _r(r.get("ms_assign_sampled")), "ms_assign": _r(r.get("ms_assign")),
                              "ms_loss": _r(r.get("ms_loss_fwd_bwd")), "ms_graph": _r(r.get("ms_step_graph_no_collective")),
+                             "ms_graph_peer": _r(r.get("ms_step_graph_peer_allreduce")),
                              "img_s_total": _r(r.get("images_per_s_total"), 0),
+                             "img_s_total_graph_peer": _r(r.get("images_per_s_total_graph_peer_allreduce"), 0),
                              "assign_frac": _r(r["assign_roofline"]["frac"], 3), "loss_frac": _r(r["loss_roofline"]["frac"], 3),
                              "batch": r.get("batch")}
     g = extras.get("train_grid_b1024")
@@ -657,6 +680,16 @@ def peer_equals_nccl(det, dev, world):
             got.append(prev.clone())
     got.append(ps.flush().clone())
     ps.check()
+    # the graph-safe form (step stamp on the device): `out` holds the previous step's world sum from the second step on
+    psg = det.dist.PeerSums(dev, graph_safe=True)
+    for k, v in enumerate(vecs):
+        prev = psg.exchange(v)
+        if k > 0:
+            got.append(prev.clone())
+            want.append(want[k - 1])
+    got.append(psg.flush().clone())
+    want.append(want[len(vecs) - 1])
+    psg.check()
     for g_, w_ in zip(got, want):
         ok = ok and bool(torch.equal(g_, w_) or torch.allclose(g_, w_, rtol=1e-6, atol=0.0))
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)

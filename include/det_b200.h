@@ -416,6 +416,12 @@ DET_API int det_yolo_loss_peer(const float* head, const int8_t* labels, const in
  * out (nothing is collected while stamp <= lag). */
 DET_API int det_peer_sums_exchange(const float* sums, float* out, int width, int rank, int world, const void* peers_dev,
                            int slots, uint32_t stamp, uint32_t lag, int64_t timeout_ns, int32_t* error_flag, void* stream);
+/* det_peer_sums_exchange with the step stamp kept on the device: the kernel uses ++(*stamp_counter) (uint32, zero before
+ * the first step) as this step's stamp, so the call can be captured in a CUDA graph and replayed -- every rank must
+ * replay the same number of times.  `out` receives the world sum of step stamp - lag (untouched on the first steps). */
+DET_API int det_peer_sums_exchange_dev(const float* sums, float* out, int width, int rank, int world, const void* peers_dev,
+                               int slots, uint32_t* stamp_counter, uint32_t lag, int64_t timeout_ns, int32_t* error_flag,
+                               void* stream);
 
 #ifdef __cplusplus
 }

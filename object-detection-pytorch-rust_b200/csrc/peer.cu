@@ -39,6 +39,24 @@ peer_sums_exchange_kernel(const float* __restrict__ sums, float* __restrict__ ou
         peer_collect(out, width, world, peers[rank], (int)((stamp - lag) % (uint32_t)slots), stamp - lag, timeout_ns, error_flag);
 }
 
+// the same with the step stamp kept on the device (++*stamp_counter): a captured CUDA graph cannot change its kernel
+// arguments from replay to replay, so the step number has to live in memory
+__global__ void __launch_bounds__(32)
+peer_sums_exchange_dev_kernel(const float* __restrict__ sums, float* __restrict__ out, int width, int rank, int world,
+                              float* const* __restrict__ peers, int slots, uint32_t* __restrict__ stamp_counter, uint32_t lag,
+                              long long timeout_ns, int32_t* __restrict__ error_flag) {
+    uint32_t stamp = 0;
+    if (threadIdx.x == 0) {
+        stamp = *stamp_counter + 1u;
+        *stamp_counter = stamp;
+    }
+    stamp = __shfl_sync(0xffffffffu, stamp, 0);
+    peer_publish(sums, width, rank, world, peers, (int)(stamp % (uint32_t)slots), stamp);
+    __syncwarp();
+    if (stamp > lag)
+        peer_collect(out, width, world, peers[rank], (int)((stamp - lag) % (uint32_t)slots), stamp - lag, timeout_ns, error_flag);
+}
+
 }  // namespace det
 
 using namespace det;
@@ -79,6 +97,20 @@ int det_peer_sums_exchange(const float* sums, float* out, int width, int rank, i
                                                                reinterpret_cast<float* const*>(peers_dev), slots, stamp, lag,
                                                                timeout_ns, error_flag);
     DET_LAUNCH_OK("peer_sums_exchange_kernel");
+    return DET_OK;
+}
+
+int det_peer_sums_exchange_dev(const float* sums, float* out, int width, int rank, int world, const void* peers_dev,
+                               int slots, uint32_t* stamp_counter, uint32_t lag, int64_t timeout_ns, int32_t* error_flag,
+                               void* stream) {
+    DET_CHECK_ARG(sums && out && peers_dev && stamp_counter, "null pointer");
+    DET_CHECK_ARG(width >= 1 && width <= kPeerMaxWidth, "width must be in [1, 12]");
+    DET_CHECK_ARG(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank / world (<= 32)");
+    DET_CHECK_ARG(slots >= 4 && lag >= 1 && (int)lag <= slots - 4 + 1 && timeout_ns > 0, "slots >= 4, 1 <= lag <= slots - 3");
+    peer_sums_exchange_dev_kernel<<<1, 32, 0, as_stream(stream)>>>(sums, out, width, rank, world,
+                                                                   reinterpret_cast<float* const*>(peers_dev), slots,
+                                                                   stamp_counter, lag, timeout_ns, error_flag);
+    DET_LAUNCH_OK("peer_sums_exchange_dev_kernel");
     return DET_OK;
 }
 

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "det_peer_sums_publish": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_p]),
     "det_peer_sums_collect": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_peer_sums_exchange": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, ctypes.c_uint32, ctypes.c_uint32, c_l, c_p, c_p]),
+    "det_peer_sums_exchange_dev": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_p, ctypes.c_uint32, c_l, c_p, c_p]),
     "det_yolo_loss_peer": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_f, c_f, c_p, c_p,
                                  c_p, c_p, c_p, c_p]),
     "det_roi_levels": (c_i, [c_p, c_l, c_i, c_i, c_f, c_i, c_p, c_p]),

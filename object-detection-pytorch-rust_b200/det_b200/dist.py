@@ -106,8 +106,9 @@ class PeerSums:
     RECORD = 16
 
     def __init__(self, device, width: int = 8, timeout_s: float = 20.0, graph_safe: bool = False):
-        """graph_safe=True keeps the step counter on the device (fused path only: det_yolo_loss_peer increments it), so the
-        training step can be captured in a CUDA graph and replayed -- every rank must replay the same number of times."""
+        """graph_safe=True keeps the step counter on the device (exchange() -> det_peer_sums_exchange_dev, and the fused
+        path det_yolo_loss_peer, increment it themselves), so the training step can be captured in a CUDA graph and
+        replayed -- every rank must replay the same number of times."""
         from . import _native as N
         self._device_stamps = bool(graph_safe)
         self._N = N
@@ -167,6 +168,16 @@ class PeerSums:
         N = self._N
         assert sums.is_cuda and sums.dtype == torch.float32 and sums.numel() >= self.width
         assert self._collected == self.step, "do not mix exchange() with publish() / collect()"
+        if self._device_stamps:
+            # graph-safe form: the step stamp is a device counter the kernel increments itself, `out` is one fixed buffer
+            # that every step overwrites with the previous step's world sum (zeros until the second step)
+            if not hasattr(self, "_stamp_dev"):
+                self._stamp_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            out = self._out[0]
+            with torch.cuda.device(self.device):
+                N.call("det_peer_sums_exchange_dev", N.ptr(sums), N.ptr(out), self.width, self.rank, self.world,
+                       N.ptr(self.peers), self.SLOTS, N.ptr(self._stamp_dev), 1, self.timeout_ns, N.ptr(self.error), N.stream())
+            return out
         self.step += 1
         out = self._out[self.step & 1]
         with torch.cuda.device(self.device):

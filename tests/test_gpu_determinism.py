@@ -154,3 +154,32 @@ def test_peer_exchange_single_rank_is_deterministic(det):
         assert torch.equal(got, vec + step)
     ps.flush()
     ps.check()
+
+
+def test_peer_exchange_graph_safe_replays(det):
+    """det_peer_sums_exchange_dev (step stamp on the device): eager calls and CUDA-graph replays advance the same counter;
+    every step returns the previous step's sum; flush() collects the last one (single rank: sum == own vector)."""
+    dev = torch.device("cuda")
+    ps = det.dist.PeerSums(dev, graph_safe=True)
+    vec = torch.arange(8, dtype=torch.float32, device=dev) + 0.5
+    out = ps.exchange(vec)            # step 1: nothing to collect yet
+    vec += 1.0
+    out = ps.exchange(vec)            # step 2: returns step 1's vector
+    assert torch.equal(out, torch.arange(8, dtype=torch.float32, device=dev) + 0.5)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        ps.exchange(vec)              # step 3 (warm-up outside capture)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        vec.add_(1.0)
+        res = ps.exchange(vec)
+    for rep in range(20):             # steps 4..23
+        graph.replay()
+        torch.cuda.synchronize()
+        want = torch.arange(8, dtype=torch.float32, device=dev) + 0.5 + 1.0 + rep  # the vector published one step earlier
+        assert torch.equal(res, want), rep
+    assert torch.equal(ps.flush(), vec)
+    ps.check()
