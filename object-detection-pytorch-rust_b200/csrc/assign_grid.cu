@@ -358,7 +358,7 @@ __device__ __forceinline__ void match_one(const float4 gb, float rm, int t, cons
 }
 
 template <int A, bool DENSE>
-__global__ void __launch_bounds__(kGridWarps * 32, A <= 3 ? 4 : 2)
+__global__ void __launch_bounds__(kGridWarps * 32, A <= 3 ? 3 : 2)
 match_grid_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_off, const float4* __restrict__ anchors,
                   int n, int imgs, int64_t r, GridLayoutDev lay, MatchRule rule, const float* __restrict__ rowmax,
                   const int32_t* __restrict__ flags, const uint32_t* __restrict__ mask, int64_t* __restrict__ matched,
@@ -385,6 +385,24 @@ match_grid_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_
         aa[a] = box_area(ab[a]);
     }
     const int nvalid = __popc(__ballot_sync(FULLMASK, valid));
+    // Output plan.  A lane computes the A anchors of ONE position, which in memory are A consecutive entries followed by the
+    // next position's: stored from the computing lane, a warp store would touch every sector of the tile A times with a
+    // third of it each (the L1/TEX pipe was the busiest unit of this kernel: 78 %).  Instead the tile's 32 * A results
+    // pass through a per-warp shared-memory patch in memory order (entry e = lane * A + a: conflict-free both ways) and
+    // are stored A times as 32 CONSECUTIVE entries: entry e = k * 32 + lane lives in tile row e / (8A), column e % (8A).
+    __shared__ int s_idx[kGridWarps][32 * A];
+    __shared__ int8_t s_lab[kGridWarps][32 * A];
+    int* my_idx = s_idx[threadIdx.x >> 5];
+    int8_t* my_lab = s_lab[threadIdx.x >> 5];
+    int64_t eoff[A];   // element offset of entry k * 32 + lane from the image's row start (valid entries only)
+    bool eok[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        const int e = k * 32 + lane, er = e / (kTileW * A), ec = e - er * (kTileW * A);
+        const int ey = (tl / L.tiles_x) * kTileH + er, ex = (tl % L.tiles_x) * kTileW + ec / A;
+        eok[k] = ey < L.h && ex < L.w;
+        eoff[k] = L.first_row + ((int64_t)ey * L.w + ex) * A + (ec - (ec / A) * A);
+    }
     const int lab_none = rule.lab[0];  // label of an anchor that overlaps no gt box (IoU 0): bucket (-inf, thr[0])
     const float thr0 = rule.thr[0], thr1 = rule.thr[1];  // the reference's rules have one or two thresholds (thr[i >= nthr] = +inf)
     const int lab1 = rule.lab[1], lab2 = rule.lab[2];
@@ -406,13 +424,15 @@ match_grid_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_
         if (todo == 0u && !(fl & kFlagManyGt) && !promote_all) {
             // no gt box reaches this tile (the usual case on the fine levels; also an image without gt,
             // matcher.py:67-77): every anchor has IoU 0 with every box -- match 0, the label of the lowest bucket
-            if (DENSE && valid) {
+            if (DENSE) {
+                const int64_t ob = (int64_t)img * r;
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    matched[o + a] = 0;
-                    labels[o + a] = (int8_t)lab_none;
-                    if (matched_iou) matched_iou[o + a] = 0.0f;
-                }
+                for (int k = 0; k < A; ++k)
+                    if (eok[k]) {
+                        matched[ob + eoff[k]] = 0;
+                        labels[ob + eoff[k]] = (int8_t)lab_none;
+                        if (matched_iou) matched_iou[ob + eoff[k]] = 0.0f;
+                    }
             }
             // (a rule whose lowest bucket is positive makes positives dense: the list overflows by construction and the
             //  sampler takes its generic path, so untouched tiles only count)
@@ -490,12 +510,24 @@ match_grid_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_
         }
         const int tot_pos = stats ? __reduce_add_sync(FULLMASK, my_pos) : 0;
         const int tot_ign = stats ? __reduce_add_sync(FULLMASK, my_ign) : 0;
-        if (DENSE && valid) {
+        if (DENSE) {
+            __syncwarp();  // the previous image's reads of the patch are done
 #pragma unroll
             for (int a = 0; a < A; ++a) {
-                matched[o + a] = bidx[a];
-                labels[o + a] = (int8_t)lab[a];
-                if (matched_iou) matched_iou[o + a] = best[a];
+                my_idx[lane * A + a] = bidx[a];
+                my_lab[lane * A + a] = (int8_t)lab[a];
+            }
+            __syncwarp();
+            const int64_t ob = (int64_t)img * r;
+#pragma unroll
+            for (int k = 0; k < A; ++k)
+                if (eok[k]) {
+                    matched[ob + eoff[k]] = my_idx[k * 32 + lane];
+                    labels[ob + eoff[k]] = my_lab[k * 32 + lane];
+                }
+            if (matched_iou && valid) {  // (optional output, off the hot path: stored from the computing lane)
+#pragma unroll
+                for (int a = 0; a < A; ++a) matched_iou[o + a] = best[a];
             }
         }
         if (stats) {
