@@ -600,6 +600,38 @@ def extras_iou(det, dev, peak, quick):
                              "pair_ious_per_s": m * m / ms * 1e3}}
 
 
+def extras_proposals(det, dev, peak, quick):
+    """RPN inference path of the reference (rpn.py:299-328 -> models/utils.py:9-109): NCHW head -> decode of all pyramid levels
+    (det_rpn_decode) -> find_top_rpn_proposals for the whole batch (det_rpn_proposals), reference defaults in eval mode
+    (pre_nms_topk 12000 per level, post_nms_topk 2000, NMS 0.7), FPN-18 at 448x448: R = 50127 anchors."""
+    n = 16 if quick else 64
+    strides = [4, 8, 16, 32, 64]
+    rpn = det.RegionProposalNetwork(strides)
+    g = torch.Generator(device=dev).manual_seed(6)
+    obj = [torch.randn(n, 3, 448 // s, 448 // s, device=dev, generator=g) for s in strides]
+    dlt = [torch.randn(n, 12, 448 // s, 448 // s, device=dev, generator=g) * 0.4 for s in strides]
+    sizes = torch.tensor([[448, 448]] * n, dtype=torch.int32, device=dev)
+
+    def run():
+        logits, boxes, level_sizes = rpn.decode_heads(obj, dlt)
+        return det.rpn_proposals_batched(boxes, logits, level_sizes, sizes, 0.7, 12000, 2000, 0.0)
+
+    out = run()
+    ms = time_graph([run], 3 if quick else 10)
+    ms_dec = time_graph([lambda: rpn.decode_heads(obj, dlt)], 5 if quick else 20)
+    R = 50127
+    dec_bytes = n * 40 * R
+    return {"rpn_proposals_r50127": {
+        "workload": f"RPN head (NCHW, 5 levels, R=50127) -> decode + find_top_rpn_proposals (pre 12000/level, post 2000, NMS 0.7), "
+                    f"batch {n}, replayed from a CUDA graph",
+        "ms": ms, "images_per_s": n / ms * 1e3, "kept_per_image": float(out[2].float().mean()),
+        "ms_decode": ms_dec,
+        "decode_roofline": {"bound": "hbm", "achieved": dec_bytes / ms_dec / 1e6, "peak": peak, "unit": "GB/s",
+                            "frac": dec_bytes / ms_dec / 1e6 / peak, "algorithmic_bytes": dec_bytes,
+                            "formula": "N * 40R: 4R logits + 16R deltas read, 4R logits + 16R boxes written, anchors "
+                                       "synthesised (SURVEY 8d counts 36R without the logit copy)"}}}
+
+
 def _r(x, nd=4):
     return None if x is None else round(float(x), nd)
 
@@ -643,6 +675,9 @@ def others_summary(extras):
     p = extras.get("pairwise_iou")
     if p:
         out["pairwise_iou_20k"] = _r(p["roofline"]["frac"], 3)
+    q = extras.get("rpn_proposals_r50127")
+    if q:
+        out["rpn_decode_b64"] = _r(q["decode_roofline"]["frac"], 3)
     return out
 
 
@@ -876,6 +911,7 @@ def main():
             if world == 1 or rank == 0:
                 extras.update(extras_dense(det, dev, peak, args.quick))
                 extras.update(extras_iou(det, dev, peak, args.quick))
+                extras.update(extras_proposals(det, dev, peak, args.quick))
         except Exception as e:  # noqa: BLE001
             extras["error"] = f"{type(e).__name__}: {e}"
         barrier(world)

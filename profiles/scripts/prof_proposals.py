@@ -8,6 +8,8 @@ import torch
 import det_b200 as det
 from oracle import ref_torch as O
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+PRE = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+POST = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 dev = torch.device("cuda", 0)
 strides = [4, 8, 16, 32, 64]
 rpn = det.RegionProposalNetwork(strides)
@@ -18,7 +20,7 @@ obj_d, dlt_d = [t.to(dev) for t in obj], [t.to(dev) for t in dlt]
 sizes = torch.tensor([[448, 448]] * n, dtype=torch.int32, device=dev)
 def run():
     logits, boxes, level_sizes = rpn.decode_heads(obj_d, dlt_d)
-    return det.rpn_proposals_batched(boxes, logits, level_sizes, sizes, 0.7, 2000, 1000, 0.0)
+    return det.rpn_proposals_batched(boxes, logits, level_sizes, sizes, 0.7, PRE, POST, 0.0)
 for _ in range(3): out = run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -43,7 +45,7 @@ props, lgs = [], []
 for l in range(5):
     lg, dl = O.head_to_hwa(obj[l][:2], dlt[l][:2])
     props.append(torch.stack([O.apply_deltas(dl[i], anchors[l]) for i in range(2)])); lgs.append(lg)
-want = O.find_top_rpn_proposals(props, lgs, [(448, 448)] * 2, 0.7, 2000, 1000, 0.0, False)
+want = O.find_top_rpn_proposals(props, lgs, [(448, 448)] * 2, 0.7, PRE, POST, 0.0, False)
 dt = time.perf_counter() - t0
 print(f"CPU oracle: {dt / 2 * 1e3:.1f} ms per image ({torch.get_num_threads()} threads)")
 ob, os_, cnt, flag = out
