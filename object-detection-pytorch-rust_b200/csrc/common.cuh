@@ -172,8 +172,21 @@ static __device__ long long g_phase_block[64][16];  // the same stamps for the f
         if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clock[i] = clock64(); \
         if (blockIdx.x < 64 && threadIdx.x == 0) g_phase_block[blockIdx.x][(i) & 15] = clock64(); \
     } while (0)
+// accumulating form for phases inside loops: DET_ACC_BEGIN() once, DET_ACC(i) adds the cycles since the previous stamp
+static __device__ long long g_phase_acc[16];
+#define DET_ACC_BEGIN() long long det_acc_t = clock64()
+#define DET_ACC(i)                                        \
+    do {                                                  \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {        \
+            const long long det_acc_n = clock64();        \
+            g_phase_acc[i] += det_acc_n - det_acc_t;      \
+            det_acc_t = det_acc_n;                        \
+        }                                                 \
+    } while (0)
 #else
 #define DET_MARK(i) do { } while (0)
+#define DET_ACC_BEGIN() do { } while (0)
+#define DET_ACC(i) do { } while (0)
 #endif
 
 #endif  // __CUDACC__

@@ -186,12 +186,14 @@ __device__ int warp_segment_nms(const float4* sbox, const float* sarea, uint8_t*
                 }
             }
         }
-        unsigned rem = am, keepmask = 0;  // (c)
-        while (rem) {
-            const int l = __ffs(rem) - 1;
-            keepmask |= 1u << l;
+        // (c) only lanes that suppress some survivor of the chunk can change anything: visit those, in order
+        unsigned keepmask = am;
+        unsigned nz = (__ballot_sync(FULL, row != 0u) | __reduce_or_sync(FULL, col)) & am;
+        while (nz) {
+            const int l = __ffs(nz) - 1;
+            nz &= nz - 1;
             const unsigned killed = __shfl_sync(FULL, row, l) | __ballot_sync(FULL, (col >> l) & 1u);
-            rem &= ~(killed | (1u << l));
+            if ((keepmask >> l) & 1u) keepmask &= ~killed;
         }
         const int rank = nk + __popc(keepmask & lt_mask);  // (d)
         if (((keepmask >> lane) & 1u) && rank < max_keep) {
@@ -220,6 +222,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
     const int G = (int)blockDim.x / T;
     const int gidx = tid / T, ctid = tid - gidx * T, cw = ctid >> 5;
     int nk = 0;
+    DET_ACC_BEGIN();
     for (int base = s; base < e && nk < max_keep; base += T) {
         const int p = base + ctid;
         const bool act = (p < e) && (state[p] == 0);
@@ -229,6 +232,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             mb = sbox[p];
             ma = sarea[p];
         }
+        DET_ACC(0);
         // (a) against everything already kept in this segment (this group's slice of the list)
         bool alive;
         if (G > 1) {
@@ -246,6 +250,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
         const unsigned bal = __ballot_sync(FULL, alive);
         if (gidx == 0 && lane == 0) amask[cw] = bal;
         __syncthreads();
+        DET_ACC(1);
         // (b) bit row of this candidate as suppressor of the later survivors of the chunk
         if (alive) {
             for (int w2 = cw; w2 < W; ++w2) {
@@ -263,6 +268,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             }
         }
         __syncthreads();
+        DET_ACC(2);
         // (c) sequential resolution by warp 0, one 32-candidate word at a time: lane w owns survivor word w; inside
         //     the current word the greedy order is resolved on its diagonal bit rows, then the kept rows are
         //     OR-ed into a removal mask for the later words (independent shared-memory loads).
@@ -270,13 +276,18 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             unsigned word = (lane < W) ? amask[lane] : 0u;
             int nkl = nk;
             for (int f = 0; f < W && nkl < max_keep; ++f) {
-                unsigned rem = __shfl_sync(FULL, word, f), keepmask = 0;
+                const unsigned rem = __shfl_sync(FULL, word, f);
                 if (!rem) continue;
                 const unsigned diag = rowbits[(f * 32 + lane) * W + f];  // stale for dead lanes: only read if alive
-                while (rem) {
-                    const int b = __ffs(rem) - 1;
-                    keepmask |= 1u << b;
-                    rem &= ~(__shfl_sync(FULL, diag, b) | (1u << b));
+                // only survivors whose row reaches another survivor of the word can change anything: visit those, in
+                // order (with few suppressions -- the long, high-survival segments -- that is a handful of steps, not 32)
+                unsigned keepmask = rem;
+                unsigned nz = __ballot_sync(FULL, ((rem >> lane) & 1u) && (diag & rem) != 0u);
+                while (nz) {
+                    const int b = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const unsigned row = __shfl_sync(FULL, diag, b);
+                    if ((keepmask >> b) & 1u) keepmask &= ~row;
                 }
                 if (nkl + __popc(keepmask) > max_keep) {  // keep only the first (max_keep - nkl) of them
                     unsigned km = keepmask, trimmed = 0;
@@ -301,6 +312,7 @@ __device__ int cta_segment_nms(const float4* sbox, const float* sarea, uint8_t* 
             if (lane == 0) *s_nk = nkl;
         }
         __syncthreads();
+        DET_ACC(3);
         nk = *s_nk;
     }
     return nk;

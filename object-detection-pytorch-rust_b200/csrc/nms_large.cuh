@@ -79,7 +79,7 @@ struct LargeLayout {
 
 struct LargeWs {
     LargeImg* info;
-    int32_t* ctr;  // [0] #small segs, [1] #large segs, [2] next small, [3] next large, [4] #huge segs
+    int32_t* ctr;  // [0] #small segs, [1] #large segs, [2] next small, [3] next large, [4] #huge segs, [6] next large (spatial index)
     uint64_t *keys_a, *keys_b;
     float4* sbox;
     float* sarea;
@@ -521,6 +521,13 @@ large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const f
     __shared__ uint32_t amask[kSegThreads / 32], deadmask[kSegThreads / 32];
     __shared__ int s_nk, s_next;
     const int total = ctr[1];
+#ifdef DET_DEBUG_PHASES
+    if (total == 0) return;
+#endif
+    DET_MARK(0);
+#ifdef DET_DEBUG_PHASES
+    if (blockIdx.x < 64 && threadIdx.x == 0) g_phase_block[blockIdx.x][2] = g_phase_block[blockIdx.x][3] = 0;
+#endif
     while (true) {
         if (threadIdx.x == 0) s_next = atomicAdd(&ctr[3], 1);
         __syncthreads();
@@ -528,6 +535,13 @@ large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const f
         __syncthreads();
         if (i >= total) break;
         const int4 sg = seg_large[i];
+        if (sg.w != 0) continue;  // done by large_bin_segments_kernel
+#ifdef DET_DEBUG_PHASES
+        if (blockIdx.x < 64 && threadIdx.x == 0) {
+            g_phase_block[blockIdx.x][2] += 1;
+            g_phase_block[blockIdx.x][3] += sg.z - sg.y;
+        }
+#endif
         const int64_t o = (int64_t)sg.x * mp;
         const StagedBoxes sb = stage_boxes(sbox + o, sarea + o, sg.y, sg.z, sm_box, sm_area);
         if (info[sg.x].nonan)
@@ -537,6 +551,219 @@ large_cta_segments_kernel(int64_t mp, const LargeImg* __restrict__ info, const f
             cta_segment_nms<kSegThreads, int32_t, false>(sb.box, sb.area, state + o, klist + o, sg.y, sg.z, thr_f, max_keep,
                                                          rowbits, amask, deadmask, &s_nk);
         __syncthreads();
+    }
+    DET_MARK(1);
+}
+
+// ---- CTA-class segments through a spatial index (most pairs of a long segment never overlap) -----------------------------
+// The sweep above tests every candidate against every kept box before it: O(kept x boxes) pair tests and a serial chain
+// of 256-box chunks -- 190 us for the ~960 best level-0 proposals of an RPN image, 90 % of which survive.  For an IoU
+// threshold of at least 0.5 a suppressing pair is confined in space: inter / union > 0.5 means that the intersection
+// covers more than half of EITHER box in x and in y, hence it contains both centres; in particular
+//     box j suppresses box i  =>  the centre of j lies inside box i.
+// So every candidate is filed under the grid cell of its centre (one linked-list node per box), and box i only meets the
+// boxes filed in the cells its own extent reaches, and of those only the better-scored ones whose centre it contains:
+//   1  stage the segment; bounding range of the centres, largest |coordinate|; a segment with a non-finite coordinate or
+//      an area outside [1e-30, 1e30] (where the rounding of the areas could defeat the argument) is left to the sweep
+//   2  file the candidates by centre cell (GB x GB cells over the range of the centres; the cell function is monotone in
+//      the coordinate, and the query extent is widened by m = 2^-16 x the largest |coordinate|, far more than the
+//      rounding of the centre and of the IoU quotient can move anything)
+//   3  every candidate collects its SUPPRESSORS -- better-scored boxes j with nms_suppresses(j, i), the same predicate
+//      on the same operands as the sweep -- up to kBinEdges of them; one with more re-walks its cells when asked
+//   4  greedy order without a chain over the boxes: a candidate with no suppressor is kept; in rounds, an undecided
+//      candidate dies if one of its suppressors is kept and is kept once all of them are dead.  The best undecided
+//      candidate is always decidable, so this terminates with exactly the sweep's result; after kBinRounds rounds
+//      (a long dependency chain) the segment is left to the sweep
+//   5  the first max_keep kept positions get state 2, as the sweep would leave them
+// Segments handled here are marked in seg_large[i].w; large_cta_segments_kernel skips them.
+constexpr int kBinThreads = 512;
+constexpr int kBinEdges = 4;
+constexpr int kBinRounds = 48;
+constexpr int kBinCells = 32;  // cells per axis for long segments (16 for segments of up to 1024 boxes)
+
+struct BinSmem {
+    float4 box[kHugeSeg];
+    uint16_t next[kHugeSeg];
+    uint16_t edge[kHugeSeg * kBinEdges];
+    uint8_t meta[kHugeSeg];  // bits 0-2: stored suppressors, bit 3: there are more, bits 4-5: 0 undecided 1 dead 2 kept
+    int head[kBinCells * kBinCells];
+};
+
+struct BinGrid {
+    float x0, y0, ix, iy, m, top;
+    int gb;
+    __device__ __forceinline__ int cx(float x) const { return (int)fminf(fmaxf((x - x0) * ix, 0.0f), top); }
+    __device__ __forceinline__ int cy(float y) const { return (int)fminf(fmaxf((y - y0) * iy, 0.0f), top); }
+};
+
+// walks the better-scored boxes filed in the cells box q reaches; f(j, box_j) -> true stops the walk
+template <typename F>
+__device__ __forceinline__ void bin_walk(const BinSmem& sm, const BinGrid& g, int q, const float4 bi, F f) {
+    const float lx = bi.x - g.m, hx = bi.z + g.m, ly = bi.y - g.m, hy = bi.w + g.m;
+    const int c0 = g.cx(lx), c1 = g.cx(hx), r0 = g.cy(ly), r1 = g.cy(hy);
+    for (int r = r0; r <= r1; ++r)
+        for (int c = c0; c <= c1; ++c)
+            for (int j = sm.head[r * g.gb + c]; j >= 0; j = (sm.next[j] == 0xFFFFu) ? -1 : (int)sm.next[j]) {
+                if (j >= q) continue;
+                const float4 bj = sm.box[j];
+                const float xj = 0.5f * (bj.x + bj.z), yj = 0.5f * (bj.y + bj.w);
+                if (xj < lx || xj > hx || yj < ly || yj > hy) continue;
+                if (f(j, bj)) return;
+            }
+}
+
+static __global__ void __launch_bounds__(kBinThreads, 2)
+large_bin_segments_kernel(int64_t mp, const float4* __restrict__ sbox, uint8_t* state, int32_t* ctr, int4* seg_large,
+                          float thr_f, int max_keep) {
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    BinSmem& sm = *reinterpret_cast<BinSmem*>(bin_smem);
+    __shared__ float s_red[kBinThreads / 32][5];
+    __shared__ int s_bad[kBinThreads / 32], s_wc[kBinThreads / 32];
+    __shared__ int s_next;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = kBinThreads / 32;
+    const int total = ctr[1];
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(&ctr[6], 1);
+        __syncthreads();
+        const int i = s_next;
+        if (i >= total) break;
+        const int4 sg = seg_large[i];
+        const int n = sg.z - sg.y;
+        const int64_t o = (int64_t)sg.x * mp + sg.y;
+        // ---- 1: stage, statistics
+        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY, amax = 0.0f;
+        int bad = 0;
+        for (int q = tid; q < n; q += kBinThreads) {
+            const float4 b = sbox[o + q];
+            const bool cand = state[o + q] == 0;
+            sm.box[q] = b;
+            sm.meta[q] = cand ? 0 : (1u << 4);
+            if (cand) {
+                const float a = box_area(b);
+                const bool fin = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w);
+                if (!fin || (a > 0.0f && a < 1e-30f) || a > 1e30f) bad = 1;
+                const float xc = 0.5f * (b.x + b.z), yc = 0.5f * (b.y + b.w);
+                xmin = fminf(xmin, xc); xmax = fmaxf(xmax, xc);
+                ymin = fminf(ymin, yc); ymax = fmaxf(ymax, yc);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, d)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, d));
+            ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, d)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, d));
+            amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, d));
+            bad |= __shfl_xor_sync(FULL, bad, d);
+        }
+        if (lane == 0) {
+            s_red[wid][0] = xmin; s_red[wid][1] = xmax; s_red[wid][2] = ymin; s_red[wid][3] = ymax; s_red[wid][4] = amax;
+            s_bad[wid] = bad;
+        }
+        for (int c = tid; c < kBinCells * kBinCells; c += kBinThreads) sm.head[c] = -1;
+        __syncthreads();
+        for (int w = 0; w < NW; ++w) {
+            xmin = fminf(xmin, s_red[w][0]); xmax = fmaxf(xmax, s_red[w][1]);
+            ymin = fminf(ymin, s_red[w][2]); ymax = fmaxf(ymax, s_red[w][3]);
+            amax = fmaxf(amax, s_red[w][4]);
+            bad |= s_bad[w];
+        }
+        // (coordinates of at least 1e-20 keep the widening m far above the absolute error of denormal extents)
+        if (bad || !(amax < 1e15f) || !(amax > 1e-20f)) continue;  // the barrier at the top of the loop separates the iterations
+        BinGrid g;
+        g.gb = n > 1024 ? kBinCells : kBinCells / 2;
+        g.top = (float)(g.gb - 1);
+        g.x0 = xmin; g.y0 = ymin;
+        const float rx = xmax - xmin, ry = ymax - ymin;
+        g.ix = (rx > 0.0f && (float)g.gb / rx < 1e30f) ? (float)g.gb / rx : 0.0f;
+        g.iy = (ry > 0.0f && (float)g.gb / ry < 1e30f) ? (float)g.gb / ry : 0.0f;
+        g.m = amax * 1.52587890625e-05f;
+        // ---- 2: file the candidates under the cell of their centre
+        for (int q = tid; q < n; q += kBinThreads) {
+            if (sm.meta[q]) continue;
+            const float4 b = sm.box[q];
+            const int cell = g.cy(0.5f * (b.y + b.w)) * g.gb + g.cx(0.5f * (b.x + b.z));
+            const int old = atomicExch(&sm.head[cell], q);
+            sm.next[q] = old < 0 ? (uint16_t)0xFFFFu : (uint16_t)old;
+        }
+        __syncthreads();
+        // ---- 3: suppressors of every candidate
+        for (int q = tid; q < n; q += kBinThreads) {
+            if (sm.meta[q]) continue;
+            const float4 bi = sm.box[q];
+            const float ai = box_area(bi);
+            int cnt = 0;
+            bool more = false;
+            bin_walk(sm, g, q, bi, [&](int j, const float4 bj) {
+                if (!nms_suppresses<true>(bj, box_area(bj), bi, ai, thr_f)) return false;
+                if (cnt == kBinEdges) {
+                    more = true;
+                    return true;
+                }
+                sm.edge[q * kBinEdges + cnt++] = (uint16_t)j;
+                return false;
+            });
+            sm.meta[q] = (uint8_t)(cnt | (more ? 8 : 0) | (cnt == 0 ? (2 << 4) : 0));
+        }
+        __syncthreads();
+        // ---- 4: rounds
+        const volatile uint8_t* vmeta = sm.meta;
+        int pending_any = 1;
+        for (int round = 0; round < kBinRounds && pending_any; ++round) {
+            int pending = 0;
+            for (int q = tid; q < n; q += kBinThreads) {
+                const unsigned mq = vmeta[q];
+                if (mq >> 4) continue;
+                bool kept_sup = false, open_sup = false;
+                const int cnt = (int)(mq & 7u);
+                for (int k = 0; k < cnt; ++k) {
+                    const unsigned st = vmeta[sm.edge[q * kBinEdges + k]] >> 4;
+                    kept_sup |= st == 2u;
+                    open_sup |= st == 0u;
+                }
+                if (!kept_sup && (mq & 8u)) {  // more suppressors than the list holds: look at all of them again
+                    const float4 bi = sm.box[q];
+                    const float ai = box_area(bi);
+                    bin_walk(sm, g, q, bi, [&](int j, const float4 bj) {
+                        const unsigned st = vmeta[j] >> 4;
+                        if (st == 1u || !nms_suppresses<true>(bj, box_area(bj), bi, ai, thr_f)) return false;
+                        if (st == 2u) {
+                            kept_sup = true;
+                            return true;
+                        }
+                        open_sup = true;
+                        return false;
+                    });
+                }
+                if (kept_sup) sm.meta[q] = (uint8_t)(mq | (1u << 4));
+                else if (!open_sup) sm.meta[q] = (uint8_t)(mq | (2u << 4));
+                else pending = 1;
+            }
+            pending_any = __syncthreads_or(pending);
+        }
+        if (pending_any) continue;
+        // ---- 5: the first max_keep kept positions
+        int running = 0;
+        for (int base = 0; base < n && running < max_keep; base += kBinThreads) {
+            const int q = base + tid;
+            const bool k = q < n && (sm.meta[q] >> 4) == 2u;
+            const unsigned bal = __ballot_sync(FULL, k);
+            if (lane == 0) s_wc[wid] = __popc(bal);
+            __syncthreads();
+            int pre = 0, tot = 0;
+            for (int w = 0; w < NW; ++w) {
+                const int v = s_wc[w];
+                pre += w < wid ? v : 0;
+                tot += v;
+            }
+            const int rank = running + pre + __popc(bal & ((1u << lane) - 1u));
+            if (k && rank < max_keep) state[o + q] = 2;
+            running += tot;
+            __syncthreads();
+        }
+        if (tid == 0) seg_large[i].w = 1;
     }
 }
 
@@ -712,7 +939,15 @@ static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float 
     if (!attr_set) {
         cudaError_t ea = cudaFuncSetAttribute(large_cta_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seg_smem);
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(large_cta_segments_kernel)");
+        ea = cudaFuncSetAttribute(large_bin_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BinSmem));
+        if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(large_bin_segments_kernel)");
         attr_set = true;
+    }
+    static const bool use_bins = [] { const char* v = getenv("DET_NO_BINS"); return !(v && v[0] == '1'); }();
+    if (use_bins && thr_f >= 0.5f) {  // spatial index: needs "a suppressor's centre lies inside the box" (IoU > 1/2)
+        large_bin_segments_kernel<<<sms * 2, kBinThreads, sizeof(BinSmem), st>>>(lay.mp, ws.sbox, ws.state, ws.ctr, ws.seg_large,
+                                                                              thr_f, max_keep);
+        DET_LAUNCH_OK("large_bin_segments_kernel");
     }
     large_cta_segments_kernel<<<sms * 2, kSegCtaThreads, seg_smem, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
                                                                       ws.seg_large, thr_f, max_keep);

@@ -480,4 +480,18 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     return DET_OK;
 }
 
+#ifdef DET_DEBUG_PHASES
+__attribute__((visibility("default"))) int det_debug_read_phase_blocks_proposals(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, det::g_phase_block, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -4;
+}
+__attribute__((visibility("default"))) int det_debug_read_acc_proposals(long long* out_host, int reset) {
+    if (cudaMemcpyFromSymbol(out_host, det::g_phase_acc, sizeof(long long) * 16) != cudaSuccess) return -4;
+    if (reset) {
+        long long z[16] = {0};
+        if (cudaMemcpyToSymbol(det::g_phase_acc, z, sizeof(z)) != cudaSuccess) return -4;
+    }
+    return 0;
+}
+#endif
+
 }  // extern "C"

@@ -353,3 +353,77 @@ def test_nms_images_stress_random_batches(det, O, seed):
             want = want[:max_out]
         assert int(kc[i]) == want.numel(), (i, int(kc[i]), want.numel())
         assert torch.equal(keep[i, :want.numel()], want), i
+
+
+# ---- CTA-class segments through the spatial index (large_bin_segments_kernel; IoU threshold >= 0.5) ---------------------
+def _spatial_case(kind, m, ncat, g):
+    if kind == "sparse":          # small boxes in a wide frame: nearly everything survives
+        b = rand_boxes(m, 4000.0, g, 0.015)
+    elif kind == "clustered":     # near-duplicates around a few centres: many suppressors per box, few survivors
+        k = 40
+        ctr = torch.rand(k, 2, generator=g) * 900 + 50
+        which = torch.randint(0, k, (m,), generator=g)
+        c = ctr[which] + torch.randn(m, 2, generator=g) * 4.0
+        wh = 60 + torch.randn(m, 2, generator=g) * 5.0
+        b = torch.cat([c - wh / 2, c + wh / 2], 1)
+    elif kind == "chain":         # a staircase: every box is suppressed by its predecessor only -> a dependency chain of m
+        i = torch.arange(m, dtype=torch.float32)
+        b = torch.stack([i * 15.0, i * 0.0, i * 15.0 + 100.0, i * 0.0 + 50.0], 1)
+    elif kind == "mixed":         # boxes of every size, some covering the whole frame
+        b = rand_boxes(m, 1000.0, g, 0.1)
+        big = torch.randint(0, m, (m // 50,), generator=g)
+        b[big] = torch.tensor([0.0, 0.0, 1000.0, 1000.0]) + torch.randn(big.numel(), 4, generator=g) * 20
+    elif kind == "quantised":
+        b = rand_boxes(m, 300.0, g, 0.2).round()
+    elif kind == "tiny":          # coordinates far below the range where the index is trusted: the sweep takes over
+        b = rand_boxes(m, 640.0, g, 0.2) * 1e-24
+    elif kind == "giant":
+        b = rand_boxes(m, 640.0, g, 0.2) * 1e16
+    elif kind == "degenerate":    # zero-width, inverted and far-away boxes among ordinary ones
+        b = rand_boxes(m, 500.0, g, 0.2)
+        j = torch.randperm(m, generator=g)
+        b[j[:50], 2] = b[j[:50], 0]
+        b[j[50:100], 2] = b[j[50:100], 0] - 5.0
+        b[j[100:110]] += 1e6
+    else:
+        raise AssertionError(kind)
+    return b
+
+
+@pytest.mark.parametrize("kind,m,ncat,thr,max_out,ordered", [
+    ("sparse", 6000, 3, 0.7, None, False),
+    ("sparse", 6000, 2, 0.5, 1500, False),
+    ("clustered", 6000, 4, 0.5, None, False),
+    ("clustered", 5000, 2, 0.7, None, False),
+    ("clustered", 5000, 2, 0.7, 300, False),
+    ("chain", 4500, 9, 0.7, None, True),
+    ("chain", 4500, 9, 0.7, None, False),
+    ("mixed", 6000, 3, 0.5, None, False),
+    ("mixed", 8000, 2, 0.6, None, False),
+    ("quantised", 6000, 5, 0.5, None, False),
+    ("quantised", 6000, 20, 0.5, None, False),
+    ("tiny", 5000, 3, 0.5, None, False),
+    ("giant", 5000, 3, 0.5, None, False),
+    ("degenerate", 6000, 3, 0.5, None, False),
+    ("sparse", 6000, 3, 0.4999, None, False),   # below 1/2: the index must not be used
+])
+def test_spatial_index_segments_match_oracle(det, O, kind, m, ncat, thr, max_out, ordered):
+    g = gen(77 + m % 13 + ncat)
+    n_img = 2
+    boxes = torch.stack([_spatial_case(kind, m, ncat, g) for _ in range(n_img)])
+    if ordered:   # scores fall along the chain: kept, dead, kept, ... decided one box per round
+        scores = torch.stack([torch.linspace(1.0, 0.01, m) for _ in range(n_img)])
+        cats = (torch.arange(m) * ncat // m)[None].repeat(n_img, 1)
+    else:
+        scores = torch.stack([distinct_scores(m, g) for _ in range(n_img)])
+        cats = torch.randint(0, ncat, (n_img, m), generator=g)
+    counts = torch.tensor([m, m - 777], dtype=torch.int32)
+    keep, kc = det.nms_images(boxes.cuda(), scores.cuda(), cats.cuda(), counts.cuda(), thr, max_out=max_out, mode=1)
+    keep, kc = keep.cpu(), kc.cpu()
+    for i in range(n_img):
+        k = int(counts[i])
+        want = O.batched_nms(boxes[i, :k], scores[i, :k], cats[i, :k], thr)
+        if max_out is not None:
+            want = want[:max_out]
+        assert int(kc[i]) == want.numel(), (i, int(kc[i]), want.numel())
+        assert torch.equal(keep[i, :want.numel()], want), i
