@@ -366,12 +366,14 @@ static int launch_detect_nms_t(const SelectArgs& sel, int n, float thr_f, int mo
                                float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
                                int32_t* overflow_flag, cudaStream_t st) {
     const size_t smem = sizeof(DetectSmem<CAP, T>);
+    static const int use_fast = [] { const char* v = getenv("DET_NO_FAST_NMS"); return (v && v[0] == '1') ? 0 : 1; }();
     cudaError_t e = cudaFuncSetAttribute(dense_detect_nms_kernel<CAP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dense_detect_nms_kernel)");
     // programmatic dependent launch: the CTAs take their SM slots while the select kernel drains (see common.cuh)
     e = launch_pdl(dense_detect_nms_kernel<CAP, T>, dim3(n), dim3(T), smem, st, sel.cand_count, sel.cand_box, sel.cand_score,
                    sel.cand_cls, sel.cand_id, sel.cand_cap, thr_f, mode, max_det, det_idx,
-                   reinterpret_cast<float4*>(det_boxes), det_scores, det_classes, det_count, overflow_flag, nullptr, nullptr);
+                   reinterpret_cast<float4*>(det_boxes), det_scores, det_classes, det_count, overflow_flag, nullptr, nullptr,
+                   use_fast);
     if (e != cudaSuccess) return cuda_fail(e, "dense_detect_nms_kernel");
     return DET_OK;
 }
