@@ -276,3 +276,34 @@ def test_dense_detect_stress_random_heads(det, O, seed):
     cap = [256, 1024, 4096][ri(0, 2)]
     r = dh.detect_thresholded(heads, thr, iou, max_det=max_det, cand_cap=cap, gate=bool(ri(0, 1)), check=True)
     check_against_oracle(dh, O, heads, r, thr, iou, max_det)
+
+
+def test_dense_detect_offset_trick_suppresses_across_categories(det, O):
+    """<= 1000 candidates -> torchvision's coordinate-offset branch.  A top-left box of class 1 that sticks out of the frame
+    by half its size, shifted by one span, overlaps the bottom-right box of class 0 that holds the largest coordinate:
+    at a low IoU threshold the reference suppresses ACROSS categories, and so must we (either may be the better one)."""
+    import math
+    C = 4
+    dh = det.DenseAnchorHead(STRIDES, WH, C)
+    heads = make_heads(2, 640, C, 33, -7.0)
+    v = heads[2].view(2, 3, 5 + C, 20, 20)
+    for img, (obj_q, obj_p) in enumerate(((4.0, 9.0), (9.0, 4.0))):
+        for (row, col, cls, txy, obj) in ((0, 0, 1, -20.0, obj_q), (19, 19, 0, 20.0, obj_p)):
+            v[img, 2, :, row, col] = -10.0
+            v[img, 2, 0, row, col] = txy
+            v[img, 2, 1, row, col] = txy
+            v[img, 2, 2, row, col] = math.log(600.0 / 373.0)
+            v[img, 2, 3, row, col] = math.log(600.0 / 326.0)
+            v[img, 2, 4, row, col] = obj
+            v[img, 2, 5 + cls, row, col] = 10.0
+    hg = [h.cuda() for h in heads]
+    boxes, scores, classes = [t.cpu() for t in dh.decode(hg)]
+    for gate in (True, False):
+        r = dh.detect_thresholded(hg, 0.3, 0.1, max_det=300, cand_cap=1024, gate=gate, check=False)
+        check_against_oracle(dh, O, hg, r, 0.3, 0.1, 300)
+    for i in range(2):  # the case is what it claims to be: per-category NMS would keep one detection more
+        cand = torch.nonzero(scores[i] > 0.3, as_tuple=True)[0]
+        assert cand.numel() <= 1000
+        per_cat = sum(int(O.nms(boxes[i][cand][classes[i][cand] == c], scores[i][cand][classes[i][cand] == c], 0.1).numel())
+                      for c in range(C))
+        assert int(r["count"][i]) == per_cat - 1
