@@ -614,7 +614,7 @@ __device__ __forceinline__ void bin_walk(const BinSmem& sm, const BinGrid& g, in
 
 static __global__ void __launch_bounds__(kBinThreads, 2)
 large_bin_segments_kernel(int64_t mp, const float4* __restrict__ sbox, uint8_t* state, int32_t* ctr, int4* seg_large,
-                          float thr_f, int max_keep) {
+                          float thr_f, int max_keep, int bin_fine) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
     BinSmem& sm = *reinterpret_cast<BinSmem*>(bin_smem);
     __shared__ float s_red[kBinThreads / 32][5];
@@ -673,7 +673,7 @@ large_bin_segments_kernel(int64_t mp, const float4* __restrict__ sbox, uint8_t* 
         // (coordinates of at least 1e-20 keep the widening m far above the absolute error of denormal extents)
         if (bad || !(amax < 1e15f) || !(amax > 1e-20f)) continue;  // the barrier at the top of the loop separates the iterations
         BinGrid g;
-        g.gb = n > 1024 ? kBinCells : kBinCells / 2;
+        g.gb = n > bin_fine ? kBinCells : kBinCells / 2;
         g.top = (float)(g.gb - 1);
         g.x0 = xmin; g.y0 = ymin;
         const float rx = xmax - xmin, ry = ymax - ymin;
@@ -945,8 +945,9 @@ static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float 
     }
     static const bool use_bins = [] { const char* v = getenv("DET_NO_BINS"); return !(v && v[0] == '1'); }();
     if (use_bins && thr_f >= 0.5f) {  // spatial index: needs "a suppressor's centre lies inside the box" (IoU > 1/2)
+        static const int bin_fine = [] { const char* v = getenv("DET_BIN_FINE"); return v ? atoi(v) : 1024; }();
         large_bin_segments_kernel<<<sms * 2, kBinThreads, sizeof(BinSmem), st>>>(lay.mp, ws.sbox, ws.state, ws.ctr, ws.seg_large,
-                                                                              thr_f, max_keep);
+                                                                              thr_f, max_keep, bin_fine);
         DET_LAUNCH_OK("large_bin_segments_kernel");
     }
     large_cta_segments_kernel<<<sms * 2, kSegCtaThreads, seg_smem, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,

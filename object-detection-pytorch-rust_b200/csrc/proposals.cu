@@ -37,7 +37,10 @@ __device__ __forceinline__ int level_of(const LevelTable& t, int64_t i) {
 // tiles instead of all R keys -- is sorted afterwards.  One CTA per image.
 static __global__ void __launch_bounds__(1024)
 rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LevelTable ct, int64_t len1,
-                  LargeImg* info, uint64_t* __restrict__ keys) {
+                  LargeImg* info, uint64_t* __restrict__ keys, int stage_cap) {
+    // the keys of a level that needs a selection are read from global memory once and staged here (up to stage_cap of
+    // them): the radix passes and the final compaction then run out of shared memory
+    extern __shared__ uint32_t staged_keys[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_want, s_slot, s_done, s_warp[32];
@@ -62,6 +65,13 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
         uint32_t cut = 0xffffffffu;
         bool tie_mode = false;
         int tie_want = 0;
+        const bool staged = take < size && size <= (int64_t)stage_cap;
+        if (staged) {
+            __syncthreads();  // the previous level is done with the staging area
+            for (int64_t i = tid; i < size; i += T) staged_keys[i] = score_desc_key(lg[i0 + i]);
+            __syncthreads();
+        }
+        auto key_at = [&](int64_t i) -> uint32_t { return staged ? staged_keys[i] : score_desc_key(lg[i0 + i]); };
         if (take < size) {
             // radix select of the take-th best 32-bit descending-logit key, one byte per pass
             if (tid == 0) {
@@ -75,7 +85,7 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
                 if (s_done) break;
                 const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
                 for (int64_t i = tid; i < size; i += T) {
-                    const uint32_t key = score_desc_key(lg[i0 + i]);
+                    const uint32_t key = key_at(i);
                     if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                 }
                 __syncthreads();
@@ -124,7 +134,7 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
             uint32_t k32 = 0xffffffffu;
             bool in = false, eq = false;
             if (i < size) {
-                k32 = score_desc_key(lg[i0 + i]);
+                k32 = key_at(i);
                 in = tie_mode ? (k32 < cut) : (k32 <= cut);
                 eq = tie_mode && k32 == cut;
             }
@@ -438,7 +448,15 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
         if (l < num_levels) rc += std::min(level_sizes_host[l], pre_nms_topk);
     }
     const int64_t len1 = (rc + kTile - 1) / kTile * kTile;  // <= mp
-    rpn_select_kernel<<<n, 1024, 0, st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a);
+    // staging area of the select kernel: the largest level that needs a selection, if it fits (200 KB at most)
+    int64_t stage = 0;
+    for (int l = 0; l < num_levels; ++l)
+        if (pre_nms_topk < level_sizes_host[l] && level_sizes_host[l] <= 50 * 1024) stage = std::max(stage, level_sizes_host[l]);
+    if (stage * 4 > 48 * 1024) {
+        cudaError_t ea = cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stage * 4));
+        if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(rpn_select_kernel)");
+    }
+    rpn_select_kernel<<<n, 1024, (size_t)(stage * 4), st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a, (int)stage);
     DET_LAUNCH_OK("rpn_select_kernel");
     uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st, nullptr, len1);
     uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
