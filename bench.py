@@ -553,7 +553,7 @@ def extras_dense(det, dev, peak, quick):
         thr, max_det, cap = 0.1, 300, 2048
         res = {}
         for gate in (False, True):
-            ws = torch.empty((det._native.fn("det_dense_detect_workspace_bytes")(n, cap),), dtype=torch.uint8, device=dev)
+            ws = det.DenseDetectWorkspace(n, cap, dev)  # counters zeroed once, left zero by every call
             r = dh.detect_thresholded(heads[0], thr, 0.5, max_det=max_det, cand_cap=cap, gate=gate, check=True, workspace=ws)
             fns = [(lambda hs=hs_: dh.detect_thresholded(hs, thr, 0.5, max_det=max_det, cand_cap=cap, gate=gate,
                                                          check=False, out=r, workspace=ws)) for hs_ in heads]

@@ -190,10 +190,15 @@ DET_API int det_dense_decode(const det_dense_level_t* levels_host, int num_level
  *   by descending score, ties by lower row.
  *   cand_cap (<= 4096): capacity of the per-image candidate list.  An image with more candidates gets
  *   det_count = -1 and *overflow_flag (device int32, may be NULL; written by the call) = 1 -- nothing is guessed.
- *   gate != 0: read the objectness plane first and skip the class/box planes of positions that cannot pass
- *   (exact: score <= sigmoid(objectness)); gate == 0 streams the whole head.
+ *   gate bit 0: read the objectness plane first and skip the class/box planes of positions that cannot pass
+ *   (exact: score <= sigmoid(objectness)); clear = stream the whole head.
+ *   gate bit 1: the per-image counters at the head of the workspace are known to
+ *   be zero.  The call always LEAVES them zero (the NMS CTA of an image resets its counter), so a caller that zeroes
+ *   the first det_dense_detect_counter_bytes(n) bytes of a workspace once and then uses it for nothing else may set
+ *   this bit on every call: exactly two launches, no memset node.  Clear = the call clears the counters itself.
  *   limits: every level h*w % 4 == 0 and 16-byte aligned heads (else DET_ERR_UNSUPPORTED). */
 DET_API int64_t det_dense_detect_workspace_bytes(int n, int64_t cand_cap);
+DET_API int64_t det_dense_detect_counter_bytes(int n); /* size of the counter block at the head of the workspace */
 DET_API int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
                      float score_thresh, double iou_threshold, int mode, int gate, int64_t cand_cap, int64_t max_det,
                      int64_t* det_idx, float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,

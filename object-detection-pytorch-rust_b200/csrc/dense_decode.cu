@@ -43,7 +43,7 @@ struct DenseLevelDev {
 // 1 / (1 + e^-x): __frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to the IEEE quotient 1.0f / d
 __device__ __forceinline__ float sigmoidf_dd(float x) { return __frcp_rn(1.0f + expf(-x)); }
 
-constexpr int kFlatThreads = 256;
+constexpr int kFlatThreads = 128;  // 8 CTAs per SM: at one or two waves (N=32) the finer grain trims the tail, 62.0 -> 61.2 us
 
 struct FlatArgs {
     DenseLevelDev lv[kMaxLevels];
@@ -62,12 +62,16 @@ struct FlatArgs {
     float* cand_score;
     int32_t* cand_cls;
     int32_t* cand_id;
+    int32_t* overflow_flag;  // cleared here (first thread of the grid); the NMS kernel behind this one sets it
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kFlatThreads) dense_decode_flat_kernel(const __grid_constant__ FlatArgs g) {
-    if (MODE != kModeDense) pdl_trigger();  // det_dense_detect: the NMS kernel's CTAs may move in as SM slots free up
-    long long gt = (long long)blockIdx.x * kFlatThreads + threadIdx.x;
+template <int MODE, int TH = kFlatThreads>
+__global__ void __launch_bounds__(TH) dense_decode_flat_kernel(const __grid_constant__ FlatArgs g) {
+    if (MODE != kModeDense) {
+        pdl_trigger();  // det_dense_detect: the NMS kernel's CTAs may move in as SM slots free up
+        if (blockIdx.x == 0 && threadIdx.x == 0 && g.overflow_flag) *g.overflow_flag = 0;
+    }
+    long long gt = (long long)blockIdx.x * TH + threadIdx.x;
     bool active = gt < g.thread_begin[g.num_levels];
     if (MODE == kModeDense) {
         if (!active) return;
@@ -359,6 +363,7 @@ struct SelectArgs {
     float* cand_score;
     int32_t* cand_cls;
     int32_t* cand_id;
+    int32_t* overflow_flag;
 };
 
 template <int CAP, int T>
@@ -407,7 +412,7 @@ static int launch_flat(const det_dense_level_t* levels_host, int num_levels, int
     f.score_thresh = sel ? sel->score_thresh : 0.f; f.cand_cap = sel ? sel->cand_cap : 0;
     f.cand_count = sel ? sel->cand_count : nullptr; f.cand_box = sel ? sel->cand_box : nullptr;
     f.cand_score = sel ? sel->cand_score : nullptr; f.cand_cls = sel ? sel->cand_cls : nullptr;
-    f.cand_id = sel ? sel->cand_id : nullptr;
+    f.cand_id = sel ? sel->cand_id : nullptr; f.overflow_flag = sel ? sel->overflow_flag : nullptr;
     f.num_levels = num_levels; f.n = n; f.a = a; f.c = c; f.scale_clamp = scale_clamp; f.out_img_stride = out_img_stride;
     f.boxes_out = reinterpret_cast<float4*>(boxes_out); f.score_out = score_out; f.class_out = class_out;
     long long tb = 0;
@@ -428,11 +433,21 @@ static int launch_flat(const det_dense_level_t* levels_host, int num_levels, int
     }
     for (int l = num_levels; l <= kMaxLevels; ++l) f.thread_begin[l] = tb;
     if (tb == 0) return DET_OK;
-    const long long blocks = (tb + kFlatThreads - 1) / kFlatThreads;
+    static const int th_env = [] { const char* v = getenv("DET_FLAT_THREADS"); return v ? atoi(v) : 0; }();
+    const int th = (th_env == 256 || th_env == 512) ? th_env : kFlatThreads;
+    const long long blocks = (tb + th - 1) / th;
     DET_CHECK_ARG(blocks < (1ll << 31), "too many positions");
-    if (!sel) dense_decode_flat_kernel<kModeDense><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
-    else if (sel->mode == kModeSelectGated) dense_decode_flat_kernel<kModeSelectGated><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
-    else dense_decode_flat_kernel<kModeSelect><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    if (!sel) {
+        if (th == 256) dense_decode_flat_kernel<kModeDense, 256><<<(unsigned)blocks, 256, 0, st>>>(f);
+        else if (th == 512) dense_decode_flat_kernel<kModeDense, 512><<<(unsigned)blocks, 512, 0, st>>>(f);
+        else dense_decode_flat_kernel<kModeDense><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    } else if (sel->mode == kModeSelectGated) {
+        dense_decode_flat_kernel<kModeSelectGated><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    } else {
+        if (th == 256) dense_decode_flat_kernel<kModeSelect, 256><<<(unsigned)blocks, 256, 0, st>>>(f);
+        else if (th == 512) dense_decode_flat_kernel<kModeSelect, 512><<<(unsigned)blocks, 512, 0, st>>>(f);
+        else dense_decode_flat_kernel<kModeSelect><<<(unsigned)blocks, kFlatThreads, 0, st>>>(f);
+    }
     DET_LAUNCH_OK("dense_decode_flat_kernel");
     return DET_OK;
 }
@@ -497,6 +512,8 @@ int64_t det_dense_detect_workspace_bytes(int n, int64_t cand_cap) {
     return (int64_t)n * kCountStride * 4 + (int64_t)n * cand_cap * (16 + 4 + 4 + 4);
 }
 
+int64_t det_dense_detect_counter_bytes(int n) { return n <= 0 ? 0 : (int64_t)n * kCountStride * 4; }
+
 int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n, int a, int c, float scale_clamp,
                      float score_thresh, double iou_threshold, int mode, int gate, int64_t cand_cap, int64_t max_det,
                      int64_t* det_idx, float* det_boxes, float* det_scores, int64_t* det_classes, int32_t* det_count,
@@ -536,7 +553,8 @@ int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n
     }
     unsigned char* w = static_cast<unsigned char*>(workspace);
     SelectArgs sel;
-    sel.mode = gate ? kModeSelectGated : kModeSelect;
+    sel.mode = (gate & 1) ? kModeSelectGated : kModeSelect;
+    sel.overflow_flag = overflow_flag;
     sel.score_thresh = score_thresh;
     sel.cand_cap = (int)cand_cap;
     sel.cand_count = reinterpret_cast<int32_t*>(w);
@@ -548,10 +566,11 @@ int det_dense_detect(const det_dense_level_t* levels_host, int num_levels, int n
     sel.cand_cls = reinterpret_cast<int32_t*>(w);
     w += (int64_t)n * cand_cap * 4;
     sel.cand_id = reinterpret_cast<int32_t*>(w);
-    cudaError_t e = cudaMemsetAsync(sel.cand_count, 0, sizeof(int32_t) * (size_t)n * kCountStride, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    if (overflow_flag) {
-        e = cudaMemsetAsync(overflow_flag, 0, sizeof(int32_t), st);
+    // The NMS CTA of an image puts the image's counter back to zero once it has read it and the select kernel clears
+    // the overflow word itself, so a call on a workspace whose counters are known to be zero (gate bit 1: zeroed once by
+    // the caller, then only ever used by this call) is exactly two launches; otherwise the counters are cleared here.
+    if (!(gate & 2)) {
+        cudaError_t e = cudaMemsetAsync(sel.cand_count, 0, sizeof(int32_t) * (size_t)n * kCountStride, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     }
     int rc = launch_flat(levels_host, num_levels, n, a, c, scale_clamp, nullptr, nullptr, nullptr, rows, st, &sel);

@@ -921,7 +921,7 @@ static int launch_list_nms_ext(const int32_t* tier_count, const float4* box, con
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(list nms)");
         attr_set = true;
     }
-    dense_detect_nms_kernel<kTierCap, T><<<n, T, smem, st>>>(tier_count, box, score, cls, id, kTierCap, thr_f, mode,
+    dense_detect_nms_kernel<kTierCap, T><<<n, T, smem, st>>>(const_cast<int32_t*>(tier_count), box, score, cls, id, kTierCap, thr_f, mode,
                                                              max_out, keep, nullptr, nullptr, nullptr, keep_counts,
                                                              nullptr, full, todo);
     DET_LAUNCH_OK("list_nms_kernel(ext)");

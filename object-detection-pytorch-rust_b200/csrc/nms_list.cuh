@@ -105,11 +105,18 @@ static __device__ __noinline__ bool fast_suppresses(const float4 a, const float4
     return nms_suppresses<true>(a, box_area(a), b, box_area(b), thr_f);
 }
 
+// candidate `threadIdx.x` of the list, loaded before the count is known (slot tid < cand_cap always exists in the workspace)
+struct FastFirst {
+    float4 b;
+    float s;
+    int c, id;
+};
+
 template <int CAP, int T>
 __device__ int detect_fast(DetectFastSmem<CAP>& fs, int cnt, const float4* __restrict__ cbox, const float* __restrict__ cscore,
                            const int32_t* __restrict__ ccls, const int32_t* __restrict__ cid, float thr_f, int mode,
                            int cap_out, int64_t out0, int64_t* __restrict__ det_idx, float4* __restrict__ det_boxes,
-                           float* __restrict__ det_scores, int64_t* __restrict__ det_classes) {
+                           float* __restrict__ det_scores, int64_t* __restrict__ det_classes, const FastFirst& first) {
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = T / 32;
@@ -141,9 +148,10 @@ __device__ int detect_fast(DetectFastSmem<CAP>& fs, int cnt, const float4* __res
     for (int i = tid; i < cnt; i += 2 * T) {  // two candidates per trip: both sets of loads are in flight together
         const int i2 = i + T;
         const bool two = i2 < cnt;
-        const float4 b0 = cbox[i];
-        const int c0 = ccls[i], id0 = cid[i];
-        const float s0 = cscore[i];
+        const bool pre = i == tid;  // candidate `tid` was requested together with the count (FastFirst)
+        const float4 b0 = pre ? first.b : cbox[i];
+        const int c0 = pre ? first.c : ccls[i], id0 = pre ? first.id : cid[i];
+        const float s0 = pre ? first.s : cscore[i];
         float4 b1 = b0;
         int c1 = 0, id1 = 0;
         float s1 = 0.0f;
@@ -499,7 +507,7 @@ __device__ int detect_fast(DetectFastSmem<CAP>& fs, int cnt, const float4* __res
 
 template <int CAP, int T>
 __global__ void __launch_bounds__(T, 512 / T)
-dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __restrict__ cand_box,
+dense_detect_nms_kernel(int32_t* cand_count, const float4* __restrict__ cand_box,
                         const float* __restrict__ cand_score, const int32_t* __restrict__ cand_cls,
                         const int32_t* __restrict__ cand_id, int cand_cap, float thr_f, int mode, int64_t max_det,
                         int64_t* __restrict__ det_idx, float4* __restrict__ det_boxes, float* __restrict__ det_scores,
@@ -512,7 +520,17 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
     const int img = blockIdx.x, tid = threadIdx.x;
     pdl_wait();  // no-op unless launched with launch_pdl (det_dense_detect): the candidate lists are complete from here
     DET_MARK(0);
+    FastFirst first;
+    first.b = make_float4(0.f, 0.f, 0.f, 0.f); first.s = 0.f; first.c = 0; first.id = 0;
+    if (!ext_full && use_fast && tid < cand_cap) {  // in flight together with the count
+        const int64_t o = (int64_t)img * cand_cap + tid;
+        first.b = cand_box[o]; first.s = cand_score[o]; first.c = cand_cls[o]; first.id = cand_id[o];
+    }
     const int cnt = cand_count[(int64_t)img * kCountStride];
+    if (!ext_full) {  // det_dense_detect: the counter goes back to zero for the next call on this workspace
+        __syncthreads();
+        if (tid == 0) cand_count[(int64_t)img * kCountStride] = 0;
+    }
     if (ext_full) {  // external tier: a negative count means "no usable list", the full path takes the image
         if (tid == 0) todo[img] = (cnt < 0 || cnt > cand_cap) ? 1 : 0;
         if (cnt < 0 || cnt > cand_cap) return;
@@ -531,7 +549,7 @@ dense_detect_nms_kernel(const int32_t* __restrict__ cand_count, const float4* __
         static_assert(sizeof(DetectFastSmem<CAP>) <= sizeof(DetectSmem<CAP, T>), "the fast form lives in the same shared memory");
         const int r = detect_fast<CAP, T>(*reinterpret_cast<DetectFastSmem<CAP>*>(smem_raw), cnt, cand_box + base,
                                           cand_score + base, cand_cls + base, cand_id + base, thr_f, mode, cap_out,
-                                          (int64_t)img * max_det, det_idx, det_boxes, det_scores, det_classes);
+                                          (int64_t)img * max_det, det_idx, det_boxes, det_scores, det_classes, first);
         if (r != kFastNo) {
             if (tid == 0) det_count[img] = r;
             DET_MARK(14);

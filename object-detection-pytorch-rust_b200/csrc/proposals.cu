@@ -34,7 +34,7 @@ __device__ __forceinline__ int level_of(const LevelTable& t, int64_t i) {
 // best keys (level | descending logit | anchor index -- unique, so "best k" is exact and stable) of every level are
 // found with a radix select (4 byte-passes over the 32-bit logit keys; when equal logits straddle the cut the lower
 // anchor indices win, ranked in index order) and written, in arrival order, to a compact row [coff[l], coff[l] + take_l) per level.  Only that row -- a few
-// tiles instead of all R keys -- is sorted afterwards.  One CTA per image.
+// tiles instead of all R keys -- is sorted afterwards.  One CTA per (image, level).
 static __global__ void __launch_bounds__(1024)
 rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LevelTable ct, int64_t len1,
                   LargeImg* info, uint64_t* __restrict__ keys, int stage_cap) {
@@ -48,15 +48,19 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* lg = logits + (int64_t)img * r;
     uint64_t* out = keys + (int64_t)img * mp;
-    if (tid == 0) {
-        LargeImg li;
-        li.cnt = (int32_t)ct.off[ct.num_levels]; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0;
-        li.nsurv = 0; li.nonan = 1; li.skip = 0;  // non-finite boxes are dropped by the gather kernel
-        for (int q = 0; q < 7; ++q) li.pad_[q] = 0;
-        info[img] = li;
+    // grid (images, levels): one CTA per (image, level) -- the levels of an image are independent selections into
+    // disjoint ranges of the compact row; blockIdx.y = 0 (the largest level of a pyramid) is dispatched first
+    if (blockIdx.y == 0) {
+        if (tid == 0) {
+            LargeImg li;
+            li.cnt = (int32_t)ct.off[ct.num_levels]; li.trick = 0; li.fast = 1; li.span = 0.f; li.nkept = 0; li.bad = 0;
+            li.nsurv = 0; li.nonan = 1; li.skip = 0;  // non-finite boxes are dropped by the gather kernel
+            for (int q = 0; q < 7; ++q) li.pad_[q] = 0;
+            info[img] = li;
+        }
+        for (int64_t j = ct.off[ct.num_levels] + tid; j < len1; j += T) out[j] = kSentinelKey;
     }
-    for (int64_t j = ct.off[ct.num_levels] + tid; j < len1; j += T) out[j] = kSentinelKey;
-    for (int l = 0; l < lt.num_levels; ++l) {
+    for (int l = blockIdx.y; l < min((int)blockIdx.y + 1, lt.num_levels); ++l) {
         const int64_t i0 = lt.off[l], size = lt.off[l + 1] - i0;
         const int take = (int)(ct.off[l + 1] - ct.off[l]);
         if (take == 0) continue;
@@ -66,10 +70,24 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
         bool tie_mode = false;
         int tie_want = 0;
         const bool staged = take < size && size <= (int64_t)stage_cap;
+        // the top byte of a logit key (sign + 7 exponent bits) falls into a handful of bins: lanes that share a bin
+        // are counted with ONE shared-memory atomic (match.any) instead of serialising on the same address
+        auto count_top_byte = [&](bool valid, uint32_t key) {
+            const uint32_t bin = valid ? (key >> 24) : 0xffffu;
+            const unsigned same = __match_any_sync(0xffffffffu, bin);
+            if (valid && lane == __ffs(same) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(same));
+        };
         if (staged) {
-            __syncthreads();  // the previous level is done with the staging area
-            for (int64_t i = tid; i < size; i += T) staged_keys[i] = score_desc_key(lg[i0 + i]);
-            __syncthreads();
+            // one pass over the level: keys into the staging area + the histogram of the first radix pass
+            for (int b = tid; b < 256; b += T) hist[b] = 0u;
+            __syncthreads();  // (also: the previous level is done with the staging area)
+            for (int64_t base = 0; base < size; base += T) {
+                const int64_t i = base + tid;
+                const bool valid = i < size;
+                const uint32_t key = valid ? score_desc_key(lg[i0 + i]) : 0u;
+                if (valid) staged_keys[i] = key;
+                count_top_byte(valid, key);
+            }
         }
         auto key_at = [&](int64_t i) -> uint32_t { return staged ? staged_keys[i] : score_desc_key(lg[i0 + i]); };
         if (take < size) {
@@ -80,15 +98,25 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
                 s_done = 0;
             }
             for (int shift = 24; shift >= 0; shift -= 8) {
-                for (int b = tid; b < 256; b += T) hist[b] = 0u;
-                __syncthreads();
-                if (s_done) break;
-                const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-                for (int64_t i = tid; i < size; i += T) {
-                    const uint32_t key = key_at(i);
-                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                if (shift == 24 && staged) {
+                    __syncthreads();  // staging + first histogram complete
+                } else {
+                    for (int b = tid; b < 256; b += T) hist[b] = 0u;
+                    __syncthreads();
+                    if (s_done) break;
+                    const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+                    if (shift == 24) {
+                        for (int64_t base = 0; base < size; base += T)
+                            count_top_byte(base + tid < size, base + tid < size ? key_at(base + tid) : 0u);
+                    } else {
+                        for (int64_t i = tid; i < size; i += T) {
+                            const uint32_t key = key_at(i);
+                            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
+                const uint32_t prefix = s_prefix;
                 if (wid == 0) {
                     uint32_t c8[8], tot = 0;
 #pragma unroll
@@ -161,6 +189,24 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
         }
         __syncthreads();
     }
+}
+
+// ---- per-level sort of the compact row -------------------------------------------------------------------------------------
+// The selected keys of level l lie in [coff[l], coff[l] + take_l) and carry the level in their top bits, so sorting every
+// level's range by itself IS the sort of the row.  With take_l <= kTile that is one shared-memory tile sort per
+// (image, level) and no merge passes (sort_rows: tile sort + two merge passes over 8192 keys per image at 2000 per level).
+static __global__ void __launch_bounds__(kSortThreads)
+rpn_sort_levels_kernel(uint64_t* __restrict__ keys, int64_t mp, LevelTable ct) {
+    __shared__ uint64_t s[kTile];
+    const int l = blockIdx.x, img = blockIdx.y;
+    const int take = (int)(ct.off[l + 1] - ct.off[l]);
+    if (take <= 1) return;
+    uint64_t* g = keys + (int64_t)img * mp + ct.off[l];
+    const int n2 = next_pow2(take);
+    for (int i = threadIdx.x; i < max(n2, kSortThreads); i += kSortThreads) s[i] = i < take ? g[i] : kSentinelKey;
+    __syncthreads();
+    cta_bitonic_sort<kSortThreads>(s, n2);
+    for (int i = threadIdx.x; i < take; i += kSortThreads) g[i] = s[i];
 }
 
 __device__ __forceinline__ float4 clip_box(float4 b, float w, float h) {
@@ -381,6 +427,77 @@ rpn_emit_kernel(const float4* __restrict__ boxes, const float* __restrict__ logi
     if (j == 0) out_counts[img] = (int32_t)nout;
 }
 
+// ---- kept candidates -> proposals, one CTA per image ------------------------------------------------------------------------
+// Inside a level the candidates are sorted by (descending logit, index), so the kept ones of a level form a sorted run
+// and the output order is the MERGE of the levels' runs: an order-preserving compaction of the kept keys into shared
+// memory (one block scan over the compact row), then every kept key finds its output slot as its position in its own
+// run plus, by binary search, the number of smaller keys in every other run -- and writes its clipped box and logit
+// there if the slot is below post_nms_topk.  Replaces rekey + pad + tile sort + merge pass + emit (5 launches).
+static __global__ void __launch_bounds__(1024)
+rpn_finish_kernel(const float4* __restrict__ boxes, const float* __restrict__ logits, int64_t r, int rc, int64_t mp,
+                  LevelTable ct, int cap, const uint64_t* __restrict__ keys, const uint8_t* __restrict__ state,
+                  const int32_t* __restrict__ image_sizes, int64_t post_nms_topk, float4* __restrict__ out_boxes,
+                  float* __restrict__ out_logits, int32_t* __restrict__ out_counts) {
+    extern __shared__ uint64_t fk[];  // kept keys without the level field, run after run
+    __shared__ int s_warp[32], s_lvl[kMaxLevels + 1];
+    constexpr int T = 1024;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t* k = keys + (int64_t)img * mp;
+    const uint8_t* stt = state + (int64_t)img * mp;
+    int run = 0;  // kept so far (block-uniform)
+    for (int base = 0; base < rc; base += T) {
+        const int p = base + tid;
+        const bool kept = p < rc && stt[p] == 2;
+        const uint64_t key = kept ? KLL::strip_seg(k[p]) : 0ull;
+        const unsigned bal = __ballot_sync(0xffffffffu, kept);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = run, total = 0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) {
+            const int v = s_warp[w];
+            before += (w < wid) ? v : 0;
+            total += v;
+        }
+        const int slot = before + __popc(bal & ((1u << lane) - 1u));
+        if (kept && slot < cap) fk[slot] = key;
+        if (p < rc)
+            for (int l = 0; l < ct.num_levels; ++l)
+                if ((int64_t)p == ct.off[l]) s_lvl[l] = slot;  // first slot of level l's run
+        run += total;
+        __syncthreads();
+    }
+    if (tid == 0)
+        for (int l = 0; l <= ct.num_levels; ++l)
+            if (ct.off[l] >= (int64_t)rc) s_lvl[l] = run;
+    __syncthreads();
+    const int nk = min(run, cap);
+    const float iw = (float)image_sizes[2 * img + 1], ih = (float)image_sizes[2 * img];
+    for (int j = tid; j < nk; j += T) {
+        const uint64_t key = fk[j];
+        int64_t rank = 0;
+        for (int l = 0; l < ct.num_levels; ++l) {
+            const int a = s_lvl[l], b = s_lvl[l + 1];
+            if (j >= a && j < b) {
+                rank += j - a;
+                continue;
+            }
+            int lo = a, hi = b;  // keys are unique: number of keys of this run below `key`
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (fk[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo - a;
+        }
+        if (rank < post_nms_topk) {
+            const int64_t i = KLL::idx(key);
+            out_boxes[(int64_t)img * post_nms_topk + rank] = clip_box(boxes[(int64_t)img * r + i], iw, ih);
+            out_logits[(int64_t)img * post_nms_topk + rank] = logits[(int64_t)img * r + i];
+        }
+    }
+    if (tid == 0) out_counts[img] = (int32_t)min((int64_t)nk, post_nms_topk);
+}
+
 }  // namespace det
 
 using namespace det;
@@ -456,9 +573,16 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
         cudaError_t ea = cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stage * 4));
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(rpn_select_kernel)");
     }
-    rpn_select_kernel<<<n, 1024, (size_t)(stage * 4), st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a, (int)stage);
+    rpn_select_kernel<<<dim3((unsigned)n, (unsigned)num_levels), 1024, (size_t)(stage * 4), st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a, (int)stage);
     DET_LAUNCH_OK("rpn_select_kernel");
-    uint64_t* sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st, nullptr, len1);
+    static const bool old_sorts = [] { const char* v = getenv("DET_RPN_OLD_SORTS"); return v && v[0] == '1'; }();
+    uint64_t* sorted;
+    if (!old_sorts && std::min(*std::max_element(level_sizes_host, level_sizes_host + num_levels), pre_nms_topk) <= kTile) {
+        rpn_sort_levels_kernel<<<dim3((unsigned)num_levels, (unsigned)n), kSortThreads, 0, st>>>(ws.keys_a, mp, ct);
+        sorted = ws.keys_a;
+    } else {
+        sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st, nullptr, len1);
+    }
     uint64_t* other = (sorted == ws.keys_a) ? ws.keys_b : ws.keys_a;
     DET_LAUNCH_OK("sort_rows");
     dim3 grid_e((unsigned)((len1 + 255) / 256), (unsigned)n);
@@ -483,6 +607,17 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     if (status != DET_OK) return status;
     int64_t kept_bound = 0;
     for (int l = 0; l < num_levels; ++l) kept_bound += std::min({level_sizes_host[l], pre_nms_topk, post_nms_topk});
+    if (!old_sorts && kept_bound * 8 <= 200 * 1024) {  // the kept keys of an image fit into shared memory
+        const size_t smem = (size_t)kept_bound * 8;
+        if (smem > 48 * 1024) {
+            cudaError_t ea = cudaFuncSetAttribute(rpn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(rpn_finish_kernel)");
+        }
+        rpn_finish_kernel<<<n, 1024, smem, st>>>(b4, logits, r, (int)rc, mp, ct, (int)kept_bound, sorted, ws.state, image_sizes,
+                                                 post_nms_topk, reinterpret_cast<float4*>(out_boxes), out_logits, out_counts);
+        DET_LAUNCH_OK("rpn_finish_kernel");
+        return DET_OK;
+    }
     const int64_t len2 = std::min(mp, (kept_bound + kTile - 1) / kTile * kTile);
     rpn_rekey_compact_kernel<<<grid_e, 256, 0, st>>>(rc, mp, ws.info, sorted, ws.state, other);
     DET_LAUNCH_OK("rpn_rekey_compact_kernel");

@@ -10,7 +10,7 @@ from .structures import (Boxes, Instances, pairwise_iou, pairwise_ioa, pairwise_
 from .box_regression import Box2BoxTransform
 from .anchors import AnchorGenerator, generate_cell_anchors
 from .nms import batched_nms, nms, nms_images
-from .yolo import YoloGridHead, DenseAnchorHead, YoloGridTrainer, YoloHostPipeline
+from .yolo import YoloGridHead, DenseAnchorHead, YoloGridTrainer, YoloHostPipeline, DenseDetectWorkspace
 from .matcher import Matcher, subsample_labels_
 from .proposals import find_top_rpn_proposals, rpn_proposals_batched, add_ground_truth_to_proposals
 from .rpn import RegionProposalNetwork, Assignment, _dense_box_regression_loss
@@ -21,7 +21,7 @@ from . import dist
 __all__ = [
     "Boxes", "Instances", "pairwise_iou", "pairwise_ioa", "pairwise_intersection", "matched_boxlist_iou",
     "Box2BoxTransform", "AnchorGenerator", "generate_cell_anchors", "batched_nms", "nms", "nms_images",
-    "YoloGridHead", "DenseAnchorHead", "YoloGridTrainer", "YoloHostPipeline", "Matcher", "subsample_labels_", "find_top_rpn_proposals",
+    "YoloGridHead", "DenseAnchorHead", "YoloGridTrainer", "YoloHostPipeline", "DenseDetectWorkspace", "Matcher", "subsample_labels_", "find_top_rpn_proposals",
     "rpn_proposals_batched", "add_ground_truth_to_proposals", "RegionProposalNetwork", "Assignment",
     "_dense_box_regression_loss", "ROIHeads", "subsample_labels", "ROIAlign", "ROIPooler", "assign_boxes_to_levels",
     "convert_boxes_to_pooler_format", "dist",

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "det_dense_decode_level": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_f, c_p, c_p, c_p, c_l, c_l, c_p]),
     "det_dense_decode": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_l, c_p]),
     "det_dense_detect_workspace_bytes": (c_l, [c_i, c_l]),
+    "det_dense_detect_counter_bytes": (c_l, [c_i]),
     "det_dense_detect": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_d, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p,
                                c_p, c_l, c_p]),
     "det_threshold_compact": (c_i, [c_p, c_p, c_p, c_i, c_l, c_f, c_l, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -163,6 +163,23 @@ class YoloHostPipeline:
         return self.wait(0)
 
 
+class DenseDetectWorkspace:
+    """Scratch memory of det_dense_detect that is used for nothing else: the per-image candidate counters at its head are
+    zeroed once here and every call leaves them zero, so ``detect_thresholded(..., workspace=this)`` is exactly two
+    launches (no memset node).  One object per stream of calls in flight."""
+
+    def __init__(self, n: int, cand_cap: int, device):
+        self.n, self.cand_cap, self.device = int(n), int(cand_cap), torch.device(device)
+        nbytes = N.fn("det_dense_detect_workspace_bytes")(self.n, self.cand_cap)
+        self.buf = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        self.buf[:N.fn("det_dense_detect_counter_bytes")(self.n)].zero_()
+
+    def claim(self, n: int, cand_cap: int, device) -> torch.Tensor:
+        if (n, cand_cap) != (self.n, self.cand_cap) or torch.device(device) != self.device:
+            raise ValueError(f"DenseDetectWorkspace was built for n={self.n}, cand_cap={self.cand_cap} on {self.device}")
+        return self.buf
+
+
 class _FusedYoloLoss(torch.autograd.Function):
     """Everything the backward launch reads is saved with save_for_backward (no state on the owner)."""
 
@@ -375,11 +392,15 @@ class DenseAnchorHead:
             return out
         lv, hcs, _, na, _ = self._levels(heads)
         wsb = N.fn("det_dense_detect_workspace_bytes")(n, int(cand_cap))
-        if workspace is None or workspace.numel() < wsb:
+        flags = 1 if gate else 0
+        if isinstance(workspace, DenseDetectWorkspace):
+            workspace = workspace.claim(n, int(cand_cap), dev)
+            flags |= 2  # counters zeroed once at construction and left zero by every call: no memset node
+        elif workspace is None or workspace.numel() < wsb:
             workspace = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             N.call("det_dense_detect", ctypes.cast(lv, ctypes.c_void_p), len(hcs), n, na, self.C, self.scale_clamp,
-                   float(score_thresh), float(iou_thresh), int(mode), 1 if gate else 0, int(cand_cap), max_det,
+                   float(score_thresh), float(iou_thresh), int(mode), flags, int(cand_cap), max_det,
                    N.ptr(out["idx"]), N.ptr(out["boxes"]), N.ptr(out["scores"]), N.ptr(out["classes"]),
                    N.ptr(out["count"]), N.ptr(out["overflow"]), N.ptr(workspace), wsb, N.stream())
         if check and int(out["overflow"].item()) != 0:

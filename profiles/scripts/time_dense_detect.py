@@ -22,7 +22,8 @@ for n in [int(a) for a in sys.argv[1:]] or [32, 256]:
             h.view(n, 3, 5 + C80, h.shape[2], h.shape[3])[:, :, 4] -= 4.0
         heads.append(hs)
     for thr, cap in ((0.1, 2048), (0.25, 1024)):
-        ws = torch.empty((det._native.fn("det_dense_detect_workspace_bytes")(n, cap),), dtype=torch.uint8, device=dev)
+        ws = (torch.empty((det._native.fn("det_dense_detect_workspace_bytes")(n, cap),), dtype=torch.uint8, device=dev)
+              if os.environ.get("DET_PLAIN_WS") == "1" else det.DenseDetectWorkspace(n, cap, dev))
         r = dh.detect_thresholded(heads[0], thr, 0.5, max_det=300, cand_cap=cap, gate=False, check=True, workspace=ws)
         fns = [(lambda hs=hs_: dh.detect_thresholded(hs, thr, 0.5, max_det=300, cand_cap=cap, gate=False, check=False, out=r,
                                                      workspace=ws)) for hs_ in heads]

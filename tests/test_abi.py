@@ -52,6 +52,7 @@ def test_dense_detect_queries_and_argument_checks_need_no_gpu():
     wsb = N.fn("det_dense_detect_workspace_bytes")
     assert wsb(0, 1024) == 256
     assert wsb(32, 2048) == 32 * 128 + 32 * 2048 * 28          # padded counters + (box, score, class, row) lists
+    assert N.fn("det_dense_detect_counter_bytes")(32) == 32 * 128 and N.fn("det_dense_detect_counter_bytes")(0) == 0
     assert N.fn("det_nms_workspace_bytes")(32, 25200) > wsb(32, 4096)   # the large path carries the top-k tier's lists
     f = N.fn("det_dense_detect")
     null = ctypes.c_void_p(0)

@@ -163,6 +163,29 @@ def test_dense_detect_overflow_is_reported_then_redone_exactly(det, O):
     check_against_oracle(dh, O, heads, r, 0.3, 0.5, 100)
 
 
+def test_dense_detect_owned_workspace_stays_clean_over_calls(det, O):
+    """DenseDetectWorkspace (gate bit 1: counters zeroed once, reset by the NMS CTAs, overflow word cleared by the select
+    kernel): repeated calls on different batches -- an overflowing one in between -- give the oracle's detections, and
+    the counter block is zero after every call."""
+    C = 80
+    dh = det.DenseAnchorHead(STRIDES, WH, C)
+    ws = det.DenseDetectWorkspace(3, 1024, "cuda:0")
+    nctr = det._native.fn("det_dense_detect_counter_bytes")(3)
+    batches = [[h.cuda() for h in make_heads(3, 256, C, 40 + k, bias)] for k, bias in enumerate((-4.0, 0.0, -3.5, -4.0))]
+    out = None
+    for k, heads in enumerate(batches):
+        out = dh.detect_thresholded(heads, 0.1, 0.5, max_det=300, cand_cap=1024, gate=bool(k & 1), check=False, out=out,
+                                    workspace=ws)
+        assert int(ws.buf[:nctr].view(torch.int32).abs().sum()) == 0
+        if k == 1:  # bias 0: far more than 1024 candidates per image
+            assert int(out["overflow"].item()) == 1 and (out["count"].cpu() == -1).all()
+        else:
+            assert int(out["overflow"].item()) == 0  # cleared again by the call after the overflowing one
+            check_against_oracle(dh, O, heads, out, 0.1, 0.5, 300)
+    with pytest.raises(ValueError):
+        dh.detect_thresholded(batches[0], 0.1, 0.5, cand_cap=2048, workspace=ws)
+
+
 def test_dense_detect_levels_outside_the_fused_limits(det, O):
     """5x5 level (25 positions, not a multiple of 4): detect_thresholded takes the unfused GPU path."""
     C = 10
