@@ -49,7 +49,9 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
     const float* lg = logits + (int64_t)img * r;
     uint64_t* out = keys + (int64_t)img * mp;
     // grid (images, levels): one CTA per (image, level) -- the levels of an image are independent selections into
-    // disjoint ranges of the compact row; blockIdx.y = 0 (the largest level of a pyramid) is dispatched first
+    // disjoint ranges of the compact row; blockIdx.y = 0 (the largest level of a pyramid) is dispatched first.  (With
+    // DET_RPN_SELECT_SPLIT=0 one CTA per image walks the levels: 0.199 / 0.256 / 0.560 ms per 16 / 64 / 256 images
+    // against 0.179 / 0.237 / 0.541 ms.)
     if (blockIdx.y == 0) {
         if (tid == 0) {
             LargeImg li;
@@ -60,7 +62,7 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
         }
         for (int64_t j = ct.off[ct.num_levels] + tid; j < len1; j += T) out[j] = kSentinelKey;
     }
-    for (int l = blockIdx.y; l < min((int)blockIdx.y + 1, lt.num_levels); ++l) {
+    for (int l = blockIdx.y; l < lt.num_levels; l += gridDim.y) {
         const int64_t i0 = lt.off[l], size = lt.off[l + 1] - i0;
         const int take = (int)(ct.off[l + 1] - ct.off[l]);
         if (take == 0) continue;
@@ -70,12 +72,10 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
         bool tie_mode = false;
         int tie_want = 0;
         const bool staged = take < size && size <= (int64_t)stage_cap;
-        // the top byte of a logit key (sign + 7 exponent bits) falls into a handful of bins: lanes that share a bin
-        // are counted with ONE shared-memory atomic (match.any) instead of serialising on the same address
         auto count_top_byte = [&](bool valid, uint32_t key) {
-            const uint32_t bin = valid ? (key >> 24) : 0xffffu;
-            const unsigned same = __match_any_sync(0xffffffffu, bin);
-            if (valid && lane == __ffs(same) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(same));
+            // (counting lanes that share a bin with one atomic -- match.any -- was measured slower than letting the
+            //  shared-memory atomics serialise: 82 vs 58 us per 64 images with one CTA per image)
+            if (valid) atomicAdd(&hist[key >> 24], 1u);
         };
         if (staged) {
             // one pass over the level: keys into the staging area + the histogram of the first radix pass
@@ -195,7 +195,9 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
 // The selected keys of level l lie in [coff[l], coff[l] + take_l) and carry the level in their top bits, so sorting every
 // level's range by itself IS the sort of the row.  With take_l <= kTile that is one shared-memory tile sort per
 // (image, level) and no merge passes (sort_rows: tile sort + two merge passes over 8192 keys per image at 2000 per level).
-static __global__ void __launch_bounds__(kSortThreads)
+constexpr int kLevelSortThreads = 512;  // 4 keys per thread: 16 warps hide the shuffle latency of the network better than 8
+
+static __global__ void __launch_bounds__(kLevelSortThreads)
 rpn_sort_levels_kernel(uint64_t* __restrict__ keys, int64_t mp, LevelTable ct) {
     __shared__ uint64_t s[kTile];
     const int l = blockIdx.x, img = blockIdx.y;
@@ -203,10 +205,10 @@ rpn_sort_levels_kernel(uint64_t* __restrict__ keys, int64_t mp, LevelTable ct) {
     if (take <= 1) return;
     uint64_t* g = keys + (int64_t)img * mp + ct.off[l];
     const int n2 = next_pow2(take);
-    for (int i = threadIdx.x; i < max(n2, kSortThreads); i += kSortThreads) s[i] = i < take ? g[i] : kSentinelKey;
+    for (int i = threadIdx.x; i < max(n2, kLevelSortThreads); i += kLevelSortThreads) s[i] = i < take ? g[i] : kSentinelKey;
     __syncthreads();
-    cta_bitonic_sort<kSortThreads>(s, n2);
-    for (int i = threadIdx.x; i < take; i += kSortThreads) g[i] = s[i];
+    cta_bitonic_sort<kLevelSortThreads>(s, n2);
+    for (int i = threadIdx.x; i < take; i += kLevelSortThreads) g[i] = s[i];
 }
 
 __device__ __forceinline__ float4 clip_box(float4 b, float w, float h) {
@@ -439,33 +441,49 @@ rpn_finish_kernel(const float4* __restrict__ boxes, const float* __restrict__ lo
                   const int32_t* __restrict__ image_sizes, int64_t post_nms_topk, float4* __restrict__ out_boxes,
                   float* __restrict__ out_logits, int32_t* __restrict__ out_counts) {
     extern __shared__ uint64_t fk[];  // kept keys without the level field, run after run
-    __shared__ int s_warp[32], s_lvl[kMaxLevels + 1];
+    __shared__ int s_warp[32], s_lvl[kMaxLevels + 1], s_total;
     constexpr int T = 1024;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t* k = keys + (int64_t)img * mp;
     const uint8_t* stt = state + (int64_t)img * mp;
     int run = 0;  // kept so far (block-uniform)
-    for (int base = 0; base < rc; base += T) {
-        const int p = base + tid;
-        const bool kept = p < rc && stt[p] == 2;
-        const uint64_t key = kept ? KLL::strip_seg(k[p]) : 0ull;
-        const unsigned bal = __ballot_sync(0xffffffffu, kept);
-        if (lane == 0) s_warp[wid] = __popc(bal);
-        __syncthreads();
-        int before = run, total = 0;
+    for (int base0 = 0; base0 < rc; base0 += 4 * T) {
+        uint8_t st4[4];
+        uint64_t k4[4];
 #pragma unroll
-        for (int w = 0; w < T / 32; ++w) {
-            const int v = s_warp[w];
-            before += (w < wid) ? v : 0;
-            total += v;
+        for (int u = 0; u < 4; ++u) {  // the loads of four trips in flight together
+            const int p = base0 + u * T + tid;
+            st4[u] = p < rc ? stt[p] : (uint8_t)0;
+            k4[u] = p < rc ? k[p] : 0ull;
         }
-        const int slot = before + __popc(bal & ((1u << lane) - 1u));
-        if (kept && slot < cap) fk[slot] = key;
-        if (p < rc)
-            for (int l = 0; l < ct.num_levels; ++l)
-                if ((int64_t)p == ct.off[l]) s_lvl[l] = slot;  // first slot of level l's run
-        run += total;
-        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (base0 + u * T >= rc) break;
+            const int p = base0 + u * T + tid;
+            const bool kept = p < rc && st4[u] == 2;
+            const unsigned bal = __ballot_sync(0xffffffffu, kept);
+            if (lane == 0) s_warp[wid] = __popc(bal);
+            __syncthreads();
+            if (wid == 0) {  // exclusive scan of the 32 warp counts
+                const int v = s_warp[lane];
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    incl += (lane >= o) ? up : 0;
+                }
+                s_warp[lane] = incl - v;
+                if (lane == 31) s_total = incl;
+            }
+            __syncthreads();
+            const int before = run + s_warp[wid], total = s_total;
+            const int slot = before + __popc(bal & ((1u << lane) - 1u));
+            if (kept && slot < cap) fk[slot] = KLL::strip_seg(k4[u]);
+            if (p < rc)
+                for (int l = 0; l < ct.num_levels; ++l)
+                    if ((int64_t)p == ct.off[l]) s_lvl[l] = slot;  // first slot of level l's run
+            run += total;  // (no barrier: a warp's count is only rewritten by the warp itself, s_total behind the next barrier)
+        }
     }
     if (tid == 0)
         for (int l = 0; l <= ct.num_levels; ++l)
@@ -475,19 +493,31 @@ rpn_finish_kernel(const float4* __restrict__ boxes, const float* __restrict__ lo
     const float iw = (float)image_sizes[2 * img + 1], ih = (float)image_sizes[2 * img];
     for (int j = tid; j < nk; j += T) {
         const uint64_t key = fk[j];
-        int64_t rank = 0;
-        for (int l = 0; l < ct.num_levels; ++l) {
-            const int a = s_lvl[l], b = s_lvl[l + 1];
-            if (j >= a && j < b) {
-                rank += j - a;
-                continue;
+        int rank = 0;
+        for (int l0 = 0; l0 < ct.num_levels; l0 += 4) {  // four runs searched side by side (independent chains)
+            int lo[4], hi[4], a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool real = l0 + u < ct.num_levels;
+                a[u] = real ? s_lvl[l0 + u] : 0;
+                const int b = real ? s_lvl[l0 + u + 1] : 0;
+                const bool own = j >= a[u] && j < b;  // its own run: the position is the count
+                lo[u] = own ? j : a[u];
+                hi[u] = own ? j : b;
             }
-            int lo = a, hi = b;  // keys are unique: number of keys of this run below `key`
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (fk[mid] < key) lo = mid + 1; else hi = mid;
+            for (;;) {
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (lo[u] < hi[u]) {  // keys are unique: number of keys of the run below `key`
+                        const int mid = (lo[u] + hi[u]) >> 1;
+                        if (fk[mid] < key) lo[u] = mid + 1; else hi[u] = mid;
+                        any = true;
+                    }
+                if (!any) break;
             }
-            rank += lo - a;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rank += lo[u] - a[u];
         }
         if (rank < post_nms_topk) {
             const int64_t i = KLL::idx(key);
@@ -573,12 +603,18 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
         cudaError_t ea = cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stage * 4));
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(rpn_select_kernel)");
     }
-    rpn_select_kernel<<<dim3((unsigned)n, (unsigned)num_levels), 1024, (size_t)(stage * 4), st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a, (int)stage);
+    // A cluster of four CTAs per (image, level) exchanging radix histograms through distributed shared memory was built and
+    // measured: 45.8 us instead of 54.8 us for 64 images but 163 us instead of 140 us for 256 (ten cluster barriers per CTA); a
+    // second form with two visits per key (keys below the cut's top byte written at once, the rest listed) executed MORE
+    // instructions than these seven tight visits (336 k vs 292 k warp-instructions per image) -- both rejected.
+    static const int sel_split = [] { const char* v = getenv("DET_RPN_SELECT_SPLIT"); return v ? atoi(v) : 1; }();
+    const unsigned sel_y = sel_split ? (unsigned)num_levels : 1u;
+    rpn_select_kernel<<<dim3((unsigned)n, sel_y), 1024, (size_t)(stage * 4), st>>>(logits, r, mp, lt, ct, len1, ws.info, ws.keys_a, (int)stage);
     DET_LAUNCH_OK("rpn_select_kernel");
     static const bool old_sorts = [] { const char* v = getenv("DET_RPN_OLD_SORTS"); return v && v[0] == '1'; }();
     uint64_t* sorted;
     if (!old_sorts && std::min(*std::max_element(level_sizes_host, level_sizes_host + num_levels), pre_nms_topk) <= kTile) {
-        rpn_sort_levels_kernel<<<dim3((unsigned)num_levels, (unsigned)n), kSortThreads, 0, st>>>(ws.keys_a, mp, ct);
+        rpn_sort_levels_kernel<<<dim3((unsigned)num_levels, (unsigned)n), kLevelSortThreads, 0, st>>>(ws.keys_a, mp, ct);
         sorted = ws.keys_a;
     } else {
         sorted = sort_rows(ws.keys_a, ws.keys_b, n, mp, st, nullptr, len1);
