@@ -570,7 +570,10 @@ def extras_dense(det, dev, peak, quick):
                          "frac": det_bytes / res[False][0] / 1e6 / peak, "algorithmic_bytes": det_bytes,
                          "formula": "N * (4*R*(5+C) read + (36*K + 4) written), R=25200, C=80, K = kept per image; "
                                     "both kernels (select + NMS) inside the timed region, gate off (whole head streamed)",
-                         "traffic": load_traffic(f"dense_select_kernel_n{n}")},
+                         "traffic": load_traffic(f"dense_select_kernel_n{n}"),
+                         "note": "the peak is the driver's COPY figure (half reads, half writes); this path is 99.9 % "
+                                 "reads, so a fraction slightly above 1 is a read-only stream without write turnarounds, "
+                                 "not an error"},
             "ms_gated": res[True][0], "images_per_s_gated": n / res[True][0] * 1e3,
             "gated_note": "objectness plane first; class/box planes of 4-position groups that cannot pass are never "
                           "read (exact: score <= sigmoid(obj)); fewer bytes than the formula, so no roofline claim"}

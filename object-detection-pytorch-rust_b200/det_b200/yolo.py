@@ -169,13 +169,18 @@ class DenseDetectWorkspace:
     launches (no memset node).  One object per stream of calls in flight."""
 
     def __init__(self, n: int, cand_cap: int, device):
-        self.n, self.cand_cap, self.device = int(n), int(cand_cap), torch.device(device)
+        self.n, self.cand_cap, self.device = int(n), int(cand_cap), self._norm(device)
         nbytes = N.fn("det_dense_detect_workspace_bytes")(self.n, self.cand_cap)
         self.buf = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
         self.buf[:N.fn("det_dense_detect_counter_bytes")(self.n)].zero_()
 
+    @staticmethod
+    def _norm(device) -> torch.device:
+        d = torch.device(device)
+        return torch.device("cuda", torch.cuda.current_device()) if d.type == "cuda" and d.index is None else d
+
     def claim(self, n: int, cand_cap: int, device) -> torch.Tensor:
-        if (n, cand_cap) != (self.n, self.cand_cap) or torch.device(device) != self.device:
+        if (n, cand_cap) != (self.n, self.cand_cap) or self._norm(device) != self.device:
             raise ValueError(f"DenseDetectWorkspace was built for n={self.n}, cand_cap={self.cand_cap} on {self.device}")
         return self.buf
 

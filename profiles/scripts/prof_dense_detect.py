@@ -27,7 +27,7 @@ for n in ns:
         heads.append(hs)
     for thr, cap in ((0.1, 2048), (0.25, 1024)):
         for gate in (False, True):
-            ws = torch.empty((det._native.fn("det_dense_detect_workspace_bytes")(n, cap),), dtype=torch.uint8, device=dev)
+            ws = det.DenseDetectWorkspace(n, cap, dev)
             r = dh.detect_thresholded(heads[0], thr, 0.5, max_det=300, cand_cap=cap, gate=gate, check=True, workspace=ws)
             if once:
                 torch.cuda.synchronize()
