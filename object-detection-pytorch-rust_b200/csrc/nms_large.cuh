@@ -614,7 +614,8 @@ __device__ __forceinline__ void bin_walk(const BinSmem& sm, const BinGrid& g, in
 
 static __global__ void __launch_bounds__(kBinThreads, 2)
 large_bin_segments_kernel(int64_t mp, const float4* __restrict__ sbox, uint8_t* state, int32_t* ctr, int4* seg_large,
-                          float thr_f, int max_keep, int bin_fine) {
+                          float thr_f, int max_keep, int bin_fine, const LargeImg* __restrict__ info,
+                          const float* __restrict__ sarea, int32_t* klist, const int4* __restrict__ seg_small) {
     extern __shared__ __align__(16) unsigned char bin_smem[];
     BinSmem& sm = *reinterpret_cast<BinSmem*>(bin_smem);
     __shared__ float s_red[kBinThreads / 32][5];
@@ -764,6 +765,23 @@ large_bin_segments_kernel(int64_t mp, const float4* __restrict__ sbox, uint8_t* 
             __syncthreads();
         }
         if (tid == 0) seg_large[i].w = 1;
+    }
+    // The short segments (one warp each, large_warp_segments_kernel's loop) ride in the CTAs that have run out of long
+    // ones: the lists are disjoint, and a launch of its own cost 8-12 us of mostly latency in front of this kernel.
+    if (seg_small) {
+        const int total_s = ctr[0];
+        while (true) {
+            int i = 0;
+            if (lane == 0) i = atomicAdd(&ctr[2], 1);
+            i = __shfl_sync(FULL, i, 0);
+            if (i >= total_s) break;
+            const int4 sg = seg_small[i];
+            const int64_t o = (int64_t)sg.x * mp;
+            if (info[sg.x].nonan)
+                warp_segment_nms<int32_t, true>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
+            else
+                warp_segment_nms<int32_t, false>(sbox + o, sarea + o, state + o, klist + o, sg.y, sg.z, thr_f, max_keep);
+        }
     }
 }
 
@@ -929,11 +947,20 @@ static int launch_list_nms_ext(const int32_t* tier_count, const float4* box, con
 }
 
 // runs the two persistent segment kernels over the lists built by a gather kernel
-static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float thr_f, int max_keep, cudaStream_t st) {
+// few_small: the caller knows that short segments are few (RPN levels: at most a couple per image) -- they then ride in
+// large_bin_segments_kernel; thousands of short segments (per-category NMS) keep their own launch at twice the resident warps
+static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float thr_f, int max_keep, cudaStream_t st,
+                               bool few_small = false) {
     const int sms = sm_count();
-    large_warp_segments_kernel<<<sms * 8, 128, 0, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
-                                                        ws.seg_small, thr_f, max_keep);
-    DET_LAUNCH_OK("large_warp_segments_kernel");
+    static const bool use_bins = [] { const char* v = getenv("DET_NO_BINS"); return !(v && v[0] == '1'); }();
+    static const bool merge_env = [] { const char* v = getenv("DET_NO_MERGE_SMALL"); return !(v && v[0] == '1'); }();
+    const bool merge_small = merge_env && few_small;
+    const bool bins = use_bins && thr_f >= 0.5f;  // spatial index: needs "a suppressor's centre lies inside the box" (IoU > 1/2)
+    if (!(bins && merge_small)) {  // otherwise the short segments ride in large_bin_segments_kernel
+        large_warp_segments_kernel<<<sms * 8, 128, 0, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,
+                                                            ws.seg_small, thr_f, max_keep);
+        DET_LAUNCH_OK("large_warp_segments_kernel");
+    }
     const int seg_smem = kHugeSeg * 20;
     static thread_local bool attr_set = false;
     if (!attr_set) {
@@ -943,11 +970,11 @@ static int run_segment_kernels(const LargeLayout& lay, const LargeWs& ws, float 
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(large_bin_segments_kernel)");
         attr_set = true;
     }
-    static const bool use_bins = [] { const char* v = getenv("DET_NO_BINS"); return !(v && v[0] == '1'); }();
-    if (use_bins && thr_f >= 0.5f) {  // spatial index: needs "a suppressor's centre lies inside the box" (IoU > 1/2)
+    if (bins) {
         static const int bin_fine = [] { const char* v = getenv("DET_BIN_FINE"); return v ? atoi(v) : 1024; }();
         large_bin_segments_kernel<<<sms * 2, kBinThreads, sizeof(BinSmem), st>>>(lay.mp, ws.sbox, ws.state, ws.ctr, ws.seg_large,
-                                                                              thr_f, max_keep, bin_fine);
+                                                                              thr_f, max_keep, bin_fine, ws.info, ws.sarea, ws.klist,
+                                                                              merge_small ? ws.seg_small : nullptr);
         DET_LAUNCH_OK("large_bin_segments_kernel");
     }
     large_cta_segments_kernel<<<sms * 2, kSegCtaThreads, seg_smem, st>>>(lay.mp, ws.info, ws.sbox, ws.sarea, ws.state, ws.klist, ws.ctr,

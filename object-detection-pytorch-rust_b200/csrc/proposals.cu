@@ -599,7 +599,7 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     int64_t stage = 0;
     for (int l = 0; l < num_levels; ++l)
         if (pre_nms_topk < level_sizes_host[l] && level_sizes_host[l] <= 50 * 1024) stage = std::max(stage, level_sizes_host[l]);
-    if (stage * 4 > 48 * 1024) {
+    if (stage * 4 > 40 * 1024) {  // (the 48 KB default covers static + dynamic shared memory: leave room for the 2 KB of statics)
         cudaError_t ea = cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stage * 4));
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(rpn_select_kernel)");
     }
@@ -631,7 +631,7 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     rpn_tier_kernel<<<n, 1024, 0, st>>>(0, rc, mp, ct, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
                                         ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
     DET_LAUNCH_OK("rpn_tier_kernel");
-    int status = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
+    int status = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st, true);
     if (status != DET_OK) return status;
     // images whose tier fell short of post_nms_topk survivors are swept again in full (usually none: empty lists)
     e = cudaMemsetAsync(ws.ctr, 0, 64, st);
@@ -639,13 +639,13 @@ int det_rpn_proposals(const float* boxes, const float* logits, int n, int64_t r,
     rpn_tier_kernel<<<n, 1024, 0, st>>>(1, rc, mp, ct, pre_nms_topk, post_nms_topk, ws.info, sorted, ws.state, ws.ctr,
                                         ws.seg_small, ws.seg_large, ws.seg_huge, ws.huge_nk);
     DET_LAUNCH_OK("rpn_tier_kernel(check)");
-    status = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st);
+    status = run_segment_kernels(lay, ws, thr_f, (int)min(post_nms_topk, r), st, true);
     if (status != DET_OK) return status;
     int64_t kept_bound = 0;
     for (int l = 0; l < num_levels; ++l) kept_bound += std::min({level_sizes_host[l], pre_nms_topk, post_nms_topk});
     if (!old_sorts && kept_bound * 8 <= 200 * 1024) {  // the kept keys of an image fit into shared memory
         const size_t smem = (size_t)kept_bound * 8;
-        if (smem > 48 * 1024) {
+        if (smem > 40 * 1024) {  // (static + dynamic share the 48 KB default)
             cudaError_t ea = cudaFuncSetAttribute(rpn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(rpn_finish_kernel)");
         }
