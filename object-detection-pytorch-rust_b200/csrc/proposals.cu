@@ -339,16 +339,39 @@ rpn_tier_kernel(int pass, int64_t r, int64_t mp, LevelTable lt, int64_t pre_nms_
         s_prefix = 0u;
         s_want = want;
     }
+    // the valid candidates' score keys are read ONCE (up to 8 per thread, all loads in flight together): the four radix
+    // passes were four dependent global round trips per trip of the loop, 20 us of pure latency per launch
+    constexpr int kHeld = 8;
+    const bool held = r <= (int64_t)kHeld * T;  // the compact row [0, r) is level after level without gaps
+    uint32_t myk[kHeld];
+    unsigned myv = 0u;
+    if (held) {
+#pragma unroll
+        for (int u = 0; u < kHeld; ++u) {
+            const int64_t p = (int64_t)u * T + tid;
+            const bool in = p < r;
+            const uint8_t st8 = in ? stt[p] : (uint8_t)1;
+            const uint64_t k64 = in ? k[p] : 0ull;
+            myk[u] = (uint32_t)(k64 >> KLL::kScoreShift);
+            myv |= (st8 == 0) ? (1u << u) : 0u;
+        }
+    }
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int b = tid; b < 256; b += T) hist[b] = 0u;
         __syncthreads();
         const uint32_t prefix = s_prefix, himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-        for (int l = 0; l < lt.num_levels; ++l) {
-            const int64_t s0 = lt.off[l], take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
-            for (int64_t p = s0 + tid; p < s0 + take; p += T) {
-                if (stt[p] != 0) continue;
-                const uint32_t key = (uint32_t)(k[p] >> KLL::kScoreShift);
-                if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        if (held) {
+#pragma unroll
+            for (int u = 0; u < kHeld; ++u)
+                if (((myv >> u) & 1u) && (myk[u] & himask) == prefix) atomicAdd(&hist[(myk[u] >> shift) & 255u], 1u);
+        } else {
+            for (int l = 0; l < lt.num_levels; ++l) {
+                const int64_t s0 = lt.off[l], take = min(lt.off[l + 1] - lt.off[l], pre_nms_topk);
+                for (int64_t p = s0 + tid; p < s0 + take; p += T) {
+                    if (stt[p] != 0) continue;
+                    const uint32_t key = (uint32_t)(k[p] >> KLL::kScoreShift);
+                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
             }
         }
         __syncthreads();
