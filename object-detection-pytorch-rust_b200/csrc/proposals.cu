@@ -35,12 +35,44 @@ __device__ __forceinline__ int level_of(const LevelTable& t, int64_t i) {
 // found with a radix select (4 byte-passes over the 32-bit logit keys; when equal logits straddle the cut the lower
 // anchor indices win, ranked in index order) and written, in arrival order, to a compact row [coff[l], coff[l] + take_l) per level.  Only that row -- a few
 // tiles instead of all R keys -- is sorted afterwards.  One CTA per (image, level).
+// one step of the radix select, by one warp: from the 256-bin histogram of the keys that share *prefix, find the bin that
+// holds the *want-th of them, extend the prefix by it and reduce *want to the rank inside the bin
+__device__ __forceinline__ void radix_decide(const uint32_t* hist, int lane, int shift, uint32_t* s_prefix, int* s_want,
+                                             int* s_done) {
+    uint32_t c8[8], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        c8[q] = hist[lane * 8 + q];
+        tot += c8[q];
+    }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        incl += (lane >= o) ? up : 0u;
+    }
+    const uint32_t prefix = *s_prefix, w = (uint32_t)*s_want, before = incl - tot;
+    __syncwarp();  // every lane has read the state the owner lane is about to replace
+    if (before < w && w <= incl) {
+        uint32_t run = before;
+        int q = 0;
+        for (; q < 7 && run + c8[q] < w; ++q) run += c8[q];
+        uint32_t np = prefix | ((uint32_t)(lane * 8 + q) << shift);
+        if (run + c8[q] == w) {  // the whole bin is wanted: everything that shares the prefix is in
+            np |= (shift == 0) ? 0u : ((1u << shift) - 1u);
+            *s_done = 1;
+        }
+        *s_prefix = np;
+        *s_want = (int)(w - run);
+    }
+}
+
 static __global__ void __launch_bounds__(1024)
 rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, LevelTable lt, LevelTable ct, int64_t len1,
                   LargeImg* info, uint64_t* __restrict__ keys, int stage_cap) {
     // the keys of a level that needs a selection are read from global memory once and staged here (up to stage_cap of
     // them): the radix passes and the final compaction then run out of shared memory
-    extern __shared__ uint32_t staged_keys[];
+    extern __shared__ __align__(16) uint32_t staged_keys[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_want, s_slot, s_done, s_warp[32];
@@ -78,19 +110,106 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
             if (valid) atomicAdd(&hist[key >> 24], 1u);
         };
         if (staged) {
-            // one pass over the level: keys into the staging area + the histogram of the first radix pass
+            // one pass over the level: keys into the staging area + the histogram of the first radix pass, eight
+            // loads of a thread in flight together
+            const int sz = (int)size;
+            const float* lgl = lg + i0;
             for (int b = tid; b < 256; b += T) hist[b] = 0u;
             __syncthreads();  // (also: the previous level is done with the staging area)
-            for (int64_t base = 0; base < size; base += T) {
-                const int64_t i = base + tid;
-                const bool valid = i < size;
-                const uint32_t key = valid ? score_desc_key(lg[i0 + i]) : 0u;
-                if (valid) staged_keys[i] = key;
-                count_top_byte(valid, key);
+            for (int base = 0; base < sz; base += 8 * T) {
+                uint32_t kk[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * T + tid;
+                    kk[u] = i < sz ? score_desc_key(lgl[i]) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * T + tid;
+                    if (i < sz) {
+                        staged_keys[i] = kk[u];
+                        atomicAdd(&hist[kk[u] >> 24], 1u);
+                    }
+                }
             }
+            if (tid == 0) {
+                s_prefix = 0u;
+                s_want = take;
+                s_done = 0;
+                s_slot = 0;
+            }
+            // the remaining passes and the compaction read the copy four keys at a time
+            const uint4* s4 = reinterpret_cast<const uint4*>(staged_keys);
+            const int n4 = sz >> 2;
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                if (shift != 24) {
+                    for (int b = tid; b < 256; b += T) hist[b] = 0u;
+                    __syncthreads();
+                    if (s_done) break;
+                    const uint32_t prefix = s_prefix, himask = 0xffffffffu << (shift + 8);
+                    for (int j = tid; j < n4; j += T) {
+                        const uint4 v = s4[j];
+                        if ((v.x & himask) == prefix) atomicAdd(&hist[(v.x >> shift) & 255u], 1u);
+                        if ((v.y & himask) == prefix) atomicAdd(&hist[(v.y >> shift) & 255u], 1u);
+                        if ((v.z & himask) == prefix) atomicAdd(&hist[(v.z >> shift) & 255u], 1u);
+                        if ((v.w & himask) == prefix) atomicAdd(&hist[(v.w >> shift) & 255u], 1u);
+                    }
+                    if (tid < (sz & 3)) {
+                        const uint32_t key = staged_keys[(n4 << 2) + tid];
+                        if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                    }
+                }
+                __syncthreads();
+                if (wid == 0) radix_decide(hist, lane, shift, &s_prefix, &s_want, &s_done);
+                __syncthreads();
+            }
+            __syncthreads();
+            cut = s_prefix;
+            tie_mode = s_done == 0;
+            tie_want = s_want;
+            if (!tie_mode) {
+                const uint64_t lvl = (uint64_t)l << KLL::kSegShift;
+                uint64_t* o = out + ct.off[l];
+                const uint32_t a0 = (uint32_t)i0;
+                const unsigned lt_mask = (1u << lane) - 1u;
+                for (int j0 = 0; j0 < n4; j0 += T) {
+                    const int j = j0 + tid;
+                    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                    if (j < n4) v = s4[j];
+                    const bool i0n = j < n4 && v.x <= cut, i1n = j < n4 && v.y <= cut, i2n = j < n4 && v.z <= cut,
+                               i3n = j < n4 && v.w <= cut;
+                    const unsigned b0 = __ballot_sync(0xffffffffu, i0n), b1 = __ballot_sync(0xffffffffu, i1n),
+                                   b2 = __ballot_sync(0xffffffffu, i2n), b3 = __ballot_sync(0xffffffffu, i3n);
+                    const int c0 = __popc(b0), c1 = __popc(b1), c2 = __popc(b2), c3 = __popc(b3);
+                    if (c0 + c1 + c2 + c3 == 0) continue;  // warp-uniform
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&s_slot, c0 + c1 + c2 + c3);
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                    const uint32_t a = a0 + (uint32_t)(j << 2);
+                    int q = pos + __popc(b0 & lt_mask);
+                    if (i0n && q < take) o[q] = lvl | ((uint64_t)v.x << KLL::kScoreShift) | (uint64_t)a;
+                    q = pos + c0 + __popc(b1 & lt_mask);
+                    if (i1n && q < take) o[q] = lvl | ((uint64_t)v.y << KLL::kScoreShift) | (uint64_t)(a + 1u);
+                    q = pos + c0 + c1 + __popc(b2 & lt_mask);
+                    if (i2n && q < take) o[q] = lvl | ((uint64_t)v.z << KLL::kScoreShift) | (uint64_t)(a + 2u);
+                    q = pos + c0 + c1 + c2 + __popc(b3 & lt_mask);
+                    if (i3n && q < take) o[q] = lvl | ((uint64_t)v.w << KLL::kScoreShift) | (uint64_t)(a + 3u);
+                }
+                if (tid < (sz & 3)) {
+                    const int i = (n4 << 2) + tid;
+                    const uint32_t key = staged_keys[i];
+                    if (key <= cut) {
+                        const int q = atomicAdd(&s_slot, 1);
+                        if (q < take) o[q] = lvl | ((uint64_t)key << KLL::kScoreShift) | (uint64_t)(a0 + (uint32_t)i);
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+            // ties at the cut: the index-ordered walk below (cut / tie_mode / tie_want are set)
         }
         auto key_at = [&](int64_t i) -> uint32_t { return staged ? staged_keys[i] : score_desc_key(lg[i0 + i]); };
-        if (take < size) {
+        if (take < size && !staged) {
             // radix select of the take-th best 32-bit descending-logit key, one byte per pass
             if (tid == 0) {
                 s_prefix = 0u;
@@ -98,9 +217,7 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
                 s_done = 0;
             }
             for (int shift = 24; shift >= 0; shift -= 8) {
-                if (shift == 24 && staged) {
-                    __syncthreads();  // staging + first histogram complete
-                } else {
+                {
                     for (int b = tid; b < 256; b += T) hist[b] = 0u;
                     __syncthreads();
                     if (s_done) break;
@@ -116,34 +233,7 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
                     }
                     __syncthreads();
                 }
-                const uint32_t prefix = s_prefix;
-                if (wid == 0) {
-                    uint32_t c8[8], tot = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        c8[q] = hist[lane * 8 + q];
-                        tot += c8[q];
-                    }
-                    uint32_t incl = tot;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                        incl += (lane >= o) ? up : 0u;
-                    }
-                    const uint32_t w = (uint32_t)s_want, before = incl - tot;
-                    if (before < w && w <= incl) {
-                        uint32_t run = before;
-                        int q = 0;
-                        for (; q < 7 && run + c8[q] < w; ++q) run += c8[q];
-                        uint32_t np = prefix | ((uint32_t)(lane * 8 + q) << shift);
-                        if (run + c8[q] == w) {  // the whole bin is wanted: everything that shares the prefix is in
-                            np |= (shift == 0) ? 0u : ((1u << shift) - 1u);
-                            s_done = 1;
-                        }
-                        s_prefix = np;
-                        s_want = (int)(w - run);
-                    }
-                }
+                if (wid == 0) radix_decide(hist, lane, shift, &s_prefix, &s_want, &s_done);
                 __syncthreads();
             }
             __syncthreads();
