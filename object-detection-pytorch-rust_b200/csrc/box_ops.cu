@@ -271,7 +271,9 @@ rpn_decode_level_kernel(const float* __restrict__ obj, const float* __restrict__
 // slab -- one contiguous span of 128*A boxes and logits -- with fully coalesced stores.  Small levels ride along with
 // the big one instead of paying their own launch, ramp and tail.  (Issuing the 15 loads of all three anchors before the
 // first decode -- A as a template parameter, 100 registers -- was measured: 35.1 vs 33.1 us per 64 images, 107.0 vs
-// 105.5 us per 256; the bytes in flight are not what holds this kernel at 0.74 of the copy peak.  Rejected.)
+// 105.5 us per 256; the bytes in flight are not what holds this kernel at 0.74 of the copy peak.  Rejected.  So was an
+// odd slab pitch (4A+1 entries per lane) that removes the 10-way bank conflict ncu reports on the slab stores: 33.3 vs
+// 33.1 us per 64 images, 113.0 vs 105.5 us per 256.)
 constexpr int kRpnFlatMaxLevels = 8;
 constexpr int kRpnFlatMaxA = 4;
 constexpr int kRpnTilePos = 128;
