@@ -3,9 +3,12 @@
 // Replaces find_top_rpn_proposals (python/src/models/utils.py:9-109), which sorts every level fully, gathers, and then
 // loops over the images in Python with >= 4 host synchronisations each.  Here:
 //   per-level radix select of the pre_nms_topk best keys (level | descending logit | anchor index) into a compact row
-//   -> sort of that row only -> gather with the finite / clip / min-size filters fused in -> tier cut: per-(image,
-//   level) greedy NMS (nms_core.cuh) above a global score cut first, full segments only if that falls short of
-//   post_nms_topk -> kept keys (descending logit | index) compacted -> sort of a few tiles -> emit boxes + logits.
+//   (one CTA per (image, level), the level's keys staged in shared memory) -> sort of that row only (one tile sort per
+//   (image, level); tile sort + merge passes when a level keeps more than a tile) -> gather with the finite / clip /
+//   min-size filters fused in -> tier cut: per-(image, level) greedy NMS (nms_core.cuh / nms_large.cuh) above a global
+//   score cut first, full segments only if that falls short of post_nms_topk -> finish: the kept keys of a level are a
+//   sorted run, the output order is the merge of the runs (rank by binary search), boxes + logits written in place
+//   (rekey / pad / sort / emit kernels when an image's kept keys do not fit into shared memory).
 // No host synchronisation; the "training diverged" condition (models/utils.py:79-84) is reported through a device flag.
 #include <algorithm>
 #include "nms_large.cuh"
