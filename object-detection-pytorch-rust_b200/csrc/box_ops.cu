@@ -284,7 +284,7 @@ struct RpnLevelDev {
     const float* deltas;
     const float4* cell;
     int w, hw, tiles;  // tiles of 128 positions per image
-    int stride;
+    int stride, vec;   // vec: planes are whole 16-byte tiles (hw % 4 == 0, aligned heads)
     int64_t out_offset;
 };
 
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kRpnFlatWarps * 32) rpn_decode_flat_kernel(con
     float* s_log = reinterpret_cast<float*>(reinterpret_cast<float4*>(rpn_smem) + (size_t)kRpnFlatWarps * kRpnTilePos * A) +
                    (size_t)wid * kRpnTilePos * A;
     const int p0 = pos0 + lane * 4;
-    if (lane * 4 < npos) {  // hw % 4 == 0: a lane's 4 positions are all inside or all outside
+    if (lane * 4 < npos) {  // vec levels (hw % 4 == 0): a lane's 4 positions are all inside or all outside
         const float* obj_img = L.obj + (int64_t)img * A * L.hw + p0;
         const float* del_img = L.deltas + (int64_t)img * A * 4 * L.hw + p0;
         float sx[4], sy[4];
@@ -328,10 +328,26 @@ __global__ void __launch_bounds__(kRpnFlatWarps * 32) rpn_decode_flat_kernel(con
             sy[v] = grid_shift(p / L.w, L.stride, g.offset);
         }
         for (int ai = 0; ai < A; ++ai) {
-            const float4 l4 = ld_stream(reinterpret_cast<const float4*>(obj_img + (int64_t)ai * L.hw));
-            float4 q[4];
+            float4 l4, q[4];
+            if (L.vec) {
+                l4 = ld_stream(reinterpret_cast<const float4*>(obj_img + (int64_t)ai * L.hw));
 #pragma unroll
-            for (int c = 0; c < 4; ++c) q[c] = ld_stream(reinterpret_cast<const float4*>(del_img + (int64_t)(ai * 4 + c) * L.hw));
+                for (int c = 0; c < 4; ++c) q[c] = ld_stream(reinterpret_cast<const float4*>(del_img + (int64_t)(ai * 4 + c) * L.hw));
+            } else {
+                // a level whose planes are not 16-byte tiles (h*w not a multiple of 4, e.g. the 7x7 level of a 448^2
+                // pyramid, or an unaligned view): scalar loads, positions past the plane read as 0 and are never written
+                auto ld4 = [&](const float* pl) {
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p0 + 0 < L.hw) r.x = pl[0];
+                    if (p0 + 1 < L.hw) r.y = pl[1];
+                    if (p0 + 2 < L.hw) r.z = pl[2];
+                    if (p0 + 3 < L.hw) r.w = pl[3];
+                    return r;
+                };
+                l4 = ld4(obj_img + (int64_t)ai * L.hw);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) q[c] = ld4(del_img + (int64_t)(ai * 4 + c) * L.hw);
+            }
             const float lg[4] = {l4.x, l4.y, l4.z, l4.w};
             const float d0[4] = {q[0].x, q[0].y, q[0].z, q[0].w}, d1[4] = {q[1].x, q[1].y, q[1].z, q[1].w};
             const float d2[4] = {q[2].x, q[2].y, q[2].z, q[2].w}, d3[4] = {q[3].x, q[3].y, q[3].z, q[3].w};
@@ -533,8 +549,9 @@ int det_rpn_decode(const det_rpn_level_t* levels_host, int num_levels, int n, in
         DET_CHECK_ARG(L.objectness && L.deltas && L.cell_anchors && L.h >= 0 && L.w >= 0 && L.out_offset >= 0, "bad level");
         const int64_t hw = (int64_t)L.h * L.w;
         DET_CHECK_ARG(out_img_stride >= L.out_offset + hw * a, "output slot out of range");
-        const bool flat = flat_ok && f.num_levels < kRpnFlatMaxLevels && hw % 4 == 0 && hw < (1ll << 30) &&
-                          aligned16(L.objectness) && aligned16(L.deltas) && aligned16(L.cell_anchors);
+        // (levels whose planes are not 16-byte tiles ride along with scalar loads: they are the small ones)
+        const bool flat = flat_ok && f.num_levels < kRpnFlatMaxLevels && hw < (1ll << 30) && aligned16(L.cell_anchors);
+        const bool vec_ok = hw % 4 == 0 && aligned16(L.objectness) && aligned16(L.deltas);
         if (!flat) {  // this level takes its own launch: same results
             const int rc = det_rpn_decode_level(L.objectness, L.deltas, n, a, L.h, L.w, L.stride, offset, L.cell_anchors, wx,
                                                 wy, ww, wh, scale_clamp, logits_out, boxes_out, out_img_stride,
@@ -546,13 +563,13 @@ int det_rpn_decode(const det_rpn_level_t* levels_host, int num_levels, int n, in
         f.tile_begin[f.num_levels] = tb;
         D.obj = L.objectness; D.deltas = L.deltas; D.cell = reinterpret_cast<const float4*>(L.cell_anchors);
         D.w = L.w > 0 ? L.w : 1; D.hw = L.h * L.w; D.tiles = (D.hw + kRpnTilePos - 1) / kRpnTilePos;
-        D.stride = L.stride; D.out_offset = L.out_offset;
+        D.stride = L.stride; D.vec = vec_ok ? 1 : 0; D.out_offset = L.out_offset;
         tb += (long long)n * D.tiles;
         ++f.num_levels;
     }
     for (int l = f.num_levels; l < kRpnFlatMaxLevels; ++l) {
         RpnLevelDev& D = f.lv[l];
-        D.obj = nullptr; D.deltas = nullptr; D.cell = nullptr; D.w = 1; D.hw = 0; D.tiles = 1; D.stride = 0;
+        D.obj = nullptr; D.deltas = nullptr; D.cell = nullptr; D.w = 1; D.hw = 0; D.tiles = 1; D.stride = 0; D.vec = 1;
         D.out_offset = 0;
     }
     for (int l = f.num_levels; l <= kRpnFlatMaxLevels; ++l) f.tile_begin[l] = tb;
