@@ -93,7 +93,8 @@ DET_API int det_rpn_decode_level(const float* objectness, const float* deltas, i
 /* All pyramid levels of the RPN head in ONE launch (csrc/box_ops.cu rpn_decode_flat_kernel: a warp per 128-position
  * tile, outputs staged in shared memory and written as contiguous spans).  Every level shares n and a; level l:
  * objectness (n,a,h,w), deltas (n,a*4,h,w), cell_anchors (a,4), first output row out_offset.  Levels whose h*w is not
- * a multiple of 4, unaligned heads or a > 4 fall back to one det_rpn_decode_level launch per level -- same results. */
+ * a multiple of 4 (or whose heads are not 16-byte aligned) ride along with scalar loads; unaligned cell anchors or
+ * a > 4 fall back to one det_rpn_decode_level launch per level -- same results. */
 typedef struct det_rpn_level {
     const float* objectness;
     const float* deltas;

@@ -32,7 +32,7 @@ from bench import time_graph, load_peaks
 ms_dec = time_graph([lambda: rpn.decode_heads(obj_d, dlt_d)], 20)
 R = 50127
 by = n * 40 * R  # read 4R logits + 16R deltas, write 4R logits + 16R boxes (anchors synthesised: 0 bytes)
-print(f"decode_heads (det_rpn_decode, one launch + the 7x7 level): {ms_dec * 1e3:.1f} us = {by / ms_dec / 1e6:.0f} GB/s algorithmic "
+print(f"decode_heads (det_rpn_decode, one launch for the five levels): {ms_dec * 1e3:.1f} us = {by / ms_dec / 1e6:.0f} GB/s algorithmic "
       f"= {by / ms_dec / 1e6 / load_peaks()[0]:.2f} of the HBM peak")
 ms_graph = time_graph([run], 10)
 print(f"ours, replayed from a CUDA graph: {ms_graph:.3f} ms per batch of {n} images = {n / ms_graph * 1e3:.0f} images/s")
