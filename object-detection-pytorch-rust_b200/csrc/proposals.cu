@@ -290,7 +290,7 @@ rpn_select_kernel(const float* __restrict__ logits, int64_t r, int64_t mp, Level
 // (image, level) and no merge passes (sort_rows: tile sort + two merge passes over 8192 keys per image at 2000 per level).
 constexpr int kLevelSortThreads = 512;  // 4 keys per thread: 16 warps hide the shuffle latency of the network better than 8
 
-static __global__ void __launch_bounds__(kLevelSortThreads)
+static __global__ void __launch_bounds__(kLevelSortThreads, 2)
 rpn_sort_levels_kernel(uint64_t* __restrict__ keys, int64_t mp, LevelTable ct) {
     __shared__ uint64_t s[kTile];
     const int l = blockIdx.x, img = blockIdx.y;
