@@ -628,6 +628,24 @@ def extras_proposals(det, dev, peak, quick):
     run_train_defaults()
     ms_t = time_graph([run_train_defaults], 3 if quick else 10)
     ms_dec = time_graph([lambda: rpn.decode_heads(obj, dlt)], 5 if quick else 20)
+    # the other regime: clustered logits (a coarse random field: one value per 8x8 block of positions, shared by the cell
+    # anchors, plus a little noise) and small deltas -- neighbouring anchors score alike and overlap, as the outputs of a
+    # trained RPN around objects do, so the NMS suppresses most of the top candidates, the tier cut falls short and the
+    # full segments are swept.  Random logits (above) are the low-suppression end.
+    obj_c, dlt_c = [], []
+    for o, d_, s_ in zip(obj, dlt, strides):
+        hh = 448 // s_
+        coarse = torch.randn(n, 1, (hh + 7) // 8, (hh + 7) // 8, device=dev, generator=g)
+        field = torch.nn.functional.interpolate(coarse, size=(hh, hh), mode="nearest")
+        obj_c.append((field.expand(n, 3, hh, hh) * 2.0 + 0.05 * torch.randn(n, 3, hh, hh, device=dev, generator=g)).contiguous())
+        dlt_c.append(d_ * 0.1)
+
+    def run_clustered():
+        logits, boxes, level_sizes = rpn.decode_heads(obj_c, dlt_c)
+        return det.rpn_proposals_batched(boxes, logits, level_sizes, sizes, 0.7, 2000, 1000, 0.0)
+
+    out_c = run_clustered()
+    ms_c = time_graph([run_clustered], 3 if quick else 10)
     R = 50127
     dec_bytes = n * 40 * R
     return {"rpn_proposals_r50127": {
@@ -635,6 +653,10 @@ def extras_proposals(det, dev, peak, quick):
                     f"batch {n}, replayed from a CUDA graph",
         "ms": ms, "images_per_s": n / ms * 1e3, "kept_per_image": float(out[2].float().mean()),
         "ms_pre2000_post1000": ms_t, "images_per_s_pre2000_post1000": n / ms_t * 1e3,
+        "ms_pre2000_post1000_clustered": ms_c, "images_per_s_pre2000_post1000_clustered": n / ms_c * 1e3,
+        "kept_per_image_clustered": float(out_c[2].float().mean()),
+        "clustered_note": "logits = coarse random field (8x8 blocks) + noise, small deltas: the high-suppression regime of a "
+                          "trained RPN; the random-logit lines are the low-suppression end",
         "ms_decode": ms_dec,
         "decode_roofline": {"bound": "hbm", "achieved": dec_bytes / ms_dec / 1e6, "peak": peak, "unit": "GB/s",
                             "frac": dec_bytes / ms_dec / 1e6 / peak, "algorithmic_bytes": dec_bytes,

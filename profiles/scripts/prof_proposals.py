@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "object-detectio
 import torch
 import det_b200 as det
 from oracle import ref_torch as O
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64  # usage: prof_proposals.py [n] [pre] [post] [--clustered]
 PRE = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 POST = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 dev = torch.device("cuda", 0)
@@ -16,7 +16,17 @@ rpn = det.RegionProposalNetwork(strides)
 g = torch.Generator().manual_seed(6)
 obj = [torch.randn(n, 3, 448 // s, 448 // s, generator=g) for s in strides]
 dlt = [torch.randn(n, 12, 448 // s, 448 // s, generator=g) * 0.4 for s in strides]
-obj_d, dlt_d = [t.to(dev) for t in obj], [t.to(dev) for t in dlt]
+if "--clustered" in sys.argv:
+    # objects: logits are a coarse random field (one value per 8x8 block of positions, shared by the cell anchors) plus a
+    # little noise, deltas small -- neighbouring anchors score alike and overlap, as the outputs of a trained RPN do, so
+    # the NMS suppresses most of the top candidates and the tier cut falls short (full segments are swept)
+    for l, s in enumerate(strides):
+        hh = 448 // s
+        coarse = torch.randn(n, 1, (hh + 7) // 8, (hh + 7) // 8, generator=g)
+        field = torch.nn.functional.interpolate(coarse, size=(hh, hh), mode="nearest")
+        obj[l] = field.expand(n, 3, hh, hh) * 2.0 + 0.05 * torch.randn(n, 3, hh, hh, generator=g)
+        dlt[l] = dlt[l] * 0.1
+obj_d, dlt_d = [t.contiguous().to(dev) for t in obj], [t.to(dev) for t in dlt]
 sizes = torch.tensor([[448, 448]] * n, dtype=torch.int32, device=dev)
 def run():
     logits, boxes, level_sizes = rpn.decode_heads(obj_d, dlt_d)
